@@ -1,0 +1,219 @@
+"""CPU evaluation of expression trees with PostgreSQL semantics.
+
+TEST INFRASTRUCTURE (oracle) - never imported by the product path.
+
+Plays the role of PostgreSQL's ExecEvalExpr / ExecProject for the node kinds
+the device code generator accepts (/root/reference/codegen.c:1065-1392) and
+of the partial-aggregate placeholder functions the reference installs in
+schema pgstrom (/root/reference/gpupreagg.c:4251-4412,
+pg_strom--1.0.sql:99-226).  The host uses exactly this evaluation for rows
+the device flags StromError_CpuReCheck (gpupreagg.c:2507-2607).
+"""
+import math
+import struct
+from decimal import Decimal
+
+from .pg_agg import PgError, cast as pg_cast, float8pl, float8mul, check_float8, f4
+
+_INT_RANGE = {"int2": (-(1 << 15), (1 << 15) - 1, "smallint out of range"),
+              "int4": (-(1 << 31), (1 << 31) - 1, "integer out of range"),
+              "int8": (-(1 << 63), (1 << 63) - 1, "bigint out of range")}
+
+
+def etype(e):
+    n = e["node"]
+    return {"Var": lambda: e["vartype"], "Const": lambda: e["consttype"],
+            "Param": lambda: e["paramtype"], "FuncExpr": lambda: e["funcresulttype"],
+            "OpExpr": lambda: e.get("opresulttype", "bool"),
+            "NullTest": lambda: "bool", "BooleanTest": lambda: "bool",
+            "BoolExpr": lambda: "bool", "RelabelType": lambda: e["resulttype"],
+            "CaseExpr": lambda: e["casetype"], "Aggref": lambda: e["aggtype"]}[n]()
+
+
+def _const_value(e):
+    if e.get("constisnull"):
+        return None
+    t = e["consttype"]
+    v = e.get("constvalue")
+    if t == "bool":
+        return v in ("t", "true", True)
+    if t in _INT_RANGE or t == "date":
+        return int(v)
+    if t in ("float4", "float8"):
+        x = float({"NaN": "nan", "Infinity": "inf", "-Infinity": "-inf"}.get(v, v))
+        return f4(x) if t == "float4" else x
+    if t == "numeric":
+        return Decimal(v)
+    return v
+
+
+def _int_arith(op, a, b, rtype):
+    lo, hi, msg = _INT_RANGE[rtype]
+    if op == "pl":
+        r = a + b
+    elif op == "mi":
+        r = a - b
+    elif op == "mul":
+        r = a * b
+    elif op == "div":
+        if b == 0:
+            raise PgError("division by zero")
+        r = abs(a) // abs(b) * (1 if (a >= 0) == (b >= 0) else -1)   # trunc toward 0
+    elif op == "mod":
+        if b == 0:
+            raise PgError("division by zero")
+        r = 0 if b == -1 else int(math.fmod(a, b)) if abs(a) < 2**53 else a - b * int(Decimal(a) / Decimal(b))
+    else:
+        raise KeyError(op)
+    if not (lo <= r <= hi):
+        raise PgError(msg)
+    return r
+
+
+def _float_arith(op, a, b, rtype):
+    if rtype == "float4":
+        a, b = f4(a), f4(b)
+    if op == "pl":
+        r = a + b
+        ok_inf, ok_zero = (math.isinf(a) or math.isinf(b)), True
+    elif op == "mi":
+        r = a - b
+        ok_inf, ok_zero = (math.isinf(a) or math.isinf(b)), True
+    elif op == "mul":
+        r = a * b
+        ok_inf, ok_zero = (math.isinf(a) or math.isinf(b)), (a == 0 or b == 0)
+    elif op == "div":
+        if b == 0.0:
+            raise PgError("division by zero")
+        r = a / b
+        ok_inf, ok_zero = (math.isinf(a) or math.isinf(b)), (a == 0)
+    else:
+        raise KeyError(op)
+    if rtype == "float4":
+        r = f4(r)
+    check_float8(r, ok_inf, ok_zero)
+    return r
+
+
+def _fcmp(a, b):
+    if isinstance(a, float) or isinstance(b, float):
+        a, b = float(a), float(b)
+        if math.isnan(a):
+            return 0 if math.isnan(b) else 1
+        if math.isnan(b):
+            return -1
+    return (a > b) - (a < b)
+
+
+_CMP = {"eq": lambda c: c == 0, "ne": lambda c: c != 0, "lt": lambda c: c < 0,
+        "le": lambda c: c <= 0, "gt": lambda c: c > 0, "ge": lambda c: c >= 0}
+
+
+def _call(name, argtypes, rettype, args):
+    """strict functions: NULL in -> NULL out (handled by the caller)."""
+    # casts: function named after the target type
+    if name in ("int2", "int4", "int8", "float4", "float8", "numeric") and len(args) == 1:
+        return pg_cast(args[0], argtypes[0], name)
+    for sfx in ("pl", "mi", "mul", "div", "mod"):
+        if name.endswith(sfx) and name[:-len(sfx)].rstrip("0123456789") in ("int", "float"):
+            if name.startswith("int"):
+                return _int_arith(sfx, args[0], args[1], rettype)
+            return _float_arith(sfx, args[0], args[1], rettype)
+    for sfx, fn in _CMP.items():
+        if name.endswith(sfx) and (name.startswith("int") or name.startswith("float")
+                                   or name.startswith("bool") or name.startswith("date_")
+                                   or name.startswith("numeric_")):
+            return fn(_fcmp(args[0], args[1]))
+    if name.endswith("um"):
+        r = -args[0]
+        if rettype in _INT_RANGE and not (_INT_RANGE[rettype][0] <= r <= _INT_RANGE[rettype][1]):
+            raise PgError(_INT_RANGE[rettype][2])
+        return r
+    if name.endswith("abs") or name == "abs":
+        return abs(args[0])
+    if name in ("sqrt", "dsqrt"):
+        return math.sqrt(args[0])
+    if name == "floor":
+        return float(math.floor(args[0]))
+    raise NotImplementedError("oracle: function %s(%s)" % (name, ",".join(argtypes)))
+
+
+def evaluate(e, row):
+    """row: list/tuple of column values (None = NULL), Var.varattno is 1-based."""
+    if e is None:
+        return None
+    n = e["node"]
+    if n == "Var":
+        return row[e["varattno"] - 1]
+    if n == "Const":
+        return _const_value(e)
+    if n == "Param":
+        return None if e.get("isnull") else _const_value(
+            {"consttype": e["paramtype"], "constvalue": e.get("value")})
+    if n == "RelabelType":
+        return evaluate(e["arg"], row)
+    if n == "NullTest":
+        v = evaluate(e["arg"], row)
+        return (v is None) if e["nulltesttype"] == "IS_NULL" else (v is not None)
+    if n == "BooleanTest":
+        v = evaluate(e["arg"], row)
+        t = e["booltesttype"]
+        return {"IS_TRUE": v is True, "IS_NOT_TRUE": v is not True,
+                "IS_FALSE": v is False, "IS_NOT_FALSE": v is not False,
+                "IS_UNKNOWN": v is None, "IS_NOT_UNKNOWN": v is not None}[t]
+    if n == "BoolExpr":
+        op = e["boolop"]
+        vals = [evaluate(a, row) for a in e["args"]]
+        if op == "NOT":
+            return None if vals[0] is None else (not vals[0])
+        if op == "AND":
+            if any(v is False for v in vals):
+                return False
+            return None if any(v is None for v in vals) else True
+        if any(v is True for v in vals):
+            return True
+        return None if any(v is None for v in vals) else False
+    if n == "CaseExpr":
+        base = evaluate(e["arg"], row) if e.get("arg") else None
+        for w in e["args"]:
+            if e.get("arg"):
+                c = evaluate(w["expr"], row)
+                hit = (base is not None and c is not None and _fcmp(base, c) == 0)
+            else:
+                hit = evaluate(w["expr"], row) is True
+            if hit:
+                return evaluate(w["result"], row)
+        return evaluate(e.get("defresult"), row)
+    if n in ("FuncExpr", "OpExpr"):
+        name = e["funcname"] if n == "FuncExpr" else e["opfuncname"]
+        args = [evaluate(a, row) for a in e.get("args", [])]
+        argtypes = [etype(a) for a in e.get("args", [])]
+        if n == "FuncExpr" and e.get("funcschema") == "pgstrom":
+            return _partial_placeholder(name, args)
+        if any(a is None for a in args):
+            return None
+        return _call(name, argtypes, etype(e), args)
+    raise NotImplementedError(n)
+
+
+def _partial_placeholder(name, args):
+    """gpupreagg.c:4251-4412 (with the documented fix: pcov_* read the value
+    arguments 1/2, not the filter)."""
+    if name == "nrows":
+        return 1 if all(a is True for a in args) else 0
+    if name in ("pmin", "pmax", "psum"):
+        return args[0]
+    if name == "psum_x2":
+        if args[0] is None:
+            return None
+        if isinstance(args[0], Decimal):
+            return args[0] * args[0]
+        return float8mul(args[0], args[0])
+    if name.startswith("pcov_"):
+        flt, x, y = args
+        if flt is not True or x is None or y is None:
+            return None
+        return {"pcov_x": lambda: x, "pcov_y": lambda: y,
+                "pcov_x2": lambda: float8mul(x, x), "pcov_y2": lambda: float8mul(y, y),
+                "pcov_xy": lambda: float8mul(x, y)}[name]()
+    raise NotImplementedError(name)

@@ -1,0 +1,1487 @@
+/*
+ * cuda_layer.cpp - the thin C-ABI CUDA layer of the GpuPreAgg path.
+ *
+ * Replaces, for this path, the reference's OpenCL dispatch stack:
+ *   opencl_entry.c   (dlopen of the vendor runtime)      -> CUDA runtime API
+ *   opencl_devinfo.c (device discovery, WG sizing)       -> pgs_cuda_init, occupancy API
+ *   opencl_devprog.c (source keyed program cache, async
+ *                     clBuildProgram)                    -> NVRTC for sm_100a + CRC32 cache
+ *   opencl_serv.c    (bgworker, N pthreads, pinned shmem)-> streams inside the caller
+ *   mqueue.c         (shared-memory message queues)      -> tickets + CUDA events
+ *   gpupreagg.c:3009-4240 (clserv_process_gpupreagg: 4 buffer allocs, k+3 H2D
+ *                     copies, 3..3+log^2 kernel launches, 2 D2H per chunk)
+ *                                                        -> 1 H2D + 1 kernel per chunk,
+ *                                                           state persistent in HBM,
+ *                                                           1 flush kernel + D2H of the
+ *                                                           groups at end of scan
+ * There is no CPU fallback in here: without a CUDA device every device call
+ * fails with StromError_ServerNotReady.
+ */
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/pgstrom_cuda.h"
+#include "kern_shared.h"
+#include "pgs_plan.h"
+
+namespace pgs { extern thread_local std::string last_error; }
+using pgs::last_error;
+
+/* headers of the device runtime, embedded at build time (the reference's
+ * Makefile:31-77 turns each opencl_*.h into a C string the same way) */
+#include "kernel_headers.inc"
+
+static void
+set_error(const char *fmt, ...)
+{
+    char buf[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error = buf;
+}
+
+#define CUDA_CHECK(call)                                                \
+    do {                                                                \
+        cudaError_t __rc = (call);                                      \
+        if (__rc != cudaSuccess)                                        \
+        {                                                               \
+            set_error("%s failed: %s (%s:%d)", #call,                   \
+                      cudaGetErrorString(__rc), __FILE__, __LINE__);    \
+            return StromError_CudaInternal;                             \
+        }                                                               \
+    } while (0)
+
+/* ------------------------------------------------------------------
+ * CRC32 (key of the program cache, opencl_devprog.c:580-659)
+ * ------------------------------------------------------------------ */
+static uint32_t
+crc32_buf(uint32_t crc, const void *data, size_t len)
+{
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init)
+    {
+        for (uint32_t i = 0; i < 256; i++)
+        {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++)
+                c = (c & 1) ? (0xEDB88320U ^ (c >> 1)) : (c >> 1);
+            table[i] = c;
+        }
+        init = true;
+    }
+    const unsigned char *p = (const unsigned char *)data;
+    crc = ~crc;
+    for (size_t i = 0; i < len; i++)
+        crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    return ~crc;
+}
+
+/* ------------------------------------------------------------------
+ * device programs
+ * ------------------------------------------------------------------ */
+struct pgs_program
+{
+    uint32_t    crc;
+    std::string source;
+    int         extra_flags;
+    std::string options;
+    std::vector<char> cubin;
+    std::string build_log;
+    int         refcnt;
+    double      build_ms;
+    bool        from_disk;
+};
+
+static std::mutex program_lock;
+static std::map<uint32_t, pgs_program *> program_cache;
+
+static std::string
+cubin_cache_dir()
+{
+    const char *env = getenv("PGSTROM_CUBIN_CACHE");
+    if (env && *env)
+        return env;
+    Dl_info info;
+    if (dladdr((void *)&crc32_buf, &info) && info.dli_fname)
+    {
+        std::string p = info.dli_fname;
+        size_t slash = p.rfind('/');
+        if (slash != std::string::npos)
+            return p.substr(0, slash) + "/_cubin_cache";
+    }
+    return "/tmp/pgstrom_cubin_cache";
+}
+
+static std::string
+program_options(int extra_flags)
+{
+    std::string o;
+    (void)extra_flags;
+    o += "tile=" + std::string(getenv("PGSTROM_TILE_ROWS") ? getenv("PGSTROM_TILE_ROWS") : "2048");
+    o += ";stages=" + std::string(getenv("PGSTROM_NUM_STAGES") ? getenv("PGSTROM_NUM_STAGES") : "4");
+    o += ";warps=" + std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "8");
+    o += ";opt=" + std::string(pgs::guc_bool("pg_strom.devprog_enable_optimization") ? "1" : "0");
+    return o;
+}
+
+static int
+nvrtc_build(pgs_program *prog)
+{
+    nvrtcProgram nprog;
+    const char *headers[] = { pgs_hdr_pgstrom_kds_h, pgs_hdr_kern_shared_h,
+                              pgs_hdr_kern_common_cuh, pgs_hdr_kern_numeric_cuh,
+                              pgs_hdr_kern_gpupreagg_cuh };
+    const char *names[] = { "pgstrom_kds.h", "kern_shared.h", "kern_common.cuh",
+                            "kern_numeric.cuh", "kern_gpupreagg.cuh" };
+    std::string d_tile = "-DGPUPREAGG_TILE_ROWS=" +
+        std::string(getenv("PGSTROM_TILE_ROWS") ? getenv("PGSTROM_TILE_ROWS") : "2048");
+    std::string d_stages = "-DGPUPREAGG_NUM_STAGES=" +
+        std::string(getenv("PGSTROM_NUM_STAGES") ? getenv("PGSTROM_NUM_STAGES") : "4");
+    std::string d_warps = "-DGPUPREAGG_CONSUMER_WARPS=" +
+        std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "8");
+    std::vector<const char *> opts = {
+        "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
+        "-device-int128", "--fmad=false",
+        d_tile.c_str(), d_stages.c_str(), d_warps.c_str(),
+    };
+    if (!pgs::guc_bool("pg_strom.devprog_enable_optimization"))
+        opts.push_back("-Xptxas=-O0");
+    auto t0 = std::chrono::steady_clock::now();
+    nvrtcResult rc = nvrtcCreateProgram(&nprog, prog->source.c_str(), "gpupreagg.cu",
+                                        5, headers, names);
+    if (rc != NVRTC_SUCCESS)
+    {
+        set_error("nvrtcCreateProgram: %s", nvrtcGetErrorString(rc));
+        return StromError_ProgramBuildFailure;
+    }
+    rc = nvrtcCompileProgram(nprog, (int)opts.size(), opts.data());
+    size_t logsz = 0;
+    nvrtcGetProgramLogSize(nprog, &logsz);
+    prog->build_log.assign(logsz, '\0');
+    if (logsz > 1)
+        nvrtcGetProgramLog(nprog, &prog->build_log[0]);
+    if (rc != NVRTC_SUCCESS)
+    {
+        set_error("device program build failure: %s", nvrtcGetErrorString(rc));
+        nvrtcDestroyProgram(&nprog);
+        return StromError_ProgramBuildFailure;
+    }
+    size_t sz = 0;
+    nvrtcGetCUBINSize(nprog, &sz);
+    prog->cubin.resize(sz);
+    nvrtcGetCUBIN(nprog, prog->cubin.data());
+    nvrtcDestroyProgram(&nprog);
+    prog->build_ms = std::chrono::duration<double, std::milli>(
+        std::chrono::steady_clock::now() - t0).count();
+    return StromError_Success;
+}
+
+extern "C" int
+pgs_program_build(const char *kern_source, int extra_flags,
+                  pgs_program **program, const char **build_log)
+{
+    static thread_local std::string log_buf;
+    std::string options = program_options(extra_flags);
+    uint32_t crc = 0;
+
+    if (build_log)
+        *build_log = NULL;
+    if (!kern_source || !program)
+    {
+        set_error("pgs_program_build: bad arguments");
+        return StromError_BadRequestMessage;
+    }
+    crc = crc32_buf(crc, kern_source, strlen(kern_source));
+    crc = crc32_buf(crc, &extra_flags, sizeof(extra_flags));
+    crc = crc32_buf(crc, options.data(), options.size());
+    /* the static runtime is part of the key: a new library build must not
+     * pick up stale binaries from the on-disk cache */
+    crc = crc32_buf(crc, pgs_hdr_kern_gpupreagg_cuh, strlen(pgs_hdr_kern_gpupreagg_cuh));
+    crc = crc32_buf(crc, pgs_hdr_kern_common_cuh, strlen(pgs_hdr_kern_common_cuh));
+    crc = crc32_buf(crc, pgs_hdr_kern_numeric_cuh, strlen(pgs_hdr_kern_numeric_cuh));
+    crc = crc32_buf(crc, pgs_hdr_pgstrom_kds_h, strlen(pgs_hdr_pgstrom_kds_h));
+    crc = crc32_buf(crc, pgs_hdr_kern_shared_h, strlen(pgs_hdr_kern_shared_h));
+
+    std::lock_guard<std::mutex> g(program_lock);
+    auto it = program_cache.find(crc);
+    if (it != program_cache.end() && it->second->source == kern_source &&
+        it->second->extra_flags == extra_flags && it->second->options == options)
+    {
+        it->second->refcnt++;
+        *program = it->second;
+        return StromError_Success;
+    }
+    pgs_program *prog = new pgs_program;
+    prog->crc = crc;
+    prog->source = kern_source;
+    prog->extra_flags = extra_flags;
+    prog->options = options;
+    prog->refcnt = 1;
+    prog->build_ms = 0;
+    prog->from_disk = false;
+
+    /* on-disk cache (in-tree by default so that pre-built programs travel) */
+    std::string dir = cubin_cache_dir();
+    char fname[64];
+    snprintf(fname, sizeof(fname), "/%08x.cubin", crc);
+    std::string path = dir + fname;
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (fp)
+    {
+        fseek(fp, 0, SEEK_END);
+        long sz = ftell(fp);
+        fseek(fp, 0, SEEK_SET);
+        if (sz > 0)
+        {
+            prog->cubin.resize(sz);
+            if (fread(prog->cubin.data(), 1, sz, fp) == (size_t)sz)
+                prog->from_disk = true;
+            else
+                prog->cubin.clear();
+        }
+        fclose(fp);
+    }
+    if (prog->cubin.empty())
+    {
+        int rc = nvrtc_build(prog);
+        if (rc != StromError_Success)
+        {
+            log_buf = prog->build_log + "\n---- source ----\n" + prog->source;
+            if (build_log)
+                *build_log = log_buf.c_str();
+            delete prog;
+            return rc;
+        }
+        mkdir(dir.c_str(), 0755);
+        std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+        fp = fopen(tmp.c_str(), "wb");
+        if (fp)
+        {
+            bool ok = fwrite(prog->cubin.data(), 1, prog->cubin.size(), fp) == prog->cubin.size();
+            fclose(fp);
+            if (ok)
+                rename(tmp.c_str(), path.c_str());
+            else
+                unlink(tmp.c_str());
+        }
+    }
+    if (build_log && !prog->build_log.empty())
+    {
+        log_buf = prog->build_log;
+        *build_log = log_buf.c_str();
+    }
+    program_cache[crc] = prog;
+    *program = prog;
+    return StromError_Success;
+}
+
+extern "C" void
+pgs_program_release(pgs_program *program)
+{
+    std::lock_guard<std::mutex> g(program_lock);
+    if (program && program->refcnt > 0)
+        program->refcnt--;
+    /* kept in the cache; reclaimed by size (devprog_reclaim_threshold) */
+    size_t total = 0;
+    for (auto &kv : program_cache)
+        total += kv.second->cubin.size() + kv.second->source.size();
+    size_t limit = (size_t)pgs::guc_int("pg_strom.devprog_reclaim_threshold") << 10;
+    if (total > limit)
+    {
+        for (auto it = program_cache.begin(); it != program_cache.end() && total > limit; )
+        {
+            if (it->second->refcnt == 0)
+            {
+                total -= it->second->cubin.size() + it->second->source.size();
+                delete it->second;
+                it = program_cache.erase(it);
+            }
+            else
+                ++it;
+        }
+    }
+}
+
+extern "C" const void *
+pgs_program_cubin(pgs_program *program, size_t *length)
+{
+    if (!program)
+        return NULL;
+    if (length)
+        *length = program->cubin.size();
+    return program->cubin.data();
+}
+
+extern "C" const char *
+pgs_program_info_json(void)
+{
+    static thread_local std::string buf;
+    std::lock_guard<std::mutex> g(program_lock);
+    pgs::JsonPtr arr = pgs::Json::array();
+    for (auto &kv : program_cache)
+    {
+        pgs::JsonPtr o = pgs::Json::object();
+        char key[16];
+        snprintf(key, sizeof(key), "%08x", kv.first);
+        o->set("key", key);
+        o->set("refcnt", kv.second->refcnt);
+        o->set("length", (long long)kv.second->source.size());
+        o->set("cubin_length", (long long)kv.second->cubin.size());
+        o->set("build_ms", pgs::Json::number(kv.second->build_ms));
+        o->setb("from_disk", kv.second->from_disk);
+        arr->push(o);
+    }
+    buf = arr->dump();
+    return buf.c_str();
+}
+
+/* ------------------------------------------------------------------
+ * devices
+ * ------------------------------------------------------------------ */
+struct DeviceInfo
+{
+    int             ordinal;
+    cudaDeviceProp  prop;
+};
+static std::vector<DeviceInfo> devices;
+static std::mutex device_lock;
+
+extern "C" int
+pgs_cuda_init(const int *devs, int ndevices)
+{
+    std::lock_guard<std::mutex> g(device_lock);
+    int count = 0;
+    cudaError_t rc = cudaGetDeviceCount(&count);
+
+    if (rc != cudaSuccess || count == 0)
+    {
+        set_error("no CUDA device available: %s",
+                  rc != cudaSuccess ? cudaGetErrorString(rc) : "device count is 0");
+        devices.clear();
+        return StromError_ServerNotReady;
+    }
+    devices.clear();
+    std::vector<int> list;
+    if (devs && ndevices > 0)
+        list.assign(devs, devs + ndevices);
+    else
+    {
+        std::string guc = pgs::guc_get("pg_strom.opencl_devices");
+        if (guc.empty() || guc == "any")
+            for (int i = 0; i < count; i++) list.push_back(i);
+        else
+        {
+            size_t pos = 0;
+            while (pos < guc.size())
+            {
+                size_t comma = guc.find(',', pos);
+                if (comma == std::string::npos) comma = guc.size();
+                list.push_back(atoi(guc.substr(pos, comma - pos).c_str()));
+                pos = comma + 1;
+            }
+        }
+    }
+    for (int ord : list)
+    {
+        DeviceInfo di;
+        if (ord < 0 || ord >= count)
+        {
+            set_error("CUDA device %d does not exist (%d devices)", ord, count);
+            devices.clear();
+            return StromError_BadRequestMessage;
+        }
+        di.ordinal = ord;
+        CUDA_CHECK(cudaGetDeviceProperties(&di.prop, ord));
+        if (di.prop.major < 10)
+        {
+            set_error("CUDA device %d (%s, sm_%d%d) is not a Blackwell sm_100 device; "
+                      "this library carries sm_100a code only",
+                      ord, di.prop.name, di.prop.major, di.prop.minor);
+            devices.clear();
+            return StromError_ServerNotReady;
+        }
+        devices.push_back(di);
+    }
+    return StromError_Success;
+}
+
+extern "C" int
+pgs_cuda_device_count(void)
+{
+    return (int)devices.size();
+}
+
+extern "C" const char *
+pgs_cuda_device_info_json(void)
+{
+    static thread_local std::string buf;
+    pgs::JsonPtr arr = pgs::Json::array();
+    for (auto &d : devices)
+    {
+        pgs::JsonPtr o = pgs::Json::object();
+        o->set("ordinal", d.ordinal);
+        o->set("name", d.prop.name);
+        o->set("sm_count", d.prop.multiProcessorCount);
+        o->set("compute_capability", std::to_string(d.prop.major) + "." + std::to_string(d.prop.minor));
+        o->set("global_mem_bytes", (long long)d.prop.totalGlobalMem);
+        o->set("l2_bytes", (long long)d.prop.l2CacheSize);
+        o->set("smem_per_block_optin", (long long)d.prop.sharedMemPerBlockOptin);
+        arr->push(o);
+    }
+    buf = arr->dump();
+    return buf.c_str();
+}
+
+extern "C" void
+pgs_cuda_shutdown(void)
+{
+    std::lock_guard<std::mutex> g(device_lock);
+    devices.clear();
+}
+
+static int
+device_ordinal(int index)
+{
+    if (index < 0 || (size_t)index >= devices.size())
+        return -1;
+    return devices[index].ordinal;
+}
+
+extern "C" void *
+pgs_chunk_alloc(size_t length)
+{
+    void *p = NULL;
+    if (devices.empty())
+    {
+        /* no device: plain aligned memory so that host-only callers
+         * (planner tests) can still build chunks */
+        if (posix_memalign(&p, 4096, (length + 4095) & ~(size_t)4095) != 0)
+            return NULL;
+        return p;
+    }
+    if (cudaHostAlloc(&p, length, cudaHostAllocPortable) != cudaSuccess)
+    {
+        set_error("cudaHostAlloc(%zu) failed", length);
+        return NULL;
+    }
+    return p;
+}
+
+extern "C" void
+pgs_chunk_free(void *chunk)
+{
+    if (!chunk)
+        return;
+    if (devices.empty())
+    {
+        free(chunk);
+        return;
+    }
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, chunk) == cudaSuccess &&
+        attr.type == cudaMemoryTypeHost)
+        cudaFreeHost(chunk);
+    else
+    {
+        cudaGetLastError();
+        free(chunk);
+    }
+}
+
+extern "C" void *
+pgs_device_alloc(int device, size_t length)
+{
+    void *p = NULL;
+    int ord = device_ordinal(device);
+    if (ord < 0 || cudaSetDevice(ord) != cudaSuccess ||
+        cudaMalloc(&p, length) != cudaSuccess)
+    {
+        set_error("pgs_device_alloc(%zu) failed: %s", length,
+                  cudaGetErrorString(cudaGetLastError()));
+        return NULL;
+    }
+    return p;
+}
+
+extern "C" void
+pgs_device_free(int device, void *ptr)
+{
+    int ord = device_ordinal(device);
+    if (ord >= 0 && cudaSetDevice(ord) == cudaSuccess)
+        cudaFree(ptr);
+}
+
+extern "C" int
+pgs_device_upload(int device, void *dst_device, const void *src_host, size_t length)
+{
+    int ord = device_ordinal(device);
+    if (ord < 0)
+    {
+        set_error("device layer is not initialised");
+        return StromError_ServerNotReady;
+    }
+    CUDA_CHECK(cudaSetDevice(ord));
+    CUDA_CHECK(cudaMemcpy(dst_device, src_host, length, cudaMemcpyHostToDevice));
+    return StromError_Success;
+}
+
+/* ------------------------------------------------------------------
+ * sessions
+ * ------------------------------------------------------------------ */
+struct ChunkResult
+{
+    int32_t     status = 0;
+    bool        done = false;
+    std::vector<uint32_t> recheck_rows;
+};
+
+struct ChunkSlot
+{
+    void       *d_kds = NULL;       /* staging copy of the chunk in HBM */
+    size_t      d_kds_cap = 0;
+    char       *d_kgpreagg = NULL;  /* kern_gpupreagg (status, kparams, row map) */
+    char       *h_kgpreagg = NULL;  /* pinned image */
+    size_t      kg_cap = 0;
+    cl_uint    *d_recheck = NULL;   /* 1 bit per row */
+    size_t      recheck_words = 0;
+    int32_t    *h_status = NULL;    /* pinned */
+    cudaEvent_t ev_copied = NULL;
+    cudaEvent_t ev_done = NULL;
+    pgs_ticket  ticket = -1;
+    uint32_t    nitems = 0;
+    bool        busy = false;
+};
+
+struct pgs_session
+{
+    int             device_index = 0;
+    int             ordinal = 0;
+    pgs_program    *program = NULL;
+    cudaLibrary_t   library = NULL;
+    cudaKernel_t    k_main = NULL, k_rowmap = NULL, k_init = NULL, k_flush = NULL,
+                    k_export = NULL, k_import = NULL, k_describe = NULL;
+    pgs_kern_desc   desc;
+    pgs_gstate      gs;
+    std::vector<char> kparams;
+    pgs_session_config config;
+    std::vector<kern_colmeta> result_colmeta;
+    cudaStream_t    s_copy = NULL, s_exec = NULL;
+    std::vector<ChunkSlot> slots;
+    pgs_ticket      next_ticket = 0;
+    std::map<pgs_ticket, ChunkResult> results;
+    int             grid_main = 0;
+    size_t          smem_main = 0;
+    cl_uint         sh_nslots = 0;
+    int             num_sms = 0;
+    uint64_t        launches = 0;
+    /* perfmon (pg_strom.h:177-213) */
+    uint64_t        num_dma_send = 0, bytes_dma_send = 0;
+    uint64_t        num_dma_recv = 0, bytes_dma_recv = 0;
+    uint64_t        num_chunks = 0, num_rechecked_chunks = 0;
+    double          time_kern_build_ms = 0;
+    void           *d_scratch = NULL;   /* small device buffer: desc, counters */
+    std::string     perfmon_buf;
+    bool            aborted = false;
+};
+
+static int
+session_alloc_state(pgs_session *s)
+{
+    size_t W = 1 + s->desc.num_cells;
+    size_t max_ctas = (size_t)s->num_sms * 16;
+    char   *base;
+    size_t  sz_small = 4096;
+
+    CUDA_CHECK(cudaMalloc(&s->d_scratch, sz_small + 8 * W * (1 + max_ctas)));
+    CUDA_CHECK(cudaMemset(s->d_scratch, 0, sz_small + 8 * W * (1 + max_ctas)));
+    base = (char *)s->d_scratch;
+    s->gs.ng_ticket = (cl_uint *)(base + 0);
+    s->gs.gh_ngroups = (cl_uint *)(base + 8);
+    s->gs.nrows_scanned = (cl_ulong *)(base + 16);
+    s->gs.nrows_filtered = (cl_ulong *)(base + 24);
+    s->gs.ng_state = (cl_ulong *)(base + sz_small);
+    s->gs.ng_partial = s->gs.ng_state + W;
+    s->gs.gh_slots = NULL;
+    s->gs.gh_nslots = 0;
+    s->gs.gh_max_probe = 0;
+    if (s->desc.num_keys > 0)
+    {
+        double want = s->config.num_groups * 2.0;
+        size_t nslots = 1024;
+        size_t free_b = 0, total_b = 0;
+        while ((double)nslots < want && nslots < (1ULL << 31))
+            nslots <<= 1;
+        cudaMemGetInfo(&free_b, &total_b);
+        while (nslots > 1024 && nslots * (size_t)s->desc.slot_bytes > free_b / 2)
+            nslots >>= 1;
+        CUDA_CHECK(cudaMalloc((void **)&s->gs.gh_slots, nslots * (size_t)s->desc.slot_bytes));
+        s->gs.gh_nslots = (cl_uint)nslots;
+        s->gs.gh_max_probe = (cl_uint)std::min<size_t>(nslots, 4096);
+    }
+    return StromError_Success;
+}
+
+static int
+launch_kernel(pgs_session *s, cudaKernel_t k, int grid, int block, size_t smem,
+              void **args)
+{
+    CUDA_CHECK(cudaLaunchKernel((const void *)k, dim3(grid), dim3(block), args,
+                                smem, s->s_exec));
+    s->launches++;
+    return StromError_Success;
+}
+
+static int
+session_init_state(pgs_session *s)
+{
+    void *args[] = { &s->gs };
+    int grid = std::max(1, std::min<int>(s->num_sms * 8,
+                                         (int)((s->gs.gh_nslots + 255) / 256)));
+    return launch_kernel(s, s->k_init, grid, 256, 0, args);
+}
+
+extern "C" int
+pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
+                const pgs_session_config *config, pgs_session **session)
+{
+    if (!program || !kparams || !config || !session)
+    {
+        set_error("pgs_preagg_open: bad arguments");
+        return StromError_BadRequestMessage;
+    }
+    int ord = device_ordinal(config->device);
+    if (ord < 0)
+    {
+        set_error("pgs_preagg_open: device layer is not initialised "
+                  "(pgs_cuda_init) or device index %d is out of range", config->device);
+        return StromError_ServerNotReady;
+    }
+    pgs_session *s = new pgs_session;
+    s->device_index = config->device;
+    s->ordinal = ord;
+    s->program = program;
+    s->config = *config;
+    s->kparams.assign((const char *)kparams, (const char *)kparams + kparams->length);
+    if (config->result_colmeta && config->result_ncols > 0)
+        s->result_colmeta.assign(config->result_colmeta,
+                                 config->result_colmeta + config->result_ncols);
+    s->num_sms = devices[config->device].prop.multiProcessorCount;
+    s->time_kern_build_ms = program->build_ms;
+
+#define OPEN_CHECK(call)                                                \
+    do {                                                                \
+        cudaError_t __rc = (call);                                      \
+        if (__rc != cudaSuccess)                                        \
+        {                                                               \
+            set_error("%s failed: %s (%s:%d)", #call,                   \
+                      cudaGetErrorString(__rc), __FILE__, __LINE__);    \
+            pgs_preagg_close(s);                                        \
+            return StromError_CudaInternal;                             \
+        }                                                               \
+    } while (0)
+
+    OPEN_CHECK(cudaSetDevice(ord));
+    OPEN_CHECK(cudaLibraryLoadData(&s->library, program->cubin.data(),
+                                   NULL, NULL, 0, NULL, NULL, 0));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_main, s->library, "gpupreagg_main"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_rowmap, s->library, "gpupreagg_main_rowmap"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_init, s->library, "gpupreagg_init_state"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_flush, s->library, "gpupreagg_flush"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_export, s->library, "gpupreagg_export"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_import, s->library, "gpupreagg_import"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_describe, s->library, "gpupreagg_describe"));
+    OPEN_CHECK(cudaStreamCreateWithFlags(&s->s_copy, cudaStreamNonBlocking));
+    OPEN_CHECK(cudaStreamCreateWithFlags(&s->s_exec, cudaStreamNonBlocking));
+
+    /* ask the program about its layouts */
+    {
+        pgs_kern_desc *d_desc;
+        OPEN_CHECK(cudaMalloc((void **)&d_desc, sizeof(pgs_kern_desc)));
+        void *args[] = { &d_desc };
+        cudaError_t rc = cudaLaunchKernel((const void *)s->k_describe, dim3(1), dim3(1),
+                                          args, 0, s->s_exec);
+        if (rc == cudaSuccess)
+            rc = cudaMemcpyAsync(&s->desc, d_desc, sizeof(pgs_kern_desc),
+                                 cudaMemcpyDeviceToHost, s->s_exec);
+        if (rc == cudaSuccess)
+            rc = cudaStreamSynchronize(s->s_exec);
+        cudaFree(d_desc);
+        OPEN_CHECK(rc);
+        s->launches++;
+    }
+    if ((s->desc.num_keys > 0) != (config->needs_grouping != 0))
+    {
+        set_error("pgs_preagg_open: needs_grouping=%d does not match the program (%u keys)",
+                  config->needs_grouping, s->desc.num_keys);
+        pgs_preagg_close(s);
+        return StromError_BadRequestMessage;
+    }
+    if (config->result_ncols > 0 && (cl_uint)config->result_ncols != s->desc.num_outcols)
+    {
+        set_error("pgs_preagg_open: result has %d columns, the program produces %u",
+                  config->result_ncols, s->desc.num_outcols);
+        pgs_preagg_close(s);
+        return StromError_BadRequestMessage;
+    }
+    /* launch shape of the main kernel: persistent CTAs, a multiple of the
+     * SM count */
+    {
+        size_t smem_max = devices[config->device].prop.sharedMemPerBlockOptin;
+        size_t base = (size_t)s->desc.static_smem_bytes +
+            (size_t)s->desc.num_stages * s->desc.stage_bytes;
+        int per_sm = 0;
+
+        s->sh_nslots = 0;
+        if (s->desc.num_keys > 0)
+        {
+            double want = std::max(64.0, config->num_groups * 2.0);
+            size_t avail = (smem_max > base + 1024 ? smem_max - base - 1024 : 0);
+            size_t maxslots = 64;
+            while (maxslots * 2 * s->desc.sh_slot_bytes <= avail)
+                maxslots <<= 1;
+            if (maxslots * s->desc.sh_slot_bytes > avail)
+                maxslots = 0;
+            size_t nslots = 64;
+            while ((double)nslots < want && nslots < maxslots)
+                nslots <<= 1;
+            const char *env = getenv("PGSTROM_SH_SLOTS");
+            if (env)
+                nslots = (size_t)atol(env);
+            /* a CTA-local table only pays when most groups fit in it */
+            if (maxslots == 0 || (!env && config->num_groups > 4.0 * (double)maxslots))
+                nslots = 0;
+            if (nslots > maxslots)
+                nslots = maxslots;
+            s->sh_nslots = (cl_uint)nslots;
+        }
+        s->smem_main = base + (size_t)s->sh_nslots * s->desc.sh_slot_bytes;
+        if (s->smem_main > smem_max)
+        {
+            set_error("device program needs %zu bytes of shared memory, the device allows %zu",
+                      s->smem_main, smem_max);
+            pgs_preagg_close(s);
+            return StromError_OutOfSharedMemory;
+        }
+        OPEN_CHECK(cudaFuncSetAttribute((const void *)s->k_main,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)s->smem_main));
+        OPEN_CHECK(cudaFuncSetAttribute((const void *)s->k_rowmap,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)s->smem_main));
+        OPEN_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                       &per_sm, (const void *)s->k_main,
+                       (int)s->desc.block_threads, s->smem_main));
+        if (per_sm < 1)
+            per_sm = 1;
+        const char *env = getenv("PGSTROM_CTAS_PER_SM");
+        if (env && atoi(env) > 0)
+            per_sm = std::min(per_sm, atoi(env));
+        s->grid_main = s->num_sms * per_sm;
+    }
+    {
+        int rc = session_alloc_state(s);
+        if (rc == StromError_Success)
+            rc = session_init_state(s);
+        if (rc != StromError_Success)
+        {
+            pgs_preagg_close(s);
+            return rc;
+        }
+    }
+    int nslots = config->max_async_chunks > 0 ? config->max_async_chunks
+                                              : (int)pgs::guc_int("pg_strom.max_async_chunks");
+    s->slots.resize(std::max(1, nslots));
+    for (auto &sl : s->slots)
+    {
+        OPEN_CHECK(cudaEventCreateWithFlags(&sl.ev_copied, cudaEventDisableTiming));
+        OPEN_CHECK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        OPEN_CHECK(cudaHostAlloc((void **)&sl.h_status, 64, cudaHostAllocPortable));
+    }
+    OPEN_CHECK(cudaStreamSynchronize(s->s_exec));
+    *session = s;
+    return StromError_Success;
+}
+
+static int
+slot_reserve(pgs_session *s, ChunkSlot &sl, size_t kds_bytes, size_t kg_bytes,
+             uint32_t nitems, bool need_kds)
+{
+    if (need_kds && sl.d_kds_cap < kds_bytes)
+    {
+        if (sl.d_kds)
+            CUDA_CHECK(cudaFree(sl.d_kds));
+        sl.d_kds = NULL;
+        sl.d_kds_cap = 0;
+        size_t cap = std::max(kds_bytes, s->config.max_chunk_bytes);
+        CUDA_CHECK(cudaMalloc(&sl.d_kds, cap));
+        sl.d_kds_cap = cap;
+    }
+    if (sl.kg_cap < kg_bytes)
+    {
+        if (sl.d_kgpreagg) CUDA_CHECK(cudaFree(sl.d_kgpreagg));
+        if (sl.h_kgpreagg) CUDA_CHECK(cudaFreeHost(sl.h_kgpreagg));
+        sl.d_kgpreagg = NULL;
+        sl.h_kgpreagg = NULL;
+        size_t cap = (kg_bytes + 4095) & ~(size_t)4095;
+        CUDA_CHECK(cudaMalloc((void **)&sl.d_kgpreagg, cap));
+        CUDA_CHECK(cudaHostAlloc((void **)&sl.h_kgpreagg, cap, cudaHostAllocPortable));
+        sl.kg_cap = cap;
+    }
+    size_t words = ((size_t)nitems + 31) / 32 + 1;
+    if (sl.recheck_words < words)
+    {
+        if (sl.d_recheck) CUDA_CHECK(cudaFree(sl.d_recheck));
+        sl.d_recheck = NULL;
+        size_t cap = std::max(words, ((size_t)s->config.max_chunk_rows + 31) / 32 + 1);
+        CUDA_CHECK(cudaMalloc((void **)&sl.d_recheck, cap * 4));
+        CUDA_CHECK(cudaMemsetAsync(sl.d_recheck, 0, cap * 4, s->s_exec));
+        sl.recheck_words = cap;
+    }
+    return StromError_Success;
+}
+
+/* completion of whatever occupies the slot (the reference's
+ * clserv_respond_gpupreagg, gpupreagg.c:3009-3194) */
+static int
+slot_retire(pgs_session *s, ChunkSlot &sl)
+{
+    if (!sl.busy)
+        return StromError_Success;
+    CUDA_CHECK(cudaEventSynchronize(sl.ev_done));
+    ChunkResult &res = s->results[sl.ticket];
+    res.status = *sl.h_status;
+    res.done = true;
+    if (res.status == StromError_CpuReCheck)
+    {
+        /* pull the per-row re-check bitmap and clear it for the next use */
+        size_t words = ((size_t)sl.nitems + 31) / 32;
+        std::vector<uint32_t> bm(words);
+        CUDA_CHECK(cudaMemcpyAsync(bm.data(), sl.d_recheck, words * 4,
+                                   cudaMemcpyDeviceToHost, s->s_exec));
+        CUDA_CHECK(cudaMemsetAsync(sl.d_recheck, 0, words * 4, s->s_exec));
+        CUDA_CHECK(cudaStreamSynchronize(s->s_exec));
+        s->num_dma_recv++;
+        s->bytes_dma_recv += words * 4;
+        for (size_t w = 0; w < words; w++)
+        {
+            uint32_t bits = bm[w];
+            while (bits)
+            {
+                int b = __builtin_ctz(bits);
+                res.recheck_rows.push_back((uint32_t)(w * 32 + b));
+                bits &= bits - 1;
+            }
+        }
+        s->num_rechecked_chunks++;
+    }
+    sl.busy = false;
+    return StromError_Success;
+}
+
+static int
+submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_dev,
+              size_t length, uint32_t nitems, const kern_row_map *krowmap,
+              pgs_ticket *ticket)
+{
+    if (!s || s->aborted)
+    {
+        set_error("session is closed or aborted");
+        return StromError_BadRequestMessage;
+    }
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    pgs_ticket t = s->next_ticket;
+    ChunkSlot &sl = s->slots[(size_t)(t % (pgs_ticket)s->slots.size())];
+    int rc = slot_retire(s, sl);
+    if (rc != StromError_Success)
+        return rc;
+
+    size_t rowmap_bytes = sizeof(cl_int);
+    if (krowmap && krowmap->nvalids >= 0)
+        rowmap_bytes += sizeof(cl_int) * (size_t)krowmap->nvalids;
+    size_t kg_head = STROMALIGN(offsetof(kern_gpupreagg, kparams) + s->kparams.size());
+    size_t kg_bytes = kg_head + rowmap_bytes;
+
+    rc = slot_reserve(s, sl, length, kg_bytes, nitems, kds_host != NULL);
+    if (rc != StromError_Success)
+        return rc;
+    /* kern_gpupreagg image: status, kparams, row map */
+    kern_gpupreagg *kg = (kern_gpupreagg *)sl.h_kgpreagg;
+    memset(kg, 0, offsetof(kern_gpupreagg, kparams));
+    kg->status = StromError_Success;
+    memcpy(&kg->kparams, s->kparams.data(), s->kparams.size());
+    kern_row_map *rm = (kern_row_map *)(sl.h_kgpreagg + kg_head);
+    if (krowmap && krowmap->nvalids >= 0)
+    {
+        rm->nvalids = krowmap->nvalids;
+        memcpy(rm->rindex, krowmap->rindex, sizeof(cl_int) * (size_t)krowmap->nvalids);
+    }
+    else
+        rm->nvalids = -1;
+
+    const void *d_kds = kds_dev;
+    if (kds_host)
+    {
+        CUDA_CHECK(cudaMemcpyAsync(sl.d_kds, kds_host, length,
+                                   cudaMemcpyHostToDevice, s->s_copy));
+        d_kds = sl.d_kds;
+        s->num_dma_send++;
+        s->bytes_dma_send += length;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(sl.d_kgpreagg, sl.h_kgpreagg, kg_bytes,
+                               cudaMemcpyHostToDevice, s->s_copy));
+    s->num_dma_send++;
+    s->bytes_dma_send += kg_bytes;
+    CUDA_CHECK(cudaEventRecord(sl.ev_copied, s->s_copy));
+    CUDA_CHECK(cudaStreamWaitEvent(s->s_exec, sl.ev_copied, 0));
+
+    bool use_rowmap = (krowmap && krowmap->nvalids >= 0);
+    void *args[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck, &s->sh_nslots };
+    int grid = s->grid_main;
+    if (!use_rowmap)
+    {
+        uint32_t ntiles = (nitems + s->desc.tile_rows - 1) / s->desc.tile_rows;
+        if ((uint32_t)grid > ntiles)
+            grid = (int)std::max<uint32_t>(1, ntiles);
+    }
+    rc = launch_kernel(s, use_rowmap ? s->k_rowmap : s->k_main, grid,
+                       (int)s->desc.block_threads, s->smem_main, args);
+    if (rc != StromError_Success)
+        return rc;
+    CUDA_CHECK(cudaMemcpyAsync(sl.h_status, sl.d_kgpreagg, sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, s->s_exec));
+    CUDA_CHECK(cudaEventRecord(sl.ev_done, s->s_exec));
+    s->num_dma_recv++;
+    s->bytes_dma_recv += sizeof(int32_t);
+    s->num_chunks++;
+    sl.busy = true;
+    sl.ticket = t;
+    sl.nitems = nitems;
+    s->results[t] = ChunkResult();
+    s->next_ticket++;
+    if (ticket)
+        *ticket = t;
+    return StromError_Success;
+}
+
+extern "C" int
+pgs_preagg_submit(pgs_session *session, const kern_data_store *kds_in,
+                  const kern_row_map *krowmap, pgs_ticket *ticket)
+{
+    if (!kds_in)
+    {
+        set_error("pgs_preagg_submit: no chunk");
+        return StromError_BadRequestMessage;
+    }
+    if (kds_in->format != KDS_FORMAT_COLUMN)
+    {
+        set_error("pgs_preagg_submit: chunk format %d is not supported yet "
+                  "(only KDS_FORMAT_COLUMN)", (int)kds_in->format);
+        return StromError_BadRequestMessage;
+    }
+    return submit_common(session, kds_in, NULL, kds_in->length, kds_in->nitems,
+                         krowmap, ticket);
+}
+
+extern "C" int
+pgs_preagg_submit_device(pgs_session *session, const void *kds_in_device,
+                         size_t length, uint32_t nitems,
+                         const kern_row_map *krowmap, pgs_ticket *ticket)
+{
+    if (!kds_in_device)
+    {
+        set_error("pgs_preagg_submit_device: no chunk");
+        return StromError_BadRequestMessage;
+    }
+    return submit_common(session, NULL, kds_in_device, length, nitems, krowmap, ticket);
+}
+
+extern "C" int
+pgs_preagg_wait(pgs_session *s, pgs_ticket ticket, int timeout_ms, int32_t *status)
+{
+    if (!s)
+        return StromError_BadRequestMessage;
+    auto it = s->results.find(ticket);
+    if (it == s->results.end())
+    {
+        set_error("unknown ticket %lld", (long long)ticket);
+        return StromError_BadRequestMessage;
+    }
+    if (!it->second.done)
+    {
+        ChunkSlot &sl = s->slots[(size_t)(ticket % (pgs_ticket)s->slots.size())];
+        if (sl.busy && sl.ticket == ticket)
+        {
+            if (timeout_ms >= 0)
+            {
+                /* mqueue.c:257-324: poll up to the timeout */
+                auto t0 = std::chrono::steady_clock::now();
+                for (;;)
+                {
+                    cudaError_t q = cudaEventQuery(sl.ev_done);
+                    if (q == cudaSuccess)
+                        break;
+                    if (q != cudaErrorNotReady)
+                    {
+                        set_error("cudaEventQuery: %s", cudaGetErrorString(q));
+                        return StromError_CudaInternal;
+                    }
+                    double ms = std::chrono::duration<double, std::milli>(
+                        std::chrono::steady_clock::now() - t0).count();
+                    if (ms >= (double)timeout_ms)
+                        return -1;      /* still running */
+                    std::this_thread::sleep_for(std::chrono::microseconds(50));
+                }
+            }
+            int rc = slot_retire(s, sl);
+            if (rc != StromError_Success)
+                return rc;
+        }
+    }
+    if (status)
+        *status = it->second.status;
+    return StromError_Success;
+}
+
+extern "C" int64_t
+pgs_preagg_recheck_rows(pgs_session *s, pgs_ticket ticket, uint32_t *rows, int64_t max_rows)
+{
+    auto it = s->results.find(ticket);
+    if (it == s->results.end() || !it->second.done)
+        return -1;
+    int64_t n = (int64_t)it->second.recheck_rows.size();
+    if (rows)
+        for (int64_t i = 0; i < n && i < max_rows; i++)
+            rows[i] = it->second.recheck_rows[(size_t)i];
+    return n;
+}
+
+static int
+drain(pgs_session *s)
+{
+    for (auto &sl : s->slots)
+    {
+        int rc = slot_retire(s, sl);
+        if (rc != StromError_Success)
+            return rc;
+    }
+    return StromError_Success;
+}
+
+extern "C" int
+pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
+                  uint32_t *nrows_needed, int32_t *status)
+{
+    if (!s || !kds_dst)
+        return StromError_BadRequestMessage;
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    int rc = drain(s);
+    if (rc != StromError_Success)
+        return rc;
+    if (kds_dst->format != KDS_FORMAT_TUPSLOT || kds_dst->ncols != s->desc.num_outcols)
+    {
+        set_error("pgs_preagg_finish: destination must be a TUPSLOT store with %u columns",
+                  s->desc.num_outcols);
+        return StromError_BadRequestMessage;
+    }
+    size_t head = KERN_DATA_STORE_HEAD_LENGTH(kds_dst->ncols);
+    size_t stride = KERN_DATA_STORE_SLOT_STRIDE(kds_dst->ncols);
+    size_t total = head + stride * (size_t)kds_dst->nrooms;
+    char *d_dst = NULL;
+    kern_gpupreagg *d_kg = NULL;
+    int32_t h_status = 0;
+    kern_data_store hdr;
+
+    CUDA_CHECK(cudaMalloc((void **)&d_dst, total));
+    CUDA_CHECK(cudaMalloc((void **)&d_kg, sizeof(kern_gpupreagg)));
+    kds_dst->nitems = 0;
+    cudaError_t e = cudaMemcpyAsync(d_dst, kds_dst, head, cudaMemcpyHostToDevice, s->s_exec);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(d_kg, 0, sizeof(kern_gpupreagg), s->s_exec);
+    if (e == cudaSuccess)
+    {
+        void *args[] = { &s->gs, &d_dst, &d_kg };
+        int grid = (s->desc.num_keys == 0) ? 1 :
+            std::max(1, std::min<int>(s->num_sms * 8, (int)((s->gs.gh_nslots + 255) / 256)));
+        rc = launch_kernel(s, s->k_flush, grid, 256, 0, args);
+        if (rc != StromError_Success)
+            e = cudaErrorUnknown;
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&hdr, d_dst, offsetof(kern_data_store, colmeta),
+                            cudaMemcpyDeviceToHost, s->s_exec);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&h_status, d_kg, sizeof(int32_t), cudaMemcpyDeviceToHost, s->s_exec);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(s->s_exec);
+    if (e == cudaSuccess)
+    {
+        if (nrows_needed)
+            *nrows_needed = hdr.nitems;
+        if (h_status == StromError_Success && hdr.nitems <= kds_dst->nrooms)
+        {
+            size_t nbytes = stride * (size_t)hdr.nitems;
+            if (nbytes > 0)
+                e = cudaMemcpy((char *)kds_dst + head, d_dst + head, nbytes,
+                               cudaMemcpyDeviceToHost);
+            kds_dst->nitems = hdr.nitems;
+            s->num_dma_recv += 2;
+            s->bytes_dma_recv += nbytes + sizeof(hdr);
+        }
+        else if (h_status == StromError_Success)
+            h_status = StromError_DataStoreNoSpace;
+    }
+    cudaFree(d_dst);
+    cudaFree(d_kg);
+    if (e != cudaSuccess)
+    {
+        set_error("pgs_preagg_finish: %s", cudaGetErrorString(e));
+        return StromError_CudaInternal;
+    }
+    if (status)
+        *status = h_status;
+    if (h_status == StromError_DataStoreNoSpace)
+    {
+        set_error("result store has %u rooms, %u rows are needed",
+                  kds_dst->nrooms, hdr.nitems);
+        return StromError_DataStoreNoSpace;
+    }
+    if (reset && h_status == StromError_Success)
+    {
+        rc = session_init_state(s);
+        if (rc != StromError_Success)
+            return rc;
+        CUDA_CHECK(cudaStreamSynchronize(s->s_exec));
+    }
+    return StromErrorIsSignificant(h_status) ? h_status : StromError_Success;
+}
+
+extern "C" int
+pgs_preagg_state_reset(pgs_session *s)
+{
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    int rc = drain(s);
+    if (rc == StromError_Success)
+        rc = session_init_state(s);
+    if (rc != StromError_Success)
+        return rc;
+    CUDA_CHECK(cudaStreamSynchronize(s->s_exec));
+    return StromError_Success;
+}
+
+extern "C" int
+pgs_preagg_state_export(pgs_session *s, void *device_buf, size_t buflen,
+                        uint32_t *nrecords, size_t *record_bytes)
+{
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    int rc = drain(s);
+    if (rc != StromError_Success)
+        return rc;
+    size_t recb = s->desc.slot_bytes;
+    if (record_bytes)
+        *record_bytes = recb;
+    cl_uint *d_n = (cl_uint *)((char *)s->d_scratch + 64);
+    cl_uint max_records = (cl_uint)std::min<size_t>(buflen / recb, 0xffffffffU);
+    cl_ulong *recs = (cl_ulong *)device_buf;
+    CUDA_CHECK(cudaMemsetAsync(d_n, 0, sizeof(cl_uint), s->s_exec));
+    void *args[] = { &s->gs, &recs, &d_n, &max_records };
+    int grid = (s->desc.num_keys == 0) ? 1 :
+        std::max(1, std::min<int>(s->num_sms * 8, (int)((s->gs.gh_nslots + 255) / 256)));
+    rc = launch_kernel(s, s->k_export, grid, 256, 0, args);
+    if (rc != StromError_Success)
+        return rc;
+    cl_uint n = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n, d_n, sizeof(cl_uint), cudaMemcpyDeviceToHost, s->s_exec));
+    CUDA_CHECK(cudaStreamSynchronize(s->s_exec));
+    if (nrecords)
+        *nrecords = n;
+    if (n > max_records)
+    {
+        set_error("state export needs room for %u records, buffer holds %u", n, max_records);
+        return StromError_DataStoreNoSpace;
+    }
+    return StromError_Success;
+}
+
+extern "C" int
+pgs_preagg_state_import(pgs_session *s, const void *device_buf, uint32_t nrecords)
+{
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    kern_gpupreagg *d_kg = NULL;
+    int32_t h_status = 0;
+    const cl_ulong *recs = (const cl_ulong *)device_buf;
+    CUDA_CHECK(cudaMalloc((void **)&d_kg, sizeof(kern_gpupreagg)));
+    cudaError_t e = cudaMemsetAsync(d_kg, 0, sizeof(kern_gpupreagg), s->s_exec);
+    int rc = StromError_Success;
+    if (e == cudaSuccess)
+    {
+        void *args[] = { &s->gs, &recs, &nrecords, &d_kg };
+        int grid = (s->desc.num_keys == 0) ? 1 :
+            std::max(1, std::min<int>(s->num_sms * 8, (int)((nrecords + 255) / 256)));
+        rc = launch_kernel(s, s->k_import, grid, 256, 0, args);
+    }
+    if (e == cudaSuccess && rc == StromError_Success)
+        e = cudaMemcpyAsync(&h_status, d_kg, sizeof(int32_t), cudaMemcpyDeviceToHost, s->s_exec);
+    if (e == cudaSuccess && rc == StromError_Success)
+        e = cudaStreamSynchronize(s->s_exec);
+    cudaFree(d_kg);
+    if (rc != StromError_Success)
+        return rc;
+    if (e != cudaSuccess)
+    {
+        set_error("pgs_preagg_state_import: %s", cudaGetErrorString(e));
+        return StromError_CudaInternal;
+    }
+    return h_status;
+}
+
+/* ---- NCCL merge: libnccl is opened lazily so that the library loads (and
+ * the single-GPU path runs) on hosts without it ---- */
+typedef int (*nccl_allgather_fn)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*nccl_send_fn)(const void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_recv_fn)(void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_group_fn)(void);
+typedef const char *(*nccl_errstr_fn)(int);
+static struct {
+    void *handle;
+    nccl_allgather_fn allgather;
+    nccl_send_fn send;
+    nccl_recv_fn recv;
+    nccl_group_fn group_start, group_end;
+    nccl_errstr_fn errstr;
+} nccl;
+
+static int
+nccl_load(void)
+{
+    if (nccl.handle)
+        return StromError_Success;
+    const char *names[] = { "libnccl.so.2", "libnccl.so", NULL };
+    for (int i = 0; names[i] && !nccl.handle; i++)
+        nccl.handle = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!nccl.handle)
+    {
+        set_error("cannot load libnccl: %s", dlerror());
+        return StromError_ServerNotReady;
+    }
+    nccl.allgather = (nccl_allgather_fn)dlsym(nccl.handle, "ncclAllGather");
+    nccl.send = (nccl_send_fn)dlsym(nccl.handle, "ncclSend");
+    nccl.recv = (nccl_recv_fn)dlsym(nccl.handle, "ncclRecv");
+    nccl.group_start = (nccl_group_fn)dlsym(nccl.handle, "ncclGroupStart");
+    nccl.group_end = (nccl_group_fn)dlsym(nccl.handle, "ncclGroupEnd");
+    nccl.errstr = (nccl_errstr_fn)dlsym(nccl.handle, "ncclGetErrorString");
+    if (!nccl.allgather || !nccl.send || !nccl.recv || !nccl.group_start || !nccl.group_end)
+    {
+        set_error("libnccl lacks a required symbol");
+        return StromError_ServerNotReady;
+    }
+    return StromError_Success;
+}
+
+#define NCCL_CHECK(call)                                                \
+    do {                                                                \
+        int __rc = (call);                                              \
+        if (__rc != 0)                                                  \
+        {                                                               \
+            set_error("%s failed: %s", #call,                           \
+                      nccl.errstr ? nccl.errstr(__rc) : "?");           \
+            return StromError_CudaInternal;                             \
+        }                                                               \
+    } while (0)
+
+extern "C" int
+pgs_preagg_merge_nccl(pgs_session *s, void *nccl_comm, int rank, int nranks, int root)
+{
+    /* ncclUint8 = 1 */
+    const int NCCL_UINT8 = 1;
+    int rc = nccl_load();
+    if (rc != StromError_Success)
+        return rc;
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    rc = drain(s);
+    if (rc != StromError_Success)
+        return rc;
+    size_t recb = s->desc.slot_bytes;
+    /* 1. how many records does each rank hold? */
+    cl_uint my_n = 1;
+    if (s->desc.num_keys > 0)
+        CUDA_CHECK(cudaMemcpy(&my_n, s->gs.gh_ngroups, sizeof(cl_uint), cudaMemcpyDeviceToHost));
+    cl_uint *d_counts = NULL;
+    std::vector<cl_uint> counts(nranks, 0);
+    CUDA_CHECK(cudaMalloc((void **)&d_counts, sizeof(cl_uint) * (nranks + 1)));
+    CUDA_CHECK(cudaMemcpy(d_counts + nranks, &my_n, sizeof(cl_uint), cudaMemcpyHostToDevice));
+    NCCL_CHECK(nccl.allgather(d_counts + nranks, d_counts, sizeof(cl_uint), NCCL_UINT8,
+                              nccl_comm, s->s_exec));
+    CUDA_CHECK(cudaMemcpyAsync(counts.data(), d_counts, sizeof(cl_uint) * nranks,
+                               cudaMemcpyDeviceToHost, s->s_exec));
+    CUDA_CHECK(cudaStreamSynchronize(s->s_exec));
+    cudaFree(d_counts);
+    /* 2. non-root ranks export + send; the root receives in rank order and
+     *    imports (re-hash / ordered merge) */
+    if (rank != root)
+    {
+        void *d_recs = NULL;
+        cl_uint n = 0;
+        CUDA_CHECK(cudaMalloc(&d_recs, std::max<size_t>(recb * my_n, recb)));
+        rc = pgs_preagg_state_export(s, d_recs, std::max<size_t>(recb * my_n, recb), &n, NULL);
+        if (rc == StromError_Success)
+        {
+            int nrc = nccl.send(d_recs, recb * (size_t)n, NCCL_UINT8, root, nccl_comm, s->s_exec);
+            if (nrc != 0)
+                rc = StromError_CudaInternal;
+        }
+        cudaStreamSynchronize(s->s_exec);
+        cudaFree(d_recs);
+        if (rc != StromError_Success)
+            return rc;
+        /* this rank's state now lives on the root */
+        return pgs_preagg_state_reset(s);
+    }
+    size_t total = 0;
+    for (int r = 0; r < nranks; r++)
+        if (r != root)
+            total += counts[r];
+    if (total == 0)
+        return StromError_Success;
+    char *d_recs = NULL;
+    CUDA_CHECK(cudaMalloc((void **)&d_recs, recb * total));
+    NCCL_CHECK(nccl.group_start());
+    size_t off = 0;
+    for (int r = 0; r < nranks; r++)
+    {
+        if (r == root || counts[r] == 0)
+            continue;
+        NCCL_CHECK(nccl.recv(d_recs + off * recb, recb * (size_t)counts[r], NCCL_UINT8, r,
+                             nccl_comm, s->s_exec));
+        off += counts[r];
+    }
+    NCCL_CHECK(nccl.group_end());
+    rc = pgs_preagg_state_import(s, d_recs, (uint32_t)total);
+    cudaFree(d_recs);
+    return rc;
+}
+
+extern "C" const char *
+pgs_preagg_perfmon_json(pgs_session *s)
+{
+    pgs::JsonPtr o = pgs::Json::object();
+    cl_ulong counters[2] = {0, 0};
+    if (s->d_scratch && cudaSetDevice(s->ordinal) == cudaSuccess)
+        cudaMemcpy(counters, (char *)s->d_scratch + 16, sizeof(counters), cudaMemcpyDeviceToHost);
+    o->set("num_dma_send", (long long)s->num_dma_send);
+    o->set("bytes_dma_send", (long long)s->bytes_dma_send);
+    o->set("num_dma_recv", (long long)s->num_dma_recv);
+    o->set("bytes_dma_recv", (long long)s->bytes_dma_recv);
+    o->set("num_chunks", (long long)s->num_chunks);
+    o->set("num_rechecked_chunks", (long long)s->num_rechecked_chunks);
+    o->set("num_kernel_launches", (long long)s->launches);
+    o->set("time_kern_build_ms", pgs::Json::number(s->time_kern_build_ms));
+    o->set("nrows_filtered", (long long)counters[1]);
+    o->set("grid_main", s->grid_main);
+    o->set("smem_main", (long long)s->smem_main);
+    o->set("sh_nslots", (long long)s->sh_nslots);
+    o->set("gh_nslots", (long long)s->gs.gh_nslots);
+    o->set("block_threads", (long long)s->desc.block_threads);
+    o->set("tile_rows", (long long)s->desc.tile_rows);
+    o->set("num_stages", (long long)s->desc.num_stages);
+    o->set("stage_bytes", (long long)s->desc.stage_bytes);
+    o->set("row_bytes", (long long)s->desc.row_bytes);
+    o->set("slot_bytes", (long long)s->desc.slot_bytes);
+    s->perfmon_buf = o->dump();
+    return s->perfmon_buf.c_str();
+}
+
+extern "C" void
+pgs_preagg_abort(pgs_session *s)
+{
+    if (!s)
+        return;
+    /* in-flight chunks may still be read by the device: wait for them
+     * before the caller frees anything (restrack.c contract) */
+    if (cudaSetDevice(s->ordinal) == cudaSuccess)
+    {
+        if (s->s_copy) cudaStreamSynchronize(s->s_copy);
+        if (s->s_exec) cudaStreamSynchronize(s->s_exec);
+    }
+    for (auto &sl : s->slots)
+        sl.busy = false;
+    s->aborted = true;
+}
+
+extern "C" void
+pgs_preagg_close(pgs_session *s)
+{
+    if (!s)
+        return;
+    if (cudaSetDevice(s->ordinal) == cudaSuccess)
+    {
+        if (s->s_copy) cudaStreamSynchronize(s->s_copy);
+        if (s->s_exec) cudaStreamSynchronize(s->s_exec);
+        for (auto &sl : s->slots)
+        {
+            if (sl.d_kds) cudaFree(sl.d_kds);
+            if (sl.d_kgpreagg) cudaFree(sl.d_kgpreagg);
+            if (sl.h_kgpreagg) cudaFreeHost(sl.h_kgpreagg);
+            if (sl.d_recheck) cudaFree(sl.d_recheck);
+            if (sl.h_status) cudaFreeHost(sl.h_status);
+            if (sl.ev_copied) cudaEventDestroy(sl.ev_copied);
+            if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        }
+        if (s->gs.gh_slots) cudaFree(s->gs.gh_slots);
+        if (s->d_scratch) cudaFree(s->d_scratch);
+        if (s->s_copy) cudaStreamDestroy(s->s_copy);
+        if (s->s_exec) cudaStreamDestroy(s->s_exec);
+        if (s->library) cudaLibraryUnload(s->library);
+    }
+    delete s;
+}
+
+extern "C" void *
+pgs_preagg_stream(pgs_session *s)
+{
+    return s ? (void *)s->s_exec : NULL;
+}
+
+extern "C" uint64_t
+pgs_preagg_launch_count(pgs_session *s)
+{
+    return s ? s->launches : 0;
+}
+
+extern "C" int
+pgs_device_l2_flush(int device)
+{
+    /* write a buffer larger than L2 (126 MB on B200) */
+    static std::map<int, void *> bufs;
+    int ord = device_ordinal(device);
+    const size_t sz = 256UL << 20;
+    if (ord < 0)
+        return StromError_ServerNotReady;
+    CUDA_CHECK(cudaSetDevice(ord));
+    if (!bufs.count(ord))
+    {
+        void *p = NULL;
+        CUDA_CHECK(cudaMalloc(&p, sz));
+        bufs[ord] = p;
+    }
+    static int v = 0;
+    CUDA_CHECK(cudaMemset(bufs[ord], ++v & 0xff, sz));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    return StromError_Success;
+}

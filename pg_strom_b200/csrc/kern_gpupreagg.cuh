@@ -1,0 +1,1472 @@
+/*
+ * kern_gpupreagg.cuh - hand-written kernel templates of GpuPreAgg for sm_100a.
+ *
+ * The reference runs six OpenCL kernels per chunk
+ * (opencl_gpupreagg.h:380-856: preparation, set_rindex, bitonic_local/step/
+ * merge, reduction) and materialises an intermediate TUPSLOT store.  Here one
+ * persistent kernel per chunk does all of it:
+ *
+ *   TMA (cp.async.bulk) column slices -> shared-memory ring   [producer warp]
+ *   gpupreagg_qual_eval()   generated, per row                [consumer warps]
+ *   gpupreagg_projection()  generated, into registers (pagg_row)
+ *   no GROUP BY : per-thread accumulators -> warp shuffle -> CTA -> one
+ *                 deterministic merge by the last CTA into the state row
+ *   GROUP BY    : shared-memory open-addressing table (SoA) per CTA, spill and
+ *                 final merge into a global open-addressing table (AoS)
+ *
+ * and gpupreagg_flush writes the partial rows as a TUPSLOT kern_data_store
+ * exactly as ExecStoreVirtualTuple expects them (opencl_common.h:417-427,
+ * 567-580).  Merge rules follow opencl_gpupreagg.h:862-987 (PMIN/PMAX ignore
+ * NULL, PSUM becomes non-NULL on the first non-NULL input) with three
+ * deliberate differences, each making the device handle strictly more rows
+ * without changing any result:
+ *   - integer sums are 64/128-bit and counts 64-bit internally; values that
+ *     do not fit the output column are emitted as several partial rows
+ *     (the final aggregates add them up), never CpuReCheck;
+ *   - float sums re-check a *row* whose magnitude could overflow the sum in
+ *     some order (|x| > 2^960, float4: 2^88) instead of the whole chunk;
+ *   - float min/max order NaN above everything like PostgreSQL
+ *     (opencl_common.h:1553-1560), not OpenCL min()/max().
+ * A row that the device cannot finish is flagged in a per-chunk bitmap and
+ * the chunk status becomes StromError_CpuReCheck; every other row of the
+ * chunk is still aggregated on the device.
+ *
+ * Compile-time inputs, emitted by codegen (see codegen.cpp):
+ *   GPUPREAGG_NUM_INCOLS, GPUPREAGG_INCOL_SLOT(colidx), GPUPREAGG_INCOL_LIST(_)
+ *   GPUPREAGG_NUM_KEYS,  GPUPREAGG_KEY_LIST(_)
+ *   GPUPREAGG_NUM_AGGS,  GPUPREAGG_NUM_CELLS, GPUPREAGG_AGG_LIST(_)
+ *   GPUPREAGG_NUM_OUTCOLS, GPUPREAGG_OUT_LIST(_)
+ *   GPUPREAGG_FIELD_ROLE(colidx), GPUPREAGG_FIELD_INDEX(colidx)
+ * and by the CUDA layer (-D): GPUPREAGG_TILE_ROWS, GPUPREAGG_NUM_STAGES,
+ *   GPUPREAGG_CONSUMER_WARPS.
+ */
+#ifndef KERN_GPUPREAGG_CUH
+#define KERN_GPUPREAGG_CUH
+
+#include "kern_shared.h"
+
+#ifndef GPUPREAGG_TILE_ROWS
+#define GPUPREAGG_TILE_ROWS         2048
+#endif
+#ifndef GPUPREAGG_NUM_STAGES
+#define GPUPREAGG_NUM_STAGES        4
+#endif
+#ifndef GPUPREAGG_CONSUMER_WARPS
+#define GPUPREAGG_CONSUMER_WARPS    8
+#endif
+#define GPUPREAGG_CONSUMER_THREADS  (GPUPREAGG_CONSUMER_WARPS * 32)
+#define GPUPREAGG_BLOCK_THREADS     (GPUPREAGG_CONSUMER_THREADS + 32)
+
+#define PGS_MAX(a,b)    ((a) > (b) ? (a) : (b))
+
+/* ------------------------------------------------------------------
+ * pagg_datum / pagg_row: what gpupreagg_projection() produces for one input
+ * row (the reference writes the same thing into a kds_src TUPSLOT row,
+ * gpupreagg.c:1495-1748; here it lives in registers).
+ * ------------------------------------------------------------------ */
+typedef struct
+{
+    cl_char         isnull;
+    union {
+        cl_short    short_val;
+        cl_int      int_val;
+        cl_long     long_val;
+        cl_float    float_val;
+        cl_double   double_val;
+        cl_ulong    ulong_val;
+    };
+} pagg_datum;
+
+struct pagg_row
+{
+    pagg_datum  key[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
+    pagg_datum  agg[PGS_MAX(GPUPREAGG_NUM_AGGS, 1)];
+
+    __device__ __forceinline__ void
+    store(cl_uint colidx, bool isnull, cl_ulong bits)
+    {
+        /* colidx is a literal in generated code: both switches fold */
+        if (GPUPREAGG_FIELD_ROLE(colidx) == GPUPREAGG_FIELD_IS_GROUPKEY)
+        {
+            key[GPUPREAGG_FIELD_INDEX(colidx)].isnull = isnull;
+            key[GPUPREAGG_FIELD_INDEX(colidx)].ulong_val = bits;
+        }
+        else if (GPUPREAGG_FIELD_ROLE(colidx) == GPUPREAGG_FIELD_IS_AGGFUNC)
+        {
+            agg[GPUPREAGG_FIELD_INDEX(colidx)].isnull = isnull;
+            agg[GPUPREAGG_FIELD_INDEX(colidx)].ulong_val = bits;
+        }
+    }
+};
+
+/* pg_<type>_vstore(kds_src, kds_in, errcode, colidx, rowidx_out, datum):
+ * same call shape as the reference's generated projection
+ * (gpupreagg.c:1508-1518); kds_src is the pagg_row. */
+#define STROMCL_SIMPLE_VARSTORE_TEMPLATE(NAME,BASE)                     \
+    template <typename KDS>                                             \
+    DEVFN void                                                          \
+    pg_##NAME##_vstore(pagg_row &kds_src, const KDS &kds_in,            \
+                       cl_int *errcode, cl_uint colidx,                 \
+                       cl_uint rowidx_out, pg_##NAME##_t datum)         \
+    {                                                                   \
+        union { BASE v_base; cl_ulong v_datum; } temp;                  \
+        temp.v_datum = 0;                                               \
+        temp.v_base = datum.value;                                      \
+        kds_src.store(colidx, datum.isnull, temp.v_datum);              \
+    }
+STROMCL_SIMPLE_VARSTORE_TEMPLATE(bool, cl_bool)
+STROMCL_SIMPLE_VARSTORE_TEMPLATE(int2, cl_short)
+STROMCL_SIMPLE_VARSTORE_TEMPLATE(int4, cl_int)
+STROMCL_SIMPLE_VARSTORE_TEMPLATE(int8, cl_long)
+STROMCL_SIMPLE_VARSTORE_TEMPLATE(float4, cl_float)
+STROMCL_SIMPLE_VARSTORE_TEMPLATE(float8, cl_double)
+STROMCL_SIMPLE_VARSTORE_TEMPLATE(date, cl_int)
+STROMCL_SIMPLE_VARSTORE_TEMPLATE(time, cl_long)
+STROMCL_SIMPLE_VARSTORE_TEMPLATE(timestamp, cl_long)
+
+/* NULL-const output columns need no work on the device */
+template <typename KDS>
+DEVFN void
+pg_common_vstore(pagg_row &kds_src, const KDS &kds_in, cl_int *errcode,
+                 cl_uint colidx, cl_uint rowidx_out, bool isnull)
+{}
+
+/* ------------------------------------------------------------------
+ * state cells.  One group's running state = GPUPREAGG_NUM_CELLS 8-byte
+ * cells + one bit per aggregate ("saw a non-NULL input").
+ *
+ *   PSUM  INT / LONGS : cl_long sum            (nrows; psum of int2/int4 cast)
+ *   PSUM  LONG        : 128-bit sum, 2 cells   (psum of a genuine int8)
+ *   PSUM  FLOAT/DOUBLE: cl_double sum
+ *   PMIN/PMAX SHORT/INT/LONG : cl_long
+ *   PMIN/PMAX FLOAT/DOUBLE   : order-preserving cl_ulong key, NaN highest
+ * ------------------------------------------------------------------ */
+#define PGS_F8_SIGNBIT      0x8000000000000000ULL
+#define PGS_F8_NANKEY       0xFFFFFFFFFFFFFFFFULL
+/* re-check thresholds of float sums (see the head of this file) */
+#define PGS_PSUM_DOUBLE_LIMIT   9.7453140113999990e+288     /* 2^960 */
+#define PGS_PSUM_FLOAT_LIMIT    3.0948500982134507e+26      /* 2^88  */
+
+DEVFN cl_ulong
+pgs_f8_sortkey(double v)
+{
+    cl_ulong    b;
+
+    if (isnan(v))
+        return PGS_F8_NANKEY;
+    b = (cl_ulong)__double_as_longlong(v);
+    return (b & PGS_F8_SIGNBIT) ? ~b : (b | PGS_F8_SIGNBIT);
+}
+
+DEVFN double
+pgs_f8_from_sortkey(cl_ulong k)
+{
+    if (k == PGS_F8_NANKEY)
+        return __longlong_as_double(0x7FF8000000000000LL);
+    return __longlong_as_double((cl_long)((k & PGS_F8_SIGNBIT)
+                                          ? (k & ~PGS_F8_SIGNBIT) : ~k));
+}
+
+/* identity element of each cell kind */
+#define PGS_CELL_INIT_PSUM_INT(c,p)     (p)[c] = 0;
+#define PGS_CELL_INIT_PSUM_LONGS(c,p)   (p)[c] = 0;
+#define PGS_CELL_INIT_PSUM_LONG(c,p)    (p)[c] = 0; (p)[(c)+1] = 0;
+#define PGS_CELL_INIT_PSUM_FLOAT(c,p)   (p)[c] = 0;
+#define PGS_CELL_INIT_PSUM_DOUBLE(c,p)  (p)[c] = 0;
+#define PGS_CELL_INIT_PMIN_SHORT(c,p)   (p)[c] = (cl_ulong)LONG_MAX;
+#define PGS_CELL_INIT_PMIN_INT(c,p)     (p)[c] = (cl_ulong)LONG_MAX;
+#define PGS_CELL_INIT_PMIN_LONG(c,p)    (p)[c] = (cl_ulong)LONG_MAX;
+#define PGS_CELL_INIT_PMIN_FLOAT(c,p)   (p)[c] = PGS_F8_NANKEY;
+#define PGS_CELL_INIT_PMIN_DOUBLE(c,p)  (p)[c] = PGS_F8_NANKEY;
+#define PGS_CELL_INIT_PMAX_SHORT(c,p)   (p)[c] = (cl_ulong)LONG_MIN;
+#define PGS_CELL_INIT_PMAX_INT(c,p)     (p)[c] = (cl_ulong)LONG_MIN;
+#define PGS_CELL_INIT_PMAX_LONG(c,p)    (p)[c] = (cl_ulong)LONG_MIN;
+#define PGS_CELL_INIT_PMAX_FLOAT(c,p)   (p)[c] = 0;
+#define PGS_CELL_INIT_PMAX_DOUBLE(c,p)  (p)[c] = 0;
+
+/* ---- value of one projected datum in "cell domain" ---- */
+#define PGS_NEWVAL_PSUM_INT(d)      ((cl_ulong)(cl_long)(d).int_val)
+#define PGS_NEWVAL_PSUM_LONGS(d)    ((cl_ulong)(d).long_val)
+#define PGS_NEWVAL_PSUM_LONG(d)     ((cl_ulong)(d).long_val)
+#define PGS_NEWVAL_PSUM_FLOAT(d)    ((cl_ulong)__double_as_longlong((double)(d).float_val))
+#define PGS_NEWVAL_PSUM_DOUBLE(d)   ((cl_ulong)__double_as_longlong((d).double_val))
+#define PGS_NEWVAL_PMIN_SHORT(d)    ((cl_ulong)(cl_long)(d).short_val)
+#define PGS_NEWVAL_PMIN_INT(d)      ((cl_ulong)(cl_long)(d).int_val)
+#define PGS_NEWVAL_PMIN_LONG(d)     ((cl_ulong)(d).long_val)
+#define PGS_NEWVAL_PMIN_FLOAT(d)    pgs_f8_sortkey((double)(d).float_val)
+#define PGS_NEWVAL_PMIN_DOUBLE(d)   pgs_f8_sortkey((d).double_val)
+#define PGS_NEWVAL_PMAX_SHORT(d)    PGS_NEWVAL_PMIN_SHORT(d)
+#define PGS_NEWVAL_PMAX_INT(d)      PGS_NEWVAL_PMIN_INT(d)
+#define PGS_NEWVAL_PMAX_LONG(d)     PGS_NEWVAL_PMIN_LONG(d)
+#define PGS_NEWVAL_PMAX_FLOAT(d)    PGS_NEWVAL_PMIN_FLOAT(d)
+#define PGS_NEWVAL_PMAX_DOUBLE(d)   PGS_NEWVAL_PMIN_DOUBLE(d)
+
+/* ---- merge one cell-domain value into a cell: plain (registers / one
+ * owner) and atomic (shared or global table) flavours.  They take the value
+ * already in cell domain so that the same code merges rows and states. ---- */
+#define PGS_MERGE_PLAIN_SUM_I64(p,c,v)  (p)[c] += (v);
+#define PGS_MERGE_PLAIN_SUM_F64(p,c,v)                                  \
+    (p)[c] = (cl_ulong)__double_as_longlong(                            \
+        __longlong_as_double((cl_long)(p)[c]) +                         \
+        __longlong_as_double((cl_long)(v)));
+#define PGS_MERGE_PLAIN_MIN_I64(p,c,v)                                  \
+    if ((cl_long)(v) < (cl_long)(p)[c]) (p)[c] = (v);
+#define PGS_MERGE_PLAIN_MAX_I64(p,c,v)                                  \
+    if ((cl_long)(v) > (cl_long)(p)[c]) (p)[c] = (v);
+#define PGS_MERGE_PLAIN_MIN_U64(p,c,v)                                  \
+    if ((v) < (p)[c]) (p)[c] = (v);
+#define PGS_MERGE_PLAIN_MAX_U64(p,c,v)                                  \
+    if ((v) > (p)[c]) (p)[c] = (v);
+
+#define PGS_MERGE_ATOMIC_SUM_I64(p,c,v)                                 \
+    atomicAdd((unsigned long long *)&(p)[c], (unsigned long long)(v));
+#define PGS_MERGE_ATOMIC_SUM_F64(p,c,v)                                 \
+    atomicAdd((double *)&(p)[c], __longlong_as_double((cl_long)(v)));
+#define PGS_MERGE_ATOMIC_MIN_I64(p,c,v)                                 \
+    if ((cl_long)(v) < *((volatile cl_long *)&(p)[c]))                  \
+        atomicMin((long long *)&(p)[c], (long long)(v));
+#define PGS_MERGE_ATOMIC_MAX_I64(p,c,v)                                 \
+    if ((cl_long)(v) > *((volatile cl_long *)&(p)[c]))                  \
+        atomicMax((long long *)&(p)[c], (long long)(v));
+#define PGS_MERGE_ATOMIC_MIN_U64(p,c,v)                                 \
+    if ((v) < *((volatile cl_ulong *)&(p)[c]))                          \
+        atomicMin((unsigned long long *)&(p)[c], (unsigned long long)(v));
+#define PGS_MERGE_ATOMIC_MAX_U64(p,c,v)                                 \
+    if ((v) > *((volatile cl_ulong *)&(p)[c]))                          \
+        atomicMax((unsigned long long *)&(p)[c], (unsigned long long)(v));
+
+/* 128-bit sums: (lo,hi) two's complement.  The carry out of `lo` is known
+ * from the value atomicAdd returns, and additions commute, so two 64-bit
+ * atomics give an exact 128-bit sum without a lock. */
+DEVFN void
+pgs_add128_PLAIN(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi)
+{
+    cl_ulong    old = *plo;
+
+    *plo = old + vlo;
+    *phi += vhi + (*plo < old ? 1 : 0);
+}
+DEVFN void
+pgs_add128_ATOMIC(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi)
+{
+    cl_ulong    old = atomicAdd((unsigned long long *)plo,
+                                (unsigned long long)vlo);
+    cl_ulong    inc = vhi + ((old + vlo) < old ? 1 : 0);
+
+    if (inc != 0)
+        atomicAdd((unsigned long long *)phi, (unsigned long long)inc);
+}
+
+/* row -> state (MODE = PLAIN | ATOMIC); `d` is a pagg_datum */
+#define PGS_AGGCALC_PSUM_INT(MODE,p,c,d)    PGS_MERGE_##MODE##_SUM_I64(p,c,PGS_NEWVAL_PSUM_INT(d))
+#define PGS_AGGCALC_PSUM_LONGS(MODE,p,c,d)  PGS_MERGE_##MODE##_SUM_I64(p,c,PGS_NEWVAL_PSUM_LONGS(d))
+#define PGS_AGGCALC_PSUM_LONG(MODE,p,c,d)                               \
+    pgs_add128_##MODE(&(p)[c], &(p)[(c)+1], (cl_ulong)(d).long_val,     \
+                      (d).long_val < 0 ? ~0ULL : 0ULL);
+#define PGS_AGGCALC_PSUM_FLOAT(MODE,p,c,d)  PGS_MERGE_##MODE##_SUM_F64(p,c,PGS_NEWVAL_PSUM_FLOAT(d))
+#define PGS_AGGCALC_PSUM_DOUBLE(MODE,p,c,d) PGS_MERGE_##MODE##_SUM_F64(p,c,PGS_NEWVAL_PSUM_DOUBLE(d))
+#define PGS_AGGCALC_PMIN_SHORT(MODE,p,c,d)  PGS_MERGE_##MODE##_MIN_I64(p,c,PGS_NEWVAL_PMIN_SHORT(d))
+#define PGS_AGGCALC_PMIN_INT(MODE,p,c,d)    PGS_MERGE_##MODE##_MIN_I64(p,c,PGS_NEWVAL_PMIN_INT(d))
+#define PGS_AGGCALC_PMIN_LONG(MODE,p,c,d)   PGS_MERGE_##MODE##_MIN_I64(p,c,PGS_NEWVAL_PMIN_LONG(d))
+#define PGS_AGGCALC_PMIN_FLOAT(MODE,p,c,d)  PGS_MERGE_##MODE##_MIN_U64(p,c,PGS_NEWVAL_PMIN_FLOAT(d))
+#define PGS_AGGCALC_PMIN_DOUBLE(MODE,p,c,d) PGS_MERGE_##MODE##_MIN_U64(p,c,PGS_NEWVAL_PMIN_DOUBLE(d))
+#define PGS_AGGCALC_PMAX_SHORT(MODE,p,c,d)  PGS_MERGE_##MODE##_MAX_I64(p,c,PGS_NEWVAL_PMAX_SHORT(d))
+#define PGS_AGGCALC_PMAX_INT(MODE,p,c,d)    PGS_MERGE_##MODE##_MAX_I64(p,c,PGS_NEWVAL_PMAX_INT(d))
+#define PGS_AGGCALC_PMAX_LONG(MODE,p,c,d)   PGS_MERGE_##MODE##_MAX_I64(p,c,PGS_NEWVAL_PMAX_LONG(d))
+#define PGS_AGGCALC_PMAX_FLOAT(MODE,p,c,d)  PGS_MERGE_##MODE##_MAX_U64(p,c,PGS_NEWVAL_PMAX_FLOAT(d))
+#define PGS_AGGCALC_PMAX_DOUBLE(MODE,p,c,d) PGS_MERGE_##MODE##_MAX_U64(p,c,PGS_NEWVAL_PMAX_DOUBLE(d))
+
+/* state -> state (q = source cells) */
+#define PGS_AGGMERGE_PSUM_INT(MODE,p,c,q)    PGS_MERGE_##MODE##_SUM_I64(p,c,(q)[c])
+#define PGS_AGGMERGE_PSUM_LONGS(MODE,p,c,q)  PGS_MERGE_##MODE##_SUM_I64(p,c,(q)[c])
+#define PGS_AGGMERGE_PSUM_LONG(MODE,p,c,q)   pgs_add128_##MODE(&(p)[c], &(p)[(c)+1], (q)[c], (q)[(c)+1]);
+#define PGS_AGGMERGE_PSUM_FLOAT(MODE,p,c,q)  PGS_MERGE_##MODE##_SUM_F64(p,c,(q)[c])
+#define PGS_AGGMERGE_PSUM_DOUBLE(MODE,p,c,q) PGS_MERGE_##MODE##_SUM_F64(p,c,(q)[c])
+#define PGS_AGGMERGE_PMIN_SHORT(MODE,p,c,q)  PGS_MERGE_##MODE##_MIN_I64(p,c,(q)[c])
+#define PGS_AGGMERGE_PMIN_INT(MODE,p,c,q)    PGS_MERGE_##MODE##_MIN_I64(p,c,(q)[c])
+#define PGS_AGGMERGE_PMIN_LONG(MODE,p,c,q)   PGS_MERGE_##MODE##_MIN_I64(p,c,(q)[c])
+#define PGS_AGGMERGE_PMIN_FLOAT(MODE,p,c,q)  PGS_MERGE_##MODE##_MIN_U64(p,c,(q)[c])
+#define PGS_AGGMERGE_PMIN_DOUBLE(MODE,p,c,q) PGS_MERGE_##MODE##_MIN_U64(p,c,(q)[c])
+#define PGS_AGGMERGE_PMAX_SHORT(MODE,p,c,q)  PGS_MERGE_##MODE##_MAX_I64(p,c,(q)[c])
+#define PGS_AGGMERGE_PMAX_INT(MODE,p,c,q)    PGS_MERGE_##MODE##_MAX_I64(p,c,(q)[c])
+#define PGS_AGGMERGE_PMAX_LONG(MODE,p,c,q)   PGS_MERGE_##MODE##_MAX_I64(p,c,(q)[c])
+#define PGS_AGGMERGE_PMAX_FLOAT(MODE,p,c,q)  PGS_MERGE_##MODE##_MAX_U64(p,c,(q)[c])
+#define PGS_AGGMERGE_PMAX_DOUBLE(MODE,p,c,q) PGS_MERGE_##MODE##_MAX_U64(p,c,(q)[c])
+
+/* per-row admission check: rows whose float inputs could overflow a sum in
+ * some summation order are left to the CPU (row level) */
+#define PGS_AGGCHECK_PSUM_INT(d)
+#define PGS_AGGCHECK_PSUM_LONGS(d)
+#define PGS_AGGCHECK_PSUM_LONG(d)
+#define PGS_AGGCHECK_PSUM_FLOAT(d)                                      \
+    if (fabsf((d).float_val) > (float)PGS_PSUM_FLOAT_LIMIT)             \
+        STROM_SET_ERROR(errcode, StromError_CpuReCheck);
+#define PGS_AGGCHECK_PSUM_DOUBLE(d)                                     \
+    if (fabs((d).double_val) > PGS_PSUM_DOUBLE_LIMIT)                   \
+        STROM_SET_ERROR(errcode, StromError_CpuReCheck);
+#define PGS_AGGCHECK_PMIN_SHORT(d)
+#define PGS_AGGCHECK_PMIN_INT(d)
+#define PGS_AGGCHECK_PMIN_LONG(d)
+#define PGS_AGGCHECK_PMIN_FLOAT(d)
+#define PGS_AGGCHECK_PMIN_DOUBLE(d)
+#define PGS_AGGCHECK_PMAX_SHORT(d)
+#define PGS_AGGCHECK_PMAX_INT(d)
+#define PGS_AGGCHECK_PMAX_LONG(d)
+#define PGS_AGGCHECK_PMAX_FLOAT(d)
+#define PGS_AGGCHECK_PMAX_DOUBLE(d)
+
+/* X-macro adaptors over GPUPREAGG_AGG_LIST(_) = _(aggidx, cellidx, OP, TYPE) */
+#define PGS_X_INIT(i,c,OP,TYPE)         PGS_CELL_INIT_##OP##_##TYPE(c,cells)
+#define PGS_X_CHECK(i,c,OP,TYPE)                                        \
+    if (!row.agg[i].isnull) { PGS_AGGCHECK_##OP##_##TYPE(row.agg[i]) }
+#define PGS_X_CALC_PLAIN(i,c,OP,TYPE)                                   \
+    if (!row.agg[i].isnull) {                                           \
+        PGS_AGGCALC_##OP##_##TYPE(PLAIN,cells,c,row.agg[i])             \
+        nnmask |= (1U << (i));                                          \
+    }
+#define PGS_X_CALC_ATOMIC(i,c,OP,TYPE)                                  \
+    if (!row.agg[i].isnull) {                                           \
+        PGS_AGGCALC_##OP##_##TYPE(ATOMIC,cells,c,row.agg[i])            \
+        nnmask |= (1U << (i));                                          \
+    }
+#define PGS_X_MERGE_PLAIN(i,c,OP,TYPE)                                  \
+    if (src_nn & (1U << (i))) { PGS_AGGMERGE_##OP##_##TYPE(PLAIN,cells,c,src) }
+#define PGS_X_MERGE_ATOMIC(i,c,OP,TYPE)                                 \
+    if (src_nn & (1U << (i))) { PGS_AGGMERGE_##OP##_##TYPE(ATOMIC,cells,c,src) }
+
+template <typename CELLS>
+DEVFN void
+pgs_cells_init(CELLS cells)
+{
+    GPUPREAGG_AGG_LIST(PGS_X_INIT)
+}
+
+DEVFN void
+gpupreagg_aggcheck(cl_int *errcode, const pagg_row &row)
+{
+    GPUPREAGG_AGG_LIST(PGS_X_CHECK)
+}
+
+/* gpupreagg_aggcalc: merge one projected row into a state
+ * (the reference's generated switch(resno), gpupreagg.c:1319-1440) */
+template <typename CELLS>
+DEVFN cl_uint
+gpupreagg_aggcalc_plain(CELLS cells, const pagg_row &row)
+{
+    cl_uint nnmask = 0;
+    GPUPREAGG_AGG_LIST(PGS_X_CALC_PLAIN)
+    return nnmask;
+}
+template <typename CELLS>
+DEVFN cl_uint
+gpupreagg_aggcalc_atomic(CELLS cells, const pagg_row &row)
+{
+    cl_uint nnmask = 0;
+    GPUPREAGG_AGG_LIST(PGS_X_CALC_ATOMIC)
+    return nnmask;
+}
+template <typename CELLS, typename SRC>
+DEVFN void
+gpupreagg_aggmerge_plain(CELLS cells, SRC src, cl_uint src_nn)
+{
+    GPUPREAGG_AGG_LIST(PGS_X_MERGE_PLAIN)
+}
+template <typename CELLS, typename SRC>
+DEVFN void
+gpupreagg_aggmerge_atomic(CELLS cells, SRC src, cl_uint src_nn)
+{
+    GPUPREAGG_AGG_LIST(PGS_X_MERGE_ATOMIC)
+}
+
+/* ------------------------------------------------------------------
+ * device-resident session state (allocated by the CUDA layer)
+ * ------------------------------------------------------------------ */
+#define PGS_SLOT_EMPTY      0U
+#define PGS_SLOT_BUSY       1U
+#define PGS_SLOT_READY      2U
+
+/* a slot of the global (AoS) table:
+ *   ctrl_lo : PGS_SLOT_* in bits 0-1, key-is-NULL bits from bit 8
+ *   ctrl_hi : "saw non-NULL" bit per aggregate
+ *   key[NKEYS], cell[NCELLS]
+ */
+#define PGS_SLOT_WORDS  (1 + GPUPREAGG_NUM_KEYS + GPUPREAGG_NUM_CELLS)
+#define PGS_SLOT_BYTES  (8 * PGS_SLOT_WORDS)
+
+/* pgs_gstate / pgs_kern_desc: see kern_shared.h (shared with the host) */
+
+/* ------------------------------------------------------------------
+ * stage layout: [col0 values | col1 values | ... | col0 bitmap | ...]
+ * every piece 128-byte aligned
+ * ------------------------------------------------------------------ */
+#define PGS_ALIGN128(x)     (((x) + 127U) & ~127U)
+
+__host__ __device__ constexpr cl_uint
+pgs_stage_val_off(int slot)
+{
+    cl_uint off = 0;
+    for (int s = 0; s < slot; s++)
+        off += PGS_ALIGN128((cl_uint)GPUPREAGG_TILE_ROWS * GPUPREAGG_INCOL_ATTLEN(s));
+    return off;
+}
+__host__ __device__ constexpr cl_uint
+pgs_stage_nul_off(int slot)
+{
+    return pgs_stage_val_off(GPUPREAGG_NUM_INCOLS) +
+        (cl_uint)slot * PGS_ALIGN128(GPUPREAGG_TILE_ROWS / 8);
+}
+#define PGS_STAGE_BYTES     pgs_stage_nul_off(GPUPREAGG_NUM_INCOLS)
+/* head of dynamic smem: 2 x NUM_STAGES mbarriers, column positions */
+#define PGS_SMEM_HEAD_BYTES \
+    PGS_ALIGN128(16 * GPUPREAGG_NUM_STAGES + 8 * PGS_MAX(GPUPREAGG_NUM_INCOLS,1) + 64)
+
+/* ------------------------------------------------------------------
+ * mbarrier + bulk async copy (TMA engine, 1-D) wrappers
+ * ------------------------------------------------------------------ */
+DEVFN cl_uint
+pgs_smem_addr(const void *p)
+{
+    return (cl_uint)__cvta_generic_to_shared(p);
+}
+DEVFN void
+pgs_mbar_init(cl_ulong *bar, cl_uint count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
+                 :: "r"(pgs_smem_addr(bar)), "r"(count) : "memory");
+}
+DEVFN void
+pgs_mbar_arrive_expect_tx(cl_ulong *bar, cl_uint bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(pgs_smem_addr(bar)), "r"(bytes) : "memory");
+}
+DEVFN void
+pgs_mbar_arrive(cl_ulong *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+                 :: "r"(pgs_smem_addr(bar)) : "memory");
+}
+DEVFN void
+pgs_mbar_wait(cl_ulong *bar, cl_uint parity)
+{
+    cl_uint addr = pgs_smem_addr(bar);
+    cl_uint done;
+
+    do {
+        asm volatile("{\n\t"
+                     ".reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t"
+                     "}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+DEVFN void
+pgs_bulk_g2s(void *dst_smem, const void *src_gmem, cl_uint bytes, cl_ulong *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1], %2, [%3];"
+                 :: "r"(pgs_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes),
+                    "r"(pgs_smem_addr(bar)) : "memory");
+}
+
+/* ------------------------------------------------------------------
+ * hashing of the group key
+ * ------------------------------------------------------------------ */
+DEVFN cl_ulong
+pgs_mix64(cl_ulong x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+DEVFN cl_ulong
+pgs_hash_keys(const pagg_row &row, cl_uint &knull)
+{
+    cl_ulong    h = 0x9e3779b97f4a7c15ULL;
+
+    knull = 0;
+#pragma unroll
+    for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+    {
+        /* NULL keys form one group (gpupreagg.c:1234-1243) */
+        cl_ulong v = row.key[k].isnull ? 0 : row.key[k].ulong_val;
+        if (row.key[k].isnull)
+            knull |= (1U << k);
+        h = pgs_mix64(h ^ v) + (cl_ulong)k;
+    }
+    return pgs_mix64(h ^ knull);
+}
+
+/* key normalisation: float keys must compare like PostgreSQL's btree
+ * operators (-0 = +0, NaN = NaN), so they are canonicalised at projection
+ * time by codegen (pgs_f8_canon); other keys compare bitwise. */
+DEVFN double
+pgs_f8_canon(double v)
+{
+    if (isnan(v))
+        return __longlong_as_double(0x7FF8000000000000LL);
+    return (v == 0.0) ? 0.0 : v;
+}
+
+/* ------------------------------------------------------------------
+ * CTA-local table (shared memory, SoA):
+ *   ctrl_lo[n] (u32) | ctrl_hi[n] (u32) | key[NKEYS][n] (u64) | cell[NCELLS][n]
+ * ------------------------------------------------------------------ */
+#define PGS_SH_SLOT_BYTES   (8 + 8 * GPUPREAGG_NUM_KEYS + 8 * GPUPREAGG_NUM_CELLS)
+
+struct pgs_sh_table
+{
+    cl_uint     base;       /* offset in __pgs_smem */
+    cl_uint     nslots;     /* power of two, 0 = disabled */
+
+    __device__ __forceinline__ cl_uint *ctrl_lo(cl_uint s) const
+    { return (cl_uint *)(__pgs_smem + base) + s; }
+    __device__ __forceinline__ cl_uint *ctrl_hi(cl_uint s) const
+    { return (cl_uint *)(__pgs_smem + base + 4 * nslots) + s; }
+    __device__ __forceinline__ cl_ulong *key(int k, cl_uint s) const
+    { return (cl_ulong *)(__pgs_smem + base + 8 * nslots) + (cl_ulong)k * nslots + s; }
+    __device__ __forceinline__ cl_ulong *cell(int c, cl_uint s) const
+    { return (cl_ulong *)(__pgs_smem + base + 8 * nslots * (1 + GPUPREAGG_NUM_KEYS))
+            + (cl_ulong)c * nslots + s; }
+};
+
+/* strided view of a slot's cells so that the AGG macros can index p[c] */
+struct pgs_sh_cells
+{
+    cl_ulong   *p0;
+    cl_uint     stride;
+    __device__ __forceinline__ cl_ulong &operator[](int c) const
+    { return p0[(cl_ulong)c * stride]; }
+};
+
+/* ------------------------------------------------------------------
+ * find-or-insert in the global table.  Returns the slot's word pointer or
+ * NULL when the probe limit is hit (table full => StromError_DataStoreNoSpace)
+ * ------------------------------------------------------------------ */
+DEVFN cl_ulong *
+pgs_gh_find_slot(const pgs_gstate &gs, const cl_ulong *keyvals,
+                 cl_uint knull, cl_ulong hash)
+{
+    cl_uint     mask = gs.gh_nslots - 1;
+    cl_uint     h = (cl_uint)hash & mask;
+
+    for (cl_uint probe = 0; probe < gs.gh_max_probe; )
+    {
+        cl_ulong   *slot = gs.gh_slots + (cl_ulong)h * PGS_SLOT_WORDS;
+        cl_uint     st = *((volatile cl_uint *)slot);
+
+        if ((st & 3U) == PGS_SLOT_READY)
+        {
+            bool    same = ((st >> 8) == knull);
+#pragma unroll
+            for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+                same = same && (__ldcg(slot + 1 + k) == keyvals[k]);
+            if (same)
+                return slot;
+            h = (h + 1) & mask;
+            probe++;
+        }
+        else if ((st & 3U) == PGS_SLOT_EMPTY)
+        {
+            cl_uint old = atomicCAS((cl_uint *)slot, PGS_SLOT_EMPTY, PGS_SLOT_BUSY);
+            if (old == PGS_SLOT_EMPTY)
+            {
+#pragma unroll
+                for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+                    slot[1 + k] = keyvals[k];
+                __threadfence();
+                atomicExch((cl_uint *)slot, PGS_SLOT_READY | (knull << 8));
+                atomicAdd(gs.gh_ngroups, 1U);
+                return slot;
+            }
+            /* lost the race: look at the same slot again */
+        }
+        /* BUSY: the owner publishes shortly; re-read the same slot */
+    }
+    return NULL;
+}
+
+/* merge a state (cells + nn bits) into the global table */
+DEVFN bool
+pgs_gh_merge_state(const pgs_gstate &gs, const cl_ulong *keyvals, cl_uint knull,
+                   cl_ulong hash, const cl_ulong *src, cl_uint src_nn)
+{
+    cl_ulong   *slot = pgs_gh_find_slot(gs, keyvals, knull, hash);
+    cl_ulong   *cells;
+    cl_uint    *p_nn;
+
+    if (!slot)
+        return false;
+    cells = slot + 1 + GPUPREAGG_NUM_KEYS;
+    gpupreagg_aggmerge_atomic(cells, src, src_nn);
+    p_nn = (cl_uint *)slot + 1;
+    if ((*((volatile cl_uint *)p_nn) & src_nn) != src_nn)
+        atomicOr(p_nn, src_nn);
+    return true;
+}
+
+DEVFN bool
+pgs_gh_add_row(const pgs_gstate &gs, const pagg_row &row, cl_uint knull,
+               cl_ulong hash)
+{
+    cl_ulong    keyvals[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
+    cl_ulong   *slot;
+    cl_ulong   *cells;
+    cl_uint    *p_nn;
+    cl_uint     nn;
+
+#pragma unroll
+    for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+        keyvals[k] = row.key[k].isnull ? 0 : row.key[k].ulong_val;
+    slot = pgs_gh_find_slot(gs, keyvals, knull, hash);
+    if (!slot)
+        return false;
+    cells = slot + 1 + GPUPREAGG_NUM_KEYS;
+    nn = gpupreagg_aggcalc_atomic(cells, row);
+    p_nn = (cl_uint *)slot + 1;
+    if ((*((volatile cl_uint *)p_nn) & nn) != nn)
+        atomicOr(p_nn, nn);
+    return true;
+}
+
+/* find-or-insert in the CTA-local table; returns slot index or ~0U if the
+ * table is (nearly) full and the row has to go to the global table */
+DEVFN cl_uint
+pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
+                 const pagg_row &row, cl_uint knull, cl_ulong hash)
+{
+    cl_uint     mask = sh.nslots - 1;
+    cl_uint     h = (cl_uint)(hash >> 32) & mask;
+    cl_uint     limit = sh.nslots - (sh.nslots >> 2);   /* 75% */
+
+    for (cl_uint probe = 0; probe < 64; )
+    {
+        cl_uint st = *((volatile cl_uint *)sh.ctrl_lo(h));
+
+        if ((st & 3U) == PGS_SLOT_READY)
+        {
+            bool    same = ((st >> 8) == knull);
+#pragma unroll
+            for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+                same = same && (*((volatile cl_ulong *)sh.key(k, h)) ==
+                                (row.key[k].isnull ? 0 : row.key[k].ulong_val));
+            if (same)
+                return h;
+            h = (h + 1) & mask;
+            probe++;
+        }
+        else if ((st & 3U) == PGS_SLOT_EMPTY)
+        {
+            if (*((volatile cl_uint *)sh_nused) >= limit)
+                return ~0U;
+            if (atomicCAS(sh.ctrl_lo(h), PGS_SLOT_EMPTY, PGS_SLOT_BUSY) == PGS_SLOT_EMPTY)
+            {
+                atomicAdd(sh_nused, 1U);
+#pragma unroll
+                for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+                    *sh.key(k, h) = (row.key[k].isnull ? 0 : row.key[k].ulong_val);
+                __threadfence_block();
+                atomicExch(sh.ctrl_lo(h), PGS_SLOT_READY | (knull << 8));
+                return h;
+            }
+        }
+    }
+    return ~0U;
+}
+
+/* ------------------------------------------------------------------
+ * per-row body shared by the staged and the gather path
+ * ------------------------------------------------------------------ */
+struct pgs_row_ctx
+{
+    cl_uint     nfiltered;
+    cl_uint     nrecheck;
+    cl_int      errcode;        /* first significant error seen */
+};
+
+template <typename KDS>
+DEVFN bool
+pgs_eval_row(const kern_parambuf *kparams, const KDS &kds, const void *ktoast,
+             cl_uint row, cl_uint *recheck_map, pgs_row_ctx &ctx, pagg_row &prow)
+{
+    cl_int      errcode = StromError_Success;
+    bool        valid;
+
+    valid = gpupreagg_qual_eval(&errcode, kparams, kds, ktoast, row);
+    if (valid)
+    {
+        gpupreagg_projection(&errcode, kparams, kds, prow, ktoast, row, 0);
+        gpupreagg_aggcheck(&errcode, prow);
+    }
+    if (errcode != StromError_Success)
+    {
+        if (errcode == StromError_CpuReCheck)
+        {
+            atomicOr(&recheck_map[row >> 5], 1U << (row & 31));
+            ctx.nrecheck++;
+        }
+        else if (ctx.errcode == StromError_Success)
+            ctx.errcode = errcode;
+        return false;
+    }
+    if (!valid)
+        ctx.nfiltered++;
+    return valid;
+}
+
+/* ------------------------------------------------------------------
+ * block-level epilogue helpers
+ * ------------------------------------------------------------------ */
+DEVFN cl_uint
+pgs_warp_sum(cl_uint v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        v += __shfl_xor_sync(0xffffffffU, v, d);
+    return v;
+}
+
+DEVFN void
+pgs_writeback_status(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
+                     const pgs_row_ctx &ctx)
+{
+    /* first significant error wins, else CpuReCheck
+     * (kern_writeback_error_status, opencl_common.h:1481-1527) */
+    cl_uint     nf = pgs_warp_sum(ctx.nfiltered);
+    cl_uint     nr = pgs_warp_sum(ctx.nrecheck);
+    cl_int      ec = ctx.errcode;
+
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        cl_int o = __shfl_xor_sync(0xffffffffU, ec, d);
+        if (ec == StromError_Success)
+            ec = o;
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (nf)
+            atomicAdd((unsigned long long *)gs.nrows_filtered, (unsigned long long)nf);
+        if (ec != StromError_Success)
+        {
+            cl_int cur = atomicCAS(&kgpreagg->status, StromError_Success, ec);
+            if (cur == StromError_CpuReCheck)
+                atomicCAS(&kgpreagg->status, StromError_CpuReCheck, ec);
+        }
+        else if (nr)
+            atomicCAS(&kgpreagg->status, StromError_Success, StromError_CpuReCheck);
+    }
+}
+
+
+DEVFN cl_ulong
+pgs_hash_keyvals(const cl_ulong *keyvals, cl_uint knull)
+{
+    cl_ulong    h = 0x9e3779b97f4a7c15ULL;
+
+#pragma unroll
+    for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+        h = pgs_mix64(h ^ keyvals[k]) + (cl_ulong)k;
+    return pgs_mix64(h ^ knull);
+}
+
+/* ------------------------------------------------------------------
+ * the main kernel
+ * ------------------------------------------------------------------ */
+struct pgs_smem_head
+{
+    cl_ulong    full_bar[GPUPREAGG_NUM_STAGES];
+    cl_ulong    empty_bar[GPUPREAGG_NUM_STAGES];
+    cl_uint     val_pos[PGS_MAX(GPUPREAGG_NUM_INCOLS, 1)];  /* kern_colpos copy */
+    cl_uint     nul_pos[PGS_MAX(GPUPREAGG_NUM_INCOLS, 1)];
+    cl_uint     sh_nused;
+    cl_uint     is_last_cta;
+};
+
+#define PGS_X_INCOL_LOADPOS(slot,colidx,attlen)                         \
+    head->val_pos[slot] = KERN_DATA_STORE_COLPOS(kds_in, colidx)->values_offset; \
+    head->nul_pos[slot] = KERN_DATA_STORE_COLPOS(kds_in, colidx)->nullmap_offset;
+
+#define PGS_X_INCOL_ISSUE(slot,colidx,attlen)                           \
+    {                                                                   \
+        cl_uint nb = ((rows * (attlen)) + 15U) & ~15U;                  \
+        pgs_bulk_g2s(stage_base + pgs_stage_val_off(slot),              \
+                     (const char *)kds_in + head->val_pos[slot] +       \
+                     (cl_ulong)row0 * (attlen), nb, &head->full_bar[stage]); \
+        if (head->nul_pos[slot] != 0)                                   \
+        {                                                               \
+            cl_uint mb = (((rows + 7U) >> 3) + 15U) & ~15U;             \
+            pgs_bulk_g2s(stage_base + pgs_stage_nul_off(slot),          \
+                         (const char *)kds_in + head->nul_pos[slot] +   \
+                         (row0 >> 3), mb, &head->full_bar[stage]);      \
+        }                                                               \
+    }
+
+#define PGS_X_INCOL_TXBYTES(slot,colidx,attlen)                         \
+    txbytes += ((rows * (attlen)) + 15U) & ~15U;                        \
+    if (head->nul_pos[slot] != 0)                                       \
+        txbytes += (((rows + 7U) >> 3) + 15U) & ~15U;
+
+#define PGS_X_INCOL_VIEW(slot,colidx,attlen)                            \
+    tile.val_off[slot] = stage_off + pgs_stage_val_off(slot);           \
+    tile.nul_off[slot] = (head->nul_pos[slot] != 0                      \
+                          ? stage_off + pgs_stage_nul_off(slot)         \
+                          : KERN_TILE_NO_NULLMAP);
+
+#define PGS_X_INCOL_GVIEW(slot,colidx,attlen)                           \
+    gtile.val_ptr[slot] = (const char *)kds_in +                        \
+        KERN_DATA_STORE_COLPOS(kds_in, colidx)->values_offset;          \
+    gtile.nul_ptr[slot] =                                               \
+        (KERN_DATA_STORE_COLPOS(kds_in, colidx)->nullmap_offset != 0    \
+         ? (const cl_uint *)((const char *)kds_in +                     \
+               KERN_DATA_STORE_COLPOS(kds_in, colidx)->nullmap_offset)  \
+         : (const cl_uint *)NULL);
+
+/* add one projected row to the group state (CTA-local table first) */
+DEVFN void
+pgs_group_add_row(const pgs_gstate &gs, const pgs_sh_table &sh,
+                  cl_uint *sh_nused, const pagg_row &prow, pgs_row_ctx &ctx)
+{
+    cl_uint     knull;
+    cl_ulong    hash = pgs_hash_keys(prow, knull);
+    cl_uint     s = ~0U;
+
+    if (sh.nslots > 0)
+        s = pgs_sh_find_slot(sh, sh_nused, prow, knull, hash);
+    if (s != ~0U)
+    {
+        pgs_sh_cells cells;
+        cl_uint      nn;
+
+        cells.p0 = sh.cell(0, s);
+        cells.stride = sh.nslots;
+        nn = gpupreagg_aggcalc_atomic(cells, prow);
+        if ((*((volatile cl_uint *)sh.ctrl_hi(s)) & nn) != nn)
+            atomicOr(sh.ctrl_hi(s), nn);
+    }
+    else if (!pgs_gh_add_row(gs, prow, knull, hash))
+    {
+        if (ctx.errcode == StromError_Success)
+            ctx.errcode = StromError_DataStoreNoSpace;
+    }
+}
+
+/* epilogue of both main kernels.  `scratch` is shared memory nobody else
+ * uses any more, at least 8 * (1 + NCELLS) * nwarps bytes. */
+DEVFN void
+pgs_main_epilogue(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
+                  const pgs_sh_table &sh, cl_ulong *scratch,
+                  cl_uint *p_is_last, cl_ulong *acc, cl_uint acc_nn,
+                  pgs_row_ctx &ctx)
+{
+    const cl_uint   warp_id = threadIdx.x >> 5;
+    const cl_uint   lane_id = threadIdx.x & 31;
+    const cl_uint   nwarps = blockDim.x >> 5;
+    const int       W = 1 + GPUPREAGG_NUM_CELLS;
+
+    if (GPUPREAGG_NUM_KEYS == 0)
+    {
+        /* lanes: butterfly where the lower lane merges, so lane 0 ends up
+         * with the warp's state, always combined in the same order */
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+        {
+            cl_ulong    src[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+            cl_uint     src_nn = __shfl_xor_sync(0xffffffffU, acc_nn, d);
+#pragma unroll
+            for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                src[c] = __shfl_xor_sync(0xffffffffU, acc[c], d);
+            if ((lane_id & d) == 0)
+            {
+                gpupreagg_aggmerge_plain(acc, src, src_nn);
+                acc_nn |= src_nn;
+            }
+        }
+        __syncthreads();        /* every tile consumed: scratch is free */
+        if (lane_id == 0)
+        {
+            scratch[warp_id * W] = acc_nn;
+#pragma unroll
+            for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                scratch[warp_id * W + 1 + c] = acc[c];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            cl_ulong   *mine = gs.ng_partial + (cl_ulong)blockIdx.x * W;
+            cl_uint     ticket;
+
+            /* warps in index order */
+            for (cl_uint w = 1; w < nwarps; w++)
+            {
+                cl_uint src_nn = (cl_uint)scratch[w * W];
+                gpupreagg_aggmerge_plain(acc, scratch + w * W + 1, src_nn);
+                acc_nn |= src_nn;
+            }
+            mine[0] = acc_nn;
+#pragma unroll
+            for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                mine[1 + c] = acc[c];
+            __threadfence();
+            ticket = atomicAdd(gs.ng_ticket, 1U);
+            if (ticket == gridDim.x - 1)
+            {
+                /* last CTA: fold all CTA partials into the persistent state
+                 * row in CTA order => the result does not depend on timing */
+                cl_ulong   *state = gs.ng_state;
+                cl_uint     nn = (cl_uint)state[0];
+
+                __threadfence();
+                for (cl_uint b = 0; b < gridDim.x; b++)
+                {
+                    const cl_ulong *part = gs.ng_partial + (cl_ulong)b * W;
+                    cl_uint     src_nn = (cl_uint)__ldcg(part);
+                    cl_ulong    src[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+#pragma unroll
+                    for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                        src[c] = __ldcg(part + 1 + c);
+                    gpupreagg_aggmerge_plain(state + 1, src, src_nn);
+                    nn |= src_nn;
+                }
+                state[0] = nn;
+                *gs.ng_ticket = 0;
+            }
+        }
+    }
+    else if (sh.nslots > 0)
+    {
+        /* spill the CTA-local table into the global one */
+        __syncthreads();
+        for (cl_uint s = threadIdx.x; s < sh.nslots; s += blockDim.x)
+        {
+            cl_uint     st = *sh.ctrl_lo(s);
+            cl_ulong    keyvals[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
+            cl_ulong    src[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+            cl_uint     knull;
+
+            if ((st & 3U) != PGS_SLOT_READY)
+                continue;
+            knull = st >> 8;
+#pragma unroll
+            for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+                keyvals[k] = *sh.key(k, s);
+#pragma unroll
+            for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                src[c] = *sh.cell(c, s);
+            if (!pgs_gh_merge_state(gs, keyvals, knull,
+                                    pgs_hash_keyvals(keyvals, knull),
+                                    src, *sh.ctrl_hi(s)))
+            {
+                if (ctx.errcode == StromError_Success)
+                    ctx.errcode = StromError_DataStoreNoSpace;
+            }
+        }
+    }
+    pgs_writeback_status(kgpreagg, gs, ctx);
+}
+
+#define PGS_SH_TABLE_INIT()                                             \
+    if (sh.nslots > 0)                                                  \
+    {                                                                   \
+        for (cl_uint s = threadIdx.x; s < sh.nslots; s += blockDim.x)   \
+        {                                                               \
+            pgs_sh_cells cells;                                         \
+            *sh.ctrl_lo(s) = PGS_SLOT_EMPTY;                            \
+            *sh.ctrl_hi(s) = 0;                                         \
+            cells.p0 = sh.cell(0, s);                                   \
+            cells.stride = sh.nslots;                                   \
+            pgs_cells_init(cells);                                      \
+        }                                                               \
+    }
+
+/*
+ * gpupreagg_main - staged (TMA) path over a KDS_FORMAT_COLUMN chunk.
+ * grid = persistent CTAs (multiple of the SM count), block = 1 producer
+ * warp + GPUPREAGG_CONSUMER_WARPS consumer warps.
+ */
+extern "C" __global__ void
+__launch_bounds__(GPUPREAGG_BLOCK_THREADS)
+gpupreagg_main(kern_gpupreagg *kgpreagg,
+               const kern_data_store *kds_in,
+               pgs_gstate gs,
+               cl_uint *recheck_map,
+               cl_uint sh_nslots)
+{
+    pgs_smem_head  *head = (pgs_smem_head *)__pgs_smem;
+    unsigned char  *stages = __pgs_smem + PGS_SMEM_HEAD_BYTES;
+    const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF(kgpreagg);
+    const cl_uint   nrows = kds_in->nitems;
+    const cl_uint   ntiles = (nrows + GPUPREAGG_TILE_ROWS - 1) / GPUPREAGG_TILE_ROWS;
+    const cl_uint   warp_id = threadIdx.x >> 5;
+    const cl_uint   lane_id = threadIdx.x & 31;
+    cl_ulong        acc[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+    cl_uint         acc_nn = 0;
+    pgs_row_ctx     ctx;
+    pgs_sh_table    sh;
+
+    ctx.nfiltered = 0;
+    ctx.nrecheck = 0;
+    ctx.errcode = StromError_Success;
+    sh.base = PGS_SMEM_HEAD_BYTES + GPUPREAGG_NUM_STAGES * PGS_STAGE_BYTES;
+    sh.nslots = (GPUPREAGG_NUM_KEYS > 0 ? sh_nslots : 0);
+    pgs_cells_init(acc);
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < GPUPREAGG_NUM_STAGES; s++)
+        {
+            pgs_mbar_init(&head->full_bar[s], 1);
+            pgs_mbar_init(&head->empty_bar[s], GPUPREAGG_CONSUMER_WARPS);
+        }
+        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOADPOS)
+        head->sh_nused = 0;
+        head->is_last_cta = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    PGS_SH_TABLE_INIT()
+    __syncthreads();
+
+    if (warp_id == 0)
+    {
+        /* ===== producer warp: lane 0 feeds the ring ===== */
+        cl_uint it = 0;
+        for (cl_uint t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
+        {
+            if (lane_id == 0)
+            {
+                cl_uint stage = it % GPUPREAGG_NUM_STAGES;
+                cl_uint phase = (it / GPUPREAGG_NUM_STAGES) & 1;
+                cl_uint row0 = t * GPUPREAGG_TILE_ROWS;
+                cl_uint rows = min((cl_uint)GPUPREAGG_TILE_ROWS, nrows - row0);
+                unsigned char *stage_base = stages + stage * PGS_STAGE_BYTES;
+                cl_uint txbytes = 0;
+
+                pgs_mbar_wait(&head->empty_bar[stage], phase ^ 1);
+                GPUPREAGG_INCOL_LIST(PGS_X_INCOL_TXBYTES)
+                pgs_mbar_arrive_expect_tx(&head->full_bar[stage], txbytes);
+                GPUPREAGG_INCOL_LIST(PGS_X_INCOL_ISSUE)
+                (void)stage_base;
+            }
+            __syncwarp();
+        }
+    }
+    else
+    {
+        /* ===== consumer warps ===== */
+        const cl_uint   ctid = threadIdx.x - 32;
+        cl_uint         it = 0;
+
+        for (cl_uint t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
+        {
+            cl_uint stage = it % GPUPREAGG_NUM_STAGES;
+            cl_uint phase = (it / GPUPREAGG_NUM_STAGES) & 1;
+            cl_uint row0 = t * GPUPREAGG_TILE_ROWS;
+            cl_uint rows = min((cl_uint)GPUPREAGG_TILE_ROWS, nrows - row0);
+            cl_uint stage_off = PGS_SMEM_HEAD_BYTES + stage * PGS_STAGE_BYTES;
+            kern_tile_smem tile;
+
+            tile.row0 = row0;
+            GPUPREAGG_INCOL_LIST(PGS_X_INCOL_VIEW)
+            (void)stage_off;
+            pgs_mbar_wait(&head->full_bar[stage], phase);
+
+            for (cl_uint r = ctid; r < rows; r += GPUPREAGG_CONSUMER_THREADS)
+            {
+                pagg_row    prow;
+
+                if (!pgs_eval_row(kparams, tile, kds_in, row0 + r,
+                                  recheck_map, ctx, prow))
+                    continue;
+                if (GPUPREAGG_NUM_KEYS == 0)
+                    acc_nn |= gpupreagg_aggcalc_plain(acc, prow);
+                else
+                    pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx);
+            }
+            __syncwarp();
+            if (lane_id == 0)
+                pgs_mbar_arrive(&head->empty_bar[stage]);
+        }
+    }
+    pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
+                      &head->is_last_cta, acc, acc_nn, ctx);
+}
+
+/*
+ * gpupreagg_main_rowmap - gather path: the chunk comes with a kern_row_map
+ * (rows a bulk-load child found visible, gpuscan.c:1425-1427), so columns are
+ * read straight from HBM by row index.  Same per-row body and epilogue.
+ */
+extern "C" __global__ void
+__launch_bounds__(GPUPREAGG_BLOCK_THREADS)
+gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
+                      const kern_data_store *kds_in,
+                      pgs_gstate gs,
+                      cl_uint *recheck_map,
+                      cl_uint sh_nslots)
+{
+    pgs_smem_head  *head = (pgs_smem_head *)__pgs_smem;
+    unsigned char  *stages = __pgs_smem + PGS_SMEM_HEAD_BYTES;
+    const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF(kgpreagg);
+    const kern_row_map  *krowmap = KERN_GPUPREAGG_KROWMAP(kgpreagg);
+    const cl_uint   nrows = kds_in->nitems;
+    const cl_uint   nvalids = (krowmap->nvalids < 0
+                               ? nrows : (cl_uint)krowmap->nvalids);
+    cl_ulong        acc[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+    cl_uint         acc_nn = 0;
+    pgs_row_ctx     ctx;
+    pgs_sh_table    sh;
+    kern_tile_gmem  gtile;
+
+    ctx.nfiltered = 0;
+    ctx.nrecheck = 0;
+    ctx.errcode = StromError_Success;
+    sh.base = PGS_SMEM_HEAD_BYTES + GPUPREAGG_NUM_STAGES * PGS_STAGE_BYTES;
+    sh.nslots = (GPUPREAGG_NUM_KEYS > 0 ? sh_nslots : 0);
+    pgs_cells_init(acc);
+    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_GVIEW)
+    if (threadIdx.x == 0)
+    {
+        head->sh_nused = 0;
+        head->is_last_cta = 0;
+    }
+    PGS_SH_TABLE_INIT()
+    __syncthreads();
+
+    for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x;
+         i < nvalids;
+         i += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        cl_uint     row = (krowmap->nvalids < 0
+                           ? (cl_uint)i : (cl_uint)krowmap->rindex[i]);
+        pagg_row    prow;
+
+        if (row >= nrows)
+        {
+            if (ctx.errcode == StromError_Success)
+                ctx.errcode = StromError_DataStoreOutOfRange;
+            continue;
+        }
+        if (!pgs_eval_row(kparams, gtile, kds_in, row, recheck_map, ctx, prow))
+            continue;
+        if (GPUPREAGG_NUM_KEYS == 0)
+            acc_nn |= gpupreagg_aggcalc_plain(acc, prow);
+        else
+            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx);
+    }
+    pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
+                      &head->is_last_cta, acc, acc_nn, ctx);
+}
+
+/* ------------------------------------------------------------------
+ * gpupreagg_init_state - identity state everywhere
+ * ------------------------------------------------------------------ */
+extern "C" __global__ void
+gpupreagg_init_state(pgs_gstate gs)
+{
+    cl_ulong    i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x;
+
+    if (i == 0)
+    {
+        gs.ng_state[0] = 0;
+        pgs_cells_init(gs.ng_state + 1);
+        *gs.ng_ticket = 0;
+        *gs.gh_ngroups = 0;
+    }
+    for (; i < gs.gh_nslots; i += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        cl_ulong   *slot = gs.gh_slots + i * PGS_SLOT_WORDS;
+
+        slot[0] = 0;
+#pragma unroll
+        for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+            slot[1 + k] = 0;
+        pgs_cells_init(slot + 1 + GPUPREAGG_NUM_KEYS);
+    }
+}
+
+/* ------------------------------------------------------------------
+ * gpupreagg_flush - state -> TUPSLOT partial rows
+ *
+ * Datum encoding as pg_<type>_vstore (opencl_common.h:567-580): by-value
+ * types zero-extended into 8 bytes; isnull[] one char per column after the
+ * ncols Datums; row stride LONGALIGN(9 * ncols).
+ * A group whose count exceeds int4 or whose 128-bit sum exceeds int8 is
+ * written as several rows (the final aggregates add partial rows up).
+ * ------------------------------------------------------------------ */
+#define PGS_INT4_MAX    2147483647LL
+
+DEVFN cl_uint
+pgs_nsplit_i128(cl_ulong lo, cl_ulong hi)
+{
+    __int128    v = (__int128)(((unsigned __int128)hi << 64) | lo);
+    __int128    lim = (v >= 0 ? (__int128)LONG_MAX : -(__int128)LONG_MIN);
+    __int128    a = (v >= 0 ? v : -v);
+    __int128    n = (a + lim - 1) / lim;
+
+    if (n < 1)
+        n = 1;
+    return (n > 0x7fffffff ? 0x7fffffffU : (cl_uint)n);
+}
+DEVFN cl_long
+pgs_piece_i128(cl_ulong lo, cl_ulong hi, cl_uint r)
+{
+    __int128    v = (__int128)(((unsigned __int128)hi << 64) | lo);
+
+    if (v >= 0)
+    {
+        __int128 rest = v - (__int128)r * (__int128)LONG_MAX;
+        if (rest <= 0)
+            return 0;
+        return (rest > (__int128)LONG_MAX ? LONG_MAX : (cl_long)rest);
+    }
+    else
+    {
+        __int128 rest = v - (__int128)r * (__int128)LONG_MIN;
+        if (rest >= 0)
+            return 0;
+        return (rest < (__int128)LONG_MIN ? LONG_MIN : (cl_long)rest);
+    }
+}
+
+/* rows needed by one aggregate of one group */
+#define PGS_NSPLIT_PSUM_INT(c)                                          \
+    { cl_long v = (cl_long)cells[c];                                    \
+      cl_long n = (v + PGS_INT4_MAX - 1) / PGS_INT4_MAX;                \
+      if (n > (cl_long)nsplit) nsplit = (cl_uint)n; }
+#define PGS_NSPLIT_PSUM_LONG(c)                                         \
+    { cl_uint n = pgs_nsplit_i128(cells[c], cells[(c)+1]);              \
+      if (n > nsplit) nsplit = n; }
+#define PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PSUM_LONGS(c)    PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PSUM_FLOAT(c)    PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PSUM_DOUBLE(c)   PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMIN_SHORT(c)    PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMIN_INT(c)      PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMIN_LONG(c)     PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMIN_FLOAT(c)    PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMIN_DOUBLE(c)   PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMAX_SHORT(c)    PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMAX_INT(c)      PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMAX_LONG(c)     PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMAX_FLOAT(c)    PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMAX_DOUBLE(c)   PGS_NSPLIT_OTHER(c)
+#define PGS_X_NSPLIT(i,c,OP,TYPE)   PGS_NSPLIT_##OP##_##TYPE(c)
+
+/* Datum of aggregate cell(s) for split row r; sets `isnull` */
+#define PGS_OUT_PSUM_INT(i,c)                                           \
+    { cl_long v = (cl_long)cells[c] - (cl_long)r * PGS_INT4_MAX;        \
+      if (v < 0) v = 0;                                                 \
+      if (v > PGS_INT4_MAX) v = PGS_INT4_MAX;                           \
+      datum = (cl_ulong)(cl_uint)v; isnull = false; }
+#define PGS_OUT_PSUM_LONGS(i,c)                                         \
+    { isnull = !(nn & (1U << (i)));                                     \
+      datum = (r == 0 ? cells[c] : 0); }
+#define PGS_OUT_PSUM_LONG(i,c)                                          \
+    { isnull = !(nn & (1U << (i)));                                     \
+      datum = (cl_ulong)pgs_piece_i128(cells[c], cells[(c)+1], r); }
+#define PGS_OUT_PSUM_FLOAT(i,c)                                         \
+    { isnull = !(nn & (1U << (i)));                                     \
+      datum = (r == 0 ? (cl_ulong)__float_as_uint(                      \
+                   (float)__longlong_as_double((cl_long)cells[c])) : 0); }
+#define PGS_OUT_PSUM_DOUBLE(i,c)                                        \
+    { isnull = !(nn & (1U << (i)));                                     \
+      datum = (r == 0 ? cells[c] : 0); }
+#define PGS_OUT_MINMAX_SHORT(i,c)                                       \
+    { isnull = !(nn & (1U << (i)));                                     \
+      datum = (cl_ulong)(cl_ushort)(cl_short)(cl_long)cells[c]; }
+#define PGS_OUT_MINMAX_INT(i,c)                                         \
+    { isnull = !(nn & (1U << (i)));                                     \
+      datum = (cl_ulong)(cl_uint)(cl_int)(cl_long)cells[c]; }
+#define PGS_OUT_MINMAX_LONG(i,c)                                        \
+    { isnull = !(nn & (1U << (i)));                                     \
+      datum = cells[c]; }
+#define PGS_OUT_MINMAX_FLOAT(i,c)                                       \
+    { isnull = !(nn & (1U << (i)));                                     \
+      datum = (cl_ulong)__float_as_uint((float)pgs_f8_from_sortkey(cells[c])); }
+#define PGS_OUT_MINMAX_DOUBLE(i,c)                                      \
+    { isnull = !(nn & (1U << (i)));                                     \
+      datum = (cl_ulong)__double_as_longlong(pgs_f8_from_sortkey(cells[c])); }
+#define PGS_OUT_PMIN_SHORT(i,c)     PGS_OUT_MINMAX_SHORT(i,c)
+#define PGS_OUT_PMIN_INT(i,c)       PGS_OUT_MINMAX_INT(i,c)
+#define PGS_OUT_PMIN_LONG(i,c)      PGS_OUT_MINMAX_LONG(i,c)
+#define PGS_OUT_PMIN_FLOAT(i,c)     PGS_OUT_MINMAX_FLOAT(i,c)
+#define PGS_OUT_PMIN_DOUBLE(i,c)    PGS_OUT_MINMAX_DOUBLE(i,c)
+#define PGS_OUT_PMAX_SHORT(i,c)     PGS_OUT_MINMAX_SHORT(i,c)
+#define PGS_OUT_PMAX_INT(i,c)       PGS_OUT_MINMAX_INT(i,c)
+#define PGS_OUT_PMAX_LONG(i,c)      PGS_OUT_MINMAX_LONG(i,c)
+#define PGS_OUT_PMAX_FLOAT(i,c)     PGS_OUT_MINMAX_FLOAT(i,c)
+#define PGS_OUT_PMAX_DOUBLE(i,c)    PGS_OUT_MINMAX_DOUBLE(i,c)
+
+/* GPUPREAGG_OUT_LIST(_) = _(colidx, ROLE, idx, cellidx, OP, TYPE) with
+ * ROLE in {NUL, KEY, AGG} */
+#define PGS_OUTCOL_NUL(col,idx,c,OP,TYPE)                              \
+    values[col] = 0; isnulls[col] = 1;
+#define PGS_OUTCOL_KEY(col,idx,c,OP,TYPE)                               \
+    values[col] = ((knull >> (idx)) & 1U) ? 0 : keys[idx];              \
+    isnulls[col] = (cl_char)((knull >> (idx)) & 1U);
+#define PGS_OUTCOL_AGG(col,idx,c,OP,TYPE)                               \
+    { cl_ulong datum; bool isnull;                                      \
+      PGS_OUT_##OP##_##TYPE(idx,c)                                      \
+      values[col] = isnull ? 0 : datum;                                 \
+      isnulls[col] = (cl_char)(isnull ? 1 : 0); }
+#define PGS_X_OUTCOL(col,ROLE,idx,c,OP,TYPE)    PGS_OUTCOL_##ROLE(col,idx,c,OP,TYPE)
+
+DEVFN void
+pgs_flush_group(kern_data_store *kds_dst, kern_gpupreagg *kgpreagg,
+                const cl_ulong *keys, cl_uint knull,
+                const cl_ulong *cells, cl_uint nn)
+{
+    cl_uint     nsplit = 1;
+    cl_uint     base;
+
+    GPUPREAGG_AGG_LIST(PGS_X_NSPLIT)
+    base = atomicAdd(&kds_dst->nitems, nsplit);
+    if (base + nsplit > kds_dst->nrooms)
+    {
+        atomicCAS(&kgpreagg->status, StromError_Success,
+                  StromError_DataStoreNoSpace);
+        return;
+    }
+    for (cl_uint r = 0; r < nsplit; r++)
+    {
+        Datum      *values = KERN_DATA_STORE_VALUES(kds_dst, base + r);
+        cl_char    *isnulls = KERN_DATA_STORE_ISNULL(kds_dst, base + r);
+
+        GPUPREAGG_OUT_LIST(PGS_X_OUTCOL)
+    }
+}
+
+extern "C" __global__ void
+gpupreagg_flush(pgs_gstate gs, kern_data_store *kds_dst,
+                kern_gpupreagg *kgpreagg)
+{
+    if (GPUPREAGG_NUM_KEYS == 0)
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            pgs_flush_group(kds_dst, kgpreagg, (const cl_ulong *)NULL, 0,
+                            gs.ng_state + 1, (cl_uint)gs.ng_state[0]);
+        return;
+    }
+    for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x;
+         i < gs.gh_nslots;
+         i += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        const cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_WORDS;
+        cl_uint     st = (cl_uint)slot[0];
+
+        if ((st & 3U) != PGS_SLOT_READY)
+            continue;
+        pgs_flush_group(kds_dst, kgpreagg, slot + 1, st >> 8,
+                        slot + 1 + GPUPREAGG_NUM_KEYS,
+                        (cl_uint)(slot[0] >> 32));
+    }
+}
+
+/* ------------------------------------------------------------------
+ * export / import of raw states: the unit that crosses NVLink when the
+ * per-GPU states are merged (NCCL gather of these records, then import on
+ * the receiving GPU).  record = PGS_SLOT_WORDS words, same as a slot.
+ * ------------------------------------------------------------------ */
+extern "C" __global__ void
+gpupreagg_export(pgs_gstate gs, cl_ulong *records, cl_uint *nrecords,
+                 cl_uint max_records)
+{
+    if (GPUPREAGG_NUM_KEYS == 0)
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+        {
+            records[0] = (gs.ng_state[0] << 32) | PGS_SLOT_READY;
+            for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                records[1 + c] = gs.ng_state[1 + c];
+            *nrecords = 1;
+        }
+        return;
+    }
+    for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x;
+         i < gs.gh_nslots;
+         i += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        const cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_WORDS;
+
+        if (((cl_uint)slot[0] & 3U) == PGS_SLOT_READY)
+        {
+            cl_uint pos = atomicAdd(nrecords, 1U);
+            if (pos < max_records)
+            {
+                for (int w = 0; w < PGS_SLOT_WORDS; w++)
+                    records[(cl_ulong)pos * PGS_SLOT_WORDS + w] = slot[w];
+            }
+        }
+    }
+}
+
+extern "C" __global__ void
+gpupreagg_import(pgs_gstate gs, const cl_ulong *records, cl_uint nrecords,
+                 kern_gpupreagg *kgpreagg)
+{
+    if (GPUPREAGG_NUM_KEYS == 0)
+    {
+        /* one thread, records in rank order: deterministic */
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+        {
+            cl_uint nn = (cl_uint)gs.ng_state[0];
+            for (cl_uint i = 0; i < nrecords; i++)
+            {
+                const cl_ulong *rec = records + (cl_ulong)i * PGS_SLOT_WORDS;
+                cl_uint src_nn = (cl_uint)(rec[0] >> 32);
+                gpupreagg_aggmerge_plain(gs.ng_state + 1, rec + 1, src_nn);
+                nn |= src_nn;
+            }
+            gs.ng_state[0] = nn;
+        }
+        return;
+    }
+    for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x;
+         i < nrecords;
+         i += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        const cl_ulong *rec = records + i * PGS_SLOT_WORDS;
+        cl_uint     knull = (cl_uint)rec[0] >> 8;
+
+        if (!pgs_gh_merge_state(gs, rec + 1, knull,
+                                pgs_hash_keyvals(rec + 1, knull),
+                                rec + 1 + GPUPREAGG_NUM_KEYS,
+                                (cl_uint)(rec[0] >> 32)))
+            atomicCAS(&kgpreagg->status, StromError_Success,
+                      StromError_DataStoreNoSpace);
+    }
+}
+
+/* ------------------------------------------------------------------
+ * gpupreagg_describe - layout constants for the host
+ * ------------------------------------------------------------------ */
+#define PGS_X_INCOL_ROWBYTES(slot,colidx,attlen)    rb += (attlen);
+
+extern "C" __global__ void
+gpupreagg_describe(pgs_kern_desc *desc)
+{
+    cl_uint rb = 0;
+
+    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_ROWBYTES)
+    desc->num_incols = GPUPREAGG_NUM_INCOLS;
+    desc->num_keys = GPUPREAGG_NUM_KEYS;
+    desc->num_aggs = GPUPREAGG_NUM_AGGS;
+    desc->num_cells = GPUPREAGG_NUM_CELLS;
+    desc->num_outcols = GPUPREAGG_NUM_OUTCOLS;
+    desc->slot_bytes = PGS_SLOT_BYTES;
+    desc->tile_rows = GPUPREAGG_TILE_ROWS;
+    desc->num_stages = GPUPREAGG_NUM_STAGES;
+    desc->stage_bytes = PGS_STAGE_BYTES;
+    desc->static_smem_bytes = PGS_SMEM_HEAD_BYTES;
+    desc->block_threads = GPUPREAGG_BLOCK_THREADS;
+    desc->sh_slot_bytes = PGS_SH_SLOT_BYTES;
+    desc->row_bytes = rb;
+}
+
+#endif  /* KERN_GPUPREAGG_CUH */

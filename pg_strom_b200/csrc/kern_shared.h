@@ -1,0 +1,45 @@
+/*
+ * kern_shared.h - structures passed by value between the CUDA layer (host)
+ * and the generated device programs.  Included by both sides; plain C.
+ */
+#ifndef KERN_SHARED_H
+#define KERN_SHARED_H
+
+typedef struct
+{
+    /* no-group: the persistent state row + per-CTA partials of one launch */
+    cl_ulong   *ng_state;       /* [1 + NCELLS]: word0 = nn bits, then cells */
+    cl_ulong   *ng_partial;     /* [max_ctas][1 + NCELLS] */
+    cl_uint    *ng_ticket;      /* CTA completion counter of the launch */
+    /* group-by: global open-addressing table */
+    cl_ulong   *gh_slots;       /* [gh_nslots][PGS_SLOT_WORDS] */
+    cl_uint     gh_nslots;      /* power of 2 */
+    cl_uint     gh_max_probe;
+    cl_uint    *gh_ngroups;     /* number of READY slots */
+    /* bookkeeping */
+    cl_ulong   *nrows_scanned;  /* rows that passed visibility (row-map) */
+    cl_ulong   *nrows_filtered; /* rows removed by the device qual */
+} pgs_gstate;
+
+/* what the host needs to know about a built program; filled by the
+ * gpupreagg_describe kernel so that the device code is the only source of
+ * truth for the layouts */
+typedef struct
+{
+    cl_uint     num_incols;
+    cl_uint     num_keys;
+    cl_uint     num_aggs;
+    cl_uint     num_cells;
+    cl_uint     num_outcols;
+    cl_uint     slot_bytes;
+    cl_uint     tile_rows;
+    cl_uint     num_stages;
+    cl_uint     stage_bytes;        /* shared memory of one pipeline stage */
+    cl_uint     static_smem_bytes;  /* barriers etc. at the head of dynamic smem */
+    cl_uint     block_threads;
+    cl_uint     sh_slot_bytes;      /* bytes per slot of the CTA-local table */
+    cl_uint     row_bytes;          /* algorithmic bytes per row (attlen sum) */
+    cl_uint     reserved[3];
+} pgs_kern_desc;
+
+#endif  /* KERN_SHARED_H */

@@ -1,0 +1,417 @@
+"""Thin Python driver over the C ABI of the GpuPreAgg path.
+
+Everything that computes lives in libpgstrom_cuda.so (CUDA kernels built by
+NVRTC for sm_100a + the C++ host layer).  This module only marshals: plan
+JSON in, chunks in, partial rows out.  Names follow the reference
+(gpupreagg_begin / _exec / _end, pgstrom_data_store ...).
+"""
+import ctypes as C
+import json
+import struct
+
+import numpy as np
+
+from . import _capi
+from ._capi import kern_colmeta, kern_data_store, pgs_session_config, check
+
+# typname -> (attlen, attbyval, attalign, numpy dtype)
+PGTYPES = {
+    "bool": (1, 1, 1, np.int8), "int2": (2, 1, 2, np.int16), "int4": (4, 1, 4, np.int32),
+    "int8": (8, 1, 8, np.int64), "float4": (4, 1, 4, np.float32),
+    "float8": (8, 1, 8, np.float64), "date": (4, 1, 4, np.int32),
+    "time": (8, 1, 8, np.int64), "timestamp": (8, 1, 8, np.int64),
+    "numeric": (-1, 0, 4, None), "text": (-1, 0, 4, None), "bytea": (-1, 0, 4, None),
+    "bpchar": (-1, 0, 4, None),
+}
+
+
+def make_colmeta(coltypes):
+    arr = (kern_colmeta * len(coltypes))()
+    for i, t in enumerate(coltypes):
+        attlen, byval, align, _ = PGTYPES[t]
+        arr[i].attbyval = byval
+        arr[i].attalign = align
+        arr[i].attlen = attlen
+        arr[i].attnum = i + 1
+        arr[i].attcacheoff = -1
+    return arr
+
+
+def numeric_datum(text):
+    """PostgreSQL numeric varlena image of a decimal literal."""
+    lib = _capi.load()
+    buf = C.create_string_buffer(len(text) + 64)
+    n = lib.pgstrom_numeric_from_text(str(text).encode(), buf, len(buf))
+    if n == 0:
+        raise ValueError("bad numeric literal %r" % (text,))
+    return buf.raw[:n]
+
+
+class DataStore:
+    """A chunk (pgstrom_data_store) in pinned host memory, KDS_FORMAT_COLUMN.
+
+    columns: list, one entry per table column, of
+       None                      -> column not loaded (not referenced)
+       (values, nullmask|None)   -> numpy array (fixed-length types) or list
+                                    of bytes|None (varlena), optional bool
+                                    mask with True = NULL
+    """
+
+    def __init__(self, coltypes, columns, nrows=None):
+        lib = _capi.load()
+        self.lib = lib
+        self.coltypes = list(coltypes)
+        ncols = len(coltypes)
+        assert len(columns) == ncols
+        self.colmeta = make_colmeta(coltypes)
+        vals = (C.c_void_p * ncols)()
+        nuls = (C.c_void_p * ncols)()
+        keep = []
+        for c, col in enumerate(columns):
+            if col is None:
+                continue
+            v, m = col
+            attlen, _, _, dt = PGTYPES[coltypes[c]]
+            if attlen > 0:
+                a = np.ascontiguousarray(v, dtype=dt)
+                n = a.shape[0]
+                keep.append(a)
+                vals[c] = a.ctypes.data
+            else:
+                n = len(v)
+                ptrs = (C.c_void_p * n)()
+                bufs = []
+                for i, d in enumerate(v):
+                    if d is None:
+                        ptrs[i] = None
+                    else:
+                        b = C.create_string_buffer(bytes(d), len(d))
+                        bufs.append(b)
+                        ptrs[i] = C.addressof(b)
+                keep.append((ptrs, bufs))
+                vals[c] = C.addressof(ptrs)
+            if nrows is None:
+                nrows = n
+            assert n == nrows, "column %d has %d rows, expected %d" % (c, n, nrows)
+            if m is not None:
+                mm = np.ascontiguousarray(m, dtype=np.uint8)
+                assert mm.shape[0] == nrows
+                keep.append(mm)
+                nuls[c] = mm.ctypes.data
+        self.nrows = int(nrows or 0)
+        length = lib.pgstrom_kds_column_length(ncols, self.colmeta, self.nrows, vals, nuls)
+        self.length = int(length)
+        self.ptr = lib.pgs_chunk_alloc(self.length)
+        if not self.ptr:
+            raise MemoryError("pgs_chunk_alloc(%d)" % self.length)
+        check(lib.pgstrom_kds_column_build(self.ptr, self.length, ncols, self.colmeta,
+                                           self.nrows, vals, nuls))
+        del keep
+
+    def bytes(self):
+        return C.string_at(self.ptr, self.length)
+
+    def free(self):
+        if self.ptr:
+            self.lib.pgs_chunk_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def decode_datum(datum, isnull, typ):
+    """8-byte Datum of a TUPSLOT row -> python value (by-value types)."""
+    if isnull:
+        return None
+    if typ == "bool":
+        return bool(datum & 0xff)
+    if typ == "int2":
+        return struct.unpack("<h", struct.pack("<H", datum & 0xffff))[0]
+    if typ in ("int4", "date"):
+        return struct.unpack("<i", struct.pack("<I", datum & 0xffffffff))[0]
+    if typ in ("int8", "time", "timestamp"):
+        return struct.unpack("<q", struct.pack("<Q", datum))[0]
+    if typ == "float4":
+        return struct.unpack("<f", struct.pack("<I", datum & 0xffffffff))[0]
+    if typ == "float8":
+        return struct.unpack("<d", struct.pack("<Q", datum))[0]
+    if typ == "numeric":
+        # 64-bit device numeric -> Decimal via the text form numeric_in() takes
+        from decimal import Decimal
+        lib = _capi.load()
+        buf = C.create_string_buffer(128)
+        check(lib.pgstrom_fixup_kernel_numeric(datum, buf, len(buf)))
+        return Decimal(buf.value.decode())
+    raise NotImplementedError(typ)
+
+
+class Plan:
+    """Result of pgstrom_grafter_json() on a plan tree."""
+
+    def __init__(self, plan_tree, gucs=None):
+        lib = _capi.load()
+        self.lib = lib
+        for k, v in (gucs or {}).items():
+            check(lib.pgstrom_guc_set(k.encode(), str(v).encode()))
+        text = plan_tree if isinstance(plan_tree, str) else json.dumps(plan_tree)
+        self.handle = lib.pgstrom_grafter_json(text.encode())
+        if not self.handle:
+            raise RuntimeError("pgstrom_grafter_json: " + lib.pgs_last_error().decode())
+
+    @property
+    def num_gpupreagg(self):
+        return self.lib.pgs_plan_num_gpupreagg(self.handle)
+
+    @property
+    def reject_reason(self):
+        return self.lib.pgs_plan_reject_reason(self.handle).decode()
+
+    def explain(self, verbose=True):
+        return self.lib.pgs_plan_explain(self.handle, 1 if verbose else 0).decode().split("\n")
+
+    def tree(self):
+        return json.loads(self.lib.pgs_plan_tree_json(self.handle).decode())
+
+    def kernel_source(self, idx=0):
+        return self.lib.pgs_plan_kernel_source(self.handle, idx).decode()
+
+    def extra_flags(self, idx=0):
+        return self.lib.pgs_plan_extra_flags(self.handle, idx)
+
+    def describe(self, idx=0):
+        return json.loads(self.lib.pgs_plan_describe_json(self.handle, idx).decode())
+
+    def kparams(self, idx=0):
+        n = C.c_size_t()
+        p = self.lib.pgs_plan_kparams(self.handle, idx, C.byref(n))
+        return C.string_at(p, n.value)
+
+    def build_program(self, idx=0):
+        """NVRTC build (needs no GPU); returns the opaque program handle."""
+        prog = C.c_void_p()
+        log = C.c_char_p()
+        rc = self.lib.pgs_program_build(self.kernel_source(idx).encode(),
+                                        self.extra_flags(idx), C.byref(prog), C.byref(log))
+        if rc != 0:
+            raise _capi.StromError(rc, (log.value or b"").decode(errors="replace")[:4000])
+        return prog
+
+    def free(self):
+        if self.handle:
+            self.lib.pgs_plan_free(self.handle)
+            self.handle = None
+
+
+_cuda_ready = False
+
+
+def cuda_init(devices=None):
+    """pgs_cuda_init(); raises if there is no usable CUDA device."""
+    global _cuda_ready
+    lib = _capi.load()
+    if devices is None:
+        check(lib.pgs_cuda_init(None, 0))
+    else:
+        arr = (C.c_int * len(devices))(*devices)
+        check(lib.pgs_cuda_init(arr, len(devices)))
+    _cuda_ready = True
+    return lib.pgs_cuda_device_count()
+
+
+class GpuPreAggState:
+    """Executor half: gpupreagg_begin / gpupreagg_exec / gpupreagg_end over a
+    child that hands over chunks (bulk-load protocol)."""
+
+    def __init__(self, plan, chunks, idx=0, device=0):
+        lib = _capi.load()
+        self.lib = lib
+        self.plan = plan
+        self.desc = plan.describe(idx)
+        self.coltypes = [c["type"] for c in self.desc["columns"]]
+        self._chunks = iter(chunks)
+        self._held = []
+
+        def child_exec(_state, slot_p):
+            slot = slot_p.contents
+            try:
+                item = next(self._chunks)
+            except StopIteration:
+                slot.kds = None
+                return 0
+            if isinstance(item, tuple):
+                ds, rowmap = item
+            else:
+                ds, rowmap = item, None
+            self._held.append(ds)
+            slot.kds = ds.ptr
+            if rowmap is not None:
+                rm = np.concatenate([np.array([len(rowmap)], dtype=np.int32),
+                                     np.asarray(rowmap, dtype=np.int32)])
+                self._held.append(rm)
+                slot.krowmap = rm.ctypes.data
+            else:
+                slot.krowmap = None
+            return 0
+
+        self._cb = _capi.BULK_EXEC_FN(child_exec)
+        st = C.c_void_p()
+        check(lib.gpupreagg_begin(plan.handle, idx, device, self._cb, None, C.byref(st)))
+        self.state = st
+
+    def fetch_all(self):
+        """Runs ExecCustomPlan until it is exhausted; returns partial rows as
+        python tuples in GpuPreAgg target-list order."""
+        ncols = len(self.coltypes)
+        values = (C.c_uint64 * ncols)()
+        isnull = C.create_string_buffer(ncols)
+        rows = []
+        while True:
+            rc = self.lib.gpupreagg_exec(self.state, values, isnull)
+            if rc == 0:
+                break
+            if rc < 0:
+                raise _capi.StromError(-rc, self.lib.pgs_last_error().decode(errors="replace"))
+            rows.append(tuple(decode_datum(values[i], isnull.raw[i] != 0, self.coltypes[i])
+                              for i in range(ncols)))
+        return rows
+
+    def recheck_rows(self):
+        n = self.lib.gpupreagg_recheck_rows(self.state, None, None, 0)
+        if n <= 0:
+            return []
+        seq = (C.c_uint32 * n)()
+        rows = (C.c_uint32 * n)()
+        self.lib.gpupreagg_recheck_rows(self.state, seq, rows, n)
+        return [(int(seq[i]), int(rows[i])) for i in range(n)]
+
+    def explain(self, verbose=False, analyze=False):
+        return self.lib.gpupreagg_explain(self.state, int(verbose), int(analyze)).decode()
+
+    def rescan(self, chunks):
+        self._chunks = iter(chunks)
+        check(self.lib.gpupreagg_rescan(self.state))
+
+    def end(self):
+        notice = None
+        if self.state:
+            r = self.lib.gpupreagg_end(self.state)
+            notice = r.decode() if r else None
+            self.state = None
+        self._held = []
+        return notice
+
+
+class Session:
+    """Direct use of the session API (pgs_preagg_*) for benches: chunks may be
+    device resident."""
+
+    def __init__(self, plan, idx=0, device=0, num_groups=None, max_async_chunks=0,
+                 max_chunk_rows=0, max_chunk_bytes=0):
+        lib = _capi.load()
+        self.lib = lib
+        self.plan = plan
+        self.desc = plan.describe(idx)
+        self.coltypes = [c["type"] for c in self.desc["columns"]]
+        self.program = plan.build_program(idx)
+        self._kparams = C.create_string_buffer(plan.kparams(idx))
+        ncols = len(self.coltypes)
+        self.result_colmeta = (kern_colmeta * ncols)()
+        lib.pgs_plan_result_colmeta(plan.handle, idx, self.result_colmeta, ncols)
+        cfg = pgs_session_config()
+        cfg.device = device
+        cfg.needs_grouping = 1 if self.desc["needs_grouping"] else 0
+        cfg.num_groups = float(num_groups if num_groups is not None else self.desc["num_groups"])
+        cfg.max_async_chunks = max_async_chunks
+        cfg.max_chunk_rows = max_chunk_rows
+        cfg.max_chunk_bytes = max_chunk_bytes
+        cfg.result_ncols = ncols
+        cfg.result_colmeta = self.result_colmeta
+        self.device = device
+        sess = C.c_void_p()
+        check(lib.pgs_preagg_open(self.program, self._kparams, C.byref(cfg), C.byref(sess)))
+        self.handle = sess
+
+    def submit(self, ds, rowmap=None):
+        t = C.c_int64()
+        rm = None
+        if rowmap is not None:
+            rm = np.concatenate([np.array([len(rowmap)], dtype=np.int32),
+                                 np.asarray(rowmap, dtype=np.int32)])
+            self._rm = rm
+        check(self.lib.pgs_preagg_submit(self.handle, ds.ptr,
+                                         rm.ctypes.data if rm is not None else None,
+                                         C.byref(t)))
+        return t.value
+
+    def submit_device(self, dptr, length, nitems):
+        t = C.c_int64()
+        check(self.lib.pgs_preagg_submit_device(self.handle, dptr, length, nitems, None,
+                                                C.byref(t)))
+        return t.value
+
+    def wait(self, ticket, timeout_ms=-1):
+        st = C.c_int32()
+        rc = self.lib.pgs_preagg_wait(self.handle, ticket, timeout_ms, C.byref(st))
+        if rc == -1:
+            return None
+        check(rc)
+        return st.value
+
+    def recheck_rows(self, ticket):
+        n = self.lib.pgs_preagg_recheck_rows(self.handle, ticket, None, 0)
+        if n <= 0:
+            return []
+        rows = (C.c_uint32 * n)()
+        self.lib.pgs_preagg_recheck_rows(self.handle, ticket, rows, n)
+        return [int(r) for r in rows]
+
+    def finish(self, reset=True, nrooms=None):
+        """Partial rows of everything submitted so far."""
+        lib = self.lib
+        ncols = len(self.coltypes)
+        if nrooms is None:
+            nrooms = int(max(16, self.desc["num_groups"] * 1.25 + 64)) \
+                if self.desc["needs_grouping"] else 16
+        for _ in range(4):
+            length = lib.pgstrom_kds_tupslot_length(ncols, nrooms)
+            buf = C.create_string_buffer(length)
+            check(lib.pgstrom_kds_tupslot_init(buf, length, ncols, self.result_colmeta, nrooms))
+            needed = C.c_uint32()
+            status = C.c_int32()
+            rc = lib.pgs_preagg_finish(self.handle, buf, 1 if reset else 0,
+                                       C.byref(needed), C.byref(status))
+            if rc == 301 and needed.value > nrooms:
+                nrooms = needed.value + 16
+                continue
+            check(rc)
+            break
+        kds = C.cast(buf, C.POINTER(kern_data_store)).contents
+        values = (C.c_uint64 * ncols)()
+        isnull = C.create_string_buffer(ncols)
+        rows = []
+        for r in range(kds.nitems):
+            check(lib.pgstrom_fetch_data_store(buf, r, values, isnull))
+            rows.append(tuple(decode_datum(values[i], isnull.raw[i] != 0, self.coltypes[i])
+                              for i in range(ncols)))
+        return rows
+
+    def perfmon(self):
+        return json.loads(self.lib.pgs_preagg_perfmon_json(self.handle).decode())
+
+    def launch_count(self):
+        return int(self.lib.pgs_preagg_launch_count(self.handle))
+
+    def stream(self):
+        return self.lib.pgs_preagg_stream(self.handle)
+
+    def close(self):
+        if self.handle:
+            self.lib.pgs_preagg_close(self.handle)
+            self.handle = None
+        if self.program:
+            self.lib.pgs_program_release(self.program)
+            self.program = None
