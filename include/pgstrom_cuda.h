@@ -106,6 +106,11 @@ int         pgstrom_fetch_data_store(const kern_data_store *kds, uint32_t row,
 /* datastore.c:150-167 pgstrom_fixup_kernel_numeric(): 64-bit device numeric
  * -> decimal text "<sign><mantissa>e<exp>" for numeric_in() */
 int         pgstrom_fixup_kernel_numeric(Datum datum, char *buf, size_t buflen);
+/* PostgreSQL numeric varlena <-> decimal text (for numeric Consts and for
+ * harnesses without a PostgreSQL to make datums); return the length, 0 on
+ * error */
+size_t      pgstrom_numeric_from_text(const char *text, void *buf, size_t buflen);
+size_t      pgstrom_numeric_to_text(const void *varlena, char *buf, size_t buflen);
 
 /* ------------------------------------------------------------------ 4 --- */
 typedef struct pgs_program pgs_program;
@@ -190,6 +195,15 @@ int64_t     pgs_preagg_recheck_rows(pgs_session *session, pgs_ticket ticket,
 int         pgs_preagg_finish(pgs_session *session, kern_data_store *kds_dst,
                               int reset, uint32_t *nrows_needed,
                               int32_t *status);
+/* NCCL communicator for one-process-per-GPU deployments: rank 0 makes the
+ * id, the launcher (MPI, torch.distributed, PostgreSQL shared memory ...)
+ * hands its 128 bytes to every rank, each rank joins.  libnccl.so.2 is
+ * opened lazily; single-GPU use does not need it. */
+int         pgs_nccl_get_unique_id(void *unique_id_128);
+int         pgs_nccl_comm_init_rank(int device, int nranks,
+                                    const void *unique_id_128, int rank,
+                                    void **comm);
+void        pgs_nccl_comm_destroy(void *comm);
 /* multi-GPU: merge the states of all ranks into rank `root` over NCCL
  * (ncclReduce-like for no-group, gather + re-hash for GROUP BY).  Collective:
  * every rank of the communicator calls it.  comm is an ncclComm_t. */

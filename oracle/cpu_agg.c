@@ -1,0 +1,413 @@
+/*
+ * cpu_agg.c - CPU restatement of PostgreSQL's Agg-over-SeqScan for the bench
+ * queries (the "pg_strom.enabled = off" plan: HashAggregate / Aggregate over
+ * Seq Scan, /root/reference/expected/explain_agg.out first plan shape).
+ *
+ * TEST INFRASTRUCTURE (oracle) - built into oracle/_build/libcpu_agg.so; only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load it.  It is the checker and the reported CPU
+ * baseline, never the product path.
+ *
+ * What is restated (PostgreSQL core is not vendored in the reference tree):
+ * the executor's per-tuple loop - ExecQual on the scan qual, grouping hash
+ * lookup (TupleHashTable), then advance_aggregates calling each strict
+ * transition function only for non-NULL input:
+ *   count(*)            int8inc
+ *   count(x)            int8inc_any
+ *   sum(int4)           int4_sum   (int8 state)
+ *   avg(int4)           int4_avg_accum {count, sum}
+ *   avg(int8)           int8_avg_accum (numeric state; here a 128-bit sum,
+ *                       which is exact for the same inputs)
+ *   min/max             int4smaller/larger, float8smaller/larger
+ *   sum/avg(float8)     float8pl / float8_accum {N, sumX, sumX2}
+ *   variance(float8)    float8_accum {N, sumX, sumX2}
+ * It is "port" not "reference": the expression interpreter, tuple deforming
+ * from heap pages and fmgr call overhead of a real PostgreSQL are absent, so
+ * a real PostgreSQL backend is slower than this on the same core.
+ * The parallel variant cuts the rows into per-thread ranges, aggregates each
+ * with its own hash table and combines the states (what parallel aggregation
+ * of later PostgreSQL versions does; the reference-era 9.4 has none, so
+ * 1 thread is the faithful figure).
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+enum { AGG_COUNT_STAR = 0, AGG_COUNT, AGG_SUM_INT4, AGG_AVG_INT4, AGG_AVG_INT8,
+       AGG_MIN_INT4, AGG_MAX_INT4, AGG_SUM_FLOAT8, AGG_AVG_FLOAT8,
+       AGG_MIN_FLOAT8, AGG_MAX_FLOAT8, AGG_VAR_FLOAT8 };
+enum { COL_INT4 = 4, COL_INT8 = 8, COL_FLOAT8 = 108 };
+
+#define MAX_COLS    8
+#define MAX_AGGS    16
+
+typedef struct {
+    int32_t     ncols;
+    int32_t     coltype[MAX_COLS];
+    const void *values[MAX_COLS];
+    const uint8_t *nulls[MAX_COLS];     /* one byte per row, or NULL */
+    int64_t     nrows;
+} cpu_table;
+
+typedef struct {
+    int32_t     qual_col;       /* WHERE col < qual_const ; -1 = no qual */
+    int32_t     qual_const;
+    int32_t     key_col;        /* GROUP BY col ; -1 = none */
+    int32_t     naggs;
+    int32_t     agg_kind[MAX_AGGS];
+    int32_t     agg_col[MAX_AGGS];
+} cpu_query;
+
+/* transition state of one aggregate of one group */
+typedef struct {
+    int64_t     n;
+    int64_t     isum_lo;        /* 128-bit sum */
+    int64_t     isum_hi;
+    double      fsum;
+    double      fsum2;
+    int64_t     imin, imax;
+    double      fmin, fmax;
+    int32_t     has_value;
+    int32_t     pad;
+} agg_state;
+
+typedef struct {
+    int64_t     key;
+    int64_t     index;          /* group number + 1; 0 = empty slot */
+} group_entry;
+
+typedef struct {
+    group_entry *slots;
+    uint64_t    nslots;         /* power of two */
+    uint64_t    nused;
+    int32_t     naggs;
+    agg_state  *pool;           /* [ngroups][naggs] transition states */
+    int64_t    *keys;           /* [ngroups] */
+    uint64_t    pool_cap;       /* in groups */
+} group_table;
+
+static inline uint64_t
+mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+static void
+state_init(agg_state *s)
+{
+    memset(s, 0, sizeof(*s));
+}
+
+static void
+table_init(group_table *t, uint64_t nslots, int naggs)
+{
+    t->nslots = nslots;
+    t->nused = 0;
+    t->naggs = naggs;
+    t->slots = (group_entry *)calloc(nslots, sizeof(group_entry));
+    t->pool_cap = nslots;
+    t->pool = (agg_state *)malloc(sizeof(agg_state) * naggs * t->pool_cap);
+    t->keys = (int64_t *)malloc(sizeof(int64_t) * t->pool_cap);
+}
+
+static void
+table_free(group_table *t)
+{
+    free(t->slots);
+    free(t->pool);
+    free(t->keys);
+}
+
+static void
+table_grow(group_table *t)
+{
+    uint64_t nn = t->nslots * 2;
+    group_entry *ns = (group_entry *)calloc(nn, sizeof(group_entry));
+    for (uint64_t i = 0; i < t->nslots; i++)
+        if (t->slots[i].index)
+        {
+            uint64_t h = mix64((uint64_t)t->slots[i].key) & (nn - 1);
+            while (ns[h].index)
+                h = (h + 1) & (nn - 1);
+            ns[h] = t->slots[i];
+        }
+    free(t->slots);
+    t->slots = ns;
+    t->nslots = nn;
+}
+
+/* returns the transition states of the group, creating it on first sight */
+static agg_state *
+table_lookup(group_table *t, int64_t key)
+{
+    for (;;)
+    {
+        uint64_t mask = t->nslots - 1;
+        uint64_t h = mix64((uint64_t)key) & mask;
+        for (;;)
+        {
+            group_entry *e = &t->slots[h];
+            if (!e->index)
+                break;
+            if (e->key == key)
+                return t->pool + (e->index - 1) * t->naggs;
+            h = (h + 1) & mask;
+        }
+        if ((t->nused + 1) * 4 > t->nslots * 3)
+        {
+            table_grow(t);
+            continue;
+        }
+        if (t->nused == t->pool_cap)
+        {
+            t->pool_cap *= 2;
+            t->pool = (agg_state *)realloc(t->pool, sizeof(agg_state) * t->naggs * t->pool_cap);
+            t->keys = (int64_t *)realloc(t->keys, sizeof(int64_t) * t->pool_cap);
+        }
+        t->slots[h].key = key;
+        t->slots[h].index = (int64_t)(++t->nused);
+        t->keys[t->nused - 1] = key;
+        agg_state *st = t->pool + (t->nused - 1) * t->naggs;
+        for (int j = 0; j < t->naggs; j++)
+            state_init(&st[j]);
+        return st;
+    }
+}
+
+static inline void
+add128(agg_state *s, int64_t v)
+{
+    uint64_t old = (uint64_t)s->isum_lo;
+    uint64_t nw = old + (uint64_t)v;
+    s->isum_lo = (int64_t)nw;
+    s->isum_hi += (v < 0 ? -1 : 0) + (nw < old ? 1 : 0);
+}
+
+/* float8_cmp_internal: NaN sorts above everything */
+static inline int
+f8cmp(double a, double b)
+{
+    if (isnan(a)) return isnan(b) ? 0 : 1;
+    if (isnan(b)) return -1;
+    return (a > b) - (a < b);
+}
+
+static inline void
+advance(agg_state *s, int kind, const cpu_table *t, int col, int64_t r)
+{
+    if (kind == AGG_COUNT_STAR)
+    {
+        s->n++;
+        return;
+    }
+    if (t->nulls[col] && t->nulls[col][r])
+        return;                         /* strict transition function */
+    switch (kind)
+    {
+        case AGG_COUNT:
+            s->n++;
+            break;
+        case AGG_SUM_INT4:
+        case AGG_AVG_INT4:
+            s->n++;
+            s->isum_lo += ((const int32_t *)t->values[col])[r];
+            s->has_value = 1;
+            break;
+        case AGG_AVG_INT8:
+            s->n++;
+            add128(s, ((const int64_t *)t->values[col])[r]);
+            s->has_value = 1;
+            break;
+        case AGG_MIN_INT4:
+        {
+            int64_t v = ((const int32_t *)t->values[col])[r];
+            if (!s->has_value || v < s->imin) s->imin = v;
+            s->has_value = 1;
+            break;
+        }
+        case AGG_MAX_INT4:
+        {
+            int64_t v = ((const int32_t *)t->values[col])[r];
+            if (!s->has_value || v > s->imax) s->imax = v;
+            s->has_value = 1;
+            break;
+        }
+        case AGG_SUM_FLOAT8:
+        case AGG_AVG_FLOAT8:
+            s->n++;
+            s->fsum += ((const double *)t->values[col])[r];
+            s->has_value = 1;
+            break;
+        case AGG_VAR_FLOAT8:
+        {
+            double v = ((const double *)t->values[col])[r];
+            s->n++;
+            s->fsum += v;
+            s->fsum2 += v * v;
+            s->has_value = 1;
+            break;
+        }
+        case AGG_MIN_FLOAT8:
+        {
+            double v = ((const double *)t->values[col])[r];
+            if (!s->has_value || f8cmp(s->fmin, v) >= 0) s->fmin = v;
+            s->has_value = 1;
+            break;
+        }
+        case AGG_MAX_FLOAT8:
+        {
+            double v = ((const double *)t->values[col])[r];
+            if (!s->has_value || f8cmp(s->fmax, v) <= 0) s->fmax = v;
+            s->has_value = 1;
+            break;
+        }
+    }
+}
+
+/* combine function (what a Gather + Finalize Aggregate does) */
+static void
+combine(agg_state *d, const agg_state *s, int kind)
+{
+    uint64_t old;
+    d->n += s->n;
+    old = (uint64_t)d->isum_lo;
+    d->isum_lo = (int64_t)(old + (uint64_t)s->isum_lo);
+    d->isum_hi += s->isum_hi + (((uint64_t)d->isum_lo) < old ? 1 : 0);
+    d->fsum += s->fsum;
+    d->fsum2 += s->fsum2;
+    if (s->has_value)
+    {
+        if (kind == AGG_MIN_INT4 && (!d->has_value || s->imin < d->imin)) d->imin = s->imin;
+        if (kind == AGG_MAX_INT4 && (!d->has_value || s->imax > d->imax)) d->imax = s->imax;
+        if (kind == AGG_MIN_FLOAT8 && (!d->has_value || f8cmp(d->fmin, s->fmin) > 0)) d->fmin = s->fmin;
+        if (kind == AGG_MAX_FLOAT8 && (!d->has_value || f8cmp(d->fmax, s->fmax) < 0)) d->fmax = s->fmax;
+        d->has_value = 1;
+    }
+}
+
+static void
+scan_range(const cpu_table *t, const cpu_query *q, int64_t lo, int64_t hi,
+           group_table *gt, agg_state *nogroup)
+{
+    for (int64_t r = lo; r < hi; r++)
+    {
+        agg_state *st;
+        /* ExecQual: NULL or false => row is filtered */
+        if (q->qual_col >= 0)
+        {
+            if (t->nulls[q->qual_col] && t->nulls[q->qual_col][r])
+                continue;
+            if (!(((const int32_t *)t->values[q->qual_col])[r] < q->qual_const))
+                continue;
+        }
+        if (q->key_col >= 0)
+        {
+            int64_t key = (t->coltype[q->key_col] == COL_INT8)
+                ? ((const int64_t *)t->values[q->key_col])[r]
+                : (int64_t)((const int32_t *)t->values[q->key_col])[r];
+            st = table_lookup(gt, key);
+        }
+        else
+            st = nogroup;
+        for (int j = 0; j < q->naggs; j++)
+            advance(&st[j], q->agg_kind[j], t, q->agg_col[j], r);
+    }
+}
+
+typedef struct {
+    const cpu_table *t;
+    const cpu_query *q;
+    int64_t     lo, hi;
+    group_table gt;
+    agg_state   nogroup[MAX_AGGS];
+} worker_arg;
+
+static void *
+worker_main(void *p)
+{
+    worker_arg *w = (worker_arg *)p;
+    scan_range(w->t, w->q, w->lo, w->hi, &w->gt, w->nogroup);
+    return NULL;
+}
+
+/*
+ * cpu_agg_run: returns the number of groups; results are written into
+ * keys[max_groups] and states[max_groups * naggs] (group order is arbitrary).
+ * If max_groups is too small the count is still returned.
+ */
+int64_t
+cpu_agg_run(const cpu_table *t, const cpu_query *q, int nthreads,
+            int64_t *keys, agg_state *states, int64_t max_groups)
+{
+    if (nthreads < 1)
+        nthreads = 1;
+    worker_arg *w = (worker_arg *)calloc(nthreads, sizeof(worker_arg));
+    pthread_t *th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
+    int64_t per = (t->nrows + nthreads - 1) / nthreads;
+    int64_t ngroups = 0;
+
+    for (int i = 0; i < nthreads; i++)
+    {
+        w[i].t = t;
+        w[i].q = q;
+        w[i].lo = per * i < t->nrows ? per * i : t->nrows;
+        w[i].hi = per * (i + 1) < t->nrows ? per * (i + 1) : t->nrows;
+        if (q->key_col >= 0)
+            table_init(&w[i].gt, 1024, q->naggs);
+        for (int j = 0; j < q->naggs; j++)
+            state_init(&w[i].nogroup[j]);
+        if (nthreads > 1)
+            pthread_create(&th[i], NULL, worker_main, &w[i]);
+        else
+            worker_main(&w[i]);
+    }
+    if (nthreads > 1)
+        for (int i = 0; i < nthreads; i++)
+            pthread_join(th[i], NULL);
+    if (q->key_col < 0)
+    {
+        for (int i = 1; i < nthreads; i++)
+            for (int j = 0; j < q->naggs; j++)
+                combine(&w[0].nogroup[j], &w[i].nogroup[j], q->agg_kind[j]);
+        ngroups = 1;
+        if (max_groups >= 1)
+        {
+            keys[0] = 0;
+            memcpy(states, w[0].nogroup, sizeof(agg_state) * q->naggs);
+        }
+    }
+    else
+    {
+        for (int i = 1; i < nthreads; i++)
+        {
+            for (uint64_t g = 0; g < w[i].gt.nused; g++)
+            {
+                agg_state *d = table_lookup(&w[0].gt, w[i].gt.keys[g]);
+                for (int j = 0; j < q->naggs; j++)
+                    combine(&d[j], &w[i].gt.pool[g * q->naggs + j], q->agg_kind[j]);
+            }
+            table_free(&w[i].gt);
+        }
+        ngroups = (int64_t)w[0].gt.nused;
+        {
+            int64_t ncopy = ngroups < max_groups ? ngroups : max_groups;
+            memcpy(keys, w[0].gt.keys, sizeof(int64_t) * ncopy);
+            memcpy(states, w[0].gt.pool, sizeof(agg_state) * q->naggs * ncopy);
+        }
+        table_free(&w[0].gt);
+    }
+    free(w);
+    free(th);
+    return ngroups;
+}
+
+int
+cpu_agg_state_size(void)
+{
+    return (int)sizeof(agg_state);
+}

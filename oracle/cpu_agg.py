@@ -1,0 +1,103 @@
+"""ctypes wrapper of oracle/cpu_agg.c (PostgreSQL-style Agg over SeqScan in C).
+
+TEST INFRASTRUCTURE (oracle): checker and reported CPU baseline only.
+"""
+import ctypes as C
+import os
+import subprocess
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_build", "libcpu_agg.so")
+
+KINDS = {"count_star": 0, "count": 1, "sum_int4": 2, "avg_int4": 3, "avg_int8": 4,
+         "min_int4": 5, "max_int4": 6, "sum_float8": 7, "avg_float8": 8,
+         "min_float8": 9, "max_float8": 10, "var_float8": 11}
+COLTYPE = {"int4": 4, "int8": 8, "float8": 108}
+
+
+class cpu_table(C.Structure):
+    _fields_ = [("ncols", C.c_int32), ("coltype", C.c_int32 * 8),
+                ("values", C.c_void_p * 8), ("nulls", C.c_void_p * 8),
+                ("nrows", C.c_int64)]
+
+
+class cpu_query(C.Structure):
+    _fields_ = [("qual_col", C.c_int32), ("qual_const", C.c_int32),
+                ("key_col", C.c_int32), ("naggs", C.c_int32),
+                ("agg_kind", C.c_int32 * 16), ("agg_col", C.c_int32 * 16)]
+
+
+class agg_state(C.Structure):
+    _fields_ = [("n", C.c_int64), ("isum_lo", C.c_int64), ("isum_hi", C.c_int64),
+                ("fsum", C.c_double), ("fsum2", C.c_double),
+                ("imin", C.c_int64), ("imax", C.c_int64),
+                ("fmin", C.c_double), ("fmax", C.c_double),
+                ("has_value", C.c_int32), ("pad", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            subprocess.run(["make", "-s", "-C", HERE], check=True)
+        _lib = C.CDLL(LIB)
+        _lib.cpu_agg_run.restype = C.c_int64
+        _lib.cpu_agg_run.argtypes = [C.POINTER(cpu_table), C.POINTER(cpu_query), C.c_int,
+                                     C.POINTER(C.c_int64), C.POINTER(agg_state), C.c_int64]
+        assert _lib.cpu_agg_state_size() == C.sizeof(agg_state)
+    return _lib
+
+
+# the bench queries (pg_strom_b200/workloads.py) as cpu_query
+QUERIES = {
+    "nogrp_agg": dict(coltypes=["int4", "float8"], qual=None, key=None, aggs=[
+        ("count_star", 0), ("count", 0), ("sum_int4", 0), ("avg_int4", 0),
+        ("min_int4", 0), ("max_int4", 0), ("sum_float8", 1), ("avg_float8", 1),
+        ("min_float8", 1), ("max_float8", 1)]),
+    "where_agg": dict(coltypes=["int4", "int4", "float8", "int4"], qual=(0, 10), key=1, aggs=[
+        ("count_star", 0), ("sum_int4", 3), ("avg_float8", 2), ("min_float8", 2),
+        ("max_float8", 2)]),
+    "high_cardinality": dict(coltypes=["int8", "int8", "float8"], qual=None, key=0, aggs=[
+        ("count_star", 0), ("avg_int8", 1), ("avg_float8", 2), ("var_float8", 2)]),
+}
+
+
+def run(name, cols, nthreads=1, max_groups=1 << 24, qual_const=None):
+    """cols: [(values ndarray, nullmask|None)...].  Returns (seconds, keys,
+    states ndarray-of-struct, ngroups)."""
+    lib = load()
+    qd = QUERIES[name]
+    t = cpu_table()
+    keep = []
+    n = len(cols[0][0])
+    t.ncols = len(cols)
+    t.nrows = n
+    for i, (v, m) in enumerate(cols):
+        a = np.ascontiguousarray(v)
+        keep.append(a)
+        t.coltype[i] = COLTYPE[qd["coltypes"][i]]
+        t.values[i] = a.ctypes.data
+        if m is not None:
+            mm = np.ascontiguousarray(m, dtype=np.uint8)
+            keep.append(mm)
+            t.nulls[i] = mm.ctypes.data
+    q = cpu_query()
+    q.qual_col = -1 if qd["qual"] is None else qd["qual"][0]
+    q.qual_const = 0 if qd["qual"] is None else (qual_const if qual_const is not None else qd["qual"][1])
+    q.key_col = -1 if qd["key"] is None else qd["key"]
+    q.naggs = len(qd["aggs"])
+    for j, (k, c) in enumerate(qd["aggs"]):
+        q.agg_kind[j] = KINDS[k]
+        q.agg_col[j] = c
+    keys = (C.c_int64 * max_groups)()
+    states = (agg_state * (max_groups * q.naggs))()
+    t0 = time.perf_counter()
+    ng = lib.cpu_agg_run(C.byref(t), C.byref(q), nthreads, keys, states, max_groups)
+    dt = time.perf_counter() - t0
+    return dt, keys, states, int(ng)

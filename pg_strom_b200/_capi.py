@@ -99,6 +99,10 @@ PROTOTYPES = {
     "pgs_preagg_recheck_rows": (C.c_int64, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32), C.c_int64]),
     "pgs_preagg_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_int32)]),
+    "pgs_nccl_get_unique_id": (C.c_int, [C.c_void_p]),
+    "pgs_nccl_comm_init_rank": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                          C.POINTER(C.c_void_p)]),
+    "pgs_nccl_comm_destroy": (None, [C.c_void_p]),
     "pgs_preagg_merge_nccl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "pgs_preagg_state_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t,
                                           C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]),

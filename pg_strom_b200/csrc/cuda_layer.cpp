@@ -564,6 +564,8 @@ struct ChunkSlot
     int32_t    *h_status = NULL;    /* pinned */
     cudaEvent_t ev_copied = NULL;
     cudaEvent_t ev_done = NULL;
+    cudaEvent_t ev_k0 = NULL, ev_k1 = NULL; /* around the main kernel (perfmon) */
+    bool        timed = false;
     pgs_ticket  ticket = -1;
     uint32_t    nitems = 0;
     bool        busy = false;
@@ -596,6 +598,10 @@ struct pgs_session
     uint64_t        num_dma_recv = 0, bytes_dma_recv = 0;
     uint64_t        num_chunks = 0, num_rechecked_chunks = 0;
     double          time_kern_build_ms = 0;
+    bool            perfmon = false;
+    double          time_kern_main_ms = 0;  /* sum over launches, from CUDA events */
+    uint64_t        num_kern_main = 0;
+    uint64_t        rows_kern_main = 0;
     void           *d_scratch = NULL;   /* small device buffer: desc, counters */
     std::string     perfmon_buf;
     bool            aborted = false;
@@ -684,6 +690,7 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
                                  config->result_colmeta + config->result_ncols);
     s->num_sms = devices[config->device].prop.multiProcessorCount;
     s->time_kern_build_ms = program->build_ms;
+    s->perfmon = pgs::guc_bool("pg_strom.perfmon");
 
 #define OPEN_CHECK(call)                                                \
     do {                                                                \
@@ -812,6 +819,8 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
     {
         OPEN_CHECK(cudaEventCreateWithFlags(&sl.ev_copied, cudaEventDisableTiming));
         OPEN_CHECK(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        OPEN_CHECK(cudaEventCreate(&sl.ev_k0));
+        OPEN_CHECK(cudaEventCreate(&sl.ev_k1));
         OPEN_CHECK(cudaHostAlloc((void **)&sl.h_status, 64, cudaHostAllocPortable));
     }
     OPEN_CHECK(cudaStreamSynchronize(s->s_exec));
@@ -868,6 +877,17 @@ slot_retire(pgs_session *s, ChunkSlot &sl)
     ChunkResult &res = s->results[sl.ticket];
     res.status = *sl.h_status;
     res.done = true;
+    if (sl.timed)
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sl.ev_k0, sl.ev_k1) == cudaSuccess)
+        {
+            s->time_kern_main_ms += ms;
+            s->num_kern_main++;
+            s->rows_kern_main += sl.nitems;
+        }
+        sl.timed = false;
+    }
     if (res.status == StromError_CpuReCheck)
     {
         /* pull the per-row re-check bitmap and clear it for the next use */
@@ -960,10 +980,17 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
         if ((uint32_t)grid > ntiles)
             grid = (int)std::max<uint32_t>(1, ntiles);
     }
+    if (s->perfmon)
+        CUDA_CHECK(cudaEventRecord(sl.ev_k0, s->s_exec));
     rc = launch_kernel(s, use_rowmap ? s->k_rowmap : s->k_main, grid,
                        (int)s->desc.block_threads, s->smem_main, args);
     if (rc != StromError_Success)
         return rc;
+    if (s->perfmon)
+    {
+        CUDA_CHECK(cudaEventRecord(sl.ev_k1, s->s_exec));
+        sl.timed = true;
+    }
     CUDA_CHECK(cudaMemcpyAsync(sl.h_status, sl.d_kgpreagg, sizeof(int32_t),
                                cudaMemcpyDeviceToHost, s->s_exec));
     CUDA_CHECK(cudaEventRecord(sl.ev_done, s->s_exec));
@@ -1253,11 +1280,15 @@ pgs_preagg_state_import(pgs_session *s, const void *device_buf, uint32_t nrecord
 
 /* ---- NCCL merge: libnccl is opened lazily so that the library loads (and
  * the single-GPU path runs) on hosts without it ---- */
+struct pgs_nccl_uid { char internal[128]; };    /* == ncclUniqueId */
 typedef int (*nccl_allgather_fn)(const void *, void *, size_t, int, void *, cudaStream_t);
 typedef int (*nccl_send_fn)(const void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*nccl_recv_fn)(void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*nccl_group_fn)(void);
 typedef const char *(*nccl_errstr_fn)(int);
+typedef int (*nccl_uid_fn)(void *);
+typedef int (*nccl_init_rank_fn)(void **, int, /* ncclUniqueId by value */ struct pgs_nccl_uid, int);
+typedef int (*nccl_destroy_fn)(void *);
 static struct {
     void *handle;
     nccl_allgather_fn allgather;
@@ -1265,6 +1296,9 @@ static struct {
     nccl_recv_fn recv;
     nccl_group_fn group_start, group_end;
     nccl_errstr_fn errstr;
+    nccl_uid_fn get_unique_id;
+    nccl_init_rank_fn comm_init_rank;
+    nccl_destroy_fn comm_destroy;
 } nccl;
 
 static int
@@ -1286,6 +1320,9 @@ nccl_load(void)
     nccl.group_start = (nccl_group_fn)dlsym(nccl.handle, "ncclGroupStart");
     nccl.group_end = (nccl_group_fn)dlsym(nccl.handle, "ncclGroupEnd");
     nccl.errstr = (nccl_errstr_fn)dlsym(nccl.handle, "ncclGetErrorString");
+    nccl.get_unique_id = (nccl_uid_fn)dlsym(nccl.handle, "ncclGetUniqueId");
+    nccl.comm_init_rank = (nccl_init_rank_fn)dlsym(nccl.handle, "ncclCommInitRank");
+    nccl.comm_destroy = (nccl_destroy_fn)dlsym(nccl.handle, "ncclCommDestroy");
     if (!nccl.allgather || !nccl.send || !nccl.recv || !nccl.group_start || !nccl.group_end)
     {
         set_error("libnccl lacks a required symbol");
@@ -1304,6 +1341,42 @@ nccl_load(void)
             return StromError_CudaInternal;                             \
         }                                                               \
     } while (0)
+
+extern "C" int
+pgs_nccl_get_unique_id(void *unique_id_128)
+{
+    int rc = nccl_load();
+    if (rc != StromError_Success)
+        return rc;
+    if (!nccl.get_unique_id)
+        return StromError_ServerNotReady;
+    NCCL_CHECK(nccl.get_unique_id(unique_id_128));
+    return StromError_Success;
+}
+
+extern "C" int
+pgs_nccl_comm_init_rank(int device, int nranks, const void *unique_id_128, int rank,
+                        void **comm)
+{
+    int rc = nccl_load();
+    if (rc != StromError_Success)
+        return rc;
+    int ord = device_ordinal(device);
+    if (ord < 0 || !nccl.comm_init_rank)
+        return StromError_ServerNotReady;
+    CUDA_CHECK(cudaSetDevice(ord));
+    struct pgs_nccl_uid uid;
+    memcpy(&uid, unique_id_128, sizeof(uid));
+    NCCL_CHECK(nccl.comm_init_rank(comm, nranks, uid, rank));
+    return StromError_Success;
+}
+
+extern "C" void
+pgs_nccl_comm_destroy(void *comm)
+{
+    if (nccl.handle && nccl.comm_destroy && comm)
+        nccl.comm_destroy(comm);
+}
 
 extern "C" int
 pgs_preagg_merge_nccl(pgs_session *s, void *nccl_comm, int rank, int nranks, int root)
@@ -1392,6 +1465,9 @@ pgs_preagg_perfmon_json(pgs_session *s)
     o->set("num_rechecked_chunks", (long long)s->num_rechecked_chunks);
     o->set("num_kernel_launches", (long long)s->launches);
     o->set("time_kern_build_ms", pgs::Json::number(s->time_kern_build_ms));
+    o->set("time_kern_main_ms", pgs::Json::number(s->time_kern_main_ms));
+    o->set("num_kern_main", (long long)s->num_kern_main);
+    o->set("rows_kern_main", (long long)s->rows_kern_main);
     o->set("nrows_filtered", (long long)counters[1]);
     o->set("grid_main", s->grid_main);
     o->set("smem_main", (long long)s->smem_main);
@@ -1442,6 +1518,8 @@ pgs_preagg_close(pgs_session *s)
             if (sl.h_status) cudaFreeHost(sl.h_status);
             if (sl.ev_copied) cudaEventDestroy(sl.ev_copied);
             if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+            if (sl.ev_k0) cudaEventDestroy(sl.ev_k0);
+            if (sl.ev_k1) cudaEventDestroy(sl.ev_k1);
         }
         if (s->gs.gh_slots) cudaFree(s->gs.gh_slots);
         if (s->d_scratch) cudaFree(s->d_scratch);
