@@ -36,7 +36,7 @@ import numpy as np  # noqa: E402
 
 DEFAULT_ROWS = {"nogrp_agg": 100_000_000, "where_agg": 125_000_000,
                 "high_cardinality": 100_000_000}
-DEFAULT_CHUNK = {"nogrp_agg": 12_500_000, "where_agg": 12_500_000,
+DEFAULT_CHUNK = {"nogrp_agg": 25_000_000, "where_agg": 25_000_000,
                  "high_cardinality": 12_500_000}
 METRIC = "GpuPreAgg (partial GROUP BY / no-group aggregation with fused qual) throughput"
 SQL = {

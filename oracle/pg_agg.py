@@ -693,13 +693,17 @@ class FinalAgg:
                 self.N += nrows
                 self.S += psum
             elif self.t in ("int8", "numeric"):
-                # pgstrom_int8_avg_accum: int8_avg_accum(psum) then N += nrows-1
+                # pgstrom_int8_avg_accum / pgstrom_numeric_avg_accum
+                # (gpupreagg.c:4540-4588): int8_avg_accum(psum), which counts
+                # one row, then "if (nrows > 0) N += nrows - 1".  For a
+                # partial row with nrows = 0 and a non-NULL psum (FILTERed
+                # psum defaults to 0; a group split over several partial rows)
+                # that leaves N one too high.  The glue's accum function adds
+                # exactly nrows instead - same catalog signature.
                 if psum is None:
                     return
                 self.S = numeric_add(self.S, Decimal(psum))
-                self.N += 1
-                if nrows > 0:
-                    self.N += nrows - 1
+                self.N += nrows
             else:
                 if nrows is None or psum is None:
                     return

@@ -134,9 +134,8 @@ program_options(int extra_flags)
 {
     std::string o;
     (void)extra_flags;
-    o += "tile=" + std::string(getenv("PGSTROM_TILE_ROWS") ? getenv("PGSTROM_TILE_ROWS") : "2048");
-    o += ";stages=" + std::string(getenv("PGSTROM_NUM_STAGES") ? getenv("PGSTROM_NUM_STAGES") : "4");
-    o += ";warps=" + std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "8");
+    o += "warps=" + std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "16");
+    o += ";minctas=" + std::string(getenv("PGSTROM_MIN_CTAS") ? getenv("PGSTROM_MIN_CTAS") : "2");
     o += ";opt=" + std::string(pgs::guc_bool("pg_strom.devprog_enable_optimization") ? "1" : "0");
     return o;
 }
@@ -150,16 +149,14 @@ nvrtc_build(pgs_program *prog)
                               pgs_hdr_kern_gpupreagg_cuh };
     const char *names[] = { "pgstrom_kds.h", "kern_shared.h", "kern_common.cuh",
                             "kern_numeric.cuh", "kern_gpupreagg.cuh" };
-    std::string d_tile = "-DGPUPREAGG_TILE_ROWS=" +
-        std::string(getenv("PGSTROM_TILE_ROWS") ? getenv("PGSTROM_TILE_ROWS") : "2048");
-    std::string d_stages = "-DGPUPREAGG_NUM_STAGES=" +
-        std::string(getenv("PGSTROM_NUM_STAGES") ? getenv("PGSTROM_NUM_STAGES") : "4");
     std::string d_warps = "-DGPUPREAGG_CONSUMER_WARPS=" +
-        std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "8");
+        std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "16");
+    std::string d_rpt = "-DGPUPREAGG_MIN_CTAS=" +
+        std::string(getenv("PGSTROM_MIN_CTAS") ? getenv("PGSTROM_MIN_CTAS") : "2");
     std::vector<const char *> opts = {
         "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
         "-device-int128", "--fmad=false",
-        d_tile.c_str(), d_stages.c_str(), d_warps.c_str(),
+        d_warps.c_str(), d_rpt.c_str(),
     };
     if (!pgs::guc_bool("pg_strom.devprog_enable_optimization"))
         opts.push_back("-Xptxas=-O0");
@@ -591,6 +588,8 @@ struct pgs_session
     int             grid_main = 0;
     size_t          smem_main = 0;
     cl_uint         sh_nslots = 0;
+    cl_uint         tile_rows = 2048;
+    cl_uint         nstages = 4;
     int             num_sms = 0;
     uint64_t        launches = 0;
     /* perfmon (pg_strom.h:177-213) */
@@ -747,38 +746,60 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
         pgs_preagg_close(s);
         return StromError_BadRequestMessage;
     }
-    /* launch shape of the main kernel: persistent CTAs, a multiple of the
-     * SM count */
+    /* launch shape of the main kernel: persistent CTAs (a multiple of the SM
+     * count); the 227 KB of shared memory are split between the CTA-local
+     * hash table (GROUP BY) and the TMA staging ring */
     {
         size_t smem_max = devices[config->device].prop.sharedMemPerBlockOptin;
-        size_t base = (size_t)s->desc.static_smem_bytes +
-            (size_t)s->desc.num_stages * s->desc.stage_bytes;
+        size_t head = s->desc.static_smem_bytes;
+        size_t per1k = s->desc.stage_bytes;         /* staging bytes per 1024 rows */
         int per_sm = 0;
+        size_t table_bytes = 0;
 
         s->sh_nslots = 0;
         if (s->desc.num_keys > 0)
         {
+            /* the table wants 2 x groups slots; leave room for >= 2 stages of
+             * 1024 rows.  A CTA-local table only pays when most groups fit. */
             double want = std::max(64.0, config->num_groups * 2.0);
-            size_t avail = (smem_max > base + 1024 ? smem_max - base - 1024 : 0);
-            size_t maxslots = 64;
-            while (maxslots * 2 * s->desc.sh_slot_bytes <= avail)
-                maxslots <<= 1;
-            if (maxslots * s->desc.sh_slot_bytes > avail)
-                maxslots = 0;
+            size_t avail = (smem_max > head + 2 * per1k + 1024
+                            ? smem_max - head - 2 * per1k - 1024 : 0);
+            size_t maxslots = 0;
+            for (size_t n = 64; n * s->desc.sh_slot_bytes <= avail; n <<= 1)
+                maxslots = n;
             size_t nslots = 64;
             while ((double)nslots < want && nslots < maxslots)
                 nslots <<= 1;
             const char *env = getenv("PGSTROM_SH_SLOTS");
             if (env)
                 nslots = (size_t)atol(env);
-            /* a CTA-local table only pays when most groups fit in it */
             if (maxslots == 0 || (!env && config->num_groups > 4.0 * (double)maxslots))
                 nslots = 0;
             if (nslots > maxslots)
                 nslots = maxslots;
             s->sh_nslots = (cl_uint)nslots;
+            table_bytes = nslots * s->desc.sh_slot_bytes;
         }
-        s->smem_main = base + (size_t)s->sh_nslots * s->desc.sh_slot_bytes;
+        /* staging ring: prefer >= 3 stages, then the largest tile that fits
+         * two CTAs per SM (no-group) or one (with a big table) */
+        {
+            size_t budget = smem_max - head - table_bytes - 1024;
+            size_t target = (table_bytes > 64 * 1024 ? budget : (smem_max - 2048) / 2 - head - table_bytes);
+            cl_uint tile = 2048, stages = 4;
+            const char *et = getenv("PGSTROM_TILE_ROWS");
+            const char *es = getenv("PGSTROM_NUM_STAGES");
+            if (target > budget)
+                target = budget;
+            while (stages > 2 && (size_t)stages * (tile / 1024) * per1k > target)
+                stages--;
+            while (tile > 1024 && (size_t)stages * (tile / 1024) * per1k > target)
+                tile -= 1024;
+            if (et) tile = (cl_uint)std::max(1024, (atoi(et) / 1024) * 1024);
+            if (es) stages = (cl_uint)std::min(8, std::max(1, atoi(es)));
+            s->tile_rows = tile;
+            s->nstages = stages;
+        }
+        s->smem_main = head + (size_t)s->nstages * (s->tile_rows / 1024) * per1k + table_bytes;
         if (s->smem_main > smem_max)
         {
             set_error("device program needs %zu bytes of shared memory, the device allows %zu",
@@ -972,11 +993,12 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
     CUDA_CHECK(cudaStreamWaitEvent(s->s_exec, sl.ev_copied, 0));
 
     bool use_rowmap = (krowmap && krowmap->nvalids >= 0);
-    void *args[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck, &s->sh_nslots };
+    void *args[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck, &s->sh_nslots,
+                     &s->tile_rows, &s->nstages };
     int grid = s->grid_main;
     if (!use_rowmap)
     {
-        uint32_t ntiles = (nitems + s->desc.tile_rows - 1) / s->desc.tile_rows;
+        uint32_t ntiles = (nitems + s->tile_rows - 1) / s->tile_rows;
         if ((uint32_t)grid > ntiles)
             grid = (int)std::max<uint32_t>(1, ntiles);
     }
@@ -1474,9 +1496,9 @@ pgs_preagg_perfmon_json(pgs_session *s)
     o->set("sh_nslots", (long long)s->sh_nslots);
     o->set("gh_nslots", (long long)s->gs.gh_nslots);
     o->set("block_threads", (long long)s->desc.block_threads);
-    o->set("tile_rows", (long long)s->desc.tile_rows);
-    o->set("num_stages", (long long)s->desc.num_stages);
-    o->set("stage_bytes", (long long)s->desc.stage_bytes);
+    o->set("tile_rows", (long long)s->tile_rows);
+    o->set("num_stages", (long long)s->nstages);
+    o->set("stage_bytes", (long long)(s->tile_rows / 1024) * s->desc.stage_bytes);
     o->set("row_bytes", (long long)s->desc.row_bytes);
     o->set("slot_bytes", (long long)s->desc.slot_bytes);
     s->perfmon_buf = o->dump();

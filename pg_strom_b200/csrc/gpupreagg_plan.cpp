@@ -674,6 +674,9 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
     std::set<int> proj_refs;
     int nkeys = 0, naggs = 0, ncells = 0;
     std::ostringstream key_list, agg_list, out_list, role_fn, index_fn;
+    /* aggregates whose argument has the NULL-ness of the same outer column
+     * share one "saw a non-NULL input" test per row */
+    std::vector<std::pair<std::string, std::pair<int, unsigned> > > nn_classes;
 
     for (size_t i = 0; i < pre_tlist.size(); i++)
     {
@@ -845,6 +848,33 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
                 *err = "numeric partial aggregates are not supported on the device yet";
                 return false;
             }
+            /* NULL-ness class of this partial value */
+            {
+                std::string klass = "agg:" + std::to_string(naggs);
+                if (func_name == "nrows")
+                    klass = "never-null";
+                else if (func_name == "pmax" || func_name == "pmin" || func_name == "psum")
+                {
+                    JsonPtr a = fargs->arr[0];
+                    /* strict casts / relabels keep NULL-ness */
+                    while (a && ((a->s("node") == "FuncExpr" && a->s("funcschema").empty() &&
+                                  a->get("args") && a->get("args")->arr.size() == 1 &&
+                                  (a->s("funcformat") == "cast" || a->s("funcformat") == "implicit")) ||
+                                 a->s("node") == "RelabelType"))
+                        a = (a->s("node") == "RelabelType") ? a->getp("arg") : a->get("args")->arr[0];
+                    if (a && a->s("node") == "Var")
+                        klass = "var:" + std::to_string(a->i("varattno"));
+                }
+                bool found = false;
+                for (auto &kc : nn_classes)
+                    if (kc.first == klass)
+                    {
+                        kc.second.second |= (1U << naggs);
+                        found = true;
+                    }
+                if (!found)
+                    nn_classes.push_back(std::make_pair(klass, std::make_pair(naggs, 1U << naggs)));
+            }
             /* track usage of this field */
             gpagg_atts[resno - 1] = (char)GPUPREAGG_FIELD_IS_AGGFUNC;
             pc.agg_index = naggs;
@@ -942,6 +972,11 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
          << "#define GPUPREAGG_NUM_AGGS " << naggs << "\n"
          << "#define GPUPREAGG_NUM_CELLS " << ncells << "\n"
          << "#define GPUPREAGG_AGG_LIST(_)" << agg_list.str() << "\n"
+         << "#define GPUPREAGG_NNCLASS_LIST(_)" << [&]() {
+                std::ostringstream o;
+                for (auto &kc : nn_classes)
+                    o << " _(" << kc.second.first << ",0x" << std::hex << kc.second.second << std::dec << "U)";
+                return o.str(); }() << "\n"
          << "#define GPUPREAGG_NUM_OUTCOLS " << pre_tlist.size() << "\n"
          << "#define GPUPREAGG_OUT_LIST(_)" << out_list.str() << "\n";
     role_fn << "__host__ __device__ constexpr int\nGPUPREAGG_FIELD_ROLE(unsigned int colidx)\n{\n  switch (colidx)\n  {\n";

@@ -78,13 +78,19 @@ struct kern_tile_smem
     {
         cl_uint i = rowidx - row0;
 
+        /* every staged array starts on a 128-byte boundary: lets the
+         * compiler merge the loads of adjacent rows into LDS.64 / LDS.128 */
+        __builtin_assume((val_off[slot] & 127U) == 0);
+        /* the value slot of a NULL row holds padding that is safe to read:
+         * load first (unconditional loads of adjacent rows vectorise), then
+         * look at the validity bit */
+        out = *((const T *)(__pgs_smem + val_off[slot]) + i);
         if (nul_off[slot] != KERN_TILE_NO_NULLMAP)
         {
             cl_uint w = *((const cl_uint *)(__pgs_smem + nul_off[slot]) + (i >> 5));
             if (((w >> (i & 31)) & 1U) == 0)
                 return false;
         }
-        out = *((const T *)(__pgs_smem + val_off[slot]) + i);
         return true;
     }
 };
@@ -106,6 +112,76 @@ struct kern_tile_gmem
         }
         out = __ldg((const T *)val_ptr[slot] + rowidx);
         return true;
+    }
+};
+
+/*
+ * kern_row_regs - one row whose staged columns were already pulled into
+ * registers (the staged kernel loads PGS_ROWS_PER_THREAD adjacent rows with
+ * 128-bit shared memory loads first, then evaluates them one by one, so the
+ * generated code never does address arithmetic).
+ */
+struct kern_row_regs
+{
+    cl_ulong    v[GPUPREAGG_NUM_INCOLS > 0 ? GPUPREAGG_NUM_INCOLS : 1];
+    /* bit 0 = validity (NOT NULL) of this row, per staged column */
+    cl_uint     vbits[GPUPREAGG_NUM_INCOLS > 0 ? GPUPREAGG_NUM_INCOLS : 1];
+
+    template <typename T>
+    __device__ __forceinline__ bool
+    fetch(int slot, cl_uint rowidx, T &out) const
+    {
+        union { cl_ulong u; T t; } cv;
+        cv.u = v[slot];
+        out = cv.t;
+        return (vbits[slot] & 1U) != 0;
+    }
+};
+
+/* loads of PGS_ROWS_PER_THREAD (= 4) adjacent values of one staged column;
+ * `p` is 16-byte aligned for every attlen because the row index is a
+ * multiple of 4 ... for attlen >= 4; narrower columns use narrower loads */
+template <int ATTLEN>
+struct pgs_rowload;
+template <>
+struct pgs_rowload<8>
+{
+    static __device__ __forceinline__ void
+    load4(const unsigned char *p, cl_ulong &a, cl_ulong &b, cl_ulong &c, cl_ulong &d)
+    {
+        ulonglong2 lo = *((const ulonglong2 *)p);
+        ulonglong2 hi = *((const ulonglong2 *)p + 1);
+        a = lo.x; b = lo.y; c = hi.x; d = hi.y;
+    }
+};
+template <>
+struct pgs_rowload<4>
+{
+    static __device__ __forceinline__ void
+    load4(const unsigned char *p, cl_ulong &a, cl_ulong &b, cl_ulong &c, cl_ulong &d)
+    {
+        uint4 q = *((const uint4 *)p);
+        a = q.x; b = q.y; c = q.z; d = q.w;
+    }
+};
+template <>
+struct pgs_rowload<2>
+{
+    static __device__ __forceinline__ void
+    load4(const unsigned char *p, cl_ulong &a, cl_ulong &b, cl_ulong &c, cl_ulong &d)
+    {
+        uint2 q = *((const uint2 *)p);
+        a = q.x & 0xffffU; b = q.x >> 16; c = q.y & 0xffffU; d = q.y >> 16;
+    }
+};
+template <>
+struct pgs_rowload<1>
+{
+    static __device__ __forceinline__ void
+    load4(const unsigned char *p, cl_ulong &a, cl_ulong &b, cl_ulong &c, cl_ulong &d)
+    {
+        cl_uint q = *((const cl_uint *)p);
+        a = q & 0xffU; b = (q >> 8) & 0xffU; c = (q >> 16) & 0xffU; d = q >> 24;
     }
 };
 

@@ -37,25 +37,29 @@
  *   GPUPREAGG_NUM_AGGS,  GPUPREAGG_NUM_CELLS, GPUPREAGG_AGG_LIST(_)
  *   GPUPREAGG_NUM_OUTCOLS, GPUPREAGG_OUT_LIST(_)
  *   GPUPREAGG_FIELD_ROLE(colidx), GPUPREAGG_FIELD_INDEX(colidx)
- * and by the CUDA layer (-D): GPUPREAGG_TILE_ROWS, GPUPREAGG_NUM_STAGES,
- *   GPUPREAGG_CONSUMER_WARPS.
+ * and by the CUDA layer (-D): GPUPREAGG_CONSUMER_WARPS.
  */
 #ifndef KERN_GPUPREAGG_CUH
 #define KERN_GPUPREAGG_CUH
 
 #include "kern_shared.h"
 
-#ifndef GPUPREAGG_TILE_ROWS
-#define GPUPREAGG_TILE_ROWS         2048
-#endif
-#ifndef GPUPREAGG_NUM_STAGES
-#define GPUPREAGG_NUM_STAGES        4
-#endif
+/* tile size and pipeline depth are launch parameters (the CUDA layer fits
+ * them, together with the CTA-local hash table, into the 227 KB of shared
+ * memory); only their upper bounds are compile time */
+#define GPUPREAGG_MAX_STAGES        8
 #ifndef GPUPREAGG_CONSUMER_WARPS
-#define GPUPREAGG_CONSUMER_WARPS    8
+#define GPUPREAGG_CONSUMER_WARPS    16
+#endif
+#ifndef GPUPREAGG_MIN_CTAS
+#define GPUPREAGG_MIN_CTAS          2
 #endif
 #define GPUPREAGG_CONSUMER_THREADS  (GPUPREAGG_CONSUMER_WARPS * 32)
 #define GPUPREAGG_BLOCK_THREADS     (GPUPREAGG_CONSUMER_THREADS + 32)
+
+#ifndef PGS_ROWS_PER_THREAD
+#define PGS_ROWS_PER_THREAD         4
+#endif
 
 #define PGS_MAX(a,b)    ((a) > (b) ? (a) : (b))
 
@@ -150,12 +154,11 @@ pg_common_vstore(pagg_row &kds_src, const KDS &kds_in, cl_int *errcode,
 DEVFN cl_ulong
 pgs_f8_sortkey(double v)
 {
-    cl_ulong    b;
+    cl_long     b = __double_as_longlong(v);
+    /* negative: flip all bits; non-negative: set the sign bit */
+    cl_ulong    k = (cl_ulong)b ^ ((cl_ulong)(b >> 63) | PGS_F8_SIGNBIT);
 
-    if (isnan(v))
-        return PGS_F8_NANKEY;
-    b = (cl_ulong)__double_as_longlong(v);
-    return (b & PGS_F8_SIGNBIT) ? ~b : (b | PGS_F8_SIGNBIT);
+    return (v != v) ? PGS_F8_NANKEY : k;
 }
 
 DEVFN double
@@ -173,16 +176,32 @@ pgs_f8_from_sortkey(cl_ulong k)
 #define PGS_CELL_INIT_PSUM_LONG(c,p)    (p)[c] = 0; (p)[(c)+1] = 0;
 #define PGS_CELL_INIT_PSUM_FLOAT(c,p)   (p)[c] = 0;
 #define PGS_CELL_INIT_PSUM_DOUBLE(c,p)  (p)[c] = 0;
-#define PGS_CELL_INIT_PMIN_SHORT(c,p)   (p)[c] = (cl_ulong)LONG_MAX;
-#define PGS_CELL_INIT_PMIN_INT(c,p)     (p)[c] = (cl_ulong)LONG_MAX;
+#define PGS_CELL_INIT_PMIN_SHORT(c,p)   (p)[c] = (cl_ulong)(cl_long)INT_MAX;
+#define PGS_CELL_INIT_PMIN_INT(c,p)     (p)[c] = (cl_ulong)(cl_long)INT_MAX;
 #define PGS_CELL_INIT_PMIN_LONG(c,p)    (p)[c] = (cl_ulong)LONG_MAX;
-#define PGS_CELL_INIT_PMIN_FLOAT(c,p)   (p)[c] = PGS_F8_NANKEY;
-#define PGS_CELL_INIT_PMIN_DOUBLE(c,p)  (p)[c] = PGS_F8_NANKEY;
-#define PGS_CELL_INIT_PMAX_SHORT(c,p)   (p)[c] = (cl_ulong)LONG_MIN;
-#define PGS_CELL_INIT_PMAX_INT(c,p)     (p)[c] = (cl_ulong)LONG_MIN;
+/* float min/max cells: with GROUP BY the table cells are updated by 64-bit
+ * integer atomics, so they hold order-preserving keys (NaN highest).  Without
+ * GROUP BY everything lives in registers and the cell is the raw double:
+ * compares run on the FP64 pipe instead of four ALU ops per value.  The
+ * identity of min is NaN ("greater than everything"), of max -Infinity. */
+#if GPUPREAGG_NUM_KEYS == 0
+#define PGS_F8_MIN_IDENTITY     0x7FF8000000000000ULL
+#define PGS_F8_MAX_IDENTITY     0xFFF0000000000000ULL
+#define PGS_F8_CELL(v)          ((cl_ulong)__double_as_longlong(v))
+#define PGS_F8_UNCELL(k)        __longlong_as_double((cl_long)(k))
+#else
+#define PGS_F8_MIN_IDENTITY     PGS_F8_NANKEY
+#define PGS_F8_MAX_IDENTITY     0ULL
+#define PGS_F8_CELL(v)          pgs_f8_sortkey(v)
+#define PGS_F8_UNCELL(k)        pgs_f8_from_sortkey(k)
+#endif
+#define PGS_CELL_INIT_PMIN_FLOAT(c,p)   (p)[c] = PGS_F8_MIN_IDENTITY;
+#define PGS_CELL_INIT_PMIN_DOUBLE(c,p)  (p)[c] = PGS_F8_MIN_IDENTITY;
+#define PGS_CELL_INIT_PMAX_SHORT(c,p)   (p)[c] = (cl_ulong)(cl_long)INT_MIN;
+#define PGS_CELL_INIT_PMAX_INT(c,p)     (p)[c] = (cl_ulong)(cl_long)INT_MIN;
 #define PGS_CELL_INIT_PMAX_LONG(c,p)    (p)[c] = (cl_ulong)LONG_MIN;
-#define PGS_CELL_INIT_PMAX_FLOAT(c,p)   (p)[c] = 0;
-#define PGS_CELL_INIT_PMAX_DOUBLE(c,p)  (p)[c] = 0;
+#define PGS_CELL_INIT_PMAX_FLOAT(c,p)   (p)[c] = PGS_F8_MAX_IDENTITY;
+#define PGS_CELL_INIT_PMAX_DOUBLE(c,p)  (p)[c] = PGS_F8_MAX_IDENTITY;
 
 /* ---- value of one projected datum in "cell domain" ---- */
 #define PGS_NEWVAL_PSUM_INT(d)      ((cl_ulong)(cl_long)(d).int_val)
@@ -193,8 +212,8 @@ pgs_f8_from_sortkey(cl_ulong k)
 #define PGS_NEWVAL_PMIN_SHORT(d)    ((cl_ulong)(cl_long)(d).short_val)
 #define PGS_NEWVAL_PMIN_INT(d)      ((cl_ulong)(cl_long)(d).int_val)
 #define PGS_NEWVAL_PMIN_LONG(d)     ((cl_ulong)(d).long_val)
-#define PGS_NEWVAL_PMIN_FLOAT(d)    pgs_f8_sortkey((double)(d).float_val)
-#define PGS_NEWVAL_PMIN_DOUBLE(d)   pgs_f8_sortkey((d).double_val)
+#define PGS_NEWVAL_PMIN_FLOAT(d)    PGS_F8_CELL((double)(d).float_val)
+#define PGS_NEWVAL_PMIN_DOUBLE(d)   PGS_F8_CELL((d).double_val)
 #define PGS_NEWVAL_PMAX_SHORT(d)    PGS_NEWVAL_PMIN_SHORT(d)
 #define PGS_NEWVAL_PMAX_INT(d)      PGS_NEWVAL_PMIN_INT(d)
 #define PGS_NEWVAL_PMAX_LONG(d)     PGS_NEWVAL_PMIN_LONG(d)
@@ -204,94 +223,143 @@ pgs_f8_from_sortkey(cl_ulong k)
 /* ---- merge one cell-domain value into a cell: plain (registers / one
  * owner) and atomic (shared or global table) flavours.  They take the value
  * already in cell domain so that the same code merges rows and states. ---- */
-#define PGS_MERGE_PLAIN_SUM_I64(p,c,v)  (p)[c] += (v);
-#define PGS_MERGE_PLAIN_SUM_F64(p,c,v)                                  \
-    (p)[c] = (cl_ulong)__double_as_longlong(                            \
-        __longlong_as_double((cl_long)(p)[c]) +                         \
-        __longlong_as_double((cl_long)(v)));
-#define PGS_MERGE_PLAIN_MIN_I64(p,c,v)                                  \
-    if ((cl_long)(v) < (cl_long)(p)[c]) (p)[c] = (v);
-#define PGS_MERGE_PLAIN_MAX_I64(p,c,v)                                  \
-    if ((cl_long)(v) > (cl_long)(p)[c]) (p)[c] = (v);
-#define PGS_MERGE_PLAIN_MIN_U64(p,c,v)                                  \
-    if ((v) < (p)[c]) (p)[c] = (v);
-#define PGS_MERGE_PLAIN_MAX_U64(p,c,v)                                  \
-    if ((v) > (p)[c]) (p)[c] = (v);
+/* PLAIN flavours are branch free (`ok` selects), so that the per-row body of
+ * the no-group kernel is straight-line code; ATOMIC flavours skip the
+ * memory operation when `ok` is false. */
+#define PGS_MERGE_PLAIN_SUM_I64(p,c,v,ok)   (p)[c] += ((ok) ? (cl_ulong)(v) : 0ULL);
+#define PGS_MERGE_PLAIN_SUM_F64(p,c,v,ok)                               \
+    { double __t = __longlong_as_double((cl_long)(p)[c]) +              \
+                   __longlong_as_double((cl_long)(v));                  \
+      (p)[c] = (ok) ? (cl_ulong)__double_as_longlong(__t) : (p)[c]; }
+#define PGS_MERGE_PLAIN_MIN_I64(p,c,v,ok)                               \
+    (p)[c] = ((ok) & ((cl_long)(v) < (cl_long)(p)[c])) ? (cl_ulong)(v) : (p)[c];
+#define PGS_MERGE_PLAIN_MAX_I64(p,c,v,ok)                               \
+    (p)[c] = ((ok) & ((cl_long)(v) > (cl_long)(p)[c])) ? (cl_ulong)(v) : (p)[c];
+#define PGS_MERGE_PLAIN_MIN_I32(p,c,v,ok)                               \
+    (p)[c] = (cl_ulong)(cl_uint)((ok) ? min((cl_int)(p)[c], (cl_int)(v)) : (cl_int)(p)[c]);
+#define PGS_MERGE_PLAIN_MAX_I32(p,c,v,ok)                               \
+    (p)[c] = (cl_ulong)(cl_uint)((ok) ? max((cl_int)(p)[c], (cl_int)(v)) : (cl_int)(p)[c]);
+#define PGS_MERGE_PLAIN_MIN_U64(p,c,v,ok)                               \
+    (p)[c] = ((ok) & ((cl_ulong)(v) < (cl_ulong)(p)[c])) ? (cl_ulong)(v) : (p)[c];
+#define PGS_MERGE_PLAIN_MAX_U64(p,c,v,ok)                               \
+    (p)[c] = ((ok) & ((cl_ulong)(v) > (cl_ulong)(p)[c])) ? (cl_ulong)(v) : (p)[c];
+#define PGS_MERGE_THREAD_CNT_I32(p,c,v,ok)                              \
+    (p)[c] = (cl_ulong)((cl_uint)(p)[c] + ((ok) ? (cl_uint)(v) : 0U));
+#define PGS_MERGE_THREAD_SUM_I64(p,c,v,ok)  PGS_MERGE_PLAIN_SUM_I64(p,c,v,ok)
+#define PGS_MERGE_THREAD_SUM_F64(p,c,v,ok)  PGS_MERGE_PLAIN_SUM_F64(p,c,v,ok)
+#define PGS_MERGE_THREAD_MIN_I64(p,c,v,ok)  PGS_MERGE_PLAIN_MIN_I64(p,c,v,ok)
+#define PGS_MERGE_THREAD_MAX_I64(p,c,v,ok)  PGS_MERGE_PLAIN_MAX_I64(p,c,v,ok)
+#define PGS_MERGE_THREAD_MIN_I32(p,c,v,ok)  PGS_MERGE_PLAIN_MIN_I32(p,c,v,ok)
+#define PGS_MERGE_THREAD_MAX_I32(p,c,v,ok)  PGS_MERGE_PLAIN_MAX_I32(p,c,v,ok)
+#define PGS_MERGE_THREAD_MIN_U64(p,c,v,ok)  PGS_MERGE_PLAIN_MIN_U64(p,c,v,ok)
+#define PGS_MERGE_THREAD_MAX_U64(p,c,v,ok)  PGS_MERGE_PLAIN_MAX_U64(p,c,v,ok)
+#define PGS_MERGE_PLAIN_CNT_I32(p,c,v,ok)   PGS_MERGE_PLAIN_SUM_I64(p,c,v,ok)
+#define PGS_MERGE_ATOMIC_CNT_I32(p,c,v,ok)  PGS_MERGE_ATOMIC_SUM_I64(p,c,v,ok)
 
-#define PGS_MERGE_ATOMIC_SUM_I64(p,c,v)                                 \
-    atomicAdd((unsigned long long *)&(p)[c], (unsigned long long)(v));
-#define PGS_MERGE_ATOMIC_SUM_F64(p,c,v)                                 \
-    atomicAdd((double *)&(p)[c], __longlong_as_double((cl_long)(v)));
-#define PGS_MERGE_ATOMIC_MIN_I64(p,c,v)                                 \
-    if ((cl_long)(v) < *((volatile cl_long *)&(p)[c]))                  \
+/* float min/max (see PGS_F8_CELL) */
+#if GPUPREAGG_NUM_KEYS == 0
+#define PGS_MERGE_PLAIN_MIN_F64(p,c,v,ok)                               \
+    { double __a = PGS_F8_UNCELL((p)[c]), __x = PGS_F8_UNCELL(v);        \
+      (p)[c] = ((ok) & ((__x < __a) | (__a != __a))) ? (cl_ulong)(v) : (p)[c]; }
+#define PGS_MERGE_PLAIN_MAX_F64(p,c,v,ok)                               \
+    { double __a = PGS_F8_UNCELL((p)[c]), __x = PGS_F8_UNCELL(v);        \
+      (p)[c] = ((ok) & ((__x > __a) | (__x != __x))) ? (cl_ulong)(v) : (p)[c]; }
+#else
+#define PGS_MERGE_PLAIN_MIN_F64(p,c,v,ok)   PGS_MERGE_PLAIN_MIN_U64(p,c,v,ok)
+#define PGS_MERGE_PLAIN_MAX_F64(p,c,v,ok)   PGS_MERGE_PLAIN_MAX_U64(p,c,v,ok)
+#endif
+#define PGS_MERGE_THREAD_MIN_F64(p,c,v,ok)  PGS_MERGE_PLAIN_MIN_F64(p,c,v,ok)
+#define PGS_MERGE_THREAD_MAX_F64(p,c,v,ok)  PGS_MERGE_PLAIN_MAX_F64(p,c,v,ok)
+#define PGS_MERGE_ATOMIC_MIN_F64(p,c,v,ok)  PGS_MERGE_ATOMIC_MIN_U64(p,c,v,ok)
+#define PGS_MERGE_ATOMIC_MAX_F64(p,c,v,ok)  PGS_MERGE_ATOMIC_MAX_U64(p,c,v,ok)
+
+#define PGS_MERGE_ATOMIC_SUM_I64(p,c,v,ok)                              \
+    if (ok) atomicAdd((unsigned long long *)&(p)[c], (unsigned long long)(v));
+#define PGS_MERGE_ATOMIC_SUM_F64(p,c,v,ok)                              \
+    if (ok) atomicAdd((double *)&(p)[c], __longlong_as_double((cl_long)(v)));
+#define PGS_MERGE_ATOMIC_MIN_I64(p,c,v,ok)                              \
+    if ((ok) && (cl_long)(v) < *((volatile cl_long *)&(p)[c]))          \
         atomicMin((long long *)&(p)[c], (long long)(v));
-#define PGS_MERGE_ATOMIC_MAX_I64(p,c,v)                                 \
-    if ((cl_long)(v) > *((volatile cl_long *)&(p)[c]))                  \
+#define PGS_MERGE_ATOMIC_MAX_I64(p,c,v,ok)                              \
+    if ((ok) && (cl_long)(v) > *((volatile cl_long *)&(p)[c]))          \
         atomicMax((long long *)&(p)[c], (long long)(v));
-#define PGS_MERGE_ATOMIC_MIN_U64(p,c,v)                                 \
-    if ((v) < *((volatile cl_ulong *)&(p)[c]))                          \
+/* table cells keep int4 min/max sign-extended (64-bit atomics) */
+#define PGS_MERGE_ATOMIC_MIN_I32(p,c,v,ok)  PGS_MERGE_ATOMIC_MIN_I64(p,c,(cl_long)(cl_int)(v),ok)
+#define PGS_MERGE_ATOMIC_MAX_I32(p,c,v,ok)  PGS_MERGE_ATOMIC_MAX_I64(p,c,(cl_long)(cl_int)(v),ok)
+#define PGS_MERGE_ATOMIC_MIN_U64(p,c,v,ok)                              \
+    if ((ok) && (cl_ulong)(v) < *((volatile cl_ulong *)&(p)[c]))        \
         atomicMin((unsigned long long *)&(p)[c], (unsigned long long)(v));
-#define PGS_MERGE_ATOMIC_MAX_U64(p,c,v)                                 \
-    if ((v) > *((volatile cl_ulong *)&(p)[c]))                          \
+#define PGS_MERGE_ATOMIC_MAX_U64(p,c,v,ok)                              \
+    if ((ok) && (cl_ulong)(v) > *((volatile cl_ulong *)&(p)[c]))        \
         atomicMax((unsigned long long *)&(p)[c], (unsigned long long)(v));
 
 /* 128-bit sums: (lo,hi) two's complement.  The carry out of `lo` is known
  * from the value atomicAdd returns, and additions commute, so two 64-bit
  * atomics give an exact 128-bit sum without a lock. */
 DEVFN void
-pgs_add128_PLAIN(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi)
+pgs_add128_PLAIN(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool ok)
 {
     cl_ulong    old = *plo;
 
+    vlo = ok ? vlo : 0;
+    vhi = ok ? vhi : 0;
     *plo = old + vlo;
     *phi += vhi + (*plo < old ? 1 : 0);
 }
 DEVFN void
-pgs_add128_ATOMIC(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi)
+pgs_add128_THREAD(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool ok)
 {
-    cl_ulong    old = atomicAdd((unsigned long long *)plo,
-                                (unsigned long long)vlo);
-    cl_ulong    inc = vhi + ((old + vlo) < old ? 1 : 0);
+    pgs_add128_PLAIN(plo, phi, vlo, vhi, ok);
+}
+DEVFN void
+pgs_add128_ATOMIC(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool ok)
+{
+    if (ok)
+    {
+        cl_ulong    old = atomicAdd((unsigned long long *)plo,
+                                    (unsigned long long)vlo);
+        cl_ulong    inc = vhi + ((old + vlo) < old ? 1 : 0);
 
-    if (inc != 0)
-        atomicAdd((unsigned long long *)phi, (unsigned long long)inc);
+        if (inc != 0)
+            atomicAdd((unsigned long long *)phi, (unsigned long long)inc);
+    }
 }
 
 /* row -> state (MODE = PLAIN | ATOMIC); `d` is a pagg_datum */
-#define PGS_AGGCALC_PSUM_INT(MODE,p,c,d)    PGS_MERGE_##MODE##_SUM_I64(p,c,PGS_NEWVAL_PSUM_INT(d))
-#define PGS_AGGCALC_PSUM_LONGS(MODE,p,c,d)  PGS_MERGE_##MODE##_SUM_I64(p,c,PGS_NEWVAL_PSUM_LONGS(d))
-#define PGS_AGGCALC_PSUM_LONG(MODE,p,c,d)                               \
+#define PGS_AGGCALC_PSUM_INT(MODE,p,c,d,ok)    PGS_MERGE_##MODE##_CNT_I32(p,c,PGS_NEWVAL_PSUM_INT(d),ok)
+#define PGS_AGGCALC_PSUM_LONGS(MODE,p,c,d,ok)  PGS_MERGE_##MODE##_SUM_I64(p,c,PGS_NEWVAL_PSUM_LONGS(d),ok)
+#define PGS_AGGCALC_PSUM_LONG(MODE,p,c,d,ok)                            \
     pgs_add128_##MODE(&(p)[c], &(p)[(c)+1], (cl_ulong)(d).long_val,     \
-                      (d).long_val < 0 ? ~0ULL : 0ULL);
-#define PGS_AGGCALC_PSUM_FLOAT(MODE,p,c,d)  PGS_MERGE_##MODE##_SUM_F64(p,c,PGS_NEWVAL_PSUM_FLOAT(d))
-#define PGS_AGGCALC_PSUM_DOUBLE(MODE,p,c,d) PGS_MERGE_##MODE##_SUM_F64(p,c,PGS_NEWVAL_PSUM_DOUBLE(d))
-#define PGS_AGGCALC_PMIN_SHORT(MODE,p,c,d)  PGS_MERGE_##MODE##_MIN_I64(p,c,PGS_NEWVAL_PMIN_SHORT(d))
-#define PGS_AGGCALC_PMIN_INT(MODE,p,c,d)    PGS_MERGE_##MODE##_MIN_I64(p,c,PGS_NEWVAL_PMIN_INT(d))
-#define PGS_AGGCALC_PMIN_LONG(MODE,p,c,d)   PGS_MERGE_##MODE##_MIN_I64(p,c,PGS_NEWVAL_PMIN_LONG(d))
-#define PGS_AGGCALC_PMIN_FLOAT(MODE,p,c,d)  PGS_MERGE_##MODE##_MIN_U64(p,c,PGS_NEWVAL_PMIN_FLOAT(d))
-#define PGS_AGGCALC_PMIN_DOUBLE(MODE,p,c,d) PGS_MERGE_##MODE##_MIN_U64(p,c,PGS_NEWVAL_PMIN_DOUBLE(d))
-#define PGS_AGGCALC_PMAX_SHORT(MODE,p,c,d)  PGS_MERGE_##MODE##_MAX_I64(p,c,PGS_NEWVAL_PMAX_SHORT(d))
-#define PGS_AGGCALC_PMAX_INT(MODE,p,c,d)    PGS_MERGE_##MODE##_MAX_I64(p,c,PGS_NEWVAL_PMAX_INT(d))
-#define PGS_AGGCALC_PMAX_LONG(MODE,p,c,d)   PGS_MERGE_##MODE##_MAX_I64(p,c,PGS_NEWVAL_PMAX_LONG(d))
-#define PGS_AGGCALC_PMAX_FLOAT(MODE,p,c,d)  PGS_MERGE_##MODE##_MAX_U64(p,c,PGS_NEWVAL_PMAX_FLOAT(d))
-#define PGS_AGGCALC_PMAX_DOUBLE(MODE,p,c,d) PGS_MERGE_##MODE##_MAX_U64(p,c,PGS_NEWVAL_PMAX_DOUBLE(d))
+                      (d).long_val < 0 ? ~0ULL : 0ULL, (ok));
+#define PGS_AGGCALC_PSUM_FLOAT(MODE,p,c,d,ok)  PGS_MERGE_##MODE##_SUM_F64(p,c,PGS_NEWVAL_PSUM_FLOAT(d),ok)
+#define PGS_AGGCALC_PSUM_DOUBLE(MODE,p,c,d,ok) PGS_MERGE_##MODE##_SUM_F64(p,c,PGS_NEWVAL_PSUM_DOUBLE(d),ok)
+#define PGS_AGGCALC_PMIN_SHORT(MODE,p,c,d,ok)  PGS_MERGE_##MODE##_MIN_I32(p,c,PGS_NEWVAL_PMIN_SHORT(d),ok)
+#define PGS_AGGCALC_PMIN_INT(MODE,p,c,d,ok)    PGS_MERGE_##MODE##_MIN_I32(p,c,PGS_NEWVAL_PMIN_INT(d),ok)
+#define PGS_AGGCALC_PMIN_LONG(MODE,p,c,d,ok)   PGS_MERGE_##MODE##_MIN_I64(p,c,PGS_NEWVAL_PMIN_LONG(d),ok)
+#define PGS_AGGCALC_PMIN_FLOAT(MODE,p,c,d,ok)  PGS_MERGE_##MODE##_MIN_F64(p,c,PGS_NEWVAL_PMIN_FLOAT(d),ok)
+#define PGS_AGGCALC_PMIN_DOUBLE(MODE,p,c,d,ok) PGS_MERGE_##MODE##_MIN_F64(p,c,PGS_NEWVAL_PMIN_DOUBLE(d),ok)
+#define PGS_AGGCALC_PMAX_SHORT(MODE,p,c,d,ok)  PGS_MERGE_##MODE##_MAX_I32(p,c,PGS_NEWVAL_PMAX_SHORT(d),ok)
+#define PGS_AGGCALC_PMAX_INT(MODE,p,c,d,ok)    PGS_MERGE_##MODE##_MAX_I32(p,c,PGS_NEWVAL_PMAX_INT(d),ok)
+#define PGS_AGGCALC_PMAX_LONG(MODE,p,c,d,ok)   PGS_MERGE_##MODE##_MAX_I64(p,c,PGS_NEWVAL_PMAX_LONG(d),ok)
+#define PGS_AGGCALC_PMAX_FLOAT(MODE,p,c,d,ok)  PGS_MERGE_##MODE##_MAX_F64(p,c,PGS_NEWVAL_PMAX_FLOAT(d),ok)
+#define PGS_AGGCALC_PMAX_DOUBLE(MODE,p,c,d,ok) PGS_MERGE_##MODE##_MAX_F64(p,c,PGS_NEWVAL_PMAX_DOUBLE(d),ok)
 
 /* state -> state (q = source cells) */
-#define PGS_AGGMERGE_PSUM_INT(MODE,p,c,q)    PGS_MERGE_##MODE##_SUM_I64(p,c,(q)[c])
-#define PGS_AGGMERGE_PSUM_LONGS(MODE,p,c,q)  PGS_MERGE_##MODE##_SUM_I64(p,c,(q)[c])
-#define PGS_AGGMERGE_PSUM_LONG(MODE,p,c,q)   pgs_add128_##MODE(&(p)[c], &(p)[(c)+1], (q)[c], (q)[(c)+1]);
-#define PGS_AGGMERGE_PSUM_FLOAT(MODE,p,c,q)  PGS_MERGE_##MODE##_SUM_F64(p,c,(q)[c])
-#define PGS_AGGMERGE_PSUM_DOUBLE(MODE,p,c,q) PGS_MERGE_##MODE##_SUM_F64(p,c,(q)[c])
-#define PGS_AGGMERGE_PMIN_SHORT(MODE,p,c,q)  PGS_MERGE_##MODE##_MIN_I64(p,c,(q)[c])
-#define PGS_AGGMERGE_PMIN_INT(MODE,p,c,q)    PGS_MERGE_##MODE##_MIN_I64(p,c,(q)[c])
-#define PGS_AGGMERGE_PMIN_LONG(MODE,p,c,q)   PGS_MERGE_##MODE##_MIN_I64(p,c,(q)[c])
-#define PGS_AGGMERGE_PMIN_FLOAT(MODE,p,c,q)  PGS_MERGE_##MODE##_MIN_U64(p,c,(q)[c])
-#define PGS_AGGMERGE_PMIN_DOUBLE(MODE,p,c,q) PGS_MERGE_##MODE##_MIN_U64(p,c,(q)[c])
-#define PGS_AGGMERGE_PMAX_SHORT(MODE,p,c,q)  PGS_MERGE_##MODE##_MAX_I64(p,c,(q)[c])
-#define PGS_AGGMERGE_PMAX_INT(MODE,p,c,q)    PGS_MERGE_##MODE##_MAX_I64(p,c,(q)[c])
-#define PGS_AGGMERGE_PMAX_LONG(MODE,p,c,q)   PGS_MERGE_##MODE##_MAX_I64(p,c,(q)[c])
-#define PGS_AGGMERGE_PMAX_FLOAT(MODE,p,c,q)  PGS_MERGE_##MODE##_MAX_U64(p,c,(q)[c])
-#define PGS_AGGMERGE_PMAX_DOUBLE(MODE,p,c,q) PGS_MERGE_##MODE##_MAX_U64(p,c,(q)[c])
+#define PGS_AGGMERGE_PSUM_INT(MODE,p,c,q,ok)    PGS_MERGE_##MODE##_SUM_I64(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PSUM_LONGS(MODE,p,c,q,ok)  PGS_MERGE_##MODE##_SUM_I64(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PSUM_LONG(MODE,p,c,q,ok) pgs_add128_##MODE(&(p)[c], &(p)[(c)+1], (q)[c], (q)[(c)+1], (ok));
+#define PGS_AGGMERGE_PSUM_FLOAT(MODE,p,c,q,ok)  PGS_MERGE_##MODE##_SUM_F64(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PSUM_DOUBLE(MODE,p,c,q,ok) PGS_MERGE_##MODE##_SUM_F64(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PMIN_SHORT(MODE,p,c,q,ok)  PGS_MERGE_##MODE##_MIN_I32(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PMIN_INT(MODE,p,c,q,ok)    PGS_MERGE_##MODE##_MIN_I32(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PMIN_LONG(MODE,p,c,q,ok)   PGS_MERGE_##MODE##_MIN_I64(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PMIN_FLOAT(MODE,p,c,q,ok)  PGS_MERGE_##MODE##_MIN_F64(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PMIN_DOUBLE(MODE,p,c,q,ok) PGS_MERGE_##MODE##_MIN_F64(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PMAX_SHORT(MODE,p,c,q,ok)  PGS_MERGE_##MODE##_MAX_I32(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PMAX_INT(MODE,p,c,q,ok)    PGS_MERGE_##MODE##_MAX_I32(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PMAX_LONG(MODE,p,c,q,ok)   PGS_MERGE_##MODE##_MAX_I64(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PMAX_FLOAT(MODE,p,c,q,ok)  PGS_MERGE_##MODE##_MAX_F64(p,c,(q)[c],ok)
+#define PGS_AGGMERGE_PMAX_DOUBLE(MODE,p,c,q,ok) PGS_MERGE_##MODE##_MAX_F64(p,c,(q)[c],ok)
 
 /* per-row admission check: rows whose float inputs could overflow a sum in
  * some summation order are left to the CPU (row level) */
@@ -320,19 +388,32 @@ pgs_add128_ATOMIC(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi)
 #define PGS_X_CHECK(i,c,OP,TYPE)                                        \
     if (!row.agg[i].isnull) { PGS_AGGCHECK_##OP##_##TYPE(row.agg[i]) }
 #define PGS_X_CALC_PLAIN(i,c,OP,TYPE)                                   \
-    if (!row.agg[i].isnull) {                                           \
-        PGS_AGGCALC_##OP##_##TYPE(PLAIN,cells,c,row.agg[i])             \
-        nnmask |= (1U << (i));                                          \
-    }
+    { bool __ok = valid && !row.agg[i].isnull;                          \
+      PGS_AGGCALC_##OP##_##TYPE(PLAIN,cells,c,row.agg[i],__ok)          \
+      nnmask |= (__ok ? (1U << (i)) : 0U); }
+#define PGS_X_CALC_THREAD(i,c,OP,TYPE)                                  \
+    { bool __ok = valid & !row.agg[i].isnull;                           \
+      PGS_AGGCALC_##OP##_##TYPE(THREAD,cells,c,row.agg[i],__ok) }
+/* "saw a non-NULL input" per class of aggregates that share the NULL-ness of
+ * one argument (GPUPREAGG_NNCLASS_LIST(_) = _(representative agg, bit mask)) */
+#define PGS_X_NNCLASS(rep,mask)                                         \
+    nnmask |= ((valid & !row.agg[rep].isnull) ? (mask) : 0U);
+#define PGS_X_NNCLASS_COUNT(rep,mask)   + 1
+#define PGS_NUM_NNCLASSES   (0 GPUPREAGG_NNCLASS_LIST(PGS_X_NNCLASS_COUNT))
+#define PGS_X_NNCLASS_FLAG(rep,mask)                                    \
+    nnflag[__k] = nnflag[__k] | (valid & !row.agg[rep].isnull); __k++;
+#define PGS_X_NNCLASS_MASK(rep,mask)                                    \
+    nnmask |= (nnflag[__k] ? (mask) : 0U); __k++;
 #define PGS_X_CALC_ATOMIC(i,c,OP,TYPE)                                  \
-    if (!row.agg[i].isnull) {                                           \
-        PGS_AGGCALC_##OP##_##TYPE(ATOMIC,cells,c,row.agg[i])            \
-        nnmask |= (1U << (i));                                          \
-    }
+    { bool __ok = valid && !row.agg[i].isnull;                          \
+      PGS_AGGCALC_##OP##_##TYPE(ATOMIC,cells,c,row.agg[i],__ok)         \
+      nnmask |= (__ok ? (1U << (i)) : 0U); }
 #define PGS_X_MERGE_PLAIN(i,c,OP,TYPE)                                  \
-    if (src_nn & (1U << (i))) { PGS_AGGMERGE_##OP##_##TYPE(PLAIN,cells,c,src) }
+    { bool __ok = ((src_nn >> (i)) & 1U) != 0;                          \
+      PGS_AGGMERGE_##OP##_##TYPE(PLAIN,cells,c,src,__ok) }
 #define PGS_X_MERGE_ATOMIC(i,c,OP,TYPE)                                 \
-    if (src_nn & (1U << (i))) { PGS_AGGMERGE_##OP##_##TYPE(ATOMIC,cells,c,src) }
+    { bool __ok = ((src_nn >> (i)) & 1U) != 0;                          \
+      PGS_AGGMERGE_##OP##_##TYPE(ATOMIC,cells,c,src,__ok) }
 
 template <typename CELLS>
 DEVFN void
@@ -351,16 +432,38 @@ gpupreagg_aggcheck(cl_int *errcode, const pagg_row &row)
  * (the reference's generated switch(resno), gpupreagg.c:1319-1440) */
 template <typename CELLS>
 DEVFN cl_uint
-gpupreagg_aggcalc_plain(CELLS cells, const pagg_row &row)
+gpupreagg_aggcalc_plain(CELLS cells, const pagg_row &row, bool valid)
 {
     cl_uint nnmask = 0;
     GPUPREAGG_AGG_LIST(PGS_X_CALC_PLAIN)
+    return nnmask;
+}
+/* per-row accumulation into thread registers (no-group kernel); the
+ * "non-NULL seen" flags are kept as predicates over the rows of one loop
+ * iteration and folded into the bit mask by pgs_nnflags_to_mask() */
+DEVFN void
+gpupreagg_aggcalc_thread(cl_ulong *cells, const pagg_row &row, bool valid,
+                         bool *nnflag)
+{
+    int __k = 0;
+    GPUPREAGG_AGG_LIST(PGS_X_CALC_THREAD)
+    GPUPREAGG_NNCLASS_LIST(PGS_X_NNCLASS_FLAG)
+    (void)__k;
+}
+DEVFN cl_uint
+pgs_nnflags_to_mask(const bool *nnflag)
+{
+    cl_uint nnmask = 0;
+    int __k = 0;
+    GPUPREAGG_NNCLASS_LIST(PGS_X_NNCLASS_MASK)
+    (void)__k;
     return nnmask;
 }
 template <typename CELLS>
 DEVFN cl_uint
 gpupreagg_aggcalc_atomic(CELLS cells, const pagg_row &row)
 {
+    const bool valid = true;
     cl_uint nnmask = 0;
     GPUPREAGG_AGG_LIST(PGS_X_CALC_ATOMIC)
     return nnmask;
@@ -401,24 +504,26 @@ gpupreagg_aggmerge_atomic(CELLS cells, SRC src, cl_uint src_nn)
  * ------------------------------------------------------------------ */
 #define PGS_ALIGN128(x)     (((x) + 127U) & ~127U)
 
-__host__ __device__ constexpr cl_uint
-pgs_stage_val_off(int slot)
+/* tile_rows is a multiple of 1024, so every piece is 128-byte aligned */
+DEVFN cl_uint
+pgs_stage_val_off(int slot, cl_uint tile_rows)
 {
     cl_uint off = 0;
+#pragma unroll
     for (int s = 0; s < slot; s++)
-        off += PGS_ALIGN128((cl_uint)GPUPREAGG_TILE_ROWS * GPUPREAGG_INCOL_ATTLEN(s));
+        off += tile_rows * GPUPREAGG_INCOL_ATTLEN(s);
     return off;
 }
-__host__ __device__ constexpr cl_uint
-pgs_stage_nul_off(int slot)
+DEVFN cl_uint
+pgs_stage_nul_off(int slot, cl_uint tile_rows)
 {
-    return pgs_stage_val_off(GPUPREAGG_NUM_INCOLS) +
-        (cl_uint)slot * PGS_ALIGN128(GPUPREAGG_TILE_ROWS / 8);
+    return pgs_stage_val_off(GPUPREAGG_NUM_INCOLS, tile_rows) +
+        (cl_uint)slot * (tile_rows / 8);
 }
-#define PGS_STAGE_BYTES     pgs_stage_nul_off(GPUPREAGG_NUM_INCOLS)
-/* head of dynamic smem: 2 x NUM_STAGES mbarriers, column positions */
+#define PGS_STAGE_BYTES(tile_rows)  pgs_stage_nul_off(GPUPREAGG_NUM_INCOLS, (tile_rows))
+/* head of dynamic smem: 2 x MAX_STAGES mbarriers, column positions */
 #define PGS_SMEM_HEAD_BYTES \
-    PGS_ALIGN128(16 * GPUPREAGG_NUM_STAGES + 8 * PGS_MAX(GPUPREAGG_NUM_INCOLS,1) + 64)
+    PGS_ALIGN128(16 * GPUPREAGG_MAX_STAGES + 8 * PGS_MAX(GPUPREAGG_NUM_INCOLS,1) + 64)
 
 /* ------------------------------------------------------------------
  * mbarrier + bulk async copy (TMA engine, 1-D) wrappers
@@ -780,8 +885,8 @@ pgs_hash_keyvals(const cl_ulong *keyvals, cl_uint knull)
  * ------------------------------------------------------------------ */
 struct pgs_smem_head
 {
-    cl_ulong    full_bar[GPUPREAGG_NUM_STAGES];
-    cl_ulong    empty_bar[GPUPREAGG_NUM_STAGES];
+    cl_ulong    full_bar[GPUPREAGG_MAX_STAGES];
+    cl_ulong    empty_bar[GPUPREAGG_MAX_STAGES];
     cl_uint     val_pos[PGS_MAX(GPUPREAGG_NUM_INCOLS, 1)];  /* kern_colpos copy */
     cl_uint     nul_pos[PGS_MAX(GPUPREAGG_NUM_INCOLS, 1)];
     cl_uint     sh_nused;
@@ -795,13 +900,13 @@ struct pgs_smem_head
 #define PGS_X_INCOL_ISSUE(slot,colidx,attlen)                           \
     {                                                                   \
         cl_uint nb = ((rows * (attlen)) + 15U) & ~15U;                  \
-        pgs_bulk_g2s(stage_base + pgs_stage_val_off(slot),              \
+        pgs_bulk_g2s(stage_base + pgs_stage_val_off(slot, tile_rows),              \
                      (const char *)kds_in + head->val_pos[slot] +       \
                      (cl_ulong)row0 * (attlen), nb, &head->full_bar[stage]); \
         if (head->nul_pos[slot] != 0)                                   \
         {                                                               \
             cl_uint mb = (((rows + 7U) >> 3) + 15U) & ~15U;             \
-            pgs_bulk_g2s(stage_base + pgs_stage_nul_off(slot),          \
+            pgs_bulk_g2s(stage_base + pgs_stage_nul_off(slot, tile_rows),          \
                          (const char *)kds_in + head->nul_pos[slot] +   \
                          (row0 >> 3), mb, &head->full_bar[stage]);      \
         }                                                               \
@@ -813,10 +918,35 @@ struct pgs_smem_head
         txbytes += (((rows + 7U) >> 3) + 15U) & ~15U;
 
 #define PGS_X_INCOL_VIEW(slot,colidx,attlen)                            \
-    tile.val_off[slot] = stage_off + pgs_stage_val_off(slot);           \
+    tile.val_off[slot] = stage_off + pgs_stage_val_off(slot, tile_rows);           \
     tile.nul_off[slot] = (head->nul_pos[slot] != 0                      \
-                          ? stage_off + pgs_stage_nul_off(slot)         \
+                          ? stage_off + pgs_stage_nul_off(slot, tile_rows)         \
                           : KERN_TILE_NO_NULLMAP);
+
+#define PGS_CONSUME_ROW(j)                                              \
+    {                                                                   \
+        pagg_row    prow;                                               \
+        bool valid = pgs_eval_row(kparams, rr[j], kds_in, row0 + r + (j), \
+                                  recheck_map, ctx, prow);              \
+        if (GPUPREAGG_NUM_KEYS == 0)                                    \
+            gpupreagg_aggcalc_thread(acc, prow, valid, nnflag);         \
+        else if (valid)                                                 \
+            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx);      \
+    }
+
+/* phase 1 of the staged consumer loop: 4 adjacent rows of one column */
+#define PGS_X_INCOL_LOAD4(slot,colidx,attlen)                           \
+    pgs_rowload<attlen>::load4(__pgs_smem + tile.val_off[slot] +        \
+                               r * (attlen),                            \
+                               rr[0].v[slot], rr[1].v[slot],            \
+                               rr[2].v[slot], rr[3].v[slot]);           \
+    {                                                                   \
+        cl_uint __vb = 0xFU;                                            \
+        if (tile.nul_off[slot] != KERN_TILE_NO_NULLMAP)                 \
+            __vb = *((const cl_uint *)(__pgs_smem + tile.nul_off[slot]) + (r >> 5)) >> (r & 31); \
+        rr[0].vbits[slot] = __vb;       rr[1].vbits[slot] = __vb >> 1;  \
+        rr[2].vbits[slot] = __vb >> 2;  rr[3].vbits[slot] = __vb >> 3;  \
+    }
 
 #define PGS_X_INCOL_GVIEW(slot,colidx,attlen)                           \
     gtile.val_ptr[slot] = (const char *)kds_in +                        \
@@ -856,6 +986,52 @@ pgs_group_add_row(const pgs_gstate &gs, const pgs_sh_table &sh,
     }
 }
 
+/* threads of the CTA -> thread 0, always combined in the same order: lanes by
+ * a butterfly where the lower lane merges, then warps in index order.
+ * `scratch`: shared memory nobody else uses any more, 8*(1+NCELLS)*nwarps. */
+DEVFN void
+pgs_block_reduce(cl_ulong *acc, cl_uint &acc_nn, cl_ulong *scratch)
+{
+    const cl_uint   warp_id = threadIdx.x >> 5;
+    const cl_uint   lane_id = threadIdx.x & 31;
+    const cl_uint   nwarps = blockDim.x >> 5;
+    const int       W = 1 + GPUPREAGG_NUM_CELLS;
+
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        cl_ulong    src[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+        cl_uint     src_nn = __shfl_xor_sync(0xffffffffU, acc_nn, d);
+#pragma unroll
+        for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+            src[c] = __shfl_xor_sync(0xffffffffU, acc[c], d);
+        if ((lane_id & d) == 0)
+        {
+            gpupreagg_aggmerge_plain(acc, src, src_nn);
+            acc_nn |= src_nn;
+        }
+    }
+    __syncthreads();        /* scratch is free: every tile was consumed */
+    if (lane_id == 0)
+    {
+        scratch[warp_id * W] = acc_nn;
+#pragma unroll
+        for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+            scratch[warp_id * W + 1 + c] = acc[c];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (cl_uint w = 1; w < nwarps; w++)
+        {
+            cl_uint src_nn = (cl_uint)scratch[w * W];
+            gpupreagg_aggmerge_plain(acc, scratch + w * W + 1, src_nn);
+            acc_nn |= src_nn;
+        }
+    }
+    __syncthreads();
+}
+
 /* epilogue of both main kernels.  `scratch` is shared memory nobody else
  * uses any more, at least 8 * (1 + NCELLS) * nwarps bytes. */
 DEVFN void
@@ -864,76 +1040,55 @@ pgs_main_epilogue(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
                   cl_uint *p_is_last, cl_ulong *acc, cl_uint acc_nn,
                   pgs_row_ctx &ctx)
 {
-    const cl_uint   warp_id = threadIdx.x >> 5;
-    const cl_uint   lane_id = threadIdx.x & 31;
-    const cl_uint   nwarps = blockDim.x >> 5;
     const int       W = 1 + GPUPREAGG_NUM_CELLS;
 
     if (GPUPREAGG_NUM_KEYS == 0)
     {
-        /* lanes: butterfly where the lower lane merges, so lane 0 ends up
-         * with the warp's state, always combined in the same order */
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1)
-        {
-            cl_ulong    src[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
-            cl_uint     src_nn = __shfl_xor_sync(0xffffffffU, acc_nn, d);
-#pragma unroll
-            for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
-                src[c] = __shfl_xor_sync(0xffffffffU, acc[c], d);
-            if ((lane_id & d) == 0)
-            {
-                gpupreagg_aggmerge_plain(acc, src, src_nn);
-                acc_nn |= src_nn;
-            }
-        }
-        __syncthreads();        /* every tile consumed: scratch is free */
-        if (lane_id == 0)
-        {
-            scratch[warp_id * W] = acc_nn;
-#pragma unroll
-            for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
-                scratch[warp_id * W + 1 + c] = acc[c];
-        }
-        __syncthreads();
+        cl_ulong   *mine = gs.ng_partial + (cl_ulong)blockIdx.x * W;
+
+        /* threads -> CTA state (thread 0) */
+        pgs_block_reduce(acc, acc_nn, scratch);
         if (threadIdx.x == 0)
         {
-            cl_ulong   *mine = gs.ng_partial + (cl_ulong)blockIdx.x * W;
             cl_uint     ticket;
 
-            /* warps in index order */
-            for (cl_uint w = 1; w < nwarps; w++)
-            {
-                cl_uint src_nn = (cl_uint)scratch[w * W];
-                gpupreagg_aggmerge_plain(acc, scratch + w * W + 1, src_nn);
-                acc_nn |= src_nn;
-            }
             mine[0] = acc_nn;
 #pragma unroll
             for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
                 mine[1 + c] = acc[c];
             __threadfence();
             ticket = atomicAdd(gs.ng_ticket, 1U);
-            if (ticket == gridDim.x - 1)
+            *p_is_last = (ticket == gridDim.x - 1 ? 1U : 0U);
+        }
+        __syncthreads();
+        if (*p_is_last)
+        {
+            /* last CTA: fold the CTA partials of this launch into the
+             * persistent state row.  Thread t takes partials t, t+B, ... in
+             * order and the block reduction has a fixed shape, so the result
+             * does not depend on which CTA happened to finish last. */
+            __threadfence();
+            pgs_cells_init(acc);
+            acc_nn = 0;
+            for (cl_uint b = threadIdx.x; b < gridDim.x; b += blockDim.x)
             {
-                /* last CTA: fold all CTA partials into the persistent state
-                 * row in CTA order => the result does not depend on timing */
-                cl_ulong   *state = gs.ng_state;
-                cl_uint     nn = (cl_uint)state[0];
-
-                __threadfence();
-                for (cl_uint b = 0; b < gridDim.x; b++)
-                {
-                    const cl_ulong *part = gs.ng_partial + (cl_ulong)b * W;
-                    cl_uint     src_nn = (cl_uint)__ldcg(part);
-                    cl_ulong    src[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+                const cl_ulong *part = gs.ng_partial + (cl_ulong)b * W;
+                cl_uint     src_nn = (cl_uint)__ldcg(part);
+                cl_ulong    src[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
 #pragma unroll
-                    for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
-                        src[c] = __ldcg(part + 1 + c);
-                    gpupreagg_aggmerge_plain(state + 1, src, src_nn);
-                    nn |= src_nn;
-                }
-                state[0] = nn;
+                for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                    src[c] = __ldcg(part + 1 + c);
+                gpupreagg_aggmerge_plain(acc, src, src_nn);
+                acc_nn |= src_nn;
+            }
+            __syncthreads();
+            pgs_block_reduce(acc, acc_nn, scratch);
+            if (threadIdx.x == 0)
+            {
+                cl_ulong   *state = gs.ng_state;
+
+                gpupreagg_aggmerge_plain(state + 1, acc, acc_nn);
+                state[0] = (cl_uint)state[0] | acc_nn;
                 *gs.ng_ticket = 0;
             }
         }
@@ -990,18 +1145,20 @@ pgs_main_epilogue(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
  * warp + GPUPREAGG_CONSUMER_WARPS consumer warps.
  */
 extern "C" __global__ void
-__launch_bounds__(GPUPREAGG_BLOCK_THREADS)
+__launch_bounds__(GPUPREAGG_BLOCK_THREADS, GPUPREAGG_MIN_CTAS)
 gpupreagg_main(kern_gpupreagg *kgpreagg,
                const kern_data_store *kds_in,
                pgs_gstate gs,
                cl_uint *recheck_map,
-               cl_uint sh_nslots)
+               cl_uint sh_nslots,
+               cl_uint tile_rows,
+               cl_uint nstages)
 {
     pgs_smem_head  *head = (pgs_smem_head *)__pgs_smem;
     unsigned char  *stages = __pgs_smem + PGS_SMEM_HEAD_BYTES;
     const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF(kgpreagg);
     const cl_uint   nrows = kds_in->nitems;
-    const cl_uint   ntiles = (nrows + GPUPREAGG_TILE_ROWS - 1) / GPUPREAGG_TILE_ROWS;
+    const cl_uint   ntiles = (nrows + tile_rows - 1) / tile_rows;
     const cl_uint   warp_id = threadIdx.x >> 5;
     const cl_uint   lane_id = threadIdx.x & 31;
     cl_ulong        acc[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
@@ -1012,13 +1169,13 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
     ctx.nfiltered = 0;
     ctx.nrecheck = 0;
     ctx.errcode = StromError_Success;
-    sh.base = PGS_SMEM_HEAD_BYTES + GPUPREAGG_NUM_STAGES * PGS_STAGE_BYTES;
+    sh.base = PGS_SMEM_HEAD_BYTES + nstages * PGS_STAGE_BYTES(tile_rows);
     sh.nslots = (GPUPREAGG_NUM_KEYS > 0 ? sh_nslots : 0);
     pgs_cells_init(acc);
 
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < GPUPREAGG_NUM_STAGES; s++)
+        for (cl_uint s = 0; s < nstages; s++)
         {
             pgs_mbar_init(&head->full_bar[s], 1);
             pgs_mbar_init(&head->empty_bar[s], GPUPREAGG_CONSUMER_WARPS);
@@ -1040,11 +1197,11 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
         {
             if (lane_id == 0)
             {
-                cl_uint stage = it % GPUPREAGG_NUM_STAGES;
-                cl_uint phase = (it / GPUPREAGG_NUM_STAGES) & 1;
-                cl_uint row0 = t * GPUPREAGG_TILE_ROWS;
-                cl_uint rows = min((cl_uint)GPUPREAGG_TILE_ROWS, nrows - row0);
-                unsigned char *stage_base = stages + stage * PGS_STAGE_BYTES;
+                cl_uint stage = it % nstages;
+                cl_uint phase = (it / nstages) & 1;
+                cl_uint row0 = t * tile_rows;
+                cl_uint rows = min(tile_rows, nrows - row0);
+                unsigned char *stage_base = stages + stage * PGS_STAGE_BYTES(tile_rows);
                 cl_uint txbytes = 0;
 
                 pgs_mbar_wait(&head->empty_bar[stage], phase ^ 1);
@@ -1064,11 +1221,11 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
 
         for (cl_uint t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
         {
-            cl_uint stage = it % GPUPREAGG_NUM_STAGES;
-            cl_uint phase = (it / GPUPREAGG_NUM_STAGES) & 1;
-            cl_uint row0 = t * GPUPREAGG_TILE_ROWS;
-            cl_uint rows = min((cl_uint)GPUPREAGG_TILE_ROWS, nrows - row0);
-            cl_uint stage_off = PGS_SMEM_HEAD_BYTES + stage * PGS_STAGE_BYTES;
+            cl_uint stage = it % nstages;
+            cl_uint phase = (it / nstages) & 1;
+            cl_uint row0 = t * tile_rows;
+            cl_uint rows = min(tile_rows, nrows - row0);
+            cl_uint stage_off = PGS_SMEM_HEAD_BYTES + stage * PGS_STAGE_BYTES(tile_rows);
             kern_tile_smem tile;
 
             tile.row0 = row0;
@@ -1076,17 +1233,33 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
             (void)stage_off;
             pgs_mbar_wait(&head->full_bar[stage], phase);
 
-            for (cl_uint r = ctid; r < rows; r += GPUPREAGG_CONSUMER_THREADS)
+            /* each thread takes 4 consecutive rows: phase 1 pulls them out of
+             * the stage with 128-bit shared memory loads, phase 2 evaluates
+             * them one by one from registers */
+            for (cl_uint r = ctid * 4; r < rows; r += GPUPREAGG_CONSUMER_THREADS * 4)
             {
-                pagg_row    prow;
+                kern_row_regs rr[4];
+                bool        nnflag[PGS_MAX(PGS_NUM_NNCLASSES, 1)];
 
-                if (!pgs_eval_row(kparams, tile, kds_in, row0 + r,
-                                  recheck_map, ctx, prow))
-                    continue;
-                if (GPUPREAGG_NUM_KEYS == 0)
-                    acc_nn |= gpupreagg_aggcalc_plain(acc, prow);
+#pragma unroll
+                for (int k = 0; k < PGS_MAX(PGS_NUM_NNCLASSES, 1); k++)
+                    nnflag[k] = false;
+                GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+                if (r + 4 <= rows)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        PGS_CONSUME_ROW(j)
+                }
                 else
-                    pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx);
+                {
+#pragma unroll
+                    for (int j = 0; j < 3; j++)
+                        if (r + j < rows)
+                            PGS_CONSUME_ROW(j)
+                }
+                if (GPUPREAGG_NUM_KEYS == 0)
+                    acc_nn |= pgs_nnflags_to_mask(nnflag);
             }
             __syncwarp();
             if (lane_id == 0)
@@ -1108,7 +1281,9 @@ gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
                       const kern_data_store *kds_in,
                       pgs_gstate gs,
                       cl_uint *recheck_map,
-                      cl_uint sh_nslots)
+                      cl_uint sh_nslots,
+                      cl_uint tile_rows,
+                      cl_uint nstages)
 {
     pgs_smem_head  *head = (pgs_smem_head *)__pgs_smem;
     unsigned char  *stages = __pgs_smem + PGS_SMEM_HEAD_BYTES;
@@ -1126,7 +1301,7 @@ gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
     ctx.nfiltered = 0;
     ctx.nrecheck = 0;
     ctx.errcode = StromError_Success;
-    sh.base = PGS_SMEM_HEAD_BYTES + GPUPREAGG_NUM_STAGES * PGS_STAGE_BYTES;
+    sh.base = PGS_SMEM_HEAD_BYTES + nstages * PGS_STAGE_BYTES(tile_rows);
     sh.nslots = (GPUPREAGG_NUM_KEYS > 0 ? sh_nslots : 0);
     pgs_cells_init(acc);
     GPUPREAGG_INCOL_LIST(PGS_X_INCOL_GVIEW)
@@ -1152,11 +1327,10 @@ gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
                 ctx.errcode = StromError_DataStoreOutOfRange;
             continue;
         }
-        if (!pgs_eval_row(kparams, gtile, kds_in, row, recheck_map, ctx, prow))
-            continue;
+        bool valid = pgs_eval_row(kparams, gtile, kds_in, row, recheck_map, ctx, prow);
         if (GPUPREAGG_NUM_KEYS == 0)
-            acc_nn |= gpupreagg_aggcalc_plain(acc, prow);
-        else
+            acc_nn |= gpupreagg_aggcalc_plain(acc, prow, valid);
+        else if (valid)
             pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx);
     }
     pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
@@ -1288,10 +1462,10 @@ pgs_piece_i128(cl_ulong lo, cl_ulong hi, cl_uint r)
       datum = cells[c]; }
 #define PGS_OUT_MINMAX_FLOAT(i,c)                                       \
     { isnull = !(nn & (1U << (i)));                                     \
-      datum = (cl_ulong)__float_as_uint((float)pgs_f8_from_sortkey(cells[c])); }
+      datum = (cl_ulong)__float_as_uint((float)PGS_F8_UNCELL(cells[c])); }
 #define PGS_OUT_MINMAX_DOUBLE(i,c)                                      \
     { isnull = !(nn & (1U << (i)));                                     \
-      datum = (cl_ulong)__double_as_longlong(pgs_f8_from_sortkey(cells[c])); }
+      datum = (cl_ulong)__double_as_longlong(PGS_F8_UNCELL(cells[c])); }
 #define PGS_OUT_PMIN_SHORT(i,c)     PGS_OUT_MINMAX_SHORT(i,c)
 #define PGS_OUT_PMIN_INT(i,c)       PGS_OUT_MINMAX_INT(i,c)
 #define PGS_OUT_PMIN_LONG(i,c)      PGS_OUT_MINMAX_LONG(i,c)
@@ -1460,9 +1634,9 @@ gpupreagg_describe(pgs_kern_desc *desc)
     desc->num_cells = GPUPREAGG_NUM_CELLS;
     desc->num_outcols = GPUPREAGG_NUM_OUTCOLS;
     desc->slot_bytes = PGS_SLOT_BYTES;
-    desc->tile_rows = GPUPREAGG_TILE_ROWS;
-    desc->num_stages = GPUPREAGG_NUM_STAGES;
-    desc->stage_bytes = PGS_STAGE_BYTES;
+    desc->tile_rows = 1024;             /* granule of the tile size */
+    desc->num_stages = GPUPREAGG_MAX_STAGES;
+    desc->stage_bytes = PGS_STAGE_BYTES(1024);  /* per 1024 rows */
     desc->static_smem_bytes = PGS_SMEM_HEAD_BYTES;
     desc->block_threads = GPUPREAGG_BLOCK_THREADS;
     desc->sh_slot_bytes = PGS_SH_SLOT_BYTES;
