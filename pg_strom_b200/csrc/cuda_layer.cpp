@@ -135,7 +135,7 @@ program_options(int extra_flags)
     std::string o;
     (void)extra_flags;
     o += "warps=" + std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "16");
-    o += ";minctas=" + std::string(getenv("PGSTROM_MIN_CTAS") ? getenv("PGSTROM_MIN_CTAS") : "2");
+    o += ";minctas=" + std::string(getenv("PGSTROM_MIN_CTAS") ? getenv("PGSTROM_MIN_CTAS") : "1");
     o += ";opt=" + std::string(pgs::guc_bool("pg_strom.devprog_enable_optimization") ? "1" : "0");
     return o;
 }
@@ -152,7 +152,7 @@ nvrtc_build(pgs_program *prog)
     std::string d_warps = "-DGPUPREAGG_CONSUMER_WARPS=" +
         std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "16");
     std::string d_rpt = "-DGPUPREAGG_MIN_CTAS=" +
-        std::string(getenv("PGSTROM_MIN_CTAS") ? getenv("PGSTROM_MIN_CTAS") : "2");
+        std::string(getenv("PGSTROM_MIN_CTAS") ? getenv("PGSTROM_MIN_CTAS") : "1");
     std::vector<const char *> opts = {
         "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
         "-device-int128", "--fmad=false",
@@ -780,12 +780,13 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
             s->sh_nslots = (cl_uint)nslots;
             table_bytes = nslots * s->desc.sh_slot_bytes;
         }
-        /* staging ring: prefer >= 3 stages, then the largest tile that fits
-         * two CTAs per SM (no-group) or one (with a big table) */
+        /* staging ring: one CTA (1 producer + 16 consumer warps) per SM owns
+         * the whole shared memory; prefer 3 stages of 4096 rows (measured
+         * best on B200), shrink the tile, then the depth, to fit */
         {
             size_t budget = smem_max - head - table_bytes - 1024;
-            size_t target = (table_bytes > 64 * 1024 ? budget : (smem_max - 2048) / 2 - head - table_bytes);
-            cl_uint tile = 2048, stages = 4;
+            size_t target = budget;
+            cl_uint tile = 4096, stages = 3;
             const char *et = getenv("PGSTROM_TILE_ROWS");
             const char *es = getenv("PGSTROM_NUM_STAGES");
             if (target > budget)

@@ -124,8 +124,9 @@ struct kern_tile_gmem
 struct kern_row_regs
 {
     cl_ulong    v[GPUPREAGG_NUM_INCOLS > 0 ? GPUPREAGG_NUM_INCOLS : 1];
-    /* bit 0 = validity (NOT NULL) of this row, per staged column */
+    /* bit `shift` = validity (NOT NULL) of this row, per staged column */
     cl_uint     vbits[GPUPREAGG_NUM_INCOLS > 0 ? GPUPREAGG_NUM_INCOLS : 1];
+    int         shift;
 
     template <typename T>
     __device__ __forceinline__ bool
@@ -134,7 +135,7 @@ struct kern_row_regs
         union { cl_ulong u; T t; } cv;
         cv.u = v[slot];
         out = cv.t;
-        return (vbits[slot] & 1U) != 0;
+        return ((vbits[slot] >> shift) & 1U) != 0;
     }
 };
 

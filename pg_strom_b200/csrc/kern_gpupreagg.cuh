@@ -52,7 +52,7 @@
 #define GPUPREAGG_CONSUMER_WARPS    16
 #endif
 #ifndef GPUPREAGG_MIN_CTAS
-#define GPUPREAGG_MIN_CTAS          2
+#define GPUPREAGG_MIN_CTAS          1
 #endif
 #define GPUPREAGG_CONSUMER_THREADS  (GPUPREAGG_CONSUMER_WARPS * 32)
 #define GPUPREAGG_BLOCK_THREADS     (GPUPREAGG_CONSUMER_THREADS + 32)
@@ -70,7 +70,7 @@
  * ------------------------------------------------------------------ */
 typedef struct
 {
-    cl_char         isnull;
+    bool            isnull;
     union {
         cl_short    short_val;
         cl_int      int_val;
@@ -246,6 +246,13 @@ pgs_f8_from_sortkey(cl_ulong k)
 #define PGS_MERGE_THREAD_CNT_I32(p,c,v,ok)                              \
     (p)[c] = (cl_ulong)((cl_uint)(p)[c] + ((ok) ? (cl_uint)(v) : 0U));
 #define PGS_MERGE_THREAD_SUM_I64(p,c,v,ok)  PGS_MERGE_PLAIN_SUM_I64(p,c,v,ok)
+/* the addend is known to fit 32 bits (int2/int4 widened to int8): one
+ * IMAD.WIDE on the FMA pipe instead of select + sign extension + 64-bit add */
+#define PGS_MERGE_THREAD_SUM_I32W(p,c,v,ok)                             \
+    (p)[c] = (cl_ulong)((cl_long)(p)[c] +                               \
+                        (cl_long)(cl_int)(v) * (cl_long)(cl_int)(ok));
+#define PGS_MERGE_PLAIN_SUM_I32W(p,c,v,ok)  PGS_MERGE_PLAIN_SUM_I64(p,c,v,ok)
+#define PGS_MERGE_ATOMIC_SUM_I32W(p,c,v,ok) PGS_MERGE_ATOMIC_SUM_I64(p,c,v,ok)
 #define PGS_MERGE_THREAD_SUM_F64(p,c,v,ok)  PGS_MERGE_PLAIN_SUM_F64(p,c,v,ok)
 #define PGS_MERGE_THREAD_MIN_I64(p,c,v,ok)  PGS_MERGE_PLAIN_MIN_I64(p,c,v,ok)
 #define PGS_MERGE_THREAD_MAX_I64(p,c,v,ok)  PGS_MERGE_PLAIN_MAX_I64(p,c,v,ok)
@@ -268,8 +275,30 @@ pgs_f8_from_sortkey(cl_ulong k)
 #define PGS_MERGE_PLAIN_MIN_F64(p,c,v,ok)   PGS_MERGE_PLAIN_MIN_U64(p,c,v,ok)
 #define PGS_MERGE_PLAIN_MAX_F64(p,c,v,ok)   PGS_MERGE_PLAIN_MAX_U64(p,c,v,ok)
 #endif
+/* per-row flavour (no GROUP BY): a running min/max changes only O(log n)
+ * times, so the update sits under a rarely taken branch and the common path
+ * is a single FP64 compare.  min: cell NaN = nothing but NaN seen so far. */
+#if GPUPREAGG_NUM_KEYS == 0
+#define PGS_MERGE_THREAD_MIN_F64(p,c,v,ok)                              \
+    { double __a = PGS_F8_UNCELL((p)[c]), __x = PGS_F8_UNCELL(v);        \
+      if ((ok) & !(__x >= __a))                                         \
+      {                                                                 \
+          asm volatile("" ::: "memory");                                \
+          if (__x == __x)                                               \
+              (p)[c] = (cl_ulong)(v);                                   \
+      } }
+#define PGS_MERGE_THREAD_MAX_F64(p,c,v,ok)                              \
+    { double __a = PGS_F8_UNCELL((p)[c]), __x = PGS_F8_UNCELL(v);        \
+      if ((ok) & !(__x <= __a))                                         \
+      {                                                                 \
+          asm volatile("" ::: "memory");                                \
+          if (__a == __a)                                               \
+              (p)[c] = (cl_ulong)(v);                                   \
+      } }
+#else
 #define PGS_MERGE_THREAD_MIN_F64(p,c,v,ok)  PGS_MERGE_PLAIN_MIN_F64(p,c,v,ok)
 #define PGS_MERGE_THREAD_MAX_F64(p,c,v,ok)  PGS_MERGE_PLAIN_MAX_F64(p,c,v,ok)
+#endif
 #define PGS_MERGE_ATOMIC_MIN_F64(p,c,v,ok)  PGS_MERGE_ATOMIC_MIN_U64(p,c,v,ok)
 #define PGS_MERGE_ATOMIC_MAX_F64(p,c,v,ok)  PGS_MERGE_ATOMIC_MAX_U64(p,c,v,ok)
 
@@ -327,7 +356,7 @@ pgs_add128_ATOMIC(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool
 
 /* row -> state (MODE = PLAIN | ATOMIC); `d` is a pagg_datum */
 #define PGS_AGGCALC_PSUM_INT(MODE,p,c,d,ok)    PGS_MERGE_##MODE##_CNT_I32(p,c,PGS_NEWVAL_PSUM_INT(d),ok)
-#define PGS_AGGCALC_PSUM_LONGS(MODE,p,c,d,ok)  PGS_MERGE_##MODE##_SUM_I64(p,c,PGS_NEWVAL_PSUM_LONGS(d),ok)
+#define PGS_AGGCALC_PSUM_LONGS(MODE,p,c,d,ok)  PGS_MERGE_##MODE##_SUM_I32W(p,c,PGS_NEWVAL_PSUM_LONGS(d),ok)
 #define PGS_AGGCALC_PSUM_LONG(MODE,p,c,d,ok)                            \
     pgs_add128_##MODE(&(p)[c], &(p)[(c)+1], (cl_ulong)(d).long_val,     \
                       (d).long_val < 0 ? ~0ULL : 0ULL, (ok));
@@ -944,8 +973,8 @@ struct pgs_smem_head
         cl_uint __vb = 0xFU;                                            \
         if (tile.nul_off[slot] != KERN_TILE_NO_NULLMAP)                 \
             __vb = *((const cl_uint *)(__pgs_smem + tile.nul_off[slot]) + (r >> 5)) >> (r & 31); \
-        rr[0].vbits[slot] = __vb;       rr[1].vbits[slot] = __vb >> 1;  \
-        rr[2].vbits[slot] = __vb >> 2;  rr[3].vbits[slot] = __vb >> 3;  \
+        rr[0].vbits[slot] = rr[1].vbits[slot] = __vb;                   \
+        rr[2].vbits[slot] = rr[3].vbits[slot] = __vb;                   \
     }
 
 #define PGS_X_INCOL_GVIEW(slot,colidx,attlen)                           \
@@ -1241,6 +1270,7 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                 kern_row_regs rr[4];
                 bool        nnflag[PGS_MAX(PGS_NUM_NNCLASSES, 1)];
 
+                rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
 #pragma unroll
                 for (int k = 0; k < PGS_MAX(PGS_NUM_NNCLASSES, 1); k++)
                     nnflag[k] = false;
