@@ -602,6 +602,10 @@ struct pgs_session
     uint64_t        num_kern_main = 0;
     uint64_t        rows_kern_main = 0;
     void           *d_scratch = NULL;   /* small device buffer: desc, counters */
+    char           *d_result = NULL;    /* TUPSLOT store written by the flush kernel */
+    size_t          d_result_cap = 0;
+    kern_gpupreagg *d_kg_misc = NULL;   /* status word of flush / import kernels */
+    char           *h_result_head = NULL;   /* pinned: header + status read-back */
     std::string     perfmon_buf;
     bool            aborted = false;
 };
@@ -1158,8 +1162,20 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     int32_t h_status = 0;
     kern_data_store hdr;
 
-    CUDA_CHECK(cudaMalloc((void **)&d_dst, total));
-    CUDA_CHECK(cudaMalloc((void **)&d_kg, sizeof(kern_gpupreagg)));
+    /* the result store and the status word live as long as the session */
+    if (s->d_result_cap < total)
+    {
+        if (s->d_result)
+            CUDA_CHECK(cudaFree(s->d_result));
+        s->d_result = NULL;
+        s->d_result_cap = 0;
+        CUDA_CHECK(cudaMalloc((void **)&s->d_result, total));
+        s->d_result_cap = total;
+    }
+    if (!s->d_kg_misc)
+        CUDA_CHECK(cudaMalloc((void **)&s->d_kg_misc, sizeof(kern_gpupreagg)));
+    d_dst = s->d_result;
+    d_kg = s->d_kg_misc;
     kds_dst->nitems = 0;
     cudaError_t e = cudaMemcpyAsync(d_dst, kds_dst, head, cudaMemcpyHostToDevice, s->s_exec);
     if (e == cudaSuccess)
@@ -1197,8 +1213,6 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
         else if (h_status == StromError_Success)
             h_status = StromError_DataStoreNoSpace;
     }
-    cudaFree(d_dst);
-    cudaFree(d_kg);
     if (e != cudaSuccess)
     {
         set_error("pgs_preagg_finish: %s", cudaGetErrorString(e));
@@ -1214,10 +1228,10 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     }
     if (reset && h_status == StromError_Success)
     {
+        /* stream ordered: later chunks queue up behind it */
         rc = session_init_state(s);
         if (rc != StromError_Success)
             return rc;
-        CUDA_CHECK(cudaStreamSynchronize(s->s_exec));
     }
     return StromErrorIsSignificant(h_status) ? h_status : StromError_Success;
 }
@@ -1276,7 +1290,9 @@ pgs_preagg_state_import(pgs_session *s, const void *device_buf, uint32_t nrecord
     kern_gpupreagg *d_kg = NULL;
     int32_t h_status = 0;
     const cl_ulong *recs = (const cl_ulong *)device_buf;
-    CUDA_CHECK(cudaMalloc((void **)&d_kg, sizeof(kern_gpupreagg)));
+    if (!s->d_kg_misc)
+        CUDA_CHECK(cudaMalloc((void **)&s->d_kg_misc, sizeof(kern_gpupreagg)));
+    d_kg = s->d_kg_misc;
     cudaError_t e = cudaMemsetAsync(d_kg, 0, sizeof(kern_gpupreagg), s->s_exec);
     int rc = StromError_Success;
     if (e == cudaSuccess)
@@ -1290,7 +1306,6 @@ pgs_preagg_state_import(pgs_session *s, const void *device_buf, uint32_t nrecord
         e = cudaMemcpyAsync(&h_status, d_kg, sizeof(int32_t), cudaMemcpyDeviceToHost, s->s_exec);
     if (e == cudaSuccess && rc == StromError_Success)
         e = cudaStreamSynchronize(s->s_exec);
-    cudaFree(d_kg);
     if (rc != StromError_Success)
         return rc;
     if (e != cudaSuccess)
@@ -1545,6 +1560,8 @@ pgs_preagg_close(pgs_session *s)
             if (sl.ev_k1) cudaEventDestroy(sl.ev_k1);
         }
         if (s->gs.gh_slots) cudaFree(s->gs.gh_slots);
+        if (s->d_result) cudaFree(s->d_result);
+        if (s->d_kg_misc) cudaFree(s->d_kg_misc);
         if (s->d_scratch) cudaFree(s->d_scratch);
         if (s->s_copy) cudaStreamDestroy(s->s_copy);
         if (s->s_exec) cudaStreamDestroy(s->s_exec);
