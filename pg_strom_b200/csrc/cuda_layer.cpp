@@ -984,18 +984,26 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
     const void *d_kds = kds_dev;
     if (kds_host)
     {
+        /* host chunk: H2D on the copy stream, so that it overlaps the kernel
+         * of the previous chunk; the exec stream waits for it */
         CUDA_CHECK(cudaMemcpyAsync(sl.d_kds, kds_host, length,
                                    cudaMemcpyHostToDevice, s->s_copy));
         d_kds = sl.d_kds;
         s->num_dma_send++;
         s->bytes_dma_send += length;
+        CUDA_CHECK(cudaMemcpyAsync(sl.d_kgpreagg, sl.h_kgpreagg, kg_bytes,
+                                   cudaMemcpyHostToDevice, s->s_copy));
+        CUDA_CHECK(cudaEventRecord(sl.ev_copied, s->s_copy));
+        CUDA_CHECK(cudaStreamWaitEvent(s->s_exec, sl.ev_copied, 0));
     }
-    CUDA_CHECK(cudaMemcpyAsync(sl.d_kgpreagg, sl.h_kgpreagg, kg_bytes,
-                               cudaMemcpyHostToDevice, s->s_copy));
+    else
+    {
+        /* chunk already in HBM: nothing to overlap, keep it on one stream */
+        CUDA_CHECK(cudaMemcpyAsync(sl.d_kgpreagg, sl.h_kgpreagg, kg_bytes,
+                                   cudaMemcpyHostToDevice, s->s_exec));
+    }
     s->num_dma_send++;
     s->bytes_dma_send += kg_bytes;
-    CUDA_CHECK(cudaEventRecord(sl.ev_copied, s->s_copy));
-    CUDA_CHECK(cudaStreamWaitEvent(s->s_exec, sl.ev_copied, 0));
 
     bool use_rowmap = (krowmap && krowmap->nvalids >= 0);
     void *args[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck, &s->sh_nslots,
@@ -1161,7 +1169,14 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     kern_gpupreagg *d_kg = NULL;
     int32_t h_status = 0;
     kern_data_store hdr;
+    /* pinned staging: [status word | head + the first rows of the result].
+     * Small results (no GROUP BY, a few thousand groups) come back with one
+     * copy and one synchronisation; larger ones need a second copy once the
+     * row count is known. */
+    const size_t STAGE_BYTES = 256 * 1024;
+    size_t first = std::min(total, STAGE_BYTES - 64);
 
+    memset(&hdr, 0, sizeof(hdr));
     /* the result store and the status word live as long as the session */
     if (s->d_result_cap < total)
     {
@@ -1174,10 +1189,14 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     }
     if (!s->d_kg_misc)
         CUDA_CHECK(cudaMalloc((void **)&s->d_kg_misc, sizeof(kern_gpupreagg)));
+    if (!s->h_result_head)
+        CUDA_CHECK(cudaHostAlloc((void **)&s->h_result_head, STAGE_BYTES, cudaHostAllocPortable));
     d_dst = s->d_result;
     d_kg = s->d_kg_misc;
     kds_dst->nitems = 0;
-    cudaError_t e = cudaMemcpyAsync(d_dst, kds_dst, head, cudaMemcpyHostToDevice, s->s_exec);
+    memcpy(s->h_result_head + 64, kds_dst, head);
+    cudaError_t e = cudaMemcpyAsync(d_dst, s->h_result_head + 64, head,
+                                    cudaMemcpyHostToDevice, s->s_exec);
     if (e == cudaSuccess)
         e = cudaMemsetAsync(d_kg, 0, sizeof(kern_gpupreagg), s->s_exec);
     if (e == cudaSuccess)
@@ -1190,22 +1209,27 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
             e = cudaErrorUnknown;
     }
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(&hdr, d_dst, offsetof(kern_data_store, colmeta),
+        e = cudaMemcpyAsync(s->h_result_head, d_kg, sizeof(int32_t),
                             cudaMemcpyDeviceToHost, s->s_exec);
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(&h_status, d_kg, sizeof(int32_t), cudaMemcpyDeviceToHost, s->s_exec);
+        e = cudaMemcpyAsync(s->h_result_head + 64, d_dst, first,
+                            cudaMemcpyDeviceToHost, s->s_exec);
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(s->s_exec);
     if (e == cudaSuccess)
     {
+        h_status = *((int32_t *)s->h_result_head);
+        memcpy(&hdr, s->h_result_head + 64, offsetof(kern_data_store, colmeta));
         if (nrows_needed)
             *nrows_needed = hdr.nitems;
         if (h_status == StromError_Success && hdr.nitems <= kds_dst->nrooms)
         {
             size_t nbytes = stride * (size_t)hdr.nitems;
-            if (nbytes > 0)
-                e = cudaMemcpy((char *)kds_dst + head, d_dst + head, nbytes,
-                               cudaMemcpyDeviceToHost);
+            size_t have = std::min(nbytes, first - head);
+            memcpy((char *)kds_dst + head, s->h_result_head + 64 + head, have);
+            if (nbytes > have)
+                e = cudaMemcpy((char *)kds_dst + head + have, d_dst + head + have,
+                               nbytes - have, cudaMemcpyDeviceToHost);
             kds_dst->nitems = hdr.nitems;
             s->num_dma_recv += 2;
             s->bytes_dma_recv += nbytes + sizeof(hdr);
@@ -1228,7 +1252,8 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     }
     if (reset && h_status == StromError_Success)
     {
-        /* stream ordered: later chunks queue up behind it */
+        /* stream ordered: later chunks queue up behind it.  A flush that
+         * failed (result store too small) keeps the state for a retry. */
         rc = session_init_state(s);
         if (rc != StromError_Success)
             return rc;
@@ -1562,6 +1587,7 @@ pgs_preagg_close(pgs_session *s)
         if (s->gs.gh_slots) cudaFree(s->gs.gh_slots);
         if (s->d_result) cudaFree(s->d_result);
         if (s->d_kg_misc) cudaFree(s->d_kg_misc);
+        if (s->h_result_head) cudaFreeHost(s->h_result_head);
         if (s->d_scratch) cudaFree(s->d_scratch);
         if (s->s_copy) cudaStreamDestroy(s->s_copy);
         if (s->s_exec) cudaStreamDestroy(s->s_exec);

@@ -977,6 +977,7 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
                 for (auto &kc : nn_classes)
                     o << " _(" << kc.second.first << ",0x" << std::hex << kc.second.second << std::dec << "U)";
                 return o.str(); }() << "\n"
+         << "#define GPUPREAGG_HAS_QUAL " << (outer_quals.empty() ? 0 : 1) << "\n"
          << "#define GPUPREAGG_NUM_OUTCOLS " << pre_tlist.size() << "\n"
          << "#define GPUPREAGG_OUT_LIST(_)" << out_list.str() << "\n";
     role_fn << "__host__ __device__ constexpr int\nGPUPREAGG_FIELD_ROLE(unsigned int colidx)\n{\n  switch (colidx)\n  {\n";

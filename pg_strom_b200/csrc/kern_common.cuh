@@ -135,7 +135,7 @@ struct kern_row_regs
         union { cl_ulong u; T t; } cv;
         cv.u = v[slot];
         out = cv.t;
-        return ((vbits[slot] >> shift) & 1U) != 0;
+        return (vbits[slot] & (1U << shift)) != 0;
     }
 };
 

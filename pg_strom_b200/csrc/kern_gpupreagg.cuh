@@ -37,6 +37,7 @@
  *   GPUPREAGG_NUM_AGGS,  GPUPREAGG_NUM_CELLS, GPUPREAGG_AGG_LIST(_)
  *   GPUPREAGG_NUM_OUTCOLS, GPUPREAGG_OUT_LIST(_)
  *   GPUPREAGG_FIELD_ROLE(colidx), GPUPREAGG_FIELD_INDEX(colidx)
+ *   GPUPREAGG_HAS_QUAL, GPUPREAGG_NNCLASS_LIST(_)
  * and by the CUDA layer (-D): GPUPREAGG_CONSUMER_WARPS.
  */
 #ifndef KERN_GPUPREAGG_CUH
@@ -56,6 +57,11 @@
 #endif
 #define GPUPREAGG_CONSUMER_THREADS  (GPUPREAGG_CONSUMER_WARPS * 32)
 #define GPUPREAGG_BLOCK_THREADS     (GPUPREAGG_CONSUMER_THREADS + 32)
+
+/* 0 when gpupreagg_qual_eval() is the constant `true` (no WHERE clause) */
+#ifndef GPUPREAGG_HAS_QUAL
+#define GPUPREAGG_HAS_QUAL          1
+#endif
 
 #ifndef PGS_ROWS_PER_THREAD
 #define PGS_ROWS_PER_THREAD         4
@@ -102,6 +108,17 @@ struct pagg_row
         }
     }
 };
+
+/* the two generated functions (defined after this header is included) */
+template <typename KDS>
+DEVFN bool
+gpupreagg_qual_eval(cl_int *errcode, const kern_parambuf *kparams,
+                    const KDS &kds, const void *ktoast, cl_uint kds_index);
+template <typename KDS>
+DEVFN void
+gpupreagg_projection(cl_int *errcode, const kern_parambuf *kparams,
+                     const KDS &kds_in, pagg_row &kds_src, const void *ktoast,
+                     cl_uint rowidx_in, cl_uint rowidx_out);
 
 /* pg_<type>_vstore(kds_src, kds_in, errcode, colidx, rowidx_out, datum):
  * same call shape as the reference's generated projection
@@ -322,6 +339,140 @@ pgs_f8_from_sortkey(cl_ulong k)
     if ((ok) && (cl_ulong)(v) > *((volatile cl_ulong *)&(p)[c]))        \
         atomicMax((unsigned long long *)&(p)[c], (unsigned long long)(v));
 
+/* ---- typed thread accumulators (no GROUP BY fast path).
+ * The running state of a consumer thread lives in registers of the natural
+ * C type of each aggregate (pgs_tacc, one member a<i> per aggregate) and is
+ * folded into the 8-byte cells once, after the last tile.  Rows reach it
+ * only in batches that are free of errors and of NaN / infinite / huge float
+ * inputs (pgs_row_special), so nothing can overflow and every float compare
+ * is one DSETP: min starts as NaN ("nothing seen") and !(x >= NaN) adopts the
+ * first value, max starts at -Infinity.  Updates are predicated on `ok`. ---- */
+struct pgs_i128 { cl_ulong lo, hi; };
+
+#define PGS_TACC_TYPE_PSUM_INT      cl_uint
+#define PGS_TACC_TYPE_PSUM_LONGS    cl_long
+#define PGS_TACC_TYPE_PSUM_LONG     pgs_i128
+#define PGS_TACC_TYPE_PSUM_FLOAT    double
+#define PGS_TACC_TYPE_PSUM_DOUBLE   double
+#define PGS_TACC_TYPE_PMIN_SHORT    cl_int
+#define PGS_TACC_TYPE_PMIN_INT      cl_int
+#define PGS_TACC_TYPE_PMIN_LONG     cl_long
+#define PGS_TACC_TYPE_PMIN_FLOAT    double
+#define PGS_TACC_TYPE_PMIN_DOUBLE   double
+#define PGS_TACC_TYPE_PMAX_SHORT    cl_int
+#define PGS_TACC_TYPE_PMAX_INT      cl_int
+#define PGS_TACC_TYPE_PMAX_LONG     cl_long
+#define PGS_TACC_TYPE_PMAX_FLOAT    double
+#define PGS_TACC_TYPE_PMAX_DOUBLE   double
+
+#define PGS_F8_NAN      __longlong_as_double(0x7FF8000000000000LL)
+#define PGS_F8_NEGINF   __longlong_as_double((cl_long)0xFFF0000000000000ULL)
+
+#define PGS_TACC_INIT_PSUM_INT(a)       (a) = 0;
+#define PGS_TACC_INIT_PSUM_LONGS(a)     (a) = 0;
+#define PGS_TACC_INIT_PSUM_LONG(a)      (a).lo = 0; (a).hi = 0;
+#define PGS_TACC_INIT_PSUM_FLOAT(a)     (a) = 0.0;
+#define PGS_TACC_INIT_PSUM_DOUBLE(a)    (a) = 0.0;
+#define PGS_TACC_INIT_PMIN_SHORT(a)     (a) = INT_MAX;
+#define PGS_TACC_INIT_PMIN_INT(a)       (a) = INT_MAX;
+#define PGS_TACC_INIT_PMIN_LONG(a)      (a) = LONG_MAX;
+#define PGS_TACC_INIT_PMIN_FLOAT(a)     (a) = PGS_F8_NAN;
+#define PGS_TACC_INIT_PMIN_DOUBLE(a)    (a) = PGS_F8_NAN;
+#define PGS_TACC_INIT_PMAX_SHORT(a)     (a) = INT_MIN;
+#define PGS_TACC_INIT_PMAX_INT(a)       (a) = INT_MIN;
+#define PGS_TACC_INIT_PMAX_LONG(a)      (a) = LONG_MIN;
+#define PGS_TACC_INIT_PMAX_FLOAT(a)     (a) = PGS_F8_NEGINF;
+#define PGS_TACC_INIT_PMAX_DOUBLE(a)    (a) = PGS_F8_NEGINF;
+
+/* predicated single instructions the compiler would otherwise turn into
+ * compute + select pairs */
+DEVFN void
+pgs_pred_dadd(double &acc, double x, bool ok)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p add.f64 %0, %0, %1;\n\t}"
+        : "+d"(acc) : "d"(x), "r"((cl_uint)ok));
+}
+DEVFN void
+pgs_pred_madwide(cl_long &acc, cl_int x, bool ok)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p mad.wide.s32 %0, %1, 1, %0;\n\t}"
+        : "+l"(acc) : "r"(x), "r"((cl_uint)ok));
+}
+DEVFN void
+pgs_pred_dmin(double &acc, double x, bool ok)       /* x is not NaN */
+{
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\t"
+        "setp.ltu.and.f64 q, %1, %0, p;\n\t@q mov.f64 %0, %1;\n\t}"
+        : "+d"(acc) : "d"(x), "r"((cl_uint)ok));
+}
+DEVFN void
+pgs_pred_dmax(double &acc, double x, bool ok)       /* x is not NaN */
+{
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\t"
+        "setp.gt.and.f64 q, %1, %0, p;\n\t@q mov.f64 %0, %1;\n\t}"
+        : "+d"(acc) : "d"(x), "r"((cl_uint)ok));
+}
+
+#define PGS_TACC_CALC_PSUM_INT(a,d,ok)      (a) += ((ok) ? (cl_uint)(d).int_val : 0U);
+#define PGS_TACC_CALC_PSUM_LONGS(a,d,ok)    pgs_pred_madwide((a), (cl_int)(d).long_val, (ok));
+#define PGS_TACC_CALC_PSUM_LONG(a,d,ok)                                 \
+    pgs_add128_PLAIN(&(a).lo, &(a).hi, (cl_ulong)(d).long_val,          \
+                     (d).long_val < 0 ? ~0ULL : 0ULL, (ok));
+#define PGS_TACC_CALC_PSUM_FLOAT(a,d,ok)    pgs_pred_dadd((a), (double)(d).float_val, (ok));
+#define PGS_TACC_CALC_PSUM_DOUBLE(a,d,ok)   pgs_pred_dadd((a), (d).double_val, (ok));
+#define PGS_TACC_CALC_PMIN_SHORT(a,d,ok)    if (ok) (a) = min((a), (cl_int)(d).short_val);
+#define PGS_TACC_CALC_PMIN_INT(a,d,ok)      if (ok) (a) = min((a), (d).int_val);
+#define PGS_TACC_CALC_PMIN_LONG(a,d,ok)     if ((ok) & ((d).long_val < (a))) (a) = (d).long_val;
+#define PGS_TACC_CALC_PMIN_FLOAT(a,d,ok)    pgs_pred_dmin((a), (double)(d).float_val, (ok));
+#define PGS_TACC_CALC_PMIN_DOUBLE(a,d,ok)   pgs_pred_dmin((a), (d).double_val, (ok));
+#define PGS_TACC_CALC_PMAX_SHORT(a,d,ok)    if (ok) (a) = max((a), (cl_int)(d).short_val);
+#define PGS_TACC_CALC_PMAX_INT(a,d,ok)      if (ok) (a) = max((a), (d).int_val);
+#define PGS_TACC_CALC_PMAX_LONG(a,d,ok)     if ((ok) & ((d).long_val > (a))) (a) = (d).long_val;
+#define PGS_TACC_CALC_PMAX_FLOAT(a,d,ok)    pgs_pred_dmax((a), (double)(d).float_val, (ok));
+#define PGS_TACC_CALC_PMAX_DOUBLE(a,d,ok)   pgs_pred_dmax((a), (d).double_val, (ok));
+
+/* accumulator -> cell-domain value(s) at src[c] */
+#define PGS_TACC_CELL_PSUM_INT(a,src,c)     (src)[c] = (cl_ulong)(a);
+#define PGS_TACC_CELL_PSUM_LONGS(a,src,c)   (src)[c] = (cl_ulong)(a);
+#define PGS_TACC_CELL_PSUM_LONG(a,src,c)    (src)[c] = (a).lo; (src)[(c)+1] = (a).hi;
+#define PGS_TACC_CELL_PSUM_FLOAT(a,src,c)   (src)[c] = (cl_ulong)__double_as_longlong(a);
+#define PGS_TACC_CELL_PSUM_DOUBLE(a,src,c)  (src)[c] = (cl_ulong)__double_as_longlong(a);
+#define PGS_TACC_CELL_PMIN_SHORT(a,src,c)   (src)[c] = (cl_ulong)(cl_long)(a);
+#define PGS_TACC_CELL_PMIN_INT(a,src,c)     (src)[c] = (cl_ulong)(cl_long)(a);
+#define PGS_TACC_CELL_PMIN_LONG(a,src,c)    (src)[c] = (cl_ulong)(a);
+#define PGS_TACC_CELL_PMIN_FLOAT(a,src,c)   (src)[c] = PGS_F8_CELL(a);
+#define PGS_TACC_CELL_PMIN_DOUBLE(a,src,c)  (src)[c] = PGS_F8_CELL(a);
+#define PGS_TACC_CELL_PMAX_SHORT(a,src,c)   PGS_TACC_CELL_PMIN_SHORT(a,src,c)
+#define PGS_TACC_CELL_PMAX_INT(a,src,c)     PGS_TACC_CELL_PMIN_INT(a,src,c)
+#define PGS_TACC_CELL_PMAX_LONG(a,src,c)    PGS_TACC_CELL_PMIN_LONG(a,src,c)
+#define PGS_TACC_CELL_PMAX_FLOAT(a,src,c)   PGS_TACC_CELL_PMIN_FLOAT(a,src,c)
+#define PGS_TACC_CELL_PMAX_DOUBLE(a,src,c)  PGS_TACC_CELL_PMIN_DOUBLE(a,src,c)
+
+/* ---- SHARED flavours (CTA-local table): shared memory has native 32-bit
+ * atomics only, every 64-bit add / min / max is a compare-and-swap loop.
+ * Counts of one launch fit 32 bits (the low half of the cell); a sum of
+ * 32-bit addends is carried by hand from the low into the high half. ---- */
+#define PGS_MERGE_SHARED_CNT_I32(p,c,v,ok)                              \
+    if (ok) atomicAdd((cl_uint *)&(p)[c], (cl_uint)(v));
+#define PGS_MERGE_SHARED_SUM_I32W(p,c,v,ok)                             \
+    if (ok)                                                             \
+    {                                                                   \
+        cl_uint __lo = (cl_uint)(v);                                    \
+        cl_uint __old = atomicAdd((cl_uint *)&(p)[c], __lo);            \
+        cl_uint __hi = (cl_uint)((cl_int)__lo >> 31) +                  \
+                       ((cl_uint)(__old + __lo) < __old ? 1U : 0U);     \
+        if (__hi != 0)                                                  \
+            atomicAdd((cl_uint *)&(p)[c] + 1, __hi);                    \
+    }
+#define PGS_MERGE_SHARED_SUM_I64(p,c,v,ok)  PGS_MERGE_ATOMIC_SUM_I64(p,c,v,ok)
+#define PGS_MERGE_SHARED_SUM_F64(p,c,v,ok)  PGS_MERGE_ATOMIC_SUM_F64(p,c,v,ok)
+#define PGS_MERGE_SHARED_MIN_I32(p,c,v,ok)  PGS_MERGE_ATOMIC_MIN_I32(p,c,v,ok)
+#define PGS_MERGE_SHARED_MAX_I32(p,c,v,ok)  PGS_MERGE_ATOMIC_MAX_I32(p,c,v,ok)
+#define PGS_MERGE_SHARED_MIN_I64(p,c,v,ok)  PGS_MERGE_ATOMIC_MIN_I64(p,c,v,ok)
+#define PGS_MERGE_SHARED_MAX_I64(p,c,v,ok)  PGS_MERGE_ATOMIC_MAX_I64(p,c,v,ok)
+#define PGS_MERGE_SHARED_MIN_F64(p,c,v,ok)  PGS_MERGE_ATOMIC_MIN_F64(p,c,v,ok)
+#define PGS_MERGE_SHARED_MAX_F64(p,c,v,ok)  PGS_MERGE_ATOMIC_MAX_F64(p,c,v,ok)
+
 /* 128-bit sums: (lo,hi) two's complement.  The carry out of `lo` is known
  * from the value atomicAdd returns, and additions commute, so two 64-bit
  * atomics give an exact 128-bit sum without a lock. */
@@ -341,6 +492,11 @@ pgs_add128_THREAD(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool
     pgs_add128_PLAIN(plo, phi, vlo, vhi, ok);
 }
 DEVFN void
+pgs_add128_FAST(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool ok)
+{
+    pgs_add128_PLAIN(plo, phi, vlo, vhi, ok);
+}
+DEVFN void
 pgs_add128_ATOMIC(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool ok)
 {
     if (ok)
@@ -354,7 +510,14 @@ pgs_add128_ATOMIC(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool
     }
 }
 
-/* row -> state (MODE = PLAIN | ATOMIC); `d` is a pagg_datum */
+DEVFN void
+pgs_add128_SHARED(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool ok)
+{
+    pgs_add128_ATOMIC(plo, phi, vlo, vhi, ok);
+}
+
+/* row -> state (MODE = PLAIN | THREAD | FAST | ATOMIC | SHARED); `d` is a
+ * pagg_datum */
 #define PGS_AGGCALC_PSUM_INT(MODE,p,c,d,ok)    PGS_MERGE_##MODE##_CNT_I32(p,c,PGS_NEWVAL_PSUM_INT(d),ok)
 #define PGS_AGGCALC_PSUM_LONGS(MODE,p,c,d,ok)  PGS_MERGE_##MODE##_SUM_I32W(p,c,PGS_NEWVAL_PSUM_LONGS(d),ok)
 #define PGS_AGGCALC_PSUM_LONG(MODE,p,c,d,ok)                            \
@@ -412,6 +575,22 @@ pgs_add128_ATOMIC(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool
 #define PGS_AGGCHECK_PMAX_FLOAT(d)
 #define PGS_AGGCHECK_PMAX_DOUBLE(d)
 
+/* per-row "special float" probe of the no-group fast path: the largest
+ * exponent field among the float inputs of a batch of rows, as an integer
+ * (sign stripped).  At or above the limit the batch holds NaN, +-Infinity or
+ * a magnitude the sum re-checks (PGS_PSUM_*_LIMIT) and takes the careful path. */
+#define PGS_SPECIAL_F8_LIMIT    0x7BF00000U     /* high word of 2^960 */
+#define PGS_SPECIAL_F4_LIMIT    0x6B800000U     /* bits of 2^88 */
+#define PGS_SPECIAL_SHORT(d)
+#define PGS_SPECIAL_INT(d)
+#define PGS_SPECIAL_LONG(d)
+#define PGS_SPECIAL_LONGS(d)
+#define PGS_SPECIAL_FLOAT(d)                                            \
+    mf = max(mf, __float_as_uint((d).float_val) & 0x7fffffffU);
+#define PGS_SPECIAL_DOUBLE(d)                                           \
+    md = max(md, (cl_uint)((d).ulong_val >> 32) & 0x7fffffffU);
+#define PGS_X_SPECIAL(i,c,OP,TYPE)      PGS_SPECIAL_##TYPE(row.agg[i])
+
 /* X-macro adaptors over GPUPREAGG_AGG_LIST(_) = _(aggidx, cellidx, OP, TYPE) */
 #define PGS_X_INIT(i,c,OP,TYPE)         PGS_CELL_INIT_##OP##_##TYPE(c,cells)
 #define PGS_X_CHECK(i,c,OP,TYPE)                                        \
@@ -423,6 +602,16 @@ pgs_add128_ATOMIC(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool
 #define PGS_X_CALC_THREAD(i,c,OP,TYPE)                                  \
     { bool __ok = valid & !row.agg[i].isnull;                           \
       PGS_AGGCALC_##OP##_##TYPE(THREAD,cells,c,row.agg[i],__ok) }
+#define PGS_X_TACC_DECL(i,c,OP,TYPE)    PGS_TACC_TYPE_##OP##_##TYPE a##i;
+#define PGS_X_TACC_INIT(i,c,OP,TYPE)    PGS_TACC_INIT_##OP##_##TYPE(a##i)
+#define PGS_X_TACC_CALC(i,c,OP,TYPE)                                    \
+    { bool __ok = valid & !row.agg[i].isnull;                           \
+      PGS_TACC_CALC_##OP##_##TYPE(a##i,row.agg[i],__ok) }
+#define PGS_X_TACC_CELL(i,c,OP,TYPE)    PGS_TACC_CELL_##OP##_##TYPE(a##i,src,c)
+#define PGS_X_CALC_SHARED(i,c,OP,TYPE)                                  \
+    { bool __ok = !row.agg[i].isnull;                                   \
+      PGS_AGGCALC_##OP##_##TYPE(SHARED,cells,c,row.agg[i],__ok)         \
+      nnmask |= (__ok ? (1U << (i)) : 0U); }
 /* "saw a non-NULL input" per class of aggregates that share the NULL-ness of
  * one argument (GPUPREAGG_NNCLASS_LIST(_) = _(representative agg, bit mask)) */
 #define PGS_X_NNCLASS(rep,mask)                                         \
@@ -431,6 +620,12 @@ pgs_add128_ATOMIC(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool
 #define PGS_NUM_NNCLASSES   (0 GPUPREAGG_NNCLASS_LIST(PGS_X_NNCLASS_COUNT))
 #define PGS_X_NNCLASS_FLAG(rep,mask)                                    \
     nnflag[__k] = nnflag[__k] | (valid & !row.agg[rep].isnull); __k++;
+#define PGS_X_NNCLASS_FLAG4(rep,mask)                                   \
+    nnflag[__k] = nnflag[__k] |                                         \
+        ((valids[0] & !rows[0].agg[rep].isnull) |                       \
+         (valids[1] & !rows[1].agg[rep].isnull) |                       \
+         (valids[2] & !rows[2].agg[rep].isnull) |                       \
+         (valids[3] & !rows[3].agg[rep].isnull)); __k++;
 #define PGS_X_NNCLASS_MASK(rep,mask)                                    \
     nnmask |= (nnflag[__k] ? (mask) : 0U); __k++;
 #define PGS_X_CALC_ATOMIC(i,c,OP,TYPE)                                  \
@@ -488,6 +683,53 @@ pgs_nnflags_to_mask(const bool *nnflag)
     (void)__k;
     return nnmask;
 }
+/* typed per-thread state of the no-group fast path (see PGS_TACC_*) */
+struct pgs_tacc
+{
+    GPUPREAGG_AGG_LIST(PGS_X_TACC_DECL)
+    bool    nnflag[PGS_MAX(PGS_NUM_NNCLASSES, 1)];
+
+    __device__ __forceinline__ void
+    init(void)
+    {
+        GPUPREAGG_AGG_LIST(PGS_X_TACC_INIT)
+#pragma unroll
+        for (int k = 0; k < PGS_MAX(PGS_NUM_NNCLASSES, 1); k++)
+            nnflag[k] = false;
+    }
+    /* one row of a batch without errors and special floats */
+    __device__ __forceinline__ void
+    calc(const pagg_row &row, bool valid)
+    {
+        GPUPREAGG_AGG_LIST(PGS_X_TACC_CALC)
+    }
+    /* "saw a non-NULL input" of the whole batch: OR over the rows first, so
+     * that tests of adjacent validity bits fold into one */
+    __device__ __forceinline__ void
+    note_nonnull(const pagg_row *rows, const bool *valids)
+    {
+        int __k = 0;
+        GPUPREAGG_NNCLASS_LIST(PGS_X_NNCLASS_FLAG4)
+        (void)__k;
+    }
+    /* fold into the cells of the thread */
+    __device__ __forceinline__ cl_uint
+    fold(cl_ulong *cells) const
+    {
+        cl_ulong    src[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+        cl_uint     src_nn = pgs_nnflags_to_mask(nnflag);
+
+        GPUPREAGG_AGG_LIST(PGS_X_TACC_CELL)
+        GPUPREAGG_AGG_LIST(PGS_X_MERGE_PLAIN)
+        return src_nn;
+    }
+};
+
+DEVFN void
+pgs_row_special(const pagg_row &row, cl_uint &md, cl_uint &mf)
+{
+    GPUPREAGG_AGG_LIST(PGS_X_SPECIAL)
+}
 template <typename CELLS>
 DEVFN cl_uint
 gpupreagg_aggcalc_atomic(CELLS cells, const pagg_row &row)
@@ -495,6 +737,14 @@ gpupreagg_aggcalc_atomic(CELLS cells, const pagg_row &row)
     const bool valid = true;
     cl_uint nnmask = 0;
     GPUPREAGG_AGG_LIST(PGS_X_CALC_ATOMIC)
+    return nnmask;
+}
+template <typename CELLS>
+DEVFN cl_uint
+gpupreagg_aggcalc_shared(CELLS cells, const pagg_row &row)
+{
+    cl_uint nnmask = 0;
+    GPUPREAGG_AGG_LIST(PGS_X_CALC_SHARED)
     return nnmask;
 }
 template <typename CELLS, typename SRC>
@@ -551,8 +801,17 @@ pgs_stage_nul_off(int slot, cl_uint tile_rows)
 }
 #define PGS_STAGE_BYTES(tile_rows)  pgs_stage_nul_off(GPUPREAGG_NUM_INCOLS, (tile_rows))
 /* head of dynamic smem: 2 x MAX_STAGES mbarriers, column positions */
+/* per consumer warp: queue of the tile rows that passed the qual (GROUP BY
+ * with a WHERE clause only, see the consumer loop) */
+#define PGS_ROWQ_ENTRIES    160             /* 128 new per iteration + < 32 left */
+#if GPUPREAGG_NUM_KEYS > 0 && GPUPREAGG_HAS_QUAL
+#define PGS_ROWQ_BYTES      (2 * PGS_ROWQ_ENTRIES * GPUPREAGG_CONSUMER_WARPS)
+#else
+#define PGS_ROWQ_BYTES      0
+#endif
 #define PGS_SMEM_HEAD_BYTES \
-    PGS_ALIGN128(16 * GPUPREAGG_MAX_STAGES + 8 * PGS_MAX(GPUPREAGG_NUM_INCOLS,1) + 64)
+    PGS_ALIGN128(16 * GPUPREAGG_MAX_STAGES + 8 * PGS_MAX(GPUPREAGG_NUM_INCOLS,1) + 64 + \
+                 PGS_ROWQ_BYTES)
 
 /* ------------------------------------------------------------------
  * mbarrier + bulk async copy (TMA engine, 1-D) wrappers
@@ -618,22 +877,51 @@ pgs_mix64(cl_ulong x)
     return x;
 }
 
+/* hash of (key values with NULL -> 0, NULL bits): 32-bit multiply-add fold of
+ * the key halves, then the murmur3 finaliser - a dozen 32-bit instructions
+ * instead of three 64-bit multiplies per key.  The CTA-local table indexes
+ * with the high bits, the global table with the low bits. */
+DEVFN cl_uint
+pgs_fmix32(cl_uint h)
+{
+    h ^= h >> 16;
+    h *= 0x85ebca6bU;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35U;
+    h ^= h >> 16;
+    return h;
+}
+
+DEVFN cl_ulong
+pgs_hash_keyvals(const cl_ulong *keyvals, cl_uint knull)
+{
+    cl_uint     h = 0x9e3779b9U + knull;
+
+#pragma unroll
+    for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+    {
+        h = h * 0x9e3779b1U + (cl_uint)keyvals[k];
+        h = h * 0x85ebca77U + (cl_uint)(keyvals[k] >> 32);
+    }
+    h = pgs_fmix32(h);
+    return ((cl_ulong)h << 32) | h;
+}
+
 DEVFN cl_ulong
 pgs_hash_keys(const pagg_row &row, cl_uint &knull)
 {
-    cl_ulong    h = 0x9e3779b97f4a7c15ULL;
+    cl_ulong    keyvals[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
 
     knull = 0;
 #pragma unroll
     for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
     {
         /* NULL keys form one group (gpupreagg.c:1234-1243) */
-        cl_ulong v = row.key[k].isnull ? 0 : row.key[k].ulong_val;
+        keyvals[k] = row.key[k].isnull ? 0 : row.key[k].ulong_val;
         if (row.key[k].isnull)
             knull |= (1U << k);
-        h = pgs_mix64(h ^ v) + (cl_ulong)k;
     }
-    return pgs_mix64(h ^ knull);
+    return pgs_hash_keyvals(keyvals, knull);
 }
 
 /* key normalisation: float keys must compare like PostgreSQL's btree
@@ -682,14 +970,23 @@ struct pgs_sh_cells
  * find-or-insert in the global table.  Returns the slot's word pointer or
  * NULL when the probe limit is hit (table full => StromError_DataStoreNoSpace)
  * ------------------------------------------------------------------ */
+/* Both find-or-insert loops below leave only through the loop condition:
+ * a lane that won a slot publishes it inside its own iteration, and a lane
+ * that found the slot BUSY just goes round again.  (With an early `return`
+ * the compiler may park the winner at the reconvergence point behind the
+ * loop while a lane of the same warp spins on the slot it has yet to
+ * publish.) */
 DEVFN cl_ulong *
 pgs_gh_find_slot(const pgs_gstate &gs, const cl_ulong *keyvals,
                  cl_uint knull, cl_ulong hash)
 {
-    cl_uint     mask = gs.gh_nslots - 1;
+    const cl_uint mask = gs.gh_nslots - 1;
     cl_uint     h = (cl_uint)hash & mask;
+    cl_uint     probe = 0;
+    cl_ulong   *found = NULL;
+    bool        done = false;
 
-    for (cl_uint probe = 0; probe < gs.gh_max_probe; )
+    while (!done)
     {
         cl_ulong   *slot = gs.gh_slots + (cl_ulong)h * PGS_SLOT_WORDS;
         cl_uint     st = *((volatile cl_uint *)slot);
@@ -701,14 +998,20 @@ pgs_gh_find_slot(const pgs_gstate &gs, const cl_ulong *keyvals,
             for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
                 same = same && (__ldcg(slot + 1 + k) == keyvals[k]);
             if (same)
-                return slot;
-            h = (h + 1) & mask;
-            probe++;
+            {
+                found = slot;
+                done = true;
+            }
+            else
+            {
+                h = (h + 1) & mask;
+                if (++probe >= gs.gh_max_probe)
+                    done = true;        /* table full */
+            }
         }
         else if ((st & 3U) == PGS_SLOT_EMPTY)
         {
-            cl_uint old = atomicCAS((cl_uint *)slot, PGS_SLOT_EMPTY, PGS_SLOT_BUSY);
-            if (old == PGS_SLOT_EMPTY)
+            if (atomicCAS((cl_uint *)slot, PGS_SLOT_EMPTY, PGS_SLOT_BUSY) == PGS_SLOT_EMPTY)
             {
 #pragma unroll
                 for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
@@ -716,13 +1019,14 @@ pgs_gh_find_slot(const pgs_gstate &gs, const cl_ulong *keyvals,
                 __threadfence();
                 atomicExch((cl_uint *)slot, PGS_SLOT_READY | (knull << 8));
                 atomicAdd(gs.gh_ngroups, 1U);
-                return slot;
+                found = slot;
+                done = true;
             }
             /* lost the race: look at the same slot again */
         }
-        /* BUSY: the owner publishes shortly; re-read the same slot */
+        /* BUSY: the owner publishes shortly; look at the same slot again */
     }
-    return NULL;
+    return found;
 }
 
 /* merge a state (cells + nn bits) into the global table */
@@ -774,11 +1078,14 @@ DEVFN cl_uint
 pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
                  const pagg_row &row, cl_uint knull, cl_ulong hash)
 {
-    cl_uint     mask = sh.nslots - 1;
-    cl_uint     h = (cl_uint)(hash >> 32) & mask;
-    cl_uint     limit = sh.nslots - (sh.nslots >> 2);   /* 75% */
+    const cl_uint mask = sh.nslots - 1;
+    const cl_uint limit = sh.nslots - (sh.nslots >> 2);     /* 75% */
+    cl_uint     h = __umulhi((cl_uint)(hash >> 32), sh.nslots);    /* high bits */
+    cl_uint     probe = 0;
+    cl_uint     found = ~0U;
+    bool        done = false;
 
-    for (cl_uint probe = 0; probe < 64; )
+    while (!done)
     {
         cl_uint st = *((volatile cl_uint *)sh.ctrl_lo(h));
 
@@ -790,15 +1097,22 @@ pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
                 same = same && (*((volatile cl_ulong *)sh.key(k, h)) ==
                                 (row.key[k].isnull ? 0 : row.key[k].ulong_val));
             if (same)
-                return h;
-            h = (h + 1) & mask;
-            probe++;
+            {
+                found = h;
+                done = true;
+            }
+            else
+            {
+                h = (h + 1) & mask;
+                if (++probe >= 64)
+                    done = true;
+            }
         }
         else if ((st & 3U) == PGS_SLOT_EMPTY)
         {
             if (*((volatile cl_uint *)sh_nused) >= limit)
-                return ~0U;
-            if (atomicCAS(sh.ctrl_lo(h), PGS_SLOT_EMPTY, PGS_SLOT_BUSY) == PGS_SLOT_EMPTY)
+                done = true;
+            else if (atomicCAS(sh.ctrl_lo(h), PGS_SLOT_EMPTY, PGS_SLOT_BUSY) == PGS_SLOT_EMPTY)
             {
                 atomicAdd(sh_nused, 1U);
 #pragma unroll
@@ -806,11 +1120,12 @@ pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
                     *sh.key(k, h) = (row.key[k].isnull ? 0 : row.key[k].ulong_val);
                 __threadfence_block();
                 atomicExch(sh.ctrl_lo(h), PGS_SLOT_READY | (knull << 8));
-                return h;
+                found = h;
+                done = true;
             }
         }
     }
-    return ~0U;
+    return found;
 }
 
 /* ------------------------------------------------------------------
@@ -898,17 +1213,6 @@ pgs_writeback_status(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
 }
 
 
-DEVFN cl_ulong
-pgs_hash_keyvals(const cl_ulong *keyvals, cl_uint knull)
-{
-    cl_ulong    h = 0x9e3779b97f4a7c15ULL;
-
-#pragma unroll
-    for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
-        h = pgs_mix64(h ^ keyvals[k]) + (cl_ulong)k;
-    return pgs_mix64(h ^ knull);
-}
-
 /* ------------------------------------------------------------------
  * the main kernel
  * ------------------------------------------------------------------ */
@@ -920,6 +1224,7 @@ struct pgs_smem_head
     cl_uint     nul_pos[PGS_MAX(GPUPREAGG_NUM_INCOLS, 1)];
     cl_uint     sh_nused;
     cl_uint     is_last_cta;
+    cl_ushort   rowq[PGS_MAX(PGS_ROWQ_BYTES / 2, 1)];
 };
 
 #define PGS_X_INCOL_LOADPOS(slot,colidx,attlen)                         \
@@ -1004,7 +1309,7 @@ pgs_group_add_row(const pgs_gstate &gs, const pgs_sh_table &sh,
 
         cells.p0 = sh.cell(0, s);
         cells.stride = sh.nslots;
-        nn = gpupreagg_aggcalc_atomic(cells, prow);
+        nn = gpupreagg_aggcalc_shared(cells, prow);
         if ((*((volatile cl_uint *)sh.ctrl_hi(s)) & nn) != nn)
             atomicOr(sh.ctrl_hi(s), nn);
     }
@@ -1013,6 +1318,40 @@ pgs_group_add_row(const pgs_gstate &gs, const pgs_sh_table &sh,
         if (ctx.errcode == StromError_Success)
             ctx.errcode = StromError_DataStoreNoSpace;
     }
+}
+
+/* a row whose qual / projection raised an error: re-check rows are flagged in
+ * the chunk's bitmap, the first significant error is kept */
+DEVFN void
+pgs_note_error(cl_int errcode, cl_uint row, cl_uint *recheck_map, pgs_row_ctx &ctx)
+{
+    if (errcode == StromError_CpuReCheck)
+    {
+        atomicOr(&recheck_map[row >> 5], 1U << (row & 31));
+        ctx.nrecheck++;
+    }
+    else if (ctx.errcode == StromError_Success)
+        ctx.errcode = errcode;
+}
+
+/* one queued row (it passed the qual already): projection from the staged
+ * tile, then into the group state */
+template <typename KDS>
+DEVFN void
+pgs_group_add_queued(const kern_parambuf *kparams, const KDS &tile,
+                     const void *ktoast, cl_uint row,
+                     const pgs_gstate &gs, const pgs_sh_table &sh,
+                     cl_uint *sh_nused, cl_uint *recheck_map, pgs_row_ctx &ctx)
+{
+    pagg_row    prow;
+    cl_int      e = StromError_Success;
+
+    gpupreagg_projection(&e, kparams, tile, prow, ktoast, row, 0);
+    gpupreagg_aggcheck(&e, prow);
+    if (e != StromError_Success)
+        pgs_note_error(e, row, recheck_map, ctx);
+    else
+        pgs_group_add_row(gs, sh, sh_nused, prow, ctx);
 }
 
 /* threads of the CTA -> thread 0, always combined in the same order: lanes by
@@ -1247,7 +1586,11 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
         /* ===== consumer warps ===== */
         const cl_uint   ctid = threadIdx.x - 32;
         cl_uint         it = 0;
+#if GPUPREAGG_NUM_KEYS == 0
+        pgs_tacc        tacc;
 
+        tacc.init();
+#endif
         for (cl_uint t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
         {
             cl_uint stage = it % nstages;
@@ -1264,37 +1607,150 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
 
             /* each thread takes 4 consecutive rows: phase 1 pulls them out of
              * the stage with 128-bit shared memory loads, phase 2 evaluates
-             * them one by one from registers */
+             * them from registers */
+#if GPUPREAGG_NUM_KEYS == 0
             for (cl_uint r = ctid * 4; r < rows; r += GPUPREAGG_CONSUMER_THREADS * 4)
             {
                 kern_row_regs rr[4];
-                bool        nnflag[PGS_MAX(PGS_NUM_NNCLASSES, 1)];
+                pagg_row    prow4[4];
+                bool        valid4[4];
+                bool        fast = (r + 4 <= rows);
 
                 rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
-#pragma unroll
-                for (int k = 0; k < PGS_MAX(PGS_NUM_NNCLASSES, 1); k++)
-                    nnflag[k] = false;
                 GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
-                if (r + 4 <= rows)
+                if (fast)
+                {
+                    /* qual and projection of all 4 rows, straight-line; any
+                     * error or special float sends the batch down the
+                     * careful path below, which evaluates it again */
+                    cl_int      berr = StromError_Success;
+                    cl_uint     md = 0, mf = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        cl_int  e1 = StromError_Success;
+                        cl_int  e2 = StromError_Success;
+
+                        valid4[j] = gpupreagg_qual_eval(&e1, kparams, rr[j], kds_in,
+                                                        row0 + r + j);
+                        gpupreagg_projection(&e2, kparams, rr[j], prow4[j], kds_in,
+                                             row0 + r + j, 0);
+                        berr |= e1 | (valid4[j] ? e2 : StromError_Success);
+                        pgs_row_special(prow4[j], md, mf);
+                    }
+                    fast = (berr == StromError_Success) &
+                           (md < PGS_SPECIAL_F8_LIMIT) & (mf < PGS_SPECIAL_F4_LIMIT);
+                }
+                if (fast)
                 {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        PGS_CONSUME_ROW(j)
+                    {
+                        tacc.calc(prow4[j], valid4[j]);
+#if GPUPREAGG_HAS_QUAL
+                        ctx.nfiltered += (valid4[j] ? 0U : 1U);
+#endif
+                    }
+                    tacc.note_nonnull(prow4, valid4);
                 }
                 else
                 {
+                    bool    nnflag[PGS_MAX(PGS_NUM_NNCLASSES, 1)];
 #pragma unroll
-                    for (int j = 0; j < 3; j++)
+                    for (int k = 0; k < PGS_MAX(PGS_NUM_NNCLASSES, 1); k++)
+                        nnflag[k] = false;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
                         if (r + j < rows)
                             PGS_CONSUME_ROW(j)
-                }
-                if (GPUPREAGG_NUM_KEYS == 0)
                     acc_nn |= pgs_nnflags_to_mask(nnflag);
+                }
             }
+#elif !GPUPREAGG_HAS_QUAL
+            /* GROUP BY, every row takes part: no divergence to repair */
+            for (cl_uint r = ctid * 4; r < rows; r += GPUPREAGG_CONSUMER_THREADS * 4)
+            {
+                kern_row_regs rr[4];
+                bool        nnflag[1];
+
+                rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (r + j < rows)
+                        PGS_CONSUME_ROW(j)
+                (void)nnflag;
+            }
+#else
+            /* GROUP BY under a WHERE clause.  Only a fraction of the rows
+             * reaches the hash table; taking that path per row would run it
+             * with a few lanes of each warp.  So a warp first evaluates the
+             * qual of 128 rows (4 per lane, from registers), compacts the
+             * survivors' tile row numbers into its queue with ballots, and
+             * feeds the table from the queue 32 rows at a time: every lane
+             * re-reads one queued row from the stage (kern_tile_smem view)
+             * and runs projection + find-or-insert + the cell updates.  The
+             * queue is drained before the stage is handed back. */
+            {
+                cl_ushort  *rowq = head->rowq + (warp_id - 1) * PGS_ROWQ_ENTRIES;
+                cl_uint     qn = 0;         /* warp-uniform */
+
+                /* the trip count is the same for every lane of the warp
+                 * (ballots inside): bounds are checked per row */
+                for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
+                     rb += GPUPREAGG_CONSUMER_THREADS * 4)
+                {
+                    const cl_uint r = rb + lane_id * 4;
+                    kern_row_regs rr[4];
+
+                    rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        cl_int      e = StromError_Success;
+                        bool        valid = false;
+                        cl_uint     votes;
+
+                        if (r + j < rows)
+                        {
+                            valid = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
+                                                        row0 + r + j);
+                            if (e != StromError_Success)
+                            {
+                                pgs_note_error(e, row0 + r + j, recheck_map, ctx);
+                                valid = false;
+                            }
+                            else if (!valid)
+                                ctx.nfiltered++;
+                        }
+                        votes = __ballot_sync(0xffffffffU, valid);
+                        if (valid)
+                            rowq[qn + __popc(votes & ((1U << lane_id) - 1U))] =
+                                (cl_ushort)(r + j);
+                        qn += __popc(votes);
+                    }
+                    __syncwarp();
+                    while (qn >= 32)
+                    {
+                        qn -= 32;
+                        pgs_group_add_queued(kparams, tile, kds_in, row0 + rowq[qn + lane_id],
+                                             gs, sh, &head->sh_nused, recheck_map, ctx);
+                    }
+                    __syncwarp();
+                }
+                if (lane_id < qn)
+                    pgs_group_add_queued(kparams, tile, kds_in, row0 + rowq[lane_id],
+                                         gs, sh, &head->sh_nused, recheck_map, ctx);
+            }
+#endif
             __syncwarp();
             if (lane_id == 0)
                 pgs_mbar_arrive(&head->empty_bar[stage]);
         }
+#if GPUPREAGG_NUM_KEYS == 0
+        acc_nn |= tacc.fold(acc);
+#endif
     }
     pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
                       &head->is_last_cta, acc, acc_nn, ctx);

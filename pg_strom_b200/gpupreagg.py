@@ -331,6 +331,8 @@ class Session:
         cfg.result_ncols = ncols
         cfg.result_colmeta = self.result_colmeta
         self.device = device
+        self._result_buf = None
+        self._result_len = 0
         sess = C.c_void_p()
         check(lib.pgs_preagg_open(self.program, self._kparams, C.byref(cfg), C.byref(sess)))
         self.handle = sess
@@ -369,8 +371,10 @@ class Session:
         self.lib.pgs_preagg_recheck_rows(self.handle, ticket, rows, n)
         return [int(r) for r in rows]
 
-    def finish(self, reset=True, nrooms=None):
-        """Partial rows of everything submitted so far."""
+    def finish_raw(self, reset=True, nrooms=None):
+        """Partial rows of everything submitted so far as a TUPSLOT
+        kern_data_store in a pinned buffer the session keeps and reuses:
+        returns (address, kern_data_store view)."""
         lib = self.lib
         ncols = len(self.coltypes)
         if nrooms is None:
@@ -378,7 +382,15 @@ class Session:
                 if self.desc["needs_grouping"] else 16
         for _ in range(4):
             length = lib.pgstrom_kds_tupslot_length(ncols, nrooms)
-            buf = C.create_string_buffer(length)
+            if self._result_len < length:
+                if self._result_buf:
+                    lib.pgs_chunk_free(self._result_buf)
+                self._result_buf = lib.pgs_chunk_alloc(length)
+                if not self._result_buf:
+                    self._result_len = 0
+                    raise MemoryError("pgs_chunk_alloc(%d)" % length)
+                self._result_len = length
+            buf = C.c_void_p(self._result_buf)
             check(lib.pgstrom_kds_tupslot_init(buf, length, ncols, self.result_colmeta, nrooms))
             needed = C.c_uint32()
             status = C.c_int32()
@@ -389,7 +401,13 @@ class Session:
                 continue
             check(rc)
             break
-        kds = C.cast(buf, C.POINTER(kern_data_store)).contents
+        return buf, C.cast(buf, C.POINTER(kern_data_store)).contents
+
+    def finish(self, reset=True, nrooms=None):
+        """Partial rows of everything submitted so far, decoded."""
+        lib = self.lib
+        ncols = len(self.coltypes)
+        buf, kds = self.finish_raw(reset, nrooms)
         values = (C.c_uint64 * ncols)()
         isnull = C.create_string_buffer(ncols)
         rows = []
@@ -412,6 +430,10 @@ class Session:
         if self.handle:
             self.lib.pgs_preagg_close(self.handle)
             self.handle = None
+        if getattr(self, "_result_buf", None):
+            self.lib.pgs_chunk_free(self._result_buf)
+            self._result_buf = None
+            self._result_len = 0
         if self.program:
             self.lib.pgs_program_release(self.program)
             self.program = None
