@@ -36,8 +36,14 @@ import numpy as np  # noqa: E402
 
 DEFAULT_ROWS = {"nogrp_agg": 100_000_000, "where_agg": 125_000_000,
                 "high_cardinality": 100_000_000}
-DEFAULT_CHUNK = {"nogrp_agg": 25_000_000, "where_agg": 25_000_000,
-                 "high_cardinality": 12_500_000}
+# device-resident chunks: the column format (KDS_FORMAT_COLUMN) has no 15 MB
+# limit, a chunk is as large as its 32-bit length field allows
+DEFAULT_CHUNK = {"nogrp_agg": 100_000_000, "where_agg": 125_000_000,
+                 "high_cardinality": 50_000_000}
+# host chunks of the end-to-end run: small enough that the H2D copy of one
+# chunk overlaps the kernel of the previous one
+DEFAULT_E2E_CHUNK = {"nogrp_agg": 12_500_000, "where_agg": 12_500_000,
+                     "high_cardinality": 12_500_000}
 METRIC = "GpuPreAgg (partial GROUP BY / no-group aggregation with fused qual) throughput"
 SQL = {
     "nogrp_agg": "SELECT count(*), count(x), sum(x), avg(x), min(x), max(x), sum(y), "
@@ -58,6 +64,7 @@ def parse_args():
     ap.add_argument("--workload", default="nogrp_agg", choices=sorted(DEFAULT_ROWS))
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU")
     ap.add_argument("--chunk-rows", type=int, default=0)
+    ap.add_argument("--e2e-chunk-rows", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
@@ -238,23 +245,27 @@ def bench_ours(args):
     desc = plan.describe()
     node = plan.tree()["lefttree"]
 
-    # ---- synthetic table: pinned host chunks + resident device copies ----
+    # ---- synthetic table: resident device chunks + pinned host chunks ----
     colchunks = generate_columns(workload, rank, rows, chunk_rows)
     coltypes = [t for _, t in w["table"].columns]
     host_chunks, dev_chunks = [], []
     for cols in colchunks:
         ds = gp.DataStore(coltypes, cols, nrows=len(cols[0][0]))
-        host_chunks.append(ds)
         dptr = lib.pgs_device_alloc(0, ds.length)
         assert dptr, lib.pgs_last_error()
         _capi.check(lib.pgs_device_upload(0, dptr, ds.ptr, ds.length))
         dev_chunks.append((dptr, ds.length, ds.nrows))
+        ds.free()
+    e2e_chunk_rows = min(args.e2e_chunk_rows or DEFAULT_E2E_CHUNK[workload], rows)
+    for cols in generate_columns(workload, rank, rows, e2e_chunk_rows):
+        host_chunks.append(gp.DataStore(coltypes, cols, nrows=len(cols[0][0])))
     total_bytes = sum(d.length for d in host_chunks)
     nullable = sum(1 for c in colchunks[0] if c[1] is not None)
     alg_bytes_per_row = desc["row_bytes"] + nullable / 8.0
 
     sess = gp.Session(plan, max_async_chunks=3, max_chunk_rows=chunk_rows,
                       max_chunk_bytes=max(d.length for d in host_chunks))
+    total_dev_bytes = sum(length for _, length, _ in dev_chunks)
     comm = C.c_void_p()
     if world > 1:
         uid = C.create_string_buffer(128)
@@ -381,7 +392,8 @@ def bench_ours(args):
             "config": {"workload": workload, "sql": SQL[workload],
                        "rows_per_gpu": rows, "chunk_rows": chunk_rows,
                        "chunks_per_step": len(dev_chunks),
-                       "input_bytes_per_gpu": total_bytes,
+                       "e2e_chunk_rows": e2e_chunk_rows,
+                       "input_bytes_per_gpu": total_dev_bytes,
                        "algorithmic_bytes_per_row": alg_bytes_per_row,
                        "l2_policy": "inputs (%.2f GB per step) are larger than L2 (126 MB)"
                                     % (total_bytes / 1e9),

@@ -137,6 +137,8 @@ program_options(int extra_flags)
     o += "warps=" + std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "16");
     o += ";minctas=" + std::string(getenv("PGSTROM_MIN_CTAS") ? getenv("PGSTROM_MIN_CTAS") : "1");
     o += ";opt=" + std::string(pgs::guc_bool("pg_strom.devprog_enable_optimization") ? "1" : "0");
+    if (getenv("PGSTROM_DEBUG_LEVEL"))      /* timing experiments only: wrong results */
+        o += ";debug=" + std::string(getenv("PGSTROM_DEBUG_LEVEL"));
     return o;
 }
 
@@ -153,10 +155,12 @@ nvrtc_build(pgs_program *prog)
         std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "16");
     std::string d_rpt = "-DGPUPREAGG_MIN_CTAS=" +
         std::string(getenv("PGSTROM_MIN_CTAS") ? getenv("PGSTROM_MIN_CTAS") : "1");
+    std::string d_dbg = "-DGPUPREAGG_DEBUG_LEVEL=" +
+        std::string(getenv("PGSTROM_DEBUG_LEVEL") ? getenv("PGSTROM_DEBUG_LEVEL") : "0");
     std::vector<const char *> opts = {
         "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
         "-device-int128", "--fmad=false",
-        d_warps.c_str(), d_rpt.c_str(),
+        d_warps.c_str(), d_rpt.c_str(), d_dbg.c_str(),
     };
     if (!pgs::guc_bool("pg_strom.devprog_enable_optimization"))
         opts.push_back("-Xptxas=-O0");
@@ -763,21 +767,20 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
         s->sh_nslots = 0;
         if (s->desc.num_keys > 0)
         {
-            /* the table wants 2 x groups slots; leave room for >= 2 stages of
-             * 1024 rows.  A CTA-local table only pays when most groups fit. */
-            double want = std::max(64.0, config->num_groups * 2.0);
+            /* the table is used up to 75%; 1.7 x groups slots (any multiple
+             * of 32) keeps linear-probe chains short without eating the
+             * staging ring (measured: 1408 / 1696 / 2048 slots for 1000
+             * groups -> 0.66 / 0.51 / 0.84 ms per 50M rows).  A CTA-local
+             * table only pays when most groups fit. */
+            double want = std::max(64.0, config->num_groups * 1.7);
             size_t avail = (smem_max > head + 2 * per1k + 1024
                             ? smem_max - head - 2 * per1k - 1024 : 0);
-            size_t maxslots = 0;
-            for (size_t n = 64; n * s->desc.sh_slot_bytes <= avail; n <<= 1)
-                maxslots = n;
-            size_t nslots = 64;
-            while ((double)nslots < want && nslots < maxslots)
-                nslots <<= 1;
+            size_t maxslots = (avail / s->desc.sh_slot_bytes) & ~(size_t)31;
+            size_t nslots = ((size_t)want + 31) & ~(size_t)31;
             const char *env = getenv("PGSTROM_SH_SLOTS");
             if (env)
-                nslots = (size_t)atol(env);
-            if (maxslots == 0 || (!env && config->num_groups > 4.0 * (double)maxslots))
+                nslots = ((size_t)atol(env) + 31) & ~(size_t)31;
+            if (maxslots == 0 || (!env && config->num_groups > 3.0 * (double)maxslots))
                 nslots = 0;
             if (nslots > maxslots)
                 nslots = maxslots;
@@ -1153,9 +1156,7 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     if (!s || !kds_dst)
         return StromError_BadRequestMessage;
     CUDA_CHECK(cudaSetDevice(s->ordinal));
-    int rc = drain(s);
-    if (rc != StromError_Success)
-        return rc;
+    int rc = StromError_Success;
     if (kds_dst->format != KDS_FORMAT_TUPSLOT || kds_dst->ncols != s->desc.num_outcols)
     {
         set_error("pgs_preagg_finish: destination must be a TUPSLOT store with %u columns",
@@ -1214,8 +1215,16 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(s->h_result_head + 64, d_dst, first,
                             cudaMemcpyDeviceToHost, s->s_exec);
+    /* one wait for everything: the chunks still in flight, the flush and
+     * the copies are ordered on the exec stream */
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(s->s_exec);
+    if (e == cudaSuccess)
+    {
+        rc = drain(s);          /* chunk results; nothing left to wait for */
+        if (rc != StromError_Success)
+            return rc;
+    }
     if (e == cudaSuccess)
     {
         h_status = *((int32_t *)s->h_result_head);

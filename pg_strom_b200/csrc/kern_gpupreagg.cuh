@@ -63,6 +63,9 @@
 #define GPUPREAGG_HAS_QUAL          1
 #endif
 
+#ifndef GPUPREAGG_DEBUG_LEVEL
+#define GPUPREAGG_DEBUG_LEVEL       0
+#endif
 #ifndef PGS_ROWS_PER_THREAD
 #define PGS_ROWS_PER_THREAD         4
 #endif
@@ -384,52 +387,107 @@ struct pgs_i128 { cl_ulong lo, hi; };
 #define PGS_TACC_INIT_PMAX_FLOAT(a)     (a) = PGS_F8_NEGINF;
 #define PGS_TACC_INIT_PMAX_DOUBLE(a)    (a) = PGS_F8_NEGINF;
 
-/* predicated single instructions the compiler would otherwise turn into
- * compute + select pairs */
-DEVFN void
-pgs_pred_dadd(double &acc, double x, bool ok)
+/* Updates take a batch of 4 rows (d0..d3 projected datums, k0..k3 "row is
+ * valid and the datum is not NULL").  The consumer loop is bound by the ALU
+ * pipe (LOP3 / SEL / IADD3 / VIMNMX, one warp instruction per two cycles and
+ * SM sub-partition), so the formulations below push work to the FMA and FP64
+ * pipes where they can:
+ *   - int4 -> int8 sums: zero the NULL addends (1 SEL each), then
+ *     IMAD.WIDE acc = x * one + acc; `one` is a run-time 1 the compiler cannot
+ *     fold, otherwise it emits IADD3 + LEA.HI.X.SX32 (two more ALU ops)
+ *   - float8 sums: acc = fma(x, k ? 1.0 : 0.0, acc): one SEL for the high word
+ *     of the factor and one DFMA, instead of DADD + two FSEL.  x * 0.0 is an
+ *     exact zero because special floats never reach this path.
+ *   - counts: one 3-input add per two rows. */
+#define PGS_K01(k)      ((k) ? 1U : 0U)
+#define PGS_KF8(k)      __hiloint2double((k) ? 0x3FF00000 : 0, 0)
+
+DEVFN cl_long
+pgs_madwide(cl_int x, cl_int y, cl_long acc)
 {
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p add.f64 %0, %0, %1;\n\t}"
-        : "+d"(acc) : "d"(x), "r"((cl_uint)ok));
-}
-DEVFN void
-pgs_pred_madwide(cl_long &acc, cl_int x, bool ok)
-{
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p mad.wide.s32 %0, %1, 1, %0;\n\t}"
-        : "+l"(acc) : "r"(x), "r"((cl_uint)ok));
-}
-DEVFN void
-pgs_pred_dmin(double &acc, double x, bool ok)       /* x is not NaN */
-{
-    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\t"
-        "setp.ltu.and.f64 q, %1, %0, p;\n\t@q mov.f64 %0, %1;\n\t}"
-        : "+d"(acc) : "d"(x), "r"((cl_uint)ok));
-}
-DEVFN void
-pgs_pred_dmax(double &acc, double x, bool ok)       /* x is not NaN */
-{
-    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\t"
-        "setp.gt.and.f64 q, %1, %0, p;\n\t@q mov.f64 %0, %1;\n\t}"
-        : "+d"(acc) : "d"(x), "r"((cl_uint)ok));
+    cl_long r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(x), "r"(y), "l"(acc));
+    return r;
 }
 
-#define PGS_TACC_CALC_PSUM_INT(a,d,ok)      (a) += ((ok) ? (cl_uint)(d).int_val : 0U);
-#define PGS_TACC_CALC_PSUM_LONGS(a,d,ok)    pgs_pred_madwide((a), (cl_int)(d).long_val, (ok));
-#define PGS_TACC_CALC_PSUM_LONG(a,d,ok)                                 \
+/* nrows(): the addend is 0 or 1 (gpupreagg.c:1559-1600) - count bits */
+#define PGS_TACC_CALC4_PSUM_INT(a,d0,d1,d2,d3,k0,k1,k2,k3)              \
+    (a) += __popc((((k0) & ((d0).int_val != 0)) ? 1U : 0U) |            \
+                  (((k1) & ((d1).int_val != 0)) ? 2U : 0U) |            \
+                  (((k2) & ((d2).int_val != 0)) ? 4U : 0U) |            \
+                  (((k3) & ((d3).int_val != 0)) ? 8U : 0U));
+#define PGS_TACC_CALC4_PSUM_LONGS(a,d0,d1,d2,d3,k0,k1,k2,k3)            \
+    (a) = pgs_madwide((k0) ? (cl_int)(d0).long_val : 0, one, (a));      \
+    (a) = pgs_madwide((k1) ? (cl_int)(d1).long_val : 0, one, (a));      \
+    (a) = pgs_madwide((k2) ? (cl_int)(d2).long_val : 0, one, (a));      \
+    (a) = pgs_madwide((k3) ? (cl_int)(d3).long_val : 0, one, (a));
+#define PGS_TACC_ADD128(a,d,k)                                          \
     pgs_add128_PLAIN(&(a).lo, &(a).hi, (cl_ulong)(d).long_val,          \
-                     (d).long_val < 0 ? ~0ULL : 0ULL, (ok));
-#define PGS_TACC_CALC_PSUM_FLOAT(a,d,ok)    pgs_pred_dadd((a), (double)(d).float_val, (ok));
-#define PGS_TACC_CALC_PSUM_DOUBLE(a,d,ok)   pgs_pred_dadd((a), (d).double_val, (ok));
-#define PGS_TACC_CALC_PMIN_SHORT(a,d,ok)    if (ok) (a) = min((a), (cl_int)(d).short_val);
-#define PGS_TACC_CALC_PMIN_INT(a,d,ok)      if (ok) (a) = min((a), (d).int_val);
-#define PGS_TACC_CALC_PMIN_LONG(a,d,ok)     if ((ok) & ((d).long_val < (a))) (a) = (d).long_val;
-#define PGS_TACC_CALC_PMIN_FLOAT(a,d,ok)    pgs_pred_dmin((a), (double)(d).float_val, (ok));
-#define PGS_TACC_CALC_PMIN_DOUBLE(a,d,ok)   pgs_pred_dmin((a), (d).double_val, (ok));
-#define PGS_TACC_CALC_PMAX_SHORT(a,d,ok)    if (ok) (a) = max((a), (cl_int)(d).short_val);
-#define PGS_TACC_CALC_PMAX_INT(a,d,ok)      if (ok) (a) = max((a), (d).int_val);
-#define PGS_TACC_CALC_PMAX_LONG(a,d,ok)     if ((ok) & ((d).long_val > (a))) (a) = (d).long_val;
-#define PGS_TACC_CALC_PMAX_FLOAT(a,d,ok)    pgs_pred_dmax((a), (double)(d).float_val, (ok));
-#define PGS_TACC_CALC_PMAX_DOUBLE(a,d,ok)   pgs_pred_dmax((a), (d).double_val, (ok));
+                     (d).long_val < 0 ? ~0ULL : 0ULL, (k));
+#define PGS_TACC_CALC4_PSUM_LONG(a,d0,d1,d2,d3,k0,k1,k2,k3)             \
+    PGS_TACC_ADD128(a,d0,k0) PGS_TACC_ADD128(a,d1,k1)                   \
+    PGS_TACC_ADD128(a,d2,k2) PGS_TACC_ADD128(a,d3,k3)
+#define PGS_TACC_CALC4_PSUM_FLOAT(a,d0,d1,d2,d3,k0,k1,k2,k3)            \
+    (a) = fma((double)(d0).float_val, PGS_KF8(k0), (a));                \
+    (a) = fma((double)(d1).float_val, PGS_KF8(k1), (a));                \
+    (a) = fma((double)(d2).float_val, PGS_KF8(k2), (a));                \
+    (a) = fma((double)(d3).float_val, PGS_KF8(k3), (a));
+#define PGS_TACC_CALC4_PSUM_DOUBLE(a,d0,d1,d2,d3,k0,k1,k2,k3)           \
+    (a) = fma((d0).double_val, PGS_KF8(k0), (a));                       \
+    (a) = fma((d1).double_val, PGS_KF8(k1), (a));                       \
+    (a) = fma((d2).double_val, PGS_KF8(k2), (a));                       \
+    (a) = fma((d3).double_val, PGS_KF8(k3), (a));
+#define PGS_TACC_MIN1(a,v,k)    if (k) (a) = min((a), (v));
+#define PGS_TACC_MAX1(a,v,k)    if (k) (a) = max((a), (v));
+#define PGS_TACC_CALC4_PMIN_SHORT(a,d0,d1,d2,d3,k0,k1,k2,k3)            \
+    PGS_TACC_MIN1(a,(cl_int)(d0).short_val,k0) PGS_TACC_MIN1(a,(cl_int)(d1).short_val,k1) \
+    PGS_TACC_MIN1(a,(cl_int)(d2).short_val,k2) PGS_TACC_MIN1(a,(cl_int)(d3).short_val,k3)
+#define PGS_TACC_CALC4_PMIN_INT(a,d0,d1,d2,d3,k0,k1,k2,k3)              \
+    PGS_TACC_MIN1(a,(d0).int_val,k0) PGS_TACC_MIN1(a,(d1).int_val,k1)   \
+    PGS_TACC_MIN1(a,(d2).int_val,k2) PGS_TACC_MIN1(a,(d3).int_val,k3)
+#define PGS_TACC_CALC4_PMIN_LONG(a,d0,d1,d2,d3,k0,k1,k2,k3)             \
+    PGS_TACC_MIN1(a,(d0).long_val,k0) PGS_TACC_MIN1(a,(d1).long_val,k1) \
+    PGS_TACC_MIN1(a,(d2).long_val,k2) PGS_TACC_MIN1(a,(d3).long_val,k3)
+#define PGS_TACC_CALC4_PMAX_SHORT(a,d0,d1,d2,d3,k0,k1,k2,k3)            \
+    PGS_TACC_MAX1(a,(cl_int)(d0).short_val,k0) PGS_TACC_MAX1(a,(cl_int)(d1).short_val,k1) \
+    PGS_TACC_MAX1(a,(cl_int)(d2).short_val,k2) PGS_TACC_MAX1(a,(cl_int)(d3).short_val,k3)
+#define PGS_TACC_CALC4_PMAX_INT(a,d0,d1,d2,d3,k0,k1,k2,k3)              \
+    PGS_TACC_MAX1(a,(d0).int_val,k0) PGS_TACC_MAX1(a,(d1).int_val,k1)   \
+    PGS_TACC_MAX1(a,(d2).int_val,k2) PGS_TACC_MAX1(a,(d3).int_val,k3)
+#define PGS_TACC_CALC4_PMAX_LONG(a,d0,d1,d2,d3,k0,k1,k2,k3)             \
+    PGS_TACC_MAX1(a,(d0).long_val,k0) PGS_TACC_MAX1(a,(d1).long_val,k1) \
+    PGS_TACC_MAX1(a,(d2).long_val,k2) PGS_TACC_MAX1(a,(d3).long_val,k3)
+/* x is never NaN here: the unordered compare also adopts x while the cell is
+ * still NaN.  Written in PTX so that the predicate stays an input of the one
+ * DSETP instead of a second level of selects. */
+DEVFN void
+pgs_pred_dmin(double &acc, double x, bool ok)
+{
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\t"
+        "setp.ltu.and.f64 q, %1, %0, p;\n\tselp.f64 %0, %1, %0, q;\n\t}"
+        : "+d"(acc) : "d"(x), "r"((cl_uint)ok));
+}
+DEVFN void
+pgs_pred_dmax(double &acc, double x, bool ok)
+{
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\t"
+        "setp.gt.and.f64 q, %1, %0, p;\n\tselp.f64 %0, %1, %0, q;\n\t}"
+        : "+d"(acc) : "d"(x), "r"((cl_uint)ok));
+}
+#define PGS_TACC_FMIN1(a,x,k)   pgs_pred_dmin((a), (x), (k));
+#define PGS_TACC_FMAX1(a,x,k)   pgs_pred_dmax((a), (x), (k));
+#define PGS_TACC_CALC4_PMIN_FLOAT(a,d0,d1,d2,d3,k0,k1,k2,k3)            \
+    PGS_TACC_FMIN1(a,(double)(d0).float_val,k0) PGS_TACC_FMIN1(a,(double)(d1).float_val,k1) \
+    PGS_TACC_FMIN1(a,(double)(d2).float_val,k2) PGS_TACC_FMIN1(a,(double)(d3).float_val,k3)
+#define PGS_TACC_CALC4_PMIN_DOUBLE(a,d0,d1,d2,d3,k0,k1,k2,k3)           \
+    PGS_TACC_FMIN1(a,(d0).double_val,k0) PGS_TACC_FMIN1(a,(d1).double_val,k1) \
+    PGS_TACC_FMIN1(a,(d2).double_val,k2) PGS_TACC_FMIN1(a,(d3).double_val,k3)
+#define PGS_TACC_CALC4_PMAX_FLOAT(a,d0,d1,d2,d3,k0,k1,k2,k3)            \
+    PGS_TACC_FMAX1(a,(double)(d0).float_val,k0) PGS_TACC_FMAX1(a,(double)(d1).float_val,k1) \
+    PGS_TACC_FMAX1(a,(double)(d2).float_val,k2) PGS_TACC_FMAX1(a,(double)(d3).float_val,k3)
+#define PGS_TACC_CALC4_PMAX_DOUBLE(a,d0,d1,d2,d3,k0,k1,k2,k3)           \
+    PGS_TACC_FMAX1(a,(d0).double_val,k0) PGS_TACC_FMAX1(a,(d1).double_val,k1) \
+    PGS_TACC_FMAX1(a,(d2).double_val,k2) PGS_TACC_FMAX1(a,(d3).double_val,k3)
 
 /* accumulator -> cell-domain value(s) at src[c] */
 #define PGS_TACC_CELL_PSUM_INT(a,src,c)     (src)[c] = (cl_ulong)(a);
@@ -604,9 +662,13 @@ pgs_add128_SHARED(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool
       PGS_AGGCALC_##OP##_##TYPE(THREAD,cells,c,row.agg[i],__ok) }
 #define PGS_X_TACC_DECL(i,c,OP,TYPE)    PGS_TACC_TYPE_##OP##_##TYPE a##i;
 #define PGS_X_TACC_INIT(i,c,OP,TYPE)    PGS_TACC_INIT_##OP##_##TYPE(a##i)
-#define PGS_X_TACC_CALC(i,c,OP,TYPE)                                    \
-    { bool __ok = valid & !row.agg[i].isnull;                           \
-      PGS_TACC_CALC_##OP##_##TYPE(a##i,row.agg[i],__ok) }
+#define PGS_X_TACC_CALC4(i,c,OP,TYPE)                                   \
+    PGS_TACC_CALC4_##OP##_##TYPE(a##i,                                  \
+        rows[0].agg[i], rows[1].agg[i], rows[2].agg[i], rows[3].agg[i], \
+        (valids[0] & !rows[0].agg[i].isnull),                           \
+        (valids[1] & !rows[1].agg[i].isnull),                           \
+        (valids[2] & !rows[2].agg[i].isnull),                           \
+        (valids[3] & !rows[3].agg[i].isnull))
 #define PGS_X_TACC_CELL(i,c,OP,TYPE)    PGS_TACC_CELL_##OP##_##TYPE(a##i,src,c)
 #define PGS_X_CALC_SHARED(i,c,OP,TYPE)                                  \
     { bool __ok = !row.agg[i].isnull;                                   \
@@ -697,11 +759,12 @@ struct pgs_tacc
         for (int k = 0; k < PGS_MAX(PGS_NUM_NNCLASSES, 1); k++)
             nnflag[k] = false;
     }
-    /* one row of a batch without errors and special floats */
+    /* a batch of 4 rows without errors and special floats; `one` is 1 */
     __device__ __forceinline__ void
-    calc(const pagg_row &row, bool valid)
+    calc4(const pagg_row *rows, const bool *valids, cl_int one)
     {
-        GPUPREAGG_AGG_LIST(PGS_X_TACC_CALC)
+        GPUPREAGG_AGG_LIST(PGS_X_TACC_CALC4)
+        (void)one;
     }
     /* "saw a non-NULL input" of the whole batch: OR over the rows first, so
      * that tests of adjacent validity bits fold into one */
@@ -801,17 +864,73 @@ pgs_stage_nul_off(int slot, cl_uint tile_rows)
 }
 #define PGS_STAGE_BYTES(tile_rows)  pgs_stage_nul_off(GPUPREAGG_NUM_INCOLS, (tile_rows))
 /* head of dynamic smem: 2 x MAX_STAGES mbarriers, column positions */
-/* per consumer warp: queue of the tile rows that passed the qual (GROUP BY
- * with a WHERE clause only, see the consumer loop) */
-#define PGS_ROWQ_ENTRIES    160             /* 128 new per iteration + < 32 left */
+/* per consumer warp: queue of the rows that passed the qual (GROUP BY with a
+ * WHERE clause only, see the consumer loop).  It carries the staged column
+ * values of the row, so it outlives the tile the row came from:
+ *   [col0 values | col1 values | ... | validity mask (u32) | row number (u32)]
+ * with PGS_ROWQ_ENTRIES entries per array. */
+#define PGS_ROWQ_ENTRIES    64              /* < 32 left over + 32 new */
+DEVFN cl_uint
+pgs_rowq_val_off(int slot)
+{
+    cl_uint off = 0;
+#pragma unroll
+    for (int s = 0; s < slot; s++)
+        off += PGS_ROWQ_ENTRIES * GPUPREAGG_INCOL_ATTLEN(s);
+    return off;
+}
+#define PGS_ROWQ_MASK_OFF   pgs_rowq_val_off(GPUPREAGG_NUM_INCOLS)
+#define PGS_ROWQ_ROW_OFF    (PGS_ROWQ_MASK_OFF + 4 * PGS_ROWQ_ENTRIES)
+#define PGS_ROWQ_WARP_BYTES (PGS_ROWQ_ROW_OFF + 4 * PGS_ROWQ_ENTRIES)
 #if GPUPREAGG_NUM_KEYS > 0 && GPUPREAGG_HAS_QUAL
-#define PGS_ROWQ_BYTES      (2 * PGS_ROWQ_ENTRIES * GPUPREAGG_CONSUMER_WARPS)
+#define PGS_ROWQ_BYTES      (PGS_ROWQ_WARP_BYTES * GPUPREAGG_CONSUMER_WARPS)
 #else
 #define PGS_ROWQ_BYTES      0
 #endif
-#define PGS_SMEM_HEAD_BYTES \
-    PGS_ALIGN128(16 * GPUPREAGG_MAX_STAGES + 8 * PGS_MAX(GPUPREAGG_NUM_INCOLS,1) + 64 + \
-                 PGS_ROWQ_BYTES)
+/* head of dynamic smem: 2 x MAX_STAGES mbarriers, column positions, misc
+ * (pgs_smem_head, 128-byte aligned), then the row queues */
+#define PGS_SMEM_HEAD_FIXED \
+    PGS_ALIGN128(16 * GPUPREAGG_MAX_STAGES + 8 * PGS_MAX(GPUPREAGG_NUM_INCOLS,1) + 64)
+#define PGS_SMEM_HEAD_BYTES     PGS_ALIGN128(PGS_SMEM_HEAD_FIXED + PGS_ROWQ_BYTES)
+
+/* view of one warp's row queue for the generated functions: "row" i is
+ * queue entry i */
+struct kern_rowq_smem
+{
+    cl_uint     base;           /* smem offset of the warp's queue */
+
+    template <typename T>
+    __device__ __forceinline__ bool
+    fetch(int slot, cl_uint idx, T &out) const
+    {
+        out = *((const T *)(__pgs_smem + base + pgs_rowq_val_off(slot)) + idx);
+        return ((*((const cl_uint *)(__pgs_smem + base + PGS_ROWQ_MASK_OFF) + idx)
+                 >> slot) & 1U) != 0;
+    }
+    __device__ __forceinline__ cl_uint
+    rownum(cl_uint idx) const
+    {
+        return *((const cl_uint *)(__pgs_smem + base + PGS_ROWQ_ROW_OFF) + idx);
+    }
+};
+/* store of one value by width */
+template <int ATTLEN> struct pgs_rowq_store;
+template <> struct pgs_rowq_store<8>
+{ static __device__ __forceinline__ void put(unsigned char *p, cl_uint i, cl_ulong v)
+  { ((cl_ulong *)p)[i] = v; } };
+template <> struct pgs_rowq_store<4>
+{ static __device__ __forceinline__ void put(unsigned char *p, cl_uint i, cl_ulong v)
+  { ((cl_uint *)p)[i] = (cl_uint)v; } };
+template <> struct pgs_rowq_store<2>
+{ static __device__ __forceinline__ void put(unsigned char *p, cl_uint i, cl_ulong v)
+  { ((cl_ushort *)p)[i] = (cl_ushort)v; } };
+template <> struct pgs_rowq_store<1>
+{ static __device__ __forceinline__ void put(unsigned char *p, cl_uint i, cl_ulong v)
+  { ((unsigned char *)p)[i] = (unsigned char)v; } };
+#define PGS_X_INCOL_QPUSH(slot,colidx,attlen)                           \
+    pgs_rowq_store<attlen>::put(__pgs_smem + rowq.base + pgs_rowq_val_off(slot), \
+                                __pos, __row.v[slot]);                  \
+    __mask |= (((__row.vbits[slot] >> __row.shift) & 1U) << (slot));
 
 /* ------------------------------------------------------------------
  * mbarrier + bulk async copy (TMA engine, 1-D) wrappers
@@ -944,7 +1063,7 @@ pgs_f8_canon(double v)
 struct pgs_sh_table
 {
     cl_uint     base;       /* offset in __pgs_smem */
-    cl_uint     nslots;     /* power of two, 0 = disabled */
+    cl_uint     nslots;     /* multiple of 32, 0 = disabled */
 
     __device__ __forceinline__ cl_uint *ctrl_lo(cl_uint s) const
     { return (cl_uint *)(__pgs_smem + base) + s; }
@@ -1048,37 +1167,12 @@ pgs_gh_merge_state(const pgs_gstate &gs, const cl_ulong *keyvals, cl_uint knull,
     return true;
 }
 
-DEVFN bool
-pgs_gh_add_row(const pgs_gstate &gs, const pagg_row &row, cl_uint knull,
-               cl_ulong hash)
-{
-    cl_ulong    keyvals[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
-    cl_ulong   *slot;
-    cl_ulong   *cells;
-    cl_uint    *p_nn;
-    cl_uint     nn;
-
-#pragma unroll
-    for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
-        keyvals[k] = row.key[k].isnull ? 0 : row.key[k].ulong_val;
-    slot = pgs_gh_find_slot(gs, keyvals, knull, hash);
-    if (!slot)
-        return false;
-    cells = slot + 1 + GPUPREAGG_NUM_KEYS;
-    nn = gpupreagg_aggcalc_atomic(cells, row);
-    p_nn = (cl_uint *)slot + 1;
-    if ((*((volatile cl_uint *)p_nn) & nn) != nn)
-        atomicOr(p_nn, nn);
-    return true;
-}
-
 /* find-or-insert in the CTA-local table; returns slot index or ~0U if the
  * table is (nearly) full and the row has to go to the global table */
 DEVFN cl_uint
 pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
-                 const pagg_row &row, cl_uint knull, cl_ulong hash)
+                 const cl_ulong *keyvals, cl_uint knull, cl_ulong hash)
 {
-    const cl_uint mask = sh.nslots - 1;
     const cl_uint limit = sh.nslots - (sh.nslots >> 2);     /* 75% */
     cl_uint     h = __umulhi((cl_uint)(hash >> 32), sh.nslots);    /* high bits */
     cl_uint     probe = 0;
@@ -1094,8 +1188,7 @@ pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
             bool    same = ((st >> 8) == knull);
 #pragma unroll
             for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
-                same = same && (*((volatile cl_ulong *)sh.key(k, h)) ==
-                                (row.key[k].isnull ? 0 : row.key[k].ulong_val));
+                same = same && (*((volatile cl_ulong *)sh.key(k, h)) == keyvals[k]);
             if (same)
             {
                 found = h;
@@ -1103,7 +1196,7 @@ pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
             }
             else
             {
-                h = (h + 1) & mask;
+                h = (h + 1 < sh.nslots ? h + 1 : 0);    /* any table size */
                 if (++probe >= 64)
                     done = true;
             }
@@ -1117,7 +1210,7 @@ pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
                 atomicAdd(sh_nused, 1U);
 #pragma unroll
                 for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
-                    *sh.key(k, h) = (row.key[k].isnull ? 0 : row.key[k].ulong_val);
+                    *sh.key(k, h) = keyvals[k];
                 __threadfence_block();
                 atomicExch(sh.ctrl_lo(h), PGS_SLOT_READY | (knull << 8));
                 found = h;
@@ -1224,7 +1317,6 @@ struct pgs_smem_head
     cl_uint     nul_pos[PGS_MAX(GPUPREAGG_NUM_INCOLS, 1)];
     cl_uint     sh_nused;
     cl_uint     is_last_cta;
-    cl_ushort   rowq[PGS_MAX(PGS_ROWQ_BYTES / 2, 1)];
 };
 
 #define PGS_X_INCOL_LOADPOS(slot,colidx,attlen)                         \
@@ -1257,15 +1349,24 @@ struct pgs_smem_head
                           ? stage_off + pgs_stage_nul_off(slot, tile_rows)         \
                           : KERN_TILE_NO_NULLMAP);
 
+/* careful per-row path of the no-group kernel */
 #define PGS_CONSUME_ROW(j)                                              \
     {                                                                   \
         pagg_row    prow;                                               \
         bool valid = pgs_eval_row(kparams, rr[j], kds_in, row0 + r + (j), \
                                   recheck_map, ctx, prow);              \
-        if (GPUPREAGG_NUM_KEYS == 0)                                    \
-            gpupreagg_aggcalc_thread(acc, prow, valid, nnflag);         \
-        else if (valid)                                                 \
-            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx);      \
+        gpupreagg_aggcalc_thread(acc, prow, valid, nnflag);             \
+    }
+/* GROUP BY without a WHERE clause: every lane of the warp comes here for
+ * row j of its batch (pgs_group_add_row is warp-collective) */
+#define PGS_CONSUME_ROW_GROUPED(j)                                      \
+    {                                                                   \
+        pagg_row    prow;                                               \
+        bool valid = false;                                             \
+        if (r + (j) < rows)                                             \
+            valid = pgs_eval_row(kparams, rr[j], kds_in, row0 + r + (j), \
+                                 recheck_map, ctx, prow);               \
+        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid);   \
     }
 
 /* phase 1 of the staged consumer loop: 4 adjacent rows of one column */
@@ -1291,33 +1392,82 @@ struct pgs_smem_head
                KERN_DATA_STORE_COLPOS(kds_in, colidx)->nullmap_offset)  \
          : (const cl_uint *)NULL);
 
-/* add one projected row to the group state (CTA-local table first) */
+/*
+ * Add one projected row per lane to the group state (CTA-local table first,
+ * global table when that is full or absent).
+ *
+ * Warp-collective: all 32 lanes call it, `active` says whether the lane has
+ * a row.  The probe loops end at a different iteration for every lane; the
+ * __syncwarp() behind each of them brings the lanes back together so that
+ * the chain of cell updates runs once for the warp, not once per group of
+ * lanes that happened to leave the loop together.
+ */
 DEVFN void
 pgs_group_add_row(const pgs_gstate &gs, const pgs_sh_table &sh,
-                  cl_uint *sh_nused, const pagg_row &prow, pgs_row_ctx &ctx)
+                  cl_uint *sh_nused, const pagg_row &prow, pgs_row_ctx &ctx,
+                  bool active)
 {
-    cl_uint     knull;
-    cl_ulong    hash = pgs_hash_keys(prow, knull);
+    cl_ulong    keyvals[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
+    cl_uint     knull = 0;
+    cl_ulong    hash;
     cl_uint     s = ~0U;
+    cl_ulong   *gslot = NULL;
 
-    if (sh.nslots > 0)
-        s = pgs_sh_find_slot(sh, sh_nused, prow, knull, hash);
-    if (s != ~0U)
+#pragma unroll
+    for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
     {
-        pgs_sh_cells cells;
-        cl_uint      nn;
-
-        cells.p0 = sh.cell(0, s);
-        cells.stride = sh.nslots;
-        nn = gpupreagg_aggcalc_shared(cells, prow);
-        if ((*((volatile cl_uint *)sh.ctrl_hi(s)) & nn) != nn)
-            atomicOr(sh.ctrl_hi(s), nn);
+        /* NULL keys form one group (gpupreagg.c:1234-1243) */
+        keyvals[k] = (!active || prow.key[k].isnull) ? 0 : prow.key[k].ulong_val;
+        if (active && prow.key[k].isnull)
+            knull |= (1U << k);
     }
-    else if (!pgs_gh_add_row(gs, prow, knull, hash))
+    hash = pgs_hash_keyvals(keyvals, knull);
+#if GPUPREAGG_DEBUG_LEVEL == 1      /* timing experiment: stop after the hash */
+    ctx.nfiltered += (cl_uint)(hash & 1);
+    return;
+#endif
+    if (sh.nslots > 0)
     {
-        if (ctx.errcode == StromError_Success)
+        if (active)
+            s = pgs_sh_find_slot(sh, sh_nused, keyvals, knull, hash);
+        __syncwarp();
+    }
+#if GPUPREAGG_DEBUG_LEVEL == 2      /* timing experiment: stop after the probe */
+    ctx.nfiltered += (s & 1);
+    return;
+#endif
+    if (__any_sync(0xffffffffU, active && s == ~0U))
+    {
+        if (active && s == ~0U)
+            gslot = pgs_gh_find_slot(gs, keyvals, knull, hash);
+        __syncwarp();
+    }
+    if (active)
+    {
+        if (s != ~0U)
+        {
+            pgs_sh_cells cells;
+            cl_uint      nn;
+
+            cells.p0 = sh.cell(0, s);
+            cells.stride = sh.nslots;
+            nn = gpupreagg_aggcalc_shared(cells, prow);
+            if ((*((volatile cl_uint *)sh.ctrl_hi(s)) & nn) != nn)
+                atomicOr(sh.ctrl_hi(s), nn);
+        }
+        else if (gslot)
+        {
+            cl_ulong   *cells = gslot + 1 + GPUPREAGG_NUM_KEYS;
+            cl_uint    *p_nn = (cl_uint *)gslot + 1;
+            cl_uint     nn = gpupreagg_aggcalc_atomic(cells, prow);
+
+            if ((*((volatile cl_uint *)p_nn) & nn) != nn)
+                atomicOr(p_nn, nn);
+        }
+        else if (ctx.errcode == StromError_Success)
             ctx.errcode = StromError_DataStoreNoSpace;
     }
+    __syncwarp();
 }
 
 /* a row whose qual / projection raised an error: re-check rows are flagged in
@@ -1334,24 +1484,31 @@ pgs_note_error(cl_int errcode, cl_uint row, cl_uint *recheck_map, pgs_row_ctx &c
         ctx.errcode = errcode;
 }
 
-/* one queued row (it passed the qual already): projection from the staged
- * tile, then into the group state */
-template <typename KDS>
-DEVFN void
-pgs_group_add_queued(const kern_parambuf *kparams, const KDS &tile,
-                     const void *ktoast, cl_uint row,
+/* one queued row per lane (it passed the qual already): projection from the
+ * warp's row queue, then into the group state.  Warp-collective like
+ * pgs_group_add_row; lanes without a row pass active = false.  Not inlined:
+ * six copies of this chain would not fit the instruction cache well. */
+static __device__ __noinline__ void
+pgs_group_add_queued(const kern_parambuf *kparams, const kern_rowq_smem &rowq,
+                     const void *ktoast, cl_uint idx, bool active,
                      const pgs_gstate &gs, const pgs_sh_table &sh,
                      cl_uint *sh_nused, cl_uint *recheck_map, pgs_row_ctx &ctx)
 {
     pagg_row    prow;
-    cl_int      e = StromError_Success;
 
-    gpupreagg_projection(&e, kparams, tile, prow, ktoast, row, 0);
-    gpupreagg_aggcheck(&e, prow);
-    if (e != StromError_Success)
-        pgs_note_error(e, row, recheck_map, ctx);
-    else
-        pgs_group_add_row(gs, sh, sh_nused, prow, ctx);
+    if (active)
+    {
+        cl_int  e = StromError_Success;
+
+        gpupreagg_projection(&e, kparams, rowq, prow, ktoast, idx, 0);
+        gpupreagg_aggcheck(&e, prow);
+        if (e != StromError_Success)
+        {
+            pgs_note_error(e, rowq.rownum(idx), recheck_map, ctx);
+            active = false;
+        }
+    }
+    pgs_group_add_row(gs, sh, sh_nused, prow, ctx, active);
 }
 
 /* threads of the CTA -> thread 0, always combined in the same order: lanes by
@@ -1588,13 +1745,25 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
         cl_uint         it = 0;
 #if GPUPREAGG_NUM_KEYS == 0
         pgs_tacc        tacc;
+        const cl_int    one = (cl_int)(nstages != 0);   /* 1, opaque to the compiler */
 
         tacc.init();
+#elif GPUPREAGG_HAS_QUAL
+        kern_rowq_smem  rowq;
+        cl_uint         qn = 0;         /* queued rows, warp-uniform */
+
+        rowq.base = PGS_SMEM_HEAD_FIXED + (warp_id - 1) * PGS_ROWQ_WARP_BYTES;
 #endif
-        for (cl_uint t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
+        cl_uint         stage = 0, phase = 0;
+
+        for (cl_uint t = blockIdx.x; t < ntiles;
+             t += gridDim.x, it++, stage++)
         {
-            cl_uint stage = it % nstages;
-            cl_uint phase = (it / nstages) & 1;
+            if (stage == nstages)
+            {
+                stage = 0;
+                phase ^= 1;
+            }
             cl_uint row0 = t * tile_rows;
             cl_uint rows = min(tile_rows, nrows - row0);
             cl_uint stage_off = PGS_SMEM_HEAD_BYTES + stage * PGS_STAGE_BYTES(tile_rows);
@@ -1643,15 +1812,12 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                 }
                 if (fast)
                 {
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                    {
-                        tacc.calc(prow4[j], valid4[j]);
-#if GPUPREAGG_HAS_QUAL
-                        ctx.nfiltered += (valid4[j] ? 0U : 1U);
-#endif
-                    }
+                    tacc.calc4(prow4, valid4, one);
                     tacc.note_nonnull(prow4, valid4);
+#if GPUPREAGG_HAS_QUAL
+                    ctx.nfiltered += PGS_K01(!valid4[0]) + PGS_K01(!valid4[1]) +
+                                     PGS_K01(!valid4[2]) + PGS_K01(!valid4[3]);
+#endif
                 }
                 else
                 {
@@ -1667,82 +1833,98 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                 }
             }
 #elif !GPUPREAGG_HAS_QUAL
-            /* GROUP BY, every row takes part: no divergence to repair */
-            for (cl_uint r = ctid * 4; r < rows; r += GPUPREAGG_CONSUMER_THREADS * 4)
+            /* GROUP BY, every row takes part.  The trip count is the same
+             * for every lane of the warp (pgs_group_add_row is collective). */
+            for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
+                 rb += GPUPREAGG_CONSUMER_THREADS * 4)
             {
+                const cl_uint r = rb + lane_id * 4;
                 kern_row_regs rr[4];
-                bool        nnflag[1];
 
                 rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
                 GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    if (r + j < rows)
-                        PGS_CONSUME_ROW(j)
-                (void)nnflag;
+                    PGS_CONSUME_ROW_GROUPED(j)
             }
 #else
             /* GROUP BY under a WHERE clause.  Only a fraction of the rows
              * reaches the hash table; taking that path per row would run it
-             * with a few lanes of each warp.  So a warp first evaluates the
-             * qual of 128 rows (4 per lane, from registers), compacts the
-             * survivors' tile row numbers into its queue with ballots, and
-             * feeds the table from the queue 32 rows at a time: every lane
-             * re-reads one queued row from the stage (kern_tile_smem view)
-             * and runs projection + find-or-insert + the cell updates.  The
-             * queue is drained before the stage is handed back. */
+             * with a few lanes of each warp.  So a warp evaluates the qual
+             * of 128 rows (4 per lane, from registers) and compacts the
+             * survivors - their staged column values, with ballots - into
+             * its queue; whenever 32 rows are queued, every lane takes one
+             * through projection + find-or-insert + the cell updates.
+             * The queue carries values, not tile positions, so the warp hands
+             * the stage back as soon as its rows are queued and runs that
+             * chain of dependent shared-memory operations afterwards: it
+             * overlaps the other warps and the TMA refill instead of holding
+             * up the whole CTA once per tile.  What is left at the end of the
+             * scan is drained below the tile loop. */
+            for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
+                 rb += GPUPREAGG_CONSUMER_THREADS * 4)
             {
-                cl_ushort  *rowq = head->rowq + (warp_id - 1) * PGS_ROWQ_ENTRIES;
-                cl_uint     qn = 0;         /* warp-uniform */
-
                 /* the trip count is the same for every lane of the warp
                  * (ballots inside): bounds are checked per row */
-                for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
-                     rb += GPUPREAGG_CONSUMER_THREADS * 4)
-                {
-                    const cl_uint r = rb + lane_id * 4;
-                    kern_row_regs rr[4];
+                const cl_uint r = rb + lane_id * 4;
+                kern_row_regs rr[4];
 
-                    rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
-                    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+                rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                    {
-                        cl_int      e = StromError_Success;
-                        bool        valid = false;
-                        cl_uint     votes;
+                for (int j = 0; j < 4; j++)
+                {
+                    cl_int      e = StromError_Success;
+                    bool        valid = false;
+                    cl_uint     votes;
 
-                        if (r + j < rows)
-                        {
-                            valid = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
-                                                        row0 + r + j);
-                            if (e != StromError_Success)
-                            {
-                                pgs_note_error(e, row0 + r + j, recheck_map, ctx);
-                                valid = false;
-                            }
-                            else if (!valid)
-                                ctx.nfiltered++;
-                        }
-                        votes = __ballot_sync(0xffffffffU, valid);
-                        if (valid)
-                            rowq[qn + __popc(votes & ((1U << lane_id) - 1U))] =
-                                (cl_ushort)(r + j);
-                        qn += __popc(votes);
-                    }
-                    __syncwarp();
-                    while (qn >= 32)
+                    if (r + j < rows)
                     {
+                        valid = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
+                                                    row0 + r + j);
+                        if (e != StromError_Success)
+                        {
+                            pgs_note_error(e, row0 + r + j, recheck_map, ctx);
+                            valid = false;
+                        }
+                        else if (!valid)
+                            ctx.nfiltered++;
+                    }
+                    votes = __ballot_sync(0xffffffffU, valid);
+                    if (qn > 32)
+                    {
+                        /* no room for 32 more (selective quals rarely get
+                         * here): make room inside the tile */
+                        __syncwarp();
                         qn -= 32;
-                        pgs_group_add_queued(kparams, tile, kds_in, row0 + rowq[qn + lane_id],
+                        pgs_group_add_queued(kparams, rowq, kds_in, qn + lane_id, true,
                                              gs, sh, &head->sh_nused, recheck_map, ctx);
                     }
-                    __syncwarp();
+                    if (valid)
+                    {
+                        const kern_row_regs &__row = rr[j];
+                        cl_uint     __pos = qn + __popc(votes & ((1U << lane_id) - 1U));
+                        cl_uint     __mask = 0;
+
+                        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_QPUSH)
+                        *((cl_uint *)(__pgs_smem + rowq.base + PGS_ROWQ_MASK_OFF) + __pos) = __mask;
+                        *((cl_uint *)(__pgs_smem + rowq.base + PGS_ROWQ_ROW_OFF) + __pos) =
+                            row0 + r + j;
+                    }
+                    qn += __popc(votes);
                 }
-                if (lane_id < qn)
-                    pgs_group_add_queued(kparams, tile, kds_in, row0 + rowq[lane_id],
-                                         gs, sh, &head->sh_nused, recheck_map, ctx);
             }
+            /* done with the stage */
+            __syncwarp();
+            if (lane_id == 0)
+                pgs_mbar_arrive(&head->empty_bar[stage]);
+            while (qn >= 32)
+            {
+                qn -= 32;
+                pgs_group_add_queued(kparams, rowq, kds_in, qn + lane_id, true,
+                                     gs, sh, &head->sh_nused, recheck_map, ctx);
+            }
+            continue;
 #endif
             __syncwarp();
             if (lane_id == 0)
@@ -1750,6 +1932,11 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
         }
 #if GPUPREAGG_NUM_KEYS == 0
         acc_nn |= tacc.fold(acc);
+#elif GPUPREAGG_HAS_QUAL
+        __syncwarp();
+        if (qn > 0)
+            pgs_group_add_queued(kparams, rowq, kds_in, lane_id, lane_id < qn,
+                                 gs, sh, &head->sh_nused, recheck_map, ctx);
 #endif
     }
     pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
@@ -1799,25 +1986,32 @@ gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
     PGS_SH_TABLE_INIT()
     __syncthreads();
 
-    for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x;
-         i < nvalids;
-         i += (cl_ulong)gridDim.x * blockDim.x)
+    /* warp-uniform trip count: the group path is warp-collective */
+    for (cl_ulong base = (cl_ulong)blockIdx.x * blockDim.x + (threadIdx.x & ~31U);
+         base < nvalids;
+         base += (cl_ulong)gridDim.x * blockDim.x)
     {
-        cl_uint     row = (krowmap->nvalids < 0
-                           ? (cl_uint)i : (cl_uint)krowmap->rindex[i]);
+        cl_ulong    i = base + (threadIdx.x & 31U);
         pagg_row    prow;
+        bool        valid = false;
 
-        if (row >= nrows)
+        if (i < nvalids)
         {
-            if (ctx.errcode == StromError_Success)
-                ctx.errcode = StromError_DataStoreOutOfRange;
-            continue;
+            cl_uint row = (krowmap->nvalids < 0
+                           ? (cl_uint)i : (cl_uint)krowmap->rindex[i]);
+            if (row >= nrows)
+            {
+                if (ctx.errcode == StromError_Success)
+                    ctx.errcode = StromError_DataStoreOutOfRange;
+            }
+            else
+                valid = pgs_eval_row(kparams, gtile, kds_in, row, recheck_map, ctx, prow);
         }
-        bool valid = pgs_eval_row(kparams, gtile, kds_in, row, recheck_map, ctx, prow);
-        if (GPUPREAGG_NUM_KEYS == 0)
-            acc_nn |= gpupreagg_aggcalc_plain(acc, prow, valid);
-        else if (valid)
-            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx);
+#if GPUPREAGG_NUM_KEYS == 0
+        acc_nn |= gpupreagg_aggcalc_plain(acc, prow, valid);
+#else
+        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid);
+#endif
     }
     pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
                       &head->is_last_cta, acc, acc_nn, ctx);
