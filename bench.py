@@ -218,6 +218,7 @@ def bench_ours(args):
     import torch
     from pg_strom_b200 import _capi
     from pg_strom_b200 import gpupreagg as gp
+    from pg_strom_b200 import multigpu
     from pg_strom_b200 import workloads as W
     from oracle import bench_oracle
 
@@ -268,13 +269,7 @@ def bench_ours(args):
     total_dev_bytes = sum(length for _, length, _ in dev_chunks)
     comm = C.c_void_p()
     if world > 1:
-        uid = C.create_string_buffer(128)
-        if rank == 0:
-            _capi.check(lib.pgs_nccl_get_unique_id(uid))
-        t = torch.frombuffer(bytearray(uid.raw), dtype=torch.uint8).to(dev)
-        dist.broadcast(t, 0)
-        uid = C.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
-        _capi.check(lib.pgs_nccl_comm_init_rank(0, world, uid, rank, C.byref(comm)))
+        comm = multigpu.nccl_communicator(lib, dist, 0, rank, world, device=dev)
 
     stream = torch.cuda.ExternalStream(sess.stream(), device=dev)
 
@@ -382,7 +377,11 @@ def bench_ours(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(workload)
+                t = json.load(f).get(workload)
+            if t and t.get("rows_per_launch") and k_rows:
+                # ncu dram__bytes_read+write of one profiled launch, scaled to
+                # the rows one timed launch processed
+                traffic = t["dram_bytes_per_launch"] * (k_rows / t["rows_per_launch"])
         line = {
             "metric": METRIC,
             "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,

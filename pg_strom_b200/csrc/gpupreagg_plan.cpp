@@ -1437,20 +1437,9 @@ explain_node(const JsonPtr &plan, int depth, bool verbose, std::vector<std::stri
                 t = deparse_expression(e, scan_colnames(plan), false);
             else
             {
-                JsonPtr child = child_of(plan);
-                bool passthrough = (node == "Sort");
-                if (passthrough && child)
-                {
-                    /* a Sort's target list are references to its child */
-                    JsonPtr ce = e;
-                    std::string inner = deparse_in_plan(ce, child);
-                    /* the Sort above an Agg: tlist entries are the Agg's exprs */
-                    t = (ce->s("node") == "Var" && is_scan_node(child)) ? inner : inner;
-                    if (ce->s("node") != "Var" && ce->s("node") != "Const")
-                        t = "(" + inner + ")";
-                }
-                else
-                    t = deparse_in_plan(e, plan);
+                /* upper nodes refer to their child's outputs by OUTER Vars
+                 * (set_plan_references): print the child's expression */
+                t = deparse_in_plan(e, plan);
             }
             s += (i ? ", " : "") + t;
         }

@@ -216,8 +216,12 @@ def make_agg_plan(table, targets, group_by=(), where=(), order_by_keys=False,
         return agg
     sort = {"node": "Sort",
             "sortkeys": ["%s.%s" % (table.name, g) for g in group_by],
+            # after set_plan_references() an upper node refers to its child's
+            # output columns by OUTER_VAR Vars
             "targetlist": [{"node": "TargetEntry",
-                            "expr": t["expr"], "resno": t["resno"],
+                            "expr": {"node": "Var", "varno": "OUTER",
+                                     "varattno": t["resno"], "vartype": etype(t["expr"])},
+                            "resno": t["resno"],
                             "resname": t["resname"], "resjunk": False}
                            for t in agg["targetlist"]],
             "lefttree": agg}

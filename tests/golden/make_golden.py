@@ -29,6 +29,7 @@ REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 ROWCOUNT = re.compile(r"^\((\d+) rows?\)$")
+GUCSET = re.compile(r"^set\s+(pg_strom\.\w+)\s*(?:=|\s+to\s+)\s*([^;]+);", re.I)
 
 
 def parse_out(path):
@@ -87,15 +88,20 @@ def parse_explain(path):
     stmts = []
     i = 0
     n = len(lines)
+    gucs = {}
     while i < n:
         ln = lines[i]
+        m = GUCSET.match(ln.strip())
+        if m:
+            # the session's pg_strom.* settings at this point of the script
+            gucs[m.group(1).lower()] = m.group(2).strip().strip("'").lower()
         if not ln.strip().lower().startswith("explain"):
             i += 1
             continue
         sql = " ".join(ln.split())
         i += 1
         if i < n and lines[i].startswith("ERROR:"):
-            stmts.append({"sql": sql, "plan": None,
+            stmts.append({"sql": sql, "plan": None, "gucs": dict(gucs),
                           "error": lines[i][6:].strip()})
             i += 1
             continue
@@ -107,7 +113,7 @@ def parse_explain(path):
                         else lines[i].rstrip())
             i += 1
         i += 1
-        stmts.append({"sql": sql, "plan": plan, "error": None})
+        stmts.append({"sql": sql, "plan": plan, "gucs": dict(gucs), "error": None})
     return stmts
 
 
