@@ -287,11 +287,6 @@ def bench_ours(args):
             _capi.check(lib.pgs_preagg_merge_nccl(sess.handle, comm, rank, world, 0))
         return sess.finish_raw()[1].nitems
 
-    def step_check():
-        for dptr, length, n in dev_chunks:
-            sess.submit_device(dptr, length, n)
-        return sess.finish()
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -301,15 +296,30 @@ def bench_ours(args):
     nresult = None
     for i in range(max(args.warmup, 3)):
         nresult = step_resident()
-    if not args.no_check and world == 1:
-        result = step_check()
+    if not args.no_check:
+        # one checked pass: every rank restates its shard with the numpy
+        # oracle, the root merges the expectations and compares them with the
+        # rows the device path (NCCL merge included) returns - bit-exact
         merged = []
         for c in range(len(coltypes)):
             v = np.concatenate([ch[c][0] for ch in colchunks])
             m = None if colchunks[0][c][1] is None else np.concatenate([ch[c][1] for ch in colchunks])
             merged.append((v, m))
-        bench_oracle.assert_partial_equal_node(desc, node, result, merged)
+        part = bench_oracle.expected_partial_node(node, merged)
         del merged
+        for dptr, length, n in dev_chunks:
+            sess.submit_device(dptr, length, n)
+        if world > 1:
+            _capi.check(lib.pgs_preagg_merge_nccl(sess.handle, comm, rank, world, 0))
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object(part, parts, dst=0)
+        else:
+            parts = [part]
+        result = sess.finish()
+        if rank == 0:
+            keys, exp = bench_oracle.merge_expected(desc, parts)
+            bench_oracle.assert_rows_equal_expected(desc, result, keys, exp)
+        del part, parts
 
     # ---- timed region: device resident ----
     pm0 = sess.perfmon()
@@ -339,6 +349,26 @@ def bench_ours(args):
     k_rows = (pm1["rows_kern_main"] - pm0["rows_kern_main"]) / max(n_k, 1)
     peak, peak_src = measured_peaks()
     achieved = k_rows * alg_bytes_per_row / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
+
+    # ---- where a resident step spends its time (host clock, synchronised
+    # between the phases; diagnostic only, not part of `value`) ----
+    phase_ms = {"scan": 0.0, "merge": 0.0, "finish": 0.0}
+    for i in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for dptr, length, n in dev_chunks:
+            sess.submit_device(dptr, length, n)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if world > 1:
+            _capi.check(lib.pgs_preagg_merge_nccl(sess.handle, comm, rank, world, 0))
+            torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        sess.finish_raw()
+        t3 = time.perf_counter()
+        phase_ms["scan"] += (t1 - t0) * 1000.0 / 3
+        phase_ms["merge"] += (t2 - t1) * 1000.0 / 3
+        phase_ms["finish"] += (t3 - t2) * 1000.0 / 3
 
     # ---- timed region: end to end (host chunks in pinned memory) ----
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 5))
@@ -396,7 +426,7 @@ def bench_ours(args):
                        "algorithmic_bytes_per_row": alg_bytes_per_row,
                        "l2_policy": "inputs (%.2f GB per step) are larger than L2 (126 MB)"
                                     % (total_bytes / 1e9),
-                       "merge": "ncclSend/Recv of exported states to rank 0" if world > 1 else "none",
+                       "merge": "ncclAllGather of exported state blocks, import on rank 0" if world > 1 else "none",
                        "partial_rows": nresult},
             "gb_per_s": value * alg_bytes_per_row / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
@@ -411,6 +441,7 @@ def bench_ours(args):
                     "h2d_gb_per_s": h2d / (e2e_ms / 1000.0) / 1e9,
                     "pcie_gen5_x16_frac": h2d / (e2e_ms / 1000.0) / 1e9 / 64.0},
             "gpu_launches": int(launches),
+            "phase_ms": phase_ms,
             "clocks": clocks,
         }
         print(json.dumps(line))

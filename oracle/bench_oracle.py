@@ -210,8 +210,35 @@ def combine_device_rows(desc, rows):
     return groups
 
 
-def assert_partial_equal_node(desc, gpreagg_node, device_rows, cols, rel_tol=0.0):
-    keys, exp = expected_partial_node(gpreagg_node, cols)
+def merge_expected(desc, parts):
+    """parts: [(keys, columns)] as expected_partial_node returns them, one per
+    rank / shard -> one (keys, columns) for the union (PSUM adds, PMIN / PMAX
+    take the extreme, NULL = no non-NULL input in that shard)."""
+    dcols = desc["columns"]
+    merged = {}
+    for keys, out in parts:
+        for g, k in enumerate(keys):
+            vals = [out[i][g] for i in range(len(dcols))]
+            acc = merged.get(k)
+            if acc is None:
+                merged[k] = vals
+                continue
+            for i, c in enumerate(dcols):
+                if c["role"] != 2 or vals[i] is None:
+                    continue
+                if acc[i] is None:
+                    acc[i] = vals[i]
+                elif c["op"] == "PSUM":
+                    acc[i] = acc[i] + vals[i]
+                elif c["op"] == "PMIN":
+                    acc[i] = min(acc[i], vals[i])
+                else:
+                    acc[i] = max(acc[i], vals[i])
+    keys = sorted(merged)
+    return keys, [[merged[k][i] for k in keys] for i in range(len(dcols))]
+
+
+def assert_rows_equal_expected(desc, device_rows, keys, exp, rel_tol=0.0):
     got = combine_device_rows(desc, device_rows)
     assert len(got) == len(keys), "device produced %d groups, oracle %d" % (len(got), len(keys))
     dcols = desc["columns"]
@@ -231,6 +258,11 @@ def assert_partial_equal_node(desc, gpreagg_node, device_rows, cols, rel_tol=0.0
             else:
                 assert d == e, "group %r column %s: device %r != oracle %r" % (k, c["text"], d, e)
     return len(keys)
+
+
+def assert_partial_equal_node(desc, gpreagg_node, device_rows, cols, rel_tol=0.0):
+    keys, exp = expected_partial_node(gpreagg_node, cols)
+    return assert_rows_equal_expected(desc, device_rows, keys, exp, rel_tol)
 
 
 # -- helpers used by workloads.smoke(): resolve the node from the plan ------

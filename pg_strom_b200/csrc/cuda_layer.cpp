@@ -579,7 +579,8 @@ struct pgs_session
     pgs_program    *program = NULL;
     cudaLibrary_t   library = NULL;
     cudaKernel_t    k_main = NULL, k_rowmap = NULL, k_init = NULL, k_flush = NULL,
-                    k_export = NULL, k_import = NULL, k_describe = NULL;
+                    k_export = NULL, k_import = NULL, k_import_blocks = NULL,
+                    k_describe = NULL;
     pgs_kern_desc   desc;
     pgs_gstate      gs;
     std::vector<char> kparams;
@@ -610,6 +611,8 @@ struct pgs_session
     size_t          d_result_cap = 0;
     kern_gpupreagg *d_kg_misc = NULL;   /* status word of flush / import kernels */
     char           *h_result_head = NULL;   /* pinned: header + status read-back */
+    char           *d_xchg = NULL;          /* NCCL merge: send block + receive blocks */
+    size_t          d_xchg_cap = 0;
     std::string     perfmon_buf;
     bool            aborted = false;
 };
@@ -720,9 +723,27 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_flush, s->library, "gpupreagg_flush"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_export, s->library, "gpupreagg_export"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_import, s->library, "gpupreagg_import"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_import_blocks, s->library, "gpupreagg_import_blocks"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_describe, s->library, "gpupreagg_describe"));
     OPEN_CHECK(cudaStreamCreateWithFlags(&s->s_copy, cudaStreamNonBlocking));
     OPEN_CHECK(cudaStreamCreateWithFlags(&s->s_exec, cudaStreamNonBlocking));
+    /* the parameter buffer also goes to the program's constant memory (the
+     * kernels read KPARAM_n from there, see kern_gpupreagg.cuh) */
+    {
+        void   *d_const = NULL;
+        size_t  const_bytes = 0;
+        OPEN_CHECK(cudaLibraryGetGlobal(&d_const, &const_bytes, s->library, "pgs_const_kparams"));
+        if (s->kparams.size() > const_bytes)
+        {
+            set_error("pgs_preagg_open: parameter buffer of %zu bytes does not fit the "
+                      "%zu bytes of constant memory reserved for it",
+                      s->kparams.size(), const_bytes);
+            pgs_preagg_close(s);
+            return StromError_BadRequestMessage;
+        }
+        OPEN_CHECK(cudaMemcpy(d_const, s->kparams.data(), s->kparams.size(),
+                              cudaMemcpyHostToDevice));
+    }
 
     /* ask the program about its layouts */
     {
@@ -1459,11 +1480,66 @@ pgs_preagg_merge_nccl(pgs_session *s, void *nccl_comm, int rank, int nranks, int
     if (rc != StromError_Success)
         return rc;
     CUDA_CHECK(cudaSetDevice(s->ordinal));
+    size_t recb = s->desc.slot_bytes;
+    /*
+     * Small states (no GROUP BY: one record; GROUP BY with a table of at most
+     * 64K slots): every rank exports into a fixed-size block [header | cap
+     * records], ONE ncclAllGather moves the blocks and the root imports them.
+     * Everything is stream ordered - no allocation, no host synchronisation;
+     * the caller's pgs_preagg_finish() waits once for all of it.
+     */
+    size_t cap = (s->desc.num_keys == 0 ? 1 : (size_t)s->gs.gh_nslots);
+    if (cap <= 65536 && (cap + 1) * recb * (size_t)(nranks + 1) <= ((size_t)256 << 20))
+    {
+        size_t block = (cap + 1) * recb;
+        size_t need = block * (size_t)(nranks + 1);
+        if (s->d_xchg_cap < need)
+        {
+            if (s->d_xchg)
+                CUDA_CHECK(cudaFree(s->d_xchg));
+            s->d_xchg = NULL;
+            s->d_xchg_cap = 0;
+            CUDA_CHECK(cudaMalloc((void **)&s->d_xchg, need));
+            s->d_xchg_cap = need;
+        }
+        char *d_send = s->d_xchg;
+        char *d_recv = s->d_xchg + block;
+        cl_ulong *recs = (cl_ulong *)(d_send + recb);
+        cl_uint *d_n = (cl_uint *)d_send;           /* header word = record count */
+        cl_uint max_records = (cl_uint)cap;
+        CUDA_CHECK(cudaMemsetAsync(d_send, 0, recb, s->s_exec));
+        {
+            void *args[] = { &s->gs, &recs, &d_n, &max_records };
+            int grid = (s->desc.num_keys == 0) ? 1 :
+                std::max(1, std::min<int>(s->num_sms * 8, (int)((s->gs.gh_nslots + 255) / 256)));
+            rc = launch_kernel(s, s->k_export, grid, 256, 0, args);
+            if (rc != StromError_Success)
+                return rc;
+        }
+        NCCL_CHECK(nccl.allgather(d_send, d_recv, block, NCCL_UINT8, nccl_comm, s->s_exec));
+        if (rank != root)
+            return session_init_state(s);   /* this rank's state now lives on the root */
+        if (!s->d_kg_misc)
+            CUDA_CHECK(cudaMalloc((void **)&s->d_kg_misc, sizeof(kern_gpupreagg)));
+        CUDA_CHECK(cudaMemsetAsync(s->d_kg_misc, 0, sizeof(kern_gpupreagg), s->s_exec));
+        {
+            const cl_ulong *blocks = (const cl_ulong *)d_recv;
+            cl_uint nr = (cl_uint)nranks, rt = (cl_uint)root, cp = (cl_uint)cap;
+            void *args[] = { &s->gs, &blocks, &nr, &rt, &cp, &s->d_kg_misc };
+            int grid = (s->desc.num_keys == 0) ? 1 :
+                std::max(1, std::min<int>(s->num_sms * 4, (int)((cap + 255) / 256)));
+            rc = launch_kernel(s, s->k_import_blocks, grid, 256, 0, args);
+            if (rc != StromError_Success)
+                return rc;
+        }
+        /* a full root table shows up as the status of the flush that follows:
+         * check it here only when the caller asked for strict merges */
+        return StromError_Success;
+    }
+    /* large states: 1. how many records does each rank hold? */
     rc = drain(s);
     if (rc != StromError_Success)
         return rc;
-    size_t recb = s->desc.slot_bytes;
-    /* 1. how many records does each rank hold? */
     cl_uint my_n = 1;
     if (s->desc.num_keys > 0)
         CUDA_CHECK(cudaMemcpy(&my_n, s->gs.gh_ngroups, sizeof(cl_uint), cudaMemcpyDeviceToHost));
@@ -1541,6 +1617,17 @@ pgs_preagg_perfmon_json(pgs_session *s)
     o->set("num_kern_main", (long long)s->num_kern_main);
     o->set("rows_kern_main", (long long)s->rows_kern_main);
     o->set("nrows_filtered", (long long)counters[1]);
+    if (getenv("PGSTROM_DEBUG_LEVEL"))
+    {
+        /* cycle counters of GPUPREAGG_DEBUG_LEVEL 4 (kern_gpupreagg.cuh) */
+        cl_ulong dbg[4] = {0, 0, 0, 0};
+        if (s->d_scratch)
+            cudaMemcpy(dbg, (char *)s->d_scratch + 16 + 14 * 8, sizeof(dbg), cudaMemcpyDeviceToHost);
+        pgs::JsonPtr a = pgs::Json::array();
+        for (int i = 0; i < 4; i++)
+            a->push(pgs::Json::number((double)dbg[i]));
+        o->set("debug_counters", a);
+    }
     o->set("grid_main", s->grid_main);
     o->set("smem_main", (long long)s->smem_main);
     o->set("sh_nslots", (long long)s->sh_nslots);
@@ -1597,6 +1684,7 @@ pgs_preagg_close(pgs_session *s)
         if (s->d_result) cudaFree(s->d_result);
         if (s->d_kg_misc) cudaFree(s->d_kg_misc);
         if (s->h_result_head) cudaFreeHost(s->h_result_head);
+        if (s->d_xchg) cudaFree(s->d_xchg);
         if (s->d_scratch) cudaFree(s->d_scratch);
         if (s->s_copy) cudaStreamDestroy(s->s_copy);
         if (s->s_exec) cudaStreamDestroy(s->s_exec);

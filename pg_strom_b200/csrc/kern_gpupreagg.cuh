@@ -66,11 +66,46 @@
 #ifndef GPUPREAGG_DEBUG_LEVEL
 #define GPUPREAGG_DEBUG_LEVEL       0
 #endif
+/* GPUPREAGG_DEBUG_LEVEL 4: cycle counters of the consumer warps (lane 0),
+ * summed into 8-byte words behind gs.nrows_scanned: [16] wait for the tile,
+ * [17] qual + queueing, [18] hash chain, [19] number of chains */
+#if GPUPREAGG_DEBUG_LEVEL == 4
+#define PGS_DBG_DECL        long long __dbg_t0 = 0, __dbg_acc[4] = {0, 0, 0, 0};
+#define PGS_DBG_START()     __dbg_t0 = clock64();
+#define PGS_DBG_STOP(i)     __dbg_acc[i] += clock64() - __dbg_t0;
+#define PGS_DBG_COUNT(i)    __dbg_acc[i] += 1;
+#define PGS_DBG_FLUSH()                                                 \
+    if ((threadIdx.x & 31) == 0)                                        \
+        for (int __i = 0; __i < 4; __i++)                               \
+            atomicAdd((unsigned long long *)gs.nrows_scanned + 14 + __i, \
+                      (unsigned long long)__dbg_acc[__i]);
+#else
+#define PGS_DBG_DECL
+#define PGS_DBG_START()
+#define PGS_DBG_STOP(i)
+#define PGS_DBG_COUNT(i)
+#define PGS_DBG_FLUSH()
+#endif
+
 #ifndef PGS_ROWS_PER_THREAD
 #define PGS_ROWS_PER_THREAD         4
 #endif
 
 #define PGS_MAX(a,b)    ((a) > (b) ? (a) : (b))
+
+/* ------------------------------------------------------------------
+ * The session's kern_parambuf (Const / Param values of the query, the same
+ * image that travels in kern_gpupreagg.kparams) also lives in constant
+ * memory: the generated code fetches its KPARAM_n per row
+ * (pg_<type>_param), and from the kern_gpupreagg in HBM that is a chain of
+ * three dependent global loads the compiler may not hoist over the atomics
+ * of the loop.  From the constant bank it is three LDC.  The CUDA layer
+ * fills the symbol when it opens the session and refuses parameter buffers
+ * that do not fit.
+ * ------------------------------------------------------------------ */
+#define PGS_CONST_KPARAMS_MAX       16384
+extern "C" { __constant__ __align__(16) unsigned char pgs_const_kparams[PGS_CONST_KPARAMS_MAX]; }
+#define KERN_GPUPREAGG_PARAMBUF_CONST   ((const kern_parambuf *)pgs_const_kparams)
 
 /* ------------------------------------------------------------------
  * pagg_datum / pagg_row: what gpupreagg_projection() produces for one input
@@ -927,10 +962,23 @@ template <> struct pgs_rowq_store<2>
 template <> struct pgs_rowq_store<1>
 { static __device__ __forceinline__ void put(unsigned char *p, cl_uint i, cl_ulong v)
   { ((unsigned char *)p)[i] = (unsigned char)v; } };
+/* queue one row straight from the stage (only the columns the qual reads
+ * were pulled into registers; the others are touched for survivors only) */
+template <int ATTLEN> struct pgs_rowq_type;
+template <> struct pgs_rowq_type<8> { typedef cl_ulong T; };
+template <> struct pgs_rowq_type<4> { typedef cl_uint T; };
+template <> struct pgs_rowq_type<2> { typedef cl_ushort T; };
+template <> struct pgs_rowq_type<1> { typedef unsigned char T; };
 #define PGS_X_INCOL_QPUSH(slot,colidx,attlen)                           \
-    pgs_rowq_store<attlen>::put(__pgs_smem + rowq.base + pgs_rowq_val_off(slot), \
-                                __pos, __row.v[slot]);                  \
-    __mask |= (((__row.vbits[slot] >> __row.shift) & 1U) << (slot));
+    ((pgs_rowq_type<attlen>::T *)(__pgs_smem + __qbase + pgs_rowq_val_off(slot)))[__pos] = \
+        ((const pgs_rowq_type<attlen>::T *)(__pgs_smem + tile.val_off[slot]))[__ri]; \
+    {                                                                   \
+        cl_uint __vb = 1U;                                              \
+        if (tile.nul_off[slot] != KERN_TILE_NO_NULLMAP)                 \
+            __vb = (*((const cl_uint *)(__pgs_smem + tile.nul_off[slot]) + (__ri >> 5)) \
+                    >> (__ri & 31)) & 1U;                               \
+        __mask |= (__vb << (slot));                                     \
+    }
 
 /* ------------------------------------------------------------------
  * mbarrier + bulk async copy (TMA engine, 1-D) wrappers
@@ -1489,7 +1537,7 @@ pgs_note_error(cl_int errcode, cl_uint row, cl_uint *recheck_map, pgs_row_ctx &c
  * pgs_group_add_row; lanes without a row pass active = false.  Not inlined:
  * six copies of this chain would not fit the instruction cache well. */
 static __device__ __noinline__ void
-pgs_group_add_queued(const kern_parambuf *kparams, const kern_rowq_smem &rowq,
+pgs_group_add_queued_call(const kern_parambuf *kparams, const kern_rowq_smem &rowq,
                      const void *ktoast, cl_uint idx, bool active,
                      const pgs_gstate &gs, const pgs_sh_table &sh,
                      cl_uint *sh_nused, cl_uint *recheck_map, pgs_row_ctx &ctx)
@@ -1509,6 +1557,31 @@ pgs_group_add_queued(const kern_parambuf *kparams, const kern_rowq_smem &rowq,
         }
     }
     pgs_group_add_row(gs, sh, sh_nused, prow, ctx, active);
+}
+
+/* The callee is not inlined and takes its state by reference: hand it copies,
+ * so that the caller's hot-loop variables (row counters, table geometry) stay
+ * in registers instead of being reloaded from the stack after every call. */
+DEVFN void
+pgs_group_add_queued(const kern_parambuf *kparams, const kern_rowq_smem &rowq,
+                     const void *ktoast, cl_uint idx, bool active,
+                     const pgs_gstate &gs, const pgs_sh_table &sh,
+                     cl_uint *sh_nused, cl_uint *recheck_map, pgs_row_ctx &ctx)
+{
+    kern_rowq_smem  rowq2 = rowq;
+    pgs_gstate      gs2 = gs;
+    pgs_sh_table    sh2 = sh;
+    pgs_row_ctx     ctx2;
+
+    ctx2.nfiltered = 0;
+    ctx2.nrecheck = 0;
+    ctx2.errcode = StromError_Success;
+    pgs_group_add_queued_call(kparams, rowq2, ktoast, idx, active, gs2, sh2,
+                              sh_nused, recheck_map, ctx2);
+    ctx.nfiltered += ctx2.nfiltered;
+    ctx.nrecheck += ctx2.nrecheck;
+    if (ctx.errcode == StromError_Success)
+        ctx.errcode = ctx2.errcode;
 }
 
 /* threads of the CTA -> thread 0, always combined in the same order: lanes by
@@ -1681,7 +1754,7 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
 {
     pgs_smem_head  *head = (pgs_smem_head *)__pgs_smem;
     unsigned char  *stages = __pgs_smem + PGS_SMEM_HEAD_BYTES;
-    const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF(kgpreagg);
+    const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF_CONST;
     const cl_uint   nrows = kds_in->nitems;
     const cl_uint   ntiles = (nrows + tile_rows - 1) / tile_rows;
     const cl_uint   warp_id = threadIdx.x >> 5;
@@ -1755,6 +1828,7 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
         rowq.base = PGS_SMEM_HEAD_FIXED + (warp_id - 1) * PGS_ROWQ_WARP_BYTES;
 #endif
         cl_uint         stage = 0, phase = 0;
+        PGS_DBG_DECL
 
         for (cl_uint t = blockIdx.x; t < ntiles;
              t += gridDim.x, it++, stage++)
@@ -1772,7 +1846,10 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
             tile.row0 = row0;
             GPUPREAGG_INCOL_LIST(PGS_X_INCOL_VIEW)
             (void)stage_off;
+            PGS_DBG_START()
             pgs_mbar_wait(&head->full_bar[stage], phase);
+            PGS_DBG_STOP(0)
+            PGS_DBG_START()
 
             /* each thread takes 4 consecutive rows: phase 1 pulls them out of
              * the stage with 128-bit shared memory loads, phase 2 evaluates
@@ -1871,38 +1948,57 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
 
                 rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
                 GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+                /* the 4 rows are independent up to here: evaluate all four
+                 * quals and take the four ballots before anything is queued,
+                 * so that their latencies overlap */
+                bool        valid4[4];
+                cl_uint     votes4[4];
+                cl_uint     total = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                 {
                     cl_int      e = StromError_Success;
-                    bool        valid = false;
-                    cl_uint     votes;
 
+                    valid4[j] = false;
                     if (r + j < rows)
                     {
-                        valid = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
-                                                    row0 + r + j);
+                        valid4[j] = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
+                                                        row0 + r + j);
                         if (e != StromError_Success)
                         {
                             pgs_note_error(e, row0 + r + j, recheck_map, ctx);
-                            valid = false;
+                            valid4[j] = false;
                         }
-                        else if (!valid)
+                        else if (!valid4[j])
                             ctx.nfiltered++;
                     }
-                    votes = __ballot_sync(0xffffffffU, valid);
-                    if (qn > 32)
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    votes4[j] = __ballot_sync(0xffffffffU, valid4[j]);
+                    total += __popc(votes4[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                {
+                    const bool      valid = valid4[j];
+                    const cl_uint   votes = votes4[j];
+
+                    if (qn + __popc(votes) > PGS_ROWQ_ENTRIES)
                     {
-                        /* no room for 32 more (selective quals rarely get
-                         * here): make room inside the tile */
+                        /* no room for this step's rows (selective quals
+                         * rarely get here): make room inside the tile */
                         __syncwarp();
+                        PGS_DBG_COUNT(3)
                         qn -= 32;
                         pgs_group_add_queued(kparams, rowq, kds_in, qn + lane_id, true,
                                              gs, sh, &head->sh_nused, recheck_map, ctx);
                     }
                     if (valid)
                     {
-                        const kern_row_regs &__row = rr[j];
+                        const cl_uint __qbase = rowq.base;
+                        const cl_uint __ri = r + j;         /* row in the tile */
                         cl_uint     __pos = qn + __popc(votes & ((1U << lane_id) - 1U));
                         cl_uint     __mask = 0;
 
@@ -1913,17 +2009,22 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                     }
                     qn += __popc(votes);
                 }
+                (void)total;
             }
             /* done with the stage */
             __syncwarp();
             if (lane_id == 0)
                 pgs_mbar_arrive(&head->empty_bar[stage]);
+            PGS_DBG_STOP(1)
+            PGS_DBG_START()
             while (qn >= 32)
             {
                 qn -= 32;
+                PGS_DBG_COUNT(3)
                 pgs_group_add_queued(kparams, rowq, kds_in, qn + lane_id, true,
                                      gs, sh, &head->sh_nused, recheck_map, ctx);
             }
+            PGS_DBG_STOP(2)
             continue;
 #endif
             __syncwarp();
@@ -1937,6 +2038,7 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
         if (qn > 0)
             pgs_group_add_queued(kparams, rowq, kds_in, lane_id, lane_id < qn,
                                  gs, sh, &head->sh_nused, recheck_map, ctx);
+        PGS_DBG_FLUSH()
 #endif
     }
     pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
@@ -1960,7 +2062,7 @@ gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
 {
     pgs_smem_head  *head = (pgs_smem_head *)__pgs_smem;
     unsigned char  *stages = __pgs_smem + PGS_SMEM_HEAD_BYTES;
-    const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF(kgpreagg);
+    const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF_CONST;
     const kern_row_map  *krowmap = KERN_GPUPREAGG_KROWMAP(kgpreagg);
     const cl_uint   nrows = kds_in->nitems;
     const cl_uint   nvalids = (krowmap->nvalids < 0
@@ -2294,6 +2396,65 @@ gpupreagg_import(pgs_gstate gs, const cl_ulong *records, cl_uint nrecords,
                                 (cl_uint)(rec[0] >> 32)))
             atomicCAS(&kgpreagg->status, StromError_Success,
                       StromError_DataStoreNoSpace);
+    }
+}
+
+/*
+ * gpupreagg_import_blocks - import what ncclAllGather delivered: one block of
+ * (1 + cap) records per rank, record 0 = header whose first word is the
+ * number of records that follow.  The root merges every block but its own.
+ */
+extern "C" __global__ void
+gpupreagg_import_blocks(pgs_gstate gs, const cl_ulong *blocks, cl_uint nranks,
+                        cl_uint root, cl_uint cap, kern_gpupreagg *kgpreagg)
+{
+    const cl_ulong  block_words = (cl_ulong)(1 + cap) * PGS_SLOT_WORDS;
+
+    if (GPUPREAGG_NUM_KEYS == 0)
+    {
+        /* one thread, rank order: deterministic */
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+        {
+            cl_uint nn = (cl_uint)gs.ng_state[0];
+            for (cl_uint r = 0; r < nranks; r++)
+            {
+                const cl_ulong *rec = blocks + r * block_words + PGS_SLOT_WORDS;
+                cl_uint src_nn = (cl_uint)(rec[0] >> 32);
+                if (r == root || (cl_uint)blocks[r * block_words] == 0)
+                    continue;
+                gpupreagg_aggmerge_plain(gs.ng_state + 1, rec + 1, src_nn);
+                nn |= src_nn;
+            }
+            gs.ng_state[0] = nn;
+        }
+        return;
+    }
+    for (cl_uint r = 0; r < nranks; r++)
+    {
+        const cl_ulong *recs = blocks + r * block_words + PGS_SLOT_WORDS;
+        cl_uint     n = (cl_uint)blocks[r * block_words];
+
+        if (r == root)
+            continue;
+        if (n > cap)
+        {
+            atomicCAS(&kgpreagg->status, StromError_Success, StromError_DataStoreNoSpace);
+            n = cap;
+        }
+        for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x;
+             i < n;
+             i += (cl_ulong)gridDim.x * blockDim.x)
+        {
+            const cl_ulong *rec = recs + i * PGS_SLOT_WORDS;
+            cl_uint     knull = (cl_uint)rec[0] >> 8;
+
+            if (!pgs_gh_merge_state(gs, rec + 1, knull,
+                                    pgs_hash_keyvals(rec + 1, knull),
+                                    rec + 1 + GPUPREAGG_NUM_KEYS,
+                                    (cl_uint)(rec[0] >> 32)))
+                atomicCAS(&kgpreagg->status, StromError_Success,
+                          StromError_DataStoreNoSpace);
+        }
     }
 }
 
