@@ -645,9 +645,9 @@ session_alloc_state(pgs_session *s)
         while ((double)nslots < want && nslots < (1ULL << 31))
             nslots <<= 1;
         cudaMemGetInfo(&free_b, &total_b);
-        while (nslots > 1024 && nslots * (size_t)s->desc.slot_bytes > free_b / 2)
+        while (nslots > 1024 && nslots * (size_t)s->desc.slot_stride_bytes > free_b / 2)
             nslots >>= 1;
-        CUDA_CHECK(cudaMalloc((void **)&s->gs.gh_slots, nslots * (size_t)s->desc.slot_bytes));
+        CUDA_CHECK(cudaMalloc((void **)&s->gs.gh_slots, nslots * (size_t)s->desc.slot_stride_bytes));
         s->gs.gh_nslots = (cl_uint)nslots;
         s->gs.gh_max_probe = (cl_uint)std::min<size_t>(nslots, 4096);
     }

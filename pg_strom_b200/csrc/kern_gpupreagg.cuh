@@ -872,6 +872,10 @@ gpupreagg_aggmerge_atomic(CELLS cells, SRC src, cl_uint src_nn)
  */
 #define PGS_SLOT_WORDS  (1 + GPUPREAGG_NUM_KEYS + GPUPREAGG_NUM_CELLS)
 #define PGS_SLOT_BYTES  (8 * PGS_SLOT_WORDS)
+/* in the table a slot starts on a 32-byte boundary: it then covers whole
+ * sectors (the unit of L2 atomics and DRAM traffic) and never more of them
+ * than it has to; exported records stay packed */
+#define PGS_SLOT_STRIDE ((PGS_SLOT_WORDS + 3) & ~3)
 
 /* pgs_gstate / pgs_kern_desc: see kern_shared.h (shared with the host) */
 
@@ -898,25 +902,32 @@ pgs_stage_nul_off(int slot, cl_uint tile_rows)
         (cl_uint)slot * (tile_rows / 8);
 }
 #define PGS_STAGE_BYTES(tile_rows)  pgs_stage_nul_off(GPUPREAGG_NUM_INCOLS, (tile_rows))
-/* head of dynamic smem: 2 x MAX_STAGES mbarriers, column positions */
-/* per consumer warp: queue of the rows that passed the qual (GROUP BY with a
- * WHERE clause only, see the consumer loop).  It carries the staged column
- * values of the row, so it outlives the tile the row came from:
- *   [col0 values | col1 values | ... | validity mask (u32) | row number (u32)]
- * with PGS_ROWQ_ENTRIES entries per array. */
-#define PGS_ROWQ_ENTRIES    64              /* < 32 left over + 32 new */
+/* Per consumer warp (GROUP BY with a WHERE clause only, see the consumer
+ * loop): a circular queue of the rows that passed the qual and a buffer that
+ * keeps the values of the few queued rows a tile leaves behind.
+ *
+ *   queue   : PGS_ROWQ_ENTRIES x u16.  An entry is the row's position in the
+ *             staged tile, or PGS_ROWQ_LEFT | n for row n of the leftover buffer
+ *   leftover: [col0 values | col1 values | ... | validity mask (u32) | row
+ *             number (u32)], PGS_ROWQ_LEFT_ENTRIES entries per array.  Queue
+ *             position p always maps to leftover entry p mod 32, so an entry
+ *             that survives several tiles never moves.
+ */
+#define PGS_ROWQ_ENTRIES        256         /* power of two, > 31 + 128 */
+#define PGS_ROWQ_LEFT           0x8000U
+#define PGS_ROWQ_LEFT_ENTRIES   32
 DEVFN cl_uint
 pgs_rowq_val_off(int slot)
 {
-    cl_uint off = 0;
+    cl_uint off = 2 * PGS_ROWQ_ENTRIES;
 #pragma unroll
     for (int s = 0; s < slot; s++)
-        off += PGS_ROWQ_ENTRIES * GPUPREAGG_INCOL_ATTLEN(s);
-    return off;
+        off += PGS_ROWQ_LEFT_ENTRIES * GPUPREAGG_INCOL_ATTLEN(s);
+    return (off + 7U) & ~7U;
 }
-#define PGS_ROWQ_MASK_OFF   pgs_rowq_val_off(GPUPREAGG_NUM_INCOLS)
-#define PGS_ROWQ_ROW_OFF    (PGS_ROWQ_MASK_OFF + 4 * PGS_ROWQ_ENTRIES)
-#define PGS_ROWQ_WARP_BYTES (PGS_ROWQ_ROW_OFF + 4 * PGS_ROWQ_ENTRIES)
+#define PGS_ROWQ_MASK_OFF   ((pgs_rowq_val_off(GPUPREAGG_NUM_INCOLS) + 7U) & ~7U)
+#define PGS_ROWQ_ROW_OFF    (PGS_ROWQ_MASK_OFF + 4 * PGS_ROWQ_LEFT_ENTRIES)
+#define PGS_ROWQ_WARP_BYTES ((PGS_ROWQ_ROW_OFF + 4 * PGS_ROWQ_LEFT_ENTRIES + 15U) & ~15U)
 #if GPUPREAGG_NUM_KEYS > 0 && GPUPREAGG_HAS_QUAL
 #define PGS_ROWQ_BYTES      (PGS_ROWQ_WARP_BYTES * GPUPREAGG_CONSUMER_WARPS)
 #else
@@ -928,48 +939,43 @@ pgs_rowq_val_off(int slot)
     PGS_ALIGN128(16 * GPUPREAGG_MAX_STAGES + 8 * PGS_MAX(GPUPREAGG_NUM_INCOLS,1) + 64)
 #define PGS_SMEM_HEAD_BYTES     PGS_ALIGN128(PGS_SMEM_HEAD_FIXED + PGS_ROWQ_BYTES)
 
-/* view of one warp's row queue for the generated functions: "row" i is
- * queue entry i */
-struct kern_rowq_smem
+/* view of ONE queued row for the generated functions: the row lives either
+ * in the staged tile or in the warp's leftover buffer (per lane). */
+struct kern_qrow_smem
 {
-    cl_uint     base;           /* smem offset of the warp's queue */
+    cl_uint     val_off[PGS_MAX(GPUPREAGG_NUM_INCOLS, 1)];  /* array of the column */
+    cl_uint     nul_off[PGS_MAX(GPUPREAGG_NUM_INCOLS, 1)];  /* staged bitmap or NO_NULLMAP */
+    cl_uint     idx;            /* position in those arrays */
+    cl_uint     lmask;          /* leftover row: validity bit per slot */
+    bool        isleft;
 
     template <typename T>
     __device__ __forceinline__ bool
-    fetch(int slot, cl_uint idx, T &out) const
+    fetch(int slot, cl_uint rowidx, T &out) const
     {
-        out = *((const T *)(__pgs_smem + base + pgs_rowq_val_off(slot)) + idx);
-        return ((*((const cl_uint *)(__pgs_smem + base + PGS_ROWQ_MASK_OFF) + idx)
-                 >> slot) & 1U) != 0;
-    }
-    __device__ __forceinline__ cl_uint
-    rownum(cl_uint idx) const
-    {
-        return *((const cl_uint *)(__pgs_smem + base + PGS_ROWQ_ROW_OFF) + idx);
+        cl_uint vb = 1U;
+
+        out = *((const T *)(__pgs_smem + val_off[slot]) + idx);
+        if (nul_off[slot] != KERN_TILE_NO_NULLMAP)
+            vb = (*((const cl_uint *)(__pgs_smem + nul_off[slot]) + (idx >> 5))
+                  >> (idx & 31)) & 1U;
+        if (isleft)
+            vb = (lmask >> slot) & 1U;
+        return vb != 0;
     }
 };
-/* store of one value by width */
-template <int ATTLEN> struct pgs_rowq_store;
-template <> struct pgs_rowq_store<8>
-{ static __device__ __forceinline__ void put(unsigned char *p, cl_uint i, cl_ulong v)
-  { ((cl_ulong *)p)[i] = v; } };
-template <> struct pgs_rowq_store<4>
-{ static __device__ __forceinline__ void put(unsigned char *p, cl_uint i, cl_ulong v)
-  { ((cl_uint *)p)[i] = (cl_uint)v; } };
-template <> struct pgs_rowq_store<2>
-{ static __device__ __forceinline__ void put(unsigned char *p, cl_uint i, cl_ulong v)
-  { ((cl_ushort *)p)[i] = (cl_ushort)v; } };
-template <> struct pgs_rowq_store<1>
-{ static __device__ __forceinline__ void put(unsigned char *p, cl_uint i, cl_ulong v)
-  { ((unsigned char *)p)[i] = (unsigned char)v; } };
-/* queue one row straight from the stage (only the columns the qual reads
- * were pulled into registers; the others are touched for survivors only) */
 template <int ATTLEN> struct pgs_rowq_type;
 template <> struct pgs_rowq_type<8> { typedef cl_ulong T; };
 template <> struct pgs_rowq_type<4> { typedef cl_uint T; };
 template <> struct pgs_rowq_type<2> { typedef cl_ushort T; };
 template <> struct pgs_rowq_type<1> { typedef unsigned char T; };
-#define PGS_X_INCOL_QPUSH(slot,colidx,attlen)                           \
+/* where the view of queue entry __e finds column `slot` */
+#define PGS_X_INCOL_QVIEW(slot,colidx,attlen)                           \
+    qrow.val_off[slot] = (qrow.isleft ? __qbase + pgs_rowq_val_off(slot) \
+                                      : tile.val_off[slot]);            \
+    qrow.nul_off[slot] = (qrow.isleft ? KERN_TILE_NO_NULLMAP : tile.nul_off[slot]);
+/* copy staged row __ri into leftover entry __pos */
+#define PGS_X_INCOL_QKEEP(slot,colidx,attlen)                           \
     ((pgs_rowq_type<attlen>::T *)(__pgs_smem + __qbase + pgs_rowq_val_off(slot)))[__pos] = \
         ((const pgs_rowq_type<attlen>::T *)(__pgs_smem + tile.val_off[slot]))[__ri]; \
     {                                                                   \
@@ -1105,6 +1111,9 @@ pgs_f8_canon(double v)
 /* ------------------------------------------------------------------
  * CTA-local table (shared memory, SoA):
  *   ctrl_lo[n] (u32) | ctrl_hi[n] (u32) | key[NKEYS][n] (u64) | cell[NCELLS][n]
+ * ctrl_lo = tag (see pgs_sh_find_slot): PGS_SLOT_* in bits 0-1, key-is-NULL
+ * bits from bit 2, fingerprint of the hash above them; ctrl_hi = "saw a
+ * non-NULL input" bit per aggregate.  nslots is a multiple of 32.
  * ------------------------------------------------------------------ */
 #define PGS_SH_SLOT_BYTES   (8 + 8 * GPUPREAGG_NUM_KEYS + 8 * GPUPREAGG_NUM_CELLS)
 
@@ -1145,7 +1154,7 @@ struct pgs_sh_cells
  * publish.) */
 DEVFN cl_ulong *
 pgs_gh_find_slot(const pgs_gstate &gs, const cl_ulong *keyvals,
-                 cl_uint knull, cl_ulong hash)
+                 cl_uint knull, cl_ulong hash, cl_uint &ninserted)
 {
     const cl_uint mask = gs.gh_nslots - 1;
     cl_uint     h = (cl_uint)hash & mask;
@@ -1155,7 +1164,7 @@ pgs_gh_find_slot(const pgs_gstate &gs, const cl_ulong *keyvals,
 
     while (!done)
     {
-        cl_ulong   *slot = gs.gh_slots + (cl_ulong)h * PGS_SLOT_WORDS;
+        cl_ulong   *slot = gs.gh_slots + (cl_ulong)h * PGS_SLOT_STRIDE;
         cl_uint     st = *((volatile cl_uint *)slot);
 
         if ((st & 3U) == PGS_SLOT_READY)
@@ -1183,9 +1192,14 @@ pgs_gh_find_slot(const pgs_gstate &gs, const cl_ulong *keyvals,
 #pragma unroll
                 for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
                     slot[1 + k] = keyvals[k];
-                __threadfence();
-                atomicExch((cl_uint *)slot, PGS_SLOT_READY | (knull << 8));
-                atomicAdd(gs.gh_ngroups, 1U);
+                /* publish: the keys are visible before the state is (a
+                 * release store, not the sequentially consistent fence of
+                 * __threadfence()); the number of groups is counted per
+                 * thread and added up once per warp and launch - one
+                 * counter bumped by every insert serialises in L2 */
+                asm volatile("st.release.gpu.global.u32 [%0], %1;"
+                             :: "l"(slot), "r"(PGS_SLOT_READY | (knull << 8)) : "memory");
+                ninserted++;
                 found = slot;
                 done = true;
             }
@@ -1199,9 +1213,10 @@ pgs_gh_find_slot(const pgs_gstate &gs, const cl_ulong *keyvals,
 /* merge a state (cells + nn bits) into the global table */
 DEVFN bool
 pgs_gh_merge_state(const pgs_gstate &gs, const cl_ulong *keyvals, cl_uint knull,
-                   cl_ulong hash, const cl_ulong *src, cl_uint src_nn)
+                   cl_ulong hash, const cl_ulong *src, cl_uint src_nn,
+                   cl_uint &ninserted)
 {
-    cl_ulong   *slot = pgs_gh_find_slot(gs, keyvals, knull, hash);
+    cl_ulong   *slot = pgs_gh_find_slot(gs, keyvals, knull, hash, ninserted);
     cl_ulong   *cells;
     cl_uint    *p_nn;
 
@@ -1215,54 +1230,97 @@ pgs_gh_merge_state(const pgs_gstate &gs, const cl_ulong *keyvals, cl_uint knull,
     return true;
 }
 
-/* find-or-insert in the CTA-local table; returns slot index or ~0U if the
- * table is (nearly) full and the row has to go to the global table */
+/*
+ * find-or-insert in the CTA-local table; returns the slot index or ~0U if the
+ * table is (nearly) full and the row has to go to the global table.
+ *
+ * The table is probed a bucket of four slots at a time: one 128-bit load
+ * brings four tags, a tag = fingerprint of the hash | key-is-NULL bits |
+ * PGS_SLOT_* state, and the keys of a slot are compared only when its tag
+ * matches.  With linear probing of single slots the longest probe sequence
+ * among the 32 lanes of a warp decided how often the warp went round the loop
+ * (measured: 7 rounds with 7 lanes active on average at 58% load); with
+ * buckets nearly every lane is done after the first round.
+ * A key is only ever inserted into the first EMPTY slot of the first bucket
+ * that has one, slots never become EMPTY again, and a slot that is BUSY with
+ * the fingerprint looked for is waited for - so a key cannot be inserted twice.
+ */
+#define PGS_TAG_SHIFT       (2 + GPUPREAGG_NUM_KEYS)
+
+DEVFN uint4
+pgs_lds_volatile_v4(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(pgs_smem_addr(p)) : "memory");
+    return v;
+}
+
 DEVFN cl_uint
 pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
                  const cl_ulong *keyvals, cl_uint knull, cl_ulong hash)
 {
+    const cl_uint nbuckets = sh.nslots >> 2;
     const cl_uint limit = sh.nslots - (sh.nslots >> 2);     /* 75% */
-    cl_uint     h = __umulhi((cl_uint)(hash >> 32), sh.nslots);    /* high bits */
+    const cl_uint want = ((cl_uint)hash << PGS_TAG_SHIFT) | (knull << 2) | PGS_SLOT_READY;
+    const cl_uint busy = want ^ (PGS_SLOT_READY ^ PGS_SLOT_BUSY);
+    cl_uint     b = __umulhi((cl_uint)(hash >> 32), nbuckets);     /* high bits */
     cl_uint     probe = 0;
     cl_uint     found = ~0U;
     bool        done = false;
 
     while (!done)
     {
-        cl_uint st = *((volatile cl_uint *)sh.ctrl_lo(h));
+        uint4       t = pgs_lds_volatile_v4(sh.ctrl_lo(4 * b));
+        cl_uint     hits = (t.x == want ? 1U : 0U) | (t.y == want ? 2U : 0U) |
+                           (t.z == want ? 4U : 0U) | (t.w == want ? 8U : 0U);
 
-        if ((st & 3U) == PGS_SLOT_READY)
+        /* fingerprints collide once in 2^(30 - NKEYS) slots: nearly always
+         * the first hit is the group */
+        while (hits != 0 && found == ~0U)
         {
-            bool    same = ((st >> 8) == knull);
+            cl_uint s = 4 * b + (__ffs(hits) - 1);
+            bool    same = true;
 #pragma unroll
             for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
-                same = same && (*((volatile cl_ulong *)sh.key(k, h)) == keyvals[k]);
+                same = same && (*((volatile cl_ulong *)sh.key(k, s)) == keyvals[k]);
             if (same)
+                found = s;
+            hits &= hits - 1;
+        }
+        if (found != ~0U)
+            done = true;
+        else if (t.x == busy || t.y == busy || t.z == busy || t.w == busy)
+            ;   /* perhaps our key, published shortly: look at the bucket again */
+        else
+        {
+            cl_uint empties = (t.x == PGS_SLOT_EMPTY ? 1U : 0U) | (t.y == PGS_SLOT_EMPTY ? 2U : 0U) |
+                              (t.z == PGS_SLOT_EMPTY ? 4U : 0U) | (t.w == PGS_SLOT_EMPTY ? 8U : 0U);
+            if (empties != 0)
             {
-                found = h;
-                done = true;
+                cl_uint s = 4 * b + (__ffs(empties) - 1);
+
+                if (*((volatile cl_uint *)sh_nused) >= limit)
+                    done = true;
+                else if (atomicCAS(sh.ctrl_lo(s), PGS_SLOT_EMPTY, busy) == PGS_SLOT_EMPTY)
+                {
+                    atomicAdd(sh_nused, 1U);
+#pragma unroll
+                    for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+                        *sh.key(k, s) = keyvals[k];
+                    __threadfence_block();
+                    atomicExch(sh.ctrl_lo(s), want);
+                    found = s;
+                    done = true;
+                }
+                /* lost the race: look at the bucket again */
             }
             else
             {
-                h = (h + 1 < sh.nslots ? h + 1 : 0);    /* any table size */
-                if (++probe >= 64)
+                b = (b + 1 < nbuckets ? b + 1 : 0);         /* any table size */
+                if (++probe >= 16)
                     done = true;
-            }
-        }
-        else if ((st & 3U) == PGS_SLOT_EMPTY)
-        {
-            if (*((volatile cl_uint *)sh_nused) >= limit)
-                done = true;
-            else if (atomicCAS(sh.ctrl_lo(h), PGS_SLOT_EMPTY, PGS_SLOT_BUSY) == PGS_SLOT_EMPTY)
-            {
-                atomicAdd(sh_nused, 1U);
-#pragma unroll
-                for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
-                    *sh.key(k, h) = keyvals[k];
-                __threadfence_block();
-                atomicExch(sh.ctrl_lo(h), PGS_SLOT_READY | (knull << 8));
-                found = h;
-                done = true;
             }
         }
     }
@@ -1276,6 +1334,7 @@ struct pgs_row_ctx
 {
     cl_uint     nfiltered;
     cl_uint     nrecheck;
+    cl_uint     ninserted;      /* groups this thread added to the global table */
     cl_int      errcode;        /* first significant error seen */
 };
 
@@ -1329,6 +1388,7 @@ pgs_writeback_status(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
      * (kern_writeback_error_status, opencl_common.h:1481-1527) */
     cl_uint     nf = pgs_warp_sum(ctx.nfiltered);
     cl_uint     nr = pgs_warp_sum(ctx.nrecheck);
+    cl_uint     ni = pgs_warp_sum(ctx.ninserted);
     cl_int      ec = ctx.errcode;
 
 #pragma unroll
@@ -1342,6 +1402,8 @@ pgs_writeback_status(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
     {
         if (nf)
             atomicAdd((unsigned long long *)gs.nrows_filtered, (unsigned long long)nf);
+        if (ni)
+            atomicAdd(gs.gh_ngroups, ni);
         if (ec != StromError_Success)
         {
             cl_int cur = atomicCAS(&kgpreagg->status, StromError_Success, ec);
@@ -1487,7 +1549,7 @@ pgs_group_add_row(const pgs_gstate &gs, const pgs_sh_table &sh,
     if (__any_sync(0xffffffffU, active && s == ~0U))
     {
         if (active && s == ~0U)
-            gslot = pgs_gh_find_slot(gs, keyvals, knull, hash);
+            gslot = pgs_gh_find_slot(gs, keyvals, knull, hash, ctx.ninserted);
         __syncwarp();
     }
     if (active)
@@ -1530,58 +1592,6 @@ pgs_note_error(cl_int errcode, cl_uint row, cl_uint *recheck_map, pgs_row_ctx &c
     }
     else if (ctx.errcode == StromError_Success)
         ctx.errcode = errcode;
-}
-
-/* one queued row per lane (it passed the qual already): projection from the
- * warp's row queue, then into the group state.  Warp-collective like
- * pgs_group_add_row; lanes without a row pass active = false.  Not inlined:
- * six copies of this chain would not fit the instruction cache well. */
-static __device__ __noinline__ void
-pgs_group_add_queued_call(const kern_parambuf *kparams, const kern_rowq_smem &rowq,
-                     const void *ktoast, cl_uint idx, bool active,
-                     const pgs_gstate &gs, const pgs_sh_table &sh,
-                     cl_uint *sh_nused, cl_uint *recheck_map, pgs_row_ctx &ctx)
-{
-    pagg_row    prow;
-
-    if (active)
-    {
-        cl_int  e = StromError_Success;
-
-        gpupreagg_projection(&e, kparams, rowq, prow, ktoast, idx, 0);
-        gpupreagg_aggcheck(&e, prow);
-        if (e != StromError_Success)
-        {
-            pgs_note_error(e, rowq.rownum(idx), recheck_map, ctx);
-            active = false;
-        }
-    }
-    pgs_group_add_row(gs, sh, sh_nused, prow, ctx, active);
-}
-
-/* The callee is not inlined and takes its state by reference: hand it copies,
- * so that the caller's hot-loop variables (row counters, table geometry) stay
- * in registers instead of being reloaded from the stack after every call. */
-DEVFN void
-pgs_group_add_queued(const kern_parambuf *kparams, const kern_rowq_smem &rowq,
-                     const void *ktoast, cl_uint idx, bool active,
-                     const pgs_gstate &gs, const pgs_sh_table &sh,
-                     cl_uint *sh_nused, cl_uint *recheck_map, pgs_row_ctx &ctx)
-{
-    kern_rowq_smem  rowq2 = rowq;
-    pgs_gstate      gs2 = gs;
-    pgs_sh_table    sh2 = sh;
-    pgs_row_ctx     ctx2;
-
-    ctx2.nfiltered = 0;
-    ctx2.nrecheck = 0;
-    ctx2.errcode = StromError_Success;
-    pgs_group_add_queued_call(kparams, rowq2, ktoast, idx, active, gs2, sh2,
-                              sh_nused, recheck_map, ctx2);
-    ctx.nfiltered += ctx2.nfiltered;
-    ctx.nrecheck += ctx2.nrecheck;
-    if (ctx.errcode == StromError_Success)
-        ctx.errcode = ctx2.errcode;
 }
 
 /* threads of the CTA -> thread 0, always combined in the same order: lanes by
@@ -1704,7 +1714,7 @@ pgs_main_epilogue(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
 
             if ((st & 3U) != PGS_SLOT_READY)
                 continue;
-            knull = st >> 8;
+            knull = (st >> 2) & ((1U << GPUPREAGG_NUM_KEYS) - 1U);
 #pragma unroll
             for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
                 keyvals[k] = *sh.key(k, s);
@@ -1713,7 +1723,7 @@ pgs_main_epilogue(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
                 src[c] = *sh.cell(c, s);
             if (!pgs_gh_merge_state(gs, keyvals, knull,
                                     pgs_hash_keyvals(keyvals, knull),
-                                    src, *sh.ctrl_hi(s)))
+                                    src, *sh.ctrl_hi(s), ctx.ninserted))
             {
                 if (ctx.errcode == StromError_Success)
                     ctx.errcode = StromError_DataStoreNoSpace;
@@ -1766,6 +1776,7 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
 
     ctx.nfiltered = 0;
     ctx.nrecheck = 0;
+    ctx.ninserted = 0;
     ctx.errcode = StromError_Success;
     sh.base = PGS_SMEM_HEAD_BYTES + nstages * PGS_STAGE_BYTES(tile_rows);
     sh.nslots = (GPUPREAGG_NUM_KEYS > 0 ? sh_nslots : 0);
@@ -1822,10 +1833,13 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
 
         tacc.init();
 #elif GPUPREAGG_HAS_QUAL
-        kern_rowq_smem  rowq;
-        cl_uint         qn = 0;         /* queued rows, warp-uniform */
-
-        rowq.base = PGS_SMEM_HEAD_FIXED + (warp_id - 1) * PGS_ROWQ_WARP_BYTES;
+        /* the warp's row queue (see PGS_ROWQ_*): free-running positions,
+         * warp-uniform; npassed counts the rows its qual let through */
+        const cl_uint   __qbase = PGS_SMEM_HEAD_FIXED + (warp_id - 1) * PGS_ROWQ_WARP_BYTES;
+        cl_ushort      *rowq = (cl_ushort *)(__pgs_smem + __qbase);
+        const cl_uint   lanes_lt = (1U << lane_id) - 1U;
+        cl_uint         qhead = 0, qtail = 0;
+        cl_uint         nscanned = 0, npassed = 0;
 #endif
         cl_uint         stage = 0, phase = 0;
         PGS_DBG_DECL
@@ -1910,8 +1924,50 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                 }
             }
 #elif !GPUPREAGG_HAS_QUAL
-            /* GROUP BY, every row takes part.  The trip count is the same
-             * for every lane of the warp (pgs_group_add_row is collective). */
+            /* GROUP BY, every row takes part.
+             * Without a CTA-local table (many groups) every row goes to its
+             * slot of the global table in HBM: a chain of dependent accesses
+             * (state word, keys, atomics) whose first one misses L2 - the
+             * warp would sit out a DRAM round trip per row (measured: 4.7%
+             * issue slots used, 13 ms per 50 M rows).  So the warp first asks
+             * L2 for the home slot of every row it owns in this tile
+             * (prefetch.global.L2, nothing waits for it) and only then works
+             * through the rows. */
+            if (sh.nslots == 0)
+            {
+                for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
+                     rb += GPUPREAGG_CONSUMER_THREADS * 4)
+                {
+                    const cl_uint r = rb + lane_id * 4;
+                    kern_row_regs rr[4];
+
+                    rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        if (r + j < rows)
+                        {
+                            pagg_row    prow;
+                            cl_int      e = StromError_Success;
+                            cl_uint     knull;
+                            cl_ulong    hash;
+                            const cl_ulong *home;
+
+                            gpupreagg_projection(&e, kparams, rr[j], prow, kds_in,
+                                                 row0 + r + j, 0);
+                            hash = pgs_hash_keys(prow, knull);
+                            home = gs.gh_slots +
+                                (cl_ulong)((cl_uint)hash & (gs.gh_nslots - 1)) * PGS_SLOT_STRIDE;
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(home));
+                            if (8 * PGS_SLOT_STRIDE > 64)
+                                asm volatile("prefetch.global.L2 [%0];" :: "l"(home + 8));
+                        }
+                    }
+                }
+            }
+            /* The trip count is the same for every lane of the warp
+             * (pgs_group_add_row is collective). */
             for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
                  rb += GPUPREAGG_CONSUMER_THREADS * 4)
             {
@@ -1928,104 +1984,122 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
             /* GROUP BY under a WHERE clause.  Only a fraction of the rows
              * reaches the hash table; taking that path per row would run it
              * with a few lanes of each warp.  So a warp evaluates the qual
-             * of 128 rows (4 per lane, from registers) and compacts the
-             * survivors - their staged column values, with ballots - into
-             * its queue; whenever 32 rows are queued, every lane takes one
-             * through projection + find-or-insert + the cell updates.
-             * The queue carries values, not tile positions, so the warp hands
-             * the stage back as soon as its rows are queued and runs that
-             * chain of dependent shared-memory operations afterwards: it
-             * overlaps the other warps and the TMA refill instead of holding
-             * up the whole CTA once per tile.  What is left at the end of the
-             * scan is drained below the tile loop. */
-            for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
-                 rb += GPUPREAGG_CONSUMER_THREADS * 4)
+             * of 128 rows (4 per lane, from registers), and the survivors'
+             * positions in the tile go - compacted with ballots - into its
+             * queue: one 16-bit store per surviving row.  Whenever 32 rows
+             * are queued every lane takes one through projection (read from
+             * the stage by position) + find-or-insert + the cell updates;
+             * that chain exists once in the program, here.  The < 32 rows
+             * that are still queued when the tile is done are copied by
+             * value into the warp's leftover buffer, so the stage goes back
+             * to the producer and the rows join the next tile's first chain.
+             * Every warp makes the same number of steps per tile (bounds
+             * are checked per row), so the very last step of the scan is
+             * where each warp drains what it has left. */
             {
-                /* the trip count is the same for every lane of the warp
-                 * (ballots inside): bounds are checked per row */
-                const cl_uint r = rb + lane_id * 4;
-                kern_row_regs rr[4];
+                const cl_uint   step_rows = GPUPREAGG_CONSUMER_THREADS * 4;
+                const cl_uint   rows_up = ((rows + step_rows - 1) / step_rows) * step_rows;
+                const bool      last_tile = (t + gridDim.x >= ntiles);
 
-                rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
-                GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
-                /* the 4 rows are independent up to here: evaluate all four
-                 * quals and take the four ballots before anything is queued,
-                 * so that their latencies overlap */
-                bool        valid4[4];
-                cl_uint     votes4[4];
-                cl_uint     total = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++)
+                for (cl_uint rb = (ctid & ~31U) * 4; rb < rows_up; rb += step_rows)
                 {
-                    cl_int      e = StromError_Success;
+                    const cl_uint r = rb + lane_id * 4;
+                    const cl_uint nv = (r < rows ? min(rows - r, 4U) : 0U);
+                    kern_row_regs rr[4];
+                    bool        valid4[4];
+                    cl_uint     votes4[4];
 
-                    valid4[j] = false;
-                    if (r + j < rows)
+                    rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+                    /* the 4 rows are independent: all four quals, then the
+                     * four ballots, so that their latencies overlap */
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
                     {
+                        cl_int      e = StromError_Success;
+
                         valid4[j] = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
-                                                        row0 + r + j);
+                                                        row0 + r + j) & ((cl_uint)j < nv);
                         if (e != StromError_Success)
                         {
-                            pgs_note_error(e, row0 + r + j, recheck_map, ctx);
+                            if ((cl_uint)j < nv)
+                            {
+                                pgs_note_error(e, row0 + r + j, recheck_map, ctx);
+                                ctx.nfiltered--;    /* neither passed nor filtered */
+                            }
                             valid4[j] = false;
                         }
-                        else if (!valid4[j])
-                            ctx.nfiltered++;
                     }
-                }
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                {
-                    votes4[j] = __ballot_sync(0xffffffffU, valid4[j]);
-                    total += __popc(votes4[j]);
-                }
+                    for (int j = 0; j < 4; j++)
+                        votes4[j] = __ballot_sync(0xffffffffU, valid4[j]);
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                {
-                    const bool      valid = valid4[j];
-                    const cl_uint   votes = votes4[j];
-
-                    if (qn + __popc(votes) > PGS_ROWQ_ENTRIES)
+                    for (int j = 0; j < 4; j++)
                     {
-                        /* no room for this step's rows (selective quals
-                         * rarely get here): make room inside the tile */
-                        __syncwarp();
-                        PGS_DBG_COUNT(3)
-                        qn -= 32;
-                        pgs_group_add_queued(kparams, rowq, kds_in, qn + lane_id, true,
-                                             gs, sh, &head->sh_nused, recheck_map, ctx);
+                        if (valid4[j])
+                            rowq[(qtail + __popc(votes4[j] & lanes_lt)) & (PGS_ROWQ_ENTRIES - 1)] =
+                                (cl_ushort)(r + j);
+                        qtail += __popc(votes4[j]);
                     }
-                    if (valid)
+                    nscanned += min(rows - min(rb, rows), 128U);
+                    __syncwarp();
                     {
-                        const cl_uint __qbase = rowq.base;
-                        const cl_uint __ri = r + j;         /* row in the tile */
-                        cl_uint     __pos = qn + __popc(votes & ((1U << lane_id) - 1U));
-                        cl_uint     __mask = 0;
+                        const bool drain = last_tile && (rb + step_rows >= rows_up);
 
-                        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_QPUSH)
-                        *((cl_uint *)(__pgs_smem + rowq.base + PGS_ROWQ_MASK_OFF) + __pos) = __mask;
-                        *((cl_uint *)(__pgs_smem + rowq.base + PGS_ROWQ_ROW_OFF) + __pos) =
-                            row0 + r + j;
+                        while (qtail - qhead >= 32 || (drain && qtail != qhead))
+                        {
+                            const cl_uint   n = min(qtail - qhead, 32U);
+                            const cl_uint   __e = rowq[(qhead + lane_id) & (PGS_ROWQ_ENTRIES - 1)];
+                            bool            active = (lane_id < n);
+                            kern_qrow_smem  qrow;
+                            pagg_row        prow;
+
+                            PGS_DBG_COUNT(3)
+                            qrow.isleft = ((__e & PGS_ROWQ_LEFT) != 0);
+                            qrow.idx = (__e & (PGS_ROWQ_LEFT - 1));
+                            qrow.lmask = *((const cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_MASK_OFF) +
+                                           (qrow.idx & (PGS_ROWQ_LEFT_ENTRIES - 1)));
+                            GPUPREAGG_INCOL_LIST(PGS_X_INCOL_QVIEW)
+                            if (active)
+                            {
+                                cl_int  e = StromError_Success;
+
+                                gpupreagg_projection(&e, kparams, qrow, prow, kds_in, 0, 0);
+                                gpupreagg_aggcheck(&e, prow);
+                                if (e != StromError_Success)
+                                {
+                                    cl_uint rownum = (qrow.isleft
+                                        ? *((const cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_ROW_OFF) + qrow.idx)
+                                        : row0 + qrow.idx);
+                                    pgs_note_error(e, rownum, recheck_map, ctx);
+                                    active = false;
+                                }
+                            }
+                            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, active);
+                            qhead += n;
+                            npassed += n;
+                        }
                     }
-                    qn += __popc(votes);
                 }
-                (void)total;
+                /* keep what is still queued from this tile */
+                if (lane_id < qtail - qhead)
+                {
+                    const cl_uint   __qp = (qhead + lane_id) & (PGS_ROWQ_ENTRIES - 1);
+                    const cl_uint   __ri = rowq[__qp];
+
+                    if ((__ri & PGS_ROWQ_LEFT) == 0)
+                    {
+                        const cl_uint   __pos = __qp & (PGS_ROWQ_LEFT_ENTRIES - 1);
+                        cl_uint         __mask = 0;
+
+                        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_QKEEP)
+                        *((cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_MASK_OFF) + __pos) = __mask;
+                        *((cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_ROW_OFF) + __pos) = row0 + __ri;
+                        rowq[__qp] = (cl_ushort)(PGS_ROWQ_LEFT | __pos);
+                    }
+                }
             }
-            /* done with the stage */
-            __syncwarp();
-            if (lane_id == 0)
-                pgs_mbar_arrive(&head->empty_bar[stage]);
             PGS_DBG_STOP(1)
-            PGS_DBG_START()
-            while (qn >= 32)
-            {
-                qn -= 32;
-                PGS_DBG_COUNT(3)
-                pgs_group_add_queued(kparams, rowq, kds_in, qn + lane_id, true,
-                                     gs, sh, &head->sh_nused, recheck_map, ctx);
-            }
-            PGS_DBG_STOP(2)
-            continue;
 #endif
             __syncwarp();
             if (lane_id == 0)
@@ -2034,10 +2108,9 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
 #if GPUPREAGG_NUM_KEYS == 0
         acc_nn |= tacc.fold(acc);
 #elif GPUPREAGG_HAS_QUAL
-        __syncwarp();
-        if (qn > 0)
-            pgs_group_add_queued(kparams, rowq, kds_in, lane_id, lane_id < qn,
-                                 gs, sh, &head->sh_nused, recheck_map, ctx);
+        /* rows the qual removed, counted per warp */
+        if (lane_id == 0)
+            ctx.nfiltered += nscanned - npassed;
         PGS_DBG_FLUSH()
 #endif
     }
@@ -2075,6 +2148,7 @@ gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
 
     ctx.nfiltered = 0;
     ctx.nrecheck = 0;
+    ctx.ninserted = 0;
     ctx.errcode = StromError_Success;
     sh.base = PGS_SMEM_HEAD_BYTES + nstages * PGS_STAGE_BYTES(tile_rows);
     sh.nslots = (GPUPREAGG_NUM_KEYS > 0 ? sh_nslots : 0);
@@ -2136,7 +2210,7 @@ gpupreagg_init_state(pgs_gstate gs)
     }
     for (; i < gs.gh_nslots; i += (cl_ulong)gridDim.x * blockDim.x)
     {
-        cl_ulong   *slot = gs.gh_slots + i * PGS_SLOT_WORDS;
+        cl_ulong   *slot = gs.gh_slots + i * PGS_SLOT_STRIDE;
 
         slot[0] = 0;
 #pragma unroll
@@ -2273,16 +2347,23 @@ pgs_piece_i128(cl_ulong lo, cl_ulong hi, cl_uint r)
       isnulls[col] = (cl_char)(isnull ? 1 : 0); }
 #define PGS_X_OUTCOL(col,ROLE,idx,c,OP,TYPE)    PGS_OUTCOL_##ROLE(col,idx,c,OP,TYPE)
 
-DEVFN void
-pgs_flush_group(kern_data_store *kds_dst, kern_gpupreagg *kgpreagg,
-                const cl_ulong *keys, cl_uint knull,
-                const cl_ulong *cells, cl_uint nn)
+/* rows one group needs in the result */
+DEVFN cl_uint
+pgs_flush_nsplit(const cl_ulong *cells)
 {
     cl_uint     nsplit = 1;
-    cl_uint     base;
 
     GPUPREAGG_AGG_LIST(PGS_X_NSPLIT)
-    base = atomicAdd(&kds_dst->nitems, nsplit);
+    return nsplit;
+}
+
+/* write the `nsplit` rows of one group at row `base` of the result */
+DEVFN void
+pgs_flush_rows(kern_data_store *kds_dst, kern_gpupreagg *kgpreagg,
+               cl_uint base, cl_uint nsplit,
+               const cl_ulong *keys, cl_uint knull,
+               const cl_ulong *cells, cl_uint nn)
+{
     if (base + nsplit > kds_dst->nrooms)
     {
         atomicCAS(&kgpreagg->status, StromError_Success,
@@ -2298,29 +2379,55 @@ pgs_flush_group(kern_data_store *kds_dst, kern_gpupreagg *kgpreagg,
     }
 }
 
+/* launched with whole warps.  Result rows are reserved once per warp (an
+ * exclusive scan of the rows each lane needs, one atomicAdd on nitems by
+ * lane 0): one atomicAdd per group on that single word serialises in L2 and
+ * took 26 ms for 10 M groups. */
 extern "C" __global__ void
 gpupreagg_flush(pgs_gstate gs, kern_data_store *kds_dst,
                 kern_gpupreagg *kgpreagg)
 {
+    const cl_uint   lane_id = threadIdx.x & 31;
+
     if (GPUPREAGG_NUM_KEYS == 0)
     {
         if (blockIdx.x == 0 && threadIdx.x == 0)
-            pgs_flush_group(kds_dst, kgpreagg, (const cl_ulong *)NULL, 0,
-                            gs.ng_state + 1, (cl_uint)gs.ng_state[0]);
+        {
+            cl_uint nsplit = pgs_flush_nsplit(gs.ng_state + 1);
+            cl_uint base = atomicAdd(&kds_dst->nitems, nsplit);
+
+            pgs_flush_rows(kds_dst, kgpreagg, base, nsplit, (const cl_ulong *)NULL, 0,
+                           gs.ng_state + 1, (cl_uint)gs.ng_state[0]);
+        }
         return;
     }
-    for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x;
-         i < gs.gh_nslots;
-         i += (cl_ulong)gridDim.x * blockDim.x)
+    for (cl_ulong i0 = (cl_ulong)blockIdx.x * blockDim.x + (threadIdx.x & ~31U);
+         i0 < gs.gh_nslots;
+         i0 += (cl_ulong)gridDim.x * blockDim.x)
     {
-        const cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_WORDS;
-        cl_uint     st = (cl_uint)slot[0];
+        const cl_ulong  i = i0 + lane_id;
+        const cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_STRIDE;
+        cl_uint     st = (i < gs.gh_nslots ? (cl_uint)slot[0] : PGS_SLOT_EMPTY);
+        bool        ready = ((st & 3U) == PGS_SLOT_READY);
+        cl_uint     nsplit = (ready ? pgs_flush_nsplit(slot + 1 + GPUPREAGG_NUM_KEYS) : 0);
+        cl_uint     incl = nsplit;
+        cl_uint     base = 0;
 
-        if ((st & 3U) != PGS_SLOT_READY)
-            continue;
-        pgs_flush_group(kds_dst, kgpreagg, slot + 1, st >> 8,
-                        slot + 1 + GPUPREAGG_NUM_KEYS,
-                        (cl_uint)(slot[0] >> 32));
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            cl_uint v = __shfl_up_sync(0xffffffffU, incl, d);
+            if (lane_id >= (cl_uint)d)
+                incl += v;
+        }
+        if (lane_id == 31 && incl > 0)
+            base = atomicAdd(&kds_dst->nitems, incl);
+        base = __shfl_sync(0xffffffffU, base, 31);
+        if (ready)
+            pgs_flush_rows(kds_dst, kgpreagg, base + incl - nsplit, nsplit,
+                           slot + 1, st >> 8,
+                           slot + 1 + GPUPREAGG_NUM_KEYS,
+                           (cl_uint)(slot[0] >> 32));
     }
 }
 
@@ -2344,15 +2451,25 @@ gpupreagg_export(pgs_gstate gs, cl_ulong *records, cl_uint *nrecords,
         }
         return;
     }
-    for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x;
-         i < gs.gh_nslots;
-         i += (cl_ulong)gridDim.x * blockDim.x)
+    /* whole warps; record positions are handed out once per warp */
+    for (cl_ulong i0 = (cl_ulong)blockIdx.x * blockDim.x + (threadIdx.x & ~31U);
+         i0 < gs.gh_nslots;
+         i0 += (cl_ulong)gridDim.x * blockDim.x)
     {
-        const cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_WORDS;
+        const cl_uint   lane_id = threadIdx.x & 31;
+        const cl_ulong  i = i0 + lane_id;
+        const cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_STRIDE;
+        bool        ready = (i < gs.gh_nslots &&
+                             ((cl_uint)slot[0] & 3U) == PGS_SLOT_READY);
+        cl_uint     votes = __ballot_sync(0xffffffffU, ready);
+        cl_uint     base = 0;
 
-        if (((cl_uint)slot[0] & 3U) == PGS_SLOT_READY)
+        if (lane_id == 0 && votes != 0)
+            base = atomicAdd(nrecords, (cl_uint)__popc(votes));
+        base = __shfl_sync(0xffffffffU, base, 0);
+        if (ready)
         {
-            cl_uint pos = atomicAdd(nrecords, 1U);
+            cl_uint pos = base + __popc(votes & ((1U << lane_id) - 1U));
             if (pos < max_records)
             {
                 for (int w = 0; w < PGS_SLOT_WORDS; w++)
@@ -2383,6 +2500,8 @@ gpupreagg_import(pgs_gstate gs, const cl_ulong *records, cl_uint nrecords,
         }
         return;
     }
+    cl_uint     ninserted = 0;
+
     for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x;
          i < nrecords;
          i += (cl_ulong)gridDim.x * blockDim.x)
@@ -2393,10 +2512,12 @@ gpupreagg_import(pgs_gstate gs, const cl_ulong *records, cl_uint nrecords,
         if (!pgs_gh_merge_state(gs, rec + 1, knull,
                                 pgs_hash_keyvals(rec + 1, knull),
                                 rec + 1 + GPUPREAGG_NUM_KEYS,
-                                (cl_uint)(rec[0] >> 32)))
+                                (cl_uint)(rec[0] >> 32), ninserted))
             atomicCAS(&kgpreagg->status, StromError_Success,
                       StromError_DataStoreNoSpace);
     }
+    if (ninserted)
+        atomicAdd(gs.gh_ngroups, ninserted);
 }
 
 /*
@@ -2429,6 +2550,8 @@ gpupreagg_import_blocks(pgs_gstate gs, const cl_ulong *blocks, cl_uint nranks,
         }
         return;
     }
+    cl_uint     ninserted = 0;
+
     for (cl_uint r = 0; r < nranks; r++)
     {
         const cl_ulong *recs = blocks + r * block_words + PGS_SLOT_WORDS;
@@ -2451,11 +2574,13 @@ gpupreagg_import_blocks(pgs_gstate gs, const cl_ulong *blocks, cl_uint nranks,
             if (!pgs_gh_merge_state(gs, rec + 1, knull,
                                     pgs_hash_keyvals(rec + 1, knull),
                                     rec + 1 + GPUPREAGG_NUM_KEYS,
-                                    (cl_uint)(rec[0] >> 32)))
+                                    (cl_uint)(rec[0] >> 32), ninserted))
                 atomicCAS(&kgpreagg->status, StromError_Success,
                           StromError_DataStoreNoSpace);
         }
     }
+    if (ninserted)
+        atomicAdd(gs.gh_ngroups, ninserted);
 }
 
 /* ------------------------------------------------------------------
@@ -2475,6 +2600,7 @@ gpupreagg_describe(pgs_kern_desc *desc)
     desc->num_cells = GPUPREAGG_NUM_CELLS;
     desc->num_outcols = GPUPREAGG_NUM_OUTCOLS;
     desc->slot_bytes = PGS_SLOT_BYTES;
+    desc->slot_stride_bytes = 8 * PGS_SLOT_STRIDE;
     desc->tile_rows = 1024;             /* granule of the tile size */
     desc->num_stages = GPUPREAGG_MAX_STAGES;
     desc->stage_bytes = PGS_STAGE_BYTES(1024);  /* per 1024 rows */

@@ -39,7 +39,8 @@ typedef struct
     cl_uint     block_threads;
     cl_uint     sh_slot_bytes;      /* bytes per slot of the CTA-local table */
     cl_uint     row_bytes;          /* algorithmic bytes per row (attlen sum) */
-    cl_uint     reserved[3];
+    cl_uint     slot_stride_bytes;  /* distance of two slots of the global table */
+    cl_uint     reserved[2];
 } pgs_kern_desc;
 
 #endif  /* KERN_SHARED_H */
