@@ -66,6 +66,9 @@ def parse_args():
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--e2e-chunk-rows", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--format", default="column", choices=["column", "row"],
+                    help="input chunks: KDS_FORMAT_COLUMN, or the reference's heap-page "
+                         "KDS_FORMAT_ROW (de-formed on the device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     return ap.parse_args()
@@ -250,16 +253,29 @@ def bench_ours(args):
     colchunks = generate_columns(workload, rank, rows, chunk_rows)
     coltypes = [t for _, t in w["table"].columns]
     host_chunks, dev_chunks = [], []
+    heap = (args.format == "row")
+    fmt = gp.KDS_FORMAT_ROW if heap else gp.KDS_FORMAT_COLUMN
     for cols in colchunks:
-        ds = gp.DataStore(coltypes, cols, nrows=len(cols[0][0]))
-        dptr = lib.pgs_device_alloc(0, ds.length)
-        assert dptr, lib.pgs_last_error()
-        _capi.check(lib.pgs_device_upload(0, dptr, ds.ptr, ds.length))
-        dev_chunks.append((dptr, ds.length, ds.nrows))
+        if heap:
+            ds = gp.HeapDataStore(coltypes, cols, nrows=len(cols[0][0]))
+            dptr, length = ds.upload(0)
+        else:
+            ds = gp.DataStore(coltypes, cols, nrows=len(cols[0][0]))
+            length = ds.length
+            dptr = lib.pgs_device_alloc(0, length)
+            assert dptr, lib.pgs_last_error()
+            _capi.check(lib.pgs_device_upload(0, dptr, ds.ptr, length))
+        dev_chunks.append((dptr, length, ds.nrows))
         ds.free()
     e2e_chunk_rows = min(args.e2e_chunk_rows or DEFAULT_E2E_CHUNK[workload], rows)
+    if heap:
+        e2e_chunk_rows = min(e2e_chunk_rows, chunk_rows)
     for cols in generate_columns(workload, rank, rows, e2e_chunk_rows):
-        host_chunks.append(gp.DataStore(coltypes, cols, nrows=len(cols[0][0])))
+        if heap:
+            host_chunks.append(gp.HeapDataStore(coltypes, cols, nrows=len(cols[0][0])))
+            host_chunks[-1].length = host_chunks[-1].device_layout()[2]
+        else:
+            host_chunks.append(gp.DataStore(coltypes, cols, nrows=len(cols[0][0])))
     total_bytes = sum(d.length for d in host_chunks)
     nullable = sum(1 for c in colchunks[0] if c[1] is not None)
     alg_bytes_per_row = desc["row_bytes"] + nullable / 8.0
@@ -275,7 +291,7 @@ def bench_ours(args):
 
     def step_resident():
         for dptr, length, n in dev_chunks:
-            sess.submit_device(dptr, length, n)
+            sess.submit_device_format(dptr, length, n, fmt)
         if world > 1:
             _capi.check(lib.pgs_preagg_merge_nccl(sess.handle, comm, rank, world, 0))
         return sess.finish_raw()[1].nitems
@@ -308,7 +324,7 @@ def bench_ours(args):
         part = bench_oracle.expected_partial_node(node, merged)
         del merged
         for dptr, length, n in dev_chunks:
-            sess.submit_device(dptr, length, n)
+            sess.submit_device_format(dptr, length, n, fmt)
         if world > 1:
             _capi.check(lib.pgs_preagg_merge_nccl(sess.handle, comm, rank, world, 0))
             parts = [None] * world if rank == 0 else None
@@ -357,7 +373,7 @@ def bench_ours(args):
         barrier()
         t0 = time.perf_counter()
         for dptr, length, n in dev_chunks:
-            sess.submit_device(dptr, length, n)
+            sess.submit_device_format(dptr, length, n, fmt)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         if world > 1:
@@ -408,7 +424,7 @@ def bench_ours(args):
         if os.path.exists(tpath):
             with open(tpath) as f:
                 t = json.load(f).get(workload)
-            if t and t.get("rows_per_launch") and k_rows:
+            if t and t.get("rows_per_launch") and k_rows and not heap:
                 # ncu dram__bytes_read+write of one profiled launch, scaled to
                 # the rows one timed launch processed
                 traffic = t["dram_bytes_per_launch"] * (k_rows / t["rows_per_launch"])
@@ -419,6 +435,9 @@ def bench_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64/f64", "data": "synthetic",
             "config": {"workload": workload, "sql": SQL[workload],
+                       "input_format": "KDS_FORMAT_ROW (heap pages, %.1f physical bytes per row)"
+                                       % (total_dev_bytes / float(rows)) if heap
+                                       else "KDS_FORMAT_COLUMN",
                        "rows_per_gpu": rows, "chunk_rows": chunk_rows,
                        "chunks_per_step": len(dev_chunks),
                        "e2e_chunk_rows": e2e_chunk_rows,
@@ -432,7 +451,10 @@ def bench_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "gpupreagg_main", "launch_ms": k_ms,
+                         "kernel": ("gpupreagg_main_heap" if heap else
+                                    "gpupreagg_main + gpupreagg_partagg" if pm1.get("part_nparts")
+                                    else "gpupreagg_main"),
+                         "launch_ms": k_ms,
                          "bytes_per_launch": k_rows * alg_bytes_per_row,
                          "launches_timed": n_k},
             "cpu_baseline": cpu,

@@ -96,6 +96,34 @@ int         pgstrom_kds_column_build(void *buffer, size_t buflen,
                                      const void *const *values,
                                      const uint8_t *const *isnull);
 /* datastore.c:501-529 pgstrom_create_data_store_tupslot() */
+/* datastore.c:382-435 pgstrom_create_data_store_row(): the host form of a
+ * KDS_FORMAT_ROW chunk = head + kern_blkitem[maxblocks] + kern_rowitem[nrooms];
+ * the pages stay where they are (bitem->page) */
+size_t      pgstrom_kds_row_length(int ncols, uint32_t maxblocks, uint32_t nrooms);
+int         pgstrom_kds_row_init(void *buffer, size_t buflen, int ncols,
+                                 const kern_colmeta *colmeta,
+                                 uint32_t maxblocks, uint32_t nrooms);
+/* datastore.c:556-710 pgstrom_data_store_insert_block(); visibility is the
+ * caller's (PostgreSQL's) job: visible_offsets[] = OffsetNumbers of the
+ * tuples the snapshot sees.  Returns rows added, -1 = store full. */
+int         pgstrom_kds_row_insert_block(kern_data_store *kds, const void *page,
+                                         const uint16_t *visible_offsets,
+                                         int nvisible);
+/* datastore.c:437-470, :799-823: KDS_FORMAT_ROW_FLAT */
+int         pgstrom_kds_flat_init(void *buffer, size_t buflen, int ncols,
+                                  const kern_colmeta *colmeta, uint32_t nrooms);
+int         pgstrom_kds_flat_insert_tuple(kern_data_store *kds, const void *htup,
+                                          uint32_t t_len);
+/* TupleDesc's attcacheoff / attnum for a colmeta[] built by hand */
+void        pgstrom_colmeta_set_cacheoff(int ncols, kern_colmeta *colmeta);
+/* synthetic heap pages for benchmarks and tests (heap_form_tuple +
+ * PageAddItem); see datastore.cpp */
+long        pgstrom_heap_form_pages(int ncols, const kern_colmeta *colmeta,
+                                    uint32_t nrows, const void *const *values,
+                                    const unsigned char *const *isnull,
+                                    const unsigned char *varlena_blob,
+                                    unsigned char *pages, size_t maxpages,
+                                    uint32_t *rows_per_page);
 size_t      pgstrom_kds_tupslot_length(int ncols, uint32_t nrooms);
 int         pgstrom_kds_tupslot_init(void *buffer, size_t buflen, int ncols,
                                      const kern_colmeta *colmeta,
@@ -177,6 +205,13 @@ int         pgs_preagg_submit_device(pgs_session *session,
                                      uint32_t nitems,
                                      const kern_row_map *krowmap,
                                      pgs_ticket *ticket);
+/* same for a device chunk of any input format (KDS_FORMAT_ROW, ROW_FLAT or
+ * COLUMN); the plain call above means KDS_FORMAT_COLUMN */
+int         pgs_preagg_submit_device_format(pgs_session *session,
+                                            const void *kds_in_device, size_t length,
+                                            uint32_t nitems, int format,
+                                            const kern_row_map *krowmap,
+                                            pgs_ticket *ticket);
 /* mqueue.c:331-410 pgstrom_dequeue_message / try_dequeue: returns the chunk
  * status (0, StromError_CpuReCheck, or a significant error).
  * timeout_ms < 0 waits for ever, 0 polls (returns -1 if still running). */

@@ -71,6 +71,17 @@ PROTOTYPES = {
     "pgstrom_kds_column_build": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int,
                                            C.POINTER(kern_colmeta), C.c_uint32,
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "pgstrom_kds_row_length": (C.c_size_t, [C.c_int, C.c_uint32, C.c_uint32]),
+    "pgstrom_kds_row_init": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int,
+                                       C.POINTER(kern_colmeta), C.c_uint32, C.c_uint32]),
+    "pgstrom_kds_row_insert_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "pgstrom_kds_flat_init": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int,
+                                        C.POINTER(kern_colmeta), C.c_uint32]),
+    "pgstrom_kds_flat_insert_tuple": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "pgstrom_colmeta_set_cacheoff": (None, [C.c_int, C.POINTER(kern_colmeta)]),
+    "pgstrom_heap_form_pages": (C.c_long, [C.c_int, C.POINTER(kern_colmeta), C.c_uint32,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "pgstrom_kds_tupslot_length": (C.c_size_t, [C.c_int, C.c_uint32]),
     "pgstrom_kds_tupslot_init": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int,
                                            C.POINTER(kern_colmeta), C.c_uint32]),
@@ -95,6 +106,8 @@ PROTOTYPES = {
     "pgs_preagg_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "pgs_preagg_submit_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
                                            C.c_void_p, C.POINTER(C.c_int64)]),
+    "pgs_preagg_submit_device_format": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
+                                                  C.c_int, C.c_void_p, C.POINTER(C.c_int64)]),
     "pgs_preagg_wait": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int32)]),
     "pgs_preagg_recheck_rows": (C.c_int64, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32), C.c_int64]),
     "pgs_preagg_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint32),

@@ -527,8 +527,7 @@ devtype_is_runnable(const DevType *dtype)
     if (!dtype)
         return false;
     if (dtype->type_flags & DEVTYPE_IS_VARLENA)
-        return getenv("PGSTROM_ENABLE_NUMERIC") != NULL &&
-            std::string(dtype->type_name) == "numeric";
+        return std::string(dtype->type_name) == "numeric";  /* kern_numeric.cuh */
     return true;
 }
 

@@ -578,7 +578,8 @@ struct pgs_session
     int             ordinal = 0;
     pgs_program    *program = NULL;
     cudaLibrary_t   library = NULL;
-    cudaKernel_t    k_main = NULL, k_rowmap = NULL, k_init = NULL, k_flush = NULL,
+    cudaKernel_t    k_main = NULL, k_rowmap = NULL, k_heap = NULL, k_partagg = NULL,
+                    k_init = NULL, k_flush = NULL,
                     k_export = NULL, k_import = NULL, k_import_blocks = NULL,
                     k_describe = NULL;
     pgs_kern_desc   desc;
@@ -593,6 +594,8 @@ struct pgs_session
     int             grid_main = 0;
     size_t          smem_main = 0;
     cl_uint         sh_nslots = 0;
+    int             grid_partagg = 0;
+    size_t          smem_partagg = 0;
     cl_uint         tile_rows = 2048;
     cl_uint         nstages = 4;
     int             num_sms = 0;
@@ -637,9 +640,61 @@ session_alloc_state(pgs_session *s)
     s->gs.gh_slots = NULL;
     s->gs.gh_nslots = 0;
     s->gs.gh_max_probe = 0;
+    s->gs.part_nparts = 0;
+    s->gs.part_cap = 0;
+    s->gs.part_slots = 0;
+    s->gs.part_pad = 0;
+    s->gs.part_cursor = NULL;
+    s->gs.part_nused = NULL;
+    s->gs.part_recs = NULL;
+    s->gs.part_images = NULL;
+    s->grid_partagg = 0;
+    s->smem_partagg = 0;
+    if (s->desc.num_keys > 0 && s->desc.part_rec_bytes > 0 && s->sh_nslots == 0 &&
+        s->config.num_groups >= 65536.0 && !getenv("PGSTROM_NO_PARTITION"))
+    {
+        /* very many groups: partitioned aggregation (gpupreagg_partagg).
+         * An image holds `slots` groups at most 75% full; partitions are
+         * sized for half of that on average, their record areas for the
+         * rows of one chunk plus a quarter. */
+        const char *es = getenv("PGSTROM_PART_SLOTS");
+        size_t slots = es ? (((size_t)atol(es) + 31) & ~(size_t)31) : 1024;
+        size_t image_bytes = slots * s->desc.sh_slot_bytes;
+        size_t smem_max = devices[s->config.device].prop.sharedMemPerBlockOptin;
+        while (slots > 64 && 128 + slots * s->desc.sh_slot_bytes > smem_max)
+            slots -= 32;
+        image_bytes = slots * s->desc.sh_slot_bytes;
+        size_t nparts = (size_t)(s->config.num_groups / (slots * 0.5)) + 1;
+        size_t max_rows = s->config.max_chunk_rows ? s->config.max_chunk_rows : (64u << 20);
+        size_t cap = ((size_t)((double)max_rows / nparts * 1.25) + 64 + 3) & ~(size_t)3;
+        size_t rec_bytes = nparts * cap * s->desc.part_rec_bytes;
+        size_t img_bytes = nparts * image_bytes;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (nparts < 0x7fffffffULL && cap < 0x7fffffffULL &&
+            rec_bytes + img_bytes + 8 * nparts < free_b / 2)
+        {
+            CUDA_CHECK(cudaMalloc((void **)&s->gs.part_cursor, 4 * nparts));
+            CUDA_CHECK(cudaMalloc((void **)&s->gs.part_nused, 4 * nparts));
+            CUDA_CHECK(cudaMalloc((void **)&s->gs.part_recs, rec_bytes));
+            CUDA_CHECK(cudaMalloc((void **)&s->gs.part_images, img_bytes));
+            s->gs.part_nparts = (cl_uint)nparts;
+            s->gs.part_cap = (cl_uint)cap;
+            s->gs.part_slots = (cl_uint)slots;
+            s->smem_partagg = 128 + image_bytes;
+            CUDA_CHECK(cudaFuncSetAttribute((const void *)s->k_partagg,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)s->smem_partagg));
+            int per_sm = 0;
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                           &per_sm, (const void *)s->k_partagg, 256, s->smem_partagg));
+            s->grid_partagg = (int)std::min<size_t>(nparts, (size_t)s->num_sms * std::max(1, per_sm));
+        }
+    }
     if (s->desc.num_keys > 0)
     {
-        double want = s->config.num_groups * 2.0;
+        /* with partitions the global table only takes what they refuse */
+        double want = s->config.num_groups * (s->gs.part_nparts ? 0.125 : 2.0);
         size_t nslots = 1024;
         size_t free_b = 0, total_b = 0;
         while ((double)nslots < want && nslots < (1ULL << 31))
@@ -664,12 +719,19 @@ launch_kernel(pgs_session *s, cudaKernel_t k, int grid, int block, size_t smem,
     return StromError_Success;
 }
 
+/* slots of the persistent GROUP BY state: global table + table images */
+static size_t
+state_nslots(const pgs_session *s)
+{
+    return (size_t)s->gs.gh_nslots + (size_t)s->gs.part_nparts * s->gs.part_slots;
+}
+
 static int
 session_init_state(pgs_session *s)
 {
     void *args[] = { &s->gs };
     int grid = std::max(1, std::min<int>(s->num_sms * 8,
-                                         (int)((s->gs.gh_nslots + 255) / 256)));
+                                         (int)((state_nslots(s) + 255) / 256)));
     return launch_kernel(s, s->k_init, grid, 256, 0, args);
 }
 
@@ -719,6 +781,8 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
                                    NULL, NULL, 0, NULL, NULL, 0));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_main, s->library, "gpupreagg_main"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_rowmap, s->library, "gpupreagg_main_rowmap"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_heap, s->library, "gpupreagg_main_heap"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_partagg, s->library, "gpupreagg_partagg"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_init, s->library, "gpupreagg_init_state"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_flush, s->library, "gpupreagg_flush"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_export, s->library, "gpupreagg_export"));
@@ -794,8 +858,10 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
              * groups -> 0.66 / 0.51 / 0.84 ms per 50M rows).  A CTA-local
              * table only pays when most groups fit. */
             double want = std::max(64.0, config->num_groups * 1.7);
-            size_t avail = (smem_max > head + 2 * per1k + 1024
-                            ? smem_max - head - 2 * per1k - 1024 : 0);
+            /* the ring keeps at least 2 stages of 2048 rows: with smaller
+             * tiles half the lanes of a 128-row step have nothing to do */
+            size_t avail = (smem_max > head + 4 * per1k + 1024
+                            ? smem_max - head - 4 * per1k - 1024 : 0);
             size_t maxslots = (avail / s->desc.sh_slot_bytes) & ~(size_t)31;
             size_t nslots = ((size_t)want + 31) & ~(size_t)31;
             const char *env = getenv("PGSTROM_SH_SLOTS");
@@ -840,6 +906,9 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)s->smem_main));
         OPEN_CHECK(cudaFuncSetAttribute((const void *)s->k_rowmap,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)s->smem_main));
+        OPEN_CHECK(cudaFuncSetAttribute((const void *)s->k_heap,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)s->smem_main));
         OPEN_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
@@ -967,7 +1036,7 @@ slot_retire(pgs_session *s, ChunkSlot &sl)
 
 static int
 submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_dev,
-              size_t length, uint32_t nitems, const kern_row_map *krowmap,
+              size_t length, uint32_t nitems, int format, const kern_row_map *krowmap,
               pgs_ticket *ticket)
 {
     if (!s || s->aborted)
@@ -1010,11 +1079,48 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
     {
         /* host chunk: H2D on the copy stream, so that it overlaps the kernel
          * of the previous chunk; the exec stream waits for it */
-        CUDA_CHECK(cudaMemcpyAsync(sl.d_kds, kds_host, length,
-                                   cudaMemcpyHostToDevice, s->s_copy));
+        if (format == KDS_FORMAT_ROW)
+        {
+            /* clserv_dmasend_data_store (datastore.c:908-968): head, block
+             * items and row items in one piece, then the heap pages - which
+             * live wherever bitem->page says (shared buffers) - behind the
+             * next BLCKSZ boundary; runs of adjacent pages go as one copy */
+            size_t head_len = (size_t)((const char *)KERN_DATA_STORE_ROWITEM(kds_host, kds_host->nitems) -
+                                       (const char *)kds_host);
+            size_t offset = (size_t)((const char *)KERN_DATA_STORE_ROWBLOCK(kds_host, 0) -
+                                     (const char *)kds_host);
+            const kern_blkitem *bitem = KERN_DATA_STORE_BLKITEM(kds_host, 0);
+
+            CUDA_CHECK(cudaMemcpyAsync(sl.d_kds, kds_host, head_len,
+                                       cudaMemcpyHostToDevice, s->s_copy));
+            s->num_dma_send++;
+            s->bytes_dma_send += head_len;
+            for (cl_uint i = 0, n = 0; i < kds_host->nblocks; i++)
+            {
+                if (i + 1 < kds_host->nblocks &&
+                    bitem[i].page + BLCKSZ == bitem[i + 1].page)
+                {
+                    n++;
+                    continue;
+                }
+                CUDA_CHECK(cudaMemcpyAsync((char *)sl.d_kds + offset,
+                                           (const void *)(uintptr_t)bitem[i - n].page,
+                                           (size_t)BLCKSZ * (n + 1),
+                                           cudaMemcpyHostToDevice, s->s_copy));
+                s->num_dma_send++;
+                s->bytes_dma_send += (size_t)BLCKSZ * (n + 1);
+                offset += (size_t)BLCKSZ * (n + 1);
+                n = 0;
+            }
+        }
+        else
+        {
+            CUDA_CHECK(cudaMemcpyAsync(sl.d_kds, kds_host, length,
+                                       cudaMemcpyHostToDevice, s->s_copy));
+            s->num_dma_send++;
+            s->bytes_dma_send += length;
+        }
         d_kds = sl.d_kds;
-        s->num_dma_send++;
-        s->bytes_dma_send += length;
         CUDA_CHECK(cudaMemcpyAsync(sl.d_kgpreagg, sl.h_kgpreagg, kg_bytes,
                                    cudaMemcpyHostToDevice, s->s_copy));
         CUDA_CHECK(cudaEventRecord(sl.ev_copied, s->s_copy));
@@ -1030,10 +1136,18 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
     s->bytes_dma_send += kg_bytes;
 
     bool use_rowmap = (krowmap && krowmap->nvalids >= 0);
+    bool use_heap = (format == KDS_FORMAT_ROW || format == KDS_FORMAT_ROW_FLAT);
     void *args[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck, &s->sh_nslots,
                      &s->tile_rows, &s->nstages };
     int grid = s->grid_main;
-    if (!use_rowmap)
+    if (use_heap)
+    {
+        /* one thread per tuple, grid-stride */
+        uint32_t nblk = (nitems + s->desc.block_threads - 1) / s->desc.block_threads;
+        if ((uint32_t)grid > nblk)
+            grid = (int)std::max<uint32_t>(1, nblk);
+    }
+    else if (!use_rowmap)
     {
         uint32_t ntiles = (nitems + s->tile_rows - 1) / s->tile_rows;
         if ((uint32_t)grid > ntiles)
@@ -1041,10 +1155,19 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
     }
     if (s->perfmon)
         CUDA_CHECK(cudaEventRecord(sl.ev_k0, s->s_exec));
-    rc = launch_kernel(s, use_rowmap ? s->k_rowmap : s->k_main, grid,
+    rc = launch_kernel(s, use_heap ? s->k_heap : (use_rowmap ? s->k_rowmap : s->k_main), grid,
                        (int)s->desc.block_threads, s->smem_main, args);
     if (rc != StromError_Success)
         return rc;
+    if (s->gs.part_nparts != 0)
+    {
+        /* second pass of the partitioned GROUP BY: every partition that
+         * received records is aggregated into its table image */
+        void *pargs[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck };
+        rc = launch_kernel(s, s->k_partagg, s->grid_partagg, 256, s->smem_partagg, pargs);
+        if (rc != StromError_Success)
+            return rc;
+    }
     if (s->perfmon)
     {
         CUDA_CHECK(cudaEventRecord(sl.ev_k1, s->s_exec));
@@ -1075,14 +1198,22 @@ pgs_preagg_submit(pgs_session *session, const kern_data_store *kds_in,
         set_error("pgs_preagg_submit: no chunk");
         return StromError_BadRequestMessage;
     }
-    if (kds_in->format != KDS_FORMAT_COLUMN)
+    size_t length = kds_in->length;
+    if (kds_in->format == KDS_FORMAT_ROW)
     {
-        set_error("pgs_preagg_submit: chunk format %d is not supported yet "
-                  "(only KDS_FORMAT_COLUMN)", (int)kds_in->format);
+        /* what clserv_dmasend_data_store sends (datastore.c:908-968): head,
+         * block and row items, then the pages from the next BLCKSZ boundary */
+        length = (size_t)((const char *)KERN_DATA_STORE_ROWBLOCK(kds_in, kds_in->nblocks) -
+                          (const char *)kds_in);
+    }
+    else if (kds_in->format != KDS_FORMAT_ROW_FLAT && kds_in->format != KDS_FORMAT_COLUMN)
+    {
+        set_error("pgs_preagg_submit: chunk format %d is not an input format "
+                  "(KDS_FORMAT_ROW, ROW_FLAT or COLUMN)", (int)kds_in->format);
         return StromError_BadRequestMessage;
     }
-    return submit_common(session, kds_in, NULL, kds_in->length, kds_in->nitems,
-                         krowmap, ticket);
+    return submit_common(session, kds_in, NULL, length, kds_in->nitems,
+                         kds_in->format, krowmap, ticket);
 }
 
 extern "C" int
@@ -1090,12 +1221,26 @@ pgs_preagg_submit_device(pgs_session *session, const void *kds_in_device,
                          size_t length, uint32_t nitems,
                          const kern_row_map *krowmap, pgs_ticket *ticket)
 {
+    return pgs_preagg_submit_device_format(session, kds_in_device, length, nitems,
+                                           KDS_FORMAT_COLUMN, krowmap, ticket);
+}
+
+extern "C" int
+pgs_preagg_submit_device_format(pgs_session *session, const void *kds_in_device,
+                                size_t length, uint32_t nitems, int format,
+                                const kern_row_map *krowmap, pgs_ticket *ticket)
+{
     if (!kds_in_device)
     {
         set_error("pgs_preagg_submit_device: no chunk");
         return StromError_BadRequestMessage;
     }
-    return submit_common(session, NULL, kds_in_device, length, nitems, krowmap, ticket);
+    if (format != KDS_FORMAT_ROW && format != KDS_FORMAT_ROW_FLAT && format != KDS_FORMAT_COLUMN)
+    {
+        set_error("pgs_preagg_submit_device: chunk format %d is not an input format", format);
+        return StromError_BadRequestMessage;
+    }
+    return submit_common(session, NULL, kds_in_device, length, nitems, format, krowmap, ticket);
 }
 
 extern "C" int
@@ -1225,7 +1370,7 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     {
         void *args[] = { &s->gs, &d_dst, &d_kg };
         int grid = (s->desc.num_keys == 0) ? 1 :
-            std::max(1, std::min<int>(s->num_sms * 8, (int)((s->gs.gh_nslots + 255) / 256)));
+            std::max(1, std::min<int>(s->num_sms * 8, (int)std::min<size_t>((state_nslots(s) + 255) / 256, 1u << 30)));
         rc = launch_kernel(s, s->k_flush, grid, 256, 0, args);
         if (rc != StromError_Success)
             e = cudaErrorUnknown;
@@ -1321,7 +1466,7 @@ pgs_preagg_state_export(pgs_session *s, void *device_buf, size_t buflen,
     CUDA_CHECK(cudaMemsetAsync(d_n, 0, sizeof(cl_uint), s->s_exec));
     void *args[] = { &s->gs, &recs, &d_n, &max_records };
     int grid = (s->desc.num_keys == 0) ? 1 :
-        std::max(1, std::min<int>(s->num_sms * 8, (int)((s->gs.gh_nslots + 255) / 256)));
+        std::max(1, std::min<int>(s->num_sms * 8, (int)std::min<size_t>((state_nslots(s) + 255) / 256, 1u << 30)));
     rc = launch_kernel(s, s->k_export, grid, 256, 0, args);
     if (rc != StromError_Success)
         return rc;
@@ -1488,7 +1633,7 @@ pgs_preagg_merge_nccl(pgs_session *s, void *nccl_comm, int rank, int nranks, int
      * Everything is stream ordered - no allocation, no host synchronisation;
      * the caller's pgs_preagg_finish() waits once for all of it.
      */
-    size_t cap = (s->desc.num_keys == 0 ? 1 : (size_t)s->gs.gh_nslots);
+    size_t cap = (s->desc.num_keys == 0 ? 1 : state_nslots(s));
     if (cap <= 65536 && (cap + 1) * recb * (size_t)(nranks + 1) <= ((size_t)256 << 20))
     {
         size_t block = (cap + 1) * recb;
@@ -1511,7 +1656,7 @@ pgs_preagg_merge_nccl(pgs_session *s, void *nccl_comm, int rank, int nranks, int
         {
             void *args[] = { &s->gs, &recs, &d_n, &max_records };
             int grid = (s->desc.num_keys == 0) ? 1 :
-                std::max(1, std::min<int>(s->num_sms * 8, (int)((s->gs.gh_nslots + 255) / 256)));
+                std::max(1, std::min<int>(s->num_sms * 8, (int)std::min<size_t>((state_nslots(s) + 255) / 256, 1u << 30)));
             rc = launch_kernel(s, s->k_export, grid, 256, 0, args);
             if (rc != StromError_Success)
                 return rc;
@@ -1632,6 +1777,9 @@ pgs_preagg_perfmon_json(pgs_session *s)
     o->set("smem_main", (long long)s->smem_main);
     o->set("sh_nslots", (long long)s->sh_nslots);
     o->set("gh_nslots", (long long)s->gs.gh_nslots);
+    o->set("part_nparts", (long long)s->gs.part_nparts);
+    o->set("part_cap", (long long)s->gs.part_cap);
+    o->set("part_slots", (long long)s->gs.part_slots);
     o->set("block_threads", (long long)s->desc.block_threads);
     o->set("tile_rows", (long long)s->tile_rows);
     o->set("num_stages", (long long)s->nstages);
@@ -1681,6 +1829,10 @@ pgs_preagg_close(pgs_session *s)
             if (sl.ev_k1) cudaEventDestroy(sl.ev_k1);
         }
         if (s->gs.gh_slots) cudaFree(s->gs.gh_slots);
+        if (s->gs.part_cursor) cudaFree(s->gs.part_cursor);
+        if (s->gs.part_nused) cudaFree(s->gs.part_nused);
+        if (s->gs.part_recs) cudaFree(s->gs.part_recs);
+        if (s->gs.part_images) cudaFree(s->gs.part_images);
         if (s->d_result) cudaFree(s->d_result);
         if (s->d_kg_misc) cudaFree(s->d_kg_misc);
         if (s->h_result_head) cudaFreeHost(s->h_result_head);

@@ -202,6 +202,265 @@ pgstrom_kds_column_build(void *buffer, size_t buflen, int ncols,
     return StromError_Success;
 }
 
+/* ------------------------------------------------------------------
+ * KDS_FORMAT_ROW / KDS_FORMAT_ROW_FLAT: the reference's own input formats.
+ *
+ * pgstrom_kds_row_*   : pgstrom_create_data_store_row (datastore.c:382-435)
+ *                       and pgstrom_data_store_insert_block (:556-710).  The
+ *                       visibility check belongs to PostgreSQL: the caller
+ *                       passes the line pointers it found visible.  Pages
+ *                       are referenced, not copied (bitem->page), exactly
+ *                       like shared buffers in the reference; the CUDA layer
+ *                       gathers them at DMA time.
+ * pgstrom_kds_flat_*  : pgstrom_create_data_store_row_flat (:437-470) and
+ *                       the ROW_FLAT branch of pgstrom_data_store_insert_tuple
+ *                       (:799-823): tuples are packed from the tail.
+ * ------------------------------------------------------------------ */
+size_t
+pgstrom_kds_row_length(int ncols, uint32_t maxblocks, uint32_t nrooms)
+{
+    return STROMALIGN(KERN_DATA_STORE_HEAD_LENGTH(ncols) +
+                      STROMALIGN(sizeof(kern_blkitem) * (size_t)maxblocks) +
+                      STROMALIGN(sizeof(kern_rowitem) * (size_t)nrooms));
+}
+
+int
+pgstrom_kds_row_init(void *buffer, size_t buflen, int ncols,
+                     const kern_colmeta *colmeta, uint32_t maxblocks, uint32_t nrooms)
+{
+    size_t need = pgstrom_kds_row_length(ncols, maxblocks, nrooms);
+    kern_data_store *kds = (kern_data_store *)buffer;
+
+    if (need > buflen || (size_t)BLCKSZ * maxblocks + need > 0xffffffffULL)
+    {
+        pgs::last_error = "row store does not fit the buffer";
+        return StromError_DataStoreNoSpace;
+    }
+    init_kern_data_store(kds, ncols, colmeta, need, nrooms, KDS_FORMAT_ROW);
+    kds->maxblocks = maxblocks;
+    return StromError_Success;
+}
+
+/* returns the number of rows added, or -1 if the block has to go to the
+ * next store (datastore.c:604-613) */
+int
+pgstrom_kds_row_insert_block(kern_data_store *kds, const void *page,
+                             const uint16_t *visible_offsets, int nvisible)
+{
+    const unsigned char *pg = (const unsigned char *)page;
+    uint16_t    pd_lower;
+    int         lines;
+
+    if (kds->format != KDS_FORMAT_ROW || kds->nblocks >= kds->maxblocks)
+        return -1;
+    memcpy(&pd_lower, pg + 12, 2);
+    lines = (pd_lower <= 24 ? 0 : (pd_lower - 24) / 4);
+    if (nvisible > lines)
+    {
+        pgs::last_error = "more visible tuples than line pointers";
+        return -1;
+    }
+    if ((size_t)kds->nitems + lines > kds->nrooms ||
+        KERN_DATA_STORE_HEAD_LENGTH(kds->ncols) +
+        STROMALIGN(sizeof(kern_blkitem) * (size_t)kds->maxblocks) +
+        STROMALIGN(sizeof(kern_rowitem) * ((size_t)kds->nitems + lines)) +
+        (size_t)BLCKSZ * kds->nblocks >= (size_t)BLCKSZ * kds->maxblocks)
+        return -1;
+    kern_rowitem *ritem = KERN_DATA_STORE_ROWITEM(kds, kds->nitems);
+    kern_blkitem *bitem = KERN_DATA_STORE_BLKITEM(kds, kds->nblocks);
+    for (int i = 0; i < nvisible; i++)
+    {
+        ritem->blk_index = (cl_ushort)kds->nblocks;
+        ritem->item_offset = visible_offsets[i];
+        ritem++;
+    }
+    kds->nitems += (cl_uint)nvisible;
+    bitem->buffer = (cl_int)(kds->nblocks + 1);
+    bitem->page = (hostptr_t)(uintptr_t)page;
+    kds->nblocks++;
+    return nvisible;
+}
+
+int
+pgstrom_kds_flat_init(void *buffer, size_t buflen, int ncols,
+                      const kern_colmeta *colmeta, uint32_t nrooms)
+{
+    if (buflen > 0xffffffffULL || buflen < pgstrom_kds_row_length(ncols, 0, nrooms))
+    {
+        pgs::last_error = "flat row store does not fit the buffer";
+        return StromError_DataStoreNoSpace;
+    }
+    init_kern_data_store((kern_data_store *)buffer, ncols, colmeta,
+                         buflen & ~(size_t)15, nrooms, KDS_FORMAT_ROW_FLAT);
+    return StromError_Success;
+}
+
+/* htup: HeapTupleHeaderData + data, t_len bytes.  Returns 1, or 0 when the
+ * store is full. */
+int
+pgstrom_kds_flat_insert_tuple(kern_data_store *kds, const void *htup, uint32_t t_len)
+{
+    if (kds->format != KDS_FORMAT_ROW_FLAT || kds->nitems >= kds->nrooms)
+        return 0;
+    kern_rowitem *ritem = KERN_DATA_STORE_ROWITEM(kds, kds->nitems);
+    size_t usage = (size_t)((char *)(ritem + 1) - (char *)kds) +
+                   kds->usage + LONGALIGN(t_len);
+    if (usage > kds->length)
+        return 0;
+    char *dest = (char *)kds + kds->length - kds->usage - LONGALIGN(t_len);
+    memcpy(dest, htup, t_len);
+    ritem->htup_offset = (cl_uint)(dest - (char *)kds);
+    kds->usage += (cl_uint)LONGALIGN(t_len);
+    kds->nitems++;
+    return 1;
+}
+
+/* attcacheoff of every column the way TupleDesc caches it: known until the
+ * first variable-length attribute (heap_deform_tuple's fast path) */
+void
+pgstrom_colmeta_set_cacheoff(int ncols, kern_colmeta *colmeta)
+{
+    long off = 0;
+    bool known = true;
+
+    for (int i = 0; i < ncols; i++)
+    {
+        colmeta[i].attnum = (cl_short)(i + 1);
+        if (known && colmeta[i].attlen > 0)
+        {
+            off = (long)TYPEALIGN(colmeta[i].attalign, off);
+            colmeta[i].attcacheoff = (cl_short)off;
+            off += colmeta[i].attlen;
+        }
+        else
+        {
+            /* the first varlena still has a known offset if it needs no padding */
+            colmeta[i].attcacheoff = -1;
+            known = false;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------
+ * Synthetic heap pages (benchmarks and tests; PostgreSQL itself is the real
+ * producer).  Forms tuples like heap_form_tuple and adds them like
+ * PageAddItem: 24-byte page header, line pointers growing up, MAXALIGNed
+ * tuples growing down; 23-byte tuple header + NULL bitmap, t_hoff MAXALIGNed;
+ * attributes aligned by attalign; varlena values whose payload is < 127
+ * bytes get the 1-byte header.
+ *   values[c]   : attlen > 0: nrows * attlen bytes; attlen < 0: nrows uint32
+ *                 offsets into varlena_blob of 4-byte-header datums
+ *   isnull[c]   : nrows bytes (1 = NULL) or NULL; values[c] == NULL means the
+ *                 column is NULL in every row
+ * Returns the number of pages written, -1 if maxpages is too small;
+ * rows_per_page[p] = tuples on page p (line pointers 1..n, all normal).
+ * ------------------------------------------------------------------ */
+long
+pgstrom_heap_form_pages(int ncols, const kern_colmeta *colmeta, uint32_t nrows,
+                        const void *const *values, const unsigned char *const *isnull,
+                        const unsigned char *varlena_blob,
+                        unsigned char *pages, size_t maxpages, uint32_t *rows_per_page)
+{
+    long        npages = 0;
+    unsigned char *page = NULL;
+    uint32_t    lower = 0, upper = 0, nlines = 0;
+    unsigned char tup[BLCKSZ];
+
+    for (uint32_t r = 0; r < nrows; r++)
+    {
+        bool hasnull = false;
+        for (int c = 0; c < ncols; c++)
+            if (!values[c] || (isnull && isnull[c] && isnull[c][r]))
+                hasnull = true;
+        uint32_t hoff = (uint32_t)MAXALIGN(23 + (hasnull ? (ncols + 7) / 8 : 0));
+        uint32_t off = hoff;
+        memset(tup, 0, hoff);
+        uint16_t infomask = (uint16_t)((hasnull ? 0x0001 : 0) | 0x0100 | 0x0800);
+        uint16_t infomask2 = (uint16_t)ncols;
+        for (int c = 0; c < ncols; c++)
+        {
+            bool isn = (!values[c] || (isnull && isnull[c] && isnull[c][r]));
+            if (isn)
+                continue;
+            if (hasnull)
+                tup[23 + (c >> 3)] |= (unsigned char)(1 << (c & 7));
+            int attlen = colmeta[c].attlen;
+            if (attlen > 0)
+            {
+                uint32_t a = (uint32_t)TYPEALIGN(colmeta[c].attalign, off);
+                if (a + attlen > sizeof(tup)) return -1;
+                memset(tup + off, 0, a - off);
+                memcpy(tup + a, (const char *)values[c] + (size_t)r * attlen, attlen);
+                off = a + attlen;
+            }
+            else
+            {
+                const unsigned char *d = varlena_blob + ((const uint32_t *)values[c])[r];
+                size_t vl = varsize_any(d);
+                infomask |= 0x0002;
+                if (!(d[0] & 0x01) && vl - 4 + 1 <= 127)
+                {
+                    /* VARATT_CAN_MAKE_SHORT: 1-byte header, no alignment */
+                    size_t sl = vl - 4 + 1;
+                    if (off + sl > sizeof(tup)) return -1;
+                    tup[off] = (unsigned char)((sl << 1) | 0x01);
+                    memcpy(tup + off + 1, d + 4, vl - 4);
+                    off += (uint32_t)sl;
+                }
+                else
+                {
+                    uint32_t a = (d[0] & 0x01) ? off : (uint32_t)TYPEALIGN(colmeta[c].attalign, off);
+                    if (a + vl > sizeof(tup)) return -1;
+                    memset(tup + off, 0, a - off);
+                    memcpy(tup + a, d, vl);
+                    off = a + (uint32_t)vl;
+                }
+            }
+        }
+        memcpy(tup + 18, &infomask2, 2);
+        memcpy(tup + 20, &infomask, 2);
+        tup[22] = (unsigned char)hoff;
+        uint32_t need = (uint32_t)MAXALIGN(off);
+        if (!page || lower + 4 + need > upper)
+        {
+            if (page)
+            {
+                uint16_t v = (uint16_t)lower; memcpy(page + 12, &v, 2);
+                v = (uint16_t)upper; memcpy(page + 14, &v, 2);
+                rows_per_page[npages - 1] = nlines;
+            }
+            if ((size_t)npages >= maxpages)
+                return -1;
+            page = pages + (size_t)BLCKSZ * npages++;
+            memset(page, 0, BLCKSZ);
+            uint16_t v = BLCKSZ; memcpy(page + 16, &v, 2);          /* pd_special */
+            v = (uint16_t)(BLCKSZ | 4); memcpy(page + 18, &v, 2);   /* size | version */
+            lower = 24; upper = BLCKSZ; nlines = 0;
+        }
+        upper -= need;
+        memcpy(page + upper, tup, off);
+        uint32_t lp = (upper & 0x7fff) | (1U << 15) | ((off & 0x7fff) << 17);   /* LP_NORMAL */
+        memcpy(page + lower, &lp, 4);
+        /* t_ctid = (block, line) */
+        {
+            uint16_t bi_hi = (uint16_t)((npages - 1) >> 16), bi_lo = (uint16_t)(npages - 1);
+            uint16_t posid = (uint16_t)(nlines + 1);
+            memcpy(page + upper + 12, &bi_hi, 2);
+            memcpy(page + upper + 14, &bi_lo, 2);
+            memcpy(page + upper + 16, &posid, 2);
+        }
+        lower += 4;
+        nlines++;
+    }
+    if (page)
+    {
+        uint16_t v = (uint16_t)lower; memcpy(page + 12, &v, 2);
+        v = (uint16_t)upper; memcpy(page + 14, &v, 2);
+        rows_per_page[npages - 1] = nlines;
+    }
+    return npages;
+}
+
 size_t
 pgstrom_kds_tupslot_length(int ncols, uint32_t nrooms)
 {

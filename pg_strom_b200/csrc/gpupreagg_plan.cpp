@@ -843,11 +843,6 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
                 *err = "Bug? unexpected partial aggregate function: " + func_name;
                 return false;
             }
-            if (pc.cell_type == "NUMERIC")
-            {
-                *err = "numeric partial aggregates are not supported on the device yet";
-                return false;
-            }
             /* NULL-ness class of this partial value */
             {
                 std::string klass = "agg:" + std::to_string(naggs);
@@ -883,7 +878,10 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
             out_list << " _(" << (resno - 1) << ",AGG," << naggs << "," << ncells << ","
                      << pc.op << "," << pc.cell_type << ")";
             naggs++;
-            ncells += (pc.cell_type == "LONG" ? 2 : 1);
+            /* int8 sums are 128-bit (2 cells); numeric sums 128-bit at a fixed
+             * scale + the display scale (3 cells, kern_numeric.cuh) */
+            ncells += (pc.cell_type == "LONG" ? 2 :
+                       (pc.cell_type == "NUMERIC" && pc.op == "PSUM") ? 3 : 1);
         }
         else
         {
@@ -978,6 +976,11 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
                     o << " _(" << kc.second.first << ",0x" << std::hex << kc.second.second << std::dec << "U)";
                 return o.str(); }() << "\n"
          << "#define GPUPREAGG_HAS_QUAL " << (outer_quals.empty() ? 0 : 1) << "\n"
+         /* partitioned aggregation is compiled in when the planner expects
+          * very many groups (gpupreagg_partagg; the CUDA layer switches it on
+          * with the same threshold) */
+         << "#define GPUPREAGG_PARTITIONED "
+         << ((nkeys > 0 && gp.num_groups >= 65536.0) ? 1 : 0) << "\n"
          << "#define GPUPREAGG_NUM_OUTCOLS " << pre_tlist.size() << "\n"
          << "#define GPUPREAGG_OUT_LIST(_)" << out_list.str() << "\n";
     role_fn << "__host__ __device__ constexpr int\nGPUPREAGG_FIELD_ROLE(unsigned int colidx)\n{\n  switch (colidx)\n  {\n";

@@ -63,6 +63,17 @@
 #define GPUPREAGG_HAS_QUAL          1
 #endif
 
+/* 1 when the planner expects very many groups: the scan kernels can deal
+ * rows into partitions (pgs_part_emit) and gpupreagg_partagg has a body */
+#ifndef GPUPREAGG_PARTITIONED
+#define GPUPREAGG_PARTITIONED       0
+#endif
+#if GPUPREAGG_PARTITIONED
+#define PGS_PART_NPARTS(gs)         ((gs).part_nparts)
+#else
+#define PGS_PART_NPARTS(gs)         0U
+#endif
+
 #ifndef GPUPREAGG_DEBUG_LEVEL
 #define GPUPREAGG_DEBUG_LEVEL       0
 #endif
@@ -183,6 +194,16 @@ STROMCL_SIMPLE_VARSTORE_TEMPLATE(date, cl_int)
 STROMCL_SIMPLE_VARSTORE_TEMPLATE(time, cl_long)
 STROMCL_SIMPLE_VARSTORE_TEMPLATE(timestamp, cl_long)
 
+#ifdef KERN_NUMERIC_CUH
+template <typename KDS>
+DEVFN void
+pg_numeric_vstore(pagg_row &kds_src, const KDS &kds_in, cl_int *errcode,
+                  cl_uint colidx, cl_uint rowidx_out, pg_numeric_t datum)
+{
+    kds_src.store(colidx, datum.isnull, datum.value);
+}
+#endif
+
 /* NULL-const output columns need no work on the device */
 template <typename KDS>
 DEVFN void
@@ -257,6 +278,13 @@ pgs_f8_from_sortkey(cl_ulong k)
 #define PGS_CELL_INIT_PMAX_LONG(c,p)    (p)[c] = (cl_ulong)LONG_MIN;
 #define PGS_CELL_INIT_PMAX_FLOAT(c,p)   (p)[c] = PGS_F8_MAX_IDENTITY;
 #define PGS_CELL_INIT_PMAX_DOUBLE(c,p)  (p)[c] = PGS_F8_MAX_IDENTITY;
+
+/* NUMERIC (kern_numeric.cuh): a sum takes three cells - a 128-bit integer at
+ * scale PGS_NUMERIC_SUM_SCALE (lo, hi) and the largest display scale seen -;
+ * min / max keep the 64-bit device numeric, all ones = nothing seen */
+#define PGS_CELL_INIT_PSUM_NUMERIC(c,p) (p)[c] = 0; (p)[(c)+1] = 0; (p)[(c)+2] = 0;
+#define PGS_CELL_INIT_PMIN_NUMERIC(c,p) (p)[c] = 0xFFFFFFFFFFFFFFFFULL;
+#define PGS_CELL_INIT_PMAX_NUMERIC(c,p) (p)[c] = 0xFFFFFFFFFFFFFFFFULL;
 
 /* ---- value of one projected datum in "cell domain" ---- */
 #define PGS_NEWVAL_PSUM_INT(d)      ((cl_ulong)(cl_long)(d).int_val)
@@ -402,6 +430,20 @@ struct pgs_i128 { cl_ulong lo, hi; };
 #define PGS_TACC_TYPE_PMAX_LONG     cl_long
 #define PGS_TACC_TYPE_PMAX_FLOAT    double
 #define PGS_TACC_TYPE_PMAX_DOUBLE   double
+
+/* numeric aggregates never take the batch fast path (PGS_SPECIAL_NUMERIC) */
+#define PGS_TACC_TYPE_PSUM_NUMERIC  cl_ulong
+#define PGS_TACC_TYPE_PMIN_NUMERIC  cl_ulong
+#define PGS_TACC_TYPE_PMAX_NUMERIC  cl_ulong
+#define PGS_TACC_INIT_PSUM_NUMERIC(a)   (a) = 0;
+#define PGS_TACC_INIT_PMIN_NUMERIC(a)   (a) = 0;
+#define PGS_TACC_INIT_PMAX_NUMERIC(a)   (a) = 0;
+#define PGS_TACC_CALC4_PSUM_NUMERIC(a,d0,d1,d2,d3,k0,k1,k2,k3)
+#define PGS_TACC_CALC4_PMIN_NUMERIC(a,d0,d1,d2,d3,k0,k1,k2,k3)
+#define PGS_TACC_CALC4_PMAX_NUMERIC(a,d0,d1,d2,d3,k0,k1,k2,k3)
+#define PGS_TACC_CELL_PSUM_NUMERIC(a,src,c) (src)[c] = 0; (src)[(c)+1] = 0; (src)[(c)+2] = 0;
+#define PGS_TACC_CELL_PMIN_NUMERIC(a,src,c) (src)[c] = 0xFFFFFFFFFFFFFFFFULL;
+#define PGS_TACC_CELL_PMAX_NUMERIC(a,src,c) (src)[c] = 0xFFFFFFFFFFFFFFFFULL;
 
 #define PGS_F8_NAN      __longlong_as_double(0x7FF8000000000000LL)
 #define PGS_F8_NEGINF   __longlong_as_double((cl_long)0xFFF0000000000000ULL)
@@ -608,6 +650,87 @@ pgs_add128_SHARED(cl_ulong *plo, cl_ulong *phi, cl_ulong vlo, cl_ulong vhi, bool
 {
     pgs_add128_ATOMIC(plo, phi, vlo, vhi, ok);
 }
+
+#ifdef KERN_NUMERIC_CUH
+/* numeric sum: the addend at the fixed scale, as two 64-bit halves */
+#define PGS_NUMSUM_TEMPLATE(MODE)                                       \
+    template <typename CELLS>                                           \
+    DEVFN void                                                          \
+    pgs_numsum_##MODE(CELLS p, int c, cl_ulong packed, bool ok)         \
+    {                                                                   \
+        int         ds = (ok ? pgs_numeric_dscale(packed) : 0);         \
+        pgs_s128    add = (ok ? pgs_numeric_scaled(packed, PGS_NUMERIC_SUM_SCALE) : 0); \
+        pgs_add128_##MODE(&p[c], &p[c + 1], (cl_ulong)add,              \
+                          (cl_ulong)((pgs_u128)add >> 64), ok);         \
+        PGS_MERGE_##MODE##_MAX_I64(p, c + 2, (cl_ulong)(cl_long)ds, ok) \
+    }                                                                   \
+    template <typename CELLS, typename SRC>                             \
+    DEVFN void                                                          \
+    pgs_numsum_merge_##MODE(CELLS p, int c, SRC q, bool ok)             \
+    {                                                                   \
+        pgs_add128_##MODE(&p[c], &p[c + 1], q[c], q[c + 1], ok);        \
+        PGS_MERGE_##MODE##_MAX_I64(p, c + 2, q[c + 2], ok)              \
+    }
+PGS_NUMSUM_TEMPLATE(PLAIN)
+PGS_NUMSUM_TEMPLATE(THREAD)
+PGS_NUMSUM_TEMPLATE(ATOMIC)
+PGS_NUMSUM_TEMPLATE(SHARED)
+
+/* numeric min / max; WANT = -1 keeps the smaller, +1 the larger */
+DEVFN void
+pgs_numext_PLAIN(cl_ulong *p, cl_ulong v, bool ok, int want)
+{
+    if (ok && v != PGS_NUMERIC_EMPTY &&
+        (*p == PGS_NUMERIC_EMPTY || pgs_numeric_cmp(v, *p) == want))
+        *p = v;
+}
+DEVFN void
+pgs_numext_THREAD(cl_ulong *p, cl_ulong v, bool ok, int want)
+{
+    pgs_numext_PLAIN(p, v, ok, want);
+}
+DEVFN void
+pgs_numext_ATOMIC(cl_ulong *p, cl_ulong v, bool ok, int want)
+{
+    if (ok && v != PGS_NUMERIC_EMPTY)
+    {
+        cl_ulong    old = *((volatile cl_ulong *)p);
+
+        while (old == PGS_NUMERIC_EMPTY || pgs_numeric_cmp(v, old) == want)
+        {
+            cl_ulong seen = atomicCAS((unsigned long long *)p, (unsigned long long)old,
+                                      (unsigned long long)v);
+            if (seen == old)
+                break;
+            old = seen;
+        }
+    }
+}
+DEVFN void
+pgs_numext_SHARED(cl_ulong *p, cl_ulong v, bool ok, int want)
+{
+    pgs_numext_ATOMIC(p, v, ok, want);
+}
+#endif  /* KERN_NUMERIC_CUH */
+#define PGS_AGGCALC_PSUM_NUMERIC(MODE,p,c,d,ok) pgs_numsum_##MODE(p, c, (d).ulong_val, (ok));
+#define PGS_AGGCALC_PMIN_NUMERIC(MODE,p,c,d,ok) pgs_numext_##MODE(&(p)[c], (d).ulong_val, (ok), -1);
+#define PGS_AGGCALC_PMAX_NUMERIC(MODE,p,c,d,ok) pgs_numext_##MODE(&(p)[c], (d).ulong_val, (ok), 1);
+#define PGS_AGGMERGE_PSUM_NUMERIC(MODE,p,c,q,ok) pgs_numsum_merge_##MODE(p, c, q, (ok));
+#define PGS_AGGMERGE_PMIN_NUMERIC(MODE,p,c,q,ok) pgs_numext_##MODE(&(p)[c], (q)[c], (ok), -1);
+#define PGS_AGGMERGE_PMAX_NUMERIC(MODE,p,c,q,ok) pgs_numext_##MODE(&(p)[c], (q)[c], (ok), 1);
+/* a sum takes values up to the fixed scale whose scaled mantissa stays below
+ * 2^96: 2^31 of them cannot overflow the 128-bit cell */
+#define PGS_AGGCHECK_PSUM_NUMERIC(d)                                    \
+    {                                                                   \
+        int __ds = pgs_numeric_dscale((d).ulong_val);                   \
+        if (__ds < 0 || __ds > PGS_NUMERIC_SUM_SCALE ||                 \
+            (((pgs_u128)PG_NUMERIC_MANTISSA((d).ulong_val) *            \
+              pgs_pow10_u128(PGS_NUMERIC_SUM_SCALE - (__ds < 0 ? 0 : (__ds > PGS_NUMERIC_SUM_SCALE ? PGS_NUMERIC_SUM_SCALE : __ds)))) >> 96) != 0) \
+            STROM_SET_ERROR(errcode, StromError_CpuReCheck);            \
+    }
+#define PGS_AGGCHECK_PMIN_NUMERIC(d)
+#define PGS_AGGCHECK_PMAX_NUMERIC(d)
+#define PGS_SPECIAL_NUMERIC(d)      md = 0xffffffffU;
 
 /* row -> state (MODE = PLAIN | THREAD | FAST | ATOMIC | SHARED); `d` is a
  * pagg_datum */
@@ -910,12 +1033,12 @@ pgs_stage_nul_off(int slot, cl_uint tile_rows)
  *             staged tile, or PGS_ROWQ_LEFT | n for row n of the leftover buffer
  *   leftover: [col0 values | col1 values | ... | validity mask (u32) | row
  *             number (u32)], PGS_ROWQ_LEFT_ENTRIES entries per array.  Queue
- *             position p always maps to leftover entry p mod 32, so an entry
- *             that survives several tiles never moves.
+ *             position p always maps to entry p mod 64, so an entry that
+ *             survives several tiles never moves.
  */
 #define PGS_ROWQ_ENTRIES        256         /* power of two, > 31 + 128 */
 #define PGS_ROWQ_LEFT           0x8000U
-#define PGS_ROWQ_LEFT_ENTRIES   32
+#define PGS_ROWQ_LEFT_ENTRIES   64
 DEVFN cl_uint
 pgs_rowq_val_off(int slot)
 {
@@ -1121,6 +1244,11 @@ struct pgs_sh_table
 {
     cl_uint     base;       /* offset in __pgs_smem */
     cl_uint     nslots;     /* multiple of 32, 0 = disabled */
+    cl_uint     salt;       /* odd multiplier of the hash before the bucket is
+                             * taken from its high bits; 1 = as is.  A table
+                             * image of a partition sees only keys whose hash
+                             * shares the high bits (that is what made them
+                             * land in the partition), so it mixes first. */
 
     __device__ __forceinline__ cl_uint *ctrl_lo(cl_uint s) const
     { return (cl_uint *)(__pgs_smem + base) + s; }
@@ -1265,7 +1393,7 @@ pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
     const cl_uint limit = sh.nslots - (sh.nslots >> 2);     /* 75% */
     const cl_uint want = ((cl_uint)hash << PGS_TAG_SHIFT) | (knull << 2) | PGS_SLOT_READY;
     const cl_uint busy = want ^ (PGS_SLOT_READY ^ PGS_SLOT_BUSY);
-    cl_uint     b = __umulhi((cl_uint)(hash >> 32), nbuckets);     /* high bits */
+    cl_uint     b = __umulhi((cl_uint)(hash >> 32) * sh.salt, nbuckets);   /* high bits */
     cl_uint     probe = 0;
     cl_uint     found = ~0U;
     bool        done = false;
@@ -1325,6 +1453,97 @@ pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
         }
     }
     return found;
+}
+
+/* ------------------------------------------------------------------
+ * Partition records (GROUP BY with very many groups, see gpupreagg_partagg):
+ * the referenced columns of one row in slot order, each on its natural
+ * alignment, then the validity mask (bit per slot) and the row number.
+ * ------------------------------------------------------------------ */
+DEVFN cl_uint
+pgs_rec_val_off(int slot)
+{
+    cl_uint off = 0;
+#pragma unroll
+    for (int s = 0; s <= slot && s < GPUPREAGG_NUM_INCOLS; s++)
+    {
+        cl_uint a = GPUPREAGG_INCOL_ATTLEN(s);
+        off = (off + a - 1U) & ~(a - 1U);
+        if (s < slot)
+            off += a;
+    }
+    return off;
+}
+DEVFN cl_uint
+pgs_rec_end_off(void)
+{
+    cl_uint off = 0;
+#pragma unroll
+    for (int s = 0; s < GPUPREAGG_NUM_INCOLS; s++)
+    {
+        cl_uint a = GPUPREAGG_INCOL_ATTLEN(s);
+        off = ((off + a - 1U) & ~(a - 1U)) + a;
+    }
+    return (off + 3U) & ~3U;
+}
+#define PGS_REC_MASK_OFF    pgs_rec_end_off()
+#define PGS_REC_ROW_OFF     (PGS_REC_MASK_OFF + 4)
+#define PGS_REC_BYTES       ((PGS_REC_ROW_OFF + 4 + 7U) & ~7U)
+
+struct kern_rec_gmem
+{
+    const unsigned char *rec;
+
+    template <typename T>
+    __device__ __forceinline__ bool
+    fetch(int slot, cl_uint rowidx, T &out) const
+    {
+        out = *((const T *)(rec + pgs_rec_val_off(slot)));
+        return ((*((const cl_uint *)(rec + PGS_REC_MASK_OFF)) >> slot) & 1U) != 0;
+    }
+};
+#define PGS_X_INCOL_RECPUT(slot,colidx,attlen)                          \
+    {                                                                   \
+        pgs_rowq_type<attlen>::T __v;                                   \
+        bool __ok = kds.template fetch<pgs_rowq_type<attlen>::T>(slot, rowidx, __v); \
+        *((pgs_rowq_type<attlen>::T *)(__rec + pgs_rec_val_off(slot))) = __v; \
+        __mask |= (__ok ? (1U << (slot)) : 0U);                         \
+    }
+
+/* deal one row into its partition: reserve a record (one atomic on the
+ * partition's cursor), then write it.  A position at or beyond part_cap means
+ * the partition takes no more records this chunk (the caller sends the row
+ * to the global table). */
+DEVFN cl_uint
+pgs_part_reserve(const pgs_gstate &gs, cl_ulong hash, cl_uint &part)
+{
+    part = __umulhi((cl_uint)(hash >> 32), gs.part_nparts);
+    return atomicAdd(gs.part_cursor + part, 1U);
+}
+template <typename KDS>
+DEVFN void
+pgs_part_write(const pgs_gstate &gs, const KDS &kds, cl_uint rowidx,
+               cl_uint rownum, cl_uint part, cl_uint pos)
+{
+    unsigned char  *__rec = gs.part_recs + ((cl_ulong)part * gs.part_cap + pos) * PGS_REC_BYTES;
+    cl_uint         __mask = 0;
+
+    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_RECPUT)
+    *((cl_uint *)(__rec + PGS_REC_MASK_OFF)) = __mask;
+    *((cl_uint *)(__rec + PGS_REC_ROW_OFF)) = rownum;
+}
+template <typename KDS>
+DEVFN bool
+pgs_part_emit(const pgs_gstate &gs, const KDS &kds, cl_uint rowidx,
+              cl_uint rownum, cl_ulong hash)
+{
+    cl_uint     part;
+    cl_uint     pos = pgs_part_reserve(gs, hash, part);
+
+    if (pos >= gs.part_cap)
+        return false;
+    pgs_part_write(gs, kds, rowidx, rownum, part, pos);
+    return true;
 }
 
 /* ------------------------------------------------------------------
@@ -1556,6 +1775,10 @@ pgs_group_add_row(const pgs_gstate &gs, const pgs_sh_table &sh,
     {
         if (s != ~0U)
         {
+            /* (a per-slot lock with plain loads and stores under it was
+             * tried instead of these atomics: lanes of a warp that meet in
+             * one group then take turns through the whole update, measured
+             * 13% slower) */
             pgs_sh_cells cells;
             cl_uint      nn;
 
@@ -1704,9 +1927,13 @@ pgs_main_epilogue(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
     else if (sh.nslots > 0)
     {
         /* spill the CTA-local table into the global one */
+        /* every CTA starts somewhere else in its table: the tables hold the
+         * same groups, and CTAs that finish together would otherwise queue
+         * up on the same global slots in the same order */
         __syncthreads();
-        for (cl_uint s = threadIdx.x; s < sh.nslots; s += blockDim.x)
+        for (cl_uint s0 = threadIdx.x; s0 < sh.nslots; s0 += blockDim.x)
         {
+            cl_uint     s = (s0 + blockIdx.x * 37U) % sh.nslots;
             cl_uint     st = *sh.ctrl_lo(s);
             cl_ulong    keyvals[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
             cl_ulong    src[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
@@ -1780,6 +2007,7 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
     ctx.errcode = StromError_Success;
     sh.base = PGS_SMEM_HEAD_BYTES + nstages * PGS_STAGE_BYTES(tile_rows);
     sh.nslots = (GPUPREAGG_NUM_KEYS > 0 ? sh_nslots : 0);
+    sh.salt = 1;
     pgs_cells_init(acc);
 
     if (threadIdx.x == 0)
@@ -1933,7 +2161,7 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
              * L2 for the home slot of every row it owns in this tile
              * (prefetch.global.L2, nothing waits for it) and only then works
              * through the rows. */
-            if (sh.nslots == 0)
+            if (sh.nslots == 0 && PGS_PART_NPARTS(gs) == 0)
             {
                 for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
                      rb += GPUPREAGG_CONSUMER_THREADS * 4)
@@ -1976,9 +2204,63 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
 
                 rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
                 GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+#if GPUPREAGG_PARTITIONED
+                if (gs.part_nparts != 0)
+                {
+                    /* very many groups: deal the 4 rows into their partitions.
+                     * The four cursor atomics are issued together (each is an
+                     * L2 round trip whose result the record store needs); the
+                     * global table only takes what a full partition refuses */
+                    bool        valid4[4];
+                    cl_ulong    hash4[4];
+                    cl_uint     part4[4], pos4[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    PGS_CONSUME_ROW_GROUPED(j)
+                    for (int j = 0; j < 4; j++)
+                    {
+                        pagg_row    prow;
+                        cl_uint     knull;
+
+                        valid4[j] = false;
+                        if (r + j < rows)
+                            valid4[j] = pgs_eval_row(kparams, rr[j], kds_in, row0 + r + j,
+                                                     recheck_map, ctx, prow);
+                        hash4[j] = (valid4[j] ? pgs_hash_keys(prow, knull) : 0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        part4[j] = 0;
+                        pos4[j] = (valid4[j] ? pgs_part_reserve(gs, hash4[j], part4[j]) : 0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        bool    refused = (valid4[j] && pos4[j] >= gs.part_cap);
+
+                        if (valid4[j] && !refused)
+                            pgs_part_write(gs, rr[j], row0 + r + j, row0 + r + j,
+                                           part4[j], pos4[j]);
+                        if (__any_sync(0xffffffffU, refused))
+                        {
+                            pagg_row    prow;
+
+                            if (refused)
+                            {
+                                cl_int  e = StromError_Success;     /* evaluated above */
+                                gpupreagg_projection(&e, kparams, rr[j], prow, kds_in,
+                                                     row0 + r + j, 0);
+                            }
+                            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, refused);
+                        }
+                    }
+                }
+                else
+#endif
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        PGS_CONSUME_ROW_GROUPED(j)
+                }
             }
 #else
             /* GROUP BY under a WHERE clause.  Only a fraction of the rows
@@ -1986,69 +2268,106 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
              * with a few lanes of each warp.  So a warp evaluates the qual
              * of 128 rows (4 per lane, from registers), and the survivors'
              * positions in the tile go - compacted with ballots - into its
-             * queue: one 16-bit store per surviving row.  Whenever 32 rows
-             * are queued every lane takes one through projection (read from
-             * the stage by position) + find-or-insert + the cell updates;
-             * that chain exists once in the program, here.  The < 32 rows
-             * that are still queued when the tile is done are copied by
-             * value into the warp's leftover buffer, so the stage goes back
-             * to the producer and the rows join the next tile's first chain.
-             * Every warp makes the same number of steps per tile (bounds
-             * are checked per row), so the very last step of the scan is
-             * where each warp drains what it has left. */
+             * queue: one 16-bit store per surviving row.  When the warp is
+             * done with the tile it copies the (< 64) queued rows by value
+             * into its row buffer - one row per lane - and hands the stage
+             * back to the producer; only then, whenever 32 rows are queued,
+             * every lane takes one through projection + find-or-insert +
+             * the cell updates.  That chain of dependent shared-memory
+             * operations is the slow part; run behind the release it
+             * overlaps the other warps and the TMA refill instead of holding
+             * up the CTA's ring (measured: 33% of the warp cycles were spent
+             * waiting for tiles when the chain ran before the release).
+             * The chain exists once in the program: the loop below is a
+             * small state machine around it.  Every warp makes the same
+             * number of steps per tile (bounds are checked per row), and the
+             * last tile of the CTA is where each warp drains what is left. */
             {
                 const cl_uint   step_rows = GPUPREAGG_CONSUMER_THREADS * 4;
                 const cl_uint   rows_up = ((rows + step_rows - 1) / step_rows) * step_rows;
                 const bool      last_tile = (t + gridDim.x >= ntiles);
+                cl_uint         rb = (ctid & ~31U) * 4;
+                bool            scanning = true;
 
-                for (cl_uint rb = (ctid & ~31U) * 4; rb < rows_up; rb += step_rows)
+                for (;;)
                 {
-                    const cl_uint r = rb + lane_id * 4;
-                    const cl_uint nv = (r < rows ? min(rows - r, 4U) : 0U);
-                    kern_row_regs rr[4];
-                    bool        valid4[4];
-                    cl_uint     votes4[4];
-
-                    rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
-                    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
-                    /* the 4 rows are independent: all four quals, then the
-                     * four ballots, so that their latencies overlap */
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
+                    if (scanning && rb < rows_up)
                     {
-                        cl_int      e = StromError_Success;
+                        const cl_uint r = rb + lane_id * 4;
+                        const cl_uint nv = (r < rows ? min(rows - r, 4U) : 0U);
+                        kern_row_regs rr[4];
+                        bool        valid4[4];
+                        cl_uint     votes4[4];
 
-                        valid4[j] = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
-                                                        row0 + r + j) & ((cl_uint)j < nv);
-                        if (e != StromError_Success)
+                        rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+                        /* the 4 rows are independent: all four quals, then
+                         * the four ballots, so that their latencies overlap */
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
                         {
-                            if ((cl_uint)j < nv)
+                            cl_int      e = StromError_Success;
+
+                            valid4[j] = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
+                                                            row0 + r + j) & ((cl_uint)j < nv);
+                            if (e != StromError_Success)
                             {
-                                pgs_note_error(e, row0 + r + j, recheck_map, ctx);
-                                ctx.nfiltered--;    /* neither passed nor filtered */
+                                if ((cl_uint)j < nv)
+                                {
+                                    pgs_note_error(e, row0 + r + j, recheck_map, ctx);
+                                    ctx.nfiltered--;    /* neither passed nor filtered */
+                                }
+                                valid4[j] = false;
                             }
-                            valid4[j] = false;
                         }
-                    }
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        votes4[j] = __ballot_sync(0xffffffffU, valid4[j]);
+                        for (int j = 0; j < 4; j++)
+                            votes4[j] = __ballot_sync(0xffffffffU, valid4[j]);
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                    {
-                        if (valid4[j])
-                            rowq[(qtail + __popc(votes4[j] & lanes_lt)) & (PGS_ROWQ_ENTRIES - 1)] =
-                                (cl_ushort)(r + j);
-                        qtail += __popc(votes4[j]);
-                    }
-                    nscanned += min(rows - min(rb, rows), 128U);
-                    __syncwarp();
-                    {
-                        const bool drain = last_tile && (rb + step_rows >= rows_up);
-
-                        while (qtail - qhead >= 32 || (drain && qtail != qhead))
+                        for (int j = 0; j < 4; j++)
                         {
-                            const cl_uint   n = min(qtail - qhead, 32U);
+                            if (valid4[j])
+                                rowq[(qtail + __popc(votes4[j] & lanes_lt)) & (PGS_ROWQ_ENTRIES - 1)] =
+                                    (cl_ushort)(r + j);
+                            qtail += __popc(votes4[j]);
+                        }
+                        nscanned += min(rows - min(rb, rows), 128U);
+                        rb += step_rows;
+                        __syncwarp();
+                    }
+                    else if (scanning && qtail - qhead < PGS_ROWQ_LEFT_ENTRIES)
+                    {
+                        /* done with the tile: keep what is queued by value,
+                         * queue position p in buffer entry p mod 64 */
+                        for (cl_uint k = lane_id; k < qtail - qhead; k += 32)
+                        {
+                            const cl_uint   __qp = (qhead + k) & (PGS_ROWQ_ENTRIES - 1);
+                            const cl_uint   __ri = rowq[__qp];
+
+                            if ((__ri & PGS_ROWQ_LEFT) == 0)
+                            {
+                                const cl_uint   __pos = __qp & (PGS_ROWQ_LEFT_ENTRIES - 1);
+                                cl_uint         __mask = 0;
+
+                                GPUPREAGG_INCOL_LIST(PGS_X_INCOL_QKEEP)
+                                *((cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_MASK_OFF) + __pos) = __mask;
+                                *((cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_ROW_OFF) + __pos) = row0 + __ri;
+                                rowq[__qp] = (cl_ushort)(PGS_ROWQ_LEFT | __pos);
+                            }
+                        }
+                        __syncwarp();
+                        if (lane_id == 0)
+                            pgs_mbar_arrive(&head->empty_bar[stage]);
+                        scanning = false;
+                        PGS_DBG_STOP(1)
+                    }
+                    {
+                        const cl_uint   qn = qtail - qhead;
+
+                        if (scanning ? (qn >= PGS_ROWQ_LEFT_ENTRIES)
+                                     : (qn >= 32 || (last_tile && qn != 0)))
+                        {
+                            const cl_uint   n = min(qn, 32U);
                             const cl_uint   __e = rowq[(qhead + lane_id) & (PGS_ROWQ_ENTRIES - 1)];
                             bool            active = (lane_id < n);
                             kern_qrow_smem  qrow;
@@ -2075,30 +2394,29 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                                     active = false;
                                 }
                             }
-                            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, active);
+                            if (PGS_PART_NPARTS(gs) != 0)
+                            {
+                                if (active)
+                                {
+                                    cl_uint     knull;
+                                    cl_ulong    hash = pgs_hash_keys(prow, knull);
+                                    cl_uint     rownum = (qrow.isleft
+                                        ? *((const cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_ROW_OFF) + qrow.idx)
+                                        : row0 + qrow.idx);
+                                    active = !pgs_part_emit(gs, qrow, 0, rownum, hash);
+                                }
+                            }
+                            if (PGS_PART_NPARTS(gs) == 0 || __any_sync(0xffffffffU, active))
+                                pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, active);
                             qhead += n;
                             npassed += n;
                         }
-                    }
-                }
-                /* keep what is still queued from this tile */
-                if (lane_id < qtail - qhead)
-                {
-                    const cl_uint   __qp = (qhead + lane_id) & (PGS_ROWQ_ENTRIES - 1);
-                    const cl_uint   __ri = rowq[__qp];
-
-                    if ((__ri & PGS_ROWQ_LEFT) == 0)
-                    {
-                        const cl_uint   __pos = __qp & (PGS_ROWQ_LEFT_ENTRIES - 1);
-                        cl_uint         __mask = 0;
-
-                        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_QKEEP)
-                        *((cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_MASK_OFF) + __pos) = __mask;
-                        *((cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_ROW_OFF) + __pos) = row0 + __ri;
-                        rowq[__qp] = (cl_ushort)(PGS_ROWQ_LEFT | __pos);
+                        else if (!scanning)
+                            break;
                     }
                 }
             }
+            continue;       /* the stage was handed back above */
             PGS_DBG_STOP(1)
 #endif
             __syncwarp();
@@ -2152,6 +2470,7 @@ gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
     ctx.errcode = StromError_Success;
     sh.base = PGS_SMEM_HEAD_BYTES + nstages * PGS_STAGE_BYTES(tile_rows);
     sh.nslots = (GPUPREAGG_NUM_KEYS > 0 ? sh_nslots : 0);
+    sh.salt = 1;
     pgs_cells_init(acc);
     GPUPREAGG_INCOL_LIST(PGS_X_INCOL_GVIEW)
     if (threadIdx.x == 0)
@@ -2194,6 +2513,437 @@ gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
 }
 
 /* ------------------------------------------------------------------
+ * Heap-page input: KDS_FORMAT_ROW / KDS_FORMAT_ROW_FLAT chunks exactly as
+ * pgstrom_data_store_insert_block / _insert_tuple fill them
+ * (datastore.c:556-823) and clserv_dmasend_data_store lays them out on the
+ * device (datastore.c:837-973):
+ *   ROW      : head | kern_blkitem[maxblocks] | kern_rowitem[nitems] | pad to
+ *              BLCKSZ | raw heap pages[nblocks]; a row item names (block,
+ *              line pointer)
+ *   ROW_FLAT : head | kern_rowitem[nitems] | ... | heap tuples from the tail;
+ *              a row item is the offset of a HeapTupleHeaderData
+ * One thread de-forms one tuple: a single walk over the attributes up to the
+ * last referenced column (alignment padding, NULL bitmap, 1- and 4-byte
+ * varlena headers; the rules of kern_get_datum_tuple, opencl_common.h:
+ * 817-864) fills the register row the generated code reads, so the tuple is
+ * walked once per row and not once per referenced column.  The sanity checks
+ * of kern_get_tuple_rs (opencl_common.h:866-899) are kept: a page that does
+ * not look like a heap page yields StromError_DataStoreCorruption, never a
+ * wild address.
+ * ------------------------------------------------------------------ */
+#define PGS_HEAP_HASNULL        0x0001
+#define PGS_HEAP_NATTS_MASK     0x07FF
+#define PGS_HTUP_INFOMASK2_OFF  18
+#define PGS_HTUP_INFOMASK_OFF   20
+#define PGS_HTUP_HOFF_OFF       22
+#define PGS_HTUP_BITS_OFF       23
+#define PGS_PAGE_HEADER_SIZE    24      /* offsetof(PageHeaderData, pd_linp) */
+#define PGS_PAGE_LOWER_OFF      12
+/* ItemIdData on a little-endian host: lp_off:15, lp_flags:2, lp_len:15 */
+#define PGS_ITEMID_OFFSET(x)    ((x) & 0x7fffU)
+#define PGS_ITEMID_FLAGS(x)     (((x) >> 15) & 0x3U)
+#define PGS_ITEMID_LENGTH(x)    (((x) >> 17) & 0x7fffU)
+#define PGS_LP_NORMAL           1
+
+struct pgs_heap_chunk
+{
+    const unsigned char *base;      /* the kern_data_store */
+    const kern_rowitem  *rowitems;
+    const unsigned char *blocks;    /* ROW: first page */
+    cl_uint     nblocks;
+    cl_uint     length;             /* ROW_FLAT: bytes of the chunk */
+    bool        flat;
+};
+
+DEVFN void
+pgs_heap_chunk_init(pgs_heap_chunk &hc, const kern_data_store *kds)
+{
+    hc.base = (const unsigned char *)kds;
+    hc.flat = (kds->format == KDS_FORMAT_ROW_FLAT);
+    hc.rowitems = KERN_DATA_STORE_ROWITEM(kds, 0);
+    hc.blocks = (const unsigned char *)KERN_DATA_STORE_ROWBLOCK(kds, 0);
+    hc.nblocks = kds->nblocks;
+    hc.length = kds->length;
+}
+
+/* tuple of row `rowidx`, or NULL (bytes available behind it in *p_avail) */
+DEVFN const unsigned char *
+pgs_heap_tuple(const pgs_heap_chunk &hc, cl_uint rowidx, cl_uint *p_avail)
+{
+    kern_rowitem    ri = hc.rowitems[rowidx];
+
+    if (hc.flat)
+    {
+        if (ri.htup_offset >= hc.length || (ri.htup_offset & 7U) != 0 ||
+            ri.htup_offset + PGS_HTUP_BITS_OFF >= hc.length)
+            return NULL;
+        *p_avail = hc.length - ri.htup_offset;
+        return hc.base + ri.htup_offset;
+    }
+    else
+    {
+        const unsigned char *page;
+        cl_uint     lower, nlines, lp, off;
+
+        if (ri.blk_index >= hc.nblocks)
+            return NULL;
+        page = hc.blocks + (cl_ulong)BLCKSZ * ri.blk_index;
+        lower = *((const cl_ushort *)(page + PGS_PAGE_LOWER_OFF));
+        nlines = (lower <= PGS_PAGE_HEADER_SIZE ? 0 : (lower - PGS_PAGE_HEADER_SIZE) / 4);
+        if (PGS_PAGE_HEADER_SIZE + 4 * (nlines + 1) >= BLCKSZ ||
+            ri.item_offset == 0 || ri.item_offset > nlines)
+            return NULL;
+        lp = *((const cl_uint *)(page + PGS_PAGE_HEADER_SIZE) + (ri.item_offset - 1));
+        off = PGS_ITEMID_OFFSET(lp);
+        if (PGS_ITEMID_FLAGS(lp) != PGS_LP_NORMAL || (off & 7U) != 0 ||
+            off + PGS_HTUP_BITS_OFF >= BLCKSZ)
+            return NULL;
+        *p_avail = BLCKSZ - off;
+        return page + off;
+    }
+}
+
+/* VARSIZE_ANY (opencl_common.h:459-463) of a little-endian varlena */
+DEVFN cl_uint
+pgs_varsize_any(const unsigned char *p)
+{
+    cl_uint b = p[0];
+
+    if (b == 0x01)                      /* 1B_E: external TOAST pointer */
+        return 2 + (p[1] == 18 ? 16 : (p[1] == 1 ? 8 : 16));
+    if (b & 0x01)                       /* 1B: short header */
+        return (b >> 1) & 0x7fU;
+    /* 4B header: may sit unaligned only when it is a pad-free short one,
+     * and that case was handled above */
+    return (*((const cl_uint *)p) >> 2) & 0x3fffffffU;
+}
+
+/* value of a by-value attribute of `attlen` bytes, zero-extended */
+template <int ATTLEN> struct pgs_heap_load;
+template <> struct pgs_heap_load<8>
+{ static __device__ __forceinline__ cl_ulong get(const unsigned char *p) { return *((const cl_ulong *)p); } };
+template <> struct pgs_heap_load<4>
+{ static __device__ __forceinline__ cl_ulong get(const unsigned char *p) { return *((const cl_uint *)p); } };
+template <> struct pgs_heap_load<2>
+{ static __device__ __forceinline__ cl_ulong get(const unsigned char *p) { return *((const cl_ushort *)p); } };
+template <> struct pgs_heap_load<1>
+{ static __device__ __forceinline__ cl_ulong get(const unsigned char *p) { return p[0]; } };
+
+#define PGS_X_INCOL_HEAPMAX(slot,colidx,attlen)                         \
+    if ((cl_uint)(colidx) + 1 > lastcol) lastcol = (cl_uint)(colidx) + 1;
+#define PGS_X_INCOL_HEAPCLEAR(slot,colidx,attlen)                       \
+    rr.v[slot] = 0; rr.vbits[slot] = 0;
+#define PGS_X_INCOL_HEAPTAKE(slot,colidx,attlen)                        \
+    if (i == (cl_uint)(colidx))                                         \
+    {                                                                   \
+        if ((cl_int)(attlen) != alen)                                   \
+            return false;                                               \
+        rr.v[slot] = pgs_heap_load<attlen>::get(addr);                  \
+        rr.vbits[slot] = 1U;                                            \
+    }
+
+#define PGS_X_INCOL_HEAPTAKEV(slot,colidx,attlen)                       \
+    if (i == (cl_uint)(colidx))                                         \
+    {                                                                   \
+        rr.v[slot] = (cl_ulong)(addr - (const unsigned char *)kds);     \
+        rr.vbits[slot] = 1U;                                            \
+    }
+
+/* false: the tuple does not fit what colmeta[] says (corruption) */
+DEVFN bool
+pgs_heap_deform(const kern_data_store *kds, const unsigned char *htup,
+                cl_uint avail, kern_row_regs &rr)
+{
+    const cl_uint   infomask = *((const cl_ushort *)(htup + PGS_HTUP_INFOMASK_OFF));
+    const cl_uint   natts = *((const cl_ushort *)(htup + PGS_HTUP_INFOMASK2_OFF)) & PGS_HEAP_NATTS_MASK;
+    const bool      hasnull = (infomask & PGS_HEAP_HASNULL) != 0;
+    cl_uint         offset = htup[PGS_HTUP_HOFF_OFF];
+    cl_uint         lastcol = 0;
+
+    rr.shift = 0;
+    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_HEAPCLEAR)
+    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_HEAPMAX)
+    if (lastcol > kds->ncols)
+        return false;
+    /* attributes beyond natts are NULL (tuple older than ADD COLUMN) */
+    if (lastcol > natts)
+        lastcol = natts;
+    if (offset < PGS_HTUP_BITS_OFF + (hasnull ? (natts + 7) / 8 : 0))
+        return false;
+    for (cl_uint i = 0; i < lastcol; i++)
+    {
+        kern_colmeta    cmeta;
+        const unsigned char *addr;
+        cl_int          alen;
+
+        if (hasnull && !((htup[PGS_HTUP_BITS_OFF + (i >> 3)] >> (i & 7)) & 1))
+            continue;                   /* NULL: takes no space */
+        cmeta = kds->colmeta[i];
+        alen = cmeta.attlen;
+        if (alen > 0)
+            offset = TYPEALIGN((cl_uint)cmeta.attalign, offset);
+        else if (offset < avail && htup[offset] == 0)   /* !VARATT_NOT_PAD_BYTE */
+            offset = TYPEALIGN((cl_uint)cmeta.attalign, offset);
+        if (offset + (alen > 0 ? (cl_uint)alen : 1U) > avail)
+            return false;
+        addr = htup + offset;
+        if (alen > 0)
+        {
+            GPUPREAGG_INCOL_LIST(PGS_X_INCOL_HEAPTAKE)
+            offset += (cl_uint)alen;
+        }
+        else
+        {
+            /* varlena: the row carries the offset of the datum from the head
+             * of the chunk, like a KDS_FORMAT_COLUMN value (pg_numeric_vref) */
+            GPUPREAGG_INCOL_LIST(PGS_X_INCOL_HEAPTAKEV)
+            offset += pgs_varsize_any(addr);
+        }
+    }
+    return true;
+}
+
+/*
+ * gpupreagg_main_heap - heap-page chunks (with or without a kern_row_map).
+ * Same per-row body and epilogue as the other two main kernels; no staging:
+ * rows of one page are neighbours in memory, so the lanes of a warp read
+ * neighbouring sectors.
+ */
+extern "C" __global__ void
+__launch_bounds__(GPUPREAGG_BLOCK_THREADS)
+gpupreagg_main_heap(kern_gpupreagg *kgpreagg,
+                    const kern_data_store *kds_in,
+                    pgs_gstate gs,
+                    cl_uint *recheck_map,
+                    cl_uint sh_nslots,
+                    cl_uint tile_rows,
+                    cl_uint nstages)
+{
+    pgs_smem_head  *head = (pgs_smem_head *)__pgs_smem;
+    unsigned char  *stages = __pgs_smem + PGS_SMEM_HEAD_BYTES;
+    const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF_CONST;
+    const kern_row_map  *krowmap = KERN_GPUPREAGG_KROWMAP(kgpreagg);
+    const cl_uint   nrows = kds_in->nitems;
+    const cl_uint   nvalids = (krowmap->nvalids < 0
+                               ? nrows : (cl_uint)krowmap->nvalids);
+    cl_ulong        acc[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+    cl_uint         acc_nn = 0;
+    pgs_row_ctx     ctx;
+    pgs_sh_table    sh;
+    pgs_heap_chunk  hc;
+
+    ctx.nfiltered = 0;
+    ctx.nrecheck = 0;
+    ctx.ninserted = 0;
+    ctx.errcode = StromError_Success;
+    sh.base = PGS_SMEM_HEAD_BYTES + nstages * PGS_STAGE_BYTES(tile_rows);
+    sh.nslots = (GPUPREAGG_NUM_KEYS > 0 ? sh_nslots : 0);
+    sh.salt = 1;
+    pgs_cells_init(acc);
+    pgs_heap_chunk_init(hc, kds_in);
+    if (threadIdx.x == 0)
+    {
+        head->sh_nused = 0;
+        head->is_last_cta = 0;
+    }
+    PGS_SH_TABLE_INIT()
+    __syncthreads();
+
+    /* warp-uniform trip count: the group path is warp-collective */
+    for (cl_ulong base = (cl_ulong)blockIdx.x * blockDim.x + (threadIdx.x & ~31U);
+         base < nvalids;
+         base += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        cl_ulong    i = base + (threadIdx.x & 31U);
+        pagg_row    prow;
+        bool        valid = false;
+
+        if (i < nvalids)
+        {
+            cl_uint row = (krowmap->nvalids < 0
+                           ? (cl_uint)i : (cl_uint)krowmap->rindex[i]);
+            if (row >= nrows)
+            {
+                if (ctx.errcode == StromError_Success)
+                    ctx.errcode = StromError_DataStoreOutOfRange;
+            }
+            else
+            {
+                kern_row_regs   rr;
+                cl_uint         avail = 0;
+                const unsigned char *htup = pgs_heap_tuple(hc, row, &avail);
+
+                if (!htup || !pgs_heap_deform(kds_in, htup, avail, rr))
+                {
+                    if (ctx.errcode == StromError_Success)
+                        ctx.errcode = StromError_DataStoreCorruption;
+                }
+                else
+                    valid = pgs_eval_row(kparams, rr, kds_in, row, recheck_map, ctx, prow);
+            }
+        }
+#if GPUPREAGG_NUM_KEYS == 0
+        acc_nn |= gpupreagg_aggcalc_plain(acc, prow, valid);
+#else
+        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid);
+#endif
+    }
+    pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
+                      &head->is_last_cta, acc, acc_nn, ctx);
+}
+
+/* ------------------------------------------------------------------
+ * gpupreagg_partagg - second pass of the partitioned GROUP BY.
+ *
+ * With ~10 M groups every row used to cost a handful of atomics on a random
+ * 96-byte slot of a multi-GB table: 276 bytes of random DRAM traffic per row,
+ * 1 TB/s at best (ncu: 13.6 ms per 50 M rows).  Instead the scan deals the
+ * rows into partitions by the high bits of the key hash (pgs_part_emit: one
+ * 32-byte record, one cursor atomic), and here one CTA at a time takes a
+ * partition: its persistent table image (a few hundred groups, the CTA-local
+ * table layout) comes into shared memory with coalesced loads, the records
+ * stream through the same find-or-insert + shared-memory atomics the
+ * low-cardinality path uses, and the image goes back.  All HBM traffic is
+ * sequential.  Rows that do not fit (a full partition, a full image) take the
+ * global table as before; PostgreSQL's final Agg merges partial rows of the
+ * same key, so a group may live in both.
+ * block = PGS_PARTAGG_THREADS, dynamic smem = 128 + image bytes.
+ * ------------------------------------------------------------------ */
+#define PGS_PARTAGG_THREADS     256
+
+extern "C" __global__ void
+__launch_bounds__(PGS_PARTAGG_THREADS)
+gpupreagg_partagg(kern_gpupreagg *kgpreagg,
+                  const kern_data_store *kds_in,
+                  pgs_gstate gs,
+                  cl_uint *recheck_map)
+{
+#if GPUPREAGG_PARTITIONED
+    const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF_CONST;
+    cl_uint        *p_nused = (cl_uint *)__pgs_smem;
+    const cl_uint   image_bytes = gs.part_slots * PGS_SH_SLOT_BYTES;
+    const cl_uint   lane_id = threadIdx.x & 31;
+    pgs_row_ctx     ctx;
+    pgs_sh_table    sh;
+    cl_uint         ngrown = 0;
+
+    ctx.nfiltered = 0;
+    ctx.nrecheck = 0;
+    ctx.ninserted = 0;
+    ctx.errcode = StromError_Success;
+    sh.base = 128;
+    sh.nslots = gs.part_slots;
+    sh.salt = 0x9E3779B1U;
+
+    for (cl_uint part = blockIdx.x; part < gs.part_nparts; part += gridDim.x)
+    {
+        const cl_uint   n = min(gs.part_cursor[part], gs.part_cap);
+        uint4          *image = (uint4 *)(gs.part_images + (cl_ulong)part * image_bytes);
+        uint4          *local = (uint4 *)(__pgs_smem + sh.base);
+        const unsigned char *recs = gs.part_recs +
+            (cl_ulong)part * gs.part_cap * PGS_REC_BYTES;
+
+        if (n == 0)
+            continue;           /* nothing for this image in this chunk */
+        for (cl_uint i = threadIdx.x; i < image_bytes / 16; i += blockDim.x)
+            local[i] = image[i];
+        if (threadIdx.x == 0)
+            *p_nused = gs.part_nused[part];
+        __syncthreads();
+        for (cl_uint i0 = (threadIdx.x & ~31U); i0 < n; i0 += blockDim.x)
+        {
+            const cl_uint   i = i0 + lane_id;
+            bool            active = (i < n);
+            kern_rec_gmem   view;
+            pagg_row        prow;
+
+            view.rec = recs + (cl_ulong)min(i, n - 1) * PGS_REC_BYTES;
+            if (active)
+            {
+                cl_int  e = StromError_Success;
+
+                gpupreagg_projection(&e, kparams, view, prow, kds_in, 0, 0);
+                gpupreagg_aggcheck(&e, prow);
+                if (e != StromError_Success)
+                {
+                    pgs_note_error(e, *((const cl_uint *)(view.rec + PGS_REC_ROW_OFF)),
+                                   recheck_map, ctx);
+                    active = false;
+                }
+            }
+            pgs_group_add_row(gs, sh, p_nused, prow, ctx, active);
+        }
+        __syncthreads();
+        for (cl_uint i = threadIdx.x; i < image_bytes / 16; i += blockDim.x)
+            image[i] = local[i];
+        if (threadIdx.x == 0)
+        {
+            ngrown += *p_nused - gs.part_nused[part];
+            gs.part_nused[part] = *p_nused;
+            gs.part_cursor[part] = 0;
+        }
+        __syncthreads();
+    }
+    ctx.ninserted += ngrown;    /* thread 0: groups the images gained */
+    pgs_writeback_status(kgpreagg, gs, ctx);
+#endif
+}
+
+/*
+ * One slot of the persistent GROUP BY state, wherever it lives: index
+ * [0, gh_nslots) is the global table, the rest are the slots of the table
+ * images.  Returns whether the slot holds a group.
+ */
+DEVFN cl_ulong
+pgs_state_nslots(const pgs_gstate &gs)
+{
+    return (cl_ulong)gs.gh_nslots + (cl_ulong)gs.part_nparts * gs.part_slots;
+}
+DEVFN bool
+pgs_state_slot(const pgs_gstate &gs, cl_ulong i, cl_ulong *keys, cl_ulong *cells,
+               cl_uint &knull, cl_uint &nn)
+{
+    if (i < gs.gh_nslots)
+    {
+        const cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_STRIDE;
+        cl_uint     st = (cl_uint)slot[0];
+
+        if ((st & 3U) != PGS_SLOT_READY)
+            return false;
+        knull = st >> 8;
+        nn = (cl_uint)(slot[0] >> 32);
+#pragma unroll
+        for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+            keys[k] = slot[1 + k];
+#pragma unroll
+        for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+            cells[c] = slot[1 + GPUPREAGG_NUM_KEYS + c];
+        return true;
+    }
+    else
+    {
+        const cl_ulong  j = i - gs.gh_nslots;
+        const cl_uint   S = gs.part_slots;
+        const cl_uint   s = (cl_uint)(j % S);
+        const unsigned char *image = gs.part_images + (j / S) * ((cl_ulong)S * PGS_SH_SLOT_BYTES);
+        cl_uint     tag = ((const cl_uint *)image)[s];
+
+        if ((tag & 3U) != PGS_SLOT_READY)
+            return false;
+        knull = (tag >> 2) & ((1U << GPUPREAGG_NUM_KEYS) - 1U);
+        nn = ((const cl_uint *)(image + 4 * (cl_ulong)S))[s];
+#pragma unroll
+        for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+            keys[k] = ((const cl_ulong *)(image + 8 * (cl_ulong)S))[(cl_ulong)k * S + s];
+#pragma unroll
+        for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+            cells[c] = ((const cl_ulong *)(image + 8 * (cl_ulong)S * (1 + GPUPREAGG_NUM_KEYS)))
+                [(cl_ulong)c * S + s];
+        return true;
+    }
+}
+
+/* ------------------------------------------------------------------
  * gpupreagg_init_state - identity state everywhere
  * ------------------------------------------------------------------ */
 extern "C" __global__ void
@@ -2208,15 +2958,38 @@ gpupreagg_init_state(pgs_gstate gs)
         *gs.ng_ticket = 0;
         *gs.gh_ngroups = 0;
     }
-    for (; i < gs.gh_nslots; i += (cl_ulong)gridDim.x * blockDim.x)
+    for (cl_ulong j = i; j < gs.gh_nslots; j += (cl_ulong)gridDim.x * blockDim.x)
     {
-        cl_ulong   *slot = gs.gh_slots + i * PGS_SLOT_STRIDE;
+        cl_ulong   *slot = gs.gh_slots + j * PGS_SLOT_STRIDE;
 
         slot[0] = 0;
 #pragma unroll
         for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
             slot[1 + k] = 0;
         pgs_cells_init(slot + 1 + GPUPREAGG_NUM_KEYS);
+    }
+    /* table images of the partitions (CTA-local table layout) */
+    for (cl_ulong j = i; j < (cl_ulong)gs.part_nparts * gs.part_slots;
+         j += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        const cl_uint   S = gs.part_slots;
+        const cl_uint   s = (cl_uint)(j % S);
+        unsigned char  *image = gs.part_images + (j / S) * ((cl_ulong)S * PGS_SH_SLOT_BYTES);
+        pgs_sh_cells    cells;
+
+        ((cl_uint *)image)[s] = PGS_SLOT_EMPTY;
+        ((cl_uint *)(image + 4 * (cl_ulong)S))[s] = 0;
+#pragma unroll
+        for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+            ((cl_ulong *)(image + 8 * (cl_ulong)S))[(cl_ulong)k * S + s] = 0;
+        cells.p0 = (cl_ulong *)(image + 8 * (cl_ulong)S * (1 + GPUPREAGG_NUM_KEYS)) + s;
+        cells.stride = S;
+        pgs_cells_init(cells);
+    }
+    for (cl_ulong j = i; j < gs.part_nparts; j += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        gs.part_cursor[j] = 0;
+        gs.part_nused[j] = 0;
     }
 }
 
@@ -2286,6 +3059,60 @@ pgs_piece_i128(cl_ulong lo, cl_ulong hi, cl_uint r)
 #define PGS_NSPLIT_PMAX_LONG(c)     PGS_NSPLIT_OTHER(c)
 #define PGS_NSPLIT_PMAX_FLOAT(c)    PGS_NSPLIT_OTHER(c)
 #define PGS_NSPLIT_PMAX_DOUBLE(c)   PGS_NSPLIT_OTHER(c)
+#ifdef KERN_NUMERIC_CUH
+/* numeric sum cell(s) -> value at its display scale (exact: every addend had
+ * at most that scale) */
+DEVFN pgs_s128
+pgs_numsum_value(const cl_ulong *cells, int c, int *p_dscale)
+{
+    pgs_s128    v = (pgs_s128)(((pgs_u128)cells[c + 1] << 64) | cells[c]);
+    int         ds = (int)(cl_long)cells[c + 2];
+
+    if (ds < 0) ds = 0;
+    if (ds > PGS_NUMERIC_SUM_SCALE) ds = PGS_NUMERIC_SUM_SCALE;
+    *p_dscale = ds;
+    return v / (pgs_s128)pgs_pow10_u128(PGS_NUMERIC_SUM_SCALE - ds);
+}
+DEVFN cl_uint
+pgs_numsum_nsplit(const cl_ulong *cells, int c)
+{
+    int         ds;
+    pgs_s128    v = pgs_numsum_value(cells, c, &ds);
+    pgs_s128    a = (v < 0 ? -v : v);
+    pgs_s128    n = (a + (pgs_s128)PGS_NUMERIC_MANT_LIMIT - 1) / (pgs_s128)PGS_NUMERIC_MANT_LIMIT;
+
+    if (n < 1)
+        n = 1;
+    return (n > 0x7fffffff ? 0x7fffffffU : (cl_uint)n);
+}
+/* piece r of the sum as a device numeric */
+DEVFN cl_ulong
+pgs_numsum_piece(const cl_ulong *cells, int c, cl_uint r)
+{
+    int         ds;
+    pgs_s128    v = pgs_numsum_value(cells, c, &ds);
+    pgs_s128    a = (v < 0 ? -v : v);
+    pgs_s128    rest = a - (pgs_s128)r * (pgs_s128)PGS_NUMERIC_MANT_LIMIT;
+
+    if (rest < 0)
+        rest = 0;
+    if (rest > (pgs_s128)PGS_NUMERIC_MANT_LIMIT)
+        rest = (pgs_s128)PGS_NUMERIC_MANT_LIMIT;
+    return PG_NUMERIC_SET(-ds, (v < 0) && rest != 0, (cl_ulong)rest);
+}
+#endif
+#define PGS_NSPLIT_PSUM_NUMERIC(c)                                      \
+    { cl_uint n = pgs_numsum_nsplit(cells, c);                          \
+      if (n > nsplit) nsplit = n; }
+#define PGS_NSPLIT_PMIN_NUMERIC(c)  PGS_NSPLIT_OTHER(c)
+#define PGS_NSPLIT_PMAX_NUMERIC(c)  PGS_NSPLIT_OTHER(c)
+#define PGS_OUT_PSUM_NUMERIC(i,c)                                       \
+    { isnull = !(nn & (1U << (i)));                                     \
+      datum = pgs_numsum_piece(cells, c, r); }
+#define PGS_OUT_PMIN_NUMERIC(i,c)                                       \
+    { isnull = !(nn & (1U << (i))) || cells[c] == 0xFFFFFFFFFFFFFFFFULL; \
+      datum = cells[c]; }
+#define PGS_OUT_PMAX_NUMERIC(i,c)   PGS_OUT_PMIN_NUMERIC(i,c)
 #define PGS_X_NSPLIT(i,c,OP,TYPE)   PGS_NSPLIT_##OP##_##TYPE(c)
 
 /* Datum of aggregate cell(s) for split row r; sets `isnull` */
@@ -2401,15 +3228,18 @@ gpupreagg_flush(pgs_gstate gs, kern_data_store *kds_dst,
         }
         return;
     }
+    const cl_ulong  nstate = pgs_state_nslots(gs);
+
     for (cl_ulong i0 = (cl_ulong)blockIdx.x * blockDim.x + (threadIdx.x & ~31U);
-         i0 < gs.gh_nslots;
+         i0 < nstate;
          i0 += (cl_ulong)gridDim.x * blockDim.x)
     {
         const cl_ulong  i = i0 + lane_id;
-        const cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_STRIDE;
-        cl_uint     st = (i < gs.gh_nslots ? (cl_uint)slot[0] : PGS_SLOT_EMPTY);
-        bool        ready = ((st & 3U) == PGS_SLOT_READY);
-        cl_uint     nsplit = (ready ? pgs_flush_nsplit(slot + 1 + GPUPREAGG_NUM_KEYS) : 0);
+        cl_ulong    keys[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
+        cl_ulong    cells[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+        cl_uint     knull = 0, nn = 0;
+        bool        ready = (i < nstate && pgs_state_slot(gs, i, keys, cells, knull, nn));
+        cl_uint     nsplit = (ready ? pgs_flush_nsplit(cells) : 0);
         cl_uint     incl = nsplit;
         cl_uint     base = 0;
 
@@ -2425,9 +3255,7 @@ gpupreagg_flush(pgs_gstate gs, kern_data_store *kds_dst,
         base = __shfl_sync(0xffffffffU, base, 31);
         if (ready)
             pgs_flush_rows(kds_dst, kgpreagg, base + incl - nsplit, nsplit,
-                           slot + 1, st >> 8,
-                           slot + 1 + GPUPREAGG_NUM_KEYS,
-                           (cl_uint)(slot[0] >> 32));
+                           keys, knull, cells, nn);
     }
 }
 
@@ -2452,15 +3280,18 @@ gpupreagg_export(pgs_gstate gs, cl_ulong *records, cl_uint *nrecords,
         return;
     }
     /* whole warps; record positions are handed out once per warp */
+    const cl_ulong  nstate = pgs_state_nslots(gs);
+
     for (cl_ulong i0 = (cl_ulong)blockIdx.x * blockDim.x + (threadIdx.x & ~31U);
-         i0 < gs.gh_nslots;
+         i0 < nstate;
          i0 += (cl_ulong)gridDim.x * blockDim.x)
     {
         const cl_uint   lane_id = threadIdx.x & 31;
         const cl_ulong  i = i0 + lane_id;
-        const cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_STRIDE;
-        bool        ready = (i < gs.gh_nslots &&
-                             ((cl_uint)slot[0] & 3U) == PGS_SLOT_READY);
+        cl_ulong    keys[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
+        cl_ulong    cells[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+        cl_uint     knull = 0, nn = 0;
+        bool        ready = (i < nstate && pgs_state_slot(gs, i, keys, cells, knull, nn));
         cl_uint     votes = __ballot_sync(0xffffffffU, ready);
         cl_uint     base = 0;
 
@@ -2472,8 +3303,15 @@ gpupreagg_export(pgs_gstate gs, cl_ulong *records, cl_uint *nrecords,
             cl_uint pos = base + __popc(votes & ((1U << lane_id) - 1U));
             if (pos < max_records)
             {
-                for (int w = 0; w < PGS_SLOT_WORDS; w++)
-                    records[(cl_ulong)pos * PGS_SLOT_WORDS + w] = slot[w];
+                cl_ulong *rec = records + (cl_ulong)pos * PGS_SLOT_WORDS;
+
+                rec[0] = ((cl_ulong)nn << 32) | (knull << 8) | PGS_SLOT_READY;
+#pragma unroll
+                for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+                    rec[1 + k] = keys[k];
+#pragma unroll
+                for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                    rec[1 + GPUPREAGG_NUM_KEYS + c] = cells[c];
             }
         }
     }
@@ -2601,6 +3439,7 @@ gpupreagg_describe(pgs_kern_desc *desc)
     desc->num_outcols = GPUPREAGG_NUM_OUTCOLS;
     desc->slot_bytes = PGS_SLOT_BYTES;
     desc->slot_stride_bytes = 8 * PGS_SLOT_STRIDE;
+    desc->part_rec_bytes = (GPUPREAGG_PARTITIONED ? PGS_REC_BYTES : 0);
     desc->tile_rows = 1024;             /* granule of the tile size */
     desc->num_stages = GPUPREAGG_MAX_STAGES;
     desc->stage_bytes = PGS_STAGE_BYTES(1024);  /* per 1024 rows */

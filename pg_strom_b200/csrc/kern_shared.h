@@ -16,6 +16,17 @@ typedef struct
     cl_uint     gh_nslots;      /* power of 2 */
     cl_uint     gh_max_probe;
     cl_uint    *gh_ngroups;     /* number of READY slots */
+    /* group-by with very many groups: rows are first dealt into partitions
+     * (by the high bits of the key hash), then every partition is
+     * aggregated in shared memory into its own persistent table image */
+    cl_uint     part_nparts;    /* 0 = off */
+    cl_uint     part_cap;       /* records one partition takes per chunk */
+    cl_uint     part_slots;     /* slots of a table image (multiple of 32) */
+    cl_uint     part_pad;
+    cl_uint    *part_cursor;    /* [nparts] records of the current chunk */
+    cl_uint    *part_nused;     /* [nparts] used slots of the image */
+    unsigned char *part_recs;   /* [nparts][cap] records */
+    unsigned char *part_images; /* [nparts] images, PGS_SH_SLOT_BYTES * slots each */
     /* bookkeeping */
     cl_ulong   *nrows_scanned;  /* rows that passed visibility (row-map) */
     cl_ulong   *nrows_filtered; /* rows removed by the device qual */
@@ -40,7 +51,8 @@ typedef struct
     cl_uint     sh_slot_bytes;      /* bytes per slot of the CTA-local table */
     cl_uint     row_bytes;          /* algorithmic bytes per row (attlen sum) */
     cl_uint     slot_stride_bytes;  /* distance of two slots of the global table */
-    cl_uint     reserved[2];
+    cl_uint     part_rec_bytes;     /* bytes of a partition record */
+    cl_uint     reserved[1];
 } pgs_kern_desc;
 
 #endif  /* KERN_SHARED_H */

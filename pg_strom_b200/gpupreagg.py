@@ -123,6 +123,193 @@ class DataStore:
             pass
 
 
+KDS_FORMAT_ROW, KDS_FORMAT_ROW_FLAT, KDS_FORMAT_TUPSLOT, KDS_FORMAT_COLUMN = 1, 2, 3, 4
+BLCKSZ = 8192
+
+
+class HeapDataStore:
+    """A chunk in the reference's own input formats: KDS_FORMAT_ROW (heap
+    pages referenced by kern_blkitem.page, one kern_rowitem per visible
+    tuple - what pgstrom_data_store_insert_block builds, datastore.c:556-710)
+    or KDS_FORMAT_ROW_FLAT (tuples packed from the tail, :799-823).
+
+    `columns` as for DataStore; a column given as None is NULL in every row
+    (PostgreSQL would store all columns, the device skips the ones the query
+    does not reference either way).  `visible` optionally selects the rows a
+    snapshot sees (bool array): invisible tuples stay on their page but get no
+    kern_rowitem.  The synthetic pages stand in for shared buffers.
+    """
+
+    def __init__(self, coltypes, columns, nrows=None, flat=False, visible=None):
+        lib = _capi.load()
+        self.lib = lib
+        self.coltypes = list(coltypes)
+        ncols = len(coltypes)
+        self.colmeta = make_colmeta(coltypes)
+        lib.pgstrom_colmeta_set_cacheoff(ncols, self.colmeta)
+        vals = (C.c_void_p * ncols)()
+        nuls = (C.c_void_p * ncols)()
+        keep = []
+        blob = bytearray(b"\0" * 8)
+        rowbytes = 24 + 8 + (ncols + 7) // 8
+        for c, col in enumerate(columns):
+            if col is None:
+                continue
+            v, m = col
+            attlen, _, align, dt = PGTYPES[coltypes[c]]
+            if attlen > 0:
+                a = np.ascontiguousarray(v, dtype=dt)
+                n = a.shape[0]
+                keep.append(a)
+                vals[c] = a.ctypes.data
+                rowbytes += attlen + align
+            else:
+                n = len(v)
+                offs = np.zeros(n, dtype=np.uint32)
+                mm = np.zeros(n, dtype=np.uint8)
+                maxlen = 0
+                for i, d in enumerate(v):
+                    if d is None:
+                        mm[i] = 1
+                        continue
+                    while len(blob) % 4:
+                        blob.append(0)
+                    offs[i] = len(blob)
+                    blob += bytes(d)
+                    maxlen = max(maxlen, len(d))
+                keep.append(offs)
+                vals[c] = offs.ctypes.data
+                rowbytes += maxlen + 4
+                if m is None and mm.any():
+                    m = mm
+                elif m is not None:
+                    m = np.asarray(m, dtype=np.uint8) | mm
+            if nrows is None:
+                nrows = n
+            assert n == nrows
+            if m is not None:
+                mk = np.ascontiguousarray(m, dtype=np.uint8)
+                keep.append(mk)
+                nuls[c] = mk.ctypes.data
+        self.nrows = nrows = int(nrows or 0)
+        per_page = max(1, (BLCKSZ - 24) // (rowbytes + 4 + 8))
+        maxpages = nrows // per_page + 2
+        self._pages = lib.pgs_chunk_alloc(maxpages * BLCKSZ)
+        rpp = np.zeros(maxpages, dtype=np.uint32)
+        cblob = (C.c_char * len(blob)).from_buffer(blob)
+        npages = lib.pgstrom_heap_form_pages(ncols, self.colmeta, nrows, vals, nuls,
+                                             C.addressof(cblob), self._pages, maxpages,
+                                             rpp.ctypes.data)
+        if npages < 0:
+            raise MemoryError("pgstrom_heap_form_pages: %d pages are not enough" % maxpages)
+        del cblob
+        self.npages = int(npages)
+        vis = None if visible is None else np.asarray(visible, dtype=bool)
+        self.format = KDS_FORMAT_ROW_FLAT if flat else KDS_FORMAT_ROW
+        if not flat:
+            # the reference sizes a chunk as BLCKSZ * maxblocks bytes for
+            # head, items and pages together (datastore.c:604-613)
+            maxblocks = self.npages + 2
+            while True:
+                meta = int(lib.pgstrom_kds_row_length(ncols, maxblocks, max(nrows, 1)))
+                need = self.npages + (meta + BLCKSZ - 1) // BLCKSZ + 1
+                if need <= maxblocks:
+                    break
+                maxblocks = need
+            self.length = int(lib.pgstrom_kds_row_length(ncols, maxblocks, max(nrows, 1)))
+            self.ptr = lib.pgs_chunk_alloc(self.length)
+            check(lib.pgstrom_kds_row_init(self.ptr, self.length, ncols, self.colmeta,
+                                           maxblocks, max(nrows, 1)))
+            r0 = 0
+            for p in range(self.npages):
+                n = int(rpp[p])
+                offs = np.arange(1, n + 1, dtype=np.uint16)
+                if vis is not None:
+                    offs = offs[vis[r0:r0 + n]]
+                offs = np.ascontiguousarray(offs)
+                got = lib.pgstrom_kds_row_insert_block(self.ptr, self._pages + p * BLCKSZ,
+                                                       offs.ctypes.data, len(offs))
+                if got < 0:
+                    raise MemoryError("pgstrom_kds_row_insert_block: store is full")
+                r0 += n
+        else:
+            self.length = int(lib.pgstrom_kds_row_length(ncols, 0, max(nrows, 1))) + \
+                self.npages * BLCKSZ + 64
+            self.ptr = lib.pgs_chunk_alloc(self.length)
+            check(lib.pgstrom_kds_flat_init(self.ptr, self.length, ncols, self.colmeta,
+                                            max(nrows, 1)))
+            raw = C.string_at(self._pages, self.npages * BLCKSZ)
+            r0 = 0
+            for p in range(self.npages):
+                n = int(rpp[p])
+                for i in range(n):
+                    if vis is not None and not vis[r0 + i]:
+                        continue
+                    lp, = struct.unpack_from("<I", raw, p * BLCKSZ + 24 + 4 * i)
+                    off, ln = lp & 0x7fff, (lp >> 17) & 0x7fff
+                    if not lib.pgstrom_kds_flat_insert_tuple(
+                            self.ptr, self._pages + p * BLCKSZ + off, ln):
+                        raise MemoryError("pgstrom_kds_flat_insert_tuple: store is full")
+                r0 += n
+        kds = kern_data_store.from_address(self.ptr)
+        self.nitems = int(kds.nitems)
+        del keep
+
+    def device_image(self):
+        """The chunk as it sits in device memory (what the CUDA layer's DMA
+        assembles): bytes, for tests and device-resident runs."""
+        kds = kern_data_store.from_address(self.ptr)
+        if self.format == KDS_FORMAT_ROW_FLAT:
+            return C.string_at(self.ptr, kds.length)
+        ncols = len(self.coltypes)
+        head = int(self.lib.pgstrom_kds_head_length(ncols))
+        blk = (16 * kds.maxblocks + 15) & ~15
+        items = (4 * kds.nitems + 15) & ~15
+        first = (head + blk + items + BLCKSZ - 1) // BLCKSZ * BLCKSZ
+        img = bytearray(first + self.npages * BLCKSZ)
+        img[:head + blk + 4 * kds.nitems] = C.string_at(self.ptr, head + blk + 4 * kds.nitems)
+        img[first:] = C.string_at(self._pages, self.npages * BLCKSZ)
+        return bytes(img)
+
+    def device_layout(self):
+        """(bytes of head + items, offset of the first page, total bytes) of
+        the device image."""
+        kds = kern_data_store.from_address(self.ptr)
+        if self.format == KDS_FORMAT_ROW_FLAT:
+            return kds.length, kds.length, kds.length
+        head = int(self.lib.pgstrom_kds_head_length(len(self.coltypes)))
+        blk = (16 * kds.maxblocks + 15) & ~15
+        items = (4 * kds.nitems + 15) & ~15
+        first = (head + blk + items + BLCKSZ - 1) // BLCKSZ * BLCKSZ
+        return head + blk + 4 * kds.nitems, first, first + self.npages * BLCKSZ
+
+    def upload(self, device=0):
+        """Assembles the device image in HBM; returns (pointer, bytes)."""
+        headlen, first, total = self.device_layout()
+        dptr = self.lib.pgs_device_alloc(device, total)
+        if not dptr:
+            raise MemoryError("pgs_device_alloc(%d)" % total)
+        check(self.lib.pgs_device_upload(device, dptr, self.ptr, headlen))
+        if self.format == KDS_FORMAT_ROW:
+            check(self.lib.pgs_device_upload(device, dptr + first, self._pages,
+                                             self.npages * BLCKSZ))
+        return dptr, total
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.lib.pgs_chunk_free(self.ptr)
+            self.ptr = None
+        if getattr(self, "_pages", None):
+            self.lib.pgs_chunk_free(self._pages)
+            self._pages = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def decode_datum(datum, isnull, typ):
     """8-byte Datum of a TUPSLOT row -> python value (by-value types)."""
     if isnull:
@@ -347,6 +534,12 @@ class Session:
         check(self.lib.pgs_preagg_submit(self.handle, ds.ptr,
                                          rm.ctypes.data if rm is not None else None,
                                          C.byref(t)))
+        return t.value
+
+    def submit_device_format(self, dptr, length, nitems, fmt):
+        t = C.c_int64()
+        check(self.lib.pgs_preagg_submit_device_format(self.handle, dptr, length, nitems, fmt,
+                                                       None, C.byref(t)))
         return t.value
 
     def submit_device(self, dptr, length, nitems):

@@ -95,6 +95,50 @@ def test_where_small_local_table_spills(cuda, monkeypatch):
 
 
 def test_high_cardinality(cuda):
+    """Many groups: rows are dealt into partitions, every partition is
+    aggregated in shared memory into its persistent table image."""
     ng, rows, pm = _run("high_cardinality", 1_000_000, 500_000,
                         plan_kw={"num_groups": 200_000}, col_kw={"num_groups": 200_000})
     assert ng > 190_000
+    assert pm["part_nparts"] > 0
+
+
+def test_high_cardinality_ragged_chunks(cuda):
+    ng, rows, pm = _run("high_cardinality", 1_300_001, 299_996,
+                        plan_kw={"num_groups": 100_000}, col_kw={"num_groups": 100_000})
+    assert pm["part_nparts"] > 0
+
+
+def test_high_cardinality_global_table(cuda, monkeypatch):
+    """The same through the global open-addressing table alone."""
+    monkeypatch.setenv("PGSTROM_NO_PARTITION", "1")
+    ng, rows, pm = _run("high_cardinality", 1_000_000, 500_000,
+                        plan_kw={"num_groups": 200_000}, col_kw={"num_groups": 200_000})
+    assert ng > 190_000 and pm["part_nparts"] == 0
+
+
+def test_high_cardinality_partition_overflow(cuda):
+    """Record areas sized for 50 K-row chunks receive 500 K-row chunks: what
+    the partitions refuse goes to the global table, groups then live in both
+    and PostgreSQL's final Agg (here: the checker) merges them."""
+    ng, rows, pm = _run("high_cardinality", 1_000_000, 500_000,
+                        plan_kw={"num_groups": 200_000}, col_kw={"num_groups": 200_000},
+                        session_kw={"max_chunk_rows": 50_000})
+    assert ng > 190_000 and pm["part_nparts"] > 0
+    assert len(rows) > ng           # some groups came back as two partial rows
+
+
+def test_high_cardinality_small_images(cuda, monkeypatch):
+    """Images of 64 slots fill up (75% limit): the rest spills to the global table."""
+    monkeypatch.setenv("PGSTROM_PART_SLOTS", "64")
+    ng, rows, pm = _run("high_cardinality", 600_000, 300_000,
+                        plan_kw={"num_groups": 150_000}, col_kw={"num_groups": 150_000})
+    assert pm["part_slots"] == 64
+
+
+def test_where_many_groups(cuda):
+    """WHERE + GROUP BY with more groups than a CTA-local table takes: the
+    qual's survivors are dealt into partitions."""
+    ng, rows, pm = _run("where_agg", 1_500_000, 500_000,
+                        plan_kw={"num_groups": 120_000}, col_kw={"num_groups": 120_000})
+    assert pm["sh_nslots"] == 0 and pm["part_nparts"] > 0

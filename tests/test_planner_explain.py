@@ -20,7 +20,7 @@ from pg_strom_b200 import gpupreagg as gp  # noqa: E402
 from pg_strom_b200 import pgplan as P  # noqa: E402
 
 
-NUMERIC_GAP_STATEMENTS = 22
+NUMERIC_GAP_STATEMENTS = 0
 
 
 def _statements():
@@ -46,9 +46,8 @@ def test_explain_matches_reference_goldens(lib):
                 bad.append((s["sql"], s["gucs"], out, s["plan"]))
         finally:
             plan.free()
-    # Known gap ("numeric"): partial aggregates over a numeric
-    # column (opencl_numeric.h) are not on the device yet, the planner half
-    # leaves those statements to PostgreSQL.  Everything else must match.
+    # (partial aggregates over a numeric column used to be a gap; they are on
+    # the device now - kern_numeric.cuh - and all 612 plans must match)
     numeric_gap = [b for b in bad
                    if any("pgstrom." in ln and "nume_" in ln for ln in b[3])
                    and not any("GpuPreAgg" in ln for ln in b[2])]

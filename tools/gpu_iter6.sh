@@ -1,0 +1,2 @@
+timeout 1500 python -m pytest tests -m gpu -q --timeout 400 > gpurun_out/t_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_gpu.log
+timeout 300 python bench.py --workload high_cardinality --no-cpu-baseline > gpurun_out/bench_hc.json 2> gpurun_out/bench_hc.err; echo "rc=$?" >> gpurun_out/bench_hc.err
