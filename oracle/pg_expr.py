@@ -13,6 +13,7 @@ import math
 import struct
 from decimal import Decimal
 
+from . import pg_typelib
 from .pg_agg import PgError, cast as pg_cast, float8pl, float8mul, check_float8, f4
 
 _INT_RANGE = {"int2": (-(1 << 15), (1 << 15) - 1, "smallint out of range"),
@@ -37,8 +38,10 @@ def _const_value(e):
     v = e.get("constvalue")
     if t == "bool":
         return v in ("t", "true", True)
-    if t in _INT_RANGE or t == "date":
+    if t in _INT_RANGE or t in ("date", "time", "timestamp"):
         return int(v)
+    if t in ("text", "bpchar"):
+        return v.encode() if isinstance(v, str) else bytes(v)
     if t in ("float4", "float8"):
         x = float({"NaN": "nan", "Infinity": "inf", "-Infinity": "-inf"}.get(v, v))
         return f4(x) if t == "float4" else x
@@ -111,6 +114,9 @@ _CMP = {"eq": lambda c: c == 0, "ne": lambda c: c != 0, "lt": lambda c: c < 0,
 
 def _call(name, argtypes, rettype, args):
     """strict functions: NULL in -> NULL out (handled by the caller)."""
+    fn = pg_typelib.lookup(name, argtypes)
+    if fn is not None:
+        return fn(*args)
     # casts: function named after the target type
     if name in ("int2", "int4", "int8", "float4", "float8", "numeric") and len(args) == 1:
         return pg_cast(args[0], argtypes[0], name)

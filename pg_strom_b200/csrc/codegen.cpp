@@ -241,6 +241,8 @@ build_devfunc_catalog(void)
     cat("numeric", {"int2"}, "n/F:int2_numeric");
     cat("numeric", {"int4"}, "n/F:int4_numeric");
     cat("numeric", {"int8"}, "n/F:int8_numeric");
+    cat("numeric", {"float4"}, "n/F:float4_numeric");
+    cat("numeric", {"float8"}, "n/F:float8_numeric");
     cat("numeric_add", {"numeric", "numeric"}, "n/F:numeric_add");
     cat("numeric_sub", {"numeric", "numeric"}, "n/F:numeric_sub");
     cat("numeric_mul", {"numeric", "numeric"}, "n/F:numeric_mul");
@@ -255,6 +257,58 @@ build_devfunc_catalog(void)
     cat("numeric_gt", {"numeric", "numeric"}, "n/F:numeric_gt");
     cat("numeric_ge", {"numeric", "numeric"}, "n/F:numeric_ge");
     cat("numeric_cmp", {"numeric", "numeric"}, "n/F:numeric_cmp");
+
+    /* Date and time functions (kern_timelib.cuh) */
+    cat("date", {"date"}, "ta/c:");
+    cat("date", {"timestamp"}, "t/F:timestamp_date");
+    cat("time", {"timestamp"}, "t/F:timestamp_time");
+    cat("time", {"time"}, "ta/c:");
+    cat("timestamp", {"timestamp"}, "ta/c:");
+    cat("timestamp", {"date"}, "t/F:date_timestamp");
+    cat("date_pli", {"date", "int4"}, "t/F:date_pli");
+    cat("date_mii", {"date", "int4"}, "t/F:date_mii");
+    cat("date_mi", {"date", "date"}, "t/F:date_mi");
+    cat("datetime_pl", {"date", "time"}, "t/F:datetime_pl");
+    cat("integer_pl_date", {"int4", "date"}, "t/F:integer_pl_date");
+    cat("timedate_pl", {"time", "date"}, "t/F:timedata_pl");
+    for (const char *sfx : {"eq", "ne", "lt", "le", "gt", "ge", "cmp"})
+    {
+        cat(std::string("date_") + sfx + "_timestamp", {"date", "timestamp"},
+            std::string("t/F:date_") + sfx + "_timestamp");
+        cat(std::string("timestamp_") + sfx + "_date", {"timestamp", "date"},
+            std::string("t/F:timestamp_") + sfx + "_date");
+    }
+
+    /* Text functions (kern_textlib.cuh) */
+    for (const char *sfx : {"eq", "ne", "lt", "le", "gt", "ge", "cmp"})
+        cat(std::string("bpchar") + sfx, {"bpchar", "bpchar"}, std::string("s/F:bpchar") + sfx);
+    cat("texteq", {"text", "text"}, "s/F:texteq");
+    cat("textne", {"text", "text"}, "s/F:textne");
+    cat("text_lt", {"text", "text"}, "s/F:text_lt");
+    cat("text_le", {"text", "text"}, "s/F:text_le");
+    cat("text_gt", {"text", "text"}, "s/F:text_gt");
+    cat("text_ge", {"text", "text"}, "s/F:text_ge");
+    cat("bttextcmp", {"text", "text"}, "s/F:text_cmp");
+}
+
+/* text ordering on the device is bytewise = the "C" collation; equality does
+ * not depend on the collation (kern_textlib.cuh).  "inputcollid" is the name
+ * of the operator's input collation as the PostgreSQL glue resolves it
+ * ("default" already replaced by the database's lc_collate). */
+static bool
+collation_is_device_compatible(const std::string &func_name, const JsonPtr &node)
+{
+    static const char *ordered[] = {
+        "text_lt", "text_le", "text_gt", "text_ge", "bttextcmp",
+        "bpcharlt", "bpcharle", "bpchargt", "bpcharge", "bpcharcmp" };
+    bool is_ordered = false;
+    for (const char *n : ordered)
+        if (func_name == n)
+            is_ordered = true;
+    if (!is_ordered)
+        return true;
+    std::string coll = node->s("inputcollid", "C");
+    return coll == "C" || coll == "POSIX";
 }
 
 static std::string
@@ -527,7 +581,11 @@ devtype_is_runnable(const DevType *dtype)
     if (!dtype)
         return false;
     if (dtype->type_flags & DEVTYPE_IS_VARLENA)
-        return std::string(dtype->type_name) == "numeric";  /* kern_numeric.cuh */
+    {
+        std::string n = dtype->type_name;
+        /* kern_numeric.cuh, kern_textlib.cuh */
+        return n == "numeric" || n == "text" || n == "bpchar";
+    }
     return true;
 }
 
@@ -580,7 +638,7 @@ codegen_expression_walker(const JsonPtr &node, CodegenContext &ctx, std::string 
                                                : node->s("opfuncname"));
         const Json *args = node->get("args");
         const DevFunc *dfunc = devfunc_lookup(fname, arg_types(args), expr_type(node));
-        if (!dfunc)
+        if (!dfunc || !collation_is_device_compatible(fname, node))
             return false;
         ctx.track_func(dfunc);
         out += "pgfn_" + dfunc->func_alias + "(errcode";

@@ -148,9 +148,11 @@ nvrtc_build(pgs_program *prog)
     nvrtcProgram nprog;
     const char *headers[] = { pgs_hdr_pgstrom_kds_h, pgs_hdr_kern_shared_h,
                               pgs_hdr_kern_common_cuh, pgs_hdr_kern_numeric_cuh,
+                              pgs_hdr_kern_timelib_cuh, pgs_hdr_kern_textlib_cuh,
                               pgs_hdr_kern_gpupreagg_cuh };
     const char *names[] = { "pgstrom_kds.h", "kern_shared.h", "kern_common.cuh",
-                            "kern_numeric.cuh", "kern_gpupreagg.cuh" };
+                            "kern_numeric.cuh", "kern_timelib.cuh", "kern_textlib.cuh",
+                            "kern_gpupreagg.cuh" };
     std::string d_warps = "-DGPUPREAGG_CONSUMER_WARPS=" +
         std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "16");
     std::string d_rpt = "-DGPUPREAGG_MIN_CTAS=" +
@@ -166,7 +168,8 @@ nvrtc_build(pgs_program *prog)
         opts.push_back("-Xptxas=-O0");
     auto t0 = std::chrono::steady_clock::now();
     nvrtcResult rc = nvrtcCreateProgram(&nprog, prog->source.c_str(), "gpupreagg.cu",
-                                        5, headers, names);
+                                        (int)(sizeof(headers) / sizeof(headers[0])),
+                                        headers, names);
     if (rc != NVRTC_SUCCESS)
     {
         set_error("nvrtcCreateProgram: %s", nvrtcGetErrorString(rc));
@@ -217,6 +220,10 @@ pgs_program_build(const char *kern_source, int extra_flags,
     crc = crc32_buf(crc, pgs_hdr_kern_gpupreagg_cuh, strlen(pgs_hdr_kern_gpupreagg_cuh));
     crc = crc32_buf(crc, pgs_hdr_kern_common_cuh, strlen(pgs_hdr_kern_common_cuh));
     crc = crc32_buf(crc, pgs_hdr_kern_numeric_cuh, strlen(pgs_hdr_kern_numeric_cuh));
+    if (extra_flags & DEVFUNC_NEEDS_TIMELIB)
+        crc = crc32_buf(crc, pgs_hdr_kern_timelib_cuh, strlen(pgs_hdr_kern_timelib_cuh));
+    if (extra_flags & DEVFUNC_NEEDS_TEXTLIB)
+        crc = crc32_buf(crc, pgs_hdr_kern_textlib_cuh, strlen(pgs_hdr_kern_textlib_cuh));
     crc = crc32_buf(crc, pgs_hdr_pgstrom_kds_h, strlen(pgs_hdr_pgstrom_kds_h));
     crc = crc32_buf(crc, pgs_hdr_kern_shared_h, strlen(pgs_hdr_kern_shared_h));
 

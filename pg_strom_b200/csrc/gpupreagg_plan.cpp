@@ -667,6 +667,10 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
     else
         fn_qual << "  return true;\n";
     fn_qual << "}\n";
+    /* a qual that follows a varlena offset (numeric, text, bpchar) must not
+     * be evaluated on the unused rows of a partial batch */
+    const bool qual_derefs =
+        (context.extra_flags & (DEVFUNC_NEEDS_NUMERIC | DEVFUNC_NEEDS_TEXTLIB)) != 0;
 
     /* ---- gpupreagg_projection (gpupreagg.c:1449-1837) ---- */
     context.param_refs.clear();
@@ -976,6 +980,7 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
                     o << " _(" << kc.second.first << ",0x" << std::hex << kc.second.second << std::dec << "U)";
                 return o.str(); }() << "\n"
          << "#define GPUPREAGG_HAS_QUAL " << (outer_quals.empty() ? 0 : 1) << "\n"
+         << (qual_derefs ? "#define GPUPREAGG_QUAL_DEREFS 1\n" : "")
          /* partitioned aggregation is compiled in when the planner expects
           * very many groups (gpupreagg_partagg; the CUDA layer switches it on
           * with the same threshold) */
@@ -1002,6 +1007,10 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
         << "#include \"kern_common.cuh\"\n";
     if (context.extra_flags & DEVFUNC_NEEDS_NUMERIC)
         src << "#include \"kern_numeric.cuh\"\n";
+    if (context.extra_flags & DEVFUNC_NEEDS_TIMELIB)
+        src << "#include \"kern_timelib.cuh\"\n";
+    if (context.extra_flags & DEVFUNC_NEEDS_TEXTLIB)
+        src << "#include \"kern_textlib.cuh\"\n";
     src << "#include \"kern_gpupreagg.cuh\"\n"
         << "\n"
         << codegen_func_declarations(context) << "\n"

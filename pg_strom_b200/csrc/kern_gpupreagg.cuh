@@ -74,6 +74,11 @@
 #define PGS_PART_NPARTS(gs)         0U
 #endif
 
+/* 1 when gpupreagg_qual_eval() reads varlena datums (numeric, text) */
+#ifndef GPUPREAGG_QUAL_DEREFS
+#define GPUPREAGG_QUAL_DEREFS       0
+#endif
+
 #ifndef GPUPREAGG_DEBUG_LEVEL
 #define GPUPREAGG_DEBUG_LEVEL       0
 #endif
@@ -2308,8 +2313,17 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                         {
                             cl_int      e = StromError_Success;
 
+#if GPUPREAGG_QUAL_DEREFS
+                            /* the qual follows varlena offsets: rows past the
+                             * end of the tile hold stale ones */
+                            valid4[j] = false;
+                            if ((cl_uint)j < nv)
+                                valid4[j] = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
+                                                                row0 + r + j);
+#else
                             valid4[j] = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
                                                             row0 + r + j) & ((cl_uint)j < nv);
+#endif
                             if (e != StromError_Success)
                             {
                                 if ((cl_uint)j < nv)

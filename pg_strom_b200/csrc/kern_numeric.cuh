@@ -401,6 +401,152 @@ pgfn_numeric_float4(cl_int *errcode, pg_numeric_t a)
 PGS_NUMERIC_FROM_INT_TEMPLATE(int2)
 PGS_NUMERIC_FROM_INT_TEMPLATE(int4)
 PGS_NUMERIC_FROM_INT_TEMPLATE(int8)
+/*
+ * float8 / float4 -> numeric (numeric.c float8_numeric / float4_numeric):
+ * PostgreSQL prints the value with "%.15g" (float4: "%.6g") and reads the
+ * text back with numeric_in().  printf rounds the EXACT binary value to P
+ * significant digits (ties to even), %g drops trailing zeros, and numeric_in
+ * gives the display scale of what is left.  Here the same decimal is
+ * computed with 128-bit integers:  |v| = m * 2^e,  q = floor(|v| * 10^k)
+ * with k chosen so that 10^(P-1) <= q < 10^P, remainder kept as a fraction
+ * num/den for the tie test.  Ranges that would need more than 128 bits
+ * (|v| < ~1e-18 for float8, |v| >= 2^127) are re-checked on the host, like
+ * everything that does not fit the 57-bit device format, NaN and +-Inf.
+ */
+DEVFN pg_numeric_t
+pgs_float_to_numeric(cl_int *errcode, double v, int ndigits)
+{
+    pg_numeric_t r;
+    union { double d; cl_ulong u; } cv;
+    cv.d = v;
+    cl_ulong    bits = cv.u;
+    bool        neg = (bits >> 63) != 0;
+    int         bexp = (int)((bits >> 52) & 0x7ff);
+    cl_ulong    frac = bits & 0x000fffffffffffffULL;
+    cl_ulong    m;
+    int         e, x;
+    pgs_u128    lo = pgs_pow10_u128(ndigits - 1), hi = lo * 10;
+    pgs_u128    q = 0, num = 0, den = 1;
+    int         k = 0;
+    bool        found = false;
+
+    r.isnull = true;
+    r.value = 0;
+    if (bexp == 0x7ff)
+        goto recheck;               /* NaN (numeric NaN) / Inf (PostgreSQL error) */
+    if (bexp == 0 && frac == 0)
+        return pgs_numeric_make(errcode, false, 0, 0);
+    if (bexp == 0)
+        goto recheck;               /* subnormal: far below 10^-32 */
+    m = frac | (1ULL << 52);
+    e = bexp - 1075;
+    /* floor(log10 |v|) estimated from the binary exponent (30103/100000 ~
+     * log10 2), then corrected by the exact test below */
+    x = (int)(((cl_long)(e + 52) * 30103LL) / 100000LL);
+    if (e + 52 < 0)
+        x -= 1;
+    for (int attempt = 0; attempt < 4 && !found; attempt++)
+    {
+        k = ndigits - 1 - x;
+        if (k >= 0)
+        {
+            int     s = e + k;
+            if (k > 32)
+                goto recheck;
+            num = (pgs_u128)m * (pgs_pow10_u128(k) >> k);   /* m * 5^k < 2^128 */
+            if (s >= 0)
+            {
+                if (s > 20)
+                    goto recheck;   /* cannot happen for a correct x */
+                q = num << s;
+                num = 0;
+                den = 1;
+            }
+            else
+            {
+                if (-s >= 127)
+                    goto recheck;
+                den = (pgs_u128)1 << (-s);
+                q = num >> (-s);
+                num = num & (den - 1);
+            }
+        }
+        else
+        {
+            if (-k > 36)
+                goto recheck;
+            den = pgs_pow10_u128(-k);
+            if (e >= 0)
+            {
+                if (e > 74)
+                    goto recheck;   /* |v| >= 2^127 */
+                num = (pgs_u128)m << e;
+            }
+            else
+            {
+                /* 10^-k <= |v| < 2^(53+e): den stays below 2^58 */
+                if (-e > 52)
+                    goto recheck;   /* cannot happen: |v| >= 10^P */
+                num = (pgs_u128)m;
+                den <<= (-e);
+            }
+            q = num / den;
+            num = num % den;
+        }
+        if (q >= hi)
+            x += 1;
+        else if (q < lo)
+            x -= 1;
+        else
+            found = true;
+    }
+    if (!found)
+        goto recheck;
+    /* round to nearest, ties to even: 2*num <=> den without overflow */
+    if (num > den - num || (num == den - num && (q & 1)))
+        q += 1;
+    while (k > 0 && (q % 10) == 0)
+    {
+        q /= 10;
+        k--;
+    }
+    if (k < 0)
+    {
+        if (-k > 17)
+            goto recheck;           /* >= 10^(P-1+18): beyond 57 bits */
+        q *= pgs_pow10_u128(-k);
+        k = 0;
+    }
+    return pgs_numeric_make(errcode, neg, q, k);
+recheck:
+    STROM_SET_ERROR(errcode, StromError_CpuReCheck);
+    return r;
+}
+
+DEVFN pg_numeric_t
+pgfn_float8_numeric(cl_int *errcode, pg_float8_t a)
+{
+    pg_numeric_t r;
+
+    r.isnull = true;
+    r.value = 0;
+    if (a.isnull)
+        return r;
+    return pgs_float_to_numeric(errcode, a.value, 15);      /* DBL_DIG */
+}
+
+DEVFN pg_numeric_t
+pgfn_float4_numeric(cl_int *errcode, pg_float4_t a)
+{
+    pg_numeric_t r;
+
+    r.isnull = true;
+    r.value = 0;
+    if (a.isnull)
+        return r;
+    return pgs_float_to_numeric(errcode, (double)a.value, 6);   /* FLT_DIG */
+}
+
 /* numeric -> integer: round half away from zero (numeric.c numericvar_to_int8) */
 DEVFN cl_long
 pgs_numeric_to_long(cl_int *errcode, cl_ulong v, cl_long lo, cl_long hi, bool *isnull)

@@ -1,0 +1,218 @@
+/*
+ * kern_textlib.cuh - bpchar / text comparison of the device runtime (the
+ * counterpart of the reference's opencl_textlib.h; catalogue entries
+ * codegen.c:611-629).
+ *
+ * A text / bpchar value on the device is a pointer to the varlena image
+ * (1-byte or 4-byte header) inside the chunk or the kern_parambuf - the
+ * staged / de-formed value of a varlena column is the offset of the datum
+ * from the head of the chunk, as for numeric (kern_numeric.cuh).  Compressed
+ * and out-of-line (TOAST pointer) datums cannot be read here: the value reads
+ * as NULL and the row is flagged StromError_CpuReCheck.
+ *
+ * Comparison is bytewise on UNSIGNED bytes, i.e. PostgreSQL's result under
+ * the "C" collation (varstr_cmp: memcmp, then the shorter string first);
+ * equality is the same under every deterministic collation.  The planner
+ * half only offloads the ordering operators when the input collation is C
+ * (codegen.cpp).  bpchar ignores trailing blanks (bcTruelen).  The reference
+ * compares signed cl_char, which orders bytes >= 0x80 (every multi-byte UTF-8
+ * sequence) before ASCII - PostgreSQL does not, so that is not reproduced.
+ */
+#ifndef KERN_TEXTLIB_CUH
+#define KERN_TEXTLIB_CUH
+
+typedef struct {
+    const unsigned char *value;     /* varlena header */
+    bool        isnull;
+} pg_varlena_t;
+typedef pg_varlena_t    pg_text_t;
+typedef pg_varlena_t    pg_bpchar_t;
+
+/* VARDATA_ANY / VARSIZE_ANY_EXHDR of a little-endian varlena
+ * (opencl_common.h:459-475); false for compressed / external datums */
+DEVFN bool
+pgs_varlena_payload(const unsigned char *p, const unsigned char **data, cl_int *len)
+{
+    cl_uint     b0 = p[0];
+
+    if (b0 & 0x01)
+    {
+        if (b0 == 0x01)
+            return false;           /* VARATT_IS_1B_E: TOAST pointer */
+        *len = (cl_int)(b0 >> 1) - 1;
+        *data = p + 1;
+        return (*len >= 0);
+    }
+    if (b0 & 0x02)
+        return false;               /* VARATT_IS_4B_C: compressed in-line */
+    cl_uint     hdr = b0 | ((cl_uint)p[1] << 8) | ((cl_uint)p[2] << 16) | ((cl_uint)p[3] << 24);
+    *len = (cl_int)(hdr >> 2) - 4;
+    *data = p + 4;
+    return (*len >= 0);
+}
+
+DEVFN pg_varlena_t
+pgs_varlena_make(cl_int *errcode, const unsigned char *p)
+{
+    pg_varlena_t    r;
+    const unsigned char *data;
+    cl_int      len;
+
+    r.value = p;
+    r.isnull = false;
+    if (!pgs_varlena_payload(p, &data, &len))
+    {
+        r.value = NULL;
+        r.isnull = true;
+        STROM_SET_ERROR(errcode, StromError_CpuReCheck);
+    }
+    return r;
+}
+
+template <typename KDS>
+DEVFN pg_varlena_t
+pg_varlena_vref(const KDS &kds, const void *ktoast, cl_int *errcode,
+                cl_uint colidx, cl_uint rowidx)
+{
+    cl_uint     offset = 0;
+    bool        ok = kds.template fetch<cl_uint>(GPUPREAGG_INCOL_SLOT(colidx), rowidx, offset);
+
+    if (!ok || offset == 0)
+    {
+        pg_varlena_t r;
+        r.value = NULL;
+        r.isnull = true;
+        return r;
+    }
+    return pgs_varlena_make(errcode, (const unsigned char *)ktoast + offset);
+}
+
+DEVFN pg_varlena_t
+pg_varlena_param(const kern_parambuf *kparams, cl_int *errcode, cl_uint param_id)
+{
+    if (param_id < kparams->nparams && kparams->poffset[param_id] > 0)
+        return pgs_varlena_make(errcode, (const unsigned char *)kparams +
+                                kparams->poffset[param_id]);
+    pg_varlena_t r;
+    r.value = NULL;
+    r.isnull = true;
+    return r;
+}
+
+DEVFN pg_varlena_t
+pg_varlena_null(void)
+{
+    pg_varlena_t r;
+    r.value = NULL;
+    r.isnull = true;
+    return r;
+}
+
+#define pg_text_vref        pg_varlena_vref
+#define pg_bpchar_vref      pg_varlena_vref
+#define pg_text_param       pg_varlena_param
+#define pg_bpchar_param     pg_varlena_param
+#define pg_text_null        pg_varlena_null
+#define pg_bpchar_null      pg_varlena_null
+
+#define PGS_VARLENA_NULLTEST_TEMPLATE(NAME)                         \
+    DEVFN pg_bool_t                                                 \
+    pgfn_##NAME##_isnull(cl_int *errcode, pg_varlena_t arg)         \
+    {                                                               \
+        pg_bool_t result;                                           \
+        result.isnull = false;                                      \
+        result.value = arg.isnull;                                  \
+        return result;                                              \
+    }                                                               \
+    DEVFN pg_bool_t                                                 \
+    pgfn_##NAME##_isnotnull(cl_int *errcode, pg_varlena_t arg)      \
+    {                                                               \
+        pg_bool_t result;                                           \
+        result.isnull = false;                                      \
+        result.value = !arg.isnull;                                 \
+        return result;                                              \
+    }
+PGS_VARLENA_NULLTEST_TEMPLATE(text)
+PGS_VARLENA_NULLTEST_TEMPLATE(bpchar)
+
+/* memcmp order, the shorter string first on a common prefix */
+DEVFN cl_int
+pgs_bytes_compare(const unsigned char *s1, cl_int len1,
+                  const unsigned char *s2, cl_int len2)
+{
+    cl_int      len = (len1 < len2 ? len1 : len2);
+
+    for (cl_int i = 0; i < len; i++)
+    {
+        cl_uint     c1 = s1[i], c2 = s2[i];
+
+        if (c1 != c2)
+            return (c1 < c2 ? -1 : 1);
+    }
+    return (len1 == len2 ? 0 : (len1 < len2 ? -1 : 1));
+}
+
+DEVFN cl_int
+pgs_text_compare(pg_varlena_t arg1, pg_varlena_t arg2, bool ignore_trailing_blanks)
+{
+    const unsigned char *s1, *s2;
+    cl_int      len1 = 0, len2 = 0;
+
+    /* both were checked by pgs_varlena_make */
+    pgs_varlena_payload(arg1.value, &s1, &len1);
+    pgs_varlena_payload(arg2.value, &s2, &len2);
+    if (ignore_trailing_blanks)
+    {
+        while (len1 > 0 && s1[len1 - 1] == ' ')
+            len1--;
+        while (len2 > 0 && s2[len2 - 1] == ' ')
+            len2--;
+    }
+    return pgs_bytes_compare(s1, len1, s2, len2);
+}
+
+#define PGS_TEXT_COMPARE_TEMPLATE(FNAME,TYPE,BLANKS,OPER)                   \
+    DEVFN pg_bool_t                                                         \
+    pgfn_##FNAME(cl_int *errcode, pg_##TYPE##_t arg1, pg_##TYPE##_t arg2)   \
+    {                                                                       \
+        pg_bool_t   result;                                                 \
+                                                                            \
+        result.isnull = (arg1.isnull | arg2.isnull);                        \
+        result.value = (cl_bool)(!result.isnull &&                          \
+                                 pgs_text_compare(arg1, arg2, BLANKS) OPER 0); \
+        return result;                                                      \
+    }
+PGS_TEXT_COMPARE_TEMPLATE(bpchareq, bpchar, true, ==)
+PGS_TEXT_COMPARE_TEMPLATE(bpcharne, bpchar, true, !=)
+PGS_TEXT_COMPARE_TEMPLATE(bpcharlt, bpchar, true, <)
+PGS_TEXT_COMPARE_TEMPLATE(bpcharle, bpchar, true, <=)
+PGS_TEXT_COMPARE_TEMPLATE(bpchargt, bpchar, true, >)
+PGS_TEXT_COMPARE_TEMPLATE(bpcharge, bpchar, true, >=)
+PGS_TEXT_COMPARE_TEMPLATE(texteq, text, false, ==)
+PGS_TEXT_COMPARE_TEMPLATE(textne, text, false, !=)
+PGS_TEXT_COMPARE_TEMPLATE(text_lt, text, false, <)
+PGS_TEXT_COMPARE_TEMPLATE(text_le, text, false, <=)
+PGS_TEXT_COMPARE_TEMPLATE(text_gt, text, false, >)
+PGS_TEXT_COMPARE_TEMPLATE(text_ge, text, false, >=)
+
+DEVFN pg_int4_t
+pgfn_bpcharcmp(cl_int *errcode, pg_bpchar_t arg1, pg_bpchar_t arg2)
+{
+    pg_int4_t   result;
+
+    result.isnull = (arg1.isnull | arg2.isnull);
+    result.value = (result.isnull ? 0 : pgs_text_compare(arg1, arg2, true));
+    return result;
+}
+
+DEVFN pg_int4_t
+pgfn_text_cmp(cl_int *errcode, pg_text_t arg1, pg_text_t arg2)
+{
+    pg_int4_t   result;
+
+    result.isnull = (arg1.isnull | arg2.isnull);
+    result.value = (result.isnull ? 0 : pgs_text_compare(arg1, arg2, false));
+    return result;
+}
+
+#endif  /* KERN_TEXTLIB_CUH */

@@ -13,11 +13,22 @@ import re
 
 SQLNAME = {"bool": "boolean", "int2": "smallint", "int4": "integer", "int8": "bigint",
            "float4": "real", "float8": "double precision", "numeric": "numeric",
-           "date": "date", "text": "text"}
+           "date": "date", "text": "text", "time": "time without time zone",
+           "timestamp": "timestamp without time zone", "bpchar": "character"}
 _INTS = ("int2", "int4", "int8")
 _FLOATS = ("float4", "float8")
 _OPNAME = {"=": "eq", "<>": "ne", "<": "lt", "<=": "le", ">": "gt", ">=": "ge",
            "+": "pl", "-": "mi", "*": "mul", "/": "div", "%": "mod"}
+
+
+_CMP = ("eq", "ne", "lt", "le", "gt", "ge")
+# pg_operator rows of the date / time arithmetic the device runs
+_DATE_OPS = {("date", "int4", "pl"): ("date_pli", "date"),
+             ("date", "int4", "mi"): ("date_mii", "date"),
+             ("date", "date", "mi"): ("date_mi", "int4"),
+             ("int4", "date", "pl"): ("integer_pl_date", "date"),
+             ("date", "time", "pl"): ("datetime_pl", "timestamp"),
+             ("time", "date", "pl"): ("timedate_pl", "timestamp")}
 
 
 def Var(attno, typ):
@@ -75,8 +86,16 @@ def _opfunc(op, lt, rt):
         res = "float8" if "float8" in (lt, rt) else "float4"
     elif lt == rt == "bool":
         name, res = "bool" + sfx, "bool"
-    elif lt == rt == "date":
-        name, res = "date_" + sfx, "date"
+    elif lt == rt and lt in ("date", "time", "timestamp") and sfx in _CMP:
+        name, res = lt + "_" + sfx, "bool"
+    elif (lt, rt) in (("date", "timestamp"), ("timestamp", "date")) and sfx in _CMP:
+        name, res = "%s_%s_%s" % (lt, sfx, rt), "bool"
+    elif (lt, rt, sfx) in _DATE_OPS:
+        name, res = _DATE_OPS[(lt, rt, sfx)]
+    elif lt == rt == "text" and sfx in _CMP:
+        name, res = ("text" + sfx if sfx in ("eq", "ne") else "text_" + sfx), "bool"
+    elif lt == rt == "bpchar" and sfx in _CMP:
+        name, res = "bpchar" + sfx, "bool"
     elif lt == rt == "numeric":
         name = {"eq": "numeric_eq", "ne": "numeric_ne", "lt": "numeric_lt",
                 "le": "numeric_le", "gt": "numeric_gt", "ge": "numeric_ge",
@@ -89,10 +108,11 @@ def _opfunc(op, lt, rt):
     return name, res
 
 
-def Op(op, left, right):
+def Op(op, left, right, collation=None):
     """Binary operator with PostgreSQL-like resolution: exact match among the
     cross-type integer / float operators, else promote int -> float8 /
-    numeric."""
+    numeric.  `collation`: name of the input collation of a text operator
+    (what the PostgreSQL glue resolves inputcollid to)."""
     lt, rt = etype(left), etype(right)
     name, res = _opfunc(op, lt, rt)
     if name is None:
@@ -109,8 +129,11 @@ def Op(op, left, right):
         name, res = _opfunc(op, lt, rt)
         if name is None:
             raise TypeError("operator does not exist: %s %s %s" % (lt, op, rt))
-    return {"node": "OpExpr", "opname": op, "opfuncname": name,
+    node = {"node": "OpExpr", "opname": op, "opfuncname": name,
             "opresulttype": res, "args": [left, right]}
+    if collation is not None:
+        node["inputcollid"] = collation
+    return node
 
 
 def And(*args):

@@ -1,0 +1,329 @@
+"""CPU: the date/time, text and float->numeric device runtime
+(pg_strom_b200/csrc/kern_timelib.cuh, kern_textlib.cuh, pgs_float_to_numeric
+in kern_numeric.cuh - the counterparts of the reference's opencl_timelib.h,
+opencl_textlib.h and the float casts of its numeric catalogue,
+codegen.c:519-629) compiled with g++ through a shim and checked against the
+oracle's restatement of PostgreSQL's functions (oracle/pg_typelib.py); plus:
+queries that use them plan as GpuPreAgg and their generated device programs
+compile for sm_100a (NVRTC, no GPU needed)."""
+import ctypes as C
+import os
+import random
+import struct
+import subprocess
+from decimal import Decimal
+
+import pytest
+
+from oracle import pg_typelib as T
+from pg_strom_b200 import gpupreagg as gp
+from pg_strom_b200 import pgplan as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CPU_RECHECK = 2
+GUCS = {"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on"}
+
+
+@pytest.fixture(scope="module")
+def shim(lib):
+    out = os.path.join(HERE, "native", "_typelib_shim.so")
+    src = os.path.join(HERE, "native", "typelib_host_shim.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared",
+                    "-I", os.path.join(ROOT, "include"),
+                    "-I", os.path.join(ROOT, "pg_strom_b200", "csrc"),
+                    "-o", out, src], check=True)
+    so = C.CDLL(out)
+    so.shim_time_cast.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+    so.shim_time_binop.argtypes = [C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int)]
+    so.shim_text_op.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p,
+                                C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    so.shim_float_numeric.argtypes = [C.c_double, C.c_int, C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_int)]
+    return so
+
+
+def _expect(fn, *args):
+    """-> ("ok", value|None) or ("recheck", None)."""
+    try:
+        return "ok", fn(*args)
+    except T.PgRangeError:
+        return "recheck", None
+
+
+def _check(err, isnull, out, exp, what):
+    kind, val = exp
+    if kind == "recheck":
+        assert err == CPU_RECHECK and isnull, what
+    else:
+        assert err == 0, what
+        if val is None:
+            assert isnull, what
+        else:
+            assert not isnull and out == val, (what, out, val)
+
+
+DATES = [T.DATE_NOBEGIN, T.DATE_NOEND, T.DATE_NOBEGIN + 1, T.DATE_NOEND - 1, 0, 1, -1,
+         7305, -730119, 106751991, 106751992, -106751991, -106751992, -2451545, -2451546,
+         2 ** 31 - 2451545 - 1]
+STAMPS = [T.DT_NOBEGIN, T.DT_NOEND, T.DT_NOBEGIN + 1, T.DT_NOEND - 1, 0, 1, -1,
+          T.USECS_PER_DAY, T.USECS_PER_DAY - 1, -T.USECS_PER_DAY, -T.USECS_PER_DAY - 1,
+          631152000000000, -211813488000000000, -211813488000000001,
+          -2451545 * T.USECS_PER_DAY, -2451545 * T.USECS_PER_DAY - 1]
+
+
+def test_julian_identity():
+    """The device turns a timestamp into a date with one floor division; the
+    oracle goes through j2date / date2j like PostgreSQL: same thing."""
+    rng = random.Random(1)
+    for jd in [0, 1, 59, 60, 61, 365, 366, 1721060, 2451545, T.INT_MAX - 1, T.INT_MAX] + \
+            [rng.randrange(0, T.INT_MAX) for _ in range(20000)]:
+        assert T.date2j(*T.j2date(jd)) == jd
+
+
+def test_time_casts(shim):
+    rng = random.Random(2)
+    out, isnull = C.c_int64(), C.c_int()
+    stamps = STAMPS + [rng.randrange(-2 ** 63, 2 ** 63) for _ in range(3000)] + \
+        [rng.randrange(-10 ** 17, 10 ** 17) for _ in range(3000)]
+    for ts in stamps:
+        err = shim.shim_time_cast(0, ts, C.byref(out), C.byref(isnull))
+        _check(err, isnull.value, out.value, _expect(T.timestamp_date, ts), ("timestamp_date", ts))
+        err = shim.shim_time_cast(1, ts, C.byref(out), C.byref(isnull))
+        _check(err, isnull.value, out.value, _expect(T.timestamp_time, ts), ("timestamp_time", ts))
+    dates = DATES + [rng.randrange(-2 ** 31, 2 ** 31) for _ in range(3000)] + \
+        [rng.randrange(-10 ** 6, 10 ** 6) for _ in range(1000)]
+    for d in dates:
+        err = shim.shim_time_cast(2, d, C.byref(out), C.byref(isnull))
+        _check(err, isnull.value, out.value, _expect(T.date_timestamp, d), ("date_timestamp", d))
+
+
+def test_time_operators(shim):
+    rng = random.Random(3)
+    out, isnull = C.c_int64(), C.c_int()
+    ints = [0, 1, -1, 2 ** 31 - 1, -2 ** 31, 365, -365]
+    times = [0, 1, T.USECS_PER_DAY - 1, 43200000000]
+
+    def pick(pool, lo, hi):
+        return rng.choice(pool) if rng.random() < 0.4 else rng.randrange(lo, hi)
+
+    cmp_ops = {"eq": lambda c: c == 0, "ne": lambda c: c != 0, "lt": lambda c: c < 0,
+               "le": lambda c: c <= 0, "gt": lambda c: c > 0, "ge": lambda c: c >= 0}
+    for _ in range(6000):
+        d = pick(DATES, -2 ** 31, 2 ** 31)
+        d2 = pick(DATES, -2 ** 31, 2 ** 31)
+        n = pick(ints, -2 ** 31, 2 ** 31)
+        t = pick(times, 0, T.USECS_PER_DAY)
+        ts = pick(STAMPS, -2 ** 63, 2 ** 63)
+        if rng.random() < 0.3:      # a timestamp right at a date: equality cases
+            try:
+                ts = T.date_timestamp(d)
+            except T.PgRangeError:
+                pass
+        cases = [(0, d, n, T.date_pli, (d, n)), (1, d, n, T.date_mii, (d, n)),
+                 (2, d, d2, T.date_mi, (d, d2)), (3, d, t, T.datetime_pl, (d, t)),
+                 (4, n, d, T.date_pli, (d, n)), (5, t, d, T.datetime_pl, (d, t)),
+                 (6, d, ts, T.date_cmp_timestamp, (d, ts)),
+                 (7, ts, d, T.timestamp_cmp_date, (ts, d))]
+        for i, (name, test) in enumerate(cmp_ops.items()):
+            cases.append((10 + i, d, ts,
+                          (lambda a, b, test=test: int(test(T.date_cmp_timestamp(a, b)))), (d, ts)))
+            cases.append((20 + i, ts, d,
+                          (lambda a, b, test=test: int(test(T.timestamp_cmp_date(a, b)))), (ts, d)))
+        for fn, a, b, ofn, oargs in cases:
+            err = shim.shim_time_binop(fn, a, b, C.byref(out), C.byref(isnull))
+            _check(err, isnull.value, out.value, _expect(ofn, *oargs), (fn, a, b))
+
+
+def test_text_compare(shim):
+    rng = random.Random(4)
+    out, isnull = C.c_int(), C.c_int()
+    alphabet = [b"a", b"b", b"A", b" ", b"z", b"\x7f", b"\x80", b"\xc3\xa9", b"\xff", b"0"]
+
+    def rand_text():
+        s = b"".join(rng.choice(alphabet) for _ in range(rng.choice([0, 1, 2, 3, 5, 8, 130])))
+        if rng.random() < 0.4:
+            s += b" " * rng.randrange(0, 4)
+        return s
+
+    ops = [lambda c: c == 0, lambda c: c != 0, lambda c: c < 0, lambda c: c <= 0,
+           lambda c: c > 0, lambda c: c >= 0]
+    for _ in range(4000):
+        a = rand_text()
+        b = rand_text() if rng.random() < 0.6 else a + rng.choice([b"", b" ", b"  ", b"a"])
+        ia = T.varlena(a, short=None if rng.random() < 0.5 else False)
+        ib = T.varlena(b, short=None if rng.random() < 0.5 else False)
+        for bp, cmpfn in ((0, T.text_cmp), (1, T.bpchar_cmp)):
+            c = cmpfn(a, b)
+            for fn in range(6):
+                err = shim.shim_text_op(fn, bp, ia, ib, C.byref(out), C.byref(isnull))
+                assert err == 0 and not isnull.value
+                assert bool(out.value) == ops[fn](c), (a, b, bp, fn)
+            err = shim.shim_text_op(6, bp, ia, ib, C.byref(out), C.byref(isnull))
+            assert err == 0 and not isnull.value and out.value == c, (a, b, bp)
+    # compressed (4-byte header, bit 1) and out-of-line (0x01) datums: host only
+    ok = T.varlena(b"abc")
+    for bad in (bytes([0x02 | (20 << 2), 0, 0, 0]) + b"x" * 16, bytes([0x01, 18]) + b"p" * 16):
+        err = shim.shim_text_op(0, 0, bad, ok, C.byref(out), C.byref(isnull))
+        assert err == CPU_RECHECK and isnull.value
+
+
+def _unpack_numeric(v):
+    exp = v >> 58
+    if exp >= 32:
+        exp -= 64
+    mant = v & ((1 << 57) - 1)
+    d = Decimal(mant).scaleb(exp)
+    return (-d if (v >> 57) & 1 else d), -exp
+
+
+def test_float_to_numeric(shim):
+    rng = random.Random(5)
+    out, isnull = C.c_uint64(), C.c_int()
+    f4 = lambda x: struct.unpack("f", struct.pack("f", x))[0]
+    vals = [0.0, -0.0, 1.0, -1.0, 0.1, 0.5, 1.5, 2.5, 1e15, 1e16, 123456789012345.0,
+            1234567890123456.0, 9.999999999999995e-5, 0.30000000000000004, 1e-5, 1e-17,
+            1e-18, 1e-19, 1e-30, 5e-324, 1e22, 1e23, 1.5e17, 1e38, 1.7e38, 1e39, 1e300,
+            99999999999999.95, 999999999999999.5, 0.1 + 0.2, 2.0 ** 53, 2.0 ** 57, 2.0 ** 60,
+            float("nan"), float("inf"), float("-inf"), 8.5, 0.000123456789012345678]
+    for _ in range(20000):
+        kind = rng.random()
+        if kind < 0.3:
+            vals.append(rng.uniform(-1000, 1000))
+        elif kind < 0.5:
+            vals.append(rng.randrange(-10 ** 9, 10 ** 9) / 10.0 ** rng.randrange(0, 12))
+        elif kind < 0.7:
+            vals.append(struct.unpack("d", struct.pack("Q", rng.randrange(0, 2 ** 64)))[0])
+        else:
+            vals.append(rng.uniform(-1, 1) * 10.0 ** rng.randrange(-25, 45))
+    handled = 0
+    for v in vals:
+        for is_f4, nd in ((0, 15), (1, 6)):
+            x = f4(v) if is_f4 else v
+            if is_f4 and (x != x or abs(x) == float("inf")) and v == v and abs(v) != float("inf"):
+                continue                    # does not fit a float4: not this function's input
+            err = shim.shim_float_numeric(x, is_f4, C.byref(out), C.byref(isnull))
+            exp = T.float_numeric(x, nd)
+            if err == CPU_RECHECK:
+                assert isnull.value
+                # the device may only decline what is outside its ranges
+                if exp is not None:
+                    d, dscale = exp
+                    mant = abs(int(d.scaleb(dscale)))
+                    small = x != 0 and abs(x) < (1e-17 if not is_f4 else 1e-26)
+                    assert mant > (1 << 57) - 2 or dscale > 32 or small or abs(x) >= 2.0 ** 127, x
+                continue
+            assert err == 0 and not isnull.value, x
+            assert exp is not None, x
+            got, gscale = _unpack_numeric(out.value)
+            assert got == exp[0] and gscale == exp[1], (x, is_f4, got, gscale, exp)
+            handled += 1
+    assert handled > 20000
+
+
+# ---- planner + NVRTC ------------------------------------------------------
+EVENTS = P.Table("events", [("d", "date"), ("ts", "timestamp"), ("tm", "time"),
+                            ("s", "text"), ("c", "bpchar"), ("k", "int4"), ("v", "int8"),
+                            ("f", "float8")])
+
+
+def typelib_queries():
+    """(name, plan) of queries exercising the date/time, text and
+    float->numeric catalogue entries in WHERE, FILTER-less aggregate arguments
+    and CASE."""
+    t = EVENTS
+    d, ts, tm, s, c, k, v, f = (t.col(n) for n in ("d", "ts", "tm", "s", "c", "k", "v", "f"))
+    cnt = (P.Agg("count", star=True), "count")
+    sumv = (P.Agg("sum", [P.Cast(v, "numeric")]), "sum")
+    q = []
+    q.append(("date_arith", P.make_agg_plan(
+        t, [(k, "k"), cnt, (P.Agg("max", [P.Op("-", d, P.Const("date", 7000))]), "max")],
+        group_by=["k"], num_groups=16,
+        where=[P.Op(">", P.Op("+", d, P.Const("int4", 30)), P.Const("date", 7400)),
+               P.Op("<=", P.Op("-", d, P.Const("int4", 5)), P.Const("date", 7700))])))
+    q.append(("date_vs_timestamp", P.make_agg_plan(
+        t, [cnt, (P.Agg("min", [v]), "min")],
+        where=[P.Op("<", d, ts), P.Op(">=", ts, P.Const("date", 7300)),
+               P.Op("<>", P.Cast(ts, "date"), d)])))
+    q.append(("timestamp_parts", P.make_agg_plan(
+        t, [(k, "k"), cnt], group_by=["k"], num_groups=16,
+        where=[P.Op("<", P.Cast(ts, "time"), tm),
+               P.Op(">", P.Op("+", d, tm), ts),
+               P.Op("=", P.Cast(d, "timestamp"), P.Op("+", P.Cast(ts, "date"),
+                                                      P.Const("time", 0)))])))
+    q.append(("text_eq", P.make_agg_plan(
+        t, [(k, "k"), cnt, (P.Agg("sum", [f]), "sum")], group_by=["k"], num_groups=16,
+        where=[P.Op("=", s, P.Const("text", "bbb"))])))
+    q.append(("text_order", P.make_agg_plan(
+        t, [cnt, (P.Agg("max", [v]), "max")],
+        where=[P.Op(">=", s, P.Const("text", "ccc"), collation="C"),
+               P.Op("<", s, P.Const("text", "xx"), collation="C"),
+               P.Op("<>", c, P.Const("bpchar", "ab   "))])))
+    q.append(("bpchar_eq", P.make_agg_plan(
+        t, [(k, "k"), cnt], group_by=["k"], num_groups=16,
+        where=[P.Op("=", c, P.Const("bpchar", "ab"))])))
+    q.append(("text_isnull_case", P.make_agg_plan(
+        t, [cnt, (P.Agg("avg", [P.Case([(P.Op("=", s, P.Const("text", "aaa")), v)],
+                                       P.Const("int8", 0), "int8")]), "avg")],
+        where=[P.IsNull(s, notnull=True)])))
+    q.append(("float_numeric", P.make_agg_plan(
+        t, [(k, "k"), (P.Agg("sum", [P.Cast(f, "numeric")]), "sum"),
+            (P.Agg("max", [P.Cast(f, "numeric")]), "max"), sumv],
+        group_by=["k"], num_groups=16)))
+    return q
+
+
+@pytest.mark.parametrize("name", [n for n, _ in typelib_queries()])
+def test_queries_plan_and_compile(lib, name):
+    plan_tree = dict(typelib_queries())[name]
+    plan = gp.Plan(plan_tree, gucs=GUCS)
+    try:
+        assert plan.num_gpupreagg == 1, plan.reject_reason
+        src = plan.kernel_source()
+        if name.startswith(("date", "timestamp")):
+            assert '#include "kern_timelib.cuh"' in src
+        if name.startswith(("text", "bpchar")):
+            assert '#include "kern_textlib.cuh"' in src
+        prog = plan.build_program()         # NVRTC for sm_100a
+        plan.lib.pgs_program_release(prog)
+    finally:
+        plan.free()
+
+
+def test_text_ordering_needs_c_collation(lib):
+    t = EVENTS
+    tree = P.make_agg_plan(t, [(P.Agg("count", star=True), "count")],
+                           where=[P.Op("<", t.col("s"), P.Const("text", "m"),
+                                       collation="en_US.utf8")])
+    plan = gp.Plan(tree, gucs=GUCS)
+    try:
+        # the qual stays on the scan node (PostgreSQL's executor filters the
+        # rows); GpuPreAgg aggregates what the scan returns
+        assert plan.num_gpupreagg == 1, plan.reject_reason
+        assert "#define GPUPREAGG_HAS_QUAL 0" in plan.kernel_source()
+        assert "kern_textlib" not in plan.kernel_source()
+    finally:
+        plan.free()
+    # equality does not depend on the collation
+    tree = P.make_agg_plan(t, [(P.Agg("count", star=True), "count")],
+                           where=[P.Op("=", t.col("s"), P.Const("text", "m"),
+                                       collation="en_US.utf8")])
+    plan = gp.Plan(tree, gucs=GUCS)
+    try:
+        assert plan.num_gpupreagg == 1, plan.reject_reason
+        assert "#define GPUPREAGG_HAS_QUAL 1" in plan.kernel_source()
+    finally:
+        plan.free()
+
+
+def test_text_group_key_is_not_offloaded(lib):
+    t = EVENTS
+    tree = P.make_agg_plan(t, [(t.col("s"), "s"), (P.Agg("count", star=True), "count")],
+                           group_by=["s"], num_groups=26)
+    plan = gp.Plan(tree, gucs=GUCS)
+    try:
+        assert plan.num_gpupreagg == 0
+        assert "not supported" in plan.reject_reason
+    finally:
+        plan.free()
