@@ -112,6 +112,73 @@ _CMP = {"eq": lambda c: c == 0, "ne": lambda c: c != 0, "lt": lambda c: c < 0,
         "le": lambda c: c <= 0, "gt": lambda c: c > 0, "ge": lambda c: c >= 0}
 
 
+# float.c: dsqrt, dexp, dlog1, dlog10, dcbrt, dceil ..., dacos ... (9.4 era)
+def _domain(check, msg, fn, inf_ok=None, zero_ok=None):
+    def f(x):
+        if not math.isnan(x) and check(x):
+            raise PgError(msg)
+        try:
+            r = fn(x)
+        except OverflowError:
+            r = math.inf
+        except ValueError:
+            r = math.nan
+        if inf_ok is not None:
+            check_float8(r, inf_ok(x), zero_ok(x))
+        return r
+    return f
+
+
+def _dpow(a, b):
+    fl = b if (math.isinf(b) or math.isnan(b)) else float(math.floor(b))    # C floor()
+    if (a == 0.0 and b < 0.0) or (a < 0.0 and (fl != b)):
+        raise PgError("invalid argument for power function")
+    try:
+        r = math.pow(a, b)
+    except OverflowError:
+        # |result| too large; odd negative powers of a negative base are negative
+        neg = a < 0.0 and not math.isinf(b) and int(b) % 2 == 1
+        r = -math.inf if neg else math.inf
+    check_float8(r, math.isinf(a) or math.isinf(b), a == 0.0)
+    return r
+
+
+def _scale(factor):
+    def f(x):
+        r = x * factor
+        check_float8(r, math.isinf(x), x == 0.0)
+        return r
+    return f
+
+
+def _roundf(fn):
+    return lambda x: x if (math.isnan(x) or math.isinf(x)) else float(fn(x))
+
+
+_never = lambda x: False
+_MATH = {
+    "sqrt": _domain(lambda x: x < 0, "cannot take square root of a negative number", math.sqrt),
+    "exp": _domain(_never, "", math.exp, math.isinf, _never),
+    "ln": _domain(lambda x: x <= 0, "cannot take logarithm of zero or a negative number", math.log),
+    "log": _domain(lambda x: x <= 0, "cannot take logarithm of zero or a negative number", math.log10),
+    "cbrt": _domain(_never, "", lambda x: math.copysign(abs(x) ** (1.0 / 3.0), x)),
+    "acos": _domain(lambda x: abs(x) > 1, "input is out of range", math.acos),
+    "asin": _domain(lambda x: abs(x) > 1, "input is out of range", math.asin),
+    "atan": math.atan, "atan2": math.atan2,
+    "cos": _domain(math.isinf, "input is out of range", math.cos),
+    "sin": _domain(math.isinf, "input is out of range", math.sin),
+    "tan": _domain(math.isinf, "input is out of range", math.tan),
+    "ceil": _roundf(math.ceil), "floor": _roundf(math.floor), "trunc": _roundf(math.trunc),
+    "round": _roundf(lambda x: float.__round__(x)),      # rint(): half to even
+    "sign": lambda x: (x > 0) - (x < 0) + 0.0,
+    "degrees": _scale(180.0 / math.pi), "radians": _scale(math.pi / 180.0),
+    "power": _dpow, "pow": _dpow, "dpow": _dpow, "pi": lambda: math.pi,
+}
+for _a, _b in (("dsqrt", "sqrt"), ("dexp", "exp"), ("dlog1", "ln"), ("dlog10", "log"),
+               ("dcbrt", "cbrt"), ("ceiling", "ceil"), ("dround", "round"), ("dtrunc", "trunc")):
+    _MATH[_a] = _MATH[_b]
+
+
 def _call(name, argtypes, rettype, args):
     """strict functions: NULL in -> NULL out (handled by the caller)."""
     fn = pg_typelib.lookup(name, argtypes)
@@ -136,11 +203,12 @@ def _call(name, argtypes, rettype, args):
             raise PgError(_INT_RANGE[rettype][2])
         return r
     if name.endswith("abs") or name == "abs":
-        return abs(args[0])
-    if name in ("sqrt", "dsqrt"):
-        return math.sqrt(args[0])
-    if name == "floor":
-        return float(math.floor(args[0]))
+        r = abs(args[0])
+        if rettype in _INT_RANGE and r > _INT_RANGE[rettype][1]:
+            raise PgError(_INT_RANGE[rettype][2])       # int2abs / int4abs / int8abs
+        return r
+    if name in _MATH:
+        return _MATH[name](*args)
     raise NotImplementedError("oracle: function %s(%s)" % (name, ",".join(argtypes)))
 
 

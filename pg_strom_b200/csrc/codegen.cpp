@@ -214,6 +214,9 @@ build_devfunc_catalog(void)
     cat("log", {"float8"}, "f:log10");
     cat("dlog10", {"float8"}, "f:log10");
     cat("pi", {}, "m/F:dpi");
+    cat("sign", {"float8"}, "m/F:dsign");
+    cat("degrees", {"float8"}, "m/F:degrees");
+    cat("radians", {"float8"}, "m/F:radians");
     cat("power", {"float8", "float8"}, "m/F:dpow");
     cat("pow", {"float8", "float8"}, "m/F:dpow");
     cat("dpow", {"float8", "float8"}, "m/F:dpow");
@@ -386,11 +389,44 @@ devfunc_setup_func_decl(DevFunc *entry, const std::string &builtin, bool has_ali
     for (size_t i = 0; i < entry->func_args.size(); i++)
         s << (i ? " | " : "") << "arg" << (i + 1) << ".isnull";
     s << ";\n"
-      << "    if (!result.isnull)\n"
-      << "        result.value = (" << entry->func_rettype->type_base << ") " << builtin << "(";
+      << "    if (!result.isnull)\n";
+    /* PostgreSQL's float.c raises an error outside the function's domain
+     * (dsqrt, dlog1, dlog10, dacos, dasin: "cannot take ... / input is out of
+     * range"; dcos, dsin, dtan: errno on an infinite input) and on overflow /
+     * underflow of dexp (CHECKFLOATVAL).  The CUDA built-ins return NaN / Inf /
+     * 0 instead: such rows are left to the host (StromError_CpuReCheck),
+     * which raises the error PostgreSQL would have raised. */
+    static const struct { const char *builtin, *pre, *post; } domain[] = {
+        { "sqrt",  "arg1.value < 0.0", NULL },
+        { "log",   "arg1.value <= 0.0", NULL },
+        { "log10", "arg1.value <= 0.0", NULL },
+        { "acos",  "fabs(arg1.value) > 1.0", NULL },
+        { "asin",  "fabs(arg1.value) > 1.0", NULL },
+        { "cos",   "isinf(arg1.value)", NULL },
+        { "sin",   "isinf(arg1.value)", NULL },
+        { "tan",   "isinf(arg1.value)", NULL },
+        { "exp",   NULL, "CHECKFLOATVAL(result.value, isinf(arg1.value), false)" },
+        { "cbrt",  NULL, "CHECKFLOATVAL(result.value, isinf(arg1.value), arg1.value == 0.0)" },
+    };
+    const char *pre = NULL, *post = NULL;
+    for (auto &d : domain)
+        if (builtin == d.builtin)
+        { pre = d.pre; post = d.post; }
+    s << "    {\n";
+    if (pre)
+        s << "        if (" << pre << ")\n"
+          << "        {\n"
+          << "            PGS_MATH_FAIL(result);\n"
+          << "            return result;\n"
+          << "        }\n";
+    s << "        result.value = (" << entry->func_rettype->type_base << ") " << builtin << "(";
     for (size_t i = 0; i < entry->func_args.size(); i++)
         s << (i ? ", " : "") << "arg" << (i + 1) << ".value";
-    s << ");\n"
+    s << ");\n";
+    if (post)
+        s << "        if (" << post << ")\n"
+          << "            PGS_MATH_FAIL(result);\n";
+    s << "    }\n"
       << "    return result;\n"
       << "}\n";
     entry->func_decl = s.str();

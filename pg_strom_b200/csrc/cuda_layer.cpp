@@ -147,11 +147,11 @@ nvrtc_build(pgs_program *prog)
 {
     nvrtcProgram nprog;
     const char *headers[] = { pgs_hdr_pgstrom_kds_h, pgs_hdr_kern_shared_h,
-                              pgs_hdr_kern_common_cuh, pgs_hdr_kern_numeric_cuh,
-                              pgs_hdr_kern_timelib_cuh, pgs_hdr_kern_textlib_cuh,
+                              pgs_hdr_kern_common_cuh, pgs_hdr_kern_mathlib_cuh,
+                              pgs_hdr_kern_numeric_cuh, pgs_hdr_kern_timelib_cuh, pgs_hdr_kern_textlib_cuh,
                               pgs_hdr_kern_gpupreagg_cuh };
     const char *names[] = { "pgstrom_kds.h", "kern_shared.h", "kern_common.cuh",
-                            "kern_numeric.cuh", "kern_timelib.cuh", "kern_textlib.cuh",
+                            "kern_mathlib.cuh", "kern_numeric.cuh", "kern_timelib.cuh", "kern_textlib.cuh",
                             "kern_gpupreagg.cuh" };
     std::string d_warps = "-DGPUPREAGG_CONSUMER_WARPS=" +
         std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "16");
@@ -219,6 +219,7 @@ pgs_program_build(const char *kern_source, int extra_flags,
      * pick up stale binaries from the on-disk cache */
     crc = crc32_buf(crc, pgs_hdr_kern_gpupreagg_cuh, strlen(pgs_hdr_kern_gpupreagg_cuh));
     crc = crc32_buf(crc, pgs_hdr_kern_common_cuh, strlen(pgs_hdr_kern_common_cuh));
+    crc = crc32_buf(crc, pgs_hdr_kern_mathlib_cuh, strlen(pgs_hdr_kern_mathlib_cuh));
     crc = crc32_buf(crc, pgs_hdr_kern_numeric_cuh, strlen(pgs_hdr_kern_numeric_cuh));
     if (extra_flags & DEVFUNC_NEEDS_TIMELIB)
         crc = crc32_buf(crc, pgs_hdr_kern_timelib_cuh, strlen(pgs_hdr_kern_timelib_cuh));

@@ -165,3 +165,48 @@ def test_date_beyond_timestamp_range_is_rechecked(cuda):
     assert len(wild) > 20
     assert recheck == wild
     check(desc, node, device_rows, rows)
+
+
+def test_math_domain_errors_are_rechecked(cuda):
+    """sqrt() of a negative number / ln() of zero raise in PostgreSQL: the
+    generated wrappers flag those rows CpuReCheck, all other rows are
+    filtered and aggregated on the device (sqrt is correctly rounded on both
+    sides; ln is only compared far away from the threshold)."""
+    from test_mathlib_device_code import MATHT, _fn
+    rng = random.Random(21)
+    rows = []
+    for i in range(5000):
+        x = rng.choice([rng.randrange(-50, 4000) / 8.0, 0.0, 16.0, 9.0, 2.0 ** 40])
+        rows.append((None if rng.random() < 0.05 else x, rng.randrange(0, 7)))
+    x, k = MATHT.col("x"), MATHT.col("k")
+    tree = P.make_agg_plan(
+        MATHT, [(k, "k"), (P.Agg("count", star=True), "count"), (P.Agg("sum", [x]), "sum")],
+        group_by=["k"], num_groups=8,
+        where=[P.Op(">=", _fn("sqrt", x), P.Const("float8", "3")),
+               P.Op("<", _fn("ln", x), P.Const("float8", "20.5"))])
+    plan = gp.Plan(tree, gucs=GUCS)
+    try:
+        assert plan.num_gpupreagg == 1, plan.reject_reason
+        desc = plan.describe()
+        node = find_node(plan.tree())
+        coltypes = [t for _, t in MATHT.columns]
+        xs = np.array([0.0 if r[0] is None else r[0] for r in rows])
+        xm = np.array([r[0] is None for r in rows], dtype=np.uint8)
+        ds = gp.DataStore(coltypes, [(xs, xm), (np.array([r[1] for r in rows], np.int32), None)],
+                          nrows=len(rows))
+        st = gp.GpuPreAggState(plan, [ds])
+        try:
+            device_rows = st.fetch_all()
+            recheck = sorted(r for _s, r in st.recheck_rows())
+        finally:
+            st.end()
+        ds.free()
+    finally:
+        plan.free()
+    bad = [i for i, r in enumerate(rows) if r[0] is not None and r[0] <= 0.0]
+    assert len(bad) > 100 and recheck == bad
+    exp, _ = partial.partial_rows(node, [r for i, r in enumerate(rows) if i not in set(bad)], 2)
+    got = bench_oracle.combine_device_rows(desc, device_rows)
+    assert set(got) == set(exp)
+    for key, erow in exp.items():
+        assert list(got[key]) == list(erow), (key, got[key], erow)
