@@ -134,6 +134,11 @@ int         pgstrom_fetch_data_store(const kern_data_store *kds, uint32_t row,
 /* datastore.c:150-167 pgstrom_fixup_kernel_numeric(): 64-bit device numeric
  * -> decimal text "<sign><mantissa>e<exp>" for numeric_in() */
 int         pgstrom_fixup_kernel_numeric(Datum datum, char *buf, size_t buflen);
+/* opencl_gpupreagg.h:326-366 (varlena grouping keys of the result):
+ * a text / bpchar grouping key comes back by value as "kernel text" (<= 7
+ * bytes + length in one Datum); -> varlena with a 4-byte header, bpchar padded
+ * to `typmod` (atttypmod, -1 = none).  Returns the size, 0 if buf is too small */
+size_t      pgstrom_fixup_kernel_text(Datum datum, int typmod, void *buf, size_t buflen);
 /* PostgreSQL numeric varlena <-> decimal text (for numeric Consts and for
  * harnesses without a PostgreSQL to make datums); return the length, 0 on
  * error */

@@ -88,6 +88,7 @@ PROTOTYPES = {
     "pgstrom_fetch_data_store": (C.c_int, [C.c_void_p, C.c_uint32,
                                            C.POINTER(C.c_uint64), C.c_char_p]),
     "pgstrom_fixup_kernel_numeric": (C.c_int, [C.c_uint64, C.c_char_p, C.c_size_t]),
+    "pgstrom_fixup_kernel_text": (C.c_size_t, [C.c_uint64, C.c_int, C.c_void_p, C.c_size_t]),
     "pgstrom_numeric_from_text": (C.c_size_t, [C.c_char_p, C.c_void_p, C.c_size_t]),
     "pgstrom_numeric_to_text": (C.c_size_t, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "pgs_program_build": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p),

@@ -147,6 +147,8 @@ pgs_plan_describe_json(pgs_plan *plan, int idx)
         c->set("agg_index", pc.agg_index);
         c->set("cell_index", pc.cell_index);
         c->set("text", deparse_expression(pc.expr, gp->outer_colnames, false));
+        if (pc.expr && pc.expr->s("node") == "Var" && pc.expr->has("vartypmod"))
+            c->set("typmod", (int)pc.expr->i("vartypmod"));
         cols->push(c);
     }
     o->set("columns", cols);
@@ -190,8 +192,12 @@ pgs_plan_result_colmeta(pgs_plan *plan, int idx, kern_colmeta *colmeta, int max_
             colmeta[i].attalign = (cl_char)dtype->type_align;
             colmeta[i].attlen = (cl_short)dtype->type_length;
         }
-        else if (dtype && std::string(dtype->type_name) == "numeric")
+        else if (dtype && (std::string(dtype->type_name) == "numeric" ||
+                           ((std::string(dtype->type_name) == "text" ||
+                             std::string(dtype->type_name) == "bpchar") &&
+                            gp->columns[i].role == GPUPREAGG_FIELD_IS_GROUPKEY)))
         {
+            /* numeric; "kernel text" of a text / bpchar grouping key */
             /* internal_format=true: 64-bit device numeric, by value
              * (datastore.c:355-363) */
             colmeta[i].attbyval = 1;

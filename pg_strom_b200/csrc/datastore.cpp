@@ -514,4 +514,44 @@ pgstrom_fixup_kernel_numeric(Datum datum, char *buf, size_t buflen)
                                          : StromError_DataStoreNoSpace;
 }
 
+/*
+ * "kernel text" (kern_textlib.cuh) -> varlena: a text / bpchar grouping key
+ * of at most 7 bytes comes back from the device by value - payload byte i in
+ * bits 8i..8i+7, the length in the top byte.  bpchar keys were stripped of
+ * their trailing blanks (they compare without them); `typmod` (atttypmod of
+ * the column: VARHDRSZ + n for character(n), -1 if unknown / text) pads the
+ * value back to n characters as PostgreSQL stores it.  Writes a varlena with
+ * a 4-byte header into buf and returns its size, 0 when buf is too small.
+ * Host-side fix-up like pgstrom_fixup_kernel_numeric (datastore.c:150-167);
+ * the reference fixes key pointers up on the device
+ * (opencl_gpupreagg.h:326-366).
+ */
+size_t
+pgstrom_fixup_kernel_text(Datum datum, int typmod, void *buf, size_t buflen)
+{
+    cl_ulong    word = (cl_ulong)datum;
+    size_t      len = (size_t)(word >> 56);
+    unsigned char payload[8];
+    size_t      nchars = 0, pad = 0;
+
+    if (len > 7)
+        return 0;
+    for (size_t i = 0; i < len; i++)
+    {
+        payload[i] = (unsigned char)(word >> (8 * i));
+        if ((payload[i] & 0xC0) != 0x80)    /* not a UTF-8 continuation byte */
+            nchars++;
+    }
+    if (typmod >= 4 && (size_t)(typmod - 4) > nchars)
+        pad = (size_t)(typmod - 4) - nchars;
+    size_t      total = 4 + len + pad;
+    if (total > buflen)
+        return 0;
+    uint32_t    hdr = (uint32_t)(total << 2);       /* SET_VARSIZE */
+    memcpy(buf, &hdr, 4);
+    memcpy((char *)buf + 4, payload, len);
+    memset((char *)buf + 4 + len, ' ', pad);
+    return total;
+}
+
 }   /* extern "C" */

@@ -699,7 +699,10 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
         {
             const DevType *dtype = devtype_lookup(pc.type);
             int attno = (int)expr->i("varattno");
-            if (!dtype || (dtype->type_flags & DEVTYPE_IS_VARLENA))
+            /* variable-length keys: text / bpchar travel as "kernel text"
+             * (kern_textlib.cuh); numeric / bytea keys stay on the host */
+            if (!dtype || ((dtype->type_flags & DEVTYPE_IS_VARLENA) &&
+                           pc.type != "text" && pc.type != "bpchar"))
             {
                 *err = "grouping key of type " + pc.type + " is not supported on the device yet";
                 return false;
@@ -1098,7 +1101,12 @@ pgstrom_try_insert_gpupreagg(const JsonPtr &agg)
                 gp.reject_reason = "grouping key type " + type + " is not supported";
                 return gp;
             }
-            tle_new->set("expr", make_var(resno, type));
+            JsonPtr keyvar = make_var(resno, type);
+            /* character(n): the host pads the key back to n (kernel text) */
+            JsonPtr src = tle->getp("expr");
+            if (src && src->s("node") == "Var" && src->has("vartypmod"))
+                keyvar->set("vartypmod", (int)src->i("vartypmod"));
+            tle_new->set("expr", keyvar);
         }
         else
             tle_new->set("expr", make_null_const(type));

@@ -209,6 +209,31 @@ pg_numeric_vstore(pagg_row &kds_src, const KDS &kds_in, cl_int *errcode,
 }
 #endif
 
+#ifdef KERN_TEXTLIB_CUH
+/* text / bpchar appear in the pagg_row only as grouping keys ("kernel text",
+ * kern_textlib.cuh) */
+template <typename KDS>
+DEVFN void
+pg_text_vstore(pagg_row &kds_src, const KDS &kds_in, cl_int *errcode,
+               cl_uint colidx, cl_uint rowidx_out, pg_text_t datum)
+{
+    bool        isnull;
+    cl_ulong    word = pgs_text_keybits(errcode, datum, false, &isnull);
+
+    kds_src.store(colidx, isnull, word);
+}
+template <typename KDS>
+DEVFN void
+pg_bpchar_vstore(pagg_row &kds_src, const KDS &kds_in, cl_int *errcode,
+                 cl_uint colidx, cl_uint rowidx_out, pg_bpchar_t datum)
+{
+    bool        isnull;
+    cl_ulong    word = pgs_text_keybits(errcode, datum, true, &isnull);
+
+    kds_src.store(colidx, isnull, word);
+}
+#endif
+
 /* NULL-const output columns need no work on the device */
 template <typename KDS>
 DEVFN void

@@ -215,4 +215,47 @@ pgfn_text_cmp(cl_int *errcode, pg_text_t arg1, pg_text_t arg2)
     return result;
 }
 
+/* ------------------------------------------------------------------
+ * text / bpchar as a GROUP BY key: "kernel text".
+ *
+ * A hash-table slot keeps 8 bytes per key.  A string of at most 7 bytes is
+ * its own key word: payload byte i in bits 8i..8i+7, the length in the top
+ * byte - equal words <=> equal strings, so the tables, the partitions and
+ * the NCCL merge treat it like an int8 key.  The word is also what the
+ * result row carries (by value, like the 64-bit device numeric); the host
+ * turns it back into a varlena with pgstrom_fixup_kernel_text()
+ * (datastore.cpp), the counterpart of the reference's varlena fix-up of
+ * grouping keys (opencl_gpupreagg.h:326-366, pg_fixup_tupslot_varlena).
+ * bpchar compares without its trailing blanks, so those are not part of the
+ * word; the host pads the value back to the column's typmod.  A longer key
+ * (or a compressed / external datum) is a row for the host: CpuReCheck.
+ * ------------------------------------------------------------------ */
+#define PGS_KERNEL_TEXT_MAXLEN  7
+
+DEVFN cl_ulong
+pgs_text_keybits(cl_int *errcode, pg_varlena_t arg, bool ignore_trailing_blanks,
+                 bool *isnull)
+{
+    const unsigned char *data;
+    cl_int      len = 0;
+    cl_ulong    word = 0;
+
+    *isnull = arg.isnull;
+    if (arg.isnull)
+        return 0;
+    pgs_varlena_payload(arg.value, &data, &len);    /* checked by pgs_varlena_make */
+    if (ignore_trailing_blanks)
+        while (len > 0 && data[len - 1] == ' ')
+            len--;
+    if (len > PGS_KERNEL_TEXT_MAXLEN)
+    {
+        *isnull = true;
+        STROM_SET_ERROR(errcode, StromError_CpuReCheck);
+        return 0;
+    }
+    for (cl_int i = 0; i < len; i++)
+        word |= (cl_ulong)data[i] << (8 * i);
+    return word | ((cl_ulong)len << 56);
+}
+
 #endif  /* KERN_TEXTLIB_CUH */

@@ -310,10 +310,18 @@ class HeapDataStore:
             pass
 
 
-def decode_datum(datum, isnull, typ):
-    """8-byte Datum of a TUPSLOT row -> python value (by-value types)."""
+def decode_datum(datum, isnull, typ, typmod=-1):
+    """8-byte Datum of a TUPSLOT row -> python value (by-value types; text /
+    bpchar grouping keys come back as "kernel text" -> payload bytes)."""
     if isnull:
         return None
+    if typ in ("text", "bpchar"):
+        lib = _capi.load()
+        buf = C.create_string_buffer(max(64, typmod + 32))
+        n = lib.pgstrom_fixup_kernel_text(datum, typmod, buf, len(buf))
+        if n == 0:
+            raise ValueError("bad kernel text datum %#x" % datum)
+        return buf.raw[4:n]
     if typ == "bool":
         return bool(datum & 0xff)
     if typ == "int2":
@@ -419,6 +427,7 @@ class GpuPreAggState:
         self.plan = plan
         self.desc = plan.describe(idx)
         self.coltypes = [c["type"] for c in self.desc["columns"]]
+        self.typmods = [c.get("typmod", -1) for c in self.desc["columns"]]
         self._chunks = iter(chunks)
         self._held = []
 
@@ -462,7 +471,8 @@ class GpuPreAggState:
                 break
             if rc < 0:
                 raise _capi.StromError(-rc, self.lib.pgs_last_error().decode(errors="replace"))
-            rows.append(tuple(decode_datum(values[i], isnull.raw[i] != 0, self.coltypes[i])
+            rows.append(tuple(decode_datum(values[i], isnull.raw[i] != 0, self.coltypes[i],
+                                           self.typmods[i])
                               for i in range(ncols)))
         return rows
 
@@ -503,6 +513,7 @@ class Session:
         self.plan = plan
         self.desc = plan.describe(idx)
         self.coltypes = [c["type"] for c in self.desc["columns"]]
+        self.typmods = [c.get("typmod", -1) for c in self.desc["columns"]]
         self.program = plan.build_program(idx)
         self._kparams = C.create_string_buffer(plan.kparams(idx))
         ncols = len(self.coltypes)
@@ -606,7 +617,8 @@ class Session:
         rows = []
         for r in range(kds.nitems):
             check(lib.pgstrom_fetch_data_store(buf, r, values, isnull))
-            rows.append(tuple(decode_datum(values[i], isnull.raw[i] != 0, self.coltypes[i])
+            rows.append(tuple(decode_datum(values[i], isnull.raw[i] != 0, self.coltypes[i],
+                                           self.typmods[i])
                               for i in range(ncols)))
         return rows
 

@@ -31,8 +31,11 @@ _DATE_OPS = {("date", "int4", "pl"): ("date_pli", "date"),
              ("time", "date", "pl"): ("timedate_pl", "timestamp")}
 
 
-def Var(attno, typ):
-    return {"node": "Var", "varattno": attno, "vartype": typ}
+def Var(attno, typ, typmod=None):
+    v = {"node": "Var", "varattno": attno, "vartype": typ}
+    if typmod is not None:
+        v["vartypmod"] = typmod         # atttypmod, e.g. VARHDRSZ + n for character(n)
+    return v
 
 
 def Const(typ, value, isnull=False):
@@ -195,22 +198,24 @@ def Agg(name, args=(), filter=None, star=False):
 class Table:
     """Column catalogue of a relation: [(name, type), ...]."""
 
-    def __init__(self, name, columns, schema="public"):
+    def __init__(self, name, columns, schema="public", typmods=None):
         self.name = name
         self.schema = schema
         self.columns = list(columns)
+        self.typmods = dict(typmods or {})      # column name -> atttypmod
 
     def col(self, name):
         for i, (n, t) in enumerate(self.columns):
             if n == name:
-                return Var(i + 1, t)
+                return Var(i + 1, t, self.typmods.get(n))
         raise KeyError(name)
 
     def colnames(self):
         return [n for n, _ in self.columns]
 
     def scan_tlist(self):
-        return [{"node": "TargetEntry", "expr": Var(i + 1, t), "resno": i + 1,
+        return [{"node": "TargetEntry", "expr": Var(i + 1, t, self.typmods.get(n)),
+                 "resno": i + 1,
                  "resname": n, "resjunk": False}
                 for i, (n, t) in enumerate(self.columns)]
 

@@ -157,6 +157,17 @@ int shim_text_op(int fn, int bpchar, const unsigned char *a, const unsigned char
     return e;
 }
 
+/* varlena image -> "kernel text" key word (bpchar != 0: without trailing blanks) */
+int shim_text_keybits(const unsigned char *a, int bpchar, uint64_t *out, int *isnull)
+{
+    cl_int e = 0;
+    bool n = false;
+    pg_varlena_t x = pgs_varlena_make(&e, a);
+    *out = pgs_text_keybits(&e, x, bpchar != 0, &n);
+    *isnull = n;
+    return e;
+}
+
 /* float8 (is_f4 = 0) or float4 value -> packed device numeric */
 int shim_float_numeric(double v, int is_f4, uint64_t *out, int *isnull)
 {

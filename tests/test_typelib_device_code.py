@@ -41,6 +41,8 @@ def shim(lib):
                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]
     so.shim_float_numeric.argtypes = [C.c_double, C.c_int, C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_int)]
+    so.shim_text_keybits.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_int)]
     return so
 
 
@@ -317,13 +319,73 @@ def test_text_ordering_needs_c_collation(lib):
         plan.free()
 
 
-def test_text_group_key_is_not_offloaded(lib):
-    t = EVENTS
-    tree = P.make_agg_plan(t, [(t.col("s"), "s"), (P.Agg("count", star=True), "count")],
-                           group_by=["s"], num_groups=26)
+def test_text_group_key_is_kernel_text(lib):
+    """text / bpchar grouping keys are offloaded as "kernel text" (<= 7 bytes
+    by value); the generated program compiles; numeric keys stay on the host."""
+    t = P.Table("cats", [("cat", "text"), ("code", "bpchar"), ("n", "numeric"), ("v", "int4")],
+                typmods={"code": 4 + 5})
+    tree = P.make_agg_plan(t, [(t.col("cat"), "cat"), (t.col("code"), "code"),
+                               (P.Agg("count", star=True), "count"),
+                               (P.Agg("sum", [t.col("v")]), "sum")],
+                           group_by=["cat", "code"], num_groups=26)
+    plan = gp.Plan(tree, gucs=GUCS)
+    try:
+        assert plan.num_gpupreagg == 1, plan.reject_reason
+        src = plan.kernel_source()
+        assert "pg_text_vstore(kds_src,kds_in,errcode,0,rowidx_out,KVAR_1)" in src
+        assert "pg_bpchar_vstore(kds_src,kds_in,errcode,1,rowidx_out,KVAR_2)" in src
+        cols = plan.describe()["columns"]
+        assert cols[0]["type"] == "text" and cols[1]["type"] == "bpchar"
+        assert cols[1]["typmod"] == 9 and "typmod" not in cols[0]
+        prog = plan.build_program()
+        plan.lib.pgs_program_release(prog)
+    finally:
+        plan.free()
+    tree = P.make_agg_plan(t, [(t.col("n"), "n"), (P.Agg("count", star=True), "count")],
+                           group_by=["n"], num_groups=26)
     plan = gp.Plan(tree, gucs=GUCS)
     try:
         assert plan.num_gpupreagg == 0
         assert "not supported" in plan.reject_reason
     finally:
         plan.free()
+
+
+def test_kernel_text_fixup(lib, shim):
+    """device packing (pgs_text_keybits) and host fix-up
+    (pgstrom_fixup_kernel_text) are inverse; bpchar loses its trailing blanks
+    on the device and gets them back from the typmod."""
+    out, isnull = C.c_uint64(), C.c_int()
+    buf = C.create_string_buffer(64)
+    cases = [b"", b"a", b"abc", b"abcdefg", b"ab  ", b"   ", b"caf\xc3\xa9", b"\xe3\x81\x82",
+             b"a b", b"\xff\x00x"[:1] + b"x"]
+    for s in cases:
+        for short in (None, False):
+            img = T.varlena(s, short=short)
+            err = shim.shim_text_keybits(img, 0, C.byref(out), C.byref(isnull))
+            assert err == 0 and not isnull.value
+            n = lib.pgstrom_fixup_kernel_text(out.value, -1, buf, len(buf))
+            assert buf.raw[:n] == T.varlena(s, short=False), s
+            # bpchar: blanks are not part of the key ...
+            err = shim.shim_text_keybits(img, 1, C.byref(out), C.byref(isnull))
+            assert err == 0 and not isnull.value
+            word2 = C.c_uint64()
+            shim.shim_text_keybits(T.varlena(s.rstrip(b" ")), 1, C.byref(word2), C.byref(isnull))
+            assert word2.value == out.value
+            n = lib.pgstrom_fixup_kernel_text(out.value, -1, buf, len(buf))
+            assert buf.raw[4:n] == s.rstrip(b" ")
+            # ... and come back from character(8)
+            n = lib.pgstrom_fixup_kernel_text(out.value, 4 + 8, buf, len(buf))
+            nchars = len(s.rstrip(b" ").decode("utf-8", "replace"))
+            assert buf.raw[4:n] == s.rstrip(b" ") + b" " * max(0, 8 - nchars), s
+    # two strings, one key <=> equal
+    words = {}
+    for s in cases + [b"abcdefg", b"abcdef", b"b", b"ab"]:
+        shim.shim_text_keybits(T.varlena(s), 0, C.byref(out), C.byref(isnull))
+        assert words.setdefault(out.value, s) == s
+    # longer than 7 bytes: a row for the host
+    err = shim.shim_text_keybits(T.varlena(b"abcdefgh"), 0, C.byref(out), C.byref(isnull))
+    assert err == CPU_RECHECK and isnull.value
+    err = shim.shim_text_keybits(T.varlena(b"abcdefg   "), 1, C.byref(out), C.byref(isnull))
+    assert err == 0 and not isnull.value
+    assert lib.pgstrom_fixup_kernel_text(out.value, -1, buf, 8) == 0     # buffer too small

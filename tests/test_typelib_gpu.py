@@ -210,3 +210,80 @@ def test_math_domain_errors_are_rechecked(cuda):
     assert set(got) == set(exp)
     for key, erow in exp.items():
         assert list(got[key]) == list(erow), (key, got[key], erow)
+
+
+CATS = P.Table("cats", [("cat", "text"), ("code", "bpchar"), ("f", "int4"), ("v", "int8")],
+               typmods={"code": 4 + 5})
+
+
+def make_cats(n, seed):
+    rng = random.Random(seed)
+    cats = [bytes([97 + i]) * 3 for i in range(26)] + [b"", b"a", b"abcdefg", b"caf\xc3\xa9"]
+    long_cats = [b"abcdefgh", b"category-with-a-long-name", b"x" * 300]
+    codes = [c.ljust(5) for c in (b"ab", b"abcde", b"x", b"", b"a b")] + [b"caf\xc3\xa9 "]
+    rows = []
+    for _ in range(n):
+        cat = rng.choice(long_cats) if rng.random() < 0.03 else rng.choice(cats)
+        rows.append((None if rng.random() < 0.04 else cat,
+                     None if rng.random() < 0.04 else rng.choice(codes),
+                     rng.randrange(0, 100), rng.randrange(-10 ** 15, 10 ** 15)))
+    return rows
+
+
+@pytest.mark.parametrize("fmt", ["column", "row"])
+@pytest.mark.parametrize("with_qual", [False, True])
+def test_text_and_bpchar_group_keys(cuda, fmt, with_qual):
+    """GROUP BY a text and a character(5) column: keys of at most 7 bytes are
+    grouped on the device ("kernel text"), rows with a longer key come back
+    for the host (CpuReCheck) and PostgreSQL's final Agg - here the checker -
+    merges both."""
+    t = CATS
+    rows = make_cats(8000, seed=31)
+    tree = P.make_agg_plan(
+        t, [(t.col("cat"), "cat"), (t.col("code"), "code"), (P.Agg("count", star=True), "count"),
+            (P.Agg("sum", [t.col("f")]), "sum"), (P.Agg("min", [t.col("v")]), "min")],
+        group_by=["cat", "code"], num_groups=200,
+        where=[P.Op("<", t.col("f"), P.Const("int4", 50))] if with_qual else [])
+    plan = gp.Plan(tree, gucs=GUCS)
+    try:
+        assert plan.num_gpupreagg == 1, plan.reject_reason
+        desc = plan.describe()
+        node = find_node(plan.tree())
+        coltypes = [c for _, c in t.columns]
+        chunk_rows = 3000
+        chunks = []
+        for lo in range(0, len(rows), chunk_rows):
+            part = rows[lo:lo + chunk_rows]
+            cols = []
+            for c, typ in enumerate(coltypes):
+                raw = [r[c] for r in part]
+                if gp.PGTYPES[typ][0] > 0:
+                    cols.append((np.array(raw, dtype=gp.PGTYPES[typ][3]), None))
+                else:
+                    cols.append(([None if v is None else T.varlena(v) for v in raw], None))
+            chunks.append(gp.DataStore(coltypes, cols, nrows=len(part)) if fmt == "column"
+                          else gp.HeapDataStore(coltypes, cols, nrows=len(part)))
+        st = gp.GpuPreAggState(plan, chunks)
+        try:
+            device_rows = st.fetch_all()
+            recheck = sorted(s * chunk_rows + r for s, r in st.recheck_rows())
+        finally:
+            st.end()
+        for ds in chunks:
+            ds.free()
+    finally:
+        plan.free()
+    long_rows = [i for i, r in enumerate(rows)
+                 if r[0] is not None and len(r[0]) > 7 and (not with_qual or r[2] < 50)]
+    assert len(long_rows) > 50 and recheck == long_rows
+    # what gpupreagg_next_tuple_fallback produces for the flagged rows
+    host, _ = partial.partial_rows(node, [rows[i] for i in recheck], len(t.columns))
+    exp, _ = partial.partial_rows(node, rows, len(t.columns))
+    got = bench_oracle.combine_device_rows(desc, list(device_rows) + [tuple(v) for v in host.values()])
+    assert len(exp) > 100 and set(got) == set(exp)
+    for key, erow in exp.items():
+        assert list(got[key]) == list(erow), (key, got[key], erow)
+    # the device's own rows carry only short keys, padded back to character(5)
+    for r in device_rows:
+        assert r[0] is None or len(r[0]) <= 7
+        assert r[1] is None or len(r[1].decode("utf-8")) == 5
