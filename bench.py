@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--format", default="column", choices=["column", "row"],
                     help="input chunks: KDS_FORMAT_COLUMN, or the reference's heap-page "
                          "KDS_FORMAT_ROW (de-formed on the device)")
+    ap.add_argument("--selectivity", type=int, default=10,
+                    help="where_agg: per cent of rows the qual `f < N` keeps (10 is the "
+                         "headline configuration; 1 and 50 are its reported variants)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     return ap.parse_args()
@@ -155,7 +158,7 @@ def generate_columns(workload, rank, rows, chunk_rows):
     return out
 
 
-def run_cpu(workload, colchunks, nthreads, max_seconds=30.0):
+def run_cpu(workload, colchunks, nthreads, max_seconds=30.0, qual_const=None):
     """PostgreSQL-style Agg over SeqScan in C on the host cores; returns
     (rows/s, rows used, seconds)."""
     from oracle import cpu_agg
@@ -178,7 +181,8 @@ def run_cpu(workload, colchunks, nthreads, max_seconds=30.0):
             m = np.concatenate([np.zeros(len(ch[c][0]), np.uint8) if ch[c][1] is None
                                 else ch[c][1] for ch in use])
         cols.append((v, m))
-    dt, _, _, ng = cpu_agg.run(workload, cols, nthreads=nthreads, max_groups=1 << 24)
+    dt, _, _, ng = cpu_agg.run(workload, cols, nthreads=nthreads, max_groups=1 << 24,
+                               qual_const=qual_const)
     return total / dt, total, dt, ng
 
 
@@ -196,7 +200,8 @@ def bench_reference(args):
     times = []
     used = 0
     for i in range(args.warmup + args.steps):
-        rps, used, dt, ng = run_cpu(args.workload, colchunks, cores)
+        rps, used, dt, ng = run_cpu(args.workload, colchunks, cores,
+                                    qual_const=args.selectivity)
         if i >= args.warmup:
             times.append(dt)
     ms = 1000.0 * sum(times) / len(times)
@@ -206,7 +211,8 @@ def bench_reference(args):
         "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic",
-        "config": {"workload": args.workload, "sql": SQL[args.workload],
+        "config": {"workload": args.workload,
+                   "sql": SQL[args.workload].replace("f < 10", "f < %d" % args.selectivity),
                    "rows_per_step": used, "note": "CPU Agg over SeqScan on host cores"},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port",
                          "sample": "%d rows of the %s table per step" % (used, args.workload)},
@@ -244,7 +250,10 @@ def bench_ours(args):
     w = W.WORKLOADS[workload]
     gucs = {"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on",
             "pg_strom.perfmon": "on"}
-    plan = gp.Plan(w["plan"](), gucs=gucs)
+    plan_kw = {}
+    if workload == "where_agg" and args.selectivity != 10:
+        plan_kw["selectivity_pct"] = args.selectivity
+    plan = gp.Plan(w["plan"](**plan_kw), gucs=gucs)
     assert plan.num_gpupreagg == 1, plan.reject_reason
     desc = plan.describe()
     node = plan.tree()["lefttree"]
@@ -410,8 +419,8 @@ def bench_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        rps1, used, dt1, _ = run_cpu(workload, colchunks, 1)
-        rpsn, used, dtn, _ = run_cpu(workload, colchunks, cores)
+        rps1, used, dt1, _ = run_cpu(workload, colchunks, 1, qual_const=args.selectivity)
+        rpsn, used, dtn, _ = run_cpu(workload, colchunks, cores, qual_const=args.selectivity)
         cpu = {"value": rpsn, "unit": "rows/s", "cores": cores, "kind": "port",
                "value_1core": rps1,
                "sample": "%d rows of the %s table (oracle/cpu_agg.c: PostgreSQL-style "
@@ -434,7 +443,8 @@ def bench_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64/f64", "data": "synthetic",
-            "config": {"workload": workload, "sql": SQL[workload],
+            "config": {"workload": workload,
+                       "sql": SQL[workload].replace("f < 10", "f < %d" % args.selectivity),
                        "input_format": "KDS_FORMAT_ROW (heap pages, %.1f physical bytes per row)"
                                        % (total_dev_bytes / float(rows)) if heap
                                        else "KDS_FORMAT_COLUMN",
