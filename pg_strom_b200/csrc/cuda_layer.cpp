@@ -893,6 +893,13 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
             const char *es = getenv("PGSTROM_NUM_STAGES");
             if (target > budget)
                 target = budget;
+            if (s->desc.max_tile_rows > tile)
+            {
+                /* only the qual's columns are staged (gather variant): a
+                 * deeper ring of longer tiles keeps more bytes in flight */
+                tile = (s->desc.max_tile_rows / 1024) * 1024;
+                stages = 4;
+            }
             while (stages > 2 && (size_t)stages * (tile / 1024) * per1k > target)
                 stages--;
             while (tile > 1024 && (size_t)stages * (tile / 1024) * per1k > target)

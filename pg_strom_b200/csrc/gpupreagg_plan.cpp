@@ -2,6 +2,7 @@
  * gpupreagg_plan.cpp - planner half of GpuPreAgg.  See pgs_plan.h.
  */
 #include <cstdint>
+#include <cstdlib>
 #include <sstream>
 #include "pgs_plan.h"
 #include "../../include/pgstrom_kds.h"
@@ -627,6 +628,7 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
     std::ostringstream body, decl1;
     std::string gpagg_atts(pre_tlist.size(), (char)GPUPREAGG_FIELD_IS_NULL);
     std::set<int> attr_refs;
+    std::set<int> qual_refs;        /* columns the qual reads */
     bool ok = true;
     bool use_temp_int4 = false, use_temp_float8x = false, use_temp_float8y = false;
 
@@ -662,7 +664,10 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
                 << "\n"
                 << "  return EVAL(" << expr_code << ");\n";
         for (auto &q : outer_quals)
+        {
             pull_varattnos(q, attr_refs);
+            pull_varattnos(q, qual_refs);
+        }
     }
     else
         fn_qual << "  return true;\n";
@@ -950,7 +955,21 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
 
     /* ---- compile-time description of the query for the kernel templates ---- */
     int nincols = 0;
-    std::ostringstream incol_list, slot_fn, attlen_fn;
+    std::ostringstream incol_list, slot_fn, attlen_fn, staged_fn;
+    /* Experimental, off by default (PGSTROM_GATHER_PAYLOAD=1): under a
+     * selective WHERE clause only the qual's columns go through the TMA
+     * staging ring; the rows that pass fetch their other columns from HBM by
+     * row number (kern_gpupreagg.cuh, GPUPREAGG_GATHER_PAYLOAD). */
+    bool gather_payload = false;
+    {
+        const char *env = getenv("PGSTROM_GATHER_PAYLOAD");
+        bool unstaged = false;
+        for (int attno : attr_refs)
+            if (!qual_refs.count(attno))
+                unstaged = true;
+        gather_payload = (env && atoi(env) != 0 && !outer_quals.empty() && nkeys > 0 &&
+                          !(gp.num_groups >= 65536.0) && unstaged);
+    }
     gp.row_bytes = 0;
     for (int attno : attr_refs)
     {
@@ -961,6 +980,8 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
         incol_list << " _(" << nincols << "," << (attno - 1) << "," << attlen << ")";
         slot_fn << "    case " << (attno - 1) << ": return " << nincols << ";\n";
         attlen_fn << "    case " << nincols << ": return " << attlen << ";\n";
+        if (gather_payload && !qual_refs.count(attno))
+            staged_fn << "    case " << nincols << ": return 0;\n";
         gp.incol_index.push_back(attno - 1);
         gp.row_bytes += attlen;
         nincols++;
@@ -972,6 +993,10 @@ gpupreagg_codegen(GpuPreAggPlan &gp, const std::vector<JsonPtr> &pre_tlist,
          << "  switch (colidx)\n  {\n" << slot_fn.str() << "    default: return 0;\n  }\n}\n"
          << "__host__ __device__ constexpr unsigned int\nGPUPREAGG_INCOL_ATTLEN(int slot)\n{\n"
          << "  switch (slot)\n  {\n" << attlen_fn.str() << "    default: return 0;\n  }\n}\n"
+         /* 1: the column goes through the staging ring */
+         << "__host__ __device__ constexpr unsigned int\nGPUPREAGG_INCOL_STAGED(int slot)\n{\n"
+         << "  switch (slot)\n  {\n" << staged_fn.str() << "    default: return 1;\n  }\n}\n"
+         << "#define GPUPREAGG_GATHER_PAYLOAD " << (gather_payload ? 1 : 0) << "\n"
          << "#define GPUPREAGG_NUM_KEYS " << nkeys << "\n"
          << "#define GPUPREAGG_KEY_LIST(_)" << key_list.str() << "\n"
          << "#define GPUPREAGG_NUM_AGGS " << naggs << "\n"

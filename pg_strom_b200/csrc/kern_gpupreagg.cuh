@@ -74,6 +74,13 @@
 #define PGS_PART_NPARTS(gs)         0U
 #endif
 
+/* 1 (experimental, PGSTROM_GATHER_PAYLOAD): only the columns the qual reads
+ * are staged (GPUPREAGG_INCOL_STAGED(slot)); rows that pass the qual fetch
+ * the others from HBM by row number */
+#ifndef GPUPREAGG_GATHER_PAYLOAD
+#define GPUPREAGG_GATHER_PAYLOAD    0
+#endif
+
 /* 1 when gpupreagg_qual_eval() reads varlena datums (numeric, text) */
 #ifndef GPUPREAGG_QUAL_DEREFS
 #define GPUPREAGG_QUAL_DEREFS       0
@@ -1039,20 +1046,32 @@ gpupreagg_aggmerge_atomic(CELLS cells, SRC src, cl_uint src_nn)
 #define PGS_ALIGN128(x)     (((x) + 127U) & ~127U)
 
 /* tile_rows is a multiple of 1024, so every piece is 128-byte aligned */
+/* columns that are not staged (GPUPREAGG_GATHER_PAYLOAD) take no room */
+#define PGS_STAGE_ATTLEN(s) \
+    (GPUPREAGG_INCOL_STAGED(s) ? GPUPREAGG_INCOL_ATTLEN(s) : 0U)
 DEVFN cl_uint
 pgs_stage_val_off(int slot, cl_uint tile_rows)
 {
     cl_uint off = 0;
 #pragma unroll
     for (int s = 0; s < slot; s++)
-        off += tile_rows * GPUPREAGG_INCOL_ATTLEN(s);
+        off += tile_rows * PGS_STAGE_ATTLEN(s);
     return off;
 }
 DEVFN cl_uint
 pgs_stage_nul_off(int slot, cl_uint tile_rows)
 {
+#if GPUPREAGG_GATHER_PAYLOAD
+    cl_uint nstaged = 0;
+#pragma unroll
+    for (int s = 0; s < slot; s++)
+        nstaged += (GPUPREAGG_INCOL_STAGED(s) ? 1U : 0U);
+    return pgs_stage_val_off(GPUPREAGG_NUM_INCOLS, tile_rows) +
+        nstaged * (tile_rows / 8);
+#else
     return pgs_stage_val_off(GPUPREAGG_NUM_INCOLS, tile_rows) +
         (cl_uint)slot * (tile_rows / 8);
+#endif
 }
 #define PGS_STAGE_BYTES(tile_rows)  pgs_stage_nul_off(GPUPREAGG_NUM_INCOLS, (tile_rows))
 /* Per consumer warp (GROUP BY with a WHERE clause only, see the consumer
@@ -1683,6 +1702,7 @@ struct pgs_smem_head
     head->nul_pos[slot] = KERN_DATA_STORE_COLPOS(kds_in, colidx)->nullmap_offset;
 
 #define PGS_X_INCOL_ISSUE(slot,colidx,attlen)                           \
+    if (GPUPREAGG_INCOL_STAGED(slot))                                   \
     {                                                                   \
         cl_uint nb = ((rows * (attlen)) + 15U) & ~15U;                  \
         pgs_bulk_g2s(stage_base + pgs_stage_val_off(slot, tile_rows),              \
@@ -1698,13 +1718,16 @@ struct pgs_smem_head
     }
 
 #define PGS_X_INCOL_TXBYTES(slot,colidx,attlen)                         \
-    txbytes += ((rows * (attlen)) + 15U) & ~15U;                        \
-    if (head->nul_pos[slot] != 0)                                       \
-        txbytes += (((rows + 7U) >> 3) + 15U) & ~15U;
+    if (GPUPREAGG_INCOL_STAGED(slot))                                   \
+    {                                                                   \
+        txbytes += ((rows * (attlen)) + 15U) & ~15U;                    \
+        if (head->nul_pos[slot] != 0)                                   \
+            txbytes += (((rows + 7U) >> 3) + 15U) & ~15U;               \
+    }
 
 #define PGS_X_INCOL_VIEW(slot,colidx,attlen)                            \
     tile.val_off[slot] = stage_off + pgs_stage_val_off(slot, tile_rows);           \
-    tile.nul_off[slot] = (head->nul_pos[slot] != 0                      \
+    tile.nul_off[slot] = (head->nul_pos[slot] != 0 && GPUPREAGG_INCOL_STAGED(slot) \
                           ? stage_off + pgs_stage_nul_off(slot, tile_rows)         \
                           : KERN_TILE_NO_NULLMAP);
 
@@ -1730,10 +1753,13 @@ struct pgs_smem_head
 
 /* phase 1 of the staged consumer loop: 4 adjacent rows of one column */
 #define PGS_X_INCOL_LOAD4(slot,colidx,attlen)                           \
-    pgs_rowload<attlen>::load4(__pgs_smem + tile.val_off[slot] +        \
-                               r * (attlen),                            \
-                               rr[0].v[slot], rr[1].v[slot],            \
-                               rr[2].v[slot], rr[3].v[slot]);           \
+    if (GPUPREAGG_INCOL_STAGED(slot))                                   \
+        pgs_rowload<attlen>::load4(__pgs_smem + tile.val_off[slot] +    \
+                                   r * (attlen),                        \
+                                   rr[0].v[slot], rr[1].v[slot],        \
+                                   rr[2].v[slot], rr[3].v[slot]);       \
+    else                                                                \
+        rr[0].v[slot] = rr[1].v[slot] = rr[2].v[slot] = rr[3].v[slot] = 0; \
     {                                                                   \
         cl_uint __vb = 0xFU;                                            \
         if (tile.nul_off[slot] != KERN_TILE_NO_NULLMAP)                 \
@@ -2098,6 +2124,11 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
         const cl_uint   lanes_lt = (1U << lane_id) - 1U;
         cl_uint         qhead = 0, qtail = 0;
         cl_uint         nscanned = 0, npassed = 0;
+#if GPUPREAGG_GATHER_PAYLOAD
+        kern_tile_gmem  gtile;
+
+        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_GVIEW)
+#endif
 #endif
         cl_uint         stage = 0, phase = 0;
         PGS_DBG_DECL
@@ -2292,6 +2323,111 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                         PGS_CONSUME_ROW_GROUPED(j)
                 }
             }
+#elif GPUPREAGG_GATHER_PAYLOAD
+            /* GROUP BY under a WHERE clause, experimental variant
+             * (PGSTROM_GATHER_PAYLOAD=1): the ring only carries the columns
+             * the qual reads, so a tile of the same byte size holds several
+             * times the rows and more of the chunk is in flight per SM.  A
+             * warp evaluates the qual of 128 staged rows per step and queues
+             * the ROW NUMBERS of the survivors (32-bit, no values are kept);
+             * the stage goes back to the producer as soon as the warp has
+             * scanned its share.  Whenever 32 rows are queued, every lane
+             * takes one through projection - its columns gathered from HBM
+             * by row number (kern_tile_gmem, the view of the row-map
+             * kernel) - and find-or-insert.  With a selective qual most
+             * 32-byte sectors of the unstaged columns are never read. */
+            {
+                cl_uint        *rowq32 = (cl_uint *)(__pgs_smem + __qbase);
+                const cl_uint   step_rows = GPUPREAGG_CONSUMER_THREADS * 4;
+                const cl_uint   rows_up = ((rows + step_rows - 1) / step_rows) * step_rows;
+                const bool      last_tile = (t + gridDim.x >= ntiles);
+                cl_uint         rb = (ctid & ~31U) * 4;
+                bool            scanning = true;
+
+                for (;;)
+                {
+                    const cl_uint   qn = qtail - qhead;
+
+                    if (scanning && rb < rows_up && qn <= PGS_ROWQ_ENTRIES - 128)
+                    {
+                        const cl_uint r = rb + lane_id * 4;
+                        const cl_uint nv = (r < rows ? min(rows - r, 4U) : 0U);
+                        kern_row_regs rr[4];
+                        bool        valid4[4];
+                        cl_uint     votes4[4];
+
+                        rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                        {
+                            cl_int      e = StromError_Success;
+
+                            valid4[j] = false;
+                            if ((cl_uint)j < nv)
+                                valid4[j] = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
+                                                                row0 + r + j);
+                            if (e != StromError_Success)
+                            {
+                                pgs_note_error(e, row0 + r + j, recheck_map, ctx);
+                                ctx.nfiltered--;    /* neither passed nor filtered */
+                                valid4[j] = false;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            votes4[j] = __ballot_sync(0xffffffffU, valid4[j]);
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                        {
+                            if (valid4[j])
+                                rowq32[(qtail + __popc(votes4[j] & lanes_lt)) & (PGS_ROWQ_ENTRIES - 1)] =
+                                    row0 + r + j;
+                            qtail += __popc(votes4[j]);
+                        }
+                        nscanned += min(rows - min(rb, rows), 128U);
+                        rb += step_rows;
+                        __syncwarp();
+                        continue;
+                    }
+                    if (scanning && rb >= rows_up)
+                    {
+                        /* nothing of the stage is needed any more */
+                        __syncwarp();
+                        if (lane_id == 0)
+                            pgs_mbar_arrive(&head->empty_bar[stage]);
+                        scanning = false;
+                    }
+                    if (qn >= 32 || (!scanning && last_tile && qn != 0))
+                    {
+                        const cl_uint   n = min(qn, 32U);
+                        const cl_uint   row = rowq32[(qhead + lane_id) & (PGS_ROWQ_ENTRIES - 1)];
+                        bool            active = (lane_id < n);
+                        pagg_row        prow;
+
+                        if (active)
+                        {
+                            cl_int  e = StromError_Success;
+
+                            gpupreagg_projection(&e, kparams, gtile, prow, kds_in, row, 0);
+                            gpupreagg_aggcheck(&e, prow);
+                            if (e != StromError_Success)
+                            {
+                                pgs_note_error(e, row, recheck_map, ctx);
+                                active = false;
+                            }
+                        }
+                        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, active);
+                        __syncwarp();
+                        qhead += n;
+                        npassed += n;
+                        continue;
+                    }
+                    if (!scanning)
+                        break;
+                }
+            }
+            continue;       /* the stage was handed back above */
 #else
             /* GROUP BY under a WHERE clause.  Only a fraction of the rows
              * reaches the hash table; taking that path per row would run it
@@ -3486,6 +3622,9 @@ gpupreagg_describe(pgs_kern_desc *desc)
     desc->block_threads = GPUPREAGG_BLOCK_THREADS;
     desc->sh_slot_bytes = PGS_SH_SLOT_BYTES;
     desc->row_bytes = rb;
+    /* largest tile worth using: with only the qual's columns staged a tile
+     * of the usual byte size holds many more rows */
+    desc->max_tile_rows = (GPUPREAGG_GATHER_PAYLOAD ? 8192 : 4096);
 }
 
 #endif  /* KERN_GPUPREAGG_CUH */

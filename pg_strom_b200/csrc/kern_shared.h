@@ -52,7 +52,7 @@ typedef struct
     cl_uint     row_bytes;          /* algorithmic bytes per row (attlen sum) */
     cl_uint     slot_stride_bytes;  /* distance of two slots of the global table */
     cl_uint     part_rec_bytes;     /* bytes of a partition record */
-    cl_uint     reserved[1];
+    cl_uint     max_tile_rows;      /* upper bound of the tile size (multiple of 1024) */
 } pgs_kern_desc;
 
 #endif  /* KERN_SHARED_H */

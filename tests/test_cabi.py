@@ -115,6 +115,32 @@ def test_programs_build_for_sm_100a(lib):
         plan.free()
 
 
+def test_gather_payload_variant_builds(lib, monkeypatch):
+    """PGSTROM_GATHER_PAYLOAD=1 (experimental, off by default): only the
+    qual's columns are staged; the variant applies to GROUP BY under a WHERE
+    clause and must leave every other program as it is."""
+    gucs = {"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on"}
+    plan = gp.Plan(W.where_plan(), gucs=gucs)
+    base = plan.kernel_source()
+    plan.free()
+    assert "#define GPUPREAGG_GATHER_PAYLOAD 0" in base
+    monkeypatch.setenv("PGSTROM_GATHER_PAYLOAD", "1")
+    plan = gp.Plan(W.where_plan(), gucs=gucs)
+    src = plan.kernel_source()
+    assert "#define GPUPREAGG_GATHER_PAYLOAD 1" in src
+    # f (slot 0) is the qual's column; key, v, w are fetched by row number
+    i = src.index("GPUPREAGG_INCOL_STAGED(int slot)")
+    body = src[i:src.index("}\n}", i)]
+    assert "case 0" not in body and all("case %d: return 0;" % k in body for k in (1, 2, 3))
+    prog = plan.build_program()
+    lib.pgs_program_release(prog)
+    plan.free()
+    for mk in (W.nogrp_plan, W.hc_plan):        # no WHERE / partitioned: unchanged
+        plan = gp.Plan(mk(), gucs=gucs)
+        assert "#define GPUPREAGG_GATHER_PAYLOAD 0" in plan.kernel_source()
+        plan.free()
+
+
 def test_build_failure_reports_log(lib):
     prog = C.c_void_p()
     log = C.c_char_p()

@@ -1,6 +1,8 @@
 """-m gpu: the bench workloads through the session API (C ABI), device
 partial rows == oracle partial rows, bit-exact (the float columns sit on a
 dyadic grid, so their sums do not depend on the summation order)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -142,3 +144,22 @@ def test_where_many_groups(cuda):
     ng, rows, pm = _run("where_agg", 1_500_000, 500_000,
                         plan_kw={"num_groups": 120_000}, col_kw={"num_groups": 120_000})
     assert pm["sh_nslots"] == 0 and pm["part_nparts"] > 0
+
+
+@pytest.mark.skipif(os.environ.get("PGSTROM_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental kernel variant: set PGSTROM_TEST_EXPERIMENTAL=1")
+def test_where_gather_payload_variant(cuda, monkeypatch):
+    """PGSTROM_GATHER_PAYLOAD=1: the ring carries only the qual's column,
+    survivors gather key / v / w from HBM by row number.  Same results."""
+    monkeypatch.setenv("PGSTROM_GATHER_PAYLOAD", "1")
+    ng, rows, pm = _run("where_agg", 2_000_000, 1_000_000)
+    assert ng == 1000 and pm["tile_rows"] > 4096
+    _run("where_agg", 700_001, 233_333, col_kw={"with_nulls": True})
+    for pct in (1, 50, 100):
+        _run("where_agg", 400_000, 400_000, plan_kw={"selectivity_pct": pct})
+    for n in (4, 100, 2048, 8193):
+        _run("where_agg", n, n)
+    monkeypatch.setenv("PGSTROM_SH_SLOTS", "256")
+    _run("where_agg", 600_000, 300_000)
+    monkeypatch.setenv("PGSTROM_SH_SLOTS", "0")
+    _run("where_agg", 600_000, 300_000)
