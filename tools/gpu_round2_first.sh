@@ -1,0 +1,15 @@
+# First GPU call of the next round (one B200): the experimental where_agg variant that
+# stages only the qual's column - parity first, then the
+# bench at 1 / 10 / 50 % selectivity with and without it, then an ncu capture.
+# usage: gpurun --timeout 900 -- 'bash tools/gpu_round2_first.sh'
+mkdir -p gpurun_out
+PGSTROM_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_workloads.py -x -q \
+    --timeout 120 -k gather > gpurun_out/t_gather.log 2>&1; echo "rc=$?" >> gpurun_out/t_gather.log
+for sel in 1 10 50; do
+  for g in 0 1; do
+    PGSTROM_GATHER_PAYLOAD=$g timeout 120 python bench.py --workload where_agg --rows 50000000 \
+        --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 --selectivity $sel \
+        > gpurun_out/bench_where_sel${sel}_gather${g}.json 2> gpurun_out/bench_where_sel${sel}_gather${g}.err
+  done
+done
+PGSTROM_GATHER_PAYLOAD=1 bash tools/gpu_ncu.sh where_gather --workload where_agg
