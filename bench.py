@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--selectivity", type=int, default=10,
                     help="where_agg: per cent of rows the qual `f < N` keeps (10 is the "
                          "headline configuration; 1 and 50 are its reported variants)")
+    ap.add_argument("--zipf", action="store_true",
+                    help="high_cardinality: Zipf(1.0) keys instead of uniform ones")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     return ap.parse_args()
@@ -148,14 +150,18 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def generate_columns(workload, rank, rows, chunk_rows):
+def generate_columns(workload, rank, rows, chunk_rows, **col_kw):
     from pg_strom_b200 import workloads as W
     out = []
     base = rank * ((rows + 3) // 4 * 4)
     for r0 in range(0, rows, chunk_rows):
         n = min(chunk_rows, rows - r0)
-        out.append(W.WORKLOADS[workload]["columns"](base + r0, n))
+        out.append(W.WORKLOADS[workload]["columns"](base + r0, n, **col_kw))
     return out
+
+
+def column_options(args):
+    return {"zipf": True} if (args.zipf and args.workload == "high_cardinality") else {}
 
 
 def run_cpu(workload, colchunks, nthreads, max_seconds=30.0, qual_const=None):
@@ -196,7 +202,7 @@ def bench_reference(args):
     rows = args.rows or DEFAULT_ROWS[args.workload]
     chunk_rows = args.chunk_rows or DEFAULT_CHUNK[args.workload]
     cores = host_cores()
-    colchunks = generate_columns(args.workload, 0, rows, chunk_rows)
+    colchunks = generate_columns(args.workload, 0, rows, chunk_rows, **column_options(args))
     times = []
     used = 0
     for i in range(args.warmup + args.steps):
@@ -259,7 +265,7 @@ def bench_ours(args):
     node = plan.tree()["lefttree"]
 
     # ---- synthetic table: resident device chunks + pinned host chunks ----
-    colchunks = generate_columns(workload, rank, rows, chunk_rows)
+    colchunks = generate_columns(workload, rank, rows, chunk_rows, **column_options(args))
     coltypes = [t for _, t in w["table"].columns]
     host_chunks, dev_chunks = [], []
     heap = (args.format == "row")
@@ -279,7 +285,7 @@ def bench_ours(args):
     e2e_chunk_rows = min(args.e2e_chunk_rows or DEFAULT_E2E_CHUNK[workload], rows)
     if heap:
         e2e_chunk_rows = min(e2e_chunk_rows, chunk_rows)
-    for cols in generate_columns(workload, rank, rows, e2e_chunk_rows):
+    for cols in generate_columns(workload, rank, rows, e2e_chunk_rows, **column_options(args)):
         if heap:
             host_chunks.append(gp.HeapDataStore(coltypes, cols, nrows=len(cols[0][0])))
             host_chunks[-1].length = host_chunks[-1].device_layout()[2]
@@ -444,6 +450,7 @@ def bench_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64/f64", "data": "synthetic",
             "config": {"workload": workload,
+                       "key_distribution": ("zipf(1.0)" if column_options(args) else "uniform"),
                        "sql": SQL[workload].replace("f < 10", "f < %d" % args.selectivity),
                        "input_format": "KDS_FORMAT_ROW (heap pages, %.1f physical bytes per row)"
                                        % (total_dev_bytes / float(rows)) if heap

@@ -109,11 +109,20 @@ def hc_plan(num_groups=10_000_000):
     return P.make_agg_plan(t, targets, group_by=["key"], num_groups=num_groups)
 
 
-def hc_columns(row0, n, num_groups=10_000_000, seed=SEED):
+def hc_columns(row0, n, num_groups=10_000_000, seed=SEED, zipf=False):
     """key = mix64(u), u ~ U{0..num_groups-1}; v ~ U{0..10^6}; y = k/1024 with
-    k ~ U{0..1023}: the sum of y^2 is exact in float8 too."""
+    k ~ U{0..1023}: the sum of y^2 is exact in float8 too.  zipf: u is drawn
+    with P(u = k) ~ 1/(k+1) instead (Zipf, s = 1, by inverting its continuous
+    CDF ln(k)/ln(N)): a few keys take most of the rows."""
+    raw = _raw(seed, 21, row0, n)
+    if zipf:
+        x = (raw >> np.uint64(11)).astype(np.float64) / float(1 << 53)     # [0, 1)
+        u = np.minimum(np.floor(np.exp(x * np.log(float(num_groups)))).astype(np.uint64),
+                       np.uint64(num_groups)) - np.uint64(1)
+    else:
+        u = raw % np.uint64(num_groups)
     with np.errstate(over="ignore"):
-        key = _mix64(_raw(seed, 21, row0, n) % np.uint64(num_groups)).astype(np.int64)
+        key = _mix64(u).astype(np.int64)
     v = (_raw(seed, 22, row0, n) % np.uint64(1000001)).astype(np.int64)
     y = (_raw(seed, 23, row0, n) % np.uint64(1024)).astype(np.float64) / 1024.0
     return [(key, None), (v, None), (y, None)]
