@@ -13,3 +13,11 @@ for sel in 1 10 50; do
   done
 done
 PGSTROM_GATHER_PAYLOAD=1 bash tools/gpu_ncu.sh where_gather --workload where_agg
+# bytes in flight vs table size on the default path: a smaller CTA-local table leaves room
+# for a third stage (two in flight); 1000 groups need >= 1344 slots at the 75 % fill limit
+for cfg in "1728 2 2048" "1408 3 2048" "1344 3 2048" "1408 4 1024" "1728 3 1024" "1408 2 3072"; do
+  set -- $cfg
+  PGSTROM_SH_SLOTS=$1 PGSTROM_NUM_STAGES=$2 PGSTROM_TILE_ROWS=$3 timeout 120 python bench.py \
+      --workload where_agg --rows 50000000 --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 \
+      > gpurun_out/bench_where_slots$1_st$2_tile$3.json 2> gpurun_out/bench_where_slots$1_st$2_tile$3.err
+done
