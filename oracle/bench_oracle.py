@@ -263,12 +263,3 @@ def assert_rows_equal_expected(desc, device_rows, keys, exp, rel_tol=0.0):
 def assert_partial_equal_node(desc, gpreagg_node, device_rows, cols, rel_tol=0.0):
     keys, exp = expected_partial_node(gpreagg_node, cols)
     return assert_rows_equal_expected(desc, device_rows, keys, exp, rel_tol)
-
-
-# -- helpers used by workloads.smoke(): resolve the node from the plan ------
-def expected_partial(name, desc, cols):
-    raise NotImplementedError("use assert_partial_equal_node")
-
-
-def assert_partial_equal(desc, rows, exp):
-    raise NotImplementedError("use assert_partial_equal_node")
