@@ -238,9 +238,16 @@ DEVFN pg_int4_t
 pgfn_date_cmp_timestamp(cl_int *errcode, pg_date_t arg1, pg_timestamp_t arg2)
 {
     pg_int4_t       result;
-    pg_timestamp_t  dt1 = pgfn_date_timestamp(errcode, arg1);
+    pg_timestamp_t  dt1;
 
-    result.isnull = (dt1.isnull | arg2.isnull);
+    /* strict: with a NULL argument PostgreSQL does not call the function,
+     * so an out-of-range date must not raise anything either */
+    result.value = 0;
+    result.isnull = true;
+    if (arg1.isnull | arg2.isnull)
+        return result;
+    dt1 = pgfn_date_timestamp(errcode, arg1);
+    result.isnull = dt1.isnull;
     result.value = (result.isnull ? 0 : devfunc_int_comp(dt1.value, arg2.value));
     return result;
 }
@@ -249,9 +256,14 @@ DEVFN pg_int4_t
 pgfn_timestamp_cmp_date(cl_int *errcode, pg_timestamp_t arg1, pg_date_t arg2)
 {
     pg_int4_t       result;
-    pg_timestamp_t  dt2 = pgfn_date_timestamp(errcode, arg2);
+    pg_timestamp_t  dt2;
 
-    result.isnull = (arg1.isnull | dt2.isnull);
+    result.value = 0;
+    result.isnull = true;
+    if (arg1.isnull | arg2.isnull)
+        return result;
+    dt2 = pgfn_date_timestamp(errcode, arg2);
+    result.isnull = dt2.isnull;
     result.value = (result.isnull ? 0 : devfunc_int_comp(arg1.value, dt2.value));
     return result;
 }

@@ -1,0 +1,472 @@
+"""CPU: the code generator, end to end.  The CUDA source the planner half
+emits for a query (gpupreagg_qual_eval + gpupreagg_projection, the counterpart
+of what /root/reference/codegen.c:1065-1430 and gpupreagg.c:1449-1900 emit) is
+compiled with g++ against host stand-ins of the two CUDA-only headers - cut,
+at test time, out of the real kern_common.cuh / kern_gpupreagg.cuh, so the
+type templates, EVAL, the boolean tests, pagg_row and the vstore functions
+are the product's own text, and kern_mathlib / numeric / timelib / textlib are
+the real files - and run row by row against the oracle's evaluation of the
+same expression trees (oracle/pg_expr.py).  Hand-written queries plus a
+seeded fuzzer over typed random expression trees: NULL propagation,
+three-valued AND / OR / NOT, CASE, IS [NOT] NULL, casts, overflow / division
+by zero (-> StromError_CpuReCheck), cross-type comparison, date arithmetic,
+text comparison."""
+import ctypes as C
+import math
+import os
+import random
+import struct
+import subprocess
+
+import pytest
+
+from oracle import pg_expr, pg_typelib as T
+from oracle.pg_agg import PgError, f4
+from pg_strom_b200 import gpupreagg as gp
+from pg_strom_b200 import pgplan as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(ROOT, "pg_strom_b200", "csrc")
+SIM = os.path.join(HERE, "native", "_hostsim")
+CPU_RECHECK = 2
+GUCS = {"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on"}
+
+HOST_PREAMBLE = r'''
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+using std::isnan; using std::isinf;
+#define DEVFN static inline
+#ifndef INT_MAX
+#define SHRT_MAX    32767
+#define SHRT_MIN    (-32767-1)
+#define INT_MAX     2147483647
+#define INT_MIN     (-INT_MAX-1)
+#endif
+#undef LONG_MAX
+#undef LONG_MIN
+#define LONG_MAX    9223372036854775807LL
+#define LONG_MIN    (-LONG_MAX-1LL)
+static inline long long __mul64hi(long long a, long long b)
+{ return (long long)(((__int128)a * (__int128)b) >> 64); }
+static inline double __longlong_as_double(long long v)
+{ double d; memcpy(&d, &v, 8); return d; }
+static inline void STROM_SET_ERROR(cl_int *p_error, cl_int errcode)
+{
+    cl_int oldcode = *p_error;
+    if (StromErrorIsSignificant(errcode))
+    {
+        if (!StromErrorIsSignificant(oldcode))
+            *p_error = errcode;
+    }
+    else if (errcode > oldcode)
+        *p_error = errcode;
+}
+'''
+
+# CUDA decorations of the generated text itself (it starts with constexpr
+# helpers marked __host__ __device__)
+PRE = r'''
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __constant__
+#define __align__(x)
+'''
+
+WRAPPER = r'''
+struct host_kds
+{
+    const unsigned long long *vals;     /* one 8-byte word per staged slot */
+    unsigned int valid;                 /* bit per slot: NOT NULL */
+    template <typename T> bool fetch(int slot, cl_uint rowidx, T &out) const
+    {
+        union { unsigned long long u; T t; } cv;
+        cv.u = vals[slot];
+        out = cv.t;
+        return ((valid >> slot) & 1U) != 0;
+    }
+};
+extern "C" int sim_row(const unsigned long long *vals, unsigned int valid,
+                       const void *kparams, const void *ktoast,
+                       unsigned long long *key_out, unsigned char *key_null,
+                       unsigned long long *agg_out, unsigned char *agg_null, int *passed)
+{
+    cl_int e1 = 0, e2 = 0;
+    host_kds k = { vals, valid };
+    pagg_row prow;
+    bool v = gpupreagg_qual_eval(&e1, (const kern_parambuf *)kparams, k, ktoast, 0);
+    memset(&prow, 0, sizeof(prow));
+    *passed = v ? 1 : 0;
+    if (v && e1 == 0)
+        gpupreagg_projection(&e2, (const kern_parambuf *)kparams, k, prow, ktoast, 0, 0);
+    for (int i = 0; i < GPUPREAGG_NUM_KEYS; i++)
+    { key_out[i] = prow.key[i].ulong_val; key_null[i] = prow.key[i].isnull; }
+    for (int i = 0; i < GPUPREAGG_NUM_AGGS; i++)
+    { agg_out[i] = prow.agg[i].ulong_val; agg_null[i] = prow.agg[i].isnull; }
+    return e1 | (e2 << 8);
+}
+'''
+
+
+def _cut(path, start, end):
+    text = open(path).read()
+    i = text.index(start)
+    return text[i:text.index(end, i)]
+
+
+@pytest.fixture(scope="module")
+def simdir(lib):
+    os.makedirs(SIM, exist_ok=True)
+    common = _cut(os.path.join(CSRC, "kern_common.cuh"),
+                  "#define STROMCL_SIMPLE_DATATYPE_TEMPLATE", "#endif  /* KERN_COMMON_CUH */")
+    with open(os.path.join(SIM, "kern_common.cuh"), "w") as f:
+        f.write("#pragma once\n" + HOST_PREAMBLE + common)
+    pagg = _cut(os.path.join(CSRC, "kern_gpupreagg.cuh"),
+                "#define PGS_MAX(a,b)", "/* ------------------------------------------------------------------\n * state cells.")
+    with open(os.path.join(SIM, "kern_gpupreagg.cuh"), "w") as f:
+        f.write("#pragma once\n"
+                "static inline double pgs_f8_canon(double v)\n"
+                "{ if (isnan(v)) return __longlong_as_double(0x7FF8000000000000LL);"
+                " return (v == 0.0) ? 0.0 : v; }\n" + pagg)
+    return SIM
+
+
+_nbuilt = [0]
+
+
+def build_sim(plan, simdir):
+    _nbuilt[0] += 1
+    src = os.path.join(simdir, "q%d.cpp" % _nbuilt[0])
+    out = os.path.join(simdir, "q%d.so" % _nbuilt[0])
+    with open(src, "w") as f:
+        f.write(PRE + plan.kernel_source() + WRAPPER)
+    r = subprocess.run(["g++", "-std=c++17", "-O0", "-fPIC", "-shared", "-w", "-ffp-contract=off",
+                        "-I", simdir, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+                        "-o", out, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[:3000]
+    so = C.CDLL(out)
+    so.sim_row.argtypes = [C.POINTER(C.c_uint64), C.c_uint, C.c_char_p, C.c_char_p,
+                           C.POINTER(C.c_uint64), C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p,
+                           C.POINTER(C.c_int)]
+    return so
+
+
+def pack(value, typ):
+    if typ == "bool":
+        return int(bool(value))
+    if typ in ("int2", "int4", "int8", "date", "time", "timestamp"):
+        return value & 0xFFFFFFFFFFFFFFFF if typ in ("int8", "time", "timestamp") else \
+            value & (0xFFFF if typ == "int2" else 0xFFFFFFFF)
+    if typ == "float4":
+        return struct.unpack("<I", struct.pack("<f", value))[0]
+    if typ == "float8":
+        return struct.unpack("<Q", struct.pack("<d", value))[0]
+    raise KeyError(typ)
+
+
+def same(a, b, typ):
+    if a is None or b is None:
+        return a is None and b is None
+    if typ in ("float4", "float8"):
+        a, b = float(a), float(b)
+        if math.isnan(a) or math.isnan(b):
+            return math.isnan(a) and math.isnan(b)
+        return a == b
+    return a == b
+
+
+def find_node(tree):
+    n = tree
+    while n is not None:
+        if n.get("node") == "CustomPlan" and n.get("custom_name") == "GpuPreAgg":
+            return n
+        n = n.get("lefttree")
+    raise AssertionError("no GpuPreAgg node")
+
+
+def check_query(table, tree, rows, simdir):
+    """Runs every row through the compiled generated code and through the
+    oracle; returns (#passed, #errors) for the caller's sanity checks."""
+    plan = gp.Plan(tree, gucs=GUCS)
+    try:
+        assert plan.num_gpupreagg == 1, plan.reject_reason
+        desc = plan.describe()
+        node = find_node(plan.tree())
+        so = build_sim(plan, simdir)
+        kparams = plan.kparams()
+        incols = desc["incol_index"]
+        coltypes = [t for _, t in table.columns]
+        cols = desc["columns"]
+        keycols = [c for c in cols if c["role"] == 1]
+        aggcols = [c for c in cols if c["role"] == 2]
+        quals = node.get("outer_quals") or []
+        tlist = node["targetlist"]
+        npass = nerr = 0
+        vals = (C.c_uint64 * max(1, len(incols)))()
+        key_out = (C.c_uint64 * 16)()
+        agg_out = (C.c_uint64 * 32)()
+        key_null = C.create_string_buffer(16)
+        agg_null = C.create_string_buffer(32)
+        passed = C.c_int()
+        for row in rows:
+          try:
+            toast = bytearray(b"\0" * 8)
+            valid = 0
+            for slot, c in enumerate(incols):
+                v = row[c]
+                if v is None:
+                    vals[slot] = 0
+                    continue
+                valid |= 1 << slot
+                if coltypes[c] in ("text", "bpchar"):
+                    while len(toast) % 4:
+                        toast.append(0)
+                    vals[slot] = len(toast)
+                    toast += T.varlena(v)
+                else:
+                    vals[slot] = pack(v, coltypes[c])
+            rc = so.sim_row(vals, valid, kparams, bytes(toast), key_out, key_null,
+                            agg_out, agg_null, C.byref(passed))
+            e1, e2 = rc & 0xff, rc >> 8
+            # the device evaluates every qual (no short circuit across the
+            # implicit AND): an error anywhere flags the row
+            qvals, qerr = [], False
+            for q in quals:
+                try:
+                    qvals.append(pg_expr.evaluate(q, row))
+                except PgError:
+                    qerr = True
+            if qerr:
+                assert e1 == CPU_RECHECK, (row, rc)
+                nerr += 1
+                continue
+            assert e1 == 0, (row, rc)
+            want = all(v is True for v in qvals)
+            assert bool(passed.value) == want, (row, qvals)
+            if not want:
+                continue
+            npass += 1
+            exp, perr = {}, False
+            for c in cols:
+                if c["role"] == 0:
+                    continue
+                try:
+                    exp[c["resno"]] = pg_expr.evaluate(tlist[c["resno"] - 1]["expr"], row)
+                except PgError:
+                    perr = True
+            # a text key longer than 7 bytes does not fit the key word
+            # ("kernel text"): that row is the host's
+            for c in keycols:
+                v = exp.get(c["resno"])
+                if c["type"] in ("text", "bpchar") and v is not None and \
+                        len(v.rstrip(b" ") if c["type"] == "bpchar" else v) > 7:
+                    perr = True
+            if perr:
+                assert e2 == CPU_RECHECK, (row, rc)
+                nerr += 1
+                continue
+            assert e2 == 0, (row, rc)
+            for i, c in enumerate(keycols):
+                got = None if key_null.raw[i] != b"\0"[0] else \
+                    gp.decode_datum(key_out[i], False, c["type"], c.get("typmod", -1))
+                e = exp[c["resno"]]
+                if c["type"] in ("float4", "float8") and e is not None and e == 0:
+                    e = 0.0                                     # -0 groups with +0
+                assert same(got, e, c["type"]), (row, c["text"], got, e)
+            for i, c in enumerate(aggcols):
+                got = None if agg_null.raw[i] != b"\0"[0] else \
+                    gp.decode_datum(agg_out[i], False, c["type"])
+                e = exp[c["resno"]]
+                if c["type"] == "float4" and e is not None:
+                    e = f4(e)
+                assert same(got, e, c["type"]), (row, c["text"], got, e)
+          except AssertionError as exc:
+            raise AssertionError("%s\n%s" % (exc, "\n".join(plan.explain()[:10]))) from None
+        return npass, nerr
+    finally:
+        plan.free()
+
+
+# ---- data ------------------------------------------------------------------
+TBL = P.Table("fz", [("b", "bool"), ("s2", "int2"), ("i4", "int4"), ("i8", "int8"),
+                     ("f4", "float4"), ("f8", "float8"), ("d", "date"), ("ts", "timestamp"),
+                     ("tx", "text"), ("k", "int4")])
+EDGE = {
+    "bool": [True, False],
+    "int2": [0, 1, -1, 32767, -32768, 100, -100, 7],
+    "int4": [0, 1, -1, 2147483647, -2147483648, 65536, -65536, 10, 3],
+    "int8": [0, 1, -1, 2 ** 63 - 1, -2 ** 63, 2 ** 32, -2 ** 32, 3037000500, 5],
+    "float4": [0.0, -0.0, 1.0, -1.5, 2.5, 3.4e38, -3.4e38, 1e-38, 16777216.0, float("inf"),
+               float("nan")],
+    "float8": [0.0, -0.0, 1.0, -1.5, 2.5, 0.5, 1e308, -1e308, 1e-308, 2147483647.5,
+               9.3e18, float("inf"), float("-inf"), float("nan"), 32767.5],
+    "date": [0, 1, -1, 7305, T.DATE_NOBEGIN, T.DATE_NOEND, 106751992, -2451545, 2147483000],
+    "timestamp": [0, 1, -1, T.DT_NOBEGIN, T.DT_NOEND, 631152000000000, 86400000000,
+                  -86400000001, 2 ** 62],
+    "text": [b"", b"a", b"abc", b"abd", b"ab", b"b", b"\xc3\xa9", b"abc ", b"zzzzzzzzzzzz"],
+}
+
+
+def rand_value(typ, rng):
+    if rng.random() < 0.12:
+        return None
+    if rng.random() < 0.55:
+        v = rng.choice(EDGE[typ])
+    elif typ == "bool":
+        v = rng.random() < 0.5
+    elif typ in ("int2", "int4", "int8"):
+        bits = {"int2": 15, "int4": 31, "int8": 63}[typ]
+        v = rng.randrange(-2 ** bits, 2 ** bits) >> rng.choice([0, bits // 2, bits - 3])
+    elif typ in ("float4", "float8"):
+        v = rng.uniform(-1, 1) * 10.0 ** rng.randrange(-6, 12)
+    elif typ == "date":
+        v = rng.randrange(-20000, 20000)
+    elif typ == "timestamp":
+        v = rng.randrange(-10 ** 15, 10 ** 15)
+    else:
+        v = bytes(rng.choice(b"abz ") for _ in range(rng.randrange(0, 5)))
+    if typ == "float4":
+        v = f4(v)
+    return v
+
+
+def rand_rows(n, rng):
+    types = [t for _, t in TBL.columns]
+    return [tuple(rand_value(t, rng) for t in types[:-1]) + (rng.randrange(0, 5),)
+            for _ in range(n)]
+
+
+# ---- random typed expressions ----------------------------------------------
+NUM = ("int2", "int4", "int8", "float4", "float8")
+COLS = {"bool": ["b"], "int2": ["s2"], "int4": ["i4", "k"], "int8": ["i8"], "float4": ["f4"],
+        "float8": ["f8"], "date": ["d"], "timestamp": ["ts"], "text": ["tx"]}
+CMP = ["=", "<>", "<", "<=", ">", ">="]
+
+
+def const_of(typ, rng):
+    v = rng.choice([x for x in EDGE[typ] if not (isinstance(x, float) and (x != x or abs(x) == math.inf))])
+    if typ == "text":
+        return P.Const("text", v.decode("utf-8", "replace").rstrip("�") or "a")
+    if typ == "bool":
+        return P.Const("bool", v)
+    if typ in ("float4", "float8"):
+        return P.Const(typ, repr(float(v)))
+    return P.Const(typ, v)
+
+
+def gen(typ, depth, rng):
+    """Random expression of SQL type `typ`."""
+    if depth <= 0 or rng.random() < 0.25:
+        if rng.random() < 0.7 or typ == "text":
+            return TBL.col(rng.choice(COLS[typ]))
+        return const_of(typ, rng)
+    if typ == "bool":
+        kind = rng.random()
+        if kind < 0.35:
+            t = rng.choice(NUM)
+            u = rng.choice(NUM) if rng.random() < 0.4 else t
+            try:
+                return P.Op(rng.choice(CMP), gen(t, depth - 1, rng), gen(u, depth - 1, rng))
+            except TypeError:
+                return P.Op(rng.choice(CMP), gen(t, depth - 1, rng), gen(t, depth - 1, rng))
+        if kind < 0.45:
+            a, b = rng.choice([("date", "date"), ("timestamp", "timestamp"),
+                               ("date", "timestamp"), ("timestamp", "date")])
+            return P.Op(rng.choice(CMP), gen(a, depth - 1, rng), gen(b, depth - 1, rng))
+        if kind < 0.55:
+            return P.Op(rng.choice(CMP), gen("text", 0, rng), const_of("text", rng), collation="C")
+        if kind < 0.70:
+            n = rng.choice([2, 2, 3])
+            mk = P.And if rng.random() < 0.5 else P.Or
+            return mk(*[gen("bool", depth - 1, rng) for _ in range(n)])
+        if kind < 0.78:
+            return P.Not(gen("bool", depth - 1, rng))
+        if kind < 0.90:
+            t = rng.choice(list(COLS))
+            return P.IsNull(gen(t, depth - 1, rng) if t != "text" else TBL.col("tx"),
+                            notnull=rng.random() < 0.5)
+        return P.Case([(gen("bool", depth - 1, rng), gen("bool", depth - 1, rng))],
+                      gen("bool", depth - 1, rng) if rng.random() < 0.7 else None, "bool")
+    if typ in NUM:
+        kind = rng.random()
+        if kind < 0.45:
+            op = rng.choice(["+", "-", "*", "/"] + (["%"] if typ in ("int2", "int4", "int8") else []))
+            return P.Op(op, gen(typ, depth - 1, rng), gen(typ, depth - 1, rng))
+        if kind < 0.75:
+            src = rng.choice([t for t in NUM if t != typ])
+            return P.Cast(gen(src, depth - 1, rng), typ)
+        if kind < 0.9:
+            return P.Case([(gen("bool", depth - 1, rng), gen(typ, depth - 1, rng))],
+                          gen(typ, depth - 1, rng) if rng.random() < 0.7 else None, typ)
+        if typ == "int4" and rng.random() < 0.5:
+            return P.Op("-", gen("date", depth - 1, rng), gen("date", depth - 1, rng))
+        return gen(typ, 0, rng)
+    if typ == "date":
+        kind = rng.random()
+        if kind < 0.4:
+            return P.Op(rng.choice(["+", "-"]), gen("date", depth - 1, rng), gen("int4", depth - 1, rng))
+        if kind < 0.6:
+            return P.Cast(gen("timestamp", depth - 1, rng), "date")
+        return gen("date", 0, rng)
+    if typ == "timestamp":
+        if rng.random() < 0.5:
+            return P.Cast(gen("date", depth - 1, rng), "timestamp")
+        return gen("timestamp", 0, rng)
+    return gen(typ, 0, rng)
+
+
+def test_hand_written_queries(simdir):
+    rng = random.Random(100)
+    rows = rand_rows(400, rng)
+    t = TBL
+    cnt = (P.Agg("count", star=True), "count")
+    q1 = P.make_agg_plan(
+        t, [(t.col("k"), "k"), cnt, (P.Agg("sum", [t.col("i4")]), "sum"),
+            (P.Agg("avg", [t.col("f8")]), "avg"), (P.Agg("max", [t.col("s2")]), "max"),
+            (P.Agg("count", [t.col("tx")]), "count")],
+        group_by=["k"], num_groups=8,
+        where=[P.Or(P.Op("<", t.col("i4"), P.Const("int4", 100)), P.IsNull(t.col("f8")))])
+    npass, nerr = check_query(t, q1, rows, simdir)
+    assert npass > 50
+    q2 = P.make_agg_plan(
+        t, [(t.col("f8"), "f8"), cnt,
+            (P.Agg("sum", [P.Op("*", t.col("i4"), t.col("s2"))]), "sum"),
+            (P.Agg("min", [P.Op("/", t.col("i8"), P.Cast(t.col("i4"), "int8"))]), "min"),
+            (P.Agg("variance", [t.col("f8")]), "variance"),
+            (P.Agg("corr", [t.col("f8"), t.col("f4")]), "corr")],
+        group_by=["f8"], num_groups=8,
+        where=[P.Not(P.And(t.col("b"), P.Op(">", t.col("d"), P.Const("date", 0))))])
+    npass, nerr = check_query(t, q2, rows, simdir)
+    assert npass > 50 and nerr > 5          # int4 * int2 overflow, division by zero
+
+
+def test_fuzz_generated_code(simdir):
+    rng = random.Random(2024)
+    rows = rand_rows(250, rng)
+    total_pass = total_err = built = 0
+    for _ in range(60):
+        quals = [gen("bool", 4, rng) for _ in range(rng.choice([1, 1, 2]))]
+        aggs = []
+        for _ in range(rng.choice([1, 2, 3])):
+            typ = rng.choice(NUM)
+            fn = rng.choice(["min", "max", "sum", "avg", "count"] if typ != "int8"
+                            else ["min", "max", "avg", "count"])
+            aggs.append((P.Agg(fn, [gen(typ, 3, rng)]), fn))
+        keyed = rng.random() < 0.6
+        keycol = rng.choice(["k", "f8", "d", "b", "tx", "f4", "i8", "ts", "s2"])
+        targets = ([(TBL.col(keycol), keycol)] if keyed else []) + \
+            [(P.Agg("count", star=True), "count")] + aggs
+        tree = P.make_agg_plan(TBL, targets, group_by=[keycol] if keyed else [],
+                               where=quals, num_groups=8)
+        plan = gp.Plan(tree, gucs=GUCS)
+        ok = plan.num_gpupreagg == 1 and "#define GPUPREAGG_HAS_QUAL 1" in plan.kernel_source()
+        plan.free()
+        if not ok:
+            continue            # e.g. an aggregate the catalogue does not offload
+        npass, nerr = check_query(TBL, tree, rows, simdir)
+        total_pass += npass
+        total_err += nerr
+        built += 1
+    assert built >= 40 and total_pass > 500 and total_err > 200
