@@ -18,8 +18,11 @@ because the oracle is pg_strom.enabled=off.
 
 Parity: no golden vectors exist for these functions in the reference's test
 suite (its regression SQL only uses integer / float / numeric columns), so
-this part of the oracle is "parity unpinned" - it is anchored on PostgreSQL's
-documented behaviour only.
+this part of the oracle is "parity unpinned" against the reference; it is
+anchored on the known answers PostgreSQL's documentation publishes
+(tests/test_typelib_device_code.py::test_documented_examples: epochs, Julian
+day numbers, the date / time operator examples) and on the identity
+date2j(j2date(d)) = d.
 """
 from decimal import Decimal
 

@@ -84,6 +84,38 @@ def test_julian_identity():
         assert T.date2j(*T.j2date(jd)) == jd
 
 
+def test_documented_examples(shim):
+    """Known answers published in PostgreSQL's documentation (Date/Time
+    Operators table and the datatype-datetime chapter): the epoch of date and
+    timestamp is 2000-01-01, date '2001-09-28' + 7 = date '2001-10-05',
+    date '2001-10-01' - date '2001-09-28' = 3, date '2001-09-28' + time
+    '03:00' = timestamp '2001-09-28 03:00:00', date '2001-09-28' - 7 =
+    date '2001-09-21'; Julian day 0 is 4714-11-24 BC (year -4713)."""
+    def d(y, m, dd):
+        return T.date2j(y, m, dd) - T.POSTGRES_EPOCH_JDATE
+    assert d(2000, 1, 1) == 0 and T.date2j(2000, 1, 1) == 2451545
+    assert T.j2date(0) == (-4713, 11, 24)
+    assert T.date2j(1970, 1, 1) == 2440588          # UNIX_EPOCH_JDATE
+    out, isnull = C.c_int64(), C.c_int()
+    hour = 3600 * 1000000
+    cases = [(0, d(2001, 9, 28), 7, d(2001, 10, 5)),                # date + integer
+             (1, d(2001, 9, 28), 7, d(2001, 9, 21)),                # date - integer
+             (2, d(2001, 10, 1), d(2001, 9, 28), 3),                # date - date
+             (3, d(2001, 9, 28), 3 * hour, d(2001, 9, 28) * T.USECS_PER_DAY + 3 * hour),
+             (4, 7, d(2001, 9, 28), d(2001, 10, 5))]                # integer + date
+    for fn, a, b, want in cases:
+        assert shim.shim_time_binop(fn, a, b, C.byref(out), C.byref(isnull)) == 0
+        assert not isnull.value and out.value == want, (fn, a, b, out.value, want)
+    # timestamp '2001-09-28 03:00:00' :: date / :: time
+    ts = d(2001, 9, 28) * T.USECS_PER_DAY + 3 * hour
+    assert shim.shim_time_cast(0, ts, C.byref(out), C.byref(isnull)) == 0
+    assert out.value == d(2001, 9, 28) and T.j2date(out.value + T.POSTGRES_EPOCH_JDATE) == (2001, 9, 28)
+    assert shim.shim_time_cast(1, ts, C.byref(out), C.byref(isnull)) == 0 and out.value == 3 * hour
+    # a timestamp before the epoch: 1999-12-31 23:00 is day -1, 23:00
+    assert shim.shim_time_cast(0, -hour, C.byref(out), C.byref(isnull)) == 0 and out.value == -1
+    assert shim.shim_time_cast(1, -hour, C.byref(out), C.byref(isnull)) == 0 and out.value == 23 * hour
+
+
 def test_time_casts(shim):
     rng = random.Random(2)
     out, isnull = C.c_int64(), C.c_int()
