@@ -594,12 +594,24 @@ psum_arg_is_widened_int(const JsonPtr &arg)
             if (!psum_arg_is_widened_int(a->arr[i]->getp("result")))
                 return false;
         JsonPtr def = arg->getp("defresult");
-        if (def && !def->is_null() && def->s("node") != "Const")
+        if (def && !def->is_null())
             return psum_arg_is_widened_int(def);
         return true;
     }
     if (tag == "Const")
-        return true;
+    {
+        /* a literal counts only when its value fits 32 bits (the addend of
+         * a LONGS cell is taken from the low word and sign-extended) */
+        if (arg->flag("constisnull"))
+            return true;
+        const Json *jv = arg->get("constvalue");
+        if (!jv || (jv->kind != Json::String && jv->kind != Json::Number))
+            return false;
+        char *end = NULL;
+        long long v = strtoll(jv->str.c_str(), &end, 10);
+        return (end && *end == '\0' && !jv->str.empty() &&
+                v >= -2147483648LL && v <= 2147483647LL);
+    }
     return false;
 }
 

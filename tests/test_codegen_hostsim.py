@@ -52,6 +52,20 @@ static inline long long __mul64hi(long long a, long long b)
 { return (long long)(((__int128)a * (__int128)b) >> 64); }
 static inline double __longlong_as_double(long long v)
 { double d; memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d)
+{ long long v; memcpy(&v, &d, 8); return v; }
+static inline unsigned int __float_as_uint(float f)
+{ unsigned int v; memcpy(&v, &f, 4); return v; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned int min(unsigned int a, unsigned int b) { return a < b ? a : b; }
+static inline unsigned int max(unsigned int a, unsigned int b) { return a > b ? a : b; }
+/* single-threaded stand-ins of the atomics the ATOMIC / SHARED flavours use */
+template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <typename T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <typename T> static inline T atomicCAS(T *p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+template <typename T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
 static inline void STROM_SET_ERROR(cl_int *p_error, cl_int errcode)
 {
     cl_int oldcode = *p_error;
@@ -107,6 +121,143 @@ extern "C" int sim_row(const unsigned long long *vals, unsigned int valid,
     { agg_out[i] = prow.agg[i].ulong_val; agg_null[i] = prow.agg[i].isnull; }
     return e1 | (e2 << 8);
 }
+
+/* ---- aggregation: the same rows through every flavour of the merge rules ----
+ * The cell formats of the register flavours (PLAIN / THREAD, no GROUP BY) and
+ * of the table flavours (ATOMIC / SHARED, GROUP BY) differ (e.g. int4 min /
+ * max: zero- vs sign-extended), so each query runs the flavours its kernels
+ * use:   no GROUP BY: 0 PLAIN, 1 THREAD, 2 PLAIN(even rows) <- PLAIN(odd rows)
+ *        GROUP BY   : 0 ATOMIC, 1 SHARED, 2 ATOMIC(even) <- SHARED(odd), the
+ *                     spill of a CTA-local table into the global one
+ * state 3 holds the odd rows until agg_finish merges them into state 2. */
+#define SIM_NFLAV   4
+#define SIM_MAXGRP  1024
+struct sim_group
+{
+    bool        used;
+    cl_ulong    keys[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
+    cl_uint     knull;
+    cl_ulong    cells[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+    cl_uint     nn;
+};
+static sim_group sim_state[SIM_NFLAV][SIM_MAXGRP];
+static unsigned int sim_nrows;
+
+extern "C" void agg_reset(void)
+{
+    memset(sim_state, 0, sizeof(sim_state));
+    sim_nrows = 0;
+}
+static sim_group *sim_find(int f, const pagg_row &prow)
+{
+    cl_uint knull = 0;
+    cl_ulong keys[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)] = {0};
+    for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+    {
+        if (prow.key[k].isnull) knull |= (1U << k);
+        else keys[k] = prow.key[k].ulong_val;
+    }
+    for (int g = 0; g < SIM_MAXGRP; g++)
+    {
+        sim_group *s = &sim_state[f][g];
+        if (!s->used)
+        {
+            s->used = true;
+            s->knull = knull;
+            memcpy(s->keys, keys, sizeof(keys));
+            pgs_cells_init(s->cells);
+            s->nn = 0;
+            return s;
+        }
+        if (s->knull == knull && memcmp(s->keys, keys, sizeof(keys)) == 0)
+            return s;
+    }
+    return NULL;
+}
+/* returns the row's error code; 0x100 = filtered by the qual */
+extern "C" int agg_row(const unsigned long long *vals, unsigned int valid,
+                       const void *kparams, const void *ktoast)
+{
+    cl_int e = 0;
+    host_kds k = { vals, valid };
+    pagg_row prow;
+    memset(&prow, 0, sizeof(prow));
+    bool v = gpupreagg_qual_eval(&e, (const kern_parambuf *)kparams, k, ktoast, 0);
+    if (e != 0) return e;
+    if (!v) return 0x100;
+    gpupreagg_projection(&e, (const kern_parambuf *)kparams, k, prow, ktoast, 0, 0);
+    gpupreagg_aggcheck(&e, prow);
+    if (e != 0) return e;
+    unsigned int odd = (sim_nrows++ & 1U);
+    for (int f = 0; f < SIM_NFLAV; f++)
+    {
+        if ((f == 2 && odd) || (f == 3 && !odd))
+            continue;
+        sim_group *s = sim_find(f, prow);
+        if (!s) return -1;
+#if GPUPREAGG_NUM_KEYS == 0
+        if (f == 1)
+        {
+            bool nnflag[PGS_MAX(PGS_NUM_NNCLASSES, 1)];
+            for (int i = 0; i < PGS_MAX(PGS_NUM_NNCLASSES, 1); i++) nnflag[i] = false;
+            gpupreagg_aggcalc_thread(s->cells, prow, true, nnflag);
+            s->nn |= pgs_nnflags_to_mask(nnflag);
+        }
+        else
+            s->nn |= gpupreagg_aggcalc_plain(s->cells, prow, true);
+#else
+        if (f == 1 || f == 3)
+            s->nn |= gpupreagg_aggcalc_shared(s->cells, prow);
+        else
+            s->nn |= gpupreagg_aggcalc_atomic(s->cells, prow);
+#endif
+    }
+    return 0;
+}
+/* state 3 -> state 2 with the state -> state rules */
+extern "C" int agg_finish(void)
+{
+    for (int g = 0; g < SIM_MAXGRP; g++)
+    {
+        sim_group *src = &sim_state[3][g];
+        if (!src->used) continue;
+        pagg_row fake;
+        memset(&fake, 0, sizeof(fake));
+        for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+        { fake.key[k].isnull = (src->knull >> k) & 1U; fake.key[k].ulong_val = src->keys[k]; }
+        sim_group *dst = sim_find(2, fake);
+        if (!dst) return -1;
+#if GPUPREAGG_NUM_KEYS == 0
+        gpupreagg_aggmerge_plain(dst->cells, src->cells, src->nn);
+#else
+        gpupreagg_aggmerge_atomic(dst->cells, src->cells, src->nn);
+#endif
+        dst->nn |= src->nn;
+    }
+    return 0;
+}
+/* partial rows of one flavour into a TUPSLOT store prepared by the host library */
+extern "C" int agg_flush(int f, kern_data_store *kds_dst)
+{
+    kern_gpupreagg kg;
+    memset(&kg, 0, sizeof(kg));
+    if (GPUPREAGG_NUM_KEYS == 0 && !sim_state[f][0].used)
+    {
+        pagg_row none;              /* no row at all: the identity state */
+        memset(&none, 0, sizeof(none));
+        sim_find(f, none);
+    }
+    for (int g = 0; g < SIM_MAXGRP; g++)
+    {
+        sim_group *s = &sim_state[f][g];
+        if (!s->used) continue;
+        cl_uint nsplit = pgs_flush_nsplit(s->cells);
+        cl_uint base = kds_dst->nitems;
+        kds_dst->nitems += nsplit;
+        pgs_flush_rows(kds_dst, &kg, base, nsplit, s->keys, s->knull, s->cells, s->nn);
+    }
+    return kg.status;
+}
 '''
 
 
@@ -123,13 +274,21 @@ def simdir(lib):
                   "#define STROMCL_SIMPLE_DATATYPE_TEMPLATE", "#endif  /* KERN_COMMON_CUH */")
     with open(os.path.join(SIM, "kern_common.cuh"), "w") as f:
         f.write("#pragma once\n" + HOST_PREAMBLE + common)
-    pagg = _cut(os.path.join(CSRC, "kern_gpupreagg.cuh"),
-                "#define PGS_MAX(a,b)", "/* ------------------------------------------------------------------\n * state cells.")
+    real = os.path.join(CSRC, "kern_gpupreagg.cuh")
+    # pagg_row + vstore, the state cells and the PLAIN / THREAD / ATOMIC merge
+    # rules ... (the typed register accumulators in between are inline PTX)
+    part1 = _cut(real, "#define PGS_MAX(a,b)", "/* ---- typed thread accumulators")
+    # ... the SHARED flavours, 128-bit and numeric sums, row -> state and
+    # state -> state functions (without struct pgs_tacc) ...
+    part2 = _cut(real, "/* ---- SHARED flavours", "/* typed per-thread state of the no-group fast path")
+    part3 = _cut(real, "DEVFN void\npgs_row_special", "/* ------------------------------------------------------------------\n * device-resident session state")
+    # ... and the flush: state -> TUPSLOT partial rows, splitting big counts / sums
+    part4 = _cut(real, "#define PGS_INT4_MAX", "/* launched with whole warps.")
     with open(os.path.join(SIM, "kern_gpupreagg.cuh"), "w") as f:
         f.write("#pragma once\n"
                 "static inline double pgs_f8_canon(double v)\n"
                 "{ if (isnan(v)) return __longlong_as_double(0x7FF8000000000000LL);"
-                " return (v == 0.0) ? 0.0 : v; }\n" + pagg)
+                " return (v == 0.0) ? 0.0 : v; }\n" + part1 + part2 + part3 + part4)
     return SIM
 
 
@@ -470,3 +629,216 @@ def test_fuzz_generated_code(simdir):
         total_err += nerr
         built += 1
     assert built >= 40 and total_pass > 500 and total_err > 200
+
+
+# ---- aggregation semantics ---------------------------------------------------
+PSUM_LIMIT = {"DOUBLE": 2.0 ** 960, "FLOAT": 2.0 ** 88}
+
+
+def _canon(v):
+    from oracle.partial import _canon_key
+    return _canon_key(v)
+
+
+def check_aggregation(table, tree, rows, simdir, lib):
+    """All rows through qual + projection + the flavours of the merge rules
+    the query's kernels use (no GROUP BY: PLAIN, THREAD, two PLAIN halves
+    merged state -> state; GROUP BY: ATOMIC, SHARED, a SHARED half spilled
+    into an ATOMIC half) and the flush, compiled for the host; the partial
+    rows must equal the oracle's (oracle/partial.py).  Returns (#aggregated,
+    #rechecked)."""
+    from oracle import bench_oracle, partial
+    plan = gp.Plan(tree, gucs=GUCS)
+    try:
+        assert plan.num_gpupreagg == 1, plan.reject_reason
+        desc = plan.describe()
+        node = find_node(plan.tree())
+        so = build_sim(plan, simdir)
+        so.agg_row.argtypes = [C.POINTER(C.c_uint64), C.c_uint, C.c_char_p, C.c_char_p]
+        so.agg_flush.argtypes = [C.c_int, C.c_void_p]
+        kparams = plan.kparams()
+        incols = desc["incol_index"]
+        coltypes = [t for _, t in table.columns]
+        cols = desc["columns"]
+        quals = node.get("outer_quals") or []
+        tlist = node["targetlist"]
+        vals = (C.c_uint64 * max(1, len(incols)))()
+        so.agg_reset()
+        ok_rows, nrecheck = [], 0
+        for row in rows:
+            toast = bytearray(b"\0" * 8)
+            valid = 0
+            for slot, c in enumerate(incols):
+                v = row[c]
+                if v is None:
+                    vals[slot] = 0
+                    continue
+                valid |= 1 << slot
+                if coltypes[c] in ("text", "bpchar"):
+                    while len(toast) % 4:
+                        toast.append(0)
+                    vals[slot] = len(toast)
+                    toast += T.varlena(v)
+                else:
+                    vals[slot] = pack(v, coltypes[c])
+            rc = so.agg_row(vals, valid, kparams, bytes(toast))
+            # what the row must have done
+            want = 0
+            try:
+                qv = [pg_expr.evaluate(q, row) for q in quals]
+            except PgError:
+                qv, want = [], CPU_RECHECK
+            if want == 0 and not all(v is True for v in qv):
+                want = 0x100
+            if want == 0:
+                try:
+                    for c in cols:
+                        if c["role"] == 0:
+                            continue
+                        v = pg_expr.evaluate(tlist[c["resno"] - 1]["expr"], row)
+                        if c["role"] == 1 and c["type"] in ("text", "bpchar") and \
+                                v is not None and len(v) > 7:
+                            want = CPU_RECHECK      # key does not fit the key word
+                        if c["type"] == "numeric" and v is not None:
+                            # the 64-bit device numeric: 57-bit mantissa, scale <= 32;
+                            # a sum cell takes scale <= 16 and < 2^96 at that scale
+                            from decimal import Decimal
+                            d = Decimal(v)
+                            if not d.is_finite():           # numeric NaN: host only
+                                want = CPU_RECHECK
+                                continue
+                            scale = max(0, -d.as_tuple().exponent)
+                            mant = int(abs(d).scaleb(scale))
+                            if mant > (1 << 57) - 2 or scale > 32 or \
+                                    (c["op"] == "PSUM" and
+                                     (scale > 16 or (mant * 10 ** (16 - scale)) >> 96)):
+                                want = CPU_RECHECK
+                        if c["role"] == 2 and c["op"] == "PSUM" and v is not None and \
+                                c["cell_type"] in PSUM_LIMIT and \
+                                abs(float(v)) > PSUM_LIMIT[c["cell_type"]]:
+                            want = CPU_RECHECK      # could overflow a sum: host's row
+                except PgError:
+                    want = CPU_RECHECK
+            assert rc == want, (row, rc, want, "\n".join(plan.explain()[:8]))
+            if want == 0:
+                ok_rows.append(row)
+            elif want == CPU_RECHECK:
+                nrecheck += 1
+        assert so.agg_finish() == 0
+        exp, _ = partial.partial_rows(node, ok_rows, len(table.columns))
+        exp = {tuple(_canon(k) for k in key): v for key, v in exp.items()}
+        ncols = len(cols)
+        colmeta = (gp.kern_colmeta * ncols)()
+        lib.pgs_plan_result_colmeta(plan.handle, 0, colmeta, ncols)
+        length = lib.pgstrom_kds_tupslot_length(ncols, 4096)
+        values = (C.c_uint64 * ncols)()
+        isnull = C.create_string_buffer(ncols)
+        for flavour in range(3):
+            buf = C.create_string_buffer(length)
+            gp.check(lib.pgstrom_kds_tupslot_init(buf, length, ncols, colmeta, 4096))
+            assert so.agg_flush(flavour, buf) == 0
+            kds = gp.kern_data_store.from_buffer(buf)
+            drows = []
+            for r in range(kds.nitems):
+                gp.check(lib.pgstrom_fetch_data_store(buf, r, values, isnull))
+                drows.append(tuple(gp.decode_datum(values[i], isnull.raw[i] != 0, cols[i]["type"],
+                                                   cols[i].get("typmod", -1))
+                                   for i in range(ncols)))
+            key_idx = [i for i, c in enumerate(cols) if c["role"] == 1]
+            drows = [tuple(_canon(v) if i in key_idx else v for i, v in enumerate(r))
+                     for r in drows]
+            got = bench_oracle.combine_device_rows(desc, drows)
+            assert set(got) == set(exp), (flavour, sorted(map(repr, got))[:4],
+                                          sorted(map(repr, exp))[:4], "\n".join(plan.explain()[:8]))
+            for key, erow in exp.items():
+                for i, c in enumerate(cols):
+                    if c["role"] != 2:
+                        continue
+                    e = erow[i]
+                    if c["type"] == "float4" and e is not None:
+                        try:
+                            e = f4(e)       # a float4 sum lives in a double cell, rounded once
+                        except OverflowError:
+                            e = math.copysign(math.inf, e)
+                    g = got[key][i]
+                    if flavour == 2 and c["op"] == "PSUM" and c["type"] in ("float4", "float8") \
+                            and g is not None and e is not None \
+                            and math.isfinite(g) and math.isfinite(e):
+                        # two halves added up: another summation order (the
+                        # north star's float tolerance)
+                        tol = 1e-6 if c["type"] == "float4" else 1e-12
+                        if abs(g - e) > tol * max(abs(g), abs(e)):
+                            # cancellation (3.4e38 - 3.4e38 + 1): the error bound
+                            # of a re-ordered sum is relative to the sum of |x|
+                            expr = tlist[c["resno"] - 1]["expr"]
+                            kexprs = [tlist[k["resno"] - 1]["expr"] for k in cols if k["role"] == 1]
+                            mag = 0.0
+                            for r in ok_rows:
+                                if tuple(_canon(pg_expr.evaluate(k, r)) for k in kexprs) == key:
+                                    v = pg_expr.evaluate(expr, r)
+                                    mag += abs(float(v)) if v is not None else 0.0
+                            assert abs(g - e) <= tol * mag, (key, c["text"], g, e, mag)
+                        continue
+                    assert same(g, e, c["type"]), \
+                        (flavour, key, c["text"], g, e, "\n".join(plan.explain()[:8]))
+        return len(ok_rows), nrecheck
+    finally:
+        plan.free()
+
+
+def test_aggregation_flavours_hand_written(simdir, lib):
+    rng = random.Random(7)
+    rows = rand_rows(500, rng)
+    t = TBL
+    cnt = (P.Agg("count", star=True), "count")
+
+    def aggs_of(col):
+        return [(P.Agg(f, [t.col(col)]), f) for f in ("count", "min", "max", "sum", "avg")
+                if not (f == "sum" and col == "i8")]
+    for keycol in (None, "k", "f8", "tx"):
+        for col in ("s2", "i4", "i8", "f4", "f8"):
+            targets = ([(t.col(keycol), keycol)] if keycol else []) + [cnt] + aggs_of(col)
+            if col in ("f4", "f8"):
+                targets += [(P.Agg("stddev", [t.col(col)]), "stddev"),
+                            (P.Agg("variance", [t.col(col)]), "variance")]
+            tree = P.make_agg_plan(t, targets, group_by=[keycol] if keycol else [], num_groups=16)
+            nok, nre = check_aggregation(t, tree, rows, simdir, lib)
+            assert nok > 100
+    tree = P.make_agg_plan(
+        t, [cnt, (P.Agg("corr", [t.col("f8"), t.col("f4")]), "corr"),
+            (P.Agg("covar_pop", [t.col("f8"), t.col("i4")]), "covar_pop"),
+            (P.Agg("avg", [P.Cast(t.col("i4"), "numeric")]), "avg"),
+            (P.Agg("max", [P.Cast(t.col("f8"), "numeric")]), "max")],
+        where=[P.IsNull(t.col("b"), notnull=True)])
+    nok, nre = check_aggregation(t, tree, rows, simdir, lib)
+    assert nok > 100 and nre > 10
+
+
+def test_aggregation_flavours_fuzz(simdir, lib):
+    rng = random.Random(99)
+    rows = rand_rows(250, rng)
+    built = total = 0
+    for _ in range(30):
+        quals = [gen("bool", 3, rng)] if rng.random() < 0.7 else []
+        aggs = []
+        for _ in range(rng.choice([1, 2, 3, 4])):
+            typ = rng.choice(NUM)
+            fn = rng.choice(["min", "max", "sum", "avg", "count"] if typ != "int8"
+                            else ["min", "max", "avg", "count"])
+            aggs.append((P.Agg(fn, [gen(typ, 2, rng)]), fn))
+        keyed = rng.random() < 0.6
+        keycol = rng.choice(["k", "f8", "d", "b", "tx", "f4", "i8", "s2"])
+        targets = ([(TBL.col(keycol), keycol)] if keyed else []) + \
+            [(P.Agg("count", star=True), "count")] + aggs
+        tree = P.make_agg_plan(TBL, targets, group_by=[keycol] if keyed else [],
+                               where=quals, num_groups=8)
+        plan = gp.Plan(tree, gucs=GUCS)
+        ok = plan.num_gpupreagg == 1 and \
+            ("#define GPUPREAGG_HAS_QUAL 1" in plan.kernel_source()) == bool(quals)
+        plan.free()
+        if not ok:
+            continue
+        nok, nre = check_aggregation(TBL, tree, rows, simdir, lib)
+        built += 1
+        total += nok
+    assert built >= 20 and total > 500
