@@ -450,8 +450,13 @@ make_gpupreagg_refnode(const JsonPtr &aggref, rewrite_context &ctx)
                 expr = aggref_arg(aggref, 0);
                 if (expr_type(expr) != argtype)
                     expr = make_expr_typecast(expr, argtype);
+                /* The reference makes the unmatched branch a zero constant
+                 * (gpupreagg.c:883-892); sum(x) FILTER (WHERE ...) then yields
+                 * 0 where PostgreSQL yields NULL for a group no row of which
+                 * matches.  NULL is ignored by PSUM like any NULL input, and
+                 * the final functions are strict on it. */
                 if (expr && filter)
-                    expr = make_expr_conditional(expr, filter, make_zero_const(expr_type(expr)));
+                    expr = make_expr_conditional(expr, filter, JsonPtr());
                 if (expr)
                     expr = make_altfunc_expr(code == ALTFUNC_EXPR_PSUM ? "psum" : "psum_x2", {expr});
                 break;

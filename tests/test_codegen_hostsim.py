@@ -842,3 +842,182 @@ def test_aggregation_flavours_fuzz(simdir, lib):
         built += 1
         total += nok
     assert built >= 20 and total > 500
+
+
+# ---- end to end on the CPU: original query vs rewritten plan -----------------
+def _final_values(desc, partial_rows):
+    """PostgreSQL's final Agg over the partial rows (the pgstrom.* final
+    aggregates of pg_strom--1.0.sql:247-401, oracle/pg_agg.FinalAgg):
+    {group key: [value per Aggref of the Agg target list]}."""
+    from oracle import pg_agg
+    cols = desc["columns"]
+    key_idx = [i for i, c in enumerate(cols) if c["role"] == 1]
+    aggrefs = [t["expr"] for t in desc["agg_targetlist"] if t["expr"]["node"] == "Aggref"]
+    groups = {}
+    for pr in partial_rows:
+        groups.setdefault(tuple(_canon(pr[i]) for i in key_idx), []).append(pr)
+    if not key_idx and not groups:
+        groups[()] = []
+    out = {}
+    for k, prs in groups.items():
+        vals = []
+        for e in aggrefs:
+            fa = pg_agg.FinalAgg(e["orig_aggname"], e.get("orig_aggargtypes") or [])
+            argcols = [a["varattno"] - 1 for a in e["args"]]
+            for pr in prs:
+                fa.accum([pr[c] for c in argcols])
+            vals.append((fa.final(), fa.rettype))
+        out[k] = vals
+    return out
+
+
+def _own_values(tree, rows):
+    """The same query on PostgreSQL's own executor (pg_strom.enabled = off):
+    SeqScan qual, grouping, the aggregates' own transition / final functions."""
+    from oracle import pg_agg
+    agg = tree
+    scan = agg["lefttree"]
+    keys = [t["expr"] for t in agg["targetlist"] if t["expr"]["node"] == "Var"]
+    aggrefs = [t["expr"] for t in agg["targetlist"] if t["expr"]["node"] == "Aggref"]
+    groups = {}
+    for r in rows:
+        if not all(pg_expr.evaluate(q, r) is True for q in scan["qual"]):
+            continue
+        k = tuple(_canon(pg_expr.evaluate(e, r)) for e in keys)
+        st = groups.get(k)
+        if st is None:
+            st = groups[k] = [pg_agg.make_pg_agg(e["aggname"], e["aggargtypes"]) for e in aggrefs]
+        for e, a in zip(aggrefs, st):
+            if e.get("aggfilter") is not None and pg_expr.evaluate(e["aggfilter"], r) is not True:
+                continue
+            vals = [pg_expr.evaluate(t["expr"], r) for t in e["args"]]
+            if vals and any(v is None for v in vals):
+                continue                    # strict transition functions
+            a.accum(*vals)
+    if not keys and not groups:
+        groups[()] = [pg_agg.make_pg_agg(e["aggname"], e["aggargtypes"]) for e in aggrefs]
+    return {k: [(a.final(), a.rettype) for a in st] for k, st in groups.items()}
+
+
+def test_end_to_end_against_postgres_own_aggregates(simdir, lib):
+    """Original query on PostgreSQL's own executor == rewritten plan: device
+    partial rows (host simulation) + host partial rows of re-checked input
+    rows, merged by the pgstrom.* final aggregates.  Covers the rewrite of
+    every aggregate of the catalogue (gpupreagg.c:134-333) including FILTER
+    clauses, which the regression suite does not use."""
+    from oracle import partial
+    from oracle.pg_agg import PgError as AggError
+    rng = random.Random(4242)
+    t = TBL
+    # values that cannot make PostgreSQL itself raise: the comparison is about
+    # results, not errors
+    safe = {"s2": lambda: rng.randrange(-300, 300), "i4": lambda: rng.randrange(-10 ** 6, 10 ** 6),
+            "i8": lambda: rng.choice([rng.randrange(-10 ** 12, 10 ** 12), 2 ** 62, -2 ** 62]),
+            "f4": lambda: f4(rng.randrange(-4000, 4000) / 8.0),
+            "f8": lambda: rng.choice([rng.randrange(-10 ** 6, 10 ** 6) / 64.0, float("nan"), 2.5])}
+    rows = []
+    for _ in range(400):
+        r = list(rand_rows(1, rng)[0])
+        for name, mk in safe.items():
+            i = t.colnames().index(name)
+            r[i] = None if rng.random() < 0.1 else mk()
+        rows.append(tuple(r))
+    nqueries = 0
+    for _ in range(40):
+        aggs = [(P.Agg("count", star=True,
+                       filter=gen("bool", 1, rng) if rng.random() < 0.5 else None), "count")]
+        for _ in range(rng.choice([1, 2, 3])):
+            col = rng.choice(["s2", "i4", "i8", "f4", "f8"])
+            fns = ["count", "min", "max", "avg"] + ([] if col == "i8" else ["sum"]) + \
+                (["stddev", "variance", "var_pop", "stddev_pop"] if col in ("f4", "f8") else [])
+            fn = rng.choice(fns)
+            flt = None
+            if rng.random() < 0.5:
+                flt = P.Op(rng.choice(CMP), t.col(rng.choice(["i4", "s2", "k"])),
+                           P.Const("int4", rng.choice([0, 3, -100])))
+            aggs.append((P.Agg(fn, [t.col(col)], filter=flt), fn))
+        if rng.random() < 0.3:
+            aggs.append((P.Agg(rng.choice(["corr", "covar_pop", "covar_samp"]),
+                               [t.col("f8"), t.col("f4")]), "corr"))
+        keycol = rng.choice([None, "k", "b", "s2"])
+        where = [P.Op(">", t.col("i4"), P.Const("int4", -500000))] if rng.random() < 0.5 else []
+        tree = P.make_agg_plan(t, ([(t.col(keycol), keycol)] if keycol else []) + aggs,
+                               group_by=[keycol] if keycol else [], where=where, num_groups=8)
+        plan = gp.Plan(tree, gucs=GUCS)
+        try:
+            if plan.num_gpupreagg != 1:
+                continue
+            desc = plan.describe()
+            node = find_node(plan.tree())
+            so = build_sim(plan, simdir)
+            so.agg_row.argtypes = [C.POINTER(C.c_uint64), C.c_uint, C.c_char_p, C.c_char_p]
+            so.agg_flush.argtypes = [C.c_int, C.c_void_p]
+            kparams = plan.kparams()
+            incols = desc["incol_index"]
+            coltypes = [ty for _, ty in t.columns]
+            cols = desc["columns"]
+            vals = (C.c_uint64 * max(1, len(incols)))()
+            so.agg_reset()
+            host_rows = []
+            for row in rows:
+                valid = 0
+                toast = bytearray(b"\0" * 8)
+                for slot, c in enumerate(incols):
+                    v = row[c]
+                    vals[slot] = 0
+                    if v is None:
+                        continue
+                    valid |= 1 << slot
+                    if coltypes[c] in ("text", "bpchar"):
+                        while len(toast) % 4:
+                            toast.append(0)
+                        vals[slot] = len(toast)
+                        toast += T.varlena(v)
+                    else:
+                        vals[slot] = pack(v, coltypes[c])
+                rc = so.agg_row(vals, valid, kparams, bytes(toast))
+                assert rc in (0, 0x100, CPU_RECHECK), rc
+                if rc == CPU_RECHECK:       # gpupreagg_next_tuple_fallback
+                    host_rows.append(row)
+            ncols = len(cols)
+            colmeta = (gp.kern_colmeta * ncols)()
+            lib.pgs_plan_result_colmeta(plan.handle, 0, colmeta, ncols)
+            length = lib.pgstrom_kds_tupslot_length(ncols, 4096)
+            buf = C.create_string_buffer(length)
+            gp.check(lib.pgstrom_kds_tupslot_init(buf, length, ncols, colmeta, 4096))
+            assert so.agg_flush(0 if not keycol else 1, buf) == 0
+            kds = gp.kern_data_store.from_buffer(buf)
+            values = (C.c_uint64 * ncols)()
+            isnull = C.create_string_buffer(ncols)
+            prow_list = []
+            for r in range(kds.nitems):
+                gp.check(lib.pgstrom_fetch_data_store(buf, r, values, isnull))
+                prow_list.append(tuple(gp.decode_datum(values[i], isnull.raw[i] != 0,
+                                                       cols[i]["type"]) for i in range(ncols)))
+            try:
+                hp, _ = partial.partial_rows(node, host_rows, len(t.columns))
+                own = _own_values(tree, rows)
+            except AggError:
+                continue        # PostgreSQL itself raises (float overflow, date range ...)
+            if not (not keycol and not host_rows):
+                prow_list += [tuple(v) for v in hp.values()]
+            got = _final_values(desc, prow_list)
+            assert set(got) == set(own), (sorted(map(repr, got)), sorted(map(repr, own)))
+            for k, ovals in own.items():
+                for (gv, gt), (ov, ot), (e, name) in zip(got[k], ovals, aggs):
+                    what = (k, name, gv, ov, "\n".join(plan.explain()[:4]))
+                    if gv is None or ov is None:
+                        assert gv is None and ov is None, what
+                    elif isinstance(ov, float) or isinstance(gv, float):
+                        gv, ov = float(gv), float(ov)
+                        if math.isnan(ov) or math.isnan(gv):
+                            assert math.isnan(ov) and math.isnan(gv), what
+                        else:
+                            tol = 2e-3 if "float4" in (gt, ot) else 1e-9
+                            assert abs(gv - ov) <= tol * max(abs(gv), abs(ov), 1e-30), what
+                    else:
+                        assert gv == ov, what
+            nqueries += 1
+        finally:
+            plan.free()
+    assert nqueries >= 25
