@@ -236,6 +236,15 @@ extern "C" int agg_finish(void)
     }
     return 0;
 }
+/* overwrite one cell of group 0 (tests of the flush: values no test input reaches) */
+extern "C" void agg_poke(int f, int cell, unsigned long long value, unsigned int nn)
+{
+    pagg_row none;
+    memset(&none, 0, sizeof(none));
+    sim_group *s = sim_find(f, none);
+    s->cells[cell] = value;
+    s->nn |= nn;
+}
 /* partial rows of one flavour into a TUPSLOT store prepared by the host library */
 extern "C" int agg_flush(int f, kern_data_store *kds_dst)
 {
@@ -1021,3 +1030,67 @@ def test_end_to_end_against_postgres_own_aggregates(simdir, lib):
         finally:
             plan.free()
     assert nqueries >= 25
+
+
+def test_flush_splits_what_does_not_fit_a_column(simdir, lib):
+    """nrows is int4 in the catalogue and psum(int8) is int8: a count above
+    2^31-1 and a 128-bit sum beyond int8 leave the device as several partial
+    rows that add up to the exact value (PostgreSQL's final aggregates sum
+    partial rows).  No test input reaches such values, so the cells are set
+    directly."""
+    from oracle import bench_oracle
+    t = TBL
+    tree = P.make_agg_plan(t, [(P.Agg("count", star=True), "count"),
+                               (P.Agg("avg", [t.col("i8")]), "avg"),
+                               (P.Agg("max", [t.col("i4")]), "max")])
+    plan = gp.Plan(tree, gucs=GUCS)
+    try:
+        desc = plan.describe()
+        cols = desc["columns"]
+        so = build_sim(plan, simdir)
+        so.agg_flush.argtypes = [C.c_int, C.c_void_p]
+        so.agg_poke.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint]
+        by_text = {c["text"]: c for c in cols if c["role"] == 2}
+        nrows = by_text["pgstrom.nrows()"]
+        nrows_i8 = by_text["pgstrom.nrows((i8 IS NOT NULL))"]
+        psum = by_text["pgstrom.psum(i8)"]
+        pmax = by_text["pgstrom.pmax(i4)"]
+        assert psum["cell_type"] == "LONG"
+        ncols = len(cols)
+        colmeta = (gp.kern_colmeta * ncols)()
+        lib.pgs_plan_result_colmeta(plan.handle, 0, colmeta, ncols)
+        length = lib.pgstrom_kds_tupslot_length(ncols, 64)
+        values = (C.c_uint64 * ncols)()
+        isnull = C.create_string_buffer(ncols)
+        for count, total in ((5_000_000_000, 3 * (2 ** 63 - 1) + 12345),
+                             (2 ** 31 - 1, 2 ** 63 - 1),
+                             (2 ** 31, -(2 ** 63) - 1),
+                             (7, -5 * 2 ** 63)):
+            so.agg_reset()
+            allbits = 0xffffffff
+            so.agg_poke(0, nrows["cell_index"], count, allbits)
+            so.agg_poke(0, nrows_i8["cell_index"], count, allbits)
+            so.agg_poke(0, psum["cell_index"], total & (2 ** 64 - 1), allbits)
+            so.agg_poke(0, psum["cell_index"] + 1, (total >> 64) & (2 ** 64 - 1), allbits)
+            so.agg_poke(0, pmax["cell_index"], 42, allbits)
+            buf = C.create_string_buffer(length)
+            gp.check(lib.pgstrom_kds_tupslot_init(buf, length, ncols, colmeta, 64))
+            assert so.agg_flush(0, buf) == 0
+            kds = gp.kern_data_store.from_buffer(buf)
+            rows = []
+            for r in range(kds.nitems):
+                gp.check(lib.pgstrom_fetch_data_store(buf, r, values, isnull))
+                rows.append(tuple(gp.decode_datum(values[i], isnull.raw[i] != 0, cols[i]["type"])
+                                  for i in range(ncols)))
+            want_rows = max(-(-count // (2 ** 31 - 1)), -(-abs(total) // (2 ** 63 - 1 if total >= 0 else 2 ** 63)), 1)
+            assert len(rows) == want_rows, (count, total, len(rows), want_rows)
+            for r in rows:          # every piece fits its column
+                assert 0 <= r[nrows["resno"] - 1] <= 2 ** 31 - 1
+                assert -(2 ** 63) <= r[psum["resno"] - 1] <= 2 ** 63 - 1
+            merged = bench_oracle.combine_device_rows(desc, rows)[()]
+            assert merged[nrows["resno"] - 1] == count
+            assert merged[nrows_i8["resno"] - 1] == count
+            assert merged[psum["resno"] - 1] == total
+            assert merged[pmax["resno"] - 1] == 42
+    finally:
+        plan.free()
