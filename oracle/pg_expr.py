@@ -26,6 +26,7 @@ def etype(e):
     return {"Var": lambda: e["vartype"], "Const": lambda: e["consttype"],
             "Param": lambda: e["paramtype"], "FuncExpr": lambda: e["funcresulttype"],
             "OpExpr": lambda: e.get("opresulttype", "bool"),
+            "DistinctExpr": lambda: "bool",
             "NullTest": lambda: "bool", "BooleanTest": lambda: "bool",
             "BoolExpr": lambda: "bool", "RelabelType": lambda: e["resulttype"],
             "CaseExpr": lambda: e["casetype"], "Aggref": lambda: e["aggtype"]}[n]()
@@ -258,6 +259,12 @@ def evaluate(e, row):
             if hit:
                 return evaluate(w["result"], row)
         return evaluate(e.get("defresult"), row)
+    if n == "DistinctExpr":
+        # execQual.c ExecEvalDistinct: never NULL; NULL is not distinct from NULL
+        a, b = [evaluate(x, row) for x in e["args"]]
+        if a is None or b is None:
+            return (a is None) != (b is None)
+        return not _call(e["opfuncname"], [etype(x) for x in e["args"]], "bool", [a, b])
     if n in ("FuncExpr", "OpExpr"):
         name = e["funcname"] if n == "FuncExpr" else e["opfuncname"]
         args = [evaluate(a, row) for a in e.get("args", [])]

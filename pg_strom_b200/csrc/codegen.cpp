@@ -677,6 +677,51 @@ codegen_expression_walker(const JsonPtr &node, CodegenContext &ctx, std::string 
         if (!dfunc || !collation_is_device_compatible(fname, node))
             return false;
         ctx.track_func(dfunc);
+        if (tag == "DistinctExpr")
+        {
+            /* a IS DISTINCT FROM b: the node carries the equality operator,
+             * but the result is its NULL-safe negation - never NULL; two
+             * NULLs are not distinct, one NULL is (execQual.c
+             * ExecEvalDistinct).  The reference emits the bare operator call
+             * here (codegen.c:1171-1195), i.e. evaluates `a = b`. */
+            if (!args || args->arr.size() != 2 ||
+                std::string(dfunc->func_rettype->type_name) != "bool")
+                return false;
+            std::string dname = "distinct_" + dfunc->func_alias;
+            const DevFunc *wrap = NULL;
+            for (DevFunc *f : devfunc_cache)
+                if (f->func_name == dname && f->func_args == dfunc->func_args)
+                    wrap = f;
+            if (!wrap)
+            {
+                DevFunc *f = new DevFunc;
+                std::ostringstream s;
+
+                f->func_name = dname;
+                f->func_alias = dname + argname_suffix(dfunc->func_args);
+                f->func_args = dfunc->func_args;
+                f->func_rettype = dfunc->func_rettype;
+                f->func_flags = dfunc->func_flags;
+                s << "DEVFN pg_bool_t pgfn_" << f->func_alias << "(cl_int *errcode, pg_"
+                  << f->func_args[0]->type_name << "_t arg1, pg_"
+                  << f->func_args[1]->type_name << "_t arg2)\n"
+                  << "{\n"
+                  << "    pg_bool_t result;\n"
+                  << "    result.isnull = false;\n"
+                  << "    if (arg1.isnull | arg2.isnull)\n"
+                  << "        result.value = (cl_bool)(arg1.isnull != arg2.isnull);\n"
+                  << "    else\n"
+                  << "        result.value = (cl_bool)!EVAL(pgfn_" << dfunc->func_alias
+                  << "(errcode, arg1, arg2));\n"
+                  << "    return result;\n"
+                  << "}\n";
+                f->func_decl = s.str();
+                devfunc_cache.push_back(f);
+                wrap = f;
+            }
+            ctx.track_func(wrap);       /* after the operator it calls */
+            dfunc = wrap;
+        }
         out += "pgfn_" + dfunc->func_alias + "(errcode";
         if (args)
             for (auto &a : args->arr)
@@ -1110,6 +1155,15 @@ deparse_expression(const JsonPtr &node, const std::vector<std::string> &colnames
                 deparse_expression(args->arr[1], colnames, true);
         else if (args && args->arr.size() == 1)
             s = node->s("opname") + " " + deparse_expression(args->arr[0], colnames, true);
+        return toplevel_parens ? "(" + s + ")" : s;
+    }
+    if (tag == "DistinctExpr")
+    {
+        const Json *args = node->get("args");
+        std::string s;
+        if (args && args->arr.size() == 2)
+            s = deparse_expression(args->arr[0], colnames, true) + " IS DISTINCT FROM " +
+                deparse_expression(args->arr[1], colnames, true);
         return toplevel_parens ? "(" + s + ")" : s;
     }
     if (tag == "NullTest")

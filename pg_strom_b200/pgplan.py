@@ -65,7 +65,7 @@ def etype(e):
         return e["paramtype"]
     if n == "FuncExpr":
         return e["funcresulttype"]
-    if n == "OpExpr":
+    if n in ("OpExpr", "DistinctExpr"):
         return e.get("opresulttype", "bool")
     if n in ("NullTest", "BooleanTest", "BoolExpr"):
         return "bool"
@@ -136,6 +136,14 @@ def Op(op, left, right, collation=None):
             "opresulttype": res, "args": [left, right]}
     if collation is not None:
         node["inputcollid"] = collation
+    return node
+
+
+def Distinct(left, right, collation=None):
+    """left IS DISTINCT FROM right: a DistinctExpr carries the `=` operator of
+    its argument types (parse_oper.c make_distinct_op)."""
+    node = Op("=", left, right, collation)
+    node["node"] = "DistinctExpr"
     return node
 
 

@@ -549,9 +549,16 @@ def gen(typ, depth, rng):
             n = rng.choice([2, 2, 3])
             mk = P.And if rng.random() < 0.5 else P.Or
             return mk(*[gen("bool", depth - 1, rng) for _ in range(n)])
-        if kind < 0.78:
+        if kind < 0.74:
             return P.Not(gen("bool", depth - 1, rng))
-        if kind < 0.90:
+        if kind < 0.77:
+            return {"node": "BooleanTest", "arg": gen("bool", depth - 1, rng),
+                    "booltesttype": rng.choice(["IS_TRUE", "IS_NOT_TRUE", "IS_FALSE",
+                                                "IS_NOT_FALSE", "IS_UNKNOWN", "IS_NOT_UNKNOWN"])}
+        if kind < 0.80:
+            ty = rng.choice(list(NUM) + ["date", "bool"])
+            return P.Distinct(gen(ty, depth - 1, rng), gen(ty, depth - 1, rng))
+        if kind < 0.91:
             t = rng.choice(list(COLS))
             return P.IsNull(gen(t, depth - 1, rng) if t != "text" else TBL.col("tx"),
                             notnull=rng.random() < 0.5)
