@@ -572,9 +572,17 @@ def gen(typ, depth, rng):
         if kind < 0.75:
             src = rng.choice([t for t in NUM if t != typ])
             return P.Cast(gen(src, depth - 1, rng), typ)
-        if kind < 0.9:
+        if kind < 0.85:
             return P.Case([(gen("bool", depth - 1, rng), gen(typ, depth - 1, rng))],
                           gen(typ, depth - 1, rng) if rng.random() < 0.7 else None, typ)
+        if kind < 0.9:
+            # CASE <arg> WHEN <value> THEN ... : compares with the type's "=" operator
+            at = rng.choice(["int4", "int2", "float8", "date"])
+            whens = [{"node": "CaseWhen", "expr": const_of(at, rng),
+                      "result": gen(typ, depth - 1, rng)} for _ in range(rng.choice([1, 2]))]
+            return {"node": "CaseExpr", "casetype": typ, "arg": gen(at, depth - 1, rng),
+                    "args": whens,
+                    "defresult": gen(typ, depth - 1, rng) if rng.random() < 0.7 else None}
         if typ == "int4" and rng.random() < 0.5:
             return P.Op("-", gen("date", depth - 1, rng), gen("date", depth - 1, rng))
         return gen(typ, 0, rng)
