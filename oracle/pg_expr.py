@@ -15,6 +15,7 @@ from decimal import Decimal
 
 from . import pg_typelib
 from .pg_agg import PgError, cast as pg_cast, float8pl, float8mul, check_float8, f4
+from .pg_agg import numeric_add as pg_numeric_add, numeric_mul as pg_numeric_mul
 
 _INT_RANGE = {"int2": (-(1 << 15), (1 << 15) - 1, "smallint out of range"),
               "int4": (-(1 << 31), (1 << 31) - 1, "integer out of range"),
@@ -210,6 +211,19 @@ def _call(name, argtypes, rettype, args):
         return r
     if name in _MATH:
         return _MATH[name](*args)
+    # numeric.c: add / sub keep the larger display scale, mul adds them up
+    if name == "numeric_add":
+        return pg_numeric_add(args[0], args[1])
+    if name == "numeric_sub":
+        return pg_numeric_add(args[0], -args[1])
+    if name == "numeric_mul":
+        return pg_numeric_mul(args[0], args[1])
+    if name == "numeric_uminus":
+        return -args[0]
+    if name == "numeric_uplus":
+        return args[0]
+    if name == "numeric_abs":
+        return abs(args[0])
     raise NotImplementedError("oracle: function %s(%s)" % (name, ",".join(argtypes)))
 
 

@@ -3248,17 +3248,23 @@ pgs_numsum_value(const cl_ulong *cells, int c, int *p_dscale)
     *p_dscale = ds;
     return v / (pgs_s128)pgs_pow10_u128(PGS_NUMERIC_SUM_SCALE - ds);
 }
+/* A sum is emitted positionally in base 10^17 (< 2^57): at most three device
+ * numerics  lo * 10^-ds  +  mid * 10^(17-ds)  +  hi * 10^(34-ds)  hold any
+ * 128-bit value exactly, and PostgreSQL's final sum adds them up.  Piece 0
+ * always carries the display scale, also when it is zero.  (Cutting the value
+ * into pieces of one full mantissa each needs |v| / 2^57 rows: a sum of 10^12
+ * and 10^-16 would have asked for 10^11 of them.) */
+#define PGS_NUMSUM_BASE     100000000000000000ULL       /* 10^17 */
 DEVFN cl_uint
 pgs_numsum_nsplit(const cl_ulong *cells, int c)
 {
     int         ds;
     pgs_s128    v = pgs_numsum_value(cells, c, &ds);
-    pgs_s128    a = (v < 0 ? -v : v);
-    pgs_s128    n = (a + (pgs_s128)PGS_NUMERIC_MANT_LIMIT - 1) / (pgs_s128)PGS_NUMERIC_MANT_LIMIT;
+    pgs_u128    a = (pgs_u128)(v < 0 ? -v : v);
 
-    if (n < 1)
-        n = 1;
-    return (n > 0x7fffffff ? 0x7fffffffU : (cl_uint)n);
+    if (a < (pgs_u128)PGS_NUMSUM_BASE)
+        return 1;
+    return (a / PGS_NUMSUM_BASE < (pgs_u128)PGS_NUMSUM_BASE) ? 2 : 3;
 }
 /* piece r of the sum as a device numeric */
 DEVFN cl_ulong
@@ -3266,14 +3272,29 @@ pgs_numsum_piece(const cl_ulong *cells, int c, cl_uint r)
 {
     int         ds;
     pgs_s128    v = pgs_numsum_value(cells, c, &ds);
-    pgs_s128    a = (v < 0 ? -v : v);
-    pgs_s128    rest = a - (pgs_s128)r * (pgs_s128)PGS_NUMERIC_MANT_LIMIT;
+    pgs_u128    a = (pgs_u128)(v < 0 ? -v : v);
+    cl_ulong    mant = 0;
+    int         expo = -ds;
 
-    if (rest < 0)
-        rest = 0;
-    if (rest > (pgs_s128)PGS_NUMERIC_MANT_LIMIT)
-        rest = (pgs_s128)PGS_NUMERIC_MANT_LIMIT;
-    return PG_NUMERIC_SET(-ds, (v < 0) && rest != 0, (cl_ulong)rest);
+    if (r == 0)
+        mant = (cl_ulong)(a % PGS_NUMSUM_BASE);
+    else if (r == 1)
+    {
+        mant = (cl_ulong)((a / PGS_NUMSUM_BASE) % PGS_NUMSUM_BASE);
+        expo = 17 - ds;
+    }
+    else if (r == 2)
+    {
+        /* a < 2^127: what is left is below 1.8 * 10^4 */
+        mant = (cl_ulong)((a / PGS_NUMSUM_BASE) / PGS_NUMSUM_BASE);
+        expo = 34 - ds;
+        if (expo > PG_NUMERIC_EXPONENT_MAX)
+        {
+            mant *= pgs_pow10_u64(expo - PG_NUMERIC_EXPONENT_MAX);
+            expo = PG_NUMERIC_EXPONENT_MAX;
+        }
+    }
+    return PG_NUMERIC_SET(expo, (v < 0) && mant != 0, mant);
 }
 #endif
 #define PGS_NSPLIT_PSUM_NUMERIC(c)                                      \

@@ -388,11 +388,12 @@ def check_query(table, tree, rows, simdir):
                     vals[slot] = 0
                     continue
                 valid |= 1 << slot
-                if coltypes[c] in ("text", "bpchar"):
+                if coltypes[c] in ("text", "bpchar", "numeric"):
                     while len(toast) % 4:
                         toast.append(0)
                     vals[slot] = len(toast)
-                    toast += T.varlena(v)
+                    toast += (T.varlena(v) if coltypes[c] != "numeric"
+                              else gp.numeric_datum(format(v, "f")))
                 else:
                     vals[slot] = pack(v, coltypes[c])
             rc = so.sim_row(vals, valid, kparams, bytes(toast), key_out, key_null,
@@ -659,6 +660,28 @@ def test_fuzz_generated_code(simdir):
 PSUM_LIMIT = {"DOUBLE": 2.0 ** 960, "FLOAT": 2.0 ** 88}
 
 
+def _numeric_fits(d):
+    """the 64-bit device numeric holds it: 57-bit mantissa, display scale <= 32"""
+    if d is None:
+        return True
+    if not d.is_finite():
+        return False
+    scale = max(0, -d.as_tuple().exponent)
+    return int(abs(d).scaleb(scale)) <= (1 << 57) - 2 and scale <= 32
+
+
+def _var_attnos(e, out):
+    if isinstance(e, dict):
+        if e.get("node") == "Var":
+            out.add(e["varattno"])
+        for v in e.values():
+            _var_attnos(v, out)
+    elif isinstance(e, list):
+        for v in e:
+            _var_attnos(v, out)
+    return out
+
+
 def _canon(v):
     from oracle.partial import _canon_key
     return _canon_key(v)
@@ -687,6 +710,8 @@ def check_aggregation(table, tree, rows, simdir, lib):
         quals = node.get("outer_quals") or []
         tlist = node["targetlist"]
         vals = (C.c_uint64 * max(1, len(incols)))()
+        qual_vars = _var_attnos(quals, set())
+        tlist_vars = _var_attnos([x["expr"] for x in tlist], set())
         so.agg_reset()
         ok_rows, nrecheck = [], 0
         for row in rows:
@@ -698,11 +723,12 @@ def check_aggregation(table, tree, rows, simdir, lib):
                     vals[slot] = 0
                     continue
                 valid |= 1 << slot
-                if coltypes[c] in ("text", "bpchar"):
+                if coltypes[c] in ("text", "bpchar", "numeric"):
                     while len(toast) % 4:
                         toast.append(0)
                     vals[slot] = len(toast)
-                    toast += T.varlena(v)
+                    toast += (T.varlena(v) if coltypes[c] != "numeric"
+                              else gp.numeric_datum(format(v, "f")))
                 else:
                     vals[slot] = pack(v, coltypes[c])
             rc = so.agg_row(vals, valid, kparams, bytes(toast))
@@ -712,8 +738,16 @@ def check_aggregation(table, tree, rows, simdir, lib):
                 qv = [pg_expr.evaluate(q, row) for q in quals]
             except PgError:
                 qv, want = [], CPU_RECHECK
+            # a numeric column value beyond the device format fails where it is read
+            for a in qual_vars:
+                if coltypes[a - 1] == "numeric" and not _numeric_fits(row[a - 1]):
+                    want = CPU_RECHECK
             if want == 0 and not all(v is True for v in qv):
                 want = 0x100
+            if want == 0:
+                for a in tlist_vars:
+                    if coltypes[a - 1] == "numeric" and not _numeric_fits(row[a - 1]):
+                        want = CPU_RECHECK
             if want == 0:
                 try:
                     for c in cols:
@@ -805,6 +839,11 @@ def check_aggregation(table, tree, rows, simdir, lib):
                         continue
                     assert same(g, e, c["type"]), \
                         (flavour, key, c["text"], g, e, "\n".join(plan.explain()[:8]))
+                    if c["type"] == "numeric" and g is not None:
+                        # the display scale too: sums carry the largest input
+                        # scale, min / max return an input as it is
+                        from oracle.pg_agg import numeric_out
+                        assert numeric_out(g) == numeric_out(e), (flavour, key, c["text"], g, e)
         return len(ok_rows), nrecheck
     finally:
         plan.free()
@@ -1107,5 +1146,99 @@ def test_flush_splits_what_does_not_fit_a_column(simdir, lib):
             assert merged[nrows_i8["resno"] - 1] == count
             assert merged[psum["resno"] - 1] == total
             assert merged[pmax["resno"] - 1] == 42
+    finally:
+        plan.free()
+
+
+def test_aggregation_numeric(simdir, lib):
+    """NUMERIC through the merge rules and the flush: 128-bit sums at a fixed
+    scale with the largest display scale seen, 57-bit min / max, sums that
+    leave the device as several pieces; what does not fit (more than 17
+    digits, scale beyond 16 in a sum / 32 anywhere) is the host's row."""
+    from decimal import Decimal
+    rng = random.Random(31)
+    t = P.Table("nm", [("k", "int4"), ("n", "numeric"), ("m", "numeric"), ("i", "int4")])
+    rows = []
+    for _ in range(600):
+        def num():
+            if rng.random() < 0.08:
+                return None
+            scale = rng.choice([0, 0, 1, 2, 2, 4, 6, 10, 16, 17, 20])
+            digits = rng.choice([1, 3, 6, 9, 12, 15, 17, 18])
+            mant = rng.randrange(0, 10 ** digits)
+            d = Decimal(mant).scaleb(-scale)
+            return -d if rng.random() < 0.4 else d
+        rows.append((rng.randrange(0, 6), num(), num(), rng.randrange(-1000, 1000)))
+    n, m, i = t.col("n"), t.col("m"), t.col("i")
+    cnt = (P.Agg("count", star=True), "count")
+    total_ok = total_re = 0
+    for keycol in (None, "k"):
+        for targets, where in (
+                ([cnt, (P.Agg("sum", [n]), "sum"), (P.Agg("avg", [m]), "avg")], []),
+                ([cnt, (P.Agg("min", [n]), "min"), (P.Agg("max", [n]), "max"),
+                  (P.Agg("count", [m]), "count")], [P.Op(">", n, m)]),
+                ([cnt, (P.Agg("sum", [P.Op("+", n, P.Cast(i, "numeric"))]), "sum"),
+                  (P.Agg("max", [P.Op("*", m, P.Const("numeric", "1.5"))]), "max")],
+                 [P.Op("<>", m, P.Const("numeric", "0"))])):
+            tree = P.make_agg_plan(t, ([(t.col(keycol), keycol)] if keycol else []) + targets,
+                                   group_by=[keycol] if keycol else [], where=where, num_groups=8)
+            nok, nre = check_aggregation(t, tree, rows, simdir, lib)
+            total_ok += nok
+            total_re += nre
+    assert total_ok > 800 and total_re > 300
+
+
+def test_flush_numeric_sum_pieces(simdir, lib):
+    """A 128-bit numeric sum leaves as at most three device numerics (base
+    10^17) that add up exactly and keep the display scale - also a sum like
+    10^12 + 10^-16, whose 29 digits no single 57-bit mantissa holds."""
+    from decimal import Decimal
+    from oracle import bench_oracle
+    from oracle.pg_agg import numeric_add, numeric_out
+    t = P.Table("nm", [("n", "numeric")])
+    tree = P.make_agg_plan(t, [(P.Agg("sum", [t.col("n")]), "sum")])
+    plan = gp.Plan(tree, gucs=GUCS)
+    try:
+        desc = plan.describe()
+        cols = desc["columns"]
+        so = build_sim(plan, simdir)
+        so.agg_flush.argtypes = [C.c_int, C.c_void_p]
+        so.agg_poke.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint]
+        psum = [c for c in cols if c["role"] == 2][0]
+        assert psum["cell_type"] == "NUMERIC" and psum["op"] == "PSUM"
+        ncols = len(cols)
+        colmeta = (gp.kern_colmeta * ncols)()
+        lib.pgs_plan_result_colmeta(plan.handle, 0, colmeta, ncols)
+        length = lib.pgstrom_kds_tupslot_length(ncols, 16)
+        values = (C.c_uint64 * ncols)()
+        isnull = C.create_string_buffer(ncols)
+        for text, npieces in (("0", 1), ("12.50", 1), ("-0.0001", 1), ("99999999999999999", 1),
+                              ("100000000000000000", 2), ("1000000000000.0000000000000001", 2),
+                              ("-1000000000000.0000000000000001", 2),
+                              ("12345678901234567890.12", 2),
+                              ("1234567890123456789012.3456789012345678", 3),
+                              ("-9999999999999999999999.9999999999999999", 3)):
+            d = Decimal(text)
+            ds = max(0, -d.as_tuple().exponent)
+            v = int(d.scaleb(16))                   # the cell keeps the sum at scale 16
+            so.agg_reset()
+            so.agg_poke(0, psum["cell_index"], v & (2 ** 64 - 1), 0xffffffff)
+            so.agg_poke(0, psum["cell_index"] + 1, (v >> 64) & (2 ** 64 - 1), 0xffffffff)
+            so.agg_poke(0, psum["cell_index"] + 2, ds, 0xffffffff)
+            buf = C.create_string_buffer(length)
+            gp.check(lib.pgstrom_kds_tupslot_init(buf, length, ncols, colmeta, 16))
+            assert so.agg_flush(0, buf) == 0
+            kds = gp.kern_data_store.from_buffer(buf)
+            assert kds.nitems == npieces, (text, kds.nitems)
+            total = None
+            for r in range(kds.nitems):
+                gp.check(lib.pgstrom_fetch_data_store(buf, r, values, isnull))
+                piece = gp.decode_datum(values[psum["resno"] - 1], isnull.raw[psum["resno"] - 1] != 0,
+                                        "numeric")
+                # what PostgreSQL's numeric_in makes of the piece, then its sum
+                piece = Decimal(piece) if piece.as_tuple().exponent <= 0 else \
+                    Decimal(int(piece))
+                total = piece if total is None else numeric_add(total, piece)
+            assert total == d and numeric_out(total) == numeric_out(d), (text, total)
     finally:
         plan.free()
