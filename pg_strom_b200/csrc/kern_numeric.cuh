@@ -257,6 +257,17 @@ pg_numeric_param(const kern_parambuf *kparams, cl_int *errcode, cl_uint param_id
 
 STROMCL_SIMPLE_NULLTEST_TEMPLATE(numeric)
 
+/* NULL of a CASE without ELSE (also what an aggregate FILTER becomes) */
+DEVFN pg_numeric_t
+pg_numeric_null(void)
+{
+    pg_numeric_t r;
+
+    r.isnull = true;
+    r.value = 0;
+    return r;
+}
+
 /* ---- arithmetic (opencl_numeric.h:816-1094): exact, or CpuReCheck ---- */
 DEVFN pg_numeric_t
 pgs_numeric_addsub(cl_int *errcode, pg_numeric_t a, pg_numeric_t b, bool sub)

@@ -19,6 +19,7 @@ import struct
 import subprocess
 
 import pytest
+from decimal import Decimal
 
 from oracle import pg_expr, pg_typelib as T
 from oracle.pg_agg import PgError, f4
@@ -270,6 +271,39 @@ extern "C" int agg_flush(int f, kern_data_store *kds_dst)
 '''
 
 
+def install_device_numeric_range(setattr_fn):
+    """The oracle evaluates NUMERIC without limits; the device keeps 57 bits
+    of mantissa and a display scale <= 32 and re-checks what does not fit
+    (opencl_numeric.h:141-162), and pgs_float_to_numeric declines tiny / huge
+    floats.  Inside these tests the oracle raises where the device declines,
+    so that "PgError <=> CpuReCheck" holds for numeric intermediates too."""
+    orig = pg_expr._call
+
+    def call(name, argtypes, rettype, args):
+        if name == "numeric" and argtypes and argtypes[0] in ("float4", "float8"):
+            v = args[0]
+            if math.isfinite(v) and v != 0:
+                digits = 15 if argtypes[0] == "float8" else 6
+                if digits - 1 - Decimal(v).adjusted() > 32 or abs(v) >= 2.0 ** 127:
+                    raise PgError("float -> numeric: left to the host")
+        if name in ("numeric_add", "numeric_sub"):
+            # operands whose display scales are more than 20 apart would need
+            # more than 128 bits to align: the device declines
+            sa, sb = (max(0, -a.as_tuple().exponent) for a in args)
+            if abs(sa - sb) > 20:
+                raise PgError("numeric add: scales too far apart for the device")
+        r = orig(name, argtypes, rettype, args)
+        if isinstance(r, Decimal) and not _numeric_fits(r):
+            raise PgError("beyond the 64-bit device numeric")
+        return r
+    setattr_fn(pg_expr, "_call", call)
+
+
+@pytest.fixture(autouse=True)
+def device_numeric_range(monkeypatch):
+    install_device_numeric_range(monkeypatch.setattr)
+
+
 def _cut(path, start, end):
     text = open(path).read()
     i = text.index(start)
@@ -334,6 +368,29 @@ def pack(value, typ):
     raise KeyError(typ)
 
 
+def fill_vals(row, incols, coltypes, vals):
+    """One input row as the staged words of its referenced columns: by-value
+    types in place, varlena columns as the offset of the datum in a toast
+    buffer (what a chunk holds).  -> (validity bits, toast bytes)"""
+    toast = bytearray(b"\0" * 8)
+    valid = 0
+    for slot, c in enumerate(incols):
+        v = row[c]
+        vals[slot] = 0
+        if v is None:
+            continue
+        valid |= 1 << slot
+        if coltypes[c] in ("text", "bpchar", "numeric"):
+            while len(toast) % 4:
+                toast.append(0)
+            vals[slot] = len(toast)
+            toast += (T.varlena(v) if coltypes[c] != "numeric"
+                      else gp.numeric_datum(format(v, "f")))
+        else:
+            vals[slot] = pack(v, coltypes[c])
+    return valid, bytes(toast)
+
+
 def same(a, b, typ):
     if a is None or b is None:
         return a is None and b is None
@@ -380,23 +437,8 @@ def check_query(table, tree, rows, simdir):
         passed = C.c_int()
         for row in rows:
           try:
-            toast = bytearray(b"\0" * 8)
-            valid = 0
-            for slot, c in enumerate(incols):
-                v = row[c]
-                if v is None:
-                    vals[slot] = 0
-                    continue
-                valid |= 1 << slot
-                if coltypes[c] in ("text", "bpchar", "numeric"):
-                    while len(toast) % 4:
-                        toast.append(0)
-                    vals[slot] = len(toast)
-                    toast += (T.varlena(v) if coltypes[c] != "numeric"
-                              else gp.numeric_datum(format(v, "f")))
-                else:
-                    vals[slot] = pack(v, coltypes[c])
-            rc = so.sim_row(vals, valid, kparams, bytes(toast), key_out, key_null,
+            valid, toast = fill_vals(row, incols, coltypes, vals)
+            rc = so.sim_row(vals, valid, kparams, toast, key_out, key_null,
                             agg_out, agg_null, C.byref(passed))
             e1, e2 = rc & 0xff, rc >> 8
             # the device evaluates every qual (no short circuit across the
@@ -461,7 +503,7 @@ def check_query(table, tree, rows, simdir):
 # ---- data ------------------------------------------------------------------
 TBL = P.Table("fz", [("b", "bool"), ("s2", "int2"), ("i4", "int4"), ("i8", "int8"),
                      ("f4", "float4"), ("f8", "float8"), ("d", "date"), ("ts", "timestamp"),
-                     ("tx", "text"), ("k", "int4")])
+                     ("tx", "text"), ("n", "numeric"), ("k", "int4")])
 EDGE = {
     "bool": [True, False],
     "int2": [0, 1, -1, 32767, -32768, 100, -100, 7],
@@ -475,6 +517,8 @@ EDGE = {
     "timestamp": [0, 1, -1, T.DT_NOBEGIN, T.DT_NOEND, 631152000000000, 86400000000,
                   -86400000001, 2 ** 62],
     "text": [b"", b"a", b"abc", b"abd", b"ab", b"b", b"\xc3\xa9", b"abc ", b"zzzzzzzzzzzz"],
+    "numeric": [Decimal(x) for x in ("0", "1", "-1", "0.5", "1.50", "-2.25", "100", "0.001",
+                                     "123456789012345", "-99999.99999", "3.0000")],
 }
 
 
@@ -494,6 +538,9 @@ def rand_value(typ, rng):
         v = rng.randrange(-20000, 20000)
     elif typ == "timestamp":
         v = rng.randrange(-10 ** 15, 10 ** 15)
+    elif typ == "numeric":
+        v = Decimal(rng.randrange(-10 ** rng.choice([2, 6, 12]), 10 ** rng.choice([2, 6, 12]))) \
+            .scaleb(-rng.choice([0, 0, 1, 2, 4, 8]))
     else:
         v = bytes(rng.choice(b"abz ") for _ in range(rng.randrange(0, 5)))
     if typ == "float4":
@@ -510,7 +557,7 @@ def rand_rows(n, rng):
 # ---- random typed expressions ----------------------------------------------
 NUM = ("int2", "int4", "int8", "float4", "float8")
 COLS = {"bool": ["b"], "int2": ["s2"], "int4": ["i4", "k"], "int8": ["i8"], "float4": ["f4"],
-        "float8": ["f8"], "date": ["d"], "timestamp": ["ts"], "text": ["tx"]}
+        "float8": ["f8"], "date": ["d"], "timestamp": ["ts"], "text": ["tx"], "numeric": ["n"]}
 CMP = ["=", "<>", "<", "<=", ">", ">="]
 
 
@@ -522,6 +569,8 @@ def const_of(typ, rng):
         return P.Const("bool", v)
     if typ in ("float4", "float8"):
         return P.Const(typ, repr(float(v)))
+    if typ == "numeric":
+        return P.Const("numeric", format(v, "f"))
     return P.Const(typ, v)
 
 
@@ -540,10 +589,13 @@ def gen(typ, depth, rng):
                 return P.Op(rng.choice(CMP), gen(t, depth - 1, rng), gen(u, depth - 1, rng))
             except TypeError:
                 return P.Op(rng.choice(CMP), gen(t, depth - 1, rng), gen(t, depth - 1, rng))
-        if kind < 0.45:
+        if kind < 0.42:
             a, b = rng.choice([("date", "date"), ("timestamp", "timestamp"),
                                ("date", "timestamp"), ("timestamp", "date")])
             return P.Op(rng.choice(CMP), gen(a, depth - 1, rng), gen(b, depth - 1, rng))
+        if kind < 0.47:
+            return P.Op(rng.choice(CMP), gen("numeric", depth - 1, rng),
+                        gen("numeric", depth - 1, rng))
         if kind < 0.55:
             return P.Op(rng.choice(CMP), gen("text", 0, rng), const_of("text", rng), collation="C")
         if kind < 0.70:
@@ -570,9 +622,14 @@ def gen(typ, depth, rng):
         if kind < 0.45:
             op = rng.choice(["+", "-", "*", "/"] + (["%"] if typ in ("int2", "int4", "int8") else []))
             return P.Op(op, gen(typ, depth - 1, rng), gen(typ, depth - 1, rng))
-        if kind < 0.75:
+        if kind < 0.70:
             src = rng.choice([t for t in NUM if t != typ])
             return P.Cast(gen(src, depth - 1, rng), typ)
+        if kind < 0.75:
+            # numeric -> int rounds half away from zero; -> float only from a
+            # column / literal (<= 15 digits: exact in binary64 on both sides)
+            return P.Cast(gen("numeric", depth - 1 if typ in ("int2", "int4", "int8") else 0, rng),
+                          typ)
         if kind < 0.85:
             return P.Case([(gen("bool", depth - 1, rng), gen(typ, depth - 1, rng))],
                           gen(typ, depth - 1, rng) if rng.random() < 0.7 else None, typ)
@@ -587,6 +644,17 @@ def gen(typ, depth, rng):
         if typ == "int4" and rng.random() < 0.5:
             return P.Op("-", gen("date", depth - 1, rng), gen("date", depth - 1, rng))
         return gen(typ, 0, rng)
+    if typ == "numeric":
+        kind = rng.random()
+        if kind < 0.4:
+            return P.Op(rng.choice(["+", "-", "*"]), gen("numeric", depth - 1, rng),
+                        gen("numeric", depth - 1, rng))
+        if kind < 0.7:
+            return P.Cast(gen(rng.choice(NUM), depth - 1, rng), "numeric")
+        if kind < 0.8:
+            return P.Case([(gen("bool", depth - 1, rng), gen("numeric", depth - 1, rng))],
+                          gen("numeric", depth - 1, rng) if rng.random() < 0.7 else None, "numeric")
+        return gen("numeric", 0, rng)
     if typ == "date":
         kind = rng.random()
         if kind < 0.4:
@@ -715,23 +783,8 @@ def check_aggregation(table, tree, rows, simdir, lib):
         so.agg_reset()
         ok_rows, nrecheck = [], 0
         for row in rows:
-            toast = bytearray(b"\0" * 8)
-            valid = 0
-            for slot, c in enumerate(incols):
-                v = row[c]
-                if v is None:
-                    vals[slot] = 0
-                    continue
-                valid |= 1 << slot
-                if coltypes[c] in ("text", "bpchar", "numeric"):
-                    while len(toast) % 4:
-                        toast.append(0)
-                    vals[slot] = len(toast)
-                    toast += (T.varlena(v) if coltypes[c] != "numeric"
-                              else gp.numeric_datum(format(v, "f")))
-                else:
-                    vals[slot] = pack(v, coltypes[c])
-            rc = so.agg_row(vals, valid, kparams, bytes(toast))
+            valid, toast = fill_vals(row, incols, coltypes, vals)
+            rc = so.agg_row(vals, valid, kparams, toast)
             # what the row must have done
             want = 0
             try:
@@ -1023,22 +1076,8 @@ def test_end_to_end_against_postgres_own_aggregates(simdir, lib):
             so.agg_reset()
             host_rows = []
             for row in rows:
-                valid = 0
-                toast = bytearray(b"\0" * 8)
-                for slot, c in enumerate(incols):
-                    v = row[c]
-                    vals[slot] = 0
-                    if v is None:
-                        continue
-                    valid |= 1 << slot
-                    if coltypes[c] in ("text", "bpchar"):
-                        while len(toast) % 4:
-                            toast.append(0)
-                        vals[slot] = len(toast)
-                        toast += T.varlena(v)
-                    else:
-                        vals[slot] = pack(v, coltypes[c])
-                rc = so.agg_row(vals, valid, kparams, bytes(toast))
+                valid, toast = fill_vals(row, incols, coltypes, vals)
+                rc = so.agg_row(vals, valid, kparams, toast)
                 assert rc in (0, 0x100, CPU_RECHECK), rc
                 if rc == CPU_RECHECK:       # gpupreagg_next_tuple_fallback
                     host_rows.append(row)

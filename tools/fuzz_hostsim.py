@@ -37,6 +37,7 @@ def main():
     from pg_strom_b200 import pgplan as P
     lib = _capi.load()
     simdir = H.simdir.__wrapped__(lib)          # the fixture's body
+    H.install_device_numeric_range(setattr)     # what the autouse fixture does under pytest
     src = open(H.__file__).read()
     failures = 0
     for seed in range(args.first_seed, args.first_seed + args.seeds):
