@@ -16,6 +16,7 @@
  *                                      :3009-3194 (completion), mqueue.c:140-430,
  *                                      opencl_serv.c:76-215
  *   6. executor half (host + CUDA)     gpupreagg.c:2189-2941
+ *   7. SQL-side functions (host only)  gpupreagg.c:4251-4773, pg_strom--1.0.sql:99-401
  *
  * Convention: functions return a StromError_* code (pgstrom_kds.h), 0 = OK;
  * pgs_last_error() gives a thread-local detail message.  CpuReCheck (2) is a
@@ -303,6 +304,58 @@ const char *gpupreagg_end(pgs_gpupreagg_state *state);
 int         gpupreagg_rescan(pgs_gpupreagg_state *state);
 /* ExplainCustomPlan: gpupreagg_explain (gpupreagg.c:2859) */
 const char *gpupreagg_explain(pgs_gpupreagg_state *state, int verbose, int analyze);
+
+/* ------------------------------------------------------------------ 7 --- */
+/* SQL-side half (host only): the arithmetic under the fmgr V1 functions of
+ * pg_strom--1.0.sql:99-401 - partial placeholders, evaluated on the host for
+ * the rows of gpupreagg_recheck_rows(), and the accumulators of the final
+ * aggregates, called by PostgreSQL's Agg node for every partial row.
+ * INTEGRATION.md section 5 shows the one-line wrappers. */
+#define PGS_FINALFN_OVERFLOW    1   /* ereport: "value out of range: overflow" */
+#define PGS_FINALFN_BAD_NROWS   2   /* elog: "Bug? NULL or negative nrows was given" */
+#define PGS_FINALFN_BAD_NUMERIC 3   /* psum text is not a decimal number */
+#define PGS_PCOV_X   0
+#define PGS_PCOV_Y   1
+#define PGS_PCOV_X2  2
+#define PGS_PCOV_Y2  3
+#define PGS_PCOV_XY  4
+/* gpupreagg.c:4251 gpupreagg_partial_nrows(): pgstrom.nrows(bool, ...) */
+int32_t     pgs_partial_nrows(int nargs, const char *values, const char *isnull);
+/* gpupreagg.c:4308 gpupreagg_psum_x2_float(): pgstrom.psum_x2(float8);
+ * returns the isnull flag (pgstrom.psum / pmin / pmax return their argument,
+ * gpupreagg.c:4267-4306, and need no arithmetic) */
+int         pgs_psum_x2_float8(double x, int x_isnull, double *result);
+/* gpupreagg.c:4344-4417 gpupreagg_corr_psum_*(): pgstrom.pcov_x/y/x2/y2/xy
+ * (bool, float8, float8); kind = PGS_PCOV_*; returns the isnull flag */
+int         pgs_pcov_float8(int kind, int filter, int filter_isnull,
+                            double x, int x_isnull, double y, int y_isnull,
+                            double *result);
+/* gpupreagg.c:4434 pgstrom_avg_int8_accum(int8[2], int4 nrows, int8 psum) */
+int         pgs_avg_int8_accum(int64_t *trans, int32_t nrows, int64_t psum);
+/* gpupreagg.c:4470 pgstrom_sum_int8_accum(int8[2], int8 psum) */
+int         pgs_sum_int8_accum(int64_t *trans, int64_t psum);
+/* gpupreagg.c:4508 pgstrom_sum_int8_final(int8[2]); returns the isnull flag */
+int         pgs_sum_int8_final(const int64_t *trans, int64_t *result);
+/* gpupreagg.c:4622 pgstrom_sum_float8_accum(float8[3], int4, float8) */
+int         pgs_sum_float8_accum(double *trans, int32_t nrows, double psum);
+/* gpupreagg.c:4668 pgstrom_variance_float8_accum(float8[3], int4, float8, float8) */
+int         pgs_variance_float8_accum(double *trans, int32_t nrows,
+                                      double psum, double psum_x2);
+/* gpupreagg.c:4719 pgstrom_covariance_float8_accum(float8[6], int4, 5 x float8);
+ * psum[] = {pcov_x, pcov_x2, pcov_y, pcov_y2, pcov_xy} */
+int         pgs_covariance_float8_accum(double *trans, int32_t nrows,
+                                        const double *psum);
+/* gpupreagg.c:4540,4565 pgstrom_int8_avg_accum / pgstrom_numeric_avg_accum
+ * (internal, int4 nrows, numeric psum): N and an exact decimal sum; psum as
+ * decimal text (numeric_out / pgstrom_fixup_kernel_numeric), NULL = SQL NULL */
+typedef struct pgs_numeric_avg_state pgs_numeric_avg_state;
+pgs_numeric_avg_state *pgs_numeric_avg_init(void);
+void        pgs_numeric_avg_free(pgs_numeric_avg_state *state);
+int         pgs_numeric_avg_accum(pgs_numeric_avg_state *state, int32_t nrows,
+                                  int nrows_isnull, const char *psum_text);
+int64_t     pgs_numeric_avg_count(const pgs_numeric_avg_state *state);
+size_t      pgs_numeric_avg_sum_text(const pgs_numeric_avg_state *state,
+                                     char *buf, size_t buflen);
 
 #ifdef __cplusplus
 }

@@ -139,6 +139,24 @@ PROTOTYPES = {
     "gpupreagg_end": (C.c_char_p, [C.c_void_p]),
     "gpupreagg_rescan": (C.c_int, [C.c_void_p]),
     "gpupreagg_explain": (C.c_char_p, [C.c_void_p, C.c_int, C.c_int]),
+    # 7. SQL-side functions (host only)
+    "pgs_partial_nrows": (C.c_int32, [C.c_int, C.c_char_p, C.c_char_p]),
+    "pgs_psum_x2_float8": (C.c_int, [C.c_double, C.c_int, C.POINTER(C.c_double)]),
+    "pgs_pcov_float8": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                  C.c_double, C.c_int, C.POINTER(C.c_double)]),
+    "pgs_avg_int8_accum": (C.c_int, [C.POINTER(C.c_int64), C.c_int32, C.c_int64]),
+    "pgs_sum_int8_accum": (C.c_int, [C.POINTER(C.c_int64), C.c_int64]),
+    "pgs_sum_int8_final": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "pgs_sum_float8_accum": (C.c_int, [C.POINTER(C.c_double), C.c_int32, C.c_double]),
+    "pgs_variance_float8_accum": (C.c_int, [C.POINTER(C.c_double), C.c_int32,
+                                            C.c_double, C.c_double]),
+    "pgs_covariance_float8_accum": (C.c_int, [C.POINTER(C.c_double), C.c_int32,
+                                              C.POINTER(C.c_double)]),
+    "pgs_numeric_avg_init": (C.c_void_p, []),
+    "pgs_numeric_avg_free": (None, [C.c_void_p]),
+    "pgs_numeric_avg_accum": (C.c_int, [C.c_void_p, C.c_int32, C.c_int, C.c_char_p]),
+    "pgs_numeric_avg_count": (C.c_int64, [C.c_void_p]),
+    "pgs_numeric_avg_sum_text": (C.c_size_t, [C.c_void_p, C.c_char_p, C.c_size_t]),
 }
 
 _lib = None

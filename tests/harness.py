@@ -103,6 +103,7 @@ def final_aggregate(desc, partial_rows, q, extra_cast=None):
             argcols = [a["varattno"] - 1 for a in e["args"]]
             for pr in groups[k]:
                 fa.accum([pr[c] for c in argcols])
+            check_extension_accum(e, argcols, groups[k], fa)
             v = fa.final()
             t = fa.rettype
             if q.get("cast"):
@@ -115,6 +116,30 @@ def final_aggregate(desc, partial_rows, q, extra_cast=None):
             types.append(t)
         out.append(cells)
     return out, types
+
+
+def check_extension_accum(aggref, argcols, partial_rows, fa):
+    """The extension's own transition functions (include/pgstrom_cuda.h
+    section 7, pgstrom_*_accum of gpupreagg.c:4419-4773) over the same
+    partial rows must hold the state PostgreSQL's final function is given."""
+    from pg_strom_b200 import finalfn
+    try:
+        mine = finalfn.FinalAccum(aggref["orig_aggname"], aggref.get("orig_aggargtypes") or [])
+    except KeyError:
+        return              # count / min / max / sum(int8, float, numeric): PostgreSQL's own
+    for pr in partial_rows:
+        mine.accum([pr[c] for c in argcols])
+    got = mine.state()
+    if fa.agg == "sum":
+        exp = [fa.nn, fa.v]
+    elif fa.agg == "avg":
+        exp = [fa.N, fa.S]
+        got = got[:2]
+    else:
+        exp = list(fa.s)
+    same = len(got) == len(exp) and all(
+        a == b or (isinstance(a, float) and a != a and b != b) for a, b in zip(got, exp))
+    assert same, (aggref["orig_aggname"], got, exp)
 
 
 def recheck_partial_rows(gpreagg_node, table_rows, recheck):
