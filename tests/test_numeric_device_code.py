@@ -147,3 +147,41 @@ def test_casts(shim):
             assert rc == 0 and out.value == want, d
         else:
             assert rc == -1
+
+
+def test_recheck_agg_known_answers(shim, lib):
+    """The reference's only direct known-answer test of the device numeric
+    range: input/sql/recheck_agg.sql / expected/recheck_agg.out
+    (tests/golden/recheck_agg.json).  `select sum(<literal>)`: the literal
+    reaches the device as a numeric varlena (kern_parambuf); a value the 64-bit
+    device numeric holds comes back through pgstrom_fixup_kernel_numeric() as
+    the golden's text, one it does not hold raises CpuReCheck and PostgreSQL
+    computes the golden's text itself (the NOTICE of the golden).
+
+    One deliberate difference: here the exponent of a parsed
+    value is minus its display scale, so that sums / min / max print like
+    PostgreSQL's; 1E+48 (49 digits at scale 0) is therefore re-checked, where
+    the reference stores it as 10^17 x 10^31 and loses the display scale.  The
+    result text is the same either way."""
+    import json
+    with open(os.path.join(HERE, "golden", "recheck_agg.json")) as f:
+        stmts = json.load(f)
+    assert len(stmts) == 7
+    rechecked_here = []
+    for s in stmts:
+        lit = s["sql"].split("sum(")[1].split(")")[0]
+        d = Decimal(lit)
+        err, v, isnull = to_device(shim, d)
+        ref_rechecks = any("re-checked by CPU" in n for n in s["notices"])
+        if err == 0:
+            assert not isnull and not ref_rechecks, lit
+            buf = C.create_string_buffer(128)
+            assert lib.pgstrom_fixup_kernel_numeric(v, buf, len(buf)) == 0
+            # numeric_in() of the fixed-up text, numeric_out() of that
+            assert format(Decimal(buf.value.decode()), "f") == s["rows"][0][0], lit
+        else:
+            assert err == 2 and isnull, lit
+            rechecked_here.append(lit)
+            assert format(d, "f") == s["rows"][0][0], lit      # what the host computes
+            assert ref_rechecks or lit == "1E+48", lit
+    assert rechecked_here == ["1E+48", "1E-33", "1E+49", "1E+1000", "1E-1000"]
