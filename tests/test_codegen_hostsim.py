@@ -982,6 +982,8 @@ def _final_values(desc, partial_rows):
             argcols = [a["varattno"] - 1 for a in e["args"]]
             for pr in prs:
                 fa.accum([pr[c] for c in argcols])
+            import harness
+            harness.check_extension_accum(e, argcols, prs, fa)   # the library's pgstrom_*_accum
             vals.append((fa.final(), fa.rettype))
         out[k] = vals
     return out

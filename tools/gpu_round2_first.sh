@@ -3,6 +3,9 @@
 # bench at 1 / 10 / 50 % selectivity with and without it, then an ncu capture.
 # usage: gpurun --timeout 900 -- 'bash tools/gpu_round2_first.sh'
 mkdir -p gpurun_out
+# whole GPU suite first (no -x): several tests written at the end of round 1 have never run on a
+# GPU and are xfail(strict=False) until they have (test_zz_*, the experimental variant)
+timeout 1500 python -m pytest tests -m gpu -q -rxXf --timeout 300 > gpurun_out/t_all.log 2>&1; echo "rc=$?" >> gpurun_out/t_all.log
 PGSTROM_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_workloads.py -x -q \
     --timeout 120 -k gather > gpurun_out/t_gather.log 2>&1; echo "rc=$?" >> gpurun_out/t_gather.log
 for sel in 1 10 50; do
