@@ -1108,10 +1108,25 @@ pgstrom_try_insert_gpupreagg(const JsonPtr &agg)
         sort_plan = outer_plan;
         outer_plan = outer_plan->getp("lefttree");
     }
+    /* Any plan node can feed GpuPreAgg (gpupreagg.c:2031-2107): a SeqScan is
+     * replaced by a GpuScan whose device quals move into this kernel
+     * (gpuscan_try_replace_seqscan_plan, gpuscan.c:378-517); every other
+     * node - a join, a Result, an index scan - stays what it is, keeps its
+     * quals and hands its tuples over one by one (gpupreagg_load_next_outer,
+     * gpupreagg.c:2418-2505: pgstrom_data_store_insert_tuple into ROW_FLAT
+     * chunks). */
     std::string onode = outer_plan->s("node");
-    if (onode != "SeqScan" && onode != "GpuScan")
+    bool outer_is_scan = (onode == "SeqScan" || onode == "GpuScan");
+    if (onode.empty() || !outer_plan->getp("targetlist"))
     {
         gp.reject_reason = "outer plan " + onode + " cannot feed GpuPreAgg";
+        return gp;
+    }
+    /* a chunk needs at least one column ("select sum(1E+48)" over a Result,
+     * recheck_agg.sql, stays on the CPU) */
+    if (json_list(outer_plan->get("targetlist")).empty())
+    {
+        gp.reject_reason = "outer plan " + onode + " has no output column";
         return gp;
     }
     for (auto &g : json_list(agg->get("grpColIdx")))
@@ -1186,14 +1201,17 @@ pgstrom_try_insert_gpupreagg(const JsonPtr &agg)
     /* pull up device-runnable qualifiers of the scan
      * (gpuscan_try_replace_seqscan_plan, gpuscan.c:378-517) */
     std::vector<JsonPtr> outer_quals, host_quals;
-    for (auto &q : json_list(outer_plan->get("qual")))
+    if (outer_is_scan)
     {
-        if (codegen_available_expression(q))
-            outer_quals.push_back(q);
-        else
-            host_quals.push_back(q);
+        for (auto &q : json_list(outer_plan->get("qual")))
+        {
+            if (codegen_available_expression(q))
+                outer_quals.push_back(q);
+            else
+                host_quals.push_back(q);
+        }
     }
-    gp.outer_bulkload = host_quals.empty();
+    gp.outer_bulkload = outer_is_scan && host_quals.empty();
     gp.needs_grouping = !gp.grp_col_idx.empty();
     gp.num_groups = agg->d("numGroups", agg->d("plan_rows", 1.0));
     if (gp.num_groups < 1.0)
@@ -1209,15 +1227,19 @@ pgstrom_try_insert_gpupreagg(const JsonPtr &agg)
     gp.extra_flags |= ctx.extra_flags;
 
     /* ---- splice: Agg(alt aggregates) -> [Sort] -> GpuPreAgg -> GpuScan ---- */
-    JsonPtr gpuscan = Json::object();
-    for (auto &kv : outer_plan->obj)
-        gpuscan->set(kv.first, kv.second);
-    gpuscan->set("node", "CustomPlan");
-    gpuscan->set("custom_name", "GpuScan");
-    JsonPtr hq = Json::array();
-    for (auto &q : host_quals) hq->push(q);
-    gpuscan->set("qual", hq);
-    gpuscan->set("dev_quals", Json::array());   /* moved up */
+    JsonPtr gpuscan = outer_plan;                /* not a scan: left alone */
+    if (outer_is_scan)
+    {
+        gpuscan = Json::object();
+        for (auto &kv : outer_plan->obj)
+            gpuscan->set(kv.first, kv.second);
+        gpuscan->set("node", "CustomPlan");
+        gpuscan->set("custom_name", "GpuScan");
+        JsonPtr hq = Json::array();
+        for (auto &q : host_quals) hq->push(q);
+        gpuscan->set("qual", hq);
+        gpuscan->set("dev_quals", Json::array());   /* moved up */
+    }
 
     JsonPtr gpreagg = Json::object();
     gpreagg->set("node", "CustomPlan");

@@ -138,7 +138,7 @@ def check_extension_accum(aggref, argcols, partial_rows, fa):
     else:
         exp = list(fa.s)
     same = len(got) == len(exp) and all(
-        a == b or (isinstance(a, float) and a != a and b != b) for a, b in zip(got, exp))
+        a == b or (a != a and b != b) for a, b in zip(got, exp))     # NaN == NaN here
     assert same, (aggref["orig_aggname"], got, exp)
 
 

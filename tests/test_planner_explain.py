@@ -57,3 +57,84 @@ def test_explain_matches_reference_goldens(lib):
     n_ref = sum(1 for s in stmts if any("GpuPreAgg" in ln for ln in s["plan"]))
     assert n_off == n_ref - len(numeric_gap)
     assert n_off >= 190
+
+
+def _over_join(sql):
+    """The statement's plan with a HashJoin (of the scan with itself, its
+    output = the scan's) between the Agg and the scan."""
+    q = P.parse_regression_sql(sql)
+    table, rows = harness.fixture_table(q["table"])
+    tree = P.plan_regression_sql(sql, table)
+    agg = tree if tree["node"] == "Agg" else tree["lefttree"]
+    scan = agg["lefttree"]
+    agg["lefttree"] = {"node": "HashJoin", "targetlist": scan["targetlist"], "qual": [],
+                       "hashclauses": ["(a.id = b.id)"], "lefttree": scan,
+                       "righttree": {"node": "Hash", "targetlist": [], "lefttree": dict(scan)}}
+    return q, table, rows, tree
+
+
+def test_any_outer_plan_feeds_gpupreagg(lib):
+    """gpupreagg.c:2031-2107: only a SeqScan below the Agg becomes a GpuScan
+    whose quals move into the kernel; any other node (here a HashJoin) stays
+    as it is, keeps its quals and feeds GpuPreAgg tuple by tuple
+    (gpupreagg_load_next_outer, gpupreagg.c:2418-2505 -> "Bulkload: Off").
+    The partial rows of the join's output, merged by the final aggregates,
+    are the statement's golden result."""
+    import json
+    from oracle import partial
+    with open(os.path.join(os.path.dirname(__file__), "golden", "where_agg.json")) as f:
+        golden = {" ".join(s["sql"].split()): s["rows"] for s in json.load(f)}
+    for sql in ("select avg(smlint_x) from gpupreagg_test where key=1 group by key order by key;",
+                "select covar_pop(bigsrl_x,bigsrl_x) from gpupreagg_test where key=1 "
+                "group by key order by key;"):
+        q, table, rows, tree = _over_join(sql)
+        plan = gp.Plan(tree, gucs=harness.GUCS)
+        try:
+            assert plan.num_gpupreagg == 1, plan.reject_reason
+            out = plan.explain()
+            node = harness.find_gpreagg_node(plan.tree())
+            assert node["outer_bulkload"] is False and node["outer_quals"] == []
+            child = node["lefttree"]
+            assert child["node"] == "HashJoin"
+            scan = child["lefttree"]
+            assert scan["node"] == "SeqScan" and len(scan["qual"]) == 1    # untouched
+            i = next(k for k, ln in enumerate(out) if "Custom (GpuPreAgg)" in ln)
+            assert any("Bulkload: Off" in ln for ln in out[i:i + 4]), out
+            assert any("HashJoin" in ln for ln in out[i:]), out
+            # the kernel of this plan builds for sm_100a (its qual is empty)
+            prog = plan.build_program()
+            lib.pgs_program_release(prog)
+            # the join's output = the scan's rows that pass the scan's filter
+            tuples = [t for t, r in zip(harness.rows_as_tuples(table, rows), rows)
+                      if r["key"] == q["where_key"]]
+            desc = plan.describe()
+            prs = []
+            for row0 in range(0, len(tuples), 997):
+                g, order = partial.partial_rows(node, tuples[row0:row0 + 997], len(table.columns))
+                prs.extend(tuple(g[k]) for k in order)
+            got, types = harness.final_aggregate(desc, prs, q)
+            exp = golden[" ".join(sql.split())]
+            assert len(got) == len(exp)
+            for gr, er in zip(got, exp):
+                assert all(a == b or harness.cells_match(a, b, t)
+                           for a, b, t in zip(gr, er, types)), (sql, gr, er)
+        finally:
+            plan.free()
+
+
+def test_outer_plan_without_columns_is_left_alone(lib):
+    """`select sum(1E+48)` (recheck_agg.sql): Agg over a Result without output
+    columns - a chunk needs at least one column, the statement stays on the
+    CPU (the numeric range it probes is pinned in test_numeric_device_code.py)."""
+    agg = {"node": "Agg", "aggstrategy": "plain", "grpColIdx": [], "numGroups": 1.0,
+           "targetlist": [{"node": "TargetEntry",
+                           "expr": P.Agg("sum", [P.Const("numeric", "1E+48")]),
+                           "resno": 1, "resname": "sum", "resjunk": False}],
+           "qual": [], "lefttree": {"node": "Result", "targetlist": [], "qual": []}}
+    plan = gp.Plan(agg, gucs=harness.GUCS)
+    try:
+        assert plan.num_gpupreagg == 0
+        assert "no output column" in plan.reject_reason
+        assert not any("GpuPreAgg" in ln for ln in plan.explain())
+    finally:
+        plan.free()
