@@ -166,11 +166,16 @@ def find_gpreagg_node(tree):
     return None
 
 
-def run_statement_gpu(sql, chunk_rows=None, device=0, fmt="column"):
-    """Returns dict(offloaded, rows, error, notices, nrecheck)."""
+def run_statement_gpu(sql, chunk_rows=None, device=0, fmt="column", plan_tree=None,
+                      outer_rows=None):
+    """Returns dict(offloaded, rows, error, notices, nrecheck).  `plan_tree`
+    replaces the statement's own plan (same table), `outer_rows(row) -> bool`
+    says which table rows the node below GpuPreAgg delivers."""
     q = P.parse_regression_sql(sql)
     table, rows = fixture_table(q["table"])
-    plan = gp.Plan(P.plan_regression_sql(sql, table), gucs=GUCS)
+    if outer_rows is not None:
+        rows = [r for r in rows if outer_rows(r)]
+    plan = gp.Plan(plan_tree or P.plan_regression_sql(sql, table), gucs=GUCS)
     try:
         if plan.num_gpupreagg == 0:
             return {"offloaded": False, "reason": plan.reject_reason}
