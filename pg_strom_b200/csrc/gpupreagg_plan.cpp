@@ -1,6 +1,7 @@
 /*
  * gpupreagg_plan.cpp - planner half of GpuPreAgg.  See pgs_plan.h.
  */
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <sstream>
@@ -1081,6 +1082,101 @@ json_list(const Json *j)
     return v;
 }
 
+/* ------------------------------------------------------------------
+ * cost_gpupreagg (gpupreagg.c:366-464), the part that is the extension's own:
+ * cost / rows / width of the GpuPreAgg node from the outer plan's estimates.
+ * The costs of the Sort and the Agg above it are PostgreSQL's cost_sort() /
+ * cost_agg() over these numbers (:466-509) and the decision "cheaper than
+ * the plain Agg, unless pg_strom.debug_force_gpupreagg" (:2105-2118) is
+ * taken by the glue, which owns those functions.
+ * Only done when the outer plan carries PostgreSQL's estimates.
+ * ------------------------------------------------------------------ */
+static void
+count_operator_nodes(const Json *j, int *count)
+{
+    if (!j)
+        return;
+    if (j->kind == Json::Array)
+    {
+        for (auto &e : j->arr)
+            count_operator_nodes(e.get(), count);
+        return;
+    }
+    if (j->kind != Json::Object)
+        return;
+    /* cost_qual_eval_walker: procost (1 for every built-in and for the
+     * pgstrom.* placeholders) x cpu_operator_cost per function call */
+    std::string n = j->s("node");
+    if (n == "OpExpr" || n == "FuncExpr" || n == "DistinctExpr" ||
+        n == "NullIfExpr" || n == "CoerceViaIO")
+        (*count)++;
+    for (auto &kv : j->obj)
+        count_operator_nodes(kv.second.get(), count);
+}
+
+static int
+typavgwidth(const std::string &type, int typmod)
+{
+    /* get_typavgwidth(): typlen for fixed-length types, typmod-derived or 32
+     * for varlena */
+    static const struct { const char *name; int len; } fixed[] = {
+        {"bool", 1}, {"int2", 2}, {"int4", 4}, {"int8", 8}, {"float4", 4},
+        {"float8", 8}, {"date", 4}, {"time", 8}, {"timestamp", 8},
+        {"timestamptz", 8},
+    };
+    for (auto &f : fixed)
+        if (type == f.name)
+            return f.len;
+    if (type == "bpchar" && typmod > 4)
+        return typmod - 4;
+    return 32;
+}
+
+static void
+cost_gpupreagg(const JsonPtr &agg, const JsonPtr &outer_plan,
+               const std::vector<JsonPtr> &pre_tlist, JsonPtr &gpreagg)
+{
+    if (!outer_plan->has("total_cost") || !outer_plan->has("plan_rows"))
+        return;
+    const double BLCKSZ_ = 8192.0, page_header = 24.0, item_id = 4.0, htup_header = 24.0;
+    double cpu_operator_cost = agg->d("cpu_operator_cost", 0.0025);
+    double gpu_operator_cost = guc_real("gpu_operator_cost");
+    double startup_cost = outer_plan->d("startup_cost", 0.0);
+    double run_cost = outer_plan->d("total_cost") - startup_cost;
+    double outer_rows = outer_plan->d("plan_rows");
+    double outer_width = outer_plan->d("plan_width", 0.0);
+    double num_groups = std::max(agg->d("plan_rows", agg->d("numGroups", 1.0)), 1.0);
+    auto maxalign = [](double x) { return std::ceil(x / 8.0) * 8.0; };
+    auto log2_ = [](double x) { return std::log(x) / 0.693147180559945; };
+
+    startup_cost += guc_real("gpu_setup_cost");
+    double rows_per_chunk =
+        std::floor((double)(guc_int("pg_strom.chunk_size") << 20) / BLCKSZ_) *
+        (BLCKSZ_ - maxalign(page_header)) /
+        (item_id + maxalign(htup_header + outer_width));
+    double num_chunks = std::max(outer_rows / rows_per_chunk, 1.0);
+    double comparison_cost = 2.0 * gpu_operator_cost;
+    startup_cost += comparison_cost * log2_(rows_per_chunk * rows_per_chunk) * num_chunks;
+    run_cost += gpu_operator_cost * outer_rows;
+
+    int noperators = 0, pagg_width = 0;
+    for (auto &tle : pre_tlist)
+    {
+        JsonPtr e = tle->getp("expr");
+        count_operator_nodes(e.get(), &noperators);
+        int typmod = (e && e->has("vartypmod")) ? (int)e->i("vartypmod") : -1;
+        pagg_width += typavgwidth(expr_type(tle), typmod);
+    }
+    double per_tuple = noperators * cpu_operator_cost;
+    run_cost += per_tuple * gpu_operator_cost / cpu_operator_cost *
+        log2_(rows_per_chunk) * num_chunks;
+
+    gpreagg->set("startup_cost", Json::number(startup_cost));
+    gpreagg->set("total_cost", Json::number(startup_cost + run_cost));
+    gpreagg->set("plan_rows", Json::number(num_groups * num_chunks));
+    gpreagg->set("plan_width", pagg_width);
+}
+
 GpuPreAggPlan
 pgstrom_try_insert_gpupreagg(const JsonPtr &agg)
 {
@@ -1255,6 +1351,7 @@ pgstrom_try_insert_gpupreagg(const JsonPtr &agg)
     gpreagg->set("num_groups", Json::number(gp.num_groups));
     gpreagg->set("extra_flags", gp.extra_flags);
     gpreagg->set("lefttree", gpuscan);
+    cost_gpupreagg(agg, outer_plan, ctx.pre_tlist, gpreagg);
 
     JsonPtr new_agg = Json::object();
     for (auto &kv : agg->obj)

@@ -138,3 +138,51 @@ def test_outer_plan_without_columns_is_left_alone(lib):
         assert not any("GpuPreAgg" in ln for ln in plan.explain())
     finally:
         plan.free()
+
+
+def test_cost_gpupreagg(lib):
+    """cost_gpupreagg (gpupreagg.c:366-464): startup / total cost, rows and
+    width of the GpuPreAgg node from the outer plan's estimates, restated here
+    from the reference's formula; without estimates (the regression plans) the
+    node carries none and the plan is rewritten like under
+    pg_strom.debug_force_gpupreagg."""
+    import math
+    import pytest
+    sql = "select key, avg(float_x) from gpupreagg_test group by key order by key;"
+    q = P.parse_regression_sql(sql)
+    table, _ = harness.fixture_table(q["table"])
+    tree = P.plan_regression_sql(sql, table)
+    plan = gp.Plan(tree, gucs=harness.GUCS)
+    assert "total_cost" not in harness.find_gpreagg_node(plan.tree())
+    plan.free()
+
+    tree = P.plan_regression_sql(sql, table)
+    agg = tree["lefttree"] if tree["node"] == "Sort" else tree
+    scan = agg["lefttree"]["lefttree"] if agg["lefttree"]["node"] == "Sort" else agg["lefttree"]
+    scan.update(startup_cost=0.0, total_cost=834.0, plan_rows=40000.0, plan_width=50)
+    agg.update(plan_rows=31.0)
+    for gucs in ({}, {"pg_strom.chunk_size": "4", "gpu_setup_cost": "100",
+                      "gpu_operator_cost": "0.0001"}):
+        plan = gp.Plan(tree, gucs=dict(harness.GUCS, **gucs))
+        try:
+            node = harness.find_gpreagg_node(plan.tree())
+            chunk_mb = int(gucs.get("pg_strom.chunk_size", 15))
+            setup = float(gucs.get("gpu_setup_cost", 500))
+            gop = float(gucs.get("gpu_operator_cost", 0.000025))
+            cop = 0.0025
+            maxalign = lambda x: (x + 7) // 8 * 8
+            rows_per_chunk = ((chunk_mb << 20) // 8192) * (8192 - maxalign(24)) / \
+                (4 + maxalign(24 + 50))
+            num_chunks = max(40000.0 / rows_per_chunk, 1.0)
+            startup = 0.0 + setup + 2.0 * gop * math.log2(rows_per_chunk ** 2) * num_chunks
+            run = 834.0 + gop * 40000.0
+            # target list: 11 outer columns (key Var, NULL consts), nrows(float_x IS NOT NULL)
+            # and psum(float_x): two function calls
+            run += 2 * cop * gop / cop * math.log2(rows_per_chunk) * num_chunks
+            width = 4 + 4 + 2 + 4 + 8 + 4 + 8 + 32 + 2 + 4 + 8 + 4 + 8
+            assert node["plan_width"] == width
+            assert node["plan_rows"] == pytest.approx(31.0 * num_chunks, rel=1e-12)
+            assert node["startup_cost"] == pytest.approx(startup, rel=1e-12)
+            assert node["total_cost"] == pytest.approx(startup + run, rel=1e-12)
+        finally:
+            plan.free()
