@@ -24,3 +24,12 @@ for cfg in "1728 2 2048" "1408 3 2048" "1344 3 2048" "1408 4 1024" "1728 3 1024"
       --workload where_agg --rows 50000000 --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 \
       > gpurun_out/bench_where_slots$1_st$2_tile$3.json 2> gpurun_out/bench_where_slots$1_st$2_tile$3.err
 done
+# the many-groups path has no ncu capture yet (roofline.traffic is null for it): deal kernel first,
+# then gpupreagg_partagg (-k picks by name; make_profiles.py takes the .ncu-rep files)
+bash tools/gpu_ncu.sh hc --workload high_cardinality --rows 50000000
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gpupreagg_partagg -s 3 -c 1 -f \
+    -o gpurun_out/prof_hc_partagg python bench.py --workload high_cardinality --rows 50000000 --steps 2 \
+    --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-check > gpurun_out/ncu_hc_partagg.log 2>&1
+# not yet measured in round 1: Zipf(1.0) keys, where_agg at 50 % (covered by the loop above)
+timeout 200 python bench.py --workload high_cardinality --zipf --rows 50000000 --steps 3 --warmup 3 \
+    --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_hc_zipf.json 2> gpurun_out/bench_hc_zipf.err
