@@ -1392,7 +1392,13 @@ grafter_try_replace_recurse(const JsonPtr &plan, std::vector<GpuPreAggPlan> *pla
             newnode = gp.plan;
             if (plans)
                 plans->push_back(gp);
-            return newnode;     /* children were rebuilt */
+            /* a GpuScan below is this node's own; any other outer plan
+             * (join, sub-query scan) may hold further aggregates */
+            JsonPtr child = gp.gpreagg->getp("lefttree");
+            if (child && !child->is_null() &&
+                !(child->s("node") == "CustomPlan" && child->s("custom_name") == "GpuScan"))
+                gp.gpreagg->set("lefttree", grafter_try_replace_recurse(child, plans));
+            return newnode;
         }
     }
     JsonPtr copy = Json::object();

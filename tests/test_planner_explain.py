@@ -186,3 +186,28 @@ def test_cost_gpupreagg(lib):
             assert node["total_cost"] == pytest.approx(startup + run, rel=1e-12)
         finally:
             plan.free()
+
+
+def test_aggregates_below_a_join_are_rewritten_too(lib):
+    """Agg -> HashJoin -> (Agg -> SeqScan): both aggregates get a GpuPreAgg;
+    the inner one keeps its GpuScan with the quals pulled up."""
+    sql = "select avg(smlint_x) from gpupreagg_test where key=1 group by key order by key;"
+    q, table, rows, tree = _over_join(sql)
+    agg = tree if tree["node"] == "Agg" else tree["lefttree"]
+    join = agg["lefttree"]
+    inner = P.plan_regression_sql("select key, max(integer_x) from gpupreagg_test where key=2 "
+                                  "group by key order by key;", table)
+    join["righttree"] = {"node": "Hash", "targetlist": [], "lefttree": inner}
+    plan = gp.Plan(tree, gucs=harness.GUCS)
+    try:
+        assert plan.num_gpupreagg == 2, plan.reject_reason
+        t = plan.tree()
+        outer = harness.find_gpreagg_node(t)
+        assert outer["lefttree"]["node"] == "HashJoin" and outer["outer_quals"] == []
+        inner_g = harness.find_gpreagg_node(outer["lefttree"]["righttree"])
+        assert inner_g is not None and len(inner_g["outer_quals"]) == 1
+        assert inner_g["lefttree"]["custom_name"] == "GpuScan"
+        for idx in range(2):
+            assert "gpupreagg_projection" in plan.kernel_source(idx)
+    finally:
+        plan.free()
