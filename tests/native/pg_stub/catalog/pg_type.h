@@ -1,0 +1,3 @@
+/* TEST STAND-IN, see ../postgres.h */
+#define INT8OID     20
+#define FLOAT8OID   701
