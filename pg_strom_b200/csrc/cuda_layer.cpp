@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 #include <nvrtc.h>
 #include <dlfcn.h>
+#include <errno.h>
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -68,37 +70,111 @@ set_error(const char *fmt, ...)
     } while (0)
 
 /* ------------------------------------------------------------------
- * CRC32 (key of the program cache, opencl_devprog.c:580-659)
+ * SHA-256 (FIPS 180-4): key of the program cache.  The reference keys its
+ * cache by a CRC32 of the source and compares the full text on a hit
+ * (opencl_devprog.c:580-659); the on-disk cache here cannot compare texts, so
+ * the key is a cryptographic digest of everything the binary depends on and
+ * the file carries the digest for verification.
  * ------------------------------------------------------------------ */
-static uint32_t
-crc32_buf(uint32_t crc, const void *data, size_t len)
+struct Sha256
 {
-    static uint32_t table[256];
-    static bool init = false;
-    if (!init)
+    uint32_t    h[8];
+    uint64_t    nbytes = 0;
+    unsigned char buf[64];
+    size_t      fill = 0;
+
+    Sha256()
     {
-        for (uint32_t i = 0; i < 256; i++)
-        {
-            uint32_t c = i;
-            for (int k = 0; k < 8; k++)
-                c = (c & 1) ? (0xEDB88320U ^ (c >> 1)) : (c >> 1);
-            table[i] = c;
-        }
-        init = true;
+        static const uint32_t init[8] = {
+            0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a,
+            0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19 };
+        memcpy(h, init, sizeof(h));
     }
-    const unsigned char *p = (const unsigned char *)data;
-    crc = ~crc;
-    for (size_t i = 0; i < len; i++)
-        crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
-    return ~crc;
-}
+    static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+    void block(const unsigned char *p)
+    {
+        static const uint32_t K[64] = {
+            0x428a2f98,0x71374491,0xb5c0fbcf,0xe9b5dba5,0x3956c25b,0x59f111f1,0x923f82a4,0xab1c5ed5,
+            0xd807aa98,0x12835b01,0x243185be,0x550c7dc3,0x72be5d74,0x80deb1fe,0x9bdc06a7,0xc19bf174,
+            0xe49b69c1,0xefbe4786,0x0fc19dc6,0x240ca1cc,0x2de92c6f,0x4a7484aa,0x5cb0a9dc,0x76f988da,
+            0x983e5152,0xa831c66d,0xb00327c8,0xbf597fc7,0xc6e00bf3,0xd5a79147,0x06ca6351,0x14292967,
+            0x27b70a85,0x2e1b2138,0x4d2c6dfc,0x53380d13,0x650a7354,0x766a0abb,0x81c2c92e,0x92722c85,
+            0xa2bfe8a1,0xa81a664b,0xc24b8b70,0xc76c51a3,0xd192e819,0xd6990624,0xf40e3585,0x106aa070,
+            0x19a4c116,0x1e376c08,0x2748774c,0x34b0bcb5,0x391c0cb3,0x4ed8aa4a,0x5b9cca4f,0x682e6ff3,
+            0x748f82ee,0x78a5636f,0x84c87814,0x8cc70208,0x90befffa,0xa4506ceb,0xbef9a3f7,0xc67178f2 };
+        uint32_t w[64], v[8];
+        for (int i = 0; i < 16; i++)
+            w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) |
+                   ((uint32_t)p[4 * i + 2] << 8) | (uint32_t)p[4 * i + 3];
+        for (int i = 16; i < 64; i++)
+        {
+            uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+            uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        memcpy(v, h, sizeof(v));
+        for (int i = 0; i < 64; i++)
+        {
+            uint32_t S1 = rotr(v[4], 6) ^ rotr(v[4], 11) ^ rotr(v[4], 25);
+            uint32_t ch = (v[4] & v[5]) ^ (~v[4] & v[6]);
+            uint32_t t1 = v[7] + S1 + ch + K[i] + w[i];
+            uint32_t S0 = rotr(v[0], 2) ^ rotr(v[0], 13) ^ rotr(v[0], 22);
+            uint32_t mj = (v[0] & v[1]) ^ (v[0] & v[2]) ^ (v[1] & v[2]);
+            uint32_t t2 = S0 + mj;
+            v[7] = v[6]; v[6] = v[5]; v[5] = v[4]; v[4] = v[3] + t1;
+            v[3] = v[2]; v[2] = v[1]; v[1] = v[0]; v[0] = t1 + t2;
+        }
+        for (int i = 0; i < 8; i++)
+            h[i] += v[i];
+    }
+    void update(const void *data, size_t len)
+    {
+        const unsigned char *p = (const unsigned char *)data;
+        nbytes += len;
+        while (len > 0)
+        {
+            size_t n = std::min(len, sizeof(buf) - fill);
+            memcpy(buf + fill, p, n);
+            fill += n; p += n; len -= n;
+            if (fill == sizeof(buf))
+            {
+                block(buf);
+                fill = 0;
+            }
+        }
+    }
+    /* fields are length-prefixed so that (a, bc) and (ab, c) differ */
+    void field(const void *data, size_t len)
+    {
+        uint64_t n = len;
+        update(&n, sizeof(n));
+        update(data, len);
+    }
+    std::string hex()
+    {
+        uint64_t bits = nbytes * 8;
+        unsigned char pad = 0x80;
+        update(&pad, 1);
+        pad = 0;
+        while (fill != 56)
+            update(&pad, 1);
+        unsigned char lenb[8];
+        for (int i = 0; i < 8; i++)
+            lenb[i] = (unsigned char)(bits >> (56 - 8 * i));
+        update(lenb, 8);
+        char out[65];
+        for (int i = 0; i < 8; i++)
+            snprintf(out + 8 * i, 9, "%08x", h[i]);
+        return std::string(out, 64);
+    }
+};
 
 /* ------------------------------------------------------------------
  * device programs
  * ------------------------------------------------------------------ */
 struct pgs_program
 {
-    uint32_t    crc;
+    std::string key;        /* SHA-256 (hex) of source, flags, options, runtime headers, NVRTC */
     std::string source;
     int         extra_flags;
     std::string options;
@@ -110,23 +186,115 @@ struct pgs_program
 };
 
 static std::mutex program_lock;
-static std::map<uint32_t, pgs_program *> program_cache;
+static std::map<std::string, pgs_program *> program_cache;
+
+/*
+ * Where built programs are kept between processes: PGSTROM_CUBIN_CACHE, else
+ * _cubin_cache/ next to the library (in-tree, so that pre-built programs
+ * travel with it), else ~/.cache/pgstrom_cubin.  Never a shared directory
+ * like /tmp: a cubin found there runs on the GPU with the caller's data.  The
+ * directory is created 0700 and used only if it belongs to this user and
+ * nobody else may write to it; otherwise there is no disk cache ("").
+ */
+static bool
+cache_dir_usable(const std::string &dir)
+{
+    struct stat st;
+
+    if (mkdir(dir.c_str(), 0700) != 0 && errno != EEXIST)
+        return false;
+    if (stat(dir.c_str(), &st) != 0 || !S_ISDIR(st.st_mode))
+        return false;
+    if (st.st_uid != geteuid() || (st.st_mode & (S_IWGRP | S_IWOTH)) != 0)
+        return false;
+    return true;
+}
 
 static std::string
 cubin_cache_dir()
 {
     const char *env = getenv("PGSTROM_CUBIN_CACHE");
+    std::vector<std::string> cands;
     if (env && *env)
-        return env;
-    Dl_info info;
-    if (dladdr((void *)&crc32_buf, &info) && info.dli_fname)
+        cands.push_back(env);
+    else
     {
-        std::string p = info.dli_fname;
-        size_t slash = p.rfind('/');
-        if (slash != std::string::npos)
-            return p.substr(0, slash) + "/_cubin_cache";
+        Dl_info info;
+        if (dladdr((void *)&cache_dir_usable, &info) && info.dli_fname)
+        {
+            std::string p = info.dli_fname;
+            size_t slash = p.rfind('/');
+            if (slash != std::string::npos)
+                cands.push_back(p.substr(0, slash) + "/_cubin_cache");
+        }
+        const char *home = getenv("HOME");
+        if (home && *home)
+        {
+            std::string c = std::string(home) + "/.cache";
+            mkdir(c.c_str(), 0700);
+            cands.push_back(c + "/pgstrom_cubin");
+        }
     }
-    return "/tmp/pgstrom_cubin_cache";
+    for (auto &d : cands)
+        if (cache_dir_usable(d))
+            return d;
+    return "";
+}
+
+/* file = magic, 64 hex digits of the key, cubin.  A file whose key is not
+ * the one asked for (renamed, truncated, planted) is ignored. */
+static const char CUBIN_FILE_MAGIC[8] = { 'P', 'G', 'S', 'C', 'U', 'B', '0', '2' };
+
+static bool
+cubin_file_read(const std::string &path, const std::string &key, std::vector<char> &cubin)
+{
+    FILE *fp = fopen(path.c_str(), "rb");
+    char head[8 + 64];
+    bool ok = false;
+
+    if (!fp)
+        return false;
+    if (fread(head, 1, sizeof(head), fp) == sizeof(head) &&
+        memcmp(head, CUBIN_FILE_MAGIC, 8) == 0 && memcmp(head + 8, key.data(), 64) == 0)
+    {
+        long pos = ftell(fp);
+        fseek(fp, 0, SEEK_END);
+        long sz = ftell(fp) - pos;
+        fseek(fp, pos, SEEK_SET);
+        if (sz > 0)
+        {
+            cubin.resize((size_t)sz);
+            ok = (fread(cubin.data(), 1, (size_t)sz, fp) == (size_t)sz);
+            if (!ok)
+                cubin.clear();
+        }
+    }
+    fclose(fp);
+    return ok;
+}
+
+static void
+cubin_file_write(const std::string &path, const std::string &key, const std::vector<char> &cubin)
+{
+    std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL, 0600);
+    if (fd < 0)
+        return;
+    FILE *fp = fdopen(fd, "wb");
+    if (!fp)
+    {
+        close(fd);
+        unlink(tmp.c_str());
+        return;
+    }
+    bool ok = fwrite(CUBIN_FILE_MAGIC, 1, 8, fp) == 8 &&
+              fwrite(key.data(), 1, 64, fp) == 64 &&
+              fwrite(cubin.data(), 1, cubin.size(), fp) == cubin.size();
+    ok = (fclose(fp) == 0) && ok;
+    if (ok)
+        rename(tmp.c_str(), path.c_str());
+    else
+        unlink(tmp.c_str());
 }
 
 static std::string
@@ -203,7 +371,7 @@ pgs_program_build(const char *kern_source, int extra_flags,
 {
     static thread_local std::string log_buf;
     std::string options = program_options(extra_flags);
-    uint32_t crc = 0;
+    std::string key;
 
     if (build_log)
         *build_log = NULL;
@@ -212,33 +380,39 @@ pgs_program_build(const char *kern_source, int extra_flags,
         set_error("pgs_program_build: bad arguments");
         return StromError_BadRequestMessage;
     }
-    crc = crc32_buf(crc, kern_source, strlen(kern_source));
-    crc = crc32_buf(crc, &extra_flags, sizeof(extra_flags));
-    crc = crc32_buf(crc, options.data(), options.size());
-    /* the static runtime is part of the key: a new library build must not
-     * pick up stale binaries from the on-disk cache */
-    crc = crc32_buf(crc, pgs_hdr_kern_gpupreagg_cuh, strlen(pgs_hdr_kern_gpupreagg_cuh));
-    crc = crc32_buf(crc, pgs_hdr_kern_common_cuh, strlen(pgs_hdr_kern_common_cuh));
-    crc = crc32_buf(crc, pgs_hdr_kern_mathlib_cuh, strlen(pgs_hdr_kern_mathlib_cuh));
-    crc = crc32_buf(crc, pgs_hdr_kern_numeric_cuh, strlen(pgs_hdr_kern_numeric_cuh));
-    if (extra_flags & DEVFUNC_NEEDS_TIMELIB)
-        crc = crc32_buf(crc, pgs_hdr_kern_timelib_cuh, strlen(pgs_hdr_kern_timelib_cuh));
-    if (extra_flags & DEVFUNC_NEEDS_TEXTLIB)
-        crc = crc32_buf(crc, pgs_hdr_kern_textlib_cuh, strlen(pgs_hdr_kern_textlib_cuh));
-    crc = crc32_buf(crc, pgs_hdr_pgstrom_kds_h, strlen(pgs_hdr_pgstrom_kds_h));
-    crc = crc32_buf(crc, pgs_hdr_kern_shared_h, strlen(pgs_hdr_kern_shared_h));
+    /* everything the binary depends on: the query's source and flags, the
+     * build options, the static device runtime (a new library build must not
+     * pick up stale binaries) and the compiler itself */
+    {
+        Sha256 sha;
+        int nv_major = 0, nv_minor = 0;
+        nvrtcVersion(&nv_major, &nv_minor);
+        sha.field(kern_source, strlen(kern_source));
+        sha.field(&extra_flags, sizeof(extra_flags));
+        sha.field(options.data(), options.size());
+        sha.field(&nv_major, sizeof(nv_major));
+        sha.field(&nv_minor, sizeof(nv_minor));
+        sha.field(pgs_hdr_kern_gpupreagg_cuh, strlen(pgs_hdr_kern_gpupreagg_cuh));
+        sha.field(pgs_hdr_kern_common_cuh, strlen(pgs_hdr_kern_common_cuh));
+        sha.field(pgs_hdr_kern_mathlib_cuh, strlen(pgs_hdr_kern_mathlib_cuh));
+        sha.field(pgs_hdr_kern_numeric_cuh, strlen(pgs_hdr_kern_numeric_cuh));
+        sha.field(pgs_hdr_kern_timelib_cuh, strlen(pgs_hdr_kern_timelib_cuh));
+        sha.field(pgs_hdr_kern_textlib_cuh, strlen(pgs_hdr_kern_textlib_cuh));
+        sha.field(pgs_hdr_pgstrom_kds_h, strlen(pgs_hdr_pgstrom_kds_h));
+        sha.field(pgs_hdr_kern_shared_h, strlen(pgs_hdr_kern_shared_h));
+        key = sha.hex();
+    }
 
     std::lock_guard<std::mutex> g(program_lock);
-    auto it = program_cache.find(crc);
-    if (it != program_cache.end() && it->second->source == kern_source &&
-        it->second->extra_flags == extra_flags && it->second->options == options)
+    auto it = program_cache.find(key);
+    if (it != program_cache.end())
     {
         it->second->refcnt++;
         *program = it->second;
         return StromError_Success;
     }
     pgs_program *prog = new pgs_program;
-    prog->crc = crc;
+    prog->key = key;
     prog->source = kern_source;
     prog->extra_flags = extra_flags;
     prog->options = options;
@@ -248,25 +422,9 @@ pgs_program_build(const char *kern_source, int extra_flags,
 
     /* on-disk cache (in-tree by default so that pre-built programs travel) */
     std::string dir = cubin_cache_dir();
-    char fname[64];
-    snprintf(fname, sizeof(fname), "/%08x.cubin", crc);
-    std::string path = dir + fname;
-    FILE *fp = fopen(path.c_str(), "rb");
-    if (fp)
-    {
-        fseek(fp, 0, SEEK_END);
-        long sz = ftell(fp);
-        fseek(fp, 0, SEEK_SET);
-        if (sz > 0)
-        {
-            prog->cubin.resize(sz);
-            if (fread(prog->cubin.data(), 1, sz, fp) == (size_t)sz)
-                prog->from_disk = true;
-            else
-                prog->cubin.clear();
-        }
-        fclose(fp);
-    }
+    std::string path = dir.empty() ? "" : dir + "/" + key.substr(0, 40) + ".cubin";
+    if (!path.empty() && cubin_file_read(path, key, prog->cubin))
+        prog->from_disk = true;
     if (prog->cubin.empty())
     {
         int rc = nvrtc_build(prog);
@@ -278,25 +436,15 @@ pgs_program_build(const char *kern_source, int extra_flags,
             delete prog;
             return rc;
         }
-        mkdir(dir.c_str(), 0755);
-        std::string tmp = path + ".tmp" + std::to_string((long)getpid());
-        fp = fopen(tmp.c_str(), "wb");
-        if (fp)
-        {
-            bool ok = fwrite(prog->cubin.data(), 1, prog->cubin.size(), fp) == prog->cubin.size();
-            fclose(fp);
-            if (ok)
-                rename(tmp.c_str(), path.c_str());
-            else
-                unlink(tmp.c_str());
-        }
+        if (!path.empty())
+            cubin_file_write(path, key, prog->cubin);
     }
     if (build_log && !prog->build_log.empty())
     {
         log_buf = prog->build_log;
         *build_log = log_buf.c_str();
     }
-    program_cache[crc] = prog;
+    program_cache[key] = prog;
     *program = prog;
     return StromError_Success;
 }
@@ -347,9 +495,7 @@ pgs_program_info_json(void)
     for (auto &kv : program_cache)
     {
         pgs::JsonPtr o = pgs::Json::object();
-        char key[16];
-        snprintf(key, sizeof(key), "%08x", kv.first);
-        o->set("key", key);
+        o->set("key", kv.first.substr(0, 16));
         o->set("refcnt", kv.second->refcnt);
         o->set("length", (long long)kv.second->source.size());
         o->set("cubin_length", (long long)kv.second->cubin.size());

@@ -144,41 +144,3 @@ def make_chunk(name, row0, n, **kw):
     cols = w["columns"](row0, n, **kw)
     coltypes = [t for _, t in w["table"].columns]
     return gp.DataStore(coltypes, cols, nrows=n), cols
-
-
-def prebuild_programs():
-    """NVRTC-compiles the device programs of the workloads above for sm_100a
-    into the in-tree cubin cache (no GPU needed)."""
-    from . import gpupreagg as gp
-    gucs = {"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on"}
-    for name, w in WORKLOADS.items():
-        plan = gp.Plan(w["plan"](), gucs=gucs)
-        assert plan.num_gpupreagg == 1, (name, plan.reject_reason)
-        prog = plan.build_program()
-        plan.lib.pgs_program_release(prog)
-        plan.free()
-
-
-def smoke(nrows=400_000):
-    """One small invocation of the hot path on cuda:0 for the no-group and the
-    GROUP BY kernel, checked against the oracle (numpy restatement)."""
-    from . import gpupreagg as gp
-    from oracle import bench_oracle
-    gucs = {"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on"}
-    gp.cuda_init()
-    for name, kw in (("nogrp_agg", {}), ("where_agg", {})):
-        w = WORKLOADS[name]
-        plan = gp.Plan(w["plan"](), gucs=gucs)
-        sess = gp.Session(plan)
-        ds, cols = make_chunk(name, 0, nrows, **kw)
-        t = sess.submit(ds)
-        status = sess.wait(t)
-        assert status == 0, status
-        rows = sess.finish()
-        node = plan.tree()["lefttree"]
-        ngroups = bench_oracle.assert_partial_equal_node(plan.describe(), node, rows, cols)
-        print("smoke %s: %d rows -> %d partial rows (%d groups), %d kernel launches: OK"
-              % (name, nrows, len(rows), ngroups, sess.launch_count()))
-        sess.close()
-        ds.free()
-        plan.free()

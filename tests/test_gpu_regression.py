@@ -2,9 +2,12 @@
 the product path, compared with the goldens PostgreSQL's CPU executor
 produced (expected/*.out -> tests/golden/*.json).
 
-Integer / count / numeric cells must be identical text; float8 within the
-1e-12 relative tolerance of the north star (the suite prints 12 significant
-digits); float4 to its 3 printed digits.  Statements the planner does not
+Integer / count / numeric cells must be identical text; float8 sum / avg / min
+/ max within the 1e-12 relative tolerance of the north star (the suite prints
+12 significant digits); float4 to its 3 printed digits; variance / stddev /
+corr / covar by the float rule of harness.cells_match: partial sums against
+PostgreSQL's left-to-right sums at 1e-12, the final inside the interval that
+tolerance allows.  Statements the planner does not
 offload (the reference does not either, see tests/test_planner_explain.py)
 are skipped here: PostgreSQL runs them itself.
 """
@@ -43,10 +46,10 @@ def _check(name, chunk_rows=None, every=1, fmt="column"):
         if len(r["rows"]) != len(s["rows"]):
             bad.append((s["sql"], "row count", len(r["rows"]), len(s["rows"])))
             continue
-        for got, exp in zip(r["rows"], s["rows"]):
-            for g, e, t in zip(got, exp, r["types"]):
-                if not harness.cells_match(g, e, t):
-                    bad.append((s["sql"], t, got, exp))
+        for got, exp, bnd in zip(r["rows"], s["rows"], r["bounds"]):
+            for g, e, t, b in zip(got, exp, r["types"], bnd):
+                if not harness.cells_match(g, e, t, b):
+                    bad.append((s["sql"], t, got, exp, b))
                     break
             else:
                 continue
@@ -146,6 +149,6 @@ def test_numeric_on_device(cuda, monkeypatch):
             assert r["offloaded"], sql
             assert r["nrecheck"] == 0, (sql, r["nrecheck"])
             assert len(r["rows"]) == len(exp), sql
-            for got, want in zip(r["rows"], exp):
-                for g, e, t in zip(got, want, r["types"]):
-                    assert harness.cells_match(g, e, t), (sql, fmt, got, want)
+            for got, want, bnd in zip(r["rows"], exp, r["bounds"]):
+                for g, e, t, b in zip(got, want, r["types"], bnd):
+                    assert harness.cells_match(g, e, t, b), (sql, fmt, got, want, b)

@@ -73,7 +73,7 @@ def _worker(rank, world, port, chunk_rows, out_path):
             covered = sorted(s for sh, _ in gathered for s in sh)
             assert covered == multigpu.shard_rows(len(tuples), chunk_rows, 0, 1)
             allrows = [r for _, part in gathered for r in part]
-            out, types = harness.final_aggregate(desc, allrows, q)
+            out, types, _ = harness.final_aggregate(desc, allrows, q)
             results[sql] = out
         plan.free()
     if rank == 0:

@@ -112,7 +112,7 @@ def test_any_outer_plan_feeds_gpupreagg(lib):
             for row0 in range(0, len(tuples), 997):
                 g, order = partial.partial_rows(node, tuples[row0:row0 + 997], len(table.columns))
                 prs.extend(tuple(g[k]) for k in order)
-            got, types = harness.final_aggregate(desc, prs, q)
+            got, types, _ = harness.final_aggregate(desc, prs, q)
             exp = golden[" ".join(sql.split())]
             assert len(got) == len(exp)
             for gr, er in zip(got, exp):

@@ -2,16 +2,15 @@
 every sum leaves int8 after a handful of rows: avg(int8) must equal
 PostgreSQL's numeric results digit for digit (128-bit cells on the device,
 sums beyond int8 emitted as several partial rows, merged by the numeric
-accumulator), with and without GROUP BY, on column and heap chunks.  Written
-after the last GPU run of round 1: xfail(strict=False) until its first run."""
+accumulator), with and without GROUP BY, on column and heap chunks."""
 import pytest
 
 import harness
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run pending")]
+pytestmark = pytest.mark.gpu
 
 
-def test_int8_sums_beyond_int8(monkeypatch):
+def test_int8_sums_beyond_int8(cuda, monkeypatch):
     from oracle import pg_agg, pg_fixture
 
     orig = pg_fixture.table
@@ -40,6 +39,6 @@ def test_int8_sums_beyond_int8(monkeypatch):
             assert r["offloaded"] and r["error"] is None, (sql, r)
             assert r["nrecheck"] == 0, (sql, r["nrecheck"])
             assert len(r["rows"]) == len(exp), sql
-            for got, want in zip(r["rows"], exp):
-                for g, e, t in zip(got, want, r["types"]):
-                    assert harness.cells_match(g, e, t), (sql, fmt, got, want)
+            for got, want, bnd in zip(r["rows"], exp, r["bounds"]):
+                for g, e, t, b in zip(got, want, r["types"], bnd):
+                    assert harness.cells_match(g, e, t, b), (sql, fmt, got, want)

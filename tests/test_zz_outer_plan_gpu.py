@@ -2,8 +2,7 @@
 gpupreagg_load_next_outer :2418-2505): the plan keeps the HashJoin below the
 Agg, its tuples arrive one by one in ROW_FLAT chunks, the kernel has no qual.
 Results = the reference's where_agg goldens (the join delivers the rows the
-scan's filter lets through).  Written after the last GPU run of round 1:
-xfail(strict=False) until its first run."""
+scan's filter lets through)."""
 import json
 import os
 
@@ -12,7 +11,7 @@ import pytest
 import harness
 from test_planner_explain import _over_join
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run pending")]
+pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 STATEMENTS = [
@@ -24,7 +23,7 @@ STATEMENTS = [
 
 
 @pytest.mark.parametrize("fmt", ["flat", "row", "column"])
-def test_agg_over_join(fmt):
+def test_agg_over_join(cuda, fmt):
     with open(os.path.join(HERE, "golden", "where_agg.json")) as f:
         golden = {" ".join(s["sql"].split()): s["rows"] for s in json.load(f)}
     for sql in STATEMENTS:
@@ -34,6 +33,6 @@ def test_agg_over_join(fmt):
         assert res["offloaded"] and res["error"] is None, res
         exp = golden[" ".join(sql.split())]
         assert len(res["rows"]) == len(exp), (sql, res["rows"], exp)
-        for gr, er in zip(res["rows"], exp):
-            assert all(a == b or harness.cells_match(a, b, t)
-                       for a, b, t in zip(gr, er, res["types"])), (sql, gr, er)
+        for gr, er, bnd in zip(res["rows"], exp, res["bounds"]):
+            assert all(a == b or harness.cells_match(a, b, t, bd)
+                       for a, b, t, bd in zip(gr, er, res["types"], bnd)), (sql, gr, er)

@@ -8,10 +8,7 @@ infinite) is re-checked on the host (kern_gpupreagg.cuh, PGS_PSUM_*_LIMIT).
 
 The merge rules these kernels apply are checked on the CPU by
 tests/test_codegen_hostsim.py; what only a GPU can show is that the kernels
-route such rows to them.  Written after this round's GPU time was used up:
-not yet run on a device, hence xfail(strict=False) - a wrong expectation here
-must not turn the suite red, an XPASS is the normal outcome.  Remove the
-marker after the first GPU run."""
+route such rows to them."""
 import math
 import random
 import struct
@@ -23,8 +20,7 @@ from oracle import bench_oracle, partial
 from pg_strom_b200 import gpupreagg as gp
 from pg_strom_b200 import pgplan as P
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="new this round, not yet run on a GPU")]
+pytestmark = pytest.mark.gpu
 GUCS = {"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on"}
 TBL = P.Table("sf", [("k", "int4"), ("x", "float8"), ("y", "float4"), ("f", "int4")])
 LIMIT8 = 2.0 ** 960

@@ -4,11 +4,7 @@ NVLink) exercised on ONE device: two sessions of the same
 query scan different shards, the second session's state is exported as
 records and imported into the first, which then returns the partial rows of
 both shards - exactly what rank 0 does with the records of rank 1.  Also the
-admin JSON views and abort.
-
-Written after this round's GPU time was used up (the multi-rank path itself
-was checked by bench.py --gpus N earlier in the round): not yet run on a
-device, hence xfail(strict=False); remove the marker after the first run."""
+admin JSON views and abort."""
 import ctypes as C
 import json
 
@@ -19,8 +15,7 @@ from oracle import bench_oracle
 from pg_strom_b200 import gpupreagg as gp
 from pg_strom_b200 import workloads as W
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="new this round, not yet run on a GPU")]
+pytestmark = pytest.mark.gpu
 GUCS = {"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on"}
 
 
