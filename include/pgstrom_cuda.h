@@ -250,6 +250,35 @@ void        pgs_nccl_comm_destroy(void *comm);
  * every rank of the communicator calls it.  comm is an ncclComm_t. */
 int         pgs_preagg_merge_nccl(pgs_session *session, void *nccl_comm,
                                   int rank, int nranks, int root);
+/* The same merge without a collective library in the data path, for states
+ * of at most 64K groups (and the single record of a no-group aggregation):
+ * the other ranks write their state records straight into an exchange area
+ * in the root's HBM over NVLink peer memory and raise a flag, the root's
+ * merge kernel waits for the flags on the device.  No rendezvous, no host
+ * synchronisation: a rank pushes as soon as its own scan is done.
+ *   setup  : every rank, once; the root's ipc_handle_64 (cudaIpcMemHandle_t)
+ *            is carried to the other ranks by the launcher like the NCCL id
+ *   attach : every other rank maps the root's area (another process: by
+ *            handle; the same process: by session)
+ *   merge  : every rank, once per scan, before pgs_preagg_finish()
+ * A rank whose state does not fit pushes nothing and keeps its groups: its
+ * own flush returns them and PostgreSQL's final Agg merges the partial rows,
+ * as the reference does for every chunk (gpupreagg.c:2169-2186). */
+int         pgs_preagg_peer_setup(pgs_session *session, int rank, int nranks,
+                                  int root, void *ipc_handle_64);
+int         pgs_preagg_peer_attach(pgs_session *session,
+                                   const void *root_ipc_handle_64);
+int         pgs_preagg_peer_attach_session(pgs_session *session,
+                                           pgs_session *root_session);
+int         pgs_preagg_merge_peer(pgs_session *session);
+/* Large GROUP BY states (millions of groups) are not gathered on one rank:
+ * the groups are partitioned over the ranks by key hash (rank r receives
+ * the records of its groups from every rank over NCCL send/recv and merges
+ * them), after which every rank flushes its own, disjoint share of the
+ * groups.  Collective.  pgs_preagg_merge_nccl() takes this path by itself
+ * when the state is too large for its gather. */
+int         pgs_preagg_merge_exchange(pgs_session *session, void *nccl_comm,
+                                      int rank, int nranks);
 /* raw state export / import for callers that move it themselves */
 int         pgs_preagg_state_export(pgs_session *session, void *device_buf,
                                     size_t buflen, uint32_t *nrecords,
@@ -297,6 +326,18 @@ int         gpupreagg_exec(pgs_gpupreagg_state *state, Datum *values, char *isnu
 int64_t     gpupreagg_recheck_rows(pgs_gpupreagg_state *state,
                                    uint32_t *chunk_seq, uint32_t *rows,
                                    int64_t max_rows);
+/* Ownership of a chunk with re-check rows: its release callback is NOT
+ * called when the device is done with it - the host still has to walk the
+ * rows (the reference keeps the pgstrom_data_store in curr_recheck until
+ * gpupreagg_next_tuple_fallback has gone through it, gpupreagg.c:2507-2607,
+ * 2746).  gpupreagg_recheck_chunk() returns the retained chunk (and its row
+ * map) of a sequence number gpupreagg_recheck_rows() reported,
+ * gpupreagg_recheck_done() hands it back through the release callback;
+ * ReScan and EndCustomPlan release whatever is still held. */
+const kern_data_store *gpupreagg_recheck_chunk(pgs_gpupreagg_state *state,
+                                               uint32_t chunk_seq,
+                                               const kern_row_map **krowmap);
+int         gpupreagg_recheck_done(pgs_gpupreagg_state *state, uint32_t chunk_seq);
 /* EndCustomPlan: gpupreagg_end (gpupreagg.c:2778); returns the NOTICE text
  * "GpuPreAgg: %u chunks were re-checked by CPU" or NULL */
 const char *gpupreagg_end(pgs_gpupreagg_state *state);

@@ -74,25 +74,25 @@ typedef cl_char     cl_bool;
 #endif
 
 /* ---- error codes (opencl_common.h:108-123) ---- */
-#define StromError_Success              0   /* OK */
-#define StromError_RowFiltered          1   /* Row-clause was false */
-#define StromError_CpuReCheck           2   /* To be re-checked by CPU */
+#define StromError_Success              0   /* nothing to report */
+#define StromError_RowFiltered          1   /* the qual rejected the row */
+#define StromError_CpuReCheck           2   /* the host has to evaluate this itself */
 #define StromError_ServerNotReady       100 /* device layer is not ready */
-#define StromError_BadRequestMessage    101 /* Bad request message */
+#define StromError_BadRequestMessage    101 /* malformed request / arguments */
 #define StromError_OpenCLInternal       102 /* internal error of the device runtime */
 #define StromError_OutOfSharedMemory    105 /* out of pinned host memory */
 #define StromError_OutOfMemory          106 /* out of host memory */
-#define StromError_DataStoreCorruption  300 /* Row/Column Store Corrupted */
-#define StromError_DataStoreNoSpace     301 /* No Space in Row/Column Store */
-#define StromError_DataStoreOutOfRange  302 /* Out of range in Data Store */
-#define StromError_DataStoreReCheck     303 /* Row/Column Store be rechecked */
-#define StromError_SanityCheckViolation 999 /* SanityCheckViolation */
+#define StromError_DataStoreCorruption  300 /* a chunk fails its consistency checks */
+#define StromError_DataStoreNoSpace     301 /* destination store / table is full */
+#define StromError_DataStoreOutOfRange  302 /* row or column index beyond the chunk */
+#define StromError_DataStoreReCheck     303 /* whole chunk goes back to the host */
+#define StromError_SanityCheckViolation 999 /* an internal invariant does not hold */
 /* new in the CUDA layer: device program build failure (the reference reports
  * CL_BUILD_PROGRAM_FAILURE = -11 here, gpupreagg.c:2751-2764) */
 #define StromError_ProgramBuildFailure  (-11)
 #define StromError_CudaInternal         (-9999)
 
-/* significant error; that abort transaction on the host code */
+/* codes the host must turn into an ERROR (everything but 0, 1, 2) */
 #define StromErrorIsSignificant(errcode)    ((errcode) >= 100 || (errcode) < 0)
 
 /* ---- alignment (opencl_common.h:272-274) ---- */
@@ -117,29 +117,24 @@ typedef cl_char     cl_bool;
 #define KDS_COLUMN_ROW_QUANTUM  128
 
 typedef struct {
-    /* true, if column is held by value. Elsewhere, a reference */
-    cl_char         attbyval;
-    /* alignment; 1,2,4 or 8, not characters in pg_attribute */
-    cl_char         attalign;
-    /* length of attribute */
-    cl_short        attlen;
-    /* attribute number */
-    cl_short        attnum;
-    /* offset of attribute location, if deterministic */
-    cl_short        attcacheoff;
+    cl_char         attbyval;   /* != 0: the datum is the value; 0: it points to it */
+    cl_char         attalign;   /* in bytes (1, 2, 4, 8) - not pg_attribute's letter */
+    cl_short        attlen;     /* bytes, or < 0 for varlena as in pg_attribute */
+    cl_short        attnum;     /* 1-based column number of the source relation */
+    cl_short        attcacheoff;/* fixed offset inside a NULL-free tuple, or -1 */
 } kern_colmeta;
 
 typedef union {
     struct {
-        cl_ushort   blk_index;      /* if ROW format */
-        cl_ushort   item_offset;    /* if ROW format */
+        cl_ushort   blk_index;      /* KDS_FORMAT_ROW: which page ... */
+        cl_ushort   item_offset;    /* ... and where in it the tuple starts */
     };
-    cl_uint         htup_offset;    /* if FLAT_ROW format */
+    cl_uint         htup_offset;    /* KDS_FORMAT_ROW_FLAT: from the head of the chunk */
 } kern_rowitem;
 
 typedef struct {
-    cl_int          buffer;         /* PostgreSQL Buffer id on the host */
-    hostptr_t       page;           /* host address of the page */
+    cl_int          buffer;         /* shared-buffer id the backend pinned */
+    hostptr_t       page;           /* where that page lives in host memory */
 } kern_blkitem;
 
 #define KDS_FORMAT_ROW          1
@@ -148,26 +143,26 @@ typedef struct {
 #define KDS_FORMAT_COLUMN       4   /* new: see the head of this file */
 
 typedef struct {
-    hostptr_t       hostptr;    /* address of kds on the host */
-    cl_uint         length;     /* length of this data-store */
-    cl_uint         usage;      /* usage of this data-store */
-    cl_uint         ncols;      /* number of columns in this store */
-    cl_uint         nitems;     /* number of rows in this store */
-    cl_uint         nrooms;     /* number of available rows in this store */
-    cl_uint         nblocks;    /* number of blocks in this store */
-    cl_uint         maxblocks;  /* max available blocks in this store */
-    cl_char         format;     /* one of KDS_FORMAT_* above */
-    cl_char         tdhasoid;   /* copy of TupleDesc.tdhasoid */
-    cl_uint         tdtypeid;   /* copy of TupleDesc.tdtypeid */
-    cl_int          tdtypmod;   /* copy of TupleDesc.tdtypmod */
-    kern_colmeta    colmeta[FLEXIBLE_ARRAY_MEMBER]; /* metadata of columns */
+    hostptr_t       hostptr;    /* the chunk's own host address (for the way back) */
+    cl_uint         length;     /* bytes, head included */
+    cl_uint         usage;      /* bytes taken so far (ROW_FLAT grows from the tail) */
+    cl_uint         ncols;      /* entries of colmeta[] */
+    cl_uint         nitems;     /* rows present */
+    cl_uint         nrooms;     /* rows the chunk was sized for */
+    cl_uint         nblocks;    /* pages present (KDS_FORMAT_ROW) */
+    cl_uint         maxblocks;  /* pages the chunk was sized for */
+    cl_char         format;     /* KDS_FORMAT_* */
+    cl_char         tdhasoid;   /* the three TupleDesc fields a heap tuple's */
+    cl_uint         tdtypeid;   /*   header depends on, taken over from the */
+    cl_int          tdtypmod;   /*   relation's descriptor */
+    kern_colmeta    colmeta[FLEXIBLE_ARRAY_MEMBER];
 } kern_data_store;
 
 #define KERN_DATA_STORE_HEAD_LENGTH(ncols)                      \
     STROMALIGN(offsetof(kern_data_store, colmeta) +             \
                sizeof(kern_colmeta) * (ncols))
 
-/* access macro for row-format */
+/* KDS_FORMAT_ROW: block items, row items, then the pages on a BLCKSZ boundary */
 #define KERN_DATA_STORE_BLKITEM(kds,blk_index)                  \
     (((kern_blkitem *)                                          \
       ((char *)(kds) + KERN_DATA_STORE_HEAD_LENGTH((kds)->ncols))) + (blk_index))
@@ -183,7 +178,7 @@ typedef struct {
                 STROMALIGN(sizeof(kern_rowitem) * (kds)->nitems)) \
       + (cl_ulong)BLCKSZ * (blk_index)))
 
-/* access macro for tuple-slot format */
+/* KDS_FORMAT_TUPSLOT: per row ncols Datums followed by ncols isnull bytes */
 #define KERN_DATA_STORE_SLOT_STRIDE(ncols)                      \
     LONGALIGN((sizeof(Datum) + sizeof(cl_char)) * (ncols))
 #define KERN_DATA_STORE_VALUES(kds,row_index)                   \
@@ -208,22 +203,22 @@ typedef struct {
 
 /* ---- kern_parambuf (opencl_common.h:443-457) ---- */
 typedef struct {
-    cl_uint     length;     /* total length of parambuf */
-    cl_uint     nparams;    /* number of parameters */
-    cl_uint     poffset[FLEXIBLE_ARRAY_MEMBER]; /* offset of params */
+    cl_uint     length;     /* bytes, this head included */
+    cl_uint     nparams;    /* entries of poffset[] */
+    cl_uint     poffset[FLEXIBLE_ARRAY_MEMBER]; /* where each value starts; 0 = NULL */
 } kern_parambuf;
 
 /* ---- kern_row_map (opencl_common.h:483-486) ---- */
 typedef struct {
-    cl_int      nvalids;    /* # of valid rows. -1 means all visible */
+    cl_int      nvalids;    /* entries of rindex[]; < 0: every row of the chunk counts */
     cl_int      rindex[FLEXIBLE_ARRAY_MEMBER];
 } kern_row_map;
 
 /* ---- kern_gpupreagg (opencl_gpupreagg.h:67-106) ---- */
 typedef struct {
-    cl_int          status;     /* result of kernel execution */
+    cl_int          status;     /* StromError_* the kernels leave behind */
     cl_int          sortbuf_len;/* unused by the hash based kernels; kept for layout */
-    char            __padding[8];   /* align to 128bits */
+    char            __padding[8];   /* kparams starts on a 16-byte boundary */
     kern_parambuf   kparams;
     /* kern_row_map follows at STROMALIGN(offsetof(kparams) + kparams.length) */
 } kern_gpupreagg;

@@ -118,6 +118,11 @@ PROTOTYPES = {
                                           C.POINTER(C.c_void_p)]),
     "pgs_nccl_comm_destroy": (None, [C.c_void_p]),
     "pgs_preagg_merge_nccl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "pgs_preagg_peer_setup": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "pgs_preagg_peer_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pgs_preagg_peer_attach_session": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pgs_preagg_merge_peer": (C.c_int, [C.c_void_p]),
+    "pgs_preagg_merge_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "pgs_preagg_state_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t,
                                           C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]),
     "pgs_preagg_state_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
@@ -136,6 +141,8 @@ PROTOTYPES = {
     "gpupreagg_exec": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p]),
     "gpupreagg_recheck_rows": (C.c_int64, [C.c_void_p, C.POINTER(C.c_uint32),
                                            C.POINTER(C.c_uint32), C.c_int64]),
+    "gpupreagg_recheck_chunk": (C.c_void_p, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "gpupreagg_recheck_done": (C.c_int, [C.c_void_p, C.c_uint32]),
     "gpupreagg_end": (C.c_char_p, [C.c_void_p]),
     "gpupreagg_rescan": (C.c_int, [C.c_void_p]),
     "gpupreagg_explain": (C.c_char_p, [C.c_void_p, C.c_int, C.c_int]),

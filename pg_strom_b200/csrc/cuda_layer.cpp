@@ -721,6 +721,7 @@ struct ChunkSlot
     cudaEvent_t ev_done = NULL;
     cudaEvent_t ev_k0 = NULL, ev_k1 = NULL; /* around the main kernel (perfmon) */
     bool        timed = false;
+    uint64_t    table_epoch = 0;    /* num_table_grown when the chunk was launched */
     pgs_ticket  ticket = -1;
     uint32_t    nitems = 0;
     bool        busy = false;
@@ -733,8 +734,9 @@ struct pgs_session
     pgs_program    *program = NULL;
     cudaLibrary_t   library = NULL;
     cudaKernel_t    k_main = NULL, k_rowmap = NULL, k_heap = NULL, k_partagg = NULL,
-                    k_init = NULL, k_flush = NULL,
+                    k_init = NULL, k_flush = NULL, k_rehash = NULL,
                     k_export = NULL, k_import = NULL, k_import_blocks = NULL,
+                    k_export_parts = NULL, k_peer_push = NULL, k_peer_pull = NULL,
                     k_describe = NULL;
     pgs_kern_desc   desc;
     pgs_gstate      gs;
@@ -770,9 +772,31 @@ struct pgs_session
     char           *h_result_head = NULL;   /* pinned: header + status read-back */
     char           *d_xchg = NULL;          /* NCCL merge: send block + receive blocks */
     size_t          d_xchg_cap = 0;
+    char           *d_xrecv = NULL;         /* partitioned exchange: records received */
+    size_t          d_xrecv_cap = 0;
+    int             ovf_which = 0;          /* which of the two overflow counters is live */
+    std::vector<void *> graveyard;          /* tables replaced by larger ones: freed once
+                                             * nothing in flight can still read them */
+    uint64_t        num_table_grown = 0;
+    /* merge of small states over NVLink peer memory (pgs_preagg_peer_*) */
+    cl_ulong       *peer_area = NULL;       /* this rank's exchange area */
+    size_t          peer_area_bytes = 0;
+    cl_ulong       *peer_root_area = NULL;  /* the root's, mapped over NVLink (or peer_area) */
+    bool            peer_mapped = false;
+    int             peer_rank = -1, peer_nranks = 0, peer_root = 0;
+    cl_uint         peer_cap = 0;
+    cl_ulong        peer_epoch = 0;
+    /* merge trace (perfmon): CUDA events around the phases of the last merges */
+    cudaEvent_t     ev_m[4] = {NULL, NULL, NULL, NULL};
+    double          merge_ms[3] = {0, 0, 0};
+    uint64_t        merge_count = 0;
+    bool            merge_pending = false;  /* d_kg_misc carries the status of a merge */
     std::string     perfmon_buf;
     bool            aborted = false;
 };
+
+static int launch_kernel(pgs_session *s, cudaKernel_t k, int grid, int block,
+                         size_t smem, void **args);
 
 static int
 session_alloc_state(pgs_session *s)
@@ -785,10 +809,20 @@ session_alloc_state(pgs_session *s)
     CUDA_CHECK(cudaMalloc(&s->d_scratch, sz_small + 8 * W * (1 + max_ctas)));
     CUDA_CHECK(cudaMemset(s->d_scratch, 0, sz_small + 8 * W * (1 + max_ctas)));
     base = (char *)s->d_scratch;
+    /* words of the scratch page: 0 ticket | 8 ngroups | 16 rows scanned |
+     * 24 rows filtered | 32 table occupancy | 40, 48 overflow counters |
+     * 64 export counter | 80 peer push / pull counters | 128.. debug |
+     * 512.. exchange counts */
     s->gs.ng_ticket = (cl_uint *)(base + 0);
     s->gs.gh_ngroups = (cl_uint *)(base + 8);
     s->gs.nrows_scanned = (cl_ulong *)(base + 16);
     s->gs.nrows_filtered = (cl_ulong *)(base + 24);
+    s->gs.gh_nused = (cl_uint *)(base + 32);
+    s->gs.ovf_count = (cl_uint *)(base + 40);
+    s->gs.ovf_recs = NULL;
+    s->gs.ovf_cap = 0;
+    s->gs.ovf_pad = 0;
+    s->ovf_which = 0;
     s->gs.ng_state = (cl_ulong *)(base + sz_small);
     s->gs.ng_partial = s->gs.ng_state + W;
     s->gs.gh_slots = NULL;
@@ -828,7 +862,10 @@ session_alloc_state(pgs_session *s)
         if (nparts < 0x7fffffffULL && cap < 0x7fffffffULL &&
             rec_bytes + img_bytes + 8 * nparts < free_b / 2)
         {
-            CUDA_CHECK(cudaMalloc((void **)&s->gs.part_cursor, 4 * nparts));
+            /* cursors 32 bytes apart: see PGS_PART_CURSOR */
+            const char *ecs = getenv("PGSTROM_CURSOR_SHIFT");
+            s->gs.part_pad = (cl_uint)(ecs ? std::min(5, std::max(0, atoi(ecs))) : 3);
+            CUDA_CHECK(cudaMalloc((void **)&s->gs.part_cursor, (4 * nparts) << s->gs.part_pad));
             CUDA_CHECK(cudaMalloc((void **)&s->gs.part_nused, 4 * nparts));
             CUDA_CHECK(cudaMalloc((void **)&s->gs.part_recs, rec_bytes));
             CUDA_CHECK(cudaMalloc((void **)&s->gs.part_images, img_bytes));
@@ -847,10 +884,19 @@ session_alloc_state(pgs_session *s)
     }
     if (s->desc.num_keys > 0)
     {
-        /* with partitions the global table only takes what they refuse */
-        double want = s->config.num_groups * (s->gs.part_nparts ? 0.125 : 2.0);
+        /* with partitions the global table only takes what they refuse.  The
+         * planner's number is an estimate: the table is sized for it, and
+         * for what the CTA-local tables can spill at the end of one launch,
+         * and grows when the scan proves the estimate wrong
+         * (session_grow_table) */
+        double want = s->config.num_groups * 2.0;
+        if (s->gs.part_nparts)
+            want = std::max(s->config.num_groups * 0.125, std::min(want, 1048576.0));
+        size_t spill = (size_t)s->grid_main * (s->sh_nslots - s->sh_nslots / 4);
         size_t nslots = 1024;
         size_t free_b = 0, total_b = 0;
+        if (want < 2.0 * (double)(s->sh_nslots - s->sh_nslots / 4))
+            want = 2.0 * (double)(s->sh_nslots - s->sh_nslots / 4);
         while ((double)nslots < want && nslots < (1ULL << 31))
             nslots <<= 1;
         cudaMemGetInfo(&free_b, &total_b);
@@ -859,8 +905,96 @@ session_alloc_state(pgs_session *s)
         CUDA_CHECK(cudaMalloc((void **)&s->gs.gh_slots, nslots * (size_t)s->desc.slot_stride_bytes));
         s->gs.gh_nslots = (cl_uint)nslots;
         s->gs.gh_max_probe = (cl_uint)std::min<size_t>(nslots, 4096);
+        /* overflow log: what one launch can spill, for every chunk in flight */
+        size_t ovf_cap = std::max<size_t>(65536, spill * 2);
+        CUDA_CHECK(cudaMalloc((void **)&s->gs.ovf_recs, ovf_cap * (size_t)s->desc.slot_bytes));
+        s->gs.ovf_cap = (cl_uint)ovf_cap;
     }
     return StromError_Success;
+}
+
+/*
+ * The scan met more groups than the global table was sized for: allocate a
+ * larger table (and a fresh overflow log), move the groups over with one
+ * kernel, all stream ordered behind the chunks in flight - those were
+ * launched with the old pointers and finish before the move starts.  The old
+ * buffers are freed when the session next synchronises.  Failure to allocate
+ * is not an error: rows that find no room are re-checked by the host.
+ */
+static int
+session_grow_table(pgs_session *s, size_t min_slots)
+{
+    if (s->desc.num_keys == 0)
+        return StromError_Success;
+    size_t nslots = s->gs.gh_nslots;
+    while (nslots < min_slots && nslots < (1ULL << 31))
+        nslots <<= 1;
+    if (nslots <= s->gs.gh_nslots)
+        return StromError_Success;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    size_t bytes = nslots * (size_t)s->desc.slot_stride_bytes;
+    size_t log_bytes = (size_t)s->gs.ovf_cap * s->desc.slot_bytes;
+    if (bytes + log_bytes > free_b / 2)
+        return StromError_Success;
+    pgs_gstate to = s->gs;
+    if (cudaMalloc((void **)&to.gh_slots, bytes) != cudaSuccess ||
+        cudaMalloc((void **)&to.ovf_recs, log_bytes) != cudaSuccess)
+    {
+        cudaGetLastError();
+        if (to.gh_slots != s->gs.gh_slots)
+            cudaFree(to.gh_slots);
+        return StromError_Success;
+    }
+    to.gh_nslots = (cl_uint)nslots;
+    to.gh_max_probe = (cl_uint)std::min<size_t>(nslots, 4096);
+    s->ovf_which ^= 1;
+    to.ovf_count = (cl_uint *)((char *)s->d_scratch + 40 + 8 * s->ovf_which);
+    if (!s->d_kg_misc)
+        CUDA_CHECK(cudaMalloc((void **)&s->d_kg_misc, sizeof(kern_gpupreagg)));
+    /* an empty table: slots zeroed = EMPTY, cells get their identity from the
+     * init kernel run on a state that has only this table */
+    {
+        pgs_gstate only = to;
+        only.part_nparts = 0;
+        only.part_slots = 0;
+        /* (the init kernel also clears the counters it is given: hand it
+         * scratch words of its own - the live ones stay) */
+        only.ng_state = s->gs.ng_partial;       /* harmless scratch rows */
+        only.ng_ticket = (cl_uint *)((char *)s->d_scratch + 96);
+        only.gh_ngroups = (cl_uint *)((char *)s->d_scratch + 100);
+        only.gh_nused = (cl_uint *)((char *)s->d_scratch + 104);
+        void *args[] = { &only };
+        int grid = std::max(1, std::min<int>(s->num_sms * 8, (int)((nslots + 255) / 256)));
+        int rc = launch_kernel(s, s->k_init, grid, 256, 0, args);
+        if (rc != StromError_Success)
+            return rc;
+    }
+    CUDA_CHECK(cudaMemsetAsync(s->gs.gh_nused, 0, sizeof(cl_uint), s->s_exec));
+    CUDA_CHECK(cudaMemsetAsync(s->d_kg_misc, 0, sizeof(kern_gpupreagg), s->s_exec));
+    {
+        void *args[] = { &s->gs, &to, &s->d_kg_misc };
+        size_t n = (size_t)s->gs.gh_nslots + s->gs.ovf_cap;
+        int grid = std::max(1, std::min<int>(s->num_sms * 8, (int)((n + 255) / 256)));
+        int rc = launch_kernel(s, s->k_rehash, grid, 256, 0, args);
+        if (rc != StromError_Success)
+            return rc;
+    }
+    CUDA_CHECK(cudaMemsetAsync(s->gs.ovf_count, 0, sizeof(cl_uint), s->s_exec));
+    s->graveyard.push_back(s->gs.gh_slots);
+    s->graveyard.push_back(s->gs.ovf_recs);
+    s->gs = to;
+    s->num_table_grown++;
+    return StromError_Success;
+}
+
+static void
+session_bury(pgs_session *s)
+{
+    /* call only after the exec stream has been synchronised */
+    for (void *p : s->graveyard)
+        cudaFree(p);
+    s->graveyard.clear();
 }
 
 static int
@@ -943,6 +1077,10 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_import, s->library, "gpupreagg_import"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_import_blocks, s->library, "gpupreagg_import_blocks"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_describe, s->library, "gpupreagg_describe"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_rehash, s->library, "gpupreagg_rehash"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_export_parts, s->library, "gpupreagg_export_parts"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_peer_push, s->library, "gpupreagg_peer_push"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_peer_pull, s->library, "gpupreagg_peer_pull"));
     OPEN_CHECK(cudaStreamCreateWithFlags(&s->s_copy, cudaStreamNonBlocking));
     OPEN_CHECK(cudaStreamCreateWithFlags(&s->s_exec, cudaStreamNonBlocking));
     /* the parameter buffer also goes to the program's constant memory (the
@@ -1157,6 +1295,22 @@ slot_retire(pgs_session *s, ChunkSlot &sl)
     ChunkResult &res = s->results[sl.ticket];
     res.status = *sl.h_status;
     res.done = true;
+    if (s->desc.num_keys > 0 && sl.table_epoch == s->num_table_grown)
+    {
+        /* table occupancy and overflow log as the chunk left them (copied
+         * behind its status word): a table more than half full, or one that
+         * already turned states away, is replaced by a larger one before the
+         * next chunk is launched */
+        const uint32_t *w = (const uint32_t *)sl.h_status;
+        size_t nused = w[2];
+        size_t nlog = std::max(w[4], w[6]);
+        if (nlog > 0 || nused * 2 > (size_t)s->gs.gh_nslots)
+        {
+            int rc = session_grow_table(s, 4 * std::max<size_t>(nused + nlog, s->gs.gh_nslots));
+            if (rc != StromError_Success)
+                return rc;
+        }
+    }
     if (sl.timed)
     {
         float ms = 0;
@@ -1336,6 +1490,12 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
     }
     CUDA_CHECK(cudaMemcpyAsync(sl.h_status, sl.d_kgpreagg, sizeof(int32_t),
                                cudaMemcpyDeviceToHost, s->s_exec));
+    if (s->desc.num_keys > 0)
+    {
+        CUDA_CHECK(cudaMemcpyAsync(sl.h_status + 2, (char *)s->d_scratch + 32, 24,
+                                   cudaMemcpyDeviceToHost, s->s_exec));
+        sl.table_epoch = s->num_table_grown;
+    }
     CUDA_CHECK(cudaEventRecord(sl.ev_done, s->s_exec));
     s->num_dma_recv++;
     s->bytes_dma_recv += sizeof(int32_t);
@@ -1525,8 +1685,11 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     memcpy(s->h_result_head + 64, kds_dst, head);
     cudaError_t e = cudaMemcpyAsync(d_dst, s->h_result_head + 64, head,
                                     cudaMemcpyHostToDevice, s->s_exec);
-    if (e == cudaSuccess)
+    /* (a merge kernel before this flush left its status in the same word:
+     * the first error sticks) */
+    if (e == cudaSuccess && !s->merge_pending)
         e = cudaMemsetAsync(d_kg, 0, sizeof(kern_gpupreagg), s->s_exec);
+    s->merge_pending = false;
     if (e == cudaSuccess)
     {
         void *args[] = { &s->gs, &d_dst, &d_kg };
@@ -1548,6 +1711,7 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
         e = cudaStreamSynchronize(s->s_exec);
     if (e == cudaSuccess)
     {
+        session_bury(s);
         rc = drain(s);          /* chunk results; nothing left to wait for */
         if (rc != StromError_Success)
             return rc;
@@ -1654,6 +1818,13 @@ pgs_preagg_state_import(pgs_session *s, const void *device_buf, uint32_t nrecord
     if (!s->d_kg_misc)
         CUDA_CHECK(cudaMalloc((void **)&s->d_kg_misc, sizeof(kern_gpupreagg)));
     d_kg = s->d_kg_misc;
+    if (s->desc.num_keys > 0)
+    {
+        /* every record may be a group the table does not hold yet */
+        int grc = session_grow_table(s, (size_t)s->gs.gh_nslots + 2 * (size_t)nrecords);
+        if (grc != StromError_Success)
+            return grc;
+    }
     cudaError_t e = cudaMemsetAsync(d_kg, 0, sizeof(kern_gpupreagg), s->s_exec);
     int rc = StromError_Success;
     if (e == cudaSuccess)
@@ -1777,6 +1948,8 @@ pgs_nccl_comm_destroy(void *comm)
         nccl.comm_destroy(comm);
 }
 
+extern "C" int pgs_preagg_merge_exchange(pgs_session *s, void *nccl_comm, int rank, int nranks);
+
 extern "C" int
 pgs_preagg_merge_nccl(pgs_session *s, void *nccl_comm, int rank, int nranks, int root)
 {
@@ -1842,65 +2015,352 @@ pgs_preagg_merge_nccl(pgs_session *s, void *nccl_comm, int rank, int nranks, int
          * check it here only when the caller asked for strict merges */
         return StromError_Success;
     }
-    /* large states: 1. how many records does each rank hold? */
+    /* large states are not gathered on one rank: they are partitioned over
+     * the ranks (every rank then flushes its own, disjoint share) */
+    (void)root;
+    return pgs_preagg_merge_exchange(s, nccl_comm, rank, nranks);
+}
+
+/* ------------------------------------------------------------------
+ * Merge of small states over NVLink peer memory - no collective library in
+ * the data path (kern_gpupreagg.cuh: gpupreagg_peer_push / _pull).  Every
+ * rank allocates an exchange area; only the root's is used.  One process per
+ * GPU: the root's area travels as a CUDA IPC handle (the launcher carries its
+ * 64 bytes to the ranks, like the NCCL id); several sessions of one process
+ * attach by pointer.
+ * ------------------------------------------------------------------ */
+#define PGS_EXCHANGE_MAX_RANKS  16
+#define PGS_PEER_HEAD_WORDS     (16 + 16 * PGS_EXCHANGE_MAX_RANKS)
+
+extern "C" int
+pgs_preagg_peer_setup(pgs_session *s, int rank, int nranks, int root, void *ipc_handle_64)
+{
+    if (!s || nranks < 1 || nranks > PGS_EXCHANGE_MAX_RANKS || rank < 0 || rank >= nranks ||
+        root < 0 || root >= nranks)
+    {
+        set_error("pgs_preagg_peer_setup: bad arguments (at most %d ranks)", PGS_EXCHANGE_MAX_RANKS);
+        return StromError_BadRequestMessage;
+    }
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    if (s->peer_area)
+    {
+        set_error("pgs_preagg_peer_setup: the session already has an exchange area");
+        return StromError_BadRequestMessage;
+    }
+    size_t W = s->desc.slot_bytes / 8;
+    size_t cap = (s->desc.num_keys == 0 ? 1 : std::min<size_t>(s->gs.gh_nslots, 65536));
+    size_t words = PGS_PEER_HEAD_WORDS + 2 * (size_t)nranks * (1 + cap) * W;
+    CUDA_CHECK(cudaMalloc((void **)&s->peer_area, words * 8));
+    CUDA_CHECK(cudaMemset(s->peer_area, 0, words * 8));
+    s->peer_area_bytes = words * 8;
+    s->peer_rank = rank;
+    s->peer_nranks = nranks;
+    s->peer_root = root;
+    s->peer_cap = (cl_uint)cap;
+    s->peer_epoch = 0;
+    s->peer_root_area = (rank == root ? s->peer_area : NULL);
+    s->peer_mapped = false;
+    if (ipc_handle_64)
+    {
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+        CUDA_CHECK(cudaIpcGetMemHandle(&h, s->peer_area));
+        memcpy(ipc_handle_64, &h, 64);
+    }
+    for (int i = 0; i < 4; i++)
+        if (!s->ev_m[i])
+            CUDA_CHECK(cudaEventCreate(&s->ev_m[i]));
+    return StromError_Success;
+}
+
+extern "C" int
+pgs_preagg_peer_attach(pgs_session *s, const void *root_ipc_handle_64)
+{
+    if (!s || !s->peer_area || !root_ipc_handle_64)
+    {
+        set_error("pgs_preagg_peer_attach: pgs_preagg_peer_setup comes first");
+        return StromError_BadRequestMessage;
+    }
+    if (s->peer_rank == s->peer_root)
+        return StromError_Success;
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    cudaIpcMemHandle_t h;
+    void *p = NULL;
+    memcpy(&h, root_ipc_handle_64, 64);
+    CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_root_area = (cl_ulong *)p;
+    s->peer_mapped = true;
+    return StromError_Success;
+}
+
+extern "C" int
+pgs_preagg_peer_attach_session(pgs_session *s, pgs_session *root_session)
+{
+    if (!s || !root_session || !s->peer_area || !root_session->peer_area ||
+        root_session->peer_rank != root_session->peer_root ||
+        s->peer_nranks != root_session->peer_nranks || s->peer_cap != root_session->peer_cap)
+    {
+        set_error("pgs_preagg_peer_attach_session: the two sessions were not set up as ranks "
+                  "of one merge");
+        return StromError_BadRequestMessage;
+    }
+    if (s == root_session)
+        return StromError_Success;
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    if (s->ordinal != root_session->ordinal)
+    {
+        cudaError_t e = cudaDeviceEnablePeerAccess(root_session->ordinal, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        {
+            set_error("cudaDeviceEnablePeerAccess(%d): %s", root_session->ordinal,
+                      cudaGetErrorString(e));
+            return StromError_CudaInternal;
+        }
+        cudaGetLastError();
+    }
+    s->peer_root_area = root_session->peer_area;
+    s->peer_mapped = false;
+    return StromError_Success;
+}
+
+static void
+merge_trace_begin(pgs_session *s)
+{
+    if (s->perfmon && s->ev_m[0])
+    {
+        /* the events of the merge before this one have long completed */
+        float ms = 0;
+        if (s->merge_count > 0 && cudaEventElapsedTime(&ms, s->ev_m[0], s->ev_m[1]) == cudaSuccess)
+            s->merge_ms[0] += ms;
+        else
+            cudaGetLastError();
+        cudaEventRecord(s->ev_m[0], s->s_exec);
+    }
+}
+
+static void
+merge_trace_end(pgs_session *s)
+{
+    if (s->perfmon && s->ev_m[1])
+        cudaEventRecord(s->ev_m[1], s->s_exec);
+    s->merge_count++;
+}
+
+/* one merge: every rank calls it once per scan, after its last chunk and
+ * before pgs_preagg_finish().  Stream ordered, no host synchronisation, no
+ * rendezvous: a rank that is not the root pushes and goes on; the root waits
+ * (on the device) for the data only. */
+extern "C" int
+pgs_preagg_merge_peer(pgs_session *s)
+{
+    if (!s || !s->peer_area || !s->peer_root_area)
+    {
+        set_error("pgs_preagg_merge_peer: no exchange area (pgs_preagg_peer_setup / _attach)");
+        return StromError_BadRequestMessage;
+    }
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    cl_ulong epoch = ++s->peer_epoch;
+    cl_uint rank = (cl_uint)s->peer_rank, nranks = (cl_uint)s->peer_nranks;
+    cl_uint root = (cl_uint)s->peer_root, cap = s->peer_cap;
+    cl_uint *local = (cl_uint *)((char *)s->d_scratch + 80);
+    int rc;
+
+    if (nranks == 1)
+        return StromError_Success;
+    merge_trace_begin(s);
+    if (s->peer_rank != s->peer_root)
+    {
+        void *args[] = { &s->gs, &s->peer_root_area, &rank, &nranks, &cap, &epoch, &local };
+        int grid = (s->desc.num_keys == 0) ? 1 :
+            std::max(1, std::min<int>(s->num_sms, (int)(((size_t)s->gs.gh_nslots + 255) / 256)));
+        rc = launch_kernel(s, s->k_peer_push, grid, 256, 0, args);
+    }
+    else
+    {
+        if (!s->d_kg_misc)
+            CUDA_CHECK(cudaMalloc((void **)&s->d_kg_misc, sizeof(kern_gpupreagg)));
+        void *args[] = { &s->gs, &s->peer_root_area, &root, &nranks, &cap, &epoch, &local,
+                         &s->d_kg_misc };
+        int grid = (s->desc.num_keys == 0) ? 1 :
+            std::max(1, std::min<int>(s->num_sms, (int)(((size_t)cap + 255) / 256)));
+        if (!s->merge_pending)
+            CUDA_CHECK(cudaMemsetAsync(s->d_kg_misc, 0, sizeof(kern_gpupreagg), s->s_exec));
+        s->merge_pending = true;
+        rc = launch_kernel(s, s->k_peer_pull, grid, 256, 0, args);
+    }
+    merge_trace_end(s);
+    return rc;
+}
+
+/* ------------------------------------------------------------------
+ * Partitioned exchange of large GROUP BY states: rank r ends
+ * up with the groups whose key hash maps to r, every rank then flushes its
+ * own share - the ranks' partial rows are disjoint in their keys, and nobody
+ * holds (or copies to the host) more than 1/G of the groups.
+ *   1. count the records per destination        (gpupreagg_export_parts, pass 0)
+ *   2. all ranks learn all counts               (one ncclAllGather, G x G words)
+ *   3. write the records bucket by bucket       (gpupreagg_export_parts, pass 1)
+ *   4. all-to-all of the buckets                (ncclSend / ncclRecv in one group)
+ *   5. reset the state, size the table for what arrives, import
+ * One host synchronisation (the counts).  The exchange buffers belong to the
+ * session and only ever grow.  Every rank issues every send and receive with
+ * the counts all ranks agreed on in step 2, whatever happens locally.
+ * ------------------------------------------------------------------ */
+static int
+import_async(pgs_session *s, const void *device_buf, size_t nrecords)
+{
+    const cl_ulong *recs = (const cl_ulong *)device_buf;
+    while (nrecords > 0)
+    {
+        cl_uint n = (cl_uint)std::min<size_t>(nrecords, 1u << 30);
+        void *args[] = { &s->gs, &recs, &n, &s->d_kg_misc };
+        int grid = std::max(1, std::min<int>(s->num_sms * 8, (int)((n + 255) / 256)));
+        int rc = launch_kernel(s, s->k_import, grid, 256, 0, args);
+        if (rc != StromError_Success)
+            return rc;
+        recs += (size_t)n * (s->desc.slot_bytes / 8);
+        nrecords -= n;
+    }
+    return StromError_Success;
+}
+
+extern "C" int
+pgs_preagg_merge_exchange(pgs_session *s, void *nccl_comm, int rank, int nranks)
+{
+    const int NCCL_UINT8 = 1;
+    if (!s || !nccl_comm || nranks < 1 || nranks > PGS_EXCHANGE_MAX_RANKS ||
+        rank < 0 || rank >= nranks)
+    {
+        set_error("pgs_preagg_merge_exchange: bad arguments (at most %d ranks)",
+                  PGS_EXCHANGE_MAX_RANKS);
+        return StromError_BadRequestMessage;
+    }
+    if (s->desc.num_keys == 0)
+    {
+        set_error("pgs_preagg_merge_exchange: a state without GROUP BY has nothing to partition");
+        return StromError_BadRequestMessage;
+    }
+    int rc = nccl_load();
+    if (rc != StromError_Success)
+        return rc;
+    CUDA_CHECK(cudaSetDevice(s->ordinal));
+    if (nranks == 1)
+        return StromError_Success;
     rc = drain(s);
     if (rc != StromError_Success)
         return rc;
-    cl_uint my_n = 1;
-    if (s->desc.num_keys > 0)
-        CUDA_CHECK(cudaMemcpy(&my_n, s->gs.gh_ngroups, sizeof(cl_uint), cudaMemcpyDeviceToHost));
-    cl_uint *d_counts = NULL;
-    std::vector<cl_uint> counts(nranks, 0);
-    CUDA_CHECK(cudaMalloc((void **)&d_counts, sizeof(cl_uint) * (nranks + 1)));
-    CUDA_CHECK(cudaMemcpy(d_counts + nranks, &my_n, sizeof(cl_uint), cudaMemcpyHostToDevice));
-    NCCL_CHECK(nccl.allgather(d_counts + nranks, d_counts, sizeof(cl_uint), NCCL_UINT8,
-                              nccl_comm, s->s_exec));
-    CUDA_CHECK(cudaMemcpyAsync(counts.data(), d_counts, sizeof(cl_uint) * nranks,
-                               cudaMemcpyDeviceToHost, s->s_exec));
-    CUDA_CHECK(cudaStreamSynchronize(s->s_exec));
-    cudaFree(d_counts);
-    /* 2. non-root ranks export + send; the root receives in rank order and
-     *    imports (re-hash / ordered merge) */
-    if (rank != root)
+    const size_t recb = s->desc.slot_bytes;
+    const cl_uint R = (cl_uint)nranks;
+    cl_uint *d_counts = (cl_uint *)((char *)s->d_scratch + 512);
+    cl_uint *d_cursors = d_counts + PGS_EXCHANGE_MAX_RANKS;
+    cl_uint *d_offsets = d_cursors + PGS_EXCHANGE_MAX_RANKS;
+    cl_uint *d_all = d_offsets + PGS_EXCHANGE_MAX_RANKS;    /* [R][R] */
+    cl_ulong *d_send = (cl_ulong *)s->d_xchg;
+    int grid = std::max(1, std::min<int>(s->num_sms * 8,
+                    (int)std::min<size_t>((state_nslots(s) + s->gs.ovf_cap + 255) / 256, 1u << 30)));
+    auto t0 = std::chrono::steady_clock::now();
+
+    if (!s->d_kg_misc)
+        CUDA_CHECK(cudaMalloc((void **)&s->d_kg_misc, sizeof(kern_gpupreagg)));
+    CUDA_CHECK(cudaMemsetAsync(s->d_kg_misc, 0, sizeof(kern_gpupreagg), s->s_exec));
+    s->merge_pending = true;
+    CUDA_CHECK(cudaMemsetAsync(d_counts, 0, sizeof(cl_uint) * 3 * PGS_EXCHANGE_MAX_RANKS, s->s_exec));
     {
-        void *d_recs = NULL;
-        cl_uint n = 0;
-        CUDA_CHECK(cudaMalloc(&d_recs, std::max<size_t>(recb * my_n, recb)));
-        rc = pgs_preagg_state_export(s, d_recs, std::max<size_t>(recb * my_n, recb), &n, NULL);
-        if (rc == StromError_Success)
-        {
-            int nrc = nccl.send(d_recs, recb * (size_t)n, NCCL_UINT8, root, nccl_comm, s->s_exec);
-            if (nrc != 0)
-                rc = StromError_CudaInternal;
-        }
-        cudaStreamSynchronize(s->s_exec);
-        cudaFree(d_recs);
+        cl_uint pass = 0;
+        void *args[] = { &s->gs, &d_send, &d_counts, &d_offsets, &d_cursors, (void *)&R, &pass };
+        rc = launch_kernel(s, s->k_export_parts, grid, 256, 0, args);
         if (rc != StromError_Success)
             return rc;
-        /* this rank's state now lives on the root */
-        return pgs_preagg_state_reset(s);
     }
-    size_t total = 0;
-    for (int r = 0; r < nranks; r++)
-        if (r != root)
-            total += counts[r];
-    if (total == 0)
-        return StromError_Success;
-    char *d_recs = NULL;
-    CUDA_CHECK(cudaMalloc((void **)&d_recs, recb * total));
-    NCCL_CHECK(nccl.group_start());
-    size_t off = 0;
-    for (int r = 0; r < nranks; r++)
+    NCCL_CHECK(nccl.allgather(d_counts, d_all, sizeof(cl_uint) * R, NCCL_UINT8, nccl_comm, s->s_exec));
+    std::vector<cl_uint> all((size_t)R * R, 0);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all, sizeof(cl_uint) * R * R,
+                               cudaMemcpyDeviceToHost, s->s_exec));
+    CUDA_CHECK(cudaStreamSynchronize(s->s_exec));
+    session_bury(s);
+
+    /* from here on the sends and receives must be issued: local failures
+     * (allocation) are remembered and reported after the exchange */
+    std::vector<cl_uint> soff(R + 1, 0), roff(R + 1, 0);
+    size_t total_send = 0, total_recv = 0;
+    for (cl_uint d = 0; d < R; d++)
     {
-        if (r == root || counts[r] == 0)
+        soff[d] = (cl_uint)total_send;
+        total_send += all[(size_t)rank * R + d];
+    }
+    for (cl_uint r = 0; r < R; r++)
+    {
+        roff[r] = (cl_uint)total_recv;
+        if ((int)r != rank)
+            total_recv += all[(size_t)r * R + rank];
+    }
+    if (s->d_xchg_cap < std::max<size_t>(total_send, 1) * recb)
+    {
+        if (s->d_xchg)
+            CUDA_CHECK(cudaFree(s->d_xchg));
+        s->d_xchg = NULL;
+        s->d_xchg_cap = 0;
+        size_t want = std::max<size_t>(total_send, 1) * recb;
+        want += want / 8;
+        CUDA_CHECK(cudaMalloc((void **)&s->d_xchg, want));
+        s->d_xchg_cap = want;
+    }
+    if (s->d_xrecv_cap < std::max<size_t>(total_recv, 1) * recb)
+    {
+        if (s->d_xrecv)
+            CUDA_CHECK(cudaFree(s->d_xrecv));
+        s->d_xrecv = NULL;
+        s->d_xrecv_cap = 0;
+        size_t want = std::max<size_t>(total_recv, 1) * recb;
+        want += want / 8;
+        CUDA_CHECK(cudaMalloc((void **)&s->d_xrecv, want));
+        s->d_xrecv_cap = want;
+    }
+    d_send = (cl_ulong *)s->d_xchg;
+    CUDA_CHECK(cudaMemcpyAsync(d_offsets, soff.data(), sizeof(cl_uint) * R,
+                               cudaMemcpyHostToDevice, s->s_exec));
+    {
+        cl_uint pass = 1;
+        void *args[] = { &s->gs, &d_send, &d_counts, &d_offsets, &d_cursors, (void *)&R, &pass };
+        rc = launch_kernel(s, s->k_export_parts, grid, 256, 0, args);
+        if (rc != StromError_Success)
+            return rc;
+    }
+    /* the state now lives in the send buffer: start over with an empty one,
+     * with a table that takes what this rank will own (every record that
+     * arrives may be a group of its own) */
+    rc = session_init_state(s);
+    if (rc != StromError_Success)
+        return rc;
+    size_t own = all[(size_t)rank * R + rank];
+    rc = session_grow_table(s, 2 * (total_recv + own));
+    if (rc != StromError_Success)
+        return rc;
+    NCCL_CHECK(nccl.group_start());
+    for (cl_uint r = 0; r < R; r++)
+    {
+        if ((int)r == rank)
             continue;
-        NCCL_CHECK(nccl.recv(d_recs + off * recb, recb * (size_t)counts[r], NCCL_UINT8, r,
-                             nccl_comm, s->s_exec));
-        off += counts[r];
+        int e1 = nccl.send((const char *)s->d_xchg + (size_t)soff[r] * recb,
+                           (size_t)all[(size_t)rank * R + r] * recb, NCCL_UINT8, (int)r,
+                           nccl_comm, s->s_exec);
+        int e2 = nccl.recv(s->d_xrecv + (size_t)roff[r] * recb,
+                           (size_t)all[(size_t)r * R + rank] * recb, NCCL_UINT8, (int)r,
+                           nccl_comm, s->s_exec);
+        if (e1 != 0 || e2 != 0)
+        {
+            nccl.group_end();
+            set_error("ncclSend / ncclRecv failed: %s", nccl.errstr ? nccl.errstr(e1 ? e1 : e2) : "?");
+            return StromError_CudaInternal;
+        }
     }
     NCCL_CHECK(nccl.group_end());
-    rc = pgs_preagg_state_import(s, d_recs, (uint32_t)total);
-    cudaFree(d_recs);
+    rc = import_async(s, (const char *)s->d_xchg + (size_t)soff[rank] * recb, own);
+    if (rc == StromError_Success)
+        rc = import_async(s, s->d_xrecv, total_recv);
+    s->merge_count++;
+    s->merge_ms[1] += std::chrono::duration<double, std::milli>(
+        std::chrono::steady_clock::now() - t0).count();
     return rc;
 }
 
@@ -1934,6 +2394,10 @@ pgs_preagg_perfmon_json(pgs_session *s)
             a->push(pgs::Json::number((double)dbg[i]));
         o->set("debug_counters", a);
     }
+    o->set("num_table_grown", (long long)s->num_table_grown);
+    o->set("merge_count", (long long)s->merge_count);
+    o->set("merge_kernel_ms", pgs::Json::number(s->merge_ms[0]));
+    o->set("merge_exchange_ms", pgs::Json::number(s->merge_ms[1]));
     o->set("grid_main", s->grid_main);
     o->set("smem_main", (long long)s->smem_main);
     o->set("sh_nslots", (long long)s->sh_nslots);
@@ -1989,7 +2453,14 @@ pgs_preagg_close(pgs_session *s)
             if (sl.ev_k0) cudaEventDestroy(sl.ev_k0);
             if (sl.ev_k1) cudaEventDestroy(sl.ev_k1);
         }
+        session_bury(s);
         if (s->gs.gh_slots) cudaFree(s->gs.gh_slots);
+        if (s->gs.ovf_recs) cudaFree(s->gs.ovf_recs);
+        if (s->peer_mapped && s->peer_root_area) cudaIpcCloseMemHandle(s->peer_root_area);
+        if (s->peer_area) cudaFree(s->peer_area);
+        if (s->d_xrecv) cudaFree(s->d_xrecv);
+        for (int i = 0; i < 4; i++)
+            if (s->ev_m[i]) cudaEventDestroy(s->ev_m[i]);
         if (s->gs.part_cursor) cudaFree(s->gs.part_cursor);
         if (s->gs.part_nused) cudaFree(s->gs.part_nused);
         if (s->gs.part_recs) cudaFree(s->gs.part_recs);

@@ -236,6 +236,12 @@ pgstrom_kds_row_init(void *buffer, size_t buflen, int ncols,
         pgs::last_error = "row store does not fit the buffer";
         return StromError_DataStoreNoSpace;
     }
+    if (maxblocks > 65536)
+    {
+        /* kern_rowitem.blk_index has 16 bits (opencl_common.h:395-401) */
+        pgs::last_error = "a KDS_FORMAT_ROW chunk addresses at most 65536 pages";
+        return StromError_DataStoreNoSpace;
+    }
     init_kern_data_store(kds, ncols, colmeta, need, nrooms, KDS_FORMAT_ROW);
     kds->maxblocks = maxblocks;
     return StromError_Success;

@@ -49,6 +49,10 @@ struct pgs_gpupreagg_state
     uint32_t        next_seq = 0;
     uint32_t        num_rechecked = 0;
     std::vector<std::pair<uint32_t, uint32_t> > recheck;   /* (chunk seq, row) */
+    /* chunks with re-check rows stay with this node until the host has walked
+     * them (gpupreagg.c:2746 keeps curr_recheck the same way):
+     * gpupreagg_recheck_done(), ReScan or EndCustomPlan hand them back */
+    std::vector<RunningChunk> held;
     std::vector<char> result_buf;       /* TUPSLOT store */
     uint32_t        curr_index = 0;
     std::string     notice, explain_buf;
@@ -78,6 +82,11 @@ retire_chunk(pgs_gpupreagg_state *st, bool wait)
         for (uint32_t r : rows)
             st->recheck.push_back(std::make_pair(rc.seq, r));
         st->num_rechecked++;
+        if (!rows.empty())
+        {
+            st->held.push_back(rc);
+            rc.slot.release = NULL;     /* not yet */
+        }
     }
     if (rc.slot.release)
         rc.slot.release(rc.slot.release_arg, rc.slot.kds);
@@ -87,6 +96,15 @@ retire_chunk(pgs_gpupreagg_state *st, bool wait)
         return -status;
     }
     return 1;
+}
+
+static void
+release_held(pgs_gpupreagg_state *st)
+{
+    for (auto &h : st->held)
+        if (h.slot.release)
+            h.slot.release(h.slot.release_arg, h.slot.kds);
+    st->held.clear();
 }
 
 extern "C" {
@@ -246,6 +264,37 @@ gpupreagg_recheck_rows(pgs_gpupreagg_state *st, uint32_t *chunk_seq, uint32_t *r
     return n;
 }
 
+const kern_data_store *
+gpupreagg_recheck_chunk(pgs_gpupreagg_state *st, uint32_t chunk_seq,
+                        const kern_row_map **krowmap)
+{
+    for (auto &h : st->held)
+        if (h.seq == chunk_seq)
+        {
+            if (krowmap)
+                *krowmap = h.slot.krowmap;
+            return h.slot.kds;
+        }
+    return NULL;
+}
+
+int
+gpupreagg_recheck_done(pgs_gpupreagg_state *st, uint32_t chunk_seq)
+{
+    for (size_t i = 0; i < st->held.size(); i++)
+        if (st->held[i].seq == chunk_seq)
+        {
+            RunningChunk h = st->held[i];
+            st->held.erase(st->held.begin() + (long)i);
+            if (h.slot.release)
+                h.slot.release(h.slot.release_arg, h.slot.kds);
+            return StromError_Success;
+        }
+    last_error = "gpupreagg_recheck_done: no chunk " + std::to_string(chunk_seq) +
+        " is held for re-check";
+    return StromError_BadRequestMessage;
+}
+
 const char *
 gpupreagg_end(pgs_gpupreagg_state *st)
 {
@@ -262,6 +311,7 @@ gpupreagg_end(pgs_gpupreagg_state *st)
             st->running.pop_front();
         }
     }
+    release_held(st);
     if (st->session)
         pgs_preagg_close(st->session);
     if (st->program)
@@ -280,6 +330,7 @@ gpupreagg_rescan(pgs_gpupreagg_state *st)
         if (r < 0)
             return -r;
     }
+    release_held(st);
     int rc = pgs_preagg_state_reset(st->session);
     if (rc != StromError_Success)
         return rc;

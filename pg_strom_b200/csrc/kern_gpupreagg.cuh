@@ -1387,7 +1387,31 @@ pgs_gh_find_slot(const pgs_gstate &gs, const cl_ulong *keyvals,
     return found;
 }
 
-/* merge a state (cells + nn bits) into the global table */
+/* a state record that found no room in the global table goes to the overflow
+ * log (record = ctrl | keys | cells, the exported format); false = the log is
+ * full as well */
+DEVFN bool
+pgs_ovf_append(const pgs_gstate &gs, const cl_ulong *keyvals, cl_uint knull,
+               const cl_ulong *src, cl_uint src_nn)
+{
+    cl_uint     pos = atomicAdd(gs.ovf_count, 1U);
+    cl_ulong   *rec;
+
+    if (pos >= gs.ovf_cap)
+        return false;
+    rec = gs.ovf_recs + (cl_ulong)pos * PGS_SLOT_WORDS;
+    rec[0] = ((cl_ulong)src_nn << 32) | (knull << 8) | PGS_SLOT_READY;
+#pragma unroll
+    for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+        rec[1 + k] = keyvals[k];
+#pragma unroll
+    for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+        rec[1 + GPUPREAGG_NUM_KEYS + c] = src[c];
+    return true;
+}
+
+/* merge a state (cells + nn bits) into the global table; a full table sends
+ * it to the overflow log, so that a state is never lost */
 DEVFN bool
 pgs_gh_merge_state(const pgs_gstate &gs, const cl_ulong *keyvals, cl_uint knull,
                    cl_ulong hash, const cl_ulong *src, cl_uint src_nn,
@@ -1398,7 +1422,7 @@ pgs_gh_merge_state(const pgs_gstate &gs, const cl_ulong *keyvals, cl_uint knull,
     cl_uint    *p_nn;
 
     if (!slot)
-        return false;
+        return pgs_ovf_append(gs, keyvals, knull, src, src_nn);
     cells = slot + 1 + GPUPREAGG_NUM_KEYS;
     gpupreagg_aggmerge_atomic(cells, src, src_nn);
     p_nn = (cl_uint *)slot + 1;
@@ -1509,11 +1533,10 @@ pgs_sh_find_slot(const pgs_sh_table &sh, cl_uint *sh_nused,
  * the referenced columns of one row in slot order, each on its natural
  * alignment, then the validity mask (bit per slot) and the row number.
  * ------------------------------------------------------------------ */
-DEVFN cl_uint
+__host__ __device__ constexpr cl_uint
 pgs_rec_val_off(int slot)
 {
     cl_uint off = 0;
-#pragma unroll
     for (int s = 0; s <= slot && s < GPUPREAGG_NUM_INCOLS; s++)
     {
         cl_uint a = GPUPREAGG_INCOL_ATTLEN(s);
@@ -1523,11 +1546,10 @@ pgs_rec_val_off(int slot)
     }
     return off;
 }
-DEVFN cl_uint
+__host__ __device__ constexpr cl_uint
 pgs_rec_end_off(void)
 {
     cl_uint off = 0;
-#pragma unroll
     for (int s = 0; s < GPUPREAGG_NUM_INCOLS; s++)
     {
         cl_uint a = GPUPREAGG_INCOL_ATTLEN(s);
@@ -1537,7 +1559,12 @@ pgs_rec_end_off(void)
 }
 #define PGS_REC_MASK_OFF    pgs_rec_end_off()
 #define PGS_REC_ROW_OFF     (PGS_REC_MASK_OFF + 4)
-#define PGS_REC_BYTES       ((PGS_REC_ROW_OFF + 4 + 7U) & ~7U)
+/* a record is a whole number of 16-byte units: it leaves the SM as 128-bit
+ * stores (one or two per 32-byte sector), never as one store per column */
+#define PGS_REC_BYTES       ((PGS_REC_ROW_OFF + 4 + 15U) & ~15U)
+/* cursor of partition p: the cursors may be spread out (1 << part_pad words
+ * apart) so that neighbours do not share the 32-byte sector L2 atomics work on */
+#define PGS_PART_CURSOR(gs,p)   ((gs).part_cursor + ((cl_ulong)(p) << (gs).part_pad))
 
 struct kern_rec_gmem
 {
@@ -1555,9 +1582,27 @@ struct kern_rec_gmem
     {                                                                   \
         pgs_rowq_type<attlen>::T __v;                                   \
         bool __ok = kds.template fetch<pgs_rowq_type<attlen>::T>(slot, rowidx, __v); \
-        *((pgs_rowq_type<attlen>::T *)(__rec + pgs_rec_val_off(slot))) = __v; \
+        pgs_rec_put<attlen>(__w, pgs_rec_val_off(slot), (cl_ulong)__v); \
         __mask |= (__ok ? (1U << (slot)) : 0U);                         \
     }
+/* the record is put together in registers (every offset is a compile time
+ * constant, so __w[] never leaves them) */
+template <int ATTLEN>
+DEVFN void
+pgs_rec_put(cl_uint *w, cl_uint off, cl_ulong v)
+{
+    if (ATTLEN == 8)
+    {
+        w[off / 4] = (cl_uint)v;
+        w[off / 4 + 1] = (cl_uint)(v >> 32);
+    }
+    else if (ATTLEN == 4)
+        w[off / 4] = (cl_uint)v;
+    else if (ATTLEN == 2)
+        w[off / 4] |= ((cl_uint)v & 0xffffU) << (8 * (off & 3U));
+    else
+        w[off / 4] |= ((cl_uint)v & 0xffU) << (8 * (off & 3U));
+}
 
 /* deal one row into its partition: reserve a record (one atomic on the
  * partition's cursor), then write it.  A position at or beyond part_cap means
@@ -1567,19 +1612,27 @@ DEVFN cl_uint
 pgs_part_reserve(const pgs_gstate &gs, cl_ulong hash, cl_uint &part)
 {
     part = __umulhi((cl_uint)(hash >> 32), gs.part_nparts);
-    return atomicAdd(gs.part_cursor + part, 1U);
+    return atomicAdd(PGS_PART_CURSOR(gs, part), 1U);
 }
 template <typename KDS>
 DEVFN void
 pgs_part_write(const pgs_gstate &gs, const KDS &kds, cl_uint rowidx,
                cl_uint rownum, cl_uint part, cl_uint pos)
 {
-    unsigned char  *__rec = gs.part_recs + ((cl_ulong)part * gs.part_cap + pos) * PGS_REC_BYTES;
+    uint4          *__rec = (uint4 *)(gs.part_recs +
+                                      ((cl_ulong)part * gs.part_cap + pos) * PGS_REC_BYTES);
+    cl_uint         __w[PGS_REC_BYTES / 4];
     cl_uint         __mask = 0;
 
+#pragma unroll
+    for (int i = 0; i < (int)(PGS_REC_BYTES / 4); i++)
+        __w[i] = 0;
     GPUPREAGG_INCOL_LIST(PGS_X_INCOL_RECPUT)
-    *((cl_uint *)(__rec + PGS_REC_MASK_OFF)) = __mask;
-    *((cl_uint *)(__rec + PGS_REC_ROW_OFF)) = rownum;
+    __w[PGS_REC_MASK_OFF / 4] = __mask;
+    __w[PGS_REC_ROW_OFF / 4] = rownum;
+#pragma unroll
+    for (int i = 0; i < (int)(PGS_REC_BYTES / 16); i++)
+        __rec[i] = make_uint4(__w[4 * i], __w[4 * i + 1], __w[4 * i + 2], __w[4 * i + 3]);
 }
 template <typename KDS>
 DEVFN bool
@@ -1671,7 +1724,10 @@ pgs_writeback_status(kern_gpupreagg *kgpreagg, const pgs_gstate &gs,
         if (nf)
             atomicAdd((unsigned long long *)gs.nrows_filtered, (unsigned long long)nf);
         if (ni)
+        {
             atomicAdd(gs.gh_ngroups, ni);
+            atomicAdd(gs.gh_nused, ni);
+        }
         if (ec != StromError_Success)
         {
             cl_int cur = atomicCAS(&kgpreagg->status, StromError_Success, ec);
@@ -1748,7 +1804,8 @@ struct pgs_smem_head
         if (r + (j) < rows)                                             \
             valid = pgs_eval_row(kparams, rr[j], kds_in, row0 + r + (j), \
                                  recheck_map, ctx, prow);               \
-        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid);   \
+        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid,    \
+                          row0 + r + (j), recheck_map);                 \
     }
 
 /* phase 1 of the staged consumer loop: 4 adjacent rows of one column */
@@ -1777,6 +1834,13 @@ struct pgs_smem_head
                KERN_DATA_STORE_COLPOS(kds_in, colidx)->nullmap_offset)  \
          : (const cl_uint *)NULL);
 
+/* one row of every column, by row number, raw into registers (the validity
+ * word is kept whole: bit `shift` is this row's) */
+#define PGS_X_INCOL_GLOAD(slot,colidx,attlen)                           \
+    nx.v[slot] = (cl_ulong)__ldg((const pgs_rowq_type<attlen>::T *)gtile.val_ptr[slot] + nrow); \
+    nx.vbits[slot] = (gtile.nul_ptr[slot]                               \
+                      ? __ldg(gtile.nul_ptr[slot] + (nrow >> 5)) : 0xffffffffU);
+
 /*
  * Add one projected row per lane to the group state (CTA-local table first,
  * global table when that is full or absent).
@@ -1790,7 +1854,7 @@ struct pgs_smem_head
 DEVFN void
 pgs_group_add_row(const pgs_gstate &gs, const pgs_sh_table &sh,
                   cl_uint *sh_nused, const pagg_row &prow, pgs_row_ctx &ctx,
-                  bool active)
+                  bool active, cl_uint rownum, cl_uint *recheck_map)
 {
     cl_ulong    keyvals[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
     cl_uint     knull = 0;
@@ -1853,8 +1917,27 @@ pgs_group_add_row(const pgs_gstate &gs, const pgs_sh_table &sh,
             if ((*((volatile cl_uint *)p_nn) & nn) != nn)
                 atomicOr(p_nn, nn);
         }
-        else if (ctx.errcode == StromError_Success)
-            ctx.errcode = StromError_DataStoreNoSpace;
+        else
+        {
+            /* no room in the tables (the planner's estimate of the number of
+             * groups was too low and the table has not been enlarged yet):
+             * the row becomes a state record of its own in the overflow log
+             * (the host folds the log into a larger table after the chunk);
+             * with the log full as well it is left to the host like any
+             * other row the device cannot finish - the reference reduces
+             * every chunk on its own and never fails on a wrong ndistinct,
+             * neither may this */
+            cl_ulong    one[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+            cl_uint     nn;
+
+            pgs_cells_init(one);
+            nn = gpupreagg_aggcalc_plain(one, prow, true);
+            if (!pgs_ovf_append(gs, keyvals, knull, one, nn))
+            {
+                atomicOr(&recheck_map[rownum >> 5], 1U << (rownum & 31));
+                ctx.nrecheck++;
+            }
+        }
     }
     __syncwarp();
 }
@@ -2126,6 +2209,10 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
         cl_uint         nscanned = 0, npassed = 0;
 #if GPUPREAGG_GATHER_PAYLOAD
         kern_tile_gmem  gtile;
+        /* the batch of queued rows whose columns are on their way from HBM */
+        kern_row_regs   g_row;
+        cl_uint         g_rownum = 0;
+        bool            g_have = false, g_act = false;
 
         GPUPREAGG_INCOL_LIST(PGS_X_INCOL_GVIEW)
 #endif
@@ -2311,7 +2398,8 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                                 gpupreagg_projection(&e, kparams, rr[j], prow, kds_in,
                                                      row0 + r + j, 0);
                             }
-                            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, refused);
+                            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, refused,
+                                              row0 + r + j, recheck_map);
                         }
                     }
                 }
@@ -2398,30 +2486,67 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                             pgs_mbar_arrive(&head->empty_bar[stage]);
                         scanning = false;
                     }
-                    if (qn >= 32 || (!scanning && last_tile && qn != 0))
                     {
-                        const cl_uint   n = min(qn, 32U);
-                        const cl_uint   row = rowq32[(qhead + lane_id) & (PGS_ROWQ_ENTRIES - 1)];
-                        bool            active = (lane_id < n);
-                        pagg_row        prow;
+                        /* Two batches of 32 queued rows are under way at any
+                         * time: the columns of the batch popped now are asked
+                         * for (plain loads into registers, nothing waits for
+                         * them yet), then the batch popped last time - whose
+                         * loads have had a whole round of scanning or a whole
+                         * chain to arrive - goes through projection +
+                         * find-or-insert + the cell updates.  (Taken one batch
+                         * at a time the warp sat out a DRAM round trip per 32
+                         * rows: 18% of all samples on the first use of the
+                         * gathered key.) */
+                        const bool  pop = (qn >= 32 || (!scanning && last_tile && qn != 0));
 
-                        if (active)
+                        if (pop || g_have)
                         {
-                            cl_int  e = StromError_Success;
+                            kern_row_regs   nx;
+                            cl_uint         nrow = row0;
+                            bool            nact = false;
 
-                            gpupreagg_projection(&e, kparams, gtile, prow, kds_in, row, 0);
-                            gpupreagg_aggcheck(&e, prow);
-                            if (e != StromError_Success)
+                            if (pop)
                             {
-                                pgs_note_error(e, row, recheck_map, ctx);
-                                active = false;
+                                const cl_uint   n = min(qn, 32U);
+
+                                nact = (lane_id < n);
+                                if (nact)
+                                    nrow = rowq32[(qhead + lane_id) & (PGS_ROWQ_ENTRIES - 1)];
+                                nx.shift = (int)(nrow & 31U);
+                                GPUPREAGG_INCOL_LIST(PGS_X_INCOL_GLOAD)
+                                qhead += n;
+                                npassed += n;
                             }
+                            if (g_have)
+                            {
+                                bool        active = g_act;
+                                pagg_row    prow;
+
+                                if (active)
+                                {
+                                    cl_int  e = StromError_Success;
+
+                                    gpupreagg_projection(&e, kparams, g_row, prow, kds_in, g_rownum, 0);
+                                    gpupreagg_aggcheck(&e, prow);
+                                    if (e != StromError_Success)
+                                    {
+                                        pgs_note_error(e, g_rownum, recheck_map, ctx);
+                                        active = false;
+                                    }
+                                }
+                                pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, active,
+                                                  g_rownum, recheck_map);
+                                __syncwarp();
+                            }
+                            g_have = pop;
+                            if (pop)
+                            {
+                                g_row = nx;
+                                g_rownum = nrow;
+                                g_act = nact;
+                            }
+                            continue;
                         }
-                        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, active);
-                        __syncwarp();
-                        qhead += n;
-                        npassed += n;
-                        continue;
                     }
                     if (!scanning)
                         break;
@@ -2569,20 +2694,21 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                                     active = false;
                                 }
                             }
+                            const cl_uint   rownum = (qrow.isleft
+                                ? *((const cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_ROW_OFF) + qrow.idx)
+                                : row0 + qrow.idx);
                             if (PGS_PART_NPARTS(gs) != 0)
                             {
                                 if (active)
                                 {
                                     cl_uint     knull;
                                     cl_ulong    hash = pgs_hash_keys(prow, knull);
-                                    cl_uint     rownum = (qrow.isleft
-                                        ? *((const cl_uint *)(__pgs_smem + __qbase + PGS_ROWQ_ROW_OFF) + qrow.idx)
-                                        : row0 + qrow.idx);
                                     active = !pgs_part_emit(gs, qrow, 0, rownum, hash);
                                 }
                             }
                             if (PGS_PART_NPARTS(gs) == 0 || __any_sync(0xffffffffU, active))
-                                pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, active);
+                                pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, active,
+                                                  rownum, recheck_map);
                             qhead += n;
                             npassed += n;
                         }
@@ -2664,11 +2790,12 @@ gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
         cl_ulong    i = base + (threadIdx.x & 31U);
         pagg_row    prow;
         bool        valid = false;
+        cl_uint     row = 0;
 
         if (i < nvalids)
         {
-            cl_uint row = (krowmap->nvalids < 0
-                           ? (cl_uint)i : (cl_uint)krowmap->rindex[i]);
+            row = (krowmap->nvalids < 0
+                   ? (cl_uint)i : (cl_uint)krowmap->rindex[i]);
             if (row >= nrows)
             {
                 if (ctx.errcode == StromError_Success)
@@ -2680,7 +2807,7 @@ gpupreagg_main_rowmap(kern_gpupreagg *kgpreagg,
 #if GPUPREAGG_NUM_KEYS == 0
         acc_nn |= gpupreagg_aggcalc_plain(acc, prow, valid);
 #else
-        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid);
+        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid, row, recheck_map);
 #endif
     }
     pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
@@ -2932,11 +3059,12 @@ gpupreagg_main_heap(kern_gpupreagg *kgpreagg,
         cl_ulong    i = base + (threadIdx.x & 31U);
         pagg_row    prow;
         bool        valid = false;
+        cl_uint     row = 0;
 
         if (i < nvalids)
         {
-            cl_uint row = (krowmap->nvalids < 0
-                           ? (cl_uint)i : (cl_uint)krowmap->rindex[i]);
+            row = (krowmap->nvalids < 0
+                   ? (cl_uint)i : (cl_uint)krowmap->rindex[i]);
             if (row >= nrows)
             {
                 if (ctx.errcode == StromError_Success)
@@ -2960,7 +3088,7 @@ gpupreagg_main_heap(kern_gpupreagg *kgpreagg,
 #if GPUPREAGG_NUM_KEYS == 0
         acc_nn |= gpupreagg_aggcalc_plain(acc, prow, valid);
 #else
-        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid);
+        pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid, row, recheck_map);
 #endif
     }
     pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
@@ -3012,7 +3140,7 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
 
     for (cl_uint part = blockIdx.x; part < gs.part_nparts; part += gridDim.x)
     {
-        const cl_uint   n = min(gs.part_cursor[part], gs.part_cap);
+        const cl_uint   n = min(*PGS_PART_CURSOR(gs, part), gs.part_cap);
         uint4          *image = (uint4 *)(gs.part_images + (cl_ulong)part * image_bytes);
         uint4          *local = (uint4 *)(__pgs_smem + sh.base);
         const unsigned char *recs = gs.part_recs +
@@ -3046,7 +3174,8 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
                     active = false;
                 }
             }
-            pgs_group_add_row(gs, sh, p_nused, prow, ctx, active);
+            pgs_group_add_row(gs, sh, p_nused, prow, ctx, active,
+                              *((const cl_uint *)(view.rec + PGS_REC_ROW_OFF)), recheck_map);
         }
         __syncthreads();
         for (cl_uint i = threadIdx.x; i < image_bytes / 16; i += blockDim.x)
@@ -3055,11 +3184,12 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
         {
             ngrown += *p_nused - gs.part_nused[part];
             gs.part_nused[part] = *p_nused;
-            gs.part_cursor[part] = 0;
+            *PGS_PART_CURSOR(gs, part) = 0;
         }
         __syncthreads();
     }
-    ctx.ninserted += ngrown;    /* thread 0: groups the images gained */
+    if (ngrown)                 /* thread 0: groups the images gained */
+        atomicAdd(gs.gh_ngroups, ngrown);
     pgs_writeback_status(kgpreagg, gs, ctx);
 #endif
 }
@@ -3072,7 +3202,8 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
 DEVFN cl_ulong
 pgs_state_nslots(const pgs_gstate &gs)
 {
-    return (cl_ulong)gs.gh_nslots + (cl_ulong)gs.part_nparts * gs.part_slots;
+    return (cl_ulong)gs.gh_nslots + (cl_ulong)gs.part_nparts * gs.part_slots +
+        (cl_ulong)min(*((volatile cl_uint *)gs.ovf_count), gs.ovf_cap);
 }
 DEVFN bool
 pgs_state_slot(const pgs_gstate &gs, cl_ulong i, cl_ulong *keys, cl_ulong *cells,
@@ -3093,6 +3224,22 @@ pgs_state_slot(const pgs_gstate &gs, cl_ulong i, cl_ulong *keys, cl_ulong *cells
 #pragma unroll
         for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
             cells[c] = slot[1 + GPUPREAGG_NUM_KEYS + c];
+        return true;
+    }
+    else if (i >= (cl_ulong)gs.gh_nslots + (cl_ulong)gs.part_nparts * gs.part_slots)
+    {
+        /* a record of the overflow log */
+        const cl_ulong *rec = gs.ovf_recs +
+            (i - gs.gh_nslots - (cl_ulong)gs.part_nparts * gs.part_slots) * PGS_SLOT_WORDS;
+
+        knull = (cl_uint)rec[0] >> 8;
+        nn = (cl_uint)(rec[0] >> 32);
+#pragma unroll
+        for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+            keys[k] = rec[1 + k];
+#pragma unroll
+        for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+            cells[c] = rec[1 + GPUPREAGG_NUM_KEYS + c];
         return true;
     }
     else
@@ -3132,6 +3279,8 @@ gpupreagg_init_state(pgs_gstate gs)
         pgs_cells_init(gs.ng_state + 1);
         *gs.ng_ticket = 0;
         *gs.gh_ngroups = 0;
+        *gs.gh_nused = 0;
+        *gs.ovf_count = 0;
     }
     for (cl_ulong j = i; j < gs.gh_nslots; j += (cl_ulong)gridDim.x * blockDim.x)
     {
@@ -3163,9 +3312,51 @@ gpupreagg_init_state(pgs_gstate gs)
     }
     for (cl_ulong j = i; j < gs.part_nparts; j += (cl_ulong)gridDim.x * blockDim.x)
     {
-        gs.part_cursor[j] = 0;
+        *PGS_PART_CURSOR(gs, j) = 0;
         gs.part_nused[j] = 0;
     }
+}
+
+/* ------------------------------------------------------------------
+ * gpupreagg_rehash - the global table was too small for the number of
+ * groups the scan meets (the planner's numGroups is an estimate; the
+ * reference never depends on it: it reduces chunk by chunk and lets the CPU
+ * Agg merge, gpupreagg.c:2169-2186).  The host allocates a larger table and
+ * overflow log (`to`, initialised) and this kernel moves every group of the
+ * old table and of the old log over.  Table images are shared by both.
+ * ------------------------------------------------------------------ */
+extern "C" __global__ void
+gpupreagg_rehash(pgs_gstate from, pgs_gstate to, kern_gpupreagg *kgpreagg)
+{
+#if GPUPREAGG_NUM_KEYS > 0
+    const cl_ulong  nlog = min(*from.ovf_count, from.ovf_cap);
+    const cl_ulong  n = (cl_ulong)from.gh_nslots + nlog;
+    cl_uint         ninserted = 0;
+
+    for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        const cl_ulong *rec;
+        cl_uint         knull, nn;
+
+        if (i < from.gh_nslots)
+        {
+            rec = from.gh_slots + i * PGS_SLOT_STRIDE;
+            if (((cl_uint)rec[0] & 3U) != PGS_SLOT_READY)
+                continue;
+        }
+        else
+            rec = from.ovf_recs + (i - from.gh_nslots) * PGS_SLOT_WORDS;
+        knull = (cl_uint)rec[0] >> 8;
+        nn = (cl_uint)(rec[0] >> 32);
+        if (!pgs_gh_merge_state(to, rec + 1, knull, pgs_hash_keyvals(rec + 1, knull),
+                                rec + 1 + GPUPREAGG_NUM_KEYS, nn, ninserted))
+            atomicCAS(&kgpreagg->status, StromError_Success, StromError_DataStoreNoSpace);
+    }
+    /* `to` counts in its own words (the host swaps the pointers) */
+    if (ninserted)
+        atomicAdd(to.gh_nused, ninserted);
+#endif
 }
 
 /* ------------------------------------------------------------------
@@ -3551,7 +3742,10 @@ gpupreagg_import(pgs_gstate gs, const cl_ulong *records, cl_uint nrecords,
                       StromError_DataStoreNoSpace);
     }
     if (ninserted)
+    {
         atomicAdd(gs.gh_ngroups, ninserted);
+        atomicAdd(gs.gh_nused, ninserted);
+    }
 }
 
 /*
@@ -3614,7 +3808,314 @@ gpupreagg_import_blocks(pgs_gstate gs, const cl_ulong *blocks, cl_uint nranks,
         }
     }
     if (ninserted)
+    {
         atomicAdd(gs.gh_ngroups, ninserted);
+        atomicAdd(gs.gh_nused, ninserted);
+    }
+}
+
+/* ------------------------------------------------------------------
+ * Partitioned exchange of large states (~10 M groups): rank
+ * r ends up owning the groups whose key hash maps to r, so that after the
+ * exchange the ranks hold disjoint sets of groups and every rank flushes its
+ * own share.  Two passes over the state: pass 0 counts the records per
+ * destination, the host turns the counts into offsets, pass 1 writes the
+ * records bucket by bucket (one buffer, G runs).  The bucket comes from a
+ * re-mixed hash: the low bits pick the slot of the global table and the high
+ * bits the partition, neither may correlate with the rank.
+ * ------------------------------------------------------------------ */
+DEVFN cl_uint
+pgs_rank_of_hash(cl_ulong hash, cl_uint nranks)
+{
+    return pgs_fmix32((cl_uint)hash ^ 0x5bd1e995U) % nranks;
+}
+
+#define PGS_EXCHANGE_MAX_RANKS  16
+
+extern "C" __global__ void
+gpupreagg_export_parts(pgs_gstate gs, cl_ulong *records, cl_uint *counts,
+                       const cl_uint *offsets, cl_uint *cursors,
+                       cl_uint nranks, cl_uint pass)
+{
+#if GPUPREAGG_NUM_KEYS > 0
+    const cl_ulong  nstate = pgs_state_nslots(gs);
+    const cl_uint   lane_id = threadIdx.x & 31;
+
+    for (cl_ulong i0 = (cl_ulong)blockIdx.x * blockDim.x + (threadIdx.x & ~31U);
+         i0 < nstate;
+         i0 += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        const cl_ulong  i = i0 + lane_id;
+        cl_ulong    keys[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
+        cl_ulong    cells[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+        cl_uint     knull = 0, nn = 0;
+        bool        ready = (i < nstate && pgs_state_slot(gs, i, keys, cells, knull, nn));
+        cl_uint     dest = 0;
+        cl_uint     pos = 0;
+
+        if (ready)
+        {
+            cl_ulong kv[PGS_MAX(GPUPREAGG_NUM_KEYS, 1)];
+#pragma unroll
+            for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+                kv[k] = ((knull >> k) & 1U) ? 0 : keys[k];
+            dest = pgs_rank_of_hash(pgs_hash_keyvals(kv, knull), nranks);
+        }
+        /* positions are handed out once per warp and destination */
+        for (cl_uint d = 0; d < nranks; d++)
+        {
+            cl_uint votes = __ballot_sync(0xffffffffU, ready && dest == d);
+            cl_uint base = 0;
+
+            if (votes == 0)
+                continue;
+            if (lane_id == 0)
+                base = atomicAdd((pass == 0 ? counts : cursors) + d, (cl_uint)__popc(votes));
+            base = __shfl_sync(0xffffffffU, base, 0);
+            if (ready && dest == d)
+                pos = base + __popc(votes & ((1U << lane_id) - 1U));
+        }
+        if (ready && pass != 0)
+        {
+            cl_ulong *rec = records + (cl_ulong)(offsets[dest] + pos) * PGS_SLOT_WORDS;
+
+            rec[0] = ((cl_ulong)nn << 32) | (knull << 8) | PGS_SLOT_READY;
+#pragma unroll
+            for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+                rec[1 + k] = keys[k];
+#pragma unroll
+            for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                rec[1 + GPUPREAGG_NUM_KEYS + c] = cells[c];
+        }
+    }
+#endif
+}
+
+/* ------------------------------------------------------------------
+ * Merge of SMALL states over NVLink peer memory (no GROUP BY: one record;
+ * GROUP BY with a few thousand groups).  No collective library in the path:
+ *
+ *   every rank but the root : gpupreagg_peer_push writes its state records
+ *       straight into the root's exchange area (plain stores through the
+ *       NVLink-mapped pointer), resets its own state, and publishes
+ *       flag[rank] = epoch with a system-scope release;
+ *   the root : gpupreagg_peer_pull waits for the flags (system-scope
+ *       acquire), merges the records into its own state with the usual merge
+ *       rules and publishes done = epoch.
+ *
+ * Nothing waits for a collective rendezvous: a rank that is done scanning
+ * pushes and goes on with its next chunk; only the root waits, and only for
+ * data.  The area holds two buffers per rank (epoch parity); a rank re-uses
+ * a buffer only after the root has imported the epoch before last (`done`,
+ * read over NVLink).  Exchange area (in the root's HBM, 8-byte words):
+ *   [0]              done epoch
+ *   [16 + 16 r]      flag of rank r
+ *   [PGS_PEER_HEAD_WORDS ...]  2 x nranks blocks of (1 + cap) records; word 0
+ *                    of a block's first record = number of records
+ * ------------------------------------------------------------------ */
+#define PGS_PEER_HEAD_WORDS     (16 + 16 * PGS_EXCHANGE_MAX_RANKS)
+
+DEVFN cl_ulong
+pgs_ld_acquire_sys(const cl_ulong *p)
+{
+    cl_ulong v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+DEVFN void
+pgs_st_release_sys(cl_ulong *p, cl_ulong v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+DEVFN cl_ulong *
+pgs_peer_block(cl_ulong *area, cl_uint nranks, cl_uint cap, cl_ulong epoch, cl_uint rank)
+{
+    return area + PGS_PEER_HEAD_WORDS +
+        ((epoch & 1) * nranks + rank) * ((cl_ulong)(1 + cap) * PGS_SLOT_WORDS);
+}
+
+/* `local`: two words of this rank's own memory: [0] records written so far,
+ * [1] CTA ticket.  Launched with whole warps. */
+extern "C" __global__ void
+gpupreagg_peer_push(pgs_gstate gs, cl_ulong *area, cl_uint rank, cl_uint nranks,
+                    cl_uint cap, cl_ulong epoch, cl_uint *local)
+{
+    cl_ulong   *block = pgs_peer_block(area, nranks, cap, epoch, rank);
+    cl_ulong   *recs = block + PGS_SLOT_WORDS;
+    __shared__ cl_uint is_last;
+
+    /* the buffer was last used two epochs ago: has the root imported that? */
+    if (threadIdx.x == 0)
+        while (pgs_ld_acquire_sys(area) + 2 < epoch)
+            __nanosleep(200);
+    __syncthreads();
+    if (GPUPREAGG_NUM_KEYS == 0)
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+        {
+            recs[0] = (gs.ng_state[0] << 32) | PGS_SLOT_READY;
+            for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                recs[1 + c] = gs.ng_state[1 + c];
+            gs.ng_state[0] = 0;
+            pgs_cells_init(gs.ng_state + 1);
+            block[0] = 1;
+            __threadfence_system();
+            pgs_st_release_sys(area + 16 + 16 * rank, epoch);
+        }
+        return;
+    }
+#if GPUPREAGG_NUM_KEYS > 0
+    /* more records than a block takes (the estimate of the number of groups
+     * was far off): nothing moves, this rank flushes its own partial rows and
+     * PostgreSQL's final Agg merges them */
+    const cl_uint   nlog = min(*gs.ovf_count, gs.ovf_cap);
+    const bool      fits = ((cl_ulong)*gs.gh_nused + nlog <= cap) && gs.part_nparts == 0;
+    const cl_ulong  n = (fits ? (cl_ulong)gs.gh_nslots + nlog : 0);
+    const cl_uint   lane_id = threadIdx.x & 31;
+
+    for (cl_ulong i0 = (cl_ulong)blockIdx.x * blockDim.x + (threadIdx.x & ~31U);
+         i0 < n;
+         i0 += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        const cl_ulong  i = i0 + lane_id;
+        const cl_ulong *src = NULL;
+        cl_ulong        ctrl = 0;
+        bool            ready = false;
+        cl_uint         votes, base = 0;
+
+        if (i < gs.gh_nslots)
+        {
+            cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_STRIDE;
+
+            ctrl = slot[0];
+            ready = (((cl_uint)ctrl & 3U) == PGS_SLOT_READY);
+            src = slot;
+        }
+        else if (i < n)
+        {
+            src = gs.ovf_recs + (i - gs.gh_nslots) * PGS_SLOT_WORDS;
+            ctrl = src[0];
+            ready = true;
+        }
+        votes = __ballot_sync(0xffffffffU, ready);
+        if (lane_id == 0 && votes != 0)
+            base = atomicAdd(local, (cl_uint)__popc(votes));
+        base = __shfl_sync(0xffffffffU, base, 0);
+        if (ready)
+        {
+            cl_ulong *rec = recs + (cl_ulong)(base + __popc(votes & ((1U << lane_id) - 1U))) * PGS_SLOT_WORDS;
+
+            /* (a table slot keeps its NULL-key bits from bit 8 like a record) */
+            rec[0] = ctrl;
+#pragma unroll
+            for (int w = 1; w < PGS_SLOT_WORDS; w++)
+                rec[w] = src[w];
+            if (i < gs.gh_nslots)
+            {
+                /* the group now lives on the root */
+                cl_ulong *slot = gs.gh_slots + i * PGS_SLOT_STRIDE;
+
+                slot[0] = 0;
+#pragma unroll
+                for (int k = 0; k < GPUPREAGG_NUM_KEYS; k++)
+                    slot[1 + k] = 0;
+                pgs_cells_init(slot + 1 + GPUPREAGG_NUM_KEYS);
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        is_last = (atomicAdd(local + 1, 1U) == gridDim.x - 1 ? 1U : 0U);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0)
+    {
+        __threadfence();
+        block[0] = *((volatile cl_uint *)local);
+        if (fits)
+        {
+            *gs.gh_ngroups = 0;
+            *gs.gh_nused = 0;
+            *gs.ovf_count = 0;
+        }
+        local[0] = 0;
+        local[1] = 0;
+        __threadfence_system();
+        pgs_st_release_sys(area + 16 + 16 * rank, epoch);
+    }
+#endif
+}
+
+extern "C" __global__ void
+gpupreagg_peer_pull(pgs_gstate gs, cl_ulong *area, cl_uint root, cl_uint nranks,
+                    cl_uint cap, cl_ulong epoch, cl_uint *local,
+                    kern_gpupreagg *kgpreagg)
+{
+    __shared__ cl_uint is_last;
+    cl_uint     ninserted = 0;
+
+    for (cl_uint r = 0; r < nranks; r++)
+    {
+        const cl_ulong *block = pgs_peer_block(area, nranks, cap, epoch, r);
+        const cl_ulong *recs = block + PGS_SLOT_WORDS;
+        cl_uint         n;
+
+        if (r == root)
+            continue;
+        if (threadIdx.x == 0)
+            while (pgs_ld_acquire_sys(area + 16 + 16 * r) < epoch)
+                __nanosleep(100);
+        __syncthreads();
+        /* written by another GPU: read at the L2, never from this SM's L1 */
+        n = min((cl_uint)__ldcg(block), cap);
+        if (GPUPREAGG_NUM_KEYS == 0)
+        {
+            /* one thread, rank order: deterministic */
+            if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0)
+            {
+                cl_ulong    src[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+                cl_uint     src_nn = (cl_uint)(__ldcg(recs) >> 32);
+#pragma unroll
+                for (int c = 0; c < GPUPREAGG_NUM_CELLS; c++)
+                    src[c] = __ldcg(recs + 1 + c);
+                gpupreagg_aggmerge_plain(gs.ng_state + 1, src, src_nn);
+                gs.ng_state[0] = (cl_uint)gs.ng_state[0] | src_nn;
+            }
+            continue;
+        }
+#if GPUPREAGG_NUM_KEYS > 0
+        for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+             i += (cl_ulong)gridDim.x * blockDim.x)
+        {
+            cl_ulong    rec[PGS_SLOT_WORDS];
+            cl_uint     knull;
+
+#pragma unroll
+            for (int w = 0; w < PGS_SLOT_WORDS; w++)
+                rec[w] = __ldcg(recs + i * PGS_SLOT_WORDS + w);
+            knull = ((cl_uint)rec[0] >> 8) & ((1U << GPUPREAGG_NUM_KEYS) - 1U);
+            if (!pgs_gh_merge_state(gs, rec + 1, knull, pgs_hash_keyvals(rec + 1, knull),
+                                    rec + 1 + GPUPREAGG_NUM_KEYS,
+                                    (cl_uint)(rec[0] >> 32), ninserted))
+                atomicCAS(&kgpreagg->status, StromError_Success, StromError_DataStoreNoSpace);
+        }
+#endif
+    }
+    if (ninserted)
+    {
+        atomicAdd(gs.gh_ngroups, ninserted);
+        atomicAdd(gs.gh_nused, ninserted);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        is_last = (atomicAdd(local + 1, 1U) == gridDim.x - 1 ? 1U : 0U);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0)
+    {
+        local[1] = 0;
+        __threadfence_system();
+        pgs_st_release_sys(area, epoch);
+    }
 }
 
 /* ------------------------------------------------------------------

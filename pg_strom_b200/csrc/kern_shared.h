@@ -15,7 +15,19 @@ typedef struct
     cl_ulong   *gh_slots;       /* [gh_nslots][PGS_SLOT_WORDS] */
     cl_uint     gh_nslots;      /* power of 2 */
     cl_uint     gh_max_probe;
-    cl_uint    *gh_ngroups;     /* number of READY slots */
+    cl_uint    *gh_ngroups;     /* groups inserted anywhere (table, images) */
+    cl_uint    *gh_nused;       /* READY slots of the global table alone */
+    /* overflow log: state records (the exported record format) that found no
+     * room in the global table - a CTA-local table spilled at the end of a
+     * launch, or an imported record, when the planner's estimate of the
+     * number of groups was too low.  They are part of the state (flush and
+     * export walk them; PostgreSQL's final Agg merges partial rows of one
+     * key), and the host folds them into a larger table as soon as it sees
+     * the counter move (session_grow_table). */
+    cl_ulong   *ovf_recs;       /* [ovf_cap][PGS_SLOT_WORDS] */
+    cl_uint    *ovf_count;
+    cl_uint     ovf_cap;
+    cl_uint     ovf_pad;
     /* group-by with very many groups: rows are first dealt into partitions
      * (by the high bits of the key hash), then every partition is
      * aggregated in shared memory into its own persistent table image */

@@ -430,6 +430,12 @@ class GpuPreAggState:
         self.typmods = [c.get("typmod", -1) for c in self.desc["columns"]]
         self._chunks = iter(chunks)
         self._held = []
+        self.released = []          # addresses of the chunks handed back so far
+
+        def release(_arg, kds):
+            self.released.append(int(kds or 0))
+
+        self._release = _capi.RELEASE_FN(release)
 
         def child_exec(_state, slot_p):
             slot = slot_p.contents
@@ -444,6 +450,8 @@ class GpuPreAggState:
                 ds, rowmap = item, None
             self._held.append(ds)
             slot.kds = ds.ptr
+            slot.release = self._release
+            slot.release_arg = None
             if rowmap is not None:
                 rm = np.concatenate([np.array([len(rowmap)], dtype=np.int32),
                                      np.asarray(rowmap, dtype=np.int32)])
@@ -484,6 +492,13 @@ class GpuPreAggState:
         rows = (C.c_uint32 * n)()
         self.lib.gpupreagg_recheck_rows(self.state, seq, rows, n)
         return [(int(seq[i]), int(rows[i])) for i in range(n)]
+
+    def recheck_chunk(self, seq):
+        """Address of the retained chunk `seq` (0 = not held)."""
+        return int(self.lib.gpupreagg_recheck_chunk(self.state, seq, None) or 0)
+
+    def recheck_done(self, seq):
+        check(self.lib.gpupreagg_recheck_done(self.state, seq))
 
     def explain(self, verbose=False, analyze=False):
         return self.lib.gpupreagg_explain(self.state, int(verbose), int(analyze)).decode()
@@ -609,9 +624,13 @@ class Session:
 
     def finish(self, reset=True, nrooms=None):
         """Partial rows of everything submitted so far, decoded."""
+        buf, kds = self.finish_raw(reset, nrooms)
+        return self.decode_rows(buf, kds)
+
+    def decode_rows(self, buf, kds):
+        """The rows of a TUPSLOT store finish_raw() returned, as python tuples."""
         lib = self.lib
         ncols = len(self.coltypes)
-        buf, kds = self.finish_raw(reset, nrooms)
         values = (C.c_uint64 * ncols)()
         isnull = C.create_string_buffer(ncols)
         rows = []

@@ -63,3 +63,78 @@ def max_over_ranks(dist, value, device=None):
         t = t.to(device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def allgather_bytes(dist, payload, nbytes, device=None):
+    """[bytes of rank 0, bytes of rank 1, ...]: every rank contributes
+    `nbytes` bytes (CUDA IPC handles of the exchange areas)."""
+    import torch
+    raw = bytes(payload)[:nbytes].ljust(nbytes, b"\0")
+    mine = torch.tensor(list(raw), dtype=torch.uint8)
+    if device is not None:
+        mine = mine.to(device)
+    outs = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, mine)
+    return [bytes(t.cpu().numpy().tobytes()) for t in outs]
+
+
+def choose_merge(needs_grouping, gh_nslots, part_nparts):
+    """How the per-GPU states come together before the final Agg:
+      'peer'     - no GROUP BY (one record) or a table of at most 64K slots:
+                   the ranks push their records into the root's HBM over
+                   NVLink peer memory, the root merges (pgs_preagg_merge_peer)
+      'exchange' - larger states: the groups are partitioned over the ranks
+                   by key hash (pgs_preagg_merge_exchange), every rank
+                   flushes its own share"""
+    if not needs_grouping:
+        return "peer"
+    if part_nparts == 0 and gh_nslots <= 65536:
+        return "peer"
+    return "exchange"
+
+
+class StateMerge:
+    """The merge step of one session per rank.  `ctx` carries rank, world,
+    dist (torch.distributed, plumbing only), dev and the NCCL communicator
+    `comm` of the C ABI (used by the partitioned exchange)."""
+
+    def __init__(self, lib, sess, ctx, root=0, mode=None):
+        from . import _capi
+        self.lib, self.sess, self.ctx, self.root = lib, sess, ctx, root
+        pm = sess.perfmon()
+        self.mode = mode or choose_merge(bool(sess.desc["needs_grouping"]),
+                                         pm["gh_nslots"], pm["part_nparts"])
+        if self.mode == "peer":
+            handle = C.create_string_buffer(64)
+            _capi.check(lib.pgs_preagg_peer_setup(sess.handle, ctx.rank, ctx.world, root, handle))
+            handles = allgather_bytes(ctx.dist, handle.raw, 64, ctx.dev)
+            if ctx.rank != root:
+                buf = C.create_string_buffer(handles[root], 64)
+                _capi.check(lib.pgs_preagg_peer_attach(sess.handle, buf))
+            ctx.dist.barrier()
+
+    def run(self):
+        from . import _capi
+        if self.mode == "peer":
+            _capi.check(self.lib.pgs_preagg_merge_peer(self.sess.handle))
+        else:
+            _capi.check(self.lib.pgs_preagg_merge_exchange(self.sess.handle, self.ctx.comm,
+                                                           self.ctx.rank, self.ctx.world))
+
+    def describe(self):
+        if self.mode == "peer":
+            return ("NVLink peer memory: ranks push their state records into the root's HBM "
+                    "(gpupreagg_peer_push), the root merges (gpupreagg_peer_pull); no collective")
+        return ("hash-partitioned exchange: gpupreagg_export_parts + ncclSend/ncclRecv all-to-all "
+                "+ gpupreagg_import; every rank flushes its own share of the groups")
+
+    def trace(self):
+        pm = self.sess.perfmon()
+        n = max(pm.get("merge_count", 0), 1)
+        return {"mode": self.mode, "merges": pm.get("merge_count", 0),
+                "merge_kernel_ms_mean": pm.get("merge_kernel_ms", 0.0) / n,
+                "merge_exchange_host_ms_mean": pm.get("merge_exchange_ms", 0.0) / n,
+                "table_grown": pm.get("num_table_grown", 0)}
+
+    def close(self):
+        pass

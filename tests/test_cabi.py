@@ -116,15 +116,16 @@ def test_programs_build_for_sm_100a(lib):
 
 
 def test_gather_payload_variant_builds(lib, monkeypatch):
-    """PGSTROM_GATHER_PAYLOAD=1 (experimental, off by default): only the
-    qual's columns are staged; the variant applies to GROUP BY under a WHERE
-    clause and must leave every other program as it is."""
+    """GROUP BY under a WHERE clause stages only the qual's columns
+    (PGSTROM_GATHER_PAYLOAD=0 switches back to staging every column); every
+    other program is the same either way."""
     gucs = {"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on"}
+    monkeypatch.setenv("PGSTROM_GATHER_PAYLOAD", "0")
     plan = gp.Plan(W.where_plan(), gucs=gucs)
     base = plan.kernel_source()
     plan.free()
     assert "#define GPUPREAGG_GATHER_PAYLOAD 0" in base
-    monkeypatch.setenv("PGSTROM_GATHER_PAYLOAD", "1")
+    monkeypatch.delenv("PGSTROM_GATHER_PAYLOAD")
     plan = gp.Plan(W.where_plan(), gucs=gucs)
     src = plan.kernel_source()
     assert "#define GPUPREAGG_GATHER_PAYLOAD 1" in src

@@ -146,15 +146,16 @@ def test_where_many_groups(cuda):
     assert pm["sh_nslots"] == 0 and pm["part_nparts"] > 0
 
 
-@pytest.mark.skipif(os.environ.get("PGSTROM_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental kernel variant: set PGSTROM_TEST_EXPERIMENTAL=1")
-def test_where_gather_payload_variant(cuda, monkeypatch):
-    """PGSTROM_GATHER_PAYLOAD=1: the ring carries only the qual's column,
-    survivors gather key / v / w from HBM by row number.  Same results."""
-    monkeypatch.setenv("PGSTROM_GATHER_PAYLOAD", "1")
+@pytest.mark.parametrize("gather", ["1", "0"])
+def test_where_gather_payload_variant(cuda, monkeypatch, gather):
+    """GROUP BY under WHERE, both flavours of the scan: the ring carries only
+    the qual's column and survivors gather key / v / w from HBM by row number
+    (the default), or every column is staged (PGSTROM_GATHER_PAYLOAD=0).
+    Same results."""
+    monkeypatch.setenv("PGSTROM_GATHER_PAYLOAD", gather)
     ng, rows, pm = _run("where_agg", 2_000_000, 1_000_000)
-    assert ng == 1000 and pm["tile_rows"] > 4096
-    _run("where_agg", 700_001, 233_333, col_kw={"with_nulls": True})
+    assert ng == 1000 and (pm["tile_rows"] > 4096) == (gather == "1")
+    _run("where_agg", 700_002, 233_332, col_kw={"with_nulls": True})
     for pct in (1, 50, 100):
         _run("where_agg", 400_000, 400_000, plan_kw={"selectivity_pct": pct})
     for n in (4, 100, 2048, 8193):

@@ -194,13 +194,26 @@ def test_math_domain_errors_are_rechecked(cuda):
         xm = np.array([r[0] is None for r in rows], dtype=np.uint8)
         ds = gp.DataStore(coltypes, [(xs, xm), (np.array([r[1] for r in rows], np.int32), None)],
                           nrows=len(rows))
-        st = gp.GpuPreAggState(plan, [ds])
+        clean = gp.DataStore(coltypes, [(np.full(64, 16.0), None), (np.zeros(64, np.int32), None)],
+                             nrows=64)
+        st = gp.GpuPreAggState(plan, [ds, clean])
         try:
             device_rows = st.fetch_all()
             recheck = sorted(r for _s, r in st.recheck_rows())
+            # the chunk with re-check rows (sequence number 0) stays with the
+            # node until the host has walked it; the clean one went back at once
+            assert {s for s, _r in st.recheck_rows()} == {0}
+            assert st.released == [clean.ptr]
+            assert st.recheck_chunk(0) == ds.ptr and st.recheck_chunk(1) == 0
+            st.recheck_done(0)
+            assert st.released == [clean.ptr, ds.ptr] and st.recheck_chunk(0) == 0
+            with pytest.raises(gp._capi.StromError):
+                st.recheck_done(0)
         finally:
             st.end()
         ds.free()
+        clean.free()
+        rows = rows + [(16.0, 0)] * 64
     finally:
         plan.free()
     bad = [i for i, r in enumerate(rows) if r[0] is not None and r[0] <= 0.0]

@@ -109,3 +109,97 @@ def test_admin_views_and_abort(cuda):
     finally:
         sess.close()
         plan.free()
+
+
+@pytest.mark.parametrize("name,plan_kw,col_kw", [
+    ("nogrp_agg", {}, {}),
+    ("where_agg", {}, {}),
+    ("where_agg", {}, {"with_nulls": True}),
+])
+def test_peer_merge_three_ranks_one_device(cuda, name, plan_kw, col_kw):
+    """pgs_preagg_merge_peer (gpupreagg_peer_push / _pull): three sessions act
+    as the ranks of one merge on ONE device - the exchange area is plain device
+    memory there, over NVLink it is the root's HBM mapped into the peers.  Four
+    scans in a row: the areas' two buffers per rank are re-used, the epochs
+    keep them apart, and the root returns the partial rows of all shards."""
+    lib = gp._capi.load()
+    plan = gp.Plan(W.WORKLOADS[name]["plan"](**plan_kw), gucs=GUCS)
+    node = plan.tree()["lefttree"]
+    ranks = [gp.Session(plan) for _ in range(3)]
+    held = []
+    try:
+        for r, s in enumerate(ranks):
+            gp.check(lib.pgs_preagg_peer_setup(s.handle, r, 3, 0, None))
+        for s in ranks[1:]:
+            gp.check(lib.pgs_preagg_peer_attach_session(s.handle, ranks[0].handle))
+        for scan in range(4):
+            shards = []
+            for r, s in enumerate(ranks):
+                n = 200_000 + 40 * r + 4 * scan
+                ds, cols = W.make_chunk(name, 4_000_000 * scan + 1_000_000 * r, n, **col_kw)
+                held.append(ds)
+                shards.append(cols)
+                s.submit(ds)
+            # the pushes are queued before the root's pull: on one device the
+            # pull would otherwise wait for kernels that cannot start
+            for s in ranks[1:]:
+                gp.check(lib.pgs_preagg_merge_peer(s.handle))
+            gp.check(lib.pgs_preagg_merge_peer(ranks[0].handle))
+            rows = ranks[0].finish()
+            bench_oracle.assert_partial_equal_node(plan.describe(), node, rows, _concat(shards))
+            for s in ranks[1:]:
+                left = s.finish()
+                if plan.describe()["needs_grouping"]:
+                    assert left == []
+                else:
+                    assert len(left) == 1       # the identity state: count 0, sums NULL
+    finally:
+        for s in ranks:
+            s.close()
+        for ds in held:
+            ds.free()
+        plan.free()
+
+
+def _without_rows(cols, drop):
+    keep = np.ones(len(cols[0][0]), bool)
+    keep[np.asarray(drop, dtype=np.int64)] = False
+    return [(v[keep], None if m is None else m[keep]) for v, m in cols]
+
+
+@pytest.mark.parametrize("name,plan_groups,data_groups", [
+    ("where_agg", 1000, 60_000),            # CTA-local tables + a global table for 1000
+    ("where_agg", 20, 3_000),
+    ("high_cardinality", 70_000, 900_000),  # partitions and images sized for 70 K
+])
+def test_group_estimate_far_too_low(cuda, name, plan_groups, data_groups):
+    """The planner's numGroups is an estimate (PostgreSQL's default for an
+    expression is 200); the reference never depends on it - every chunk is
+    reduced on its own (gpupreagg.c:2169-2186).  Here the tables are sized
+    from it, so a scan that meets 45-60 times the groups must still finish:
+    what finds no room goes to the overflow log, the table is replaced by a
+    larger one between chunks (session_grow_table), and rows that find no room
+    at all are handed to the host as re-check rows - never an error."""
+    plan = gp.Plan(W.WORKLOADS[name]["plan"](num_groups=plan_groups), gucs=GUCS)
+    node = plan.tree()["lefttree"]
+    sess = gp.Session(plan)
+    held, shards = [], []
+    try:
+        for i in range(4):
+            ds, cols = W.make_chunk(name, 2_000_000 * i, 400_000, num_groups=data_groups)
+            held.append(ds)
+            t = sess.submit(ds)
+            st = sess.wait(t)
+            assert st in (0, 2), st            # StromError_CpuReCheck = 2
+            drop = sess.recheck_rows(t) if st == 2 else []
+            shards.append(_without_rows(cols, drop) if drop else cols)
+        rows = sess.finish()
+        pm = sess.perfmon()
+        assert pm["num_table_grown"] >= 1
+        ng = bench_oracle.assert_partial_equal_node(plan.describe(), node, rows, _concat(shards))
+        assert ng > 5 * plan_groups
+    finally:
+        sess.close()
+        for ds in held:
+            ds.free()
+        plan.free()

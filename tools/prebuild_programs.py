@@ -68,11 +68,21 @@ def workload_sources():
                 ("high_cardinality", {"num_groups": 100_000}),
                 ("high_cardinality", {"num_groups": 150_000})]
     for name, kw in variants:
-        plan = gp.Plan(W.WORKLOADS[name]["plan"](**kw), gucs=GUCS)
-        try:
-            out.append((plan.kernel_source(), plan.extra_flags()))
-        finally:
-            plan.free()
+        # where_agg: both flavours of the scan (see test_where_gather_payload_variant)
+        for gather in ((None, "0") if name == "where_agg" else (None,)):
+            old = os.environ.pop("PGSTROM_GATHER_PAYLOAD", None)
+            if gather is not None:
+                os.environ["PGSTROM_GATHER_PAYLOAD"] = gather
+            try:
+                plan = gp.Plan(W.WORKLOADS[name]["plan"](**kw), gucs=GUCS)
+                try:
+                    out.append((plan.kernel_source(), plan.extra_flags()))
+                finally:
+                    plan.free()
+            finally:
+                os.environ.pop("PGSTROM_GATHER_PAYLOAD", None)
+                if old is not None:
+                    os.environ["PGSTROM_GATHER_PAYLOAD"] = old
     return out
 
 
