@@ -617,6 +617,24 @@ def run_workload(ctx, name, sp, args, steps, warmup, want_cpu, headline):
     d2h = (pm3["bytes_dma_recv"] - pm2["bytes_dma_recv"]) // e2e_steps
     merge_trace = merge.trace() if merge else None
 
+    # ---- the platform's own ceiling for that copy: the same pinned chunks,
+    # plain cudaMemcpy into the resident buffers, all ranks at once ----
+    plain_gbs = None
+    if headline and not heap:       # (a heap chunk's pages do not sit behind its head)
+        scratch = lib.pgs_device_alloc(0, max(d.length for d in host_chunks))
+        assert scratch, lib.pgs_last_error()
+        nbytes = 0
+        barrier(ctx)
+        t0 = time.perf_counter()
+        for rep in range(2):
+            for ds in host_chunks:
+                _capi.check(lib.pgs_device_upload(0, scratch, ds.ptr, ds.length))
+                nbytes += ds.length
+        torch.cuda.synchronize()
+        barrier(ctx)
+        plain_gbs = nbytes / (max_over_ranks(ctx, time.perf_counter() - t0)) / 1e9
+        lib.pgs_device_free(0, scratch)
+
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and want_cpu:
@@ -658,12 +676,18 @@ def run_workload(ctx, name, sp, args, steps, warmup, want_cpu, headline):
                      "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "peak_source": peak_src, "kernel": kernel,
                      "launch_ms": k_ms, "bytes_per_launch": k_rows * alg_bytes_per_row,
-                     "launches_timed": n_k},
+                     "launches_timed": n_k,
+                     # bytes the kernel has to read as the chunks are laid out
+                     # (heap pages: tuple headers, line pointers, padding)
+                     "achieved_physical": (k_rows * (total_dev_bytes / float(rows)) /
+                                           (k_ms / 1000.0) / 1e9) if k_ms > 0 else 0.0},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "rows/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "h2d_gb_per_s": h2d / (e2e_ms / 1000.0) / 1e9,
-                "pcie_gen5_x16_frac": h2d / (e2e_ms / 1000.0) / 1e9 / 64.0},
+                "pcie_gen5_x16_frac": h2d / (e2e_ms / 1000.0) / 1e9 / 64.0,
+                "plain_copy_gb_per_s": plain_gbs,
+                "plain_copy_frac": (h2d / (e2e_ms / 1000.0) / 1e9 / plain_gbs) if plain_gbs else None},
         "gpu_launches": int(launches),
         "phase_ms": phase_ms,
         "merge_trace": merge_trace,

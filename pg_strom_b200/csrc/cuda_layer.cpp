@@ -700,6 +700,10 @@ pgs_device_upload(int device, void *dst_device, const void *src_host, size_t len
 /* ------------------------------------------------------------------
  * sessions
  * ------------------------------------------------------------------ */
+/* block size of the heap-page kernel: small blocks, so that the register file
+ * (not the block shape of the staged kernel) decides how many warps an SM holds */
+#define PGS_HEAP_BLOCK_THREADS  256
+
 struct ChunkResult
 {
     int32_t     status = 0;
@@ -714,6 +718,7 @@ struct ChunkSlot
     char       *d_kgpreagg = NULL;  /* kern_gpupreagg (status, kparams, row map) */
     char       *h_kgpreagg = NULL;  /* pinned image */
     size_t      kg_cap = 0;
+    cl_uint    *d_heap_index = NULL;/* heap pages: first row item of every page */
     cl_uint    *d_recheck = NULL;   /* 1 bit per row */
     size_t      recheck_words = 0;
     int32_t    *h_status = NULL;    /* pinned */
@@ -734,6 +739,7 @@ struct pgs_session
     pgs_program    *program = NULL;
     cudaLibrary_t   library = NULL;
     cudaKernel_t    k_main = NULL, k_rowmap = NULL, k_heap = NULL, k_partagg = NULL,
+                    k_heap_index = NULL, k_heap_staged = NULL,
                     k_init = NULL, k_flush = NULL, k_rehash = NULL,
                     k_export = NULL, k_import = NULL, k_import_blocks = NULL,
                     k_export_parts = NULL, k_peer_push = NULL, k_peer_pull = NULL,
@@ -750,6 +756,11 @@ struct pgs_session
     int             grid_main = 0;
     size_t          smem_main = 0;
     cl_uint         sh_nslots = 0;
+    int             grid_heap = 0;      /* heap-page kernel: no staging ring, more CTAs per SM */
+    size_t          smem_heap = 0;
+    cl_uint         heap_pps = 0;       /* staged heap kernel: pages per stage (0 = off) */
+    cl_uint         heap_nstages = 0;
+    size_t          smem_heap_staged = 0;
     int             grid_partagg = 0;
     size_t          smem_partagg = 0;
     cl_uint         tile_rows = 2048;
@@ -1065,6 +1076,12 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
     } while (0)
 
     OPEN_CHECK(cudaSetDevice(ord));
+    {
+        /* experiment: how much DRAM an L2 miss of a gathered sector pulls in */
+        const char *eg = getenv("PGSTROM_L2_FETCH_GRANULARITY");
+        if (eg && atoi(eg) > 0)
+            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(eg));
+    }
     OPEN_CHECK(cudaLibraryLoadData(&s->library, program->cubin.data(),
                                    NULL, NULL, 0, NULL, NULL, 0));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_main, s->library, "gpupreagg_main"));
@@ -1077,6 +1094,8 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_import, s->library, "gpupreagg_import"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_import_blocks, s->library, "gpupreagg_import_blocks"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_describe, s->library, "gpupreagg_describe"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_heap_index, s->library, "gpupreagg_heap_index"));
+    OPEN_CHECK(cudaLibraryGetKernel(&s->k_heap_staged, s->library, "gpupreagg_main_heap_staged"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_rehash, s->library, "gpupreagg_rehash"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_export_parts, s->library, "gpupreagg_export_parts"));
     OPEN_CHECK(cudaLibraryGetKernel(&s->k_peer_push, s->library, "gpupreagg_peer_push"));
@@ -1207,9 +1226,6 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
         OPEN_CHECK(cudaFuncSetAttribute((const void *)s->k_rowmap,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)s->smem_main));
-        OPEN_CHECK(cudaFuncSetAttribute((const void *)s->k_heap,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)s->smem_main));
         OPEN_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                        &per_sm, (const void *)s->k_main,
                        (int)s->desc.block_threads, s->smem_main));
@@ -1219,6 +1235,50 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
         if (env && atoi(env) > 0)
             per_sm = std::min(per_sm, atoi(env));
         s->grid_main = s->num_sms * per_sm;
+        /* the heap-page kernel reads the pages straight from HBM (a chain of
+         * dependent loads per tuple: row item, line pointer, header,
+         * attributes): it hides that latency with resident warps, not with a
+         * ring, so it only asks for the CTA-local table and the scratch of
+         * the block reduction and runs as many CTAs per SM as registers allow */
+        {
+            size_t scratch = 8 * (size_t)(1 + s->desc.num_cells) * (s->desc.block_threads / 32 + 1);
+            int heap_per_sm = 0;
+            s->smem_heap = head + std::max(table_bytes, scratch) + 128;
+            OPEN_CHECK(cudaFuncSetAttribute((const void *)s->k_heap,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)s->smem_heap));
+            OPEN_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                           &heap_per_sm, (const void *)s->k_heap,
+                           PGS_HEAP_BLOCK_THREADS, s->smem_heap));
+            s->grid_heap = s->num_sms * std::max(1, heap_per_sm);
+        }
+        /* heap pages through the ring (KDS_FORMAT_ROW without a row map):
+         * stages of 4 pages + their row items, as many as fit next to the
+         * CTA-local table (at least 3, else 2-page stages, else not at all) */
+        {
+            const char *eh = getenv("PGSTROM_HEAP_STAGED");
+            size_t budget = smem_max - head - table_bytes - 1024;
+            s->heap_pps = 0;
+            if (!(eh && atoi(eh) == 0))
+            {
+                for (cl_uint pps = 4; pps >= 2 && s->heap_pps == 0; pps -= 2)
+                {
+                    size_t sb = (size_t)pps * BLCKSZ +
+                        (((size_t)4 * (pps * 292 + 4) + 127) & ~(size_t)127) + 128;
+                    size_t n = std::min<size_t>(budget / sb, 8);
+                    if (n >= 3)
+                    {
+                        s->heap_pps = pps;
+                        s->heap_nstages = (cl_uint)n;
+                        s->smem_heap_staged = head + n * sb + table_bytes;
+                    }
+                }
+            }
+            if (s->heap_pps != 0)
+                OPEN_CHECK(cudaFuncSetAttribute((const void *)s->k_heap_staged,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)s->smem_heap_staged));
+        }
     }
     {
         int rc = session_alloc_state(s);
@@ -1455,12 +1515,15 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
     void *args[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck, &s->sh_nslots,
                      &s->tile_rows, &s->nstages };
     int grid = s->grid_main;
+    cl_uint no_stages = 0;
     if (use_heap)
     {
         /* one thread per tuple, grid-stride */
-        uint32_t nblk = (nitems + s->desc.block_threads - 1) / s->desc.block_threads;
+        uint32_t nblk = (nitems + PGS_HEAP_BLOCK_THREADS - 1) / PGS_HEAP_BLOCK_THREADS;
+        grid = s->grid_heap;
         if ((uint32_t)grid > nblk)
             grid = (int)std::max<uint32_t>(1, nblk);
+        args[6] = &no_stages;
     }
     else if (!use_rowmap)
     {
@@ -1470,8 +1533,32 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
     }
     if (s->perfmon)
         CUDA_CHECK(cudaEventRecord(sl.ev_k0, s->s_exec));
-    rc = launch_kernel(s, use_heap ? s->k_heap : (use_rowmap ? s->k_rowmap : s->k_main), grid,
-                       (int)s->desc.block_threads, s->smem_main, args);
+    if (format == KDS_FORMAT_ROW && !use_rowmap && s->heap_pps != 0)
+    {
+        /* pages through the staging ring: index of the first row item of
+         * every page, then the staged kernel (kern_gpupreagg.cuh) */
+        const size_t index_words = 65538;
+        if (!sl.d_heap_index)
+            CUDA_CHECK(cudaMalloc((void **)&sl.d_heap_index, index_words * 4));
+        CUDA_CHECK(cudaMemsetAsync(sl.d_heap_index, 0xff, (index_words - 1) * 4, s->s_exec));
+        CUDA_CHECK(cudaMemsetAsync(sl.d_heap_index + (index_words - 1), 0, 4, s->s_exec));
+        {
+            void *iargs[] = { (void *)&d_kds, &sl.d_heap_index };
+            int igrid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)s->num_sms * 8,
+                                                                      (nitems + 255) / 256));
+            rc = launch_kernel(s, s->k_heap_index, igrid, 256, 0, iargs);
+            if (rc != StromError_Success)
+                return rc;
+        }
+        void *hargs[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck, &s->sh_nslots,
+                          &s->heap_pps, &s->heap_nstages, &sl.d_heap_index };
+        rc = launch_kernel(s, s->k_heap_staged, s->num_sms, (int)s->desc.block_threads,
+                           s->smem_heap_staged, hargs);
+    }
+    else
+        rc = launch_kernel(s, use_heap ? s->k_heap : (use_rowmap ? s->k_rowmap : s->k_main), grid,
+                           use_heap ? PGS_HEAP_BLOCK_THREADS : (int)s->desc.block_threads,
+                           use_heap ? s->smem_heap : s->smem_main, args);
     if (rc != StromError_Success)
         return rc;
     if (s->gs.part_nparts != 0)
@@ -2398,6 +2485,9 @@ pgs_preagg_perfmon_json(pgs_session *s)
     o->set("merge_count", (long long)s->merge_count);
     o->set("merge_kernel_ms", pgs::Json::number(s->merge_ms[0]));
     o->set("merge_exchange_ms", pgs::Json::number(s->merge_ms[1]));
+    o->set("heap_pages_per_stage", (long long)s->heap_pps);
+    o->set("heap_num_stages", (long long)s->heap_nstages);
+    o->set("grid_heap", s->grid_heap);
     o->set("grid_main", s->grid_main);
     o->set("smem_main", (long long)s->smem_main);
     o->set("sh_nslots", (long long)s->sh_nslots);
@@ -2447,6 +2537,7 @@ pgs_preagg_close(pgs_session *s)
             if (sl.d_kgpreagg) cudaFree(sl.d_kgpreagg);
             if (sl.h_kgpreagg) cudaFreeHost(sl.h_kgpreagg);
             if (sl.d_recheck) cudaFree(sl.d_recheck);
+            if (sl.d_heap_index) cudaFree(sl.d_heap_index);
             if (sl.h_status) cudaFreeHost(sl.h_status);
             if (sl.ev_copied) cudaEventDestroy(sl.ev_copied);
             if (sl.ev_done) cudaEventDestroy(sl.ev_done);

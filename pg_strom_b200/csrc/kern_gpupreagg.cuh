@@ -1630,9 +1630,27 @@ pgs_part_write(const pgs_gstate &gs, const KDS &kds, cl_uint rowidx,
     GPUPREAGG_INCOL_LIST(PGS_X_INCOL_RECPUT)
     __w[PGS_REC_MASK_OFF / 4] = __mask;
     __w[PGS_REC_ROW_OFF / 4] = rownum;
+    if ((PGS_REC_BYTES & 31U) == 0)
+    {
+        /* whole 32-byte sectors: one 256-bit store each (STG.256, sm_100).
+         * L2 works on requests, not bytes: four 8-byte stores per record made
+         * the deal pass twice as slow as two 16-byte ones (measured) */
 #pragma unroll
-    for (int i = 0; i < (int)(PGS_REC_BYTES / 16); i++)
-        __rec[i] = make_uint4(__w[4 * i], __w[4 * i + 1], __w[4 * i + 2], __w[4 * i + 3]);
+        for (int i = 0; i < (int)(PGS_REC_BYTES / 32); i++)
+            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};"
+                         :: "l"((unsigned char *)__rec + 32 * i),
+                            "l"(((cl_ulong)__w[8 * i + 1] << 32) | __w[8 * i]),
+                            "l"(((cl_ulong)__w[8 * i + 3] << 32) | __w[8 * i + 2]),
+                            "l"(((cl_ulong)__w[8 * i + 5] << 32) | __w[8 * i + 4]),
+                            "l"(((cl_ulong)__w[8 * i + 7] << 32) | __w[8 * i + 6])
+                         : "memory");
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < (int)(PGS_REC_BYTES / 16); i++)
+            __rec[i] = make_uint4(__w[4 * i], __w[4 * i + 1], __w[4 * i + 2], __w[4 * i + 3]);
+    }
 }
 template <typename KDS>
 DEVFN bool
@@ -2868,6 +2886,28 @@ pgs_heap_chunk_init(pgs_heap_chunk &hc, const kern_data_store *kds)
     hc.length = kds->length;
 }
 
+/* tuple behind line pointer `item_offset` (1-based) of a heap page, or NULL
+ * (bytes available behind it in *p_avail); the page may sit in HBM or in a
+ * staged copy in shared memory */
+DEVFN const unsigned char *
+pgs_heap_page_tuple(const unsigned char *page, cl_uint item_offset, cl_uint *p_avail)
+{
+    cl_uint     lower, nlines, lp, off;
+
+    lower = *((const cl_ushort *)(page + PGS_PAGE_LOWER_OFF));
+    nlines = (lower <= PGS_PAGE_HEADER_SIZE ? 0 : (lower - PGS_PAGE_HEADER_SIZE) / 4);
+    if (PGS_PAGE_HEADER_SIZE + 4 * (nlines + 1) >= BLCKSZ ||
+        item_offset == 0 || item_offset > nlines)
+        return NULL;
+    lp = *((const cl_uint *)(page + PGS_PAGE_HEADER_SIZE) + (item_offset - 1));
+    off = PGS_ITEMID_OFFSET(lp);
+    if (PGS_ITEMID_FLAGS(lp) != PGS_LP_NORMAL || (off & 7U) != 0 ||
+        off + PGS_HTUP_BITS_OFF >= BLCKSZ)
+        return NULL;
+    *p_avail = BLCKSZ - off;
+    return page + off;
+}
+
 /* tuple of row `rowidx`, or NULL (bytes available behind it in *p_avail) */
 DEVFN const unsigned char *
 pgs_heap_tuple(const pgs_heap_chunk &hc, cl_uint rowidx, cl_uint *p_avail)
@@ -2882,27 +2922,10 @@ pgs_heap_tuple(const pgs_heap_chunk &hc, cl_uint rowidx, cl_uint *p_avail)
         *p_avail = hc.length - ri.htup_offset;
         return hc.base + ri.htup_offset;
     }
-    else
-    {
-        const unsigned char *page;
-        cl_uint     lower, nlines, lp, off;
-
-        if (ri.blk_index >= hc.nblocks)
-            return NULL;
-        page = hc.blocks + (cl_ulong)BLCKSZ * ri.blk_index;
-        lower = *((const cl_ushort *)(page + PGS_PAGE_LOWER_OFF));
-        nlines = (lower <= PGS_PAGE_HEADER_SIZE ? 0 : (lower - PGS_PAGE_HEADER_SIZE) / 4);
-        if (PGS_PAGE_HEADER_SIZE + 4 * (nlines + 1) >= BLCKSZ ||
-            ri.item_offset == 0 || ri.item_offset > nlines)
-            return NULL;
-        lp = *((const cl_uint *)(page + PGS_PAGE_HEADER_SIZE) + (ri.item_offset - 1));
-        off = PGS_ITEMID_OFFSET(lp);
-        if (PGS_ITEMID_FLAGS(lp) != PGS_LP_NORMAL || (off & 7U) != 0 ||
-            off + PGS_HTUP_BITS_OFF >= BLCKSZ)
-            return NULL;
-        *p_avail = BLCKSZ - off;
-        return page + off;
-    }
+    if (ri.blk_index >= hc.nblocks)
+        return NULL;
+    return pgs_heap_page_tuple(hc.blocks + (cl_ulong)BLCKSZ * ri.blk_index,
+                               ri.item_offset, p_avail);
 }
 
 /* VARSIZE_ANY (opencl_common.h:459-463) of a little-endian varlena */
@@ -2947,14 +2970,16 @@ template <> struct pgs_heap_load<1>
 #define PGS_X_INCOL_HEAPTAKEV(slot,colidx,attlen)                       \
     if (i == (cl_uint)(colidx))                                         \
     {                                                                   \
-        rr.v[slot] = (cl_ulong)(addr - (const unsigned char *)kds);     \
+        rr.v[slot] = htup_off + (cl_ulong)(addr - htup);                \
         rr.vbits[slot] = 1U;                                            \
     }
 
-/* false: the tuple does not fit what colmeta[] says (corruption) */
+/* false: the tuple does not fit what colmeta[] says (corruption).
+ * `htup` may be a staged copy; `htup_off` is where the tuple sits in the
+ * chunk (varlena values travel as chunk offsets and are read from HBM) */
 DEVFN bool
 pgs_heap_deform(const kern_data_store *kds, const unsigned char *htup,
-                cl_uint avail, kern_row_regs &rr)
+                cl_uint avail, kern_row_regs &rr, cl_ulong htup_off)
 {
     const cl_uint   infomask = *((const cl_ushort *)(htup + PGS_HTUP_INFOMASK_OFF));
     const cl_uint   natts = *((const cl_ushort *)(htup + PGS_HTUP_INFOMASK2_OFF)) & PGS_HEAP_NATTS_MASK;
@@ -3003,6 +3028,14 @@ pgs_heap_deform(const kern_data_store *kds, const unsigned char *htup,
         }
     }
     return true;
+}
+
+DEVFN bool
+pgs_heap_deform(const kern_data_store *kds, const unsigned char *htup,
+                cl_uint avail, kern_row_regs &rr)
+{
+    return pgs_heap_deform(kds, htup, avail, rr,
+                           (cl_ulong)(htup - (const unsigned char *)kds));
 }
 
 /*
@@ -3090,6 +3123,262 @@ gpupreagg_main_heap(kern_gpupreagg *kgpreagg,
 #else
         pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid, row, recheck_map);
 #endif
+    }
+    pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
+                      &head->is_last_cta, acc, acc_nn, ctx);
+}
+
+/* ------------------------------------------------------------------
+ * Heap pages through the staging ring (KDS_FORMAT_ROW without a row map).
+ *
+ * gpupreagg_main_heap reads every tuple where it lies in HBM: row item ->
+ * line pointer -> tuple header -> attributes, four dependent round trips per
+ * tuple, hidden only by the number of resident warps (measured 1.4 TB/s of
+ * physical bytes).  Here the pages themselves travel: the producer lane
+ * copies a run of whole pages and the slice of row items that points into
+ * them into a stage with two bulk copies (TMA), and the consumer threads
+ * de-form from shared memory.  Row items are written page by page
+ * (pgstrom_data_store_insert_block, datastore.c:556-710), so the rows of a
+ * run of pages are a contiguous run of row items; where it starts is what
+ * gpupreagg_heap_index finds in one pass over the row items:
+ *   first_row[b]       = first row item of page b (0xffffffff: none visible)
+ *   first_row[nblocks] = nitems
+ *   first_row[PGS_HEAP_INDEX_FLAG] != 0: the row items are not ordered by page
+ *       - the kernel then falls back to reading in place, like
+ *       gpupreagg_main_heap
+ * (the host presets the entries to 0xffffffff and the flag to 0)
+ * ------------------------------------------------------------------ */
+#define PGS_HEAP_INDEX_FLAG     65537       /* a chunk has at most 65536 pages */
+
+extern "C" __global__ void
+gpupreagg_heap_index(const kern_data_store *kds, cl_uint *first_row)
+{
+    const kern_rowitem *items = KERN_DATA_STORE_ROWITEM(kds, 0);
+    const cl_uint   nitems = kds->nitems;
+    const cl_uint   nblocks = kds->nblocks;
+
+    for (cl_ulong i = (cl_ulong)blockIdx.x * blockDim.x + threadIdx.x; i < nitems;
+         i += (cl_ulong)gridDim.x * blockDim.x)
+    {
+        cl_uint b = items[i].blk_index;
+        cl_uint prev = (i > 0 ? (cl_uint)items[i - 1].blk_index : 0xffffffffU);
+
+        if (b >= nblocks || (i > 0 && b < prev))
+            first_row[PGS_HEAP_INDEX_FLAG] = 1;
+        else if (b != prev)
+            first_row[b] = (cl_uint)i;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        first_row[nblocks] = nitems;
+}
+
+/* rows per page are bounded by the line pointer array: (8192 - 24) / (4 + 24) */
+#define PGS_HEAP_PAGE_MAXROWS   292
+/* stage: [pages | row items (+3 for the 16-byte alignment of the copy) | fr0, n] */
+#define PGS_HEAP_STAGE_BYTES(pps) \
+    ((pps) * BLCKSZ + PGS_ALIGN128(4 * ((pps) * PGS_HEAP_PAGE_MAXROWS + 4)) + 128)
+
+extern "C" __global__ void
+__launch_bounds__(GPUPREAGG_BLOCK_THREADS)
+gpupreagg_main_heap_staged(kern_gpupreagg *kgpreagg,
+                           const kern_data_store *kds_in,
+                           pgs_gstate gs,
+                           cl_uint *recheck_map,
+                           cl_uint sh_nslots,
+                           cl_uint pages_per_stage,
+                           cl_uint nstages,
+                           const cl_uint *first_row)
+{
+    pgs_smem_head  *head = (pgs_smem_head *)__pgs_smem;
+    unsigned char  *stages = __pgs_smem + PGS_SMEM_HEAD_BYTES;
+    const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF_CONST;
+    const cl_uint   nrows = kds_in->nitems;
+    const cl_uint   nblocks = kds_in->nblocks;
+    const cl_uint   stage_bytes = PGS_HEAP_STAGE_BYTES(pages_per_stage);
+    const cl_uint   ntiles = (nblocks + pages_per_stage - 1) / pages_per_stage;
+    const cl_uint   warp_id = threadIdx.x >> 5;
+    const cl_uint   lane_id = threadIdx.x & 31;
+    const unsigned char *blocks = (const unsigned char *)KERN_DATA_STORE_ROWBLOCK(kds_in, 0);
+    const kern_rowitem *items = KERN_DATA_STORE_ROWITEM(kds_in, 0);
+    const bool      ordered = (first_row[PGS_HEAP_INDEX_FLAG] == 0);
+    cl_ulong        acc[PGS_MAX(GPUPREAGG_NUM_CELLS, 1)];
+    cl_uint         acc_nn = 0;
+    pgs_row_ctx     ctx;
+    pgs_sh_table    sh;
+
+    ctx.nfiltered = 0;
+    ctx.nrecheck = 0;
+    ctx.ninserted = 0;
+    ctx.errcode = StromError_Success;
+    sh.base = PGS_SMEM_HEAD_BYTES + nstages * stage_bytes;
+    sh.nslots = (GPUPREAGG_NUM_KEYS > 0 ? sh_nslots : 0);
+    sh.salt = 1;
+    pgs_cells_init(acc);
+    if (threadIdx.x == 0)
+    {
+        for (cl_uint s = 0; s < nstages; s++)
+        {
+            pgs_mbar_init(&head->full_bar[s], 1);
+            pgs_mbar_init(&head->empty_bar[s], GPUPREAGG_CONSUMER_WARPS);
+        }
+        head->sh_nused = 0;
+        head->is_last_cta = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    PGS_SH_TABLE_INIT()
+    __syncthreads();
+
+    if (!ordered)
+    {
+        /* row items in some other order: every thread reads its tuple in place */
+        pgs_heap_chunk  hc;
+
+        pgs_heap_chunk_init(hc, kds_in);
+        for (cl_ulong base = (cl_ulong)blockIdx.x * blockDim.x + (threadIdx.x & ~31U);
+             base < nrows;
+             base += (cl_ulong)gridDim.x * blockDim.x)
+        {
+            cl_uint     row = (cl_uint)base + lane_id;
+            pagg_row    prow;
+            bool        valid = false;
+
+            if (row < nrows)
+            {
+                kern_row_regs   rr;
+                cl_uint         avail = 0;
+                const unsigned char *htup = pgs_heap_tuple(hc, row, &avail);
+
+                if (!htup || !pgs_heap_deform(kds_in, htup, avail, rr))
+                {
+                    if (ctx.errcode == StromError_Success)
+                        ctx.errcode = StromError_DataStoreCorruption;
+                }
+                else
+                    valid = pgs_eval_row(kparams, rr, kds_in, row, recheck_map, ctx, prow);
+            }
+#if GPUPREAGG_NUM_KEYS == 0
+            acc_nn |= gpupreagg_aggcalc_plain(acc, prow, valid);
+#else
+            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid, row, recheck_map);
+#endif
+        }
+    }
+    else if (warp_id == 0)
+    {
+        /* ===== producer warp: lane 0 feeds the ring ===== */
+        cl_uint it = 0;
+        for (cl_uint t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
+        {
+            if (lane_id == 0)
+            {
+                const cl_uint   stage = it % nstages;
+                const cl_uint   phase = (it / nstages) & 1;
+                const cl_uint   b0 = t * pages_per_stage;
+                const cl_uint   b1 = min(b0 + pages_per_stage, nblocks);
+                unsigned char  *stage_base = stages + stage * stage_bytes;
+                cl_uint        *meta = (cl_uint *)(stage_base + stage_bytes - 128);
+                cl_uint         fr0, fr1, bb, n, lead, ibytes;
+
+                /* first row item at or behind page b0 / b1 (pages without a
+                 * visible row carry no entry) */
+                for (bb = b0; bb < nblocks && __ldg(first_row + bb) == 0xffffffffU; bb++)
+                    ;
+                fr0 = __ldg(first_row + bb);
+                for (bb = b1; bb < nblocks && __ldg(first_row + bb) == 0xffffffffU; bb++)
+                    ;
+                fr1 = __ldg(first_row + bb);
+                n = (fr1 > fr0 ? fr1 - fr0 : 0);
+                if (n > pages_per_stage * PGS_HEAP_PAGE_MAXROWS)
+                    n = 0xffffffffU;        /* more rows than line pointers: not a heap chunk */
+                lead = fr0 & 3U;
+                ibytes = (n == 0xffffffffU ? 0 : ((lead + n) * 4 + 15U) & ~15U);
+                pgs_mbar_wait(&head->empty_bar[stage], phase ^ 1);
+                meta[0] = fr0;
+                meta[1] = n;
+                pgs_mbar_arrive_expect_tx(&head->full_bar[stage], (b1 - b0) * BLCKSZ + ibytes);
+                pgs_bulk_g2s(stage_base, blocks + (cl_ulong)b0 * BLCKSZ, (b1 - b0) * BLCKSZ,
+                             &head->full_bar[stage]);
+                if (ibytes != 0)
+                    pgs_bulk_g2s(stage_base + pages_per_stage * BLCKSZ,
+                                 (const unsigned char *)(items + (fr0 - lead)), ibytes,
+                                 &head->full_bar[stage]);
+            }
+            __syncwarp();
+        }
+    }
+    else
+    {
+        /* ===== consumer warps ===== */
+        const cl_uint   ctid = threadIdx.x - 32;
+        cl_uint         stage = 0, phase = 0;
+
+        for (cl_uint t = blockIdx.x; t < ntiles; t += gridDim.x, stage++)
+        {
+            if (stage == nstages)
+            {
+                stage = 0;
+                phase ^= 1;
+            }
+            const unsigned char *stage_base = stages + stage * stage_bytes;
+            const cl_uint  *meta = (const cl_uint *)(stage_base + stage_bytes - 128);
+            const cl_uint   b0 = t * pages_per_stage;
+            const cl_uint   npages = min(pages_per_stage, nblocks - b0);
+
+            pgs_mbar_wait(&head->full_bar[stage], phase);
+            const cl_uint   fr0 = meta[0];
+            const cl_uint   n = meta[1];
+            const kern_rowitem *sitems = (const kern_rowitem *)(stage_base + pages_per_stage * BLCKSZ) +
+                (fr0 & 3U);
+
+            if (n == 0xffffffffU)
+            {
+                if (ctx.errcode == StromError_Success)
+                    ctx.errcode = StromError_DataStoreCorruption;
+            }
+            else
+            {
+                /* warp-uniform trip count: the group path is warp-collective */
+                for (cl_uint i0 = (ctid & ~31U); i0 < n; i0 += GPUPREAGG_CONSUMER_THREADS)
+                {
+                    const cl_uint   i = i0 + lane_id;
+                    const cl_uint   row = fr0 + i;
+                    pagg_row        prow;
+                    bool            valid = false;
+
+                    if (i < n)
+                    {
+                        kern_rowitem    ri = sitems[i];
+                        cl_uint         pg = (cl_uint)ri.blk_index - b0;
+                        kern_row_regs   rr;
+                        cl_uint         avail = 0;
+                        const unsigned char *htup = NULL;
+
+                        if (pg < npages)
+                            htup = pgs_heap_page_tuple(stage_base + pg * BLCKSZ, ri.item_offset, &avail);
+                        if (!htup ||
+                            !pgs_heap_deform(kds_in, htup, avail, rr,
+                                             (cl_ulong)(blocks - (const unsigned char *)kds_in) +
+                                             (cl_ulong)ri.blk_index * BLCKSZ +
+                                             (cl_ulong)(htup - (stage_base + pg * BLCKSZ))))
+                        {
+                            if (ctx.errcode == StromError_Success)
+                                ctx.errcode = StromError_DataStoreCorruption;
+                        }
+                        else
+                            valid = pgs_eval_row(kparams, rr, kds_in, row, recheck_map, ctx, prow);
+                    }
+#if GPUPREAGG_NUM_KEYS == 0
+                    acc_nn |= gpupreagg_aggcalc_plain(acc, prow, valid);
+#else
+                    pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, valid, row, recheck_map);
+#endif
+                }
+            }
+            __syncwarp();
+            if (lane_id == 0)
+                pgs_mbar_arrive(&head->empty_bar[stage]);
+        }
     }
     pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
                       &head->is_last_cta, acc, acc_nn, ctx);

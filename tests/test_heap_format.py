@@ -138,3 +138,17 @@ def test_row_store_full(lib):
         assert lib.pgstrom_kds_row_insert_block(buf, ds._pages, offs, 4) == -1
     finally:
         ds.free()
+
+
+def test_row_store_block_limit(lib):
+    """kern_rowitem.blk_index has 16 bits (opencl_common.h:395-401): a
+    KDS_FORMAT_ROW chunk that would need more than 65536 block items is
+    refused instead of wrapping the page index."""
+    coltypes = ["int4"]
+    colmeta = gp.make_colmeta(coltypes)
+    ln = lib.pgstrom_kds_row_length(1, 65537, 10)
+    buf = C.create_string_buffer(int(ln))
+    assert lib.pgstrom_kds_row_init(buf, ln, 1, colmeta, 65537, 10) == 301
+    ln = lib.pgstrom_kds_row_length(1, 65536, 10)
+    buf = C.create_string_buffer(int(ln))
+    assert lib.pgstrom_kds_row_init(buf, ln, 1, colmeta, 65536, 10) == 0

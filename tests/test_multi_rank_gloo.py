@@ -52,6 +52,9 @@ def _worker(rank, world, port, chunk_rows, out_path):
     blob = multigpu.broadcast_bytes(dist, bytes(range(128)) if rank == 0 else b"", 128)
     assert blob == bytes(range(128))
     assert multigpu.max_over_ranks(dist, 1.0 + rank) == float(world)
+    # the CUDA IPC handles of the exchange areas travel like this (64 bytes per rank)
+    handles = multigpu.allgather_bytes(dist, bytes([rank + 1]) * 64, 64)
+    assert handles == [bytes([r + 1]) * 64 for r in range(world)]
 
     results = {}
     for sql in STATEMENTS:
@@ -103,6 +106,18 @@ def test_two_ranks_merge_like_one(tmp_path, lib):
         for g, e in zip(got, exp):
             for a, b in zip(g, e):
                 assert a == b or harness.cells_match(a, b, "float8"), (sql, g, e)
+
+
+def test_choose_merge():
+    """Which merge a session takes: one record or a small
+    table goes to the root over NVLink peer memory, millions of groups are
+    partitioned over the ranks."""
+    from pg_strom_b200 import multigpu
+    assert multigpu.choose_merge(False, 0, 0) == "peer"
+    assert multigpu.choose_merge(True, 4096, 0) == "peer"
+    assert multigpu.choose_merge(True, 65536, 0) == "peer"
+    assert multigpu.choose_merge(True, 131072, 0) == "exchange"
+    assert multigpu.choose_merge(True, 2048, 19532) == "exchange"
 
 
 def test_deal_chunks():

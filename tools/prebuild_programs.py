@@ -132,6 +132,14 @@ def main(jobs=None, force=False, quiet=False):
     if not force and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return 0
     t0 = time.time()
+    # binaries of earlier library builds can never be hit again (the key
+    # covers the runtime headers); they only bloat what travels to the GPU box
+    for fn in os.listdir(cache):
+        if fn.endswith(".cubin") or ".cubin.tmp" in fn:
+            try:
+                os.unlink(os.path.join(cache, fn))
+            except OSError:
+                pass
     items = regression_sources() + workload_sources() + extra_sources()
     uniq = list({hashlib.sha1((s + "|%d" % f).encode()).hexdigest(): (s, f)
                  for s, f in items}.values())
