@@ -297,6 +297,109 @@ cubin_file_write(const std::string &path, const std::string &key, const std::vec
         unlink(tmp.c_str());
 }
 
+/*
+ * NVRTC is resolved with dlopen, by absolute path first (the reference binds
+ * its vendor runtime the same way, opencl_entry.c).  A process that has
+ * another libnvrtc.so.12 mapped already - PyTorch preloads its bundled 12.8 -
+ * would otherwise hand us that copy through the SONAME, and the device code
+ * (256-bit global stores) needs the toolkit's 12.9 or later.  A path that
+ * does not match a loaded SONAME string is opened as its own object.
+ */
+static struct nvrtc_entry
+{
+    void       *handle;
+    std::string path;
+    nvrtcResult (*Version)(int *, int *);
+    const char *(*GetErrorString)(nvrtcResult);
+    nvrtcResult (*CreateProgram)(nvrtcProgram *, const char *, const char *, int,
+                                 const char *const *, const char *const *);
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char *const *);
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char *);
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char *);
+    nvrtcResult (*DestroyProgram)(nvrtcProgram *);
+} nvrtc;
+static std::once_flag nvrtc_once;
+
+static bool
+nvrtc_bind(void *h)
+{
+#define NVRTC_SYM(name) \
+    if (!(*(void **)(&nvrtc.name) = dlsym(h, "nvrtc" #name))) return false
+    NVRTC_SYM(Version);
+    NVRTC_SYM(GetErrorString);
+    NVRTC_SYM(CreateProgram);
+    NVRTC_SYM(CompileProgram);
+    NVRTC_SYM(GetProgramLogSize);
+    NVRTC_SYM(GetProgramLog);
+    NVRTC_SYM(GetCUBINSize);
+    NVRTC_SYM(GetCUBIN);
+    NVRTC_SYM(DestroyProgram);
+#undef NVRTC_SYM
+    return true;
+}
+
+static void
+nvrtc_load_once(void)
+{
+    std::vector<std::string> cands;
+    const char *e;
+    if ((e = getenv("PGSTROM_NVRTC_PATH")) && *e)
+        cands.push_back(e);
+    for (const char *var : { "CUDA_HOME", "CUDA_PATH" })
+        if ((e = getenv(var)) && *e)
+        {
+            cands.push_back(std::string(e) + "/lib64/libnvrtc.so.12");
+            cands.push_back(std::string(e) + "/lib64/libnvrtc.so");
+        }
+    cands.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+    cands.push_back("/usr/local/cuda/lib64/libnvrtc.so");
+    cands.push_back("libnvrtc.so.12");
+    cands.push_back("libnvrtc.so");
+    void       *fallback = NULL;
+    std::string fallback_path;
+    for (auto &c : cands)
+    {
+        void *h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+        int   major = 0, minor = 0;
+        if (!h)
+            continue;
+        if (!nvrtc_bind(h) || nvrtc.Version(&major, &minor) != NVRTC_SUCCESS)
+        {
+            dlclose(h);
+            continue;
+        }
+        if (major > 12 || (major == 12 && minor >= 9))
+        {
+            nvrtc.handle = h;
+            nvrtc.path = c;
+            return;
+        }
+        if (!fallback)
+        {
+            fallback = h;
+            fallback_path = c;
+        }
+    }
+    /* an older compiler: the device code falls back to 128-bit stores */
+    if (fallback && nvrtc_bind(fallback))
+    {
+        nvrtc.handle = fallback;
+        nvrtc.path = fallback_path;
+    }
+}
+
+static bool
+nvrtc_ready(void)
+{
+    std::call_once(nvrtc_once, nvrtc_load_once);
+    if (!nvrtc.handle)
+        set_error("NVRTC not found (tried $PGSTROM_NVRTC_PATH, $CUDA_HOME/lib64, "
+                  "/usr/local/cuda/lib64, the loader path): %s", dlerror());
+    return nvrtc.handle != NULL;
+}
+
 static std::string
 program_options(int extra_flags)
 {
@@ -334,32 +437,34 @@ nvrtc_build(pgs_program *prog)
     };
     if (!pgs::guc_bool("pg_strom.devprog_enable_optimization"))
         opts.push_back("-Xptxas=-O0");
+    if (!nvrtc_ready())
+        return StromError_ProgramBuildFailure;
     auto t0 = std::chrono::steady_clock::now();
-    nvrtcResult rc = nvrtcCreateProgram(&nprog, prog->source.c_str(), "gpupreagg.cu",
+    nvrtcResult rc = nvrtc.CreateProgram(&nprog, prog->source.c_str(), "gpupreagg.cu",
                                         (int)(sizeof(headers) / sizeof(headers[0])),
                                         headers, names);
     if (rc != NVRTC_SUCCESS)
     {
-        set_error("nvrtcCreateProgram: %s", nvrtcGetErrorString(rc));
+        set_error("nvrtcCreateProgram: %s", nvrtc.GetErrorString(rc));
         return StromError_ProgramBuildFailure;
     }
-    rc = nvrtcCompileProgram(nprog, (int)opts.size(), opts.data());
+    rc = nvrtc.CompileProgram(nprog, (int)opts.size(), opts.data());
     size_t logsz = 0;
-    nvrtcGetProgramLogSize(nprog, &logsz);
+    nvrtc.GetProgramLogSize(nprog, &logsz);
     prog->build_log.assign(logsz, '\0');
     if (logsz > 1)
-        nvrtcGetProgramLog(nprog, &prog->build_log[0]);
+        nvrtc.GetProgramLog(nprog, &prog->build_log[0]);
     if (rc != NVRTC_SUCCESS)
     {
-        set_error("device program build failure: %s", nvrtcGetErrorString(rc));
-        nvrtcDestroyProgram(&nprog);
+        set_error("device program build failure: %s", nvrtc.GetErrorString(rc));
+        nvrtc.DestroyProgram(&nprog);
         return StromError_ProgramBuildFailure;
     }
     size_t sz = 0;
-    nvrtcGetCUBINSize(nprog, &sz);
+    nvrtc.GetCUBINSize(nprog, &sz);
     prog->cubin.resize(sz);
-    nvrtcGetCUBIN(nprog, prog->cubin.data());
-    nvrtcDestroyProgram(&nprog);
+    nvrtc.GetCUBIN(nprog, prog->cubin.data());
+    nvrtc.DestroyProgram(&nprog);
     prog->build_ms = std::chrono::duration<double, std::milli>(
         std::chrono::steady_clock::now() - t0).count();
     return StromError_Success;
@@ -380,13 +485,15 @@ pgs_program_build(const char *kern_source, int extra_flags,
         set_error("pgs_program_build: bad arguments");
         return StromError_BadRequestMessage;
     }
+    if (!nvrtc_ready())
+        return StromError_ProgramBuildFailure;
     /* everything the binary depends on: the query's source and flags, the
      * build options, the static device runtime (a new library build must not
      * pick up stale binaries) and the compiler itself */
     {
         Sha256 sha;
         int nv_major = 0, nv_minor = 0;
-        nvrtcVersion(&nv_major, &nv_minor);
+        nvrtc.Version(&nv_major, &nv_minor);
         sha.field(kern_source, strlen(kern_source));
         sha.field(&extra_flags, sizeof(extra_flags));
         sha.field(options.data(), options.size());

@@ -1630,9 +1630,11 @@ pgs_part_write(const pgs_gstate &gs, const KDS &kds, cl_uint rowidx,
     GPUPREAGG_INCOL_LIST(PGS_X_INCOL_RECPUT)
     __w[PGS_REC_MASK_OFF / 4] = __mask;
     __w[PGS_REC_ROW_OFF / 4] = rownum;
+#if __CUDACC_VER_MAJOR__ > 12 || (__CUDACC_VER_MAJOR__ == 12 && __CUDACC_VER_MINOR__ >= 9)
     if ((PGS_REC_BYTES & 31U) == 0)
     {
-        /* whole 32-byte sectors: one 256-bit store each (STG.256, sm_100).
+        /* whole 32-byte sectors: one 256-bit store each (STG.256, sm_100;
+         * PTX ISA 8.8, i.e. NVRTC 12.9 or later).
          * L2 works on requests, not bytes: four 8-byte stores per record made
          * the deal pass twice as slow as two 16-byte ones (measured) */
 #pragma unroll
@@ -1646,6 +1648,7 @@ pgs_part_write(const pgs_gstate &gs, const KDS &kds, cl_uint rowidx,
                          : "memory");
     }
     else
+#endif
     {
 #pragma unroll
         for (int i = 0; i < (int)(PGS_REC_BYTES / 16); i++)
