@@ -1,4 +1,4 @@
-# usage: gpurun --gpus N --timeout T -- 'bash tools/gpu_r2_multi.sh N'
+# usage: gpurun --gpus N --timeout T -- 'bash tools/gpu_r2_multi.sh N [each|all]'
 # the merge paths on N GPUs, one workload at a time (a hang costs one timeout),
 # then the whole default line.
 N=$1
@@ -11,9 +11,13 @@ run() {  # tag, timeout, args...
       > gpurun_out/m${N}_$tag.json 2> gpurun_out/m${N}_$tag.err
   echo "rc=$?" >> gpurun_out/m${N}_$tag.err
 }
+if [ "$2" != "all" ]; then
 run nogrp 300 --workload nogrp_agg --steps 10 --warmup 3 --no-cpu-baseline
 run where 300 --workload where_agg --steps 5 --warmup 3 --no-cpu-baseline
 run hc 400 --workload high_cardinality --steps 3 --warmup 3 --no-cpu-baseline
 run heap 300 --workload nogrp_agg_heap --steps 5 --warmup 3 --no-cpu-baseline
+fi
+if [ "$2" != "each" ]; then
 run all 900 --steps 10 --warmup 3
+fi
 ls -la gpurun_out > gpurun_out/m${N}_ls.txt

@@ -71,16 +71,21 @@ def main():
             nrows_launch = int(n)
         hdr, units, rows = raw_page(path)
         lines = ["# ncu --set full --clock-control none, %s (%s)" % (name, os.path.basename(path))]
+        total, kernels = 0.0, []
         for r in rows:
             lines.append("kernel %s" % r[hdr.index("Kernel Name")])
+            kernels.append(r[hdr.index("Kernel Name")])
             for k in KEYS:
                 if k in hdr:
                     i = hdr.index(k)
                     lines.append("  %-86s %s %s" % (k, r[i], units[i]))
             rd = to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
             wr = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
-            traffic[name] = {"dram_bytes_per_launch": rd + wr, "rows_per_launch": nrows_launch,
-                             "source": os.path.basename(path)}
+            total += rd + wr
+            # a workload whose step is several kernels (deal + partagg, page
+            # index + heap scan): the sum over the kernels of one chunk
+            traffic[name] = {"dram_bytes_per_launch": total, "rows_per_launch": nrows_launch,
+                             "kernels": list(kernels), "source": os.path.basename(path)}
         with open(os.path.join(outdir, "%s_%s_ncu.txt" % (rnd, name)), "w") as f:
             f.write("\n".join(lines) + "\n")
     with open(tpath, "w") as f:
