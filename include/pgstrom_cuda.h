@@ -263,7 +263,11 @@ int         pgs_preagg_merge_nccl(pgs_session *session, void *nccl_comm,
  *   merge  : every rank, once per scan, before pgs_preagg_finish()
  * A rank whose state does not fit pushes nothing and keeps its groups: its
  * own flush returns them and PostgreSQL's final Agg merges the partial rows,
- * as the reference does for every chunk (gpupreagg.c:2169-2186). */
+ * as the reference does for every chunk (gpupreagg.c:2169-2186).
+ * A rank whose whole state went over has nothing left to flush: its
+ * pgs_preagg_finish() waits for its own chunks and returns zero rows without
+ * launching anything (the push kernel has already reset the state), so the
+ * other ranks run ahead of the root instead of holding it up. */
 int         pgs_preagg_peer_setup(pgs_session *session, int rank, int nranks,
                                   int root, void *ipc_handle_64);
 int         pgs_preagg_peer_attach(pgs_session *session,

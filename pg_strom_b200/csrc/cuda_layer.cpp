@@ -407,6 +407,8 @@ program_options(int extra_flags)
     (void)extra_flags;
     o += "warps=" + std::string(getenv("PGSTROM_CONSUMER_WARPS") ? getenv("PGSTROM_CONSUMER_WARPS") : "16");
     o += ";minctas=" + std::string(getenv("PGSTROM_MIN_CTAS") ? getenv("PGSTROM_MIN_CTAS") : "1");
+    if (getenv("PGSTROM_DEAL_STEPS"))
+        o += ";dealsteps=" + std::string(getenv("PGSTROM_DEAL_STEPS"));
     o += ";opt=" + std::string(pgs::guc_bool("pg_strom.devprog_enable_optimization") ? "1" : "0");
     if (getenv("PGSTROM_DEBUG_LEVEL"))      /* timing experiments only: wrong results */
         o += ";debug=" + std::string(getenv("PGSTROM_DEBUG_LEVEL"));
@@ -430,11 +432,16 @@ nvrtc_build(pgs_program *prog)
         std::string(getenv("PGSTROM_MIN_CTAS") ? getenv("PGSTROM_MIN_CTAS") : "1");
     std::string d_dbg = "-DGPUPREAGG_DEBUG_LEVEL=" +
         std::string(getenv("PGSTROM_DEBUG_LEVEL") ? getenv("PGSTROM_DEBUG_LEVEL") : "0");
+    std::string d_deal = "-DGPUPREAGG_DEAL_STEPS=" +
+        std::to_string(std::min(4, std::max(1, atoi(getenv("PGSTROM_DEAL_STEPS")
+                                                     ? getenv("PGSTROM_DEAL_STEPS") : "2"))));
     std::vector<const char *> opts = {
         "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
         "-device-int128", "--fmad=false",
         d_warps.c_str(), d_rpt.c_str(), d_dbg.c_str(),
     };
+    if (getenv("PGSTROM_DEAL_STEPS"))
+        opts.push_back(d_deal.c_str());
     if (!pgs::guc_bool("pg_strom.devprog_enable_optimization"))
         opts.push_back("-Xptxas=-O0");
     if (!nvrtc_ready())
@@ -909,6 +916,10 @@ struct pgs_session
     double          merge_ms[3] = {0, 0, 0};
     uint64_t        merge_count = 0;
     bool            merge_pending = false;  /* d_kg_misc carries the status of a merge */
+    /* a rank that pushed its whole state to the root has nothing to flush:
+     * the push kernel says so in a word of mapped pinned memory */
+    cl_uint        *h_moved = NULL;
+    bool            push_pending = false;
     std::string     perfmon_buf;
     bool            aborted = false;
 };
@@ -1527,6 +1538,7 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
         return StromError_BadRequestMessage;
     }
     CUDA_CHECK(cudaSetDevice(s->ordinal));
+    s->push_pending = false;    /* rows after a push: the state is not empty any more */
     pgs_ticket t = s->next_ticket;
     ChunkSlot &sl = s->slots[(size_t)(t % (pgs_ticket)s->slots.size())];
     int rc = slot_retire(s, sl);
@@ -1859,6 +1871,37 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     size_t first = std::min(total, STAGE_BYTES - 64);
 
     memset(&hdr, 0, sizeof(hdr));
+    if (s->push_pending)
+    {
+        /* this rank pushed its state to the root (pgs_preagg_merge_peer).
+         * When everything went over - always for a no-group state, for a
+         * GROUP BY state when it fitted the root's exchange area - there is
+         * nothing left to flush and the push kernel has reset the state: the
+         * rank only waits for its own chunks and returns an empty result.
+         * That keeps the ranks ahead of the root, which then never waits for
+         * a straggler's flush + read-back (measured at 8 GPUs: the root's
+         * merge kernel spent 0.07 ms per scan waiting) */
+        s->push_pending = false;
+        cudaError_t pe = cudaStreamSynchronize(s->s_exec);
+        if (pe != cudaSuccess)
+        {
+            set_error("pgs_preagg_finish: %s", cudaGetErrorString(pe));
+            return StromError_CudaInternal;
+        }
+        if (*((volatile cl_uint *)s->h_moved) == 1)
+        {
+            session_bury(s);
+            rc = drain(s);
+            if (rc != StromError_Success)
+                return rc;
+            kds_dst->nitems = 0;
+            if (nrows_needed)
+                *nrows_needed = 0;
+            if (status)
+                *status = StromError_Success;
+            return StromError_Success;
+        }
+    }
     /* the result store and the status word live as long as the session */
     if (s->d_result_cap < total)
     {
@@ -2005,6 +2048,8 @@ pgs_preagg_state_export(pgs_session *s, void *device_buf, size_t buflen,
 extern "C" int
 pgs_preagg_state_import(pgs_session *s, const void *device_buf, uint32_t nrecords)
 {
+    if (s)
+        s->push_pending = false;
     CUDA_CHECK(cudaSetDevice(s->ordinal));
     kern_gpupreagg *d_kg = NULL;
     int32_t h_status = 0;
@@ -2364,7 +2409,17 @@ pgs_preagg_merge_peer(pgs_session *s)
     merge_trace_begin(s);
     if (s->peer_rank != s->peer_root)
     {
-        void *args[] = { &s->gs, &s->peer_root_area, &rank, &nranks, &cap, &epoch, &local };
+        if (!s->h_moved)
+        {
+            CUDA_CHECK(cudaHostAlloc((void **)&s->h_moved, 64,
+                                     cudaHostAllocPortable | cudaHostAllocMapped));
+            *s->h_moved = 0;
+        }
+        cl_uint *d_moved = NULL;
+        CUDA_CHECK(cudaHostGetDevicePointer((void **)&d_moved, s->h_moved, 0));
+        void *args[] = { &s->gs, &s->peer_root_area, &rank, &nranks, &cap, &epoch, &local,
+                         &d_moved };
+        s->push_pending = true;
         int grid = (s->desc.num_keys == 0) ? 1 :
             std::max(1, std::min<int>(s->num_sms, (int)(((size_t)s->gs.gh_nslots + 255) / 256)));
         rc = launch_kernel(s, s->k_peer_push, grid, 256, 0, args);
@@ -2666,6 +2721,7 @@ pgs_preagg_close(pgs_session *s)
         if (s->d_result) cudaFree(s->d_result);
         if (s->d_kg_misc) cudaFree(s->d_kg_misc);
         if (s->h_result_head) cudaFreeHost(s->h_result_head);
+        if (s->h_moved) cudaFreeHost(s->h_moved);
         if (s->d_xchg) cudaFree(s->d_xchg);
         if (s->d_scratch) cudaFree(s->d_scratch);
         if (s->s_copy) cudaStreamDestroy(s->s_copy);

@@ -77,6 +77,10 @@
 /* 1 (experimental, PGSTROM_GATHER_PAYLOAD): only the columns the qual reads
  * are staged (GPUPREAGG_INCOL_STAGED(slot)); rows that pass the qual fetch
  * the others from HBM by row number */
+/* many-groups deal pass: 4-row batches a lane has under way at a time */
+#ifndef GPUPREAGG_DEAL_STEPS
+#define GPUPREAGG_DEAL_STEPS        2
+#endif
 #ifndef GPUPREAGG_GATHER_PAYLOAD
 #define GPUPREAGG_GATHER_PAYLOAD    0
 #endif
@@ -1086,6 +1090,12 @@ pgs_stage_nul_off(int slot, cl_uint tile_rows)
  *             survives several tiles never moves.
  */
 #define PGS_ROWQ_ENTRIES        256         /* power of two, > 31 + 128 */
+/* gather variant: steps of 128 rows a warp's share of one tile may have
+ * (one bit per row in a 32-bit mask); the host sizes the tiles accordingly */
+#define PGS_GATHER_MAX_STEPS    8
+#if GPUPREAGG_GATHER_PAYLOAD && GPUPREAGG_CONSUMER_WARPS < 8
+#error "the gather variant needs at least 8 consumer warps (tiles of 8192 rows, 8 steps per warp)"
+#endif
 #define PGS_ROWQ_LEFT           0x8000U
 #define PGS_ROWQ_LEFT_ENTRIES   64
 DEVFN cl_uint
@@ -1576,6 +1586,81 @@ struct kern_rec_gmem
     {
         out = *((const T *)(rec + pgs_rec_val_off(slot)));
         return ((*((const cl_uint *)(rec + PGS_REC_MASK_OFF)) >> slot) & 1U) != 0;
+    }
+};
+/* the same record held in registers (gpupreagg_partagg reads the records one
+ * batch ahead of the one it works on) */
+template <typename T, int SIZE> struct pgs_rec_bits;
+template <typename T> struct pgs_rec_bits<T, 8>
+{
+    static __device__ __forceinline__ T
+    get(const cl_uint *w, cl_uint off)
+    {
+        union { cl_ulong u; T t; } x;
+        x.u = ((cl_ulong)w[off / 4 + 1] << 32) | w[off / 4];
+        return x.t;
+    }
+};
+template <typename T> struct pgs_rec_bits<T, 4>
+{
+    static __device__ __forceinline__ T
+    get(const cl_uint *w, cl_uint off)
+    {
+        union { cl_uint u; T t; } x;
+        x.u = w[off / 4];
+        return x.t;
+    }
+};
+template <typename T> struct pgs_rec_bits<T, 2>
+{
+    static __device__ __forceinline__ T
+    get(const cl_uint *w, cl_uint off)
+    {
+        union { cl_ushort u; T t; } x;
+        x.u = (cl_ushort)(w[off / 4] >> (8 * (off & 3U)));
+        return x.t;
+    }
+};
+template <typename T> struct pgs_rec_bits<T, 1>
+{
+    static __device__ __forceinline__ T
+    get(const cl_uint *w, cl_uint off)
+    {
+        union { unsigned char u; T t; } x;
+        x.u = (unsigned char)(w[off / 4] >> (8 * (off & 3U)));
+        return x.t;
+    }
+};
+struct kern_rec_regs
+{
+    cl_uint     w[PGS_REC_BYTES / 4];
+
+    __device__ __forceinline__ void
+    load(const unsigned char *rec)
+    {
+#pragma unroll
+        for (int i = 0; i < (int)(PGS_REC_BYTES / 16); i++)
+        {
+            uint4   q = __ldcs((const uint4 *)rec + i);     /* read once: streaming */
+
+            w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+        }
+    }
+    __device__ __forceinline__ void
+    clear(void)
+    {
+#pragma unroll
+        for (int i = 0; i < (int)(PGS_REC_BYTES / 4); i++)
+            w[i] = 0;
+    }
+    __device__ __forceinline__ cl_uint rownum(void) const { return w[PGS_REC_ROW_OFF / 4]; }
+
+    template <typename T>
+    __device__ __forceinline__ bool
+    fetch(int slot, cl_uint rowidx, T &out) const
+    {
+        out = pgs_rec_bits<T, sizeof(T)>::get(w, pgs_rec_val_off(slot));
+        return ((w[PGS_REC_MASK_OFF / 4] >> slot) & 1U) != 0;
     }
 };
 #define PGS_X_INCOL_RECPUT(slot,colidx,attlen)                          \
@@ -2363,6 +2448,100 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                     }
                 }
             }
+#if GPUPREAGG_PARTITIONED
+            if (gs.part_nparts != 0)
+            {
+                /* very many groups: deal the rows into their partitions.
+                 * What a row costs here is the round trip of the atomic on
+                 * its partition's cursor (half of them to the far L2: ncu
+                 * shows 50% lookup misses on 100 M atomics, 60% of all warp
+                 * samples waiting for one), so a lane takes
+                 * GPUPREAGG_DEAL_STEPS x 4 rows at a time and has all their
+                 * atomics under way before the first record is written; the
+                 * global table only takes what a full partition refuses */
+                const cl_uint   step_rows = GPUPREAGG_CONSUMER_THREADS * 4;
+
+                for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
+                     rb += GPUPREAGG_DEAL_STEPS * step_rows)
+                {
+                    bool            validd[GPUPREAGG_DEAL_STEPS][4];
+                    cl_uint         partd[GPUPREAGG_DEAL_STEPS][4];
+                    cl_uint         posd[GPUPREAGG_DEAL_STEPS][4];
+
+#pragma unroll
+                    for (int h = 0; h < GPUPREAGG_DEAL_STEPS; h++)
+                    {
+                        /* (warp-uniform: rows past the end of the tile are
+                         * not even read - the stage ends there) */
+                        const bool      have = (h == 0 || rb + h * step_rows < rows);
+                        const cl_uint   r = rb + h * step_rows + lane_id * 4;
+                        kern_row_regs   rr[4];
+
+                        rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                        if (have)
+                        {
+                            GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                        {
+                            pagg_row    prow;
+                            cl_uint     knull;
+
+                            validd[h][j] = false;
+                            partd[h][j] = 0;
+                            posd[h][j] = 0;
+                            if (have && r + j < rows)
+                                validd[h][j] = pgs_eval_row(kparams, rr[j], kds_in, row0 + r + j,
+                                                            recheck_map, ctx, prow);
+                            if (validd[h][j])
+                                posd[h][j] = pgs_part_reserve(gs, pgs_hash_keys(prow, knull),
+                                                              partd[h][j]);
+                        }
+                    }
+                    /* the rows are read again from the stage (it is still
+                     * ours) instead of being kept in registers while the
+                     * atomics are under way: 8 rows x 3 columns would not fit */
+                    asm volatile("" ::: "memory");
+#pragma unroll
+                    for (int h = 0; h < GPUPREAGG_DEAL_STEPS; h++)
+                    {
+                        const bool      have = (h == 0 || rb + h * step_rows < rows);
+                        const cl_uint   r = rb + h * step_rows + lane_id * 4;
+                        kern_row_regs   rr[4];
+
+                        rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                        if (have)
+                        {
+                            GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                        {
+                            bool    refused = (validd[h][j] && posd[h][j] >= gs.part_cap);
+
+                            if (validd[h][j] && !refused)
+                                pgs_part_write(gs, rr[j], row0 + r + j, row0 + r + j,
+                                               partd[h][j], posd[h][j]);
+                            if (__any_sync(0xffffffffU, refused))
+                            {
+                                pagg_row    prow;
+
+                                if (refused)
+                                {
+                                    cl_int  e = StromError_Success;     /* evaluated above */
+                                    gpupreagg_projection(&e, kparams, rr[j], prow, kds_in,
+                                                         row0 + r + j, 0);
+                                }
+                                pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, refused,
+                                                  row0 + r + j, recheck_map);
+                            }
+                        }
+                    }
+                }
+            }
+            else
+#endif
             /* The trip count is the same for every lane of the warp
              * (pgs_group_add_row is collective). */
             for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
@@ -2373,86 +2552,110 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
 
                 rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
                 GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
-#if GPUPREAGG_PARTITIONED
-                if (gs.part_nparts != 0)
-                {
-                    /* very many groups: deal the 4 rows into their partitions.
-                     * The four cursor atomics are issued together (each is an
-                     * L2 round trip whose result the record store needs); the
-                     * global table only takes what a full partition refuses */
-                    bool        valid4[4];
-                    cl_ulong    hash4[4];
-                    cl_uint     part4[4], pos4[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                    {
-                        pagg_row    prow;
-                        cl_uint     knull;
-
-                        valid4[j] = false;
-                        if (r + j < rows)
-                            valid4[j] = pgs_eval_row(kparams, rr[j], kds_in, row0 + r + j,
-                                                     recheck_map, ctx, prow);
-                        hash4[j] = (valid4[j] ? pgs_hash_keys(prow, knull) : 0);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                    {
-                        part4[j] = 0;
-                        pos4[j] = (valid4[j] ? pgs_part_reserve(gs, hash4[j], part4[j]) : 0);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                    {
-                        bool    refused = (valid4[j] && pos4[j] >= gs.part_cap);
-
-                        if (valid4[j] && !refused)
-                            pgs_part_write(gs, rr[j], row0 + r + j, row0 + r + j,
-                                           part4[j], pos4[j]);
-                        if (__any_sync(0xffffffffU, refused))
-                        {
-                            pagg_row    prow;
-
-                            if (refused)
-                            {
-                                cl_int  e = StromError_Success;     /* evaluated above */
-                                gpupreagg_projection(&e, kparams, rr[j], prow, kds_in,
-                                                     row0 + r + j, 0);
-                            }
-                            pgs_group_add_row(gs, sh, &head->sh_nused, prow, ctx, refused,
-                                              row0 + r + j, recheck_map);
-                        }
-                    }
-                }
-                else
-#endif
-                {
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        PGS_CONSUME_ROW_GROUPED(j)
-                }
+                for (int j = 0; j < 4; j++)
+                    PGS_CONSUME_ROW_GROUPED(j)
             }
 #elif GPUPREAGG_GATHER_PAYLOAD
-            /* GROUP BY under a WHERE clause, experimental variant
-             * (PGSTROM_GATHER_PAYLOAD=1): the ring only carries the columns
-             * the qual reads, so a tile of the same byte size holds several
-             * times the rows and more of the chunk is in flight per SM.  A
-             * warp evaluates the qual of 128 staged rows per step and queues
-             * the ROW NUMBERS of the survivors (32-bit, no values are kept);
-             * the stage goes back to the producer as soon as the warp has
-             * scanned its share.  Whenever 32 rows are queued, every lane
-             * takes one through projection - its columns gathered from HBM
-             * by row number (kern_tile_gmem, the view of the row-map
-             * kernel) - and find-or-insert.  With a selective qual most
-             * 32-byte sectors of the unstaged columns are never read. */
+            /* GROUP BY under a WHERE clause: the ring only carries the columns
+             * the qual reads (GPUPREAGG_GATHER_PAYLOAD, the default), so a
+             * tile of the same byte size holds several times the rows and
+             * more of the chunk is in flight per SM.  Per tile a warp
+             *   A. evaluates the qual of its whole share of the tile (up to
+             *      PGS_GATHER_MAX_STEPS steps of 128 rows, 4 adjacent rows
+             *      per lane and step): independent 128-bit shared-memory
+             *      loads and compares, one bit per row in `vm`; nothing of
+             *      the stage is needed after that, it goes back to the
+             *      producer at once;
+             *   B. step by step turns the bits into queue entries - the ROW
+             *      NUMBERS of the survivors, compacted with ballots - and,
+             *      whenever 32 rows are queued, every lane takes one through
+             *      projection - its columns gathered from HBM by row number
+             *      (kern_tile_gmem, the view of the row-map kernel) - and
+             *      find-or-insert.
+             * (A and B used to be one loop per step: load -> qual -> ballot
+             * -> push, one dependent chain of ~1400 cycles per 128 rows with
+             * four warps per scheduler to hide it - at 1% selectivity, with
+             * next to nothing reaching the table, the kernel still needed
+             * 0.30 ms per 125 M rows.)  With a selective qual most 32-byte
+             * sectors of the unstaged columns are never read. */
             {
                 cl_uint        *rowq32 = (cl_uint *)(__pgs_smem + __qbase);
                 const cl_uint   step_rows = GPUPREAGG_CONSUMER_THREADS * 4;
                 const cl_uint   rows_up = ((rows + step_rows - 1) / step_rows) * step_rows;
                 const bool      last_tile = (t + gridDim.x >= ntiles);
-                cl_uint         rb = (ctid & ~31U) * 4;
+                const cl_uint   rb0 = (ctid & ~31U) * 4;
+                cl_uint         rb = rb0;
+                cl_uint         vm = 0;     /* bit 4 k + j: row j of step k passed */
                 bool            scanning = true;
 
+                /* ---- A ---- */
+#define PGS_GATHER_SCAN_QUALS(NV)                                               \
+                        _Pragma("unroll")                                       \
+                        for (int j = 0; j < 4; j++)                             \
+                        {                                                       \
+                            cl_int      e = StromError_Success;                 \
+                            bool        v = false;                              \
+                                                                                \
+                            if ((cl_uint)j < (NV))                              \
+                                v = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in, \
+                                                        row0 + r + j);          \
+                            if (e != StromError_Success)                        \
+                            {                                                   \
+                                pgs_note_error(e, row0 + r + j, recheck_map, ctx); \
+                                ctx.nfiltered--;    /* neither passed nor filtered */ \
+                                v = false;                                      \
+                            }                                                   \
+                            vmask |= (v ? (1U << j) : 0U);                      \
+                        }
+                if (rows == tile_rows && tile_rows == 4 * step_rows)
+                {
+                    /* a whole tile of four steps (the default shape): one
+                     * straight line, the four loads and sixteen compares
+                     * are independent of each other */
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                    {
+                        const cl_uint r = rb0 + (cl_uint)k * step_rows + lane_id * 4;
+                        kern_row_regs rr[4];
+                        cl_uint     vmask = 0;
+
+                        rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+                        PGS_GATHER_SCAN_QUALS(4U)
+                        vm |= vmask << (4 * k);
+                    }
+                    nscanned += 4 * 128U;
+                }
+                else
+                {
+#pragma unroll 1
+                    for (int k = 0; k < PGS_GATHER_MAX_STEPS; k++)
+                    {
+                        const cl_uint   rbk = rb0 + (cl_uint)k * step_rows;
+                        const cl_uint   r = rbk + lane_id * 4;
+                        const cl_uint   nv = (r < rows ? min(rows - r, 4U) : 0U);
+                        kern_row_regs   rr[4];
+                        cl_uint         vmask = 0;
+
+                        if (rbk >= rows)        /* warp-uniform */
+                            break;
+                        rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
+                        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+                        PGS_GATHER_SCAN_QUALS(nv)
+                        vm |= vmask << (4 * k);
+                        nscanned += min(rows - rbk, 128U);
+                    }
+                }
+#undef PGS_GATHER_SCAN_QUALS
+                /* nothing of the stage is needed any more */
+                __syncwarp();
+                if (lane_id == 0)
+                    pgs_mbar_arrive(&head->empty_bar[stage]);
+                PGS_DBG_STOP(1)
+                PGS_DBG_START()
+
+                /* ---- B ---- */
                 for (;;)
                 {
                     const cl_uint   qn = qtail - qhead;
@@ -2460,53 +2663,27 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                     if (scanning && rb < rows_up && qn <= PGS_ROWQ_ENTRIES - 128)
                     {
                         const cl_uint r = rb + lane_id * 4;
-                        const cl_uint nv = (r < rows ? min(rows - r, 4U) : 0U);
-                        kern_row_regs rr[4];
-                        bool        valid4[4];
+                        const cl_uint vmask = vm & 0xfU;
                         cl_uint     votes4[4];
 
-                        rr[0].shift = 0; rr[1].shift = 1; rr[2].shift = 2; rr[3].shift = 3;
-                        GPUPREAGG_INCOL_LIST(PGS_X_INCOL_LOAD4)
+                        vm >>= 4;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            votes4[j] = __ballot_sync(0xffffffffU, (vmask >> j) & 1U);
 #pragma unroll
                         for (int j = 0; j < 4; j++)
                         {
-                            cl_int      e = StromError_Success;
-
-                            valid4[j] = false;
-                            if ((cl_uint)j < nv)
-                                valid4[j] = gpupreagg_qual_eval(&e, kparams, rr[j], kds_in,
-                                                                row0 + r + j);
-                            if (e != StromError_Success)
-                            {
-                                pgs_note_error(e, row0 + r + j, recheck_map, ctx);
-                                ctx.nfiltered--;    /* neither passed nor filtered */
-                                valid4[j] = false;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            votes4[j] = __ballot_sync(0xffffffffU, valid4[j]);
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                        {
-                            if (valid4[j])
+                            if ((vmask >> j) & 1U)
                                 rowq32[(qtail + __popc(votes4[j] & lanes_lt)) & (PGS_ROWQ_ENTRIES - 1)] =
                                     row0 + r + j;
                             qtail += __popc(votes4[j]);
                         }
-                        nscanned += min(rows - min(rb, rows), 128U);
                         rb += step_rows;
                         __syncwarp();
                         continue;
                     }
                     if (scanning && rb >= rows_up)
-                    {
-                        /* nothing of the stage is needed any more */
-                        __syncwarp();
-                        if (lane_id == 0)
-                            pgs_mbar_arrive(&head->empty_bar[stage]);
                         scanning = false;
-                    }
                     {
                         /* Two batches of 32 queued rows are under way at any
                          * time: the columns of the batch popped now are asked
@@ -2543,6 +2720,7 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                                 bool        active = g_act;
                                 pagg_row    prow;
 
+                                PGS_DBG_COUNT(3)
                                 if (active)
                                 {
                                     cl_int  e = StromError_Success;
@@ -2573,6 +2751,7 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                         break;
                 }
             }
+            PGS_DBG_STOP(2)
             continue;       /* the stage was handed back above */
 #else
             /* GROUP BY under a WHERE clause.  Only a fraction of the rows
@@ -2977,29 +3156,111 @@ template <> struct pgs_heap_load<1>
         rr.vbits[slot] = 1U;                                            \
     }
 
+/* columns up to the last referenced one: what a tuple walk has to step over */
+__device__ constexpr cl_uint
+pgs_heap_lastcol_const(void)
+{
+    cl_uint lastcol = 0;
+
+    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_HEAPMAX)
+    return lastcol;
+}
+#define PGS_HEAP_LASTCOL    (pgs_heap_lastcol_const())
+/*
+ * attlen / attalign of those columns, read from colmeta[] ONCE per thread and
+ * kept in registers (the walk is unrolled over PGS_HEAP_LASTCOL, so every
+ * index is a constant).  Reading kds->colmeta[i] per attribute and tuple -
+ * what the reference does (opencl_common.h:817-864) - put a global load in
+ * front of every step of a chain that is already serial in `offset`
+ * (ncu, heap scan of the bench table: LDG.U16 / LDG.U8 of colmeta in the
+ * loop body, 16 of 32 lanes active).  Wider prefixes than
+ * PGS_HEAP_META_MAX columns keep the loads.
+ */
+#define PGS_HEAP_META_MAX   24
+struct pgs_heap_meta
+{
+    cl_uint     m[PGS_HEAP_META_MAX];   /* (ushort)attlen | attalign << 16 */
+    cl_uint     ncols;
+};
+
+DEVFN void
+pgs_heap_meta_load(pgs_heap_meta &hm, const kern_data_store *kds)
+{
+    hm.ncols = kds->ncols;
+#pragma unroll
+    for (cl_uint i = 0; i < PGS_HEAP_META_MAX; i++)
+    {
+        hm.m[i] = 0;
+        if (i < PGS_HEAP_LASTCOL && i < hm.ncols)
+        {
+            kern_colmeta    cmeta = kds->colmeta[i];
+
+            hm.m[i] = (cl_uint)(cl_ushort)cmeta.attlen |
+                      ((cl_uint)(unsigned char)cmeta.attalign << 16);
+        }
+    }
+}
+
 /* false: the tuple does not fit what colmeta[] says (corruption).
  * `htup` may be a staged copy; `htup_off` is where the tuple sits in the
  * chunk (varlena values travel as chunk offsets and are read from HBM) */
 DEVFN bool
 pgs_heap_deform(const kern_data_store *kds, const unsigned char *htup,
-                cl_uint avail, kern_row_regs &rr, cl_ulong htup_off)
+                cl_uint avail, kern_row_regs &rr, cl_ulong htup_off,
+                const pgs_heap_meta &hm)
 {
     const cl_uint   infomask = *((const cl_ushort *)(htup + PGS_HTUP_INFOMASK_OFF));
     const cl_uint   natts = *((const cl_ushort *)(htup + PGS_HTUP_INFOMASK2_OFF)) & PGS_HEAP_NATTS_MASK;
     const bool      hasnull = (infomask & PGS_HEAP_HASNULL) != 0;
     cl_uint         offset = htup[PGS_HTUP_HOFF_OFF];
-    cl_uint         lastcol = 0;
+    cl_uint         lastcol = PGS_HEAP_LASTCOL;
 
     rr.shift = 0;
     GPUPREAGG_INCOL_LIST(PGS_X_INCOL_HEAPCLEAR)
-    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_HEAPMAX)
-    if (lastcol > kds->ncols)
+    if (lastcol > hm.ncols)
         return false;
     /* attributes beyond natts are NULL (tuple older than ADD COLUMN) */
     if (lastcol > natts)
         lastcol = natts;
     if (offset < PGS_HTUP_BITS_OFF + (hasnull ? (natts + 7) / 8 : 0))
         return false;
+    if (PGS_HEAP_LASTCOL <= PGS_HEAP_META_MAX)
+    {
+#pragma unroll
+        for (cl_uint i = 0; i < PGS_HEAP_META_MAX; i++)
+        {
+            if (i < PGS_HEAP_LASTCOL && i < lastcol)
+            {
+                const unsigned char *addr;
+                const cl_int    alen = (cl_int)(cl_short)(hm.m[i] & 0xffffU);
+                const cl_uint   aalign = hm.m[i] >> 16;
+
+                if (hasnull && !((htup[PGS_HTUP_BITS_OFF + (i >> 3)] >> (i & 7)) & 1))
+                    continue;                   /* NULL: takes no space */
+                if (alen > 0)
+                    offset = TYPEALIGN(aalign, offset);
+                else if (offset < avail && htup[offset] == 0)   /* !VARATT_NOT_PAD_BYTE */
+                    offset = TYPEALIGN(aalign, offset);
+                if (offset + (alen > 0 ? (cl_uint)alen : 1U) > avail)
+                    return false;
+                addr = htup + offset;
+                if (alen > 0)
+                {
+                    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_HEAPTAKE)
+                    offset += (cl_uint)alen;
+                }
+                else
+                {
+                    /* varlena: the row carries the offset of the datum from
+                     * the head of the chunk, like a KDS_FORMAT_COLUMN value
+                     * (pg_numeric_vref) */
+                    GPUPREAGG_INCOL_LIST(PGS_X_INCOL_HEAPTAKEV)
+                    offset += pgs_varsize_any(addr);
+                }
+            }
+        }
+        return true;
+    }
     for (cl_uint i = 0; i < lastcol; i++)
     {
         kern_colmeta    cmeta;
@@ -3024,8 +3285,6 @@ pgs_heap_deform(const kern_data_store *kds, const unsigned char *htup,
         }
         else
         {
-            /* varlena: the row carries the offset of the datum from the head
-             * of the chunk, like a KDS_FORMAT_COLUMN value (pg_numeric_vref) */
             GPUPREAGG_INCOL_LIST(PGS_X_INCOL_HEAPTAKEV)
             offset += pgs_varsize_any(addr);
         }
@@ -3035,10 +3294,21 @@ pgs_heap_deform(const kern_data_store *kds, const unsigned char *htup,
 
 DEVFN bool
 pgs_heap_deform(const kern_data_store *kds, const unsigned char *htup,
-                cl_uint avail, kern_row_regs &rr)
+                cl_uint avail, kern_row_regs &rr, const pgs_heap_meta &hm)
 {
     return pgs_heap_deform(kds, htup, avail, rr,
-                           (cl_ulong)(htup - (const unsigned char *)kds));
+                           (cl_ulong)(htup - (const unsigned char *)kds), hm);
+}
+
+/* (one tuple on its own: the CPU simulation of the walk, tests/test_heap_deform_hostsim.py) */
+DEVFN bool
+pgs_heap_deform(const kern_data_store *kds, const unsigned char *htup,
+                cl_uint avail, kern_row_regs &rr)
+{
+    pgs_heap_meta   hm;
+
+    pgs_heap_meta_load(hm, kds);
+    return pgs_heap_deform(kds, htup, avail, rr, hm);
 }
 
 /*
@@ -3079,6 +3349,8 @@ gpupreagg_main_heap(kern_gpupreagg *kgpreagg,
     sh.salt = 1;
     pgs_cells_init(acc);
     pgs_heap_chunk_init(hc, kds_in);
+    pgs_heap_meta   hmeta;
+    pgs_heap_meta_load(hmeta, kds_in);
     if (threadIdx.x == 0)
     {
         head->sh_nused = 0;
@@ -3112,7 +3384,7 @@ gpupreagg_main_heap(kern_gpupreagg *kgpreagg,
                 cl_uint         avail = 0;
                 const unsigned char *htup = pgs_heap_tuple(hc, row, &avail);
 
-                if (!htup || !pgs_heap_deform(kds_in, htup, avail, rr))
+                if (!htup || !pgs_heap_deform(kds_in, htup, avail, rr, hmeta))
                 {
                     if (ctx.errcode == StromError_Success)
                         ctx.errcode = StromError_DataStoreCorruption;
@@ -3231,6 +3503,8 @@ gpupreagg_main_heap_staged(kern_gpupreagg *kgpreagg,
     }
     PGS_SH_TABLE_INIT()
     __syncthreads();
+    pgs_heap_meta   hmeta;
+    pgs_heap_meta_load(hmeta, kds_in);
 
     if (!ordered)
     {
@@ -3252,7 +3526,7 @@ gpupreagg_main_heap_staged(kern_gpupreagg *kgpreagg,
                 cl_uint         avail = 0;
                 const unsigned char *htup = pgs_heap_tuple(hc, row, &avail);
 
-                if (!htup || !pgs_heap_deform(kds_in, htup, avail, rr))
+                if (!htup || !pgs_heap_deform(kds_in, htup, avail, rr, hmeta))
                 {
                     if (ctx.errcode == StromError_Success)
                         ctx.errcode = StromError_DataStoreCorruption;
@@ -3363,7 +3637,8 @@ gpupreagg_main_heap_staged(kern_gpupreagg *kgpreagg,
                             !pgs_heap_deform(kds_in, htup, avail, rr,
                                              (cl_ulong)(blocks - (const unsigned char *)kds_in) +
                                              (cl_ulong)ri.blk_index * BLCKSZ +
-                                             (cl_ulong)(htup - (stage_base + pg * BLCKSZ))))
+                                             (cl_ulong)(htup - (stage_base + pg * BLCKSZ)),
+                                             hmeta))
                         {
                             if (ctx.errcode == StromError_Success)
                                 ctx.errcode = StromError_DataStoreCorruption;
@@ -3445,29 +3720,37 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
         if (threadIdx.x == 0)
             *p_nused = gs.part_nused[part];
         __syncthreads();
+        /* the records of the batch after this one are asked for before this
+         * one goes through the chain (ncu: 18% of the samples sat on the
+         * first use of a record read in place) */
+        kern_rec_regs   cur, nxt;
+
+        cur.clear();
+        if ((threadIdx.x & ~31U) + lane_id < n)
+            cur.load(recs + (cl_ulong)((threadIdx.x & ~31U) + lane_id) * PGS_REC_BYTES);
         for (cl_uint i0 = (threadIdx.x & ~31U); i0 < n; i0 += blockDim.x)
         {
             const cl_uint   i = i0 + lane_id;
             bool            active = (i < n);
-            kern_rec_gmem   view;
             pagg_row        prow;
 
-            view.rec = recs + (cl_ulong)min(i, n - 1) * PGS_REC_BYTES;
+            nxt.clear();
+            if (i + blockDim.x < n)
+                nxt.load(recs + (cl_ulong)(i + blockDim.x) * PGS_REC_BYTES);
             if (active)
             {
                 cl_int  e = StromError_Success;
 
-                gpupreagg_projection(&e, kparams, view, prow, kds_in, 0, 0);
+                gpupreagg_projection(&e, kparams, cur, prow, kds_in, 0, 0);
                 gpupreagg_aggcheck(&e, prow);
                 if (e != StromError_Success)
                 {
-                    pgs_note_error(e, *((const cl_uint *)(view.rec + PGS_REC_ROW_OFF)),
-                                   recheck_map, ctx);
+                    pgs_note_error(e, cur.rownum(), recheck_map, ctx);
                     active = false;
                 }
             }
-            pgs_group_add_row(gs, sh, p_nused, prow, ctx, active,
-                              *((const cl_uint *)(view.rec + PGS_REC_ROW_OFF)), recheck_map);
+            pgs_group_add_row(gs, sh, p_nused, prow, ctx, active, cur.rownum(), recheck_map);
+            cur = nxt;
         }
         __syncthreads();
         for (cl_uint i = threadIdx.x; i < image_bytes / 16; i += blockDim.x)
@@ -4227,10 +4510,12 @@ pgs_peer_block(cl_ulong *area, cl_uint nranks, cl_uint cap, cl_ulong epoch, cl_u
 }
 
 /* `local`: two words of this rank's own memory: [0] records written so far,
- * [1] CTA ticket.  Launched with whole warps. */
+ * [1] CTA ticket.  `moved` (mapped host memory) is set to 1 when the whole
+ * state went over and was reset here - the rank then has nothing to flush.
+ * Launched with whole warps. */
 extern "C" __global__ void
 gpupreagg_peer_push(pgs_gstate gs, cl_ulong *area, cl_uint rank, cl_uint nranks,
-                    cl_uint cap, cl_ulong epoch, cl_uint *local)
+                    cl_uint cap, cl_ulong epoch, cl_uint *local, cl_uint *moved)
 {
     cl_ulong   *block = pgs_peer_block(area, nranks, cap, epoch, rank);
     cl_ulong   *recs = block + PGS_SLOT_WORDS;
@@ -4251,6 +4536,7 @@ gpupreagg_peer_push(pgs_gstate gs, cl_ulong *area, cl_uint rank, cl_uint nranks,
             gs.ng_state[0] = 0;
             pgs_cells_init(gs.ng_state + 1);
             block[0] = 1;
+            *moved = 1;         /* (host memory: read after the stream is idle) */
             __threadfence_system();
             pgs_st_release_sys(area + 16 + 16 * rank, epoch);
         }
@@ -4332,6 +4618,7 @@ gpupreagg_peer_push(pgs_gstate gs, cl_ulong *area, cl_uint rank, cl_uint nranks,
         }
         local[0] = 0;
         local[1] = 0;
+        *moved = (fits ? 1U : 0U);
         __threadfence_system();
         pgs_st_release_sys(area + 16 + 16 * rank, epoch);
     }

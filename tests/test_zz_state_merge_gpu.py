@@ -148,11 +148,11 @@ def test_peer_merge_three_ranks_one_device(cuda, name, plan_kw, col_kw):
             rows = ranks[0].finish()
             bench_oracle.assert_partial_equal_node(plan.describe(), node, rows, _concat(shards))
             for s in ranks[1:]:
-                left = s.finish()
-                if plan.describe()["needs_grouping"]:
-                    assert left == []
-                else:
-                    assert len(left) == 1       # the identity state: count 0, sums NULL
+                # the whole state went to the root and was reset by the push
+                # kernel: nothing to flush (no flush kernel, no read-back)
+                launches = s.launch_count()
+                assert s.finish() == []
+                assert s.launch_count() == launches
     finally:
         for s in ranks:
             s.close()

@@ -9,9 +9,10 @@ os.environ.setdefault("PGSTROM_DEBUG_LEVEL", "4")
 from pg_strom_b200 import _capi, gpupreagg as gp, workloads as W
 wl = sys.argv[1] if len(sys.argv) > 1 else "where_agg"
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 50_000_000
+sel = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 lib = _capi.load(); gp.cuda_init([0])
 w = W.WORKLOADS[wl]
-plan = gp.Plan(w["plan"](), gucs={"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on", "pg_strom.perfmon": "on"})
+plan = gp.Plan(w["plan"](**({"selectivity_pct": sel} if wl == "where_agg" and sel != 10 else {})), gucs={"pg_strom.enabled": "on", "pg_strom.debug_force_gpupreagg": "on", "pg_strom.perfmon": "on"})
 cols = w["columns"](0, rows)
 ds = gp.DataStore([t for _, t in w["table"].columns], cols, nrows=rows)
 dptr = lib.pgs_device_alloc(0, ds.length); _capi.check(lib.pgs_device_upload(0, dptr, ds.ptr, ds.length))
