@@ -434,7 +434,7 @@ nvrtc_build(pgs_program *prog)
         std::string(getenv("PGSTROM_DEBUG_LEVEL") ? getenv("PGSTROM_DEBUG_LEVEL") : "0");
     std::string d_deal = "-DGPUPREAGG_DEAL_STEPS=" +
         std::to_string(std::min(4, std::max(1, atoi(getenv("PGSTROM_DEAL_STEPS")
-                                                     ? getenv("PGSTROM_DEAL_STEPS") : "2"))));
+                                                     ? getenv("PGSTROM_DEAL_STEPS") : "1"))));
     std::vector<const char *> opts = {
         "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
         "-device-int128", "--fmad=false",
@@ -916,6 +916,7 @@ struct pgs_session
     double          merge_ms[3] = {0, 0, 0};
     uint64_t        merge_count = 0;
     bool            merge_pending = false;  /* d_kg_misc carries the status of a merge */
+    size_t          seg_cursor_bytes = 0;   /* segment mode: shared memory of the cursors */
     /* a rank that pushed its whole state to the root has nothing to flush:
      * the push kernel says so in a word of mapped pinned memory */
     cl_uint        *h_moved = NULL;
@@ -926,6 +927,25 @@ struct pgs_session
 
 static int launch_kernel(pgs_session *s, cudaKernel_t k, int grid, int block,
                          size_t smem, void **args);
+
+/* Partitioned GROUP BY (very many groups): how many partitions, how many
+ * slots per table image.  0 partitions = not partitioned. */
+static size_t
+partition_plan(const pgs_session *s, size_t *p_slots)
+{
+    if (!(s->desc.num_keys > 0 && s->desc.part_rec_bytes > 0 &&
+          s->config.num_groups >= 65536.0 && !getenv("PGSTROM_NO_PARTITION")))
+        return 0;
+    const char *es = getenv("PGSTROM_PART_SLOTS");
+    size_t slots = es ? (((size_t)atol(es) + 31) & ~(size_t)31) : 1024;
+    size_t smem_max = devices[s->config.device].prop.sharedMemPerBlockOptin;
+    size_t head = std::max<size_t>(128, s->desc.partagg_head_bytes);
+    while (slots > 64 && head + slots * s->desc.sh_slot_bytes > smem_max)
+        slots -= 32;
+    if (p_slots)
+        *p_slots = slots;
+    return (size_t)(s->config.num_groups / (slots * 0.5)) + 1;
+}
 
 static int
 session_alloc_state(pgs_session *s)
@@ -967,27 +987,46 @@ session_alloc_state(pgs_session *s)
     s->gs.part_images = NULL;
     s->grid_partagg = 0;
     s->smem_partagg = 0;
-    if (s->desc.num_keys > 0 && s->desc.part_rec_bytes > 0 && s->sh_nslots == 0 &&
-        s->config.num_groups >= 65536.0 && !getenv("PGSTROM_NO_PARTITION"))
+    s->gs.part_seg_cap = 0;
+    s->gs.part_seg_max = 0;
+    s->gs.part_seg_counts = NULL;
+    size_t plan_slots = 0;
+    size_t plan_nparts = (s->sh_nslots == 0 ? partition_plan(s, &plan_slots) : 0);
+    if (plan_nparts != 0)
     {
         /* very many groups: partitioned aggregation (gpupreagg_partagg).
          * An image holds `slots` groups at most 75% full; partitions are
          * sized for half of that on average, their record areas for the
-         * rows of one chunk plus a quarter. */
-        const char *es = getenv("PGSTROM_PART_SLOTS");
-        size_t slots = es ? (((size_t)atol(es) + 31) & ~(size_t)31) : 1024;
+         * rows of one chunk plus a quarter (segment mode: plus a half,
+         * segment by segment, + 16). */
+        size_t slots = plan_slots;
         size_t image_bytes = slots * s->desc.sh_slot_bytes;
-        size_t smem_max = devices[s->config.device].prop.sharedMemPerBlockOptin;
-        while (slots > 64 && 128 + slots * s->desc.sh_slot_bytes > smem_max)
-            slots -= 32;
-        image_bytes = slots * s->desc.sh_slot_bytes;
-        size_t nparts = (size_t)(s->config.num_groups / (slots * 0.5)) + 1;
+        size_t nparts = plan_nparts;
         size_t max_rows = s->config.max_chunk_rows ? s->config.max_chunk_rows : (64u << 20);
         size_t cap = ((size_t)((double)max_rows / nparts * 1.25) + 64 + 3) & ~(size_t)3;
+        size_t seg_cap = 0, seg_max = 0;
+        if (s->seg_cursor_bytes != 0)
+        {
+            /* one segment per CTA of the scan kernel, cursors in its shared
+             * memory (see pgs_part_reserve_seg for the 16-bit bound) */
+            seg_max = (size_t)s->grid_main;
+            seg_cap = ((size_t)((double)max_rows / nparts / seg_max * 1.5) + 16 + 3) & ~(size_t)3;
+            if (seg_max > 256 || seg_cap + 8 * (size_t)s->desc.block_threads >= 65535)
+                seg_cap = seg_max = 0;
+            else
+                cap = seg_cap * seg_max;
+        }
         size_t rec_bytes = nparts * cap * s->desc.part_rec_bytes;
         size_t img_bytes = nparts * image_bytes;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
+        if (seg_cap != 0 && rec_bytes + img_bytes + 8 * nparts >= free_b / 2)
+        {
+            /* not enough memory for the padded segments: global cursors */
+            seg_cap = seg_max = 0;
+            cap = ((size_t)((double)max_rows / nparts * 1.25) + 64 + 3) & ~(size_t)3;
+            rec_bytes = nparts * cap * s->desc.part_rec_bytes;
+        }
         if (nparts < 0x7fffffffULL && cap < 0x7fffffffULL &&
             rec_bytes + img_bytes + 8 * nparts < free_b / 2)
         {
@@ -998,10 +1037,17 @@ session_alloc_state(pgs_session *s)
             CUDA_CHECK(cudaMalloc((void **)&s->gs.part_nused, 4 * nparts));
             CUDA_CHECK(cudaMalloc((void **)&s->gs.part_recs, rec_bytes));
             CUDA_CHECK(cudaMalloc((void **)&s->gs.part_images, img_bytes));
+            if (seg_cap != 0)
+            {
+                CUDA_CHECK(cudaMalloc((void **)&s->gs.part_seg_counts, 2 * nparts * seg_max));
+                CUDA_CHECK(cudaMemset(s->gs.part_seg_counts, 0, 2 * nparts * seg_max));
+            }
             s->gs.part_nparts = (cl_uint)nparts;
             s->gs.part_cap = (cl_uint)cap;
             s->gs.part_slots = (cl_uint)slots;
-            s->smem_partagg = 128 + image_bytes;
+            s->gs.part_seg_cap = (cl_uint)seg_cap;
+            s->gs.part_seg_max = (cl_uint)seg_max;
+            s->smem_partagg = std::max<size_t>(128, s->desc.partagg_head_bytes) + image_bytes;
             CUDA_CHECK(cudaFuncSetAttribute((const void *)s->k_partagg,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)s->smem_partagg));
@@ -1302,6 +1348,25 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
                 nslots = maxslots;
             s->sh_nslots = (cl_uint)nslots;
             table_bytes = nslots * s->desc.sh_slot_bytes;
+            /* very many groups, no WHERE clause: the deal pass keeps the
+             * cursors of its record segments in shared memory (16 bits per
+             * partition), in the place of the CTA-local table */
+            s->seg_cursor_bytes = 0;
+            /* (measured on B200, 100 M rows / 10 M groups: 5.78 ms against
+             * 5.33 ms with global cursors - the 2.9 M segment tails no longer
+             * fit L2, so the 32-byte record stores reach DRAM one by one
+             * instead of as merged 128-byte lines, which costs more than the
+             * cursor atomics did.  Kept behind PGSTROM_SEGMENTS=1.) */
+            if (nslots == 0 && !s->desc.has_qual && getenv("PGSTROM_SEGMENTS") &&
+                atoi(getenv("PGSTROM_SEGMENTS")) != 0)
+            {
+                size_t nparts = partition_plan(s, NULL);
+                if (nparts != 0 && 2 * nparts <= 65536)
+                {
+                    s->seg_cursor_bytes = (4 * ((nparts + 1) / 2) + 127) & ~(size_t)127;
+                    table_bytes = s->seg_cursor_bytes;
+                }
+            }
         }
         /* staging ring: one CTA (1 producer + 16 consumer warps) per SM owns
          * the whole shared memory; prefer 3 stages of 4096 rows (measured
@@ -1325,6 +1390,15 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
                 stages--;
             while (tile > 1024 && (size_t)stages * (tile / 1024) * per1k > target)
                 tile -= 1024;
+            if (s->seg_cursor_bytes != 0)
+            {
+                /* one step of 128 rows per warp and tile: every warp has the
+                 * same share, and shared-memory cursors need no batching */
+                tile = (cl_uint)std::max<size_t>(1024, ((size_t)s->desc.block_threads - 32) * 4 / 1024 * 1024);
+                stages = (cl_uint)std::min<size_t>(4, std::max<size_t>(2, target / ((tile / 1024) * per1k)));
+                while (tile > 1024 && (size_t)stages * (tile / 1024) * per1k > target)
+                    tile -= 1024;
+            }
             if (et) tile = (cl_uint)std::max(1024, (atoi(et) / 1024) * 1024);
             if (es) stages = (cl_uint)std::min(8, std::max(1, atoi(es)));
             s->tile_rows = tile;
@@ -1631,7 +1705,14 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
 
     bool use_rowmap = (krowmap && krowmap->nvalids >= 0);
     bool use_heap = (format == KDS_FORMAT_ROW || format == KDS_FORMAT_ROW_FLAT);
-    void *args[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck, &s->sh_nslots,
+    /* segment mode belongs to gpupreagg_main alone (its grid is what the
+     * record areas are cut for); every other scan kernel deals through the
+     * global cursors */
+    const bool seg_launch = (s->gs.part_seg_cap != 0 && !use_rowmap && !use_heap);
+    pgs_gstate gs_launch = s->gs;
+    if (!seg_launch)
+        gs_launch.part_seg_cap = 0;
+    void *args[] = { &sl.d_kgpreagg, (void *)&d_kds, &gs_launch, &sl.d_recheck, &s->sh_nslots,
                      &s->tile_rows, &s->nstages };
     int grid = s->grid_main;
     cl_uint no_stages = 0;
@@ -1669,7 +1750,7 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
             if (rc != StromError_Success)
                 return rc;
         }
-        void *hargs[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck, &s->sh_nslots,
+        void *hargs[] = { &sl.d_kgpreagg, (void *)&d_kds, &gs_launch, &sl.d_recheck, &s->sh_nslots,
                           &s->heap_pps, &s->heap_nstages, &sl.d_heap_index };
         rc = launch_kernel(s, s->k_heap_staged, s->num_sms, (int)s->desc.block_threads,
                            s->smem_heap_staged, hargs);
@@ -1684,7 +1765,8 @@ submit_common(pgs_session *s, const kern_data_store *kds_host, const void *kds_d
     {
         /* second pass of the partitioned GROUP BY: every partition that
          * received records is aggregated into its table image */
-        void *pargs[] = { &sl.d_kgpreagg, (void *)&d_kds, &s->gs, &sl.d_recheck };
+        cl_uint nseg = (seg_launch ? (cl_uint)grid : 0U);
+        void *pargs[] = { &sl.d_kgpreagg, (void *)&d_kds, &gs_launch, &sl.d_recheck, &nseg };
         rc = launch_kernel(s, s->k_partagg, s->grid_partagg, 256, s->smem_partagg, pargs);
         if (rc != StromError_Success)
             return rc;
@@ -2656,6 +2738,8 @@ pgs_preagg_perfmon_json(pgs_session *s)
     o->set("gh_nslots", (long long)s->gs.gh_nslots);
     o->set("part_nparts", (long long)s->gs.part_nparts);
     o->set("part_cap", (long long)s->gs.part_cap);
+    o->set("part_seg_cap", (long long)s->gs.part_seg_cap);
+    o->set("part_seg_max", (long long)s->gs.part_seg_max);
     o->set("part_slots", (long long)s->gs.part_slots);
     o->set("block_threads", (long long)s->desc.block_threads);
     o->set("tile_rows", (long long)s->tile_rows);
@@ -2718,6 +2802,7 @@ pgs_preagg_close(pgs_session *s)
         if (s->gs.part_nused) cudaFree(s->gs.part_nused);
         if (s->gs.part_recs) cudaFree(s->gs.part_recs);
         if (s->gs.part_images) cudaFree(s->gs.part_images);
+        if (s->gs.part_seg_counts) cudaFree(s->gs.part_seg_counts);
         if (s->d_result) cudaFree(s->d_result);
         if (s->d_kg_misc) cudaFree(s->d_kg_misc);
         if (s->h_result_head) cudaFreeHost(s->h_result_head);

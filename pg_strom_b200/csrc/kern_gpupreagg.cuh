@@ -77,9 +77,11 @@
 /* 1 (experimental, PGSTROM_GATHER_PAYLOAD): only the columns the qual reads
  * are staged (GPUPREAGG_INCOL_STAGED(slot)); rows that pass the qual fetch
  * the others from HBM by row number */
-/* many-groups deal pass: 4-row batches a lane has under way at a time */
+/* many-groups deal pass: 4-row batches a lane has under way at a time
+ * (measured: 1 and 2 take the same time - the global cursor atomics are bound
+ * by throughput, not by latency - so the default is the one without spills) */
 #ifndef GPUPREAGG_DEAL_STEPS
-#define GPUPREAGG_DEAL_STEPS        2
+#define GPUPREAGG_DEAL_STEPS        1
 #endif
 #ifndef GPUPREAGG_GATHER_PAYLOAD
 #define GPUPREAGG_GATHER_PAYLOAD    0
@@ -1109,7 +1111,12 @@ pgs_rowq_val_off(int slot)
 }
 #define PGS_ROWQ_MASK_OFF   ((pgs_rowq_val_off(GPUPREAGG_NUM_INCOLS) + 7U) & ~7U)
 #define PGS_ROWQ_ROW_OFF    (PGS_ROWQ_MASK_OFF + 4 * PGS_ROWQ_LEFT_ENTRIES)
+#if GPUPREAGG_GATHER_PAYLOAD
+/* gather variant: the queue holds 32-bit row numbers and nothing else */
+#define PGS_ROWQ_WARP_BYTES (4U * PGS_ROWQ_ENTRIES)
+#else
 #define PGS_ROWQ_WARP_BYTES ((PGS_ROWQ_ROW_OFF + 4 * PGS_ROWQ_LEFT_ENTRIES + 15U) & ~15U)
+#endif
 #if GPUPREAGG_NUM_KEYS > 0 && GPUPREAGG_HAS_QUAL
 #define PGS_ROWQ_BYTES      (PGS_ROWQ_WARP_BYTES * GPUPREAGG_CONSUMER_WARPS)
 #else
@@ -1208,6 +1215,29 @@ pgs_mbar_wait(cl_ulong *bar, cl_uint parity)
                      "}"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
+}
+/* the producer lane's wait for a free stage: it has nothing else to do, but
+ * its polling must not take issue slots from the consumer warps that share
+ * its scheduler (ncu, WHERE + GROUP BY: 12% of all executed instructions were
+ * this loop) */
+DEVFN void
+pgs_mbar_wait_relaxed(cl_ulong *bar, cl_uint parity)
+{
+    cl_uint addr = pgs_smem_addr(bar);
+    cl_uint done;
+
+    for (;;)
+    {
+        asm volatile("{\n\t"
+                     ".reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t"
+                     "}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done)
+            break;
+        __nanosleep(64);
+    }
 }
 DEVFN void
 pgs_bulk_g2s(void *dst_smem, const void *src_gmem, cl_uint bytes, cl_ulong *bar)
@@ -1698,6 +1728,29 @@ pgs_part_reserve(const pgs_gstate &gs, cl_ulong hash, cl_uint &part)
 {
     part = __umulhi((cl_uint)(hash >> 32), gs.part_nparts);
     return atomicAdd(PGS_PART_CURSOR(gs, part), 1U);
+}
+/* Segment mode: the cursors of this CTA's segments are 16-bit counters in
+ * shared memory, two per word.  A counter is read before it is bumped and
+ * left alone once it has reached the capacity, so it never runs into its
+ * neighbour: at most one add per thread and row in flight can follow a read
+ * that still saw room (capacity + 8 x block size < 65536, the host checks).
+ * Returns the position in the segment; >= part_seg_cap: no room. */
+DEVFN cl_uint
+pgs_part_reserve_seg(const pgs_gstate &gs, cl_uint *segcur, cl_ulong hash, cl_uint &part)
+{
+    part = __umulhi((cl_uint)(hash >> 32), gs.part_nparts);
+    const cl_uint   sh = (part & 1U) * 16U;
+    cl_uint         c = (*((volatile cl_uint *)&segcur[part >> 1]) >> sh) & 0xffffU;
+
+    if (c >= gs.part_seg_cap)
+        return gs.part_seg_cap;
+    return (atomicAdd(&segcur[part >> 1], 1U << sh) >> sh) & 0xffffU;
+}
+/* position of record `pos` of segment `seg` of a partition inside its area */
+DEVFN cl_uint
+pgs_part_seg_pos(const pgs_gstate &gs, cl_uint seg, cl_uint pos)
+{
+    return seg * gs.part_seg_cap + pos;
 }
 template <typename KDS>
 DEVFN void
@@ -2269,6 +2322,12 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     PGS_SH_TABLE_INIT()
+#if GPUPREAGG_PARTITIONED
+    /* segment mode of the deal pass: this CTA's cursors, behind the ring */
+    if (gs.part_nparts != 0 && gs.part_seg_cap != 0)
+        for (cl_uint i = threadIdx.x; i < (gs.part_nparts + 1) / 2; i += blockDim.x)
+            ((cl_uint *)(__pgs_smem + sh.base))[i] = 0;
+#endif
     __syncthreads();
 
     if (warp_id == 0)
@@ -2286,7 +2345,7 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                 unsigned char *stage_base = stages + stage * PGS_STAGE_BYTES(tile_rows);
                 cl_uint txbytes = 0;
 
-                pgs_mbar_wait(&head->empty_bar[stage], phase ^ 1);
+                pgs_mbar_wait_relaxed(&head->empty_bar[stage], phase ^ 1);
                 GPUPREAGG_INCOL_LIST(PGS_X_INCOL_TXBYTES)
                 pgs_mbar_arrive_expect_tx(&head->full_bar[stage], txbytes);
                 GPUPREAGG_INCOL_LIST(PGS_X_INCOL_ISSUE)
@@ -2460,6 +2519,8 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                  * atomics under way before the first record is written; the
                  * global table only takes what a full partition refuses */
                 const cl_uint   step_rows = GPUPREAGG_CONSUMER_THREADS * 4;
+                const bool      seg_mode = (gs.part_seg_cap != 0);
+                cl_uint        *segcur = (cl_uint *)(__pgs_smem + sh.base);
 
                 for (cl_uint rb = (ctid & ~31U) * 4; rb < rows;
                      rb += GPUPREAGG_DEAL_STEPS * step_rows)
@@ -2495,8 +2556,21 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                                 validd[h][j] = pgs_eval_row(kparams, rr[j], kds_in, row0 + r + j,
                                                             recheck_map, ctx, prow);
                             if (validd[h][j])
-                                posd[h][j] = pgs_part_reserve(gs, pgs_hash_keys(prow, knull),
-                                                              partd[h][j]);
+                            {
+                                if (seg_mode)
+                                {
+                                    /* this CTA's own segment of the partition,
+                                     * cursor in shared memory */
+                                    const cl_uint   q = pgs_part_reserve_seg(
+                                        gs, segcur, pgs_hash_keys(prow, knull), partd[h][j]);
+
+                                    posd[h][j] = (q >= gs.part_seg_cap ? gs.part_cap
+                                                  : pgs_part_seg_pos(gs, blockIdx.x, q));
+                                }
+                                else
+                                    posd[h][j] = pgs_part_reserve(gs, pgs_hash_keys(prow, knull),
+                                                                  partd[h][j]);
+                            }
                         }
                     }
                     /* the rows are read again from the stage (it is still
@@ -2656,6 +2730,46 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
                 PGS_DBG_START()
 
                 /* ---- B ---- */
+                {
+                    /* all survivors of the warp's share at once when the queue
+                     * has room for them (it has, unless most rows pass): one
+                     * prefix sum over the lanes' counts instead of four ballots
+                     * and eight population counts per step (the per-step loop
+                     * below stays for the rest: 0.54 k cycles per step and
+                     * warp, 18% of the kernel at 10% selectivity) */
+                    const cl_uint   cnt = __popc(vm);
+                    cl_uint         incl = cnt;
+
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1)
+                    {
+                        const cl_uint v = __shfl_up_sync(0xffffffffU, incl, d);
+
+                        if (lane_id >= (cl_uint)d)
+                            incl += v;
+                    }
+                    const cl_uint   total = __shfl_sync(0xffffffffU, incl, 31);
+
+                    if (total + (qtail - qhead) <= PGS_ROWQ_ENTRIES)
+                    {
+                        cl_uint     pos = qtail + incl - cnt;
+                        cl_uint     m = vm;
+
+                        while (m != 0)
+                        {
+                            const cl_uint b = __ffs(m) - 1;
+
+                            m &= m - 1;
+                            rowq32[pos & (PGS_ROWQ_ENTRIES - 1)] =
+                                row0 + rb0 + (b >> 2) * step_rows + lane_id * 4 + (b & 3U);
+                            pos++;
+                        }
+                        qtail += total;
+                        rb = rows_up;
+                        scanning = false;
+                        __syncwarp();
+                    }
+                }
                 for (;;)
                 {
                     const cl_uint   qn = qtail - qhead;
@@ -2933,6 +3047,20 @@ gpupreagg_main(kern_gpupreagg *kgpreagg,
         PGS_DBG_FLUSH()
 #endif
     }
+#if GPUPREAGG_PARTITIONED
+    if (gs.part_nparts != 0 && gs.part_seg_cap != 0)
+    {
+        /* segment mode: how many records this CTA left in each partition */
+        const cl_uint  *segcur = (const cl_uint *)(__pgs_smem + sh.base);
+        cl_ushort      *counts = gs.part_seg_counts + (cl_ulong)blockIdx.x * gs.part_nparts;
+
+        __syncthreads();
+        for (cl_uint p = threadIdx.x; p < gs.part_nparts; p += blockDim.x)
+            counts[p] = (cl_ushort)min((segcur[p >> 1] >> ((p & 1U) * 16U)) & 0xffffU,
+                                       gs.part_seg_cap);
+        __syncthreads();
+    }
+#endif
     pgs_main_epilogue(kgpreagg, gs, sh, (cl_ulong *)stages,
                       &head->is_last_cta, acc, acc_nn, ctx);
 }
@@ -3570,7 +3698,7 @@ gpupreagg_main_heap_staged(kern_gpupreagg *kgpreagg,
                     n = 0xffffffffU;        /* more rows than line pointers: not a heap chunk */
                 lead = fr0 & 3U;
                 ibytes = (n == 0xffffffffU ? 0 : ((lead + n) * 4 + 15U) & ~15U);
-                pgs_mbar_wait(&head->empty_bar[stage], phase ^ 1);
+                pgs_mbar_wait_relaxed(&head->empty_bar[stage], phase ^ 1);
                 meta[0] = fr0;
                 meta[1] = n;
                 pgs_mbar_arrive_expect_tx(&head->full_bar[stage], (b1 - b0) * BLCKSZ + ibytes);
@@ -3681,16 +3809,23 @@ gpupreagg_main_heap_staged(kern_gpupreagg *kgpreagg,
  * ------------------------------------------------------------------ */
 #define PGS_PARTAGG_THREADS     256
 
+/* shared memory of gpupreagg_partagg: [0] used slots of the image, [64...]
+ * prefix sums of the segment lengths (segment mode), then the image */
+#define PGS_PARTAGG_MAX_SEGS    256
+#define PGS_PARTAGG_HEAD_BYTES  (64 + 4 * (PGS_PARTAGG_MAX_SEGS + 1) + 60)
+
 extern "C" __global__ void
 __launch_bounds__(PGS_PARTAGG_THREADS)
 gpupreagg_partagg(kern_gpupreagg *kgpreagg,
                   const kern_data_store *kds_in,
                   pgs_gstate gs,
-                  cl_uint *recheck_map)
+                  cl_uint *recheck_map,
+                  cl_uint nseg)
 {
 #if GPUPREAGG_PARTITIONED
     const kern_parambuf *kparams = KERN_GPUPREAGG_PARAMBUF_CONST;
     cl_uint        *p_nused = (cl_uint *)__pgs_smem;
+    cl_uint        *prefix = (cl_uint *)(__pgs_smem + 64);  /* [nseg + 1] */
     const cl_uint   image_bytes = gs.part_slots * PGS_SH_SLOT_BYTES;
     const cl_uint   lane_id = threadIdx.x & 31;
     pgs_row_ctx     ctx;
@@ -3701,18 +3836,62 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
     ctx.nrecheck = 0;
     ctx.ninserted = 0;
     ctx.errcode = StromError_Success;
-    sh.base = 128;
+    sh.base = PGS_PARTAGG_HEAD_BYTES;
     sh.nslots = gs.part_slots;
     sh.salt = 0x9E3779B1U;
 
     for (cl_uint part = blockIdx.x; part < gs.part_nparts; part += gridDim.x)
     {
-        const cl_uint   n = min(*PGS_PART_CURSOR(gs, part), gs.part_cap);
         uint4          *image = (uint4 *)(gs.part_images + (cl_ulong)part * image_bytes);
         uint4          *local = (uint4 *)(__pgs_smem + sh.base);
         const unsigned char *recs = gs.part_recs +
             (cl_ulong)part * gs.part_cap * PGS_REC_BYTES;
+        cl_uint         n;
 
+        if (nseg == 0)
+            n = min(*PGS_PART_CURSOR(gs, part), gs.part_cap);
+        else
+        {
+            /* segment mode: the records lie in one segment per CTA of the scan
+             * kernel.  Warp 0 turns the segment lengths into prefix sums (8
+             * segments per lane); record i of the partition is then found by
+             * a binary search over them */
+            if (threadIdx.x < 32)
+            {
+                cl_uint c[8], sum = 0, excl;
+
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                {
+                    const cl_uint seg = threadIdx.x * 8 + k;
+
+                    c[k] = (seg < nseg
+                            ? (cl_uint)gs.part_seg_counts[(cl_ulong)seg * gs.part_nparts + part]
+                            : 0U);
+                    sum += c[k];
+                }
+                excl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1)
+                {
+                    cl_uint v = __shfl_up_sync(0xffffffffU, excl, d);
+                    if (lane_id >= (cl_uint)d)
+                        excl += v;
+                }
+                excl -= sum;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                {
+                    prefix[threadIdx.x * 8 + k] = excl;
+                    excl += c[k];
+                }
+                if (threadIdx.x == 31)
+                    prefix[PGS_PARTAGG_MAX_SEGS] = excl;
+            }
+            __syncthreads();
+            n = prefix[PGS_PARTAGG_MAX_SEGS];
+            __syncthreads();        /* (prefix[] is rewritten for the next partition) */
+        }
         if (n == 0)
             continue;           /* nothing for this image in this chunk */
         for (cl_uint i = threadIdx.x; i < image_bytes / 16; i += blockDim.x)
@@ -3720,6 +3899,23 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
         if (threadIdx.x == 0)
             *p_nused = gs.part_nused[part];
         __syncthreads();
+        /* where record i of the partition lies */
+#define PGS_PARTAGG_REC(i, out)                                                 \
+        {                                                                       \
+            cl_uint __pos = (i);                                                \
+            if (nseg != 0)                                                      \
+            {                                                                   \
+                cl_uint __lo = 0, __hi = PGS_PARTAGG_MAX_SEGS;                  \
+                _Pragma("unroll")                                               \
+                for (int __s = 0; __s < 8; __s++)                               \
+                {                                                               \
+                    const cl_uint __mid = (__lo + __hi) >> 1;                   \
+                    if (prefix[__mid] <= (i)) __lo = __mid; else __hi = __mid;  \
+                }                                                               \
+                __pos = pgs_part_seg_pos(gs, __lo, (i) - prefix[__lo]);         \
+            }                                                                   \
+            (out) = recs + (cl_ulong)__pos * PGS_REC_BYTES;                     \
+        }
         /* the records of the batch after this one are asked for before this
          * one goes through the chain (ncu: 18% of the samples sat on the
          * first use of a record read in place) */
@@ -3727,7 +3923,12 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
 
         cur.clear();
         if ((threadIdx.x & ~31U) + lane_id < n)
-            cur.load(recs + (cl_ulong)((threadIdx.x & ~31U) + lane_id) * PGS_REC_BYTES);
+        {
+            const unsigned char *rp;
+
+            PGS_PARTAGG_REC((threadIdx.x & ~31U) + lane_id, rp)
+            cur.load(rp);
+        }
         for (cl_uint i0 = (threadIdx.x & ~31U); i0 < n; i0 += blockDim.x)
         {
             const cl_uint   i = i0 + lane_id;
@@ -3736,7 +3937,12 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
 
             nxt.clear();
             if (i + blockDim.x < n)
-                nxt.load(recs + (cl_ulong)(i + blockDim.x) * PGS_REC_BYTES);
+            {
+                const unsigned char *rp;
+
+                PGS_PARTAGG_REC(i + blockDim.x, rp)
+                nxt.load(rp);
+            }
             if (active)
             {
                 cl_int  e = StromError_Success;
@@ -3752,6 +3958,7 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
             pgs_group_add_row(gs, sh, p_nused, prow, ctx, active, cur.rownum(), recheck_map);
             cur = nxt;
         }
+#undef PGS_PARTAGG_REC
         __syncthreads();
         for (cl_uint i = threadIdx.x; i < image_bytes / 16; i += blockDim.x)
             image[i] = local[i];
@@ -3759,7 +3966,8 @@ gpupreagg_partagg(kern_gpupreagg *kgpreagg,
         {
             ngrown += *p_nused - gs.part_nused[part];
             gs.part_nused[part] = *p_nused;
-            *PGS_PART_CURSOR(gs, part) = 0;
+            if (nseg == 0)
+                *PGS_PART_CURSOR(gs, part) = 0;
         }
         __syncthreads();
     }
@@ -4726,6 +4934,8 @@ gpupreagg_describe(pgs_kern_desc *desc)
     /* largest tile worth using: with only the qual's columns staged a tile
      * of the usual byte size holds many more rows */
     desc->max_tile_rows = (GPUPREAGG_GATHER_PAYLOAD ? 8192 : 4096);
+    desc->has_qual = GPUPREAGG_HAS_QUAL;
+    desc->partagg_head_bytes = PGS_PARTAGG_HEAD_BYTES;
 }
 
 #endif  /* KERN_GPUPREAGG_CUH */

@@ -39,6 +39,13 @@ typedef struct
     cl_uint    *part_nused;     /* [nparts] used slots of the image */
     unsigned char *part_recs;   /* [nparts][cap] records */
     unsigned char *part_images; /* [nparts] images, PGS_SH_SLOT_BYTES * slots each */
+    /* segment mode of the deal pass (gpupreagg_main on column chunks): the
+     * record area of a partition is cut into one segment per CTA of the scan
+     * kernel, whose cursors live in that CTA's shared memory - no global
+     * atomic per row.  part_cap = part_seg_max * part_seg_cap. */
+    cl_uint     part_seg_cap;   /* records per segment; 0 = off */
+    cl_uint     part_seg_max;   /* segments per partition the area is cut into */
+    cl_ushort  *part_seg_counts;/* [part_seg_max][nparts] records of the current chunk */
     /* bookkeeping */
     cl_ulong   *nrows_scanned;  /* rows that passed visibility (row-map) */
     cl_ulong   *nrows_filtered; /* rows removed by the device qual */
@@ -65,6 +72,8 @@ typedef struct
     cl_uint     slot_stride_bytes;  /* distance of two slots of the global table */
     cl_uint     part_rec_bytes;     /* bytes of a partition record */
     cl_uint     max_tile_rows;      /* upper bound of the tile size (multiple of 1024) */
+    cl_uint     has_qual;           /* the scan evaluates a WHERE clause */
+    cl_uint     partagg_head_bytes; /* shared memory of gpupreagg_partagg in front of the image */
 } pgs_kern_desc;
 
 #endif  /* KERN_SHARED_H */

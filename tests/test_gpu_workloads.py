@@ -130,6 +130,23 @@ def test_high_cardinality_partition_overflow(cuda):
     assert len(rows) > ng           # some groups came back as two partial rows
 
 
+def test_high_cardinality_segment_mode(cuda, monkeypatch):
+    """The deal pass with one record segment per CTA and its cursors in shared
+    memory (PGSTROM_SEGMENTS=1; off by default: measured slower than the global
+    cursors at 10 M groups): full chunks, ragged chunks and segments far too
+    small for their chunk (the rest goes to the global table)."""
+    monkeypatch.setenv("PGSTROM_SEGMENTS", "1")
+    ng, rows, pm = _run("high_cardinality", 1_000_000, 500_000,
+                        plan_kw={"num_groups": 200_000}, col_kw={"num_groups": 200_000})
+    assert ng > 190_000 and pm["part_seg_cap"] > 0 and pm["part_seg_max"] >= 1
+    _run("high_cardinality", 1_300_001, 299_996,
+         plan_kw={"num_groups": 100_000}, col_kw={"num_groups": 100_000})
+    ng, rows, pm = _run("high_cardinality", 1_000_000, 500_000,
+                        plan_kw={"num_groups": 200_000}, col_kw={"num_groups": 200_000},
+                        session_kw={"max_chunk_rows": 50_000})
+    assert pm["part_seg_cap"] > 0 and len(rows) > ng
+
+
 def test_high_cardinality_small_images(cuda, monkeypatch):
     """Images of 64 slots fill up (75% limit): the rest spills to the global table."""
     monkeypatch.setenv("PGSTROM_PART_SLOTS", "64")
