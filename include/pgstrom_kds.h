@@ -97,15 +97,26 @@ typedef cl_char     cl_bool;
 
 /* ---- alignment (opencl_common.h:272-274) ---- */
 #define STROMALIGN_LEN          16
+/* (PostgreSQL's c.h has its own TYPEALIGN family: inside a backend those win) */
+#ifndef TYPEALIGN
 #define TYPEALIGN(ALIGNVAL,LEN) \
     (((cl_ulong)(LEN) + ((ALIGNVAL) - 1)) & ~((cl_ulong)((ALIGNVAL) - 1)))
+#endif
+#ifndef TYPEALIGN_DOWN
 #define TYPEALIGN_DOWN(ALIGNVAL,LEN) \
     (((cl_ulong)(LEN)) & ~((cl_ulong)((ALIGNVAL) - 1)))
+#endif
 #define STROMALIGN(LEN)         TYPEALIGN(STROMALIGN_LEN,(LEN))
 #define STROMALIGN_DOWN(LEN)    TYPEALIGN_DOWN(STROMALIGN_LEN,(LEN))
+#ifndef LONGALIGN
 #define LONGALIGN(LEN)          TYPEALIGN(8,(LEN))
+#endif
+#ifndef INTALIGN
 #define INTALIGN(LEN)           TYPEALIGN(4,(LEN))
+#endif
+#ifndef MAXALIGN
 #define MAXALIGN(LEN)           TYPEALIGN(8,(LEN))
+#endif
 #ifndef BLCKSZ
 #define BLCKSZ                  8192
 #endif

@@ -1393,7 +1393,13 @@ grafter_try_replace_recurse(const JsonPtr &plan, std::vector<GpuPreAggPlan> *pla
         {
             newnode = gp.plan;
             if (plans)
+            {
+                /* the idx the per-node entry points of the C ABI take
+                 * (pgs_plan_kernel_source(plan, idx) ...): the glue reads it
+                 * when it turns the tree back into plan nodes */
+                gp.gpreagg->set("gpupreagg_index", (int)plans->size());
                 plans->push_back(gp);
+            }
             /* a GpuScan below is this node's own; any other outer plan
              * (join, sub-query scan) may hold further aggregates */
             JsonPtr child = gp.gpreagg->getp("lefttree");
