@@ -84,6 +84,54 @@ def test_julian_identity():
         assert T.date2j(*T.j2date(jd)) == jd
 
 
+def test_dates_against_python_datetime(shim):
+    """oracle/pg_typelib.py has no golden vectors in the reference (its
+    regression SQL has no date column); beyond the documented examples below it
+    is pinned on an independent implementation of the proleptic Gregorian
+    calendar, Python's datetime: EVERY day from 0001-01-01 to 9999-12-31
+    (3.65 M days) through j2date / date2j, and the device's casts (timestamp ->
+    date / time, date -> timestamp; CPU build of kern_timelib.cuh) on every
+    37th day at a random time of day."""
+    import datetime
+    first = datetime.date(1, 1, 1)
+    jd0 = T.date2j(1, 1, 1)
+    assert jd0 == first.toordinal() + 1721425       # JDN of 0001-01-01 is 1721426
+    n = datetime.date(9999, 12, 31).toordinal() - first.toordinal() + 1
+    y, m, d = 1, 1, 1
+    mdays = [31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
+    for i in range(n):
+        # (walking the calendar by hand is 10x faster than date.fromordinal and
+        # just as independent; every year boundary is checked against datetime)
+        assert T.j2date(jd0 + i) == (y, m, d), (i, y, m, d)
+        if m == 1 and d == 1:
+            assert datetime.date(y, 1, 1).toordinal() - first.toordinal() == i
+            assert T.date2j(y, 1, 1) == jd0 + i
+        leap = (y % 4 == 0 and (y % 100 != 0 or y % 400 == 0))
+        d += 1
+        if d > mdays[m - 1] + (1 if (m == 2 and leap) else 0):
+            d = 1
+            m += 1
+            if m > 12:
+                m = 1
+                y += 1
+    assert (y, m, d) == (10000, 1, 1)
+    rng = random.Random(7)
+    out, isnull = C.c_int64(), C.c_int()
+    epoch = datetime.datetime(2000, 1, 1)
+    for i in range(0, n, 37):
+        day = first + datetime.timedelta(days=i)
+        usec = rng.randrange(0, T.USECS_PER_DAY)
+        pgdate = day.toordinal() - datetime.date(2000, 1, 1).toordinal()
+        ts = pgdate * T.USECS_PER_DAY + usec
+        if 1 < day.year < 9999:
+            dt = epoch + datetime.timedelta(microseconds=ts)
+            assert (dt.year, dt.month, dt.day) == (day.year, day.month, day.day)
+        assert T.timestamp_date(ts) == pgdate and T.timestamp_time(ts) == usec
+        assert shim.shim_time_cast(0, ts, C.byref(out), C.byref(isnull)) == 0
+        assert not isnull.value and out.value == pgdate
+        assert shim.shim_time_cast(1, ts, C.byref(out), C.byref(isnull)) == 0 and out.value == usec
+
+
 def test_documented_examples(shim):
     """Known answers published in PostgreSQL's documentation (Date/Time
     Operators table and the datatype-datetime chapter): the epoch of date and
