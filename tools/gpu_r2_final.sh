@@ -21,6 +21,5 @@ cap() {  # tag, kernel regex, skip, count, bench args...
 cap nogrp '^gpupreagg_main$' 3 1 --workload nogrp_agg
 cap where '^gpupreagg_main$' 3 1 --workload where_agg
 cap hc 'gpupreagg_main$|gpupreagg_partagg' 6 2 --workload high_cardinality
-cap hc_flush '^gpupreagg_flush$' 3 1 --workload high_cardinality
 cap heap 'gpupreagg_heap_index|gpupreagg_main_heap' 6 2 --workload nogrp_agg_heap
 ls -la gpurun_out > gpurun_out/z_ls.txt
