@@ -656,7 +656,7 @@ def run_workload(ctx, name, sp, args, steps, warmup, want_cpu, headline):
             # ncu dram__bytes_read+write of one profiled launch, scaled to
             # the rows one timed launch processed
             traffic = t["dram_bytes_per_launch"] * (k_rows / t["rows_per_launch"])
-    kernel = "gpupreagg_main_heap" if heap else (
+    kernel = "gpupreagg_heap_index + gpupreagg_main_heap_staged" if heap else (
         "gpupreagg_main + gpupreagg_partagg" if pm1.get("part_nparts") else "gpupreagg_main")
     config = workload_config(name, sp)
     result = {

@@ -4705,6 +4705,22 @@ pgs_ld_acquire_sys(const cl_ulong *p)
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+/* polling: a relaxed load per look, ONE acquire when the value is there.
+ * A system-scope acquire / fence costs ~10 us on a GPU whose memory its peers
+ * have mapped (measured: gpupreagg_peer_pull with one acquire load per rank
+ * took 18 us with 2 ranks and 84 us with 8, the flags already set) */
+DEVFN cl_ulong
+pgs_ld_relaxed_sys(const cl_ulong *p)
+{
+    cl_ulong v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+DEVFN void
+pgs_fence_acquire_sys(void)
+{
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
 DEVFN void
 pgs_st_release_sys(cl_ulong *p, cl_ulong v)
 {
@@ -4729,10 +4745,15 @@ gpupreagg_peer_push(pgs_gstate gs, cl_ulong *area, cl_uint rank, cl_uint nranks,
     cl_ulong   *recs = block + PGS_SLOT_WORDS;
     __shared__ cl_uint is_last;
 
-    /* the buffer was last used two epochs ago: has the root imported that? */
+    /* the buffer was last used two epochs ago: has the root imported that?
+     * (the word lives in the root's HBM: a look every microsecond, so that
+     * seven waiting ranks do not keep the root's memory busy) */
     if (threadIdx.x == 0)
-        while (pgs_ld_acquire_sys(area) + 2 < epoch)
-            __nanosleep(200);
+    {
+        while (pgs_ld_relaxed_sys(area) + 2 < epoch)
+            __nanosleep(1000);
+        pgs_fence_acquire_sys();
+    }
     __syncthreads();
     if (GPUPREAGG_NUM_KEYS == 0)
     {
@@ -4745,7 +4766,7 @@ gpupreagg_peer_push(pgs_gstate gs, cl_ulong *area, cl_uint rank, cl_uint nranks,
             pgs_cells_init(gs.ng_state + 1);
             block[0] = 1;
             *moved = 1;         /* (host memory: read after the stream is idle) */
-            __threadfence_system();
+            /* (the release store orders this thread's writes before it) */
             pgs_st_release_sys(area + 16 + 16 * rank, epoch);
         }
         return;
@@ -4827,7 +4848,8 @@ gpupreagg_peer_push(pgs_gstate gs, cl_ulong *area, cl_uint rank, cl_uint nranks,
         local[0] = 0;
         local[1] = 0;
         *moved = (fits ? 1U : 0U);
-        __threadfence_system();
+        /* (every thread fenced its records before the ticket; the release
+         * store is cumulative over what this thread has observed) */
         pgs_st_release_sys(area + 16 + 16 * rank, epoch);
     }
 #endif
@@ -4841,6 +4863,17 @@ gpupreagg_peer_pull(pgs_gstate gs, cl_ulong *area, cl_uint root, cl_uint nranks,
     __shared__ cl_uint is_last;
     cl_uint     ninserted = 0;
 
+    /* wait for every rank's flag (local memory, relaxed looks), then ONE
+     * system-scope acquire for all of them */
+    if (threadIdx.x == 0)
+    {
+        for (cl_uint r = 0; r < nranks; r++)
+            if (r != root)
+                while (pgs_ld_relaxed_sys(area + 16 + 16 * r) < epoch)
+                    __nanosleep(100);
+        pgs_fence_acquire_sys();
+    }
+    __syncthreads();
     for (cl_uint r = 0; r < nranks; r++)
     {
         const cl_ulong *block = pgs_peer_block(area, nranks, cap, epoch, r);
@@ -4849,10 +4882,6 @@ gpupreagg_peer_pull(pgs_gstate gs, cl_ulong *area, cl_uint root, cl_uint nranks,
 
         if (r == root)
             continue;
-        if (threadIdx.x == 0)
-            while (pgs_ld_acquire_sys(area + 16 + 16 * r) < epoch)
-                __nanosleep(100);
-        __syncthreads();
         /* written by another GPU: read at the L2, never from this SM's L1 */
         n = min((cl_uint)__ldcg(block), cap);
         if (GPUPREAGG_NUM_KEYS == 0)
@@ -4900,7 +4929,6 @@ gpupreagg_peer_pull(pgs_gstate gs, cl_ulong *area, cl_uint root, cl_uint nranks,
     if (is_last && threadIdx.x == 0)
     {
         local[1] = 0;
-        __threadfence_system();
         pgs_st_release_sys(area, epoch);
     }
 }
