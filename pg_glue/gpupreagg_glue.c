@@ -1028,11 +1028,14 @@ pgstrom_grafter_entrypoint(Query *parse, int cursorOptions, ParamListInfo boundP
 /* ------------------------------------------------------------------
  * executor (CustomPlanMethods, gpupreagg.c:2189-2941)
  * ------------------------------------------------------------------ */
+/* chunks live in pinned, 128-byte aligned host memory (pgs_chunk_alloc: the
+ * reference's pgstrom_shmem_alloc of a pgstrom_data_store): the H2D copy is
+ * asynchronous and the column arrays keep the alignment the bulk copies need */
 static void
 chunk_release(void *arg, const kern_data_store *kds)
 {
     (void) arg;
-    pfree((void *) kds);
+    pgs_chunk_free((void *) kds);
 }
 
 static void
@@ -1089,11 +1092,16 @@ gpupreagg_next_chunk(void *child_state, pgs_bulkslot *slot)
     length = pgstrom_kds_column_length(gpas->ncols, gpas->colmeta, gpas->nrows,
                                        (const void *const *) gpas->values,
                                        (const uint8_t *const *) gpas->isnull);
-    kds = palloc(length);
+    kds = pgs_chunk_alloc(length);
+    if (kds == NULL)
+        return StromError_OutOfMemory;
     if (pgstrom_kds_column_build(kds, length, gpas->ncols, gpas->colmeta, gpas->nrows,
                                  (const void *const *) gpas->values,
                                  (const uint8_t *const *) gpas->isnull) != 0)
+    {
+        pgs_chunk_free(kds);
         return StromError_DataStoreCorruption;
+    }
     slot->kds = (const kern_data_store *) kds;
     slot->release = chunk_release;
     return 0;
@@ -1140,9 +1148,17 @@ gpupreagg_begin_glue(CustomPlan *node, EState *estate, int eflags)
     }
 
     /* devices are opened by the first GpuPreAgg of the backend */
-    rc = pgs_cuda_init(NULL, 0);
-    if (rc != 0)
-        elog(ERROR, "PG-Strom: %s (%s)", pgs_last_error(), pgstrom_strerror(rc));
+    {
+        static bool cuda_ready = false;
+
+        if (!cuda_ready)
+        {
+            rc = pgs_cuda_init(NULL, 0);
+            if (rc != 0)
+                elog(ERROR, "PG-Strom: %s (%s)", pgs_last_error(), pgstrom_strerror(rc));
+            cuda_ready = true;
+        }
+    }
     /* device program + session (pgstrom_get_devprog_key / clserv_lookup_device_program,
      * gpupreagg.c:2281-2307) */
     rc = gpupreagg_begin(gpreagg->plan, gpreagg->idx, 0, gpupreagg_next_chunk, gpas, &gpas->state);
@@ -1200,25 +1216,39 @@ gpupreagg_explain_glue(CustomPlanState *node, List *ancestors, ExplainState *es)
     const char     *text = gpupreagg_explain(gpas->state, es->verbose, es->analyze);
 
     (void) ancestors;
-    /* "label: value" lines (Bulkload, Kernel Source, perfmon under ANALYZE) */
+    /* "label: value" entries; the value of Kernel Source spans many lines, so
+     * an entry ends where the next known label begins */
     while (text && *text)
     {
-        const char *eol = strchr(text, '\n');
+        static const char *labels[] = { "Bulkload: ", "Kernel Source: ", "Perfmon: " };
+        const char *next = NULL;
         const char *sep = strstr(text, ": ");
-        size_t      len = eol ? (size_t) (eol - text) : strlen(text);
+        char       *label, *value;
+        size_t      len;
 
-        if (sep && sep < text + len)
+        if (!sep)
+            break;
+        for (size_t i = 0; i < sizeof(labels) / sizeof(labels[0]); i++)
         {
-            char *label = pstrdup(text), *value;
+            /* the next label at the start of a line behind this entry's own */
+            const char *p = sep;
 
-            label[sep - text] = '\0';
-            label[len] = '\0';
-            value = label + (sep - text) + 2;
-            while (*label == ' ')
-                label++;
-            ExplainPropertyText(label, value, es);
+            while ((p = strstr(p, labels[i])) != NULL)
+            {
+                if (p > text && p[-1] == '\n' && (!next || p < next))
+                    next = p;
+                p += strlen(labels[i]);
+            }
         }
-        text += len + (eol ? 1 : 0);
+        len = next ? (size_t) (next - text) : strlen(text);
+        label = pstrdup(text);
+        label[len] = '\0';
+        while (len > 0 && label[len - 1] == '\n')
+            label[--len] = '\0';
+        label[sep - text] = '\0';
+        value = label + (sep - text) + 2;
+        ExplainPropertyText(label, value, es);
+        text = next;
     }
 }
 
