@@ -113,7 +113,11 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region.  The region of
+    the headline workload lasts a few milliseconds, far less than one period of
+    `nvidia-smi -lms`, so the samples are taken in-process through NVML by a
+    thread that polls as fast as the calls return (~0.1 ms each) from start()
+    to stop(); `nvidia-smi -lms 100` is the fallback when NVML is not there."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -123,8 +127,40 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []           # (sm MHz, reasons bitmask)
+        self.running = False
+        self.thread = None
+
+    def _nvml_open(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml = (pynvml, h)
+        except Exception:           # noqa: BLE001  (no NVML: nvidia-smi below)
+            self.nvml = None
+        return self.nvml is not None
+
+    def _nvml_poll(self):
+        pynvml, h = self.nvml
+        reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.running:
+            try:
+                self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                     int(reasons_fn(h))))
+            except Exception:       # noqa: BLE001
+                break
+            time.sleep(0.0002)
 
     def start(self):
+        if self._nvml_open():
+            self.running = True
+            self.thread = threading.Thread(target=self._nvml_poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
@@ -139,7 +175,25 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def _stop_nvml(self):
+        pynvml, h = self.nvml
+        self.running = False
+        self.thread.join(timeout=2)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                "hw_thermal_slowdown": 0x40}
+        try:
+            smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:           # noqa: BLE001
+            smmax = None
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": smmax, "reasons": ["no samples"]}
+        reasons = sorted(n for n, b in bits.items() if any(r & b for _, r in self.samples))
+        return {"sm_mhz": float(np.median([c for c, _ in self.samples])), "sm_max_mhz": smmax,
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml, in-process"}
+
     def stop(self):
+        if self.nvml:
+            return self._stop_nvml()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -165,7 +219,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smmax)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def host_cores():
