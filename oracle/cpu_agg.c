@@ -21,9 +21,11 @@
  *   min/max             int4smaller/larger, float8smaller/larger
  *   sum/avg(float8)     float8pl / float8_accum {N, sumX, sumX2}
  *   variance(float8)    float8_accum {N, sumX, sumX2}
- * It is "port" not "reference": the expression interpreter, tuple deforming
- * from heap pages and fmgr call overhead of a real PostgreSQL are absent, so
- * a real PostgreSQL backend is slower than this on the same core.
+ * It is "port" not "reference": the expression interpreter and the fmgr call
+ * overhead of a real PostgreSQL are absent, so a real PostgreSQL backend is
+ * slower than this on the same core.  cpu_agg_run() scans column arrays;
+ * cpu_agg_run_heap() scans heap pages and de-forms every tuple like
+ * slot_deform_tuple (the baseline of the heap-page workload).
  * The parallel variant cuts the rows into per-thread ranges, aggregates each
  * with its own hash table and combines the states (what parallel aggregation
  * of later PostgreSQL versions does; the reference-era 9.4 has none, so
@@ -365,6 +367,279 @@ cpu_agg_run(const cpu_table *t, const cpu_query *q, int nthreads,
             pthread_create(&th[i], NULL, worker_main, &w[i]);
         else
             worker_main(&w[i]);
+    }
+    if (nthreads > 1)
+        for (int i = 0; i < nthreads; i++)
+            pthread_join(th[i], NULL);
+    if (q->key_col < 0)
+    {
+        for (int i = 1; i < nthreads; i++)
+            for (int j = 0; j < q->naggs; j++)
+                combine(&w[0].nogroup[j], &w[i].nogroup[j], q->agg_kind[j]);
+        ngroups = 1;
+        if (max_groups >= 1)
+        {
+            keys[0] = 0;
+            memcpy(states, w[0].nogroup, sizeof(agg_state) * q->naggs);
+        }
+    }
+    else
+    {
+        for (int i = 1; i < nthreads; i++)
+        {
+            for (uint64_t g = 0; g < w[i].gt.nused; g++)
+            {
+                agg_state *d = table_lookup(&w[0].gt, w[i].gt.keys[g]);
+                for (int j = 0; j < q->naggs; j++)
+                    combine(&d[j], &w[i].gt.pool[g * q->naggs + j], q->agg_kind[j]);
+            }
+            table_free(&w[i].gt);
+        }
+        ngroups = (int64_t)w[0].gt.nused;
+        {
+            int64_t ncopy = ngroups < max_groups ? ngroups : max_groups;
+            memcpy(keys, w[0].gt.keys, sizeof(int64_t) * ncopy);
+            memcpy(states, w[0].gt.pool, sizeof(agg_state) * q->naggs * ncopy);
+        }
+        table_free(&w[0].gt);
+    }
+    free(w);
+    free(th);
+    return ngroups;
+}
+
+/* ------------------------------------------------------------------
+ * The same over HEAP PAGES: what a PostgreSQL backend actually scans
+ * (SURVEY.md 8d asks for per-tuple deform in the CPU baseline).  The page and
+ * tuple layout is PostgreSQL's (bufpage.h PageHeaderData / ItemIdData,
+ * htup_details.h HeapTupleHeaderData; not vendored in the reference tree):
+ *   page  : 24-byte header with pd_lower @12 / pd_upper @14, line pointers
+ *           (lp_off:15 | lp_flags:2 | lp_len:15) from byte 24, tuples packed
+ *           from the end of the page, each MAXALIGNed
+ *   tuple : 23-byte header - t_infomask2 @18 (natts in the low 11 bits),
+ *           t_infomask @20 (HEAP_HASNULL = 0x0001), t_hoff @22 - then the
+ *           NULL bitmap when HEAP_HASNULL, then at MAXALIGN(t_hoff) the
+ *           attributes, each aligned to its typalign, NULLs taking no room
+ * The scan below is heapgettup_pagemode + slot_deform_tuple for the columns
+ * a query needs, followed by the same ExecQual / hash lookup / advance as the
+ * columnar loop above.
+ * ------------------------------------------------------------------ */
+#define CPU_BLCKSZ          8192
+#define CPU_PAGE_HEADER     24
+#define CPU_HTUP_HEADER     23
+#define CPU_HEAP_HASNULL    0x0001
+#define CPU_LP_NORMAL       1
+#define CPU_MAXALIGN(x)     (((x) + 7) & ~(size_t)7)
+
+static inline int
+col_len(int coltype)
+{
+    return coltype == COL_INT4 ? 4 : 8;
+}
+
+/*
+ * heap_form_tuple + PageAddItem for rows [row0, nrows) of a columnar table:
+ * fills `pages` (maxpages * 8192 bytes, zeroed by the caller) and returns the
+ * number of pages used; *rows_done = rows that found room.
+ */
+int64_t
+cpu_heap_form_pages(const cpu_table *t, unsigned char *pages, int64_t maxpages,
+                    int64_t row0, int64_t *rows_done)
+{
+    int64_t npages = 0;
+    int64_t r = row0;
+
+    while (r < t->nrows && npages < maxpages)
+    {
+        unsigned char  *page = pages + npages * CPU_BLCKSZ;
+        uint16_t        lower = CPU_PAGE_HEADER, upper = CPU_BLCKSZ;
+
+        for (; r < t->nrows; r++)
+        {
+            unsigned char   tup[CPU_HTUP_HEADER + 8 + 8 * MAX_COLS + 16];
+            int             hasnull = 0;
+            size_t          hoff, off, len;
+
+            for (int c = 0; c < t->ncols; c++)
+                if (t->nulls[c] && t->nulls[c][r])
+                    hasnull = 1;
+            hoff = CPU_MAXALIGN(CPU_HTUP_HEADER + (hasnull ? (size_t)(t->ncols + 7) / 8 : 0));
+            memset(tup, 0, sizeof(tup));
+            off = hoff;
+            for (int c = 0; c < t->ncols; c++)
+            {
+                size_t  alen = (size_t)col_len(t->coltype[c]);
+
+                if (t->nulls[c] && t->nulls[c][r])
+                    continue;
+                if (hasnull)
+                    tup[CPU_HTUP_HEADER + (c >> 3)] |= (unsigned char)(1 << (c & 7));
+                off = (off + alen - 1) & ~(alen - 1);
+                memcpy(tup + off, (const char *)t->values[c] + (size_t)r * alen, alen);
+                off += alen;
+            }
+            len = off;
+            tup[18] = (unsigned char)(t->ncols & 0xff);
+            tup[19] = (unsigned char)((t->ncols >> 8) & 0x07);
+            tup[20] = (unsigned char)(hasnull ? CPU_HEAP_HASNULL : 0);
+            tup[22] = (unsigned char)hoff;
+            if ((size_t)lower + 4 + CPU_MAXALIGN(len) > (size_t)upper)
+                break;                  /* page full */
+            upper = (uint16_t)(upper - CPU_MAXALIGN(len));
+            memcpy(page + upper, tup, len);
+            {
+                uint32_t lp = (uint32_t)upper | ((uint32_t)CPU_LP_NORMAL << 15) | ((uint32_t)len << 17);
+                memcpy(page + lower, &lp, 4);
+            }
+            lower = (uint16_t)(lower + 4);
+        }
+        memcpy(page + 12, &lower, 2);
+        memcpy(page + 14, &upper, 2);
+        {
+            uint16_t special = CPU_BLCKSZ, pagesize_version = CPU_BLCKSZ | 4;
+            memcpy(page + 16, &special, 2);
+            memcpy(page + 18, &pagesize_version, 2);
+        }
+        npages++;
+    }
+    if (rows_done)
+        *rows_done = r - row0;
+    return npages;
+}
+
+typedef struct {
+    int32_t     ncols;
+    int32_t     coltype[MAX_COLS];
+    const unsigned char *pages;
+    int64_t     npages;
+} cpu_heap;
+
+static void
+scan_pages(const cpu_heap *h, const cpu_query *q, int64_t lo, int64_t hi,
+           group_table *gt, agg_state *nogroup)
+{
+    /* the slot one tuple is de-formed into: a one-row "table" */
+    cpu_table   slot;
+    uint8_t     isnull[MAX_COLS];
+    int         lastcol = 0;
+
+    memset(&slot, 0, sizeof(slot));
+    slot.ncols = h->ncols;
+    slot.nrows = 1;
+    for (int c = 0; c < h->ncols; c++)
+    {
+        slot.coltype[c] = h->coltype[c];
+        slot.nulls[c] = &isnull[c];
+    }
+    /* slot_getsomeattrs: de-form up to the last attribute the query needs */
+    if (q->qual_col >= lastcol) lastcol = q->qual_col + 1;
+    if (q->key_col >= lastcol) lastcol = q->key_col + 1;
+    for (int j = 0; j < q->naggs; j++)
+        if (q->agg_kind[j] != AGG_COUNT_STAR && q->agg_col[j] >= lastcol)
+            lastcol = q->agg_col[j] + 1;
+
+    for (int64_t p = lo; p < hi; p++)
+    {
+        const unsigned char *page = h->pages + p * CPU_BLCKSZ;
+        uint16_t    lower;
+        int         nlines;
+
+        memcpy(&lower, page + 12, 2);
+        nlines = (lower <= CPU_PAGE_HEADER ? 0 : (lower - CPU_PAGE_HEADER) / 4);
+        for (int i = 0; i < nlines; i++)
+        {
+            uint32_t    lp;
+            const unsigned char *tup;
+            int         hasnull, natts;
+            size_t      off;
+            agg_state  *st;
+
+            memcpy(&lp, page + CPU_PAGE_HEADER + 4 * i, 4);
+            if (((lp >> 15) & 3) != CPU_LP_NORMAL)
+                continue;
+            tup = page + (lp & 0x7fff);
+            hasnull = (tup[20] & CPU_HEAP_HASNULL) != 0;
+            natts = tup[18] | ((tup[19] & 0x07) << 8);
+            off = tup[22];
+            for (int c = 0; c < lastcol; c++)
+            {
+                size_t  alen = (size_t)col_len(h->coltype[c]);
+
+                if (c >= natts || (hasnull && !((tup[CPU_HTUP_HEADER + (c >> 3)] >> (c & 7)) & 1)))
+                {
+                    isnull[c] = 1;
+                    continue;
+                }
+                isnull[c] = 0;
+                off = (off + alen - 1) & ~(alen - 1);
+                slot.values[c] = tup + off;
+                off += alen;
+            }
+            /* ExecQual: NULL or false => row is filtered */
+            if (q->qual_col >= 0)
+            {
+                if (isnull[q->qual_col])
+                    continue;
+                if (!(*(const int32_t *)slot.values[q->qual_col] < q->qual_const))
+                    continue;
+            }
+            if (q->key_col >= 0)
+            {
+                int64_t key = (h->coltype[q->key_col] == COL_INT8)
+                    ? *(const int64_t *)slot.values[q->key_col]
+                    : (int64_t)*(const int32_t *)slot.values[q->key_col];
+                st = table_lookup(gt, key);
+            }
+            else
+                st = nogroup;
+            for (int j = 0; j < q->naggs; j++)
+                advance(&st[j], q->agg_kind[j], &slot, q->agg_col[j], 0);
+        }
+    }
+}
+
+typedef struct {
+    const cpu_heap  *h;
+    const cpu_query *q;
+    int64_t     lo, hi;
+    group_table gt;
+    agg_state   nogroup[MAX_AGGS];
+} heap_worker_arg;
+
+static void *
+heap_worker_main(void *p)
+{
+    heap_worker_arg *w = (heap_worker_arg *)p;
+    scan_pages(w->h, w->q, w->lo, w->hi, &w->gt, w->nogroup);
+    return NULL;
+}
+
+/* cpu_agg_run over heap pages; same results and conventions */
+int64_t
+cpu_agg_run_heap(const cpu_heap *h, const cpu_query *q, int nthreads,
+                 int64_t *keys, agg_state *states, int64_t max_groups)
+{
+    if (nthreads < 1)
+        nthreads = 1;
+    heap_worker_arg *w = (heap_worker_arg *)calloc(nthreads, sizeof(heap_worker_arg));
+    pthread_t *th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
+    int64_t per = (h->npages + nthreads - 1) / nthreads;
+    int64_t ngroups = 0;
+
+    for (int i = 0; i < nthreads; i++)
+    {
+        w[i].h = h;
+        w[i].q = q;
+        w[i].lo = per * i < h->npages ? per * i : h->npages;
+        w[i].hi = per * (i + 1) < h->npages ? per * (i + 1) : h->npages;
+        if (q->key_col >= 0)
+            table_init(&w[i].gt, 1024, q->naggs);
+        for (int j = 0; j < q->naggs; j++)
+            state_init(&w[i].nogroup[j]);
+        if (nthreads > 1)
+            pthread_create(&th[i], NULL, heap_worker_main, &w[i]);
+        else
+            heap_worker_main(&w[i]);
     }
     if (nthreads > 1)
         for (int i = 0; i < nthreads; i++)

@@ -30,6 +30,11 @@ class cpu_query(C.Structure):
                 ("agg_kind", C.c_int32 * 16), ("agg_col", C.c_int32 * 16)]
 
 
+class cpu_heap(C.Structure):
+    _fields_ = [("ncols", C.c_int32), ("coltype", C.c_int32 * 8),
+                ("pages", C.c_void_p), ("npages", C.c_int64)]
+
+
 class agg_state(C.Structure):
     _fields_ = [("n", C.c_int64), ("isum_lo", C.c_int64), ("isum_hi", C.c_int64),
                 ("fsum", C.c_double), ("fsum2", C.c_double),
@@ -50,6 +55,12 @@ def load():
         _lib.cpu_agg_run.restype = C.c_int64
         _lib.cpu_agg_run.argtypes = [C.POINTER(cpu_table), C.POINTER(cpu_query), C.c_int,
                                      C.POINTER(C.c_int64), C.POINTER(agg_state), C.c_int64]
+        _lib.cpu_agg_run_heap.restype = C.c_int64
+        _lib.cpu_agg_run_heap.argtypes = [C.POINTER(cpu_heap), C.POINTER(cpu_query), C.c_int,
+                                          C.POINTER(C.c_int64), C.POINTER(agg_state), C.c_int64]
+        _lib.cpu_heap_form_pages.restype = C.c_int64
+        _lib.cpu_heap_form_pages.argtypes = [C.POINTER(cpu_table), C.c_void_p, C.c_int64, C.c_int64,
+                                             C.POINTER(C.c_int64)]
         assert _lib.cpu_agg_state_size() == C.sizeof(agg_state)
     return _lib
 
@@ -68,16 +79,11 @@ QUERIES = {
 }
 
 
-def run(name, cols, nthreads=1, max_groups=1 << 24, qual_const=None):
-    """cols: [(values ndarray, nullmask|None)...].  Returns (seconds, keys,
-    states ndarray-of-struct, ngroups)."""
-    lib = load()
-    qd = QUERIES[name]
+def _table(qd, cols):
     t = cpu_table()
     keep = []
-    n = len(cols[0][0])
     t.ncols = len(cols)
-    t.nrows = n
+    t.nrows = len(cols[0][0])
     for i, (v, m) in enumerate(cols):
         a = np.ascontiguousarray(v)
         keep.append(a)
@@ -87,6 +93,10 @@ def run(name, cols, nthreads=1, max_groups=1 << 24, qual_const=None):
             mm = np.ascontiguousarray(m, dtype=np.uint8)
             keep.append(mm)
             t.nulls[i] = mm.ctypes.data
+    return t, keep
+
+
+def _query(qd, qual_const):
     q = cpu_query()
     q.qual_col = -1 if qd["qual"] is None else qd["qual"][0]
     q.qual_const = 0 if qd["qual"] is None else (qual_const if qual_const is not None else qd["qual"][1])
@@ -95,9 +105,55 @@ def run(name, cols, nthreads=1, max_groups=1 << 24, qual_const=None):
     for j, (k, c) in enumerate(qd["aggs"]):
         q.agg_kind[j] = KINDS[k]
         q.agg_col[j] = c
+    return q
+
+
+def run(name, cols, nthreads=1, max_groups=1 << 24, qual_const=None):
+    """cols: [(values ndarray, nullmask|None)...].  Returns (seconds, keys,
+    states ndarray-of-struct, ngroups)."""
+    lib = load()
+    qd = QUERIES[name]
+    t, keep = _table(qd, cols)
+    q = _query(qd, qual_const)
     keys = (C.c_int64 * max_groups)()
     states = (agg_state * (max_groups * q.naggs))()
     t0 = time.perf_counter()
     ng = lib.cpu_agg_run(C.byref(t), C.byref(q), nthreads, keys, states, max_groups)
+    dt = time.perf_counter() - t0
+    return dt, keys, states, int(ng)
+
+
+def form_heap_pages(name, cols):
+    """The table as PostgreSQL heap pages (heap_form_tuple + PageAddItem in C):
+    returns (uint8 ndarray of npages * 8192 bytes, npages)."""
+    lib = load()
+    qd = QUERIES[name]
+    t, keep = _table(qd, cols)
+    width = 24 + 8 + sum(8 if c != "int4" else 4 for c in qd["coltypes"]) + 8 + 4
+    per_page = max(1, (8192 - 24) // width)
+    maxpages = int(t.nrows) // per_page + 2
+    pages = np.zeros(maxpages * 8192, dtype=np.uint8)
+    done = C.c_int64()
+    npages = int(lib.cpu_heap_form_pages(C.byref(t), pages.ctypes.data, maxpages, 0, C.byref(done)))
+    assert done.value == t.nrows, "pages estimate too small: %d of %d rows" % (done.value, t.nrows)
+    return pages, npages
+
+
+def run_heap(name, pages, npages, nthreads=1, max_groups=1 << 24, qual_const=None):
+    """The same query over heap pages (address or uint8 ndarray): every tuple
+    is de-formed like slot_deform_tuple.  Returns like run()."""
+    lib = load()
+    qd = QUERIES[name]
+    h = cpu_heap()
+    h.ncols = len(qd["coltypes"])
+    for i, c in enumerate(qd["coltypes"]):
+        h.coltype[i] = COLTYPE[c]
+    h.pages = pages.ctypes.data if hasattr(pages, "ctypes") else int(pages)
+    h.npages = npages
+    q = _query(qd, qual_const)
+    keys = (C.c_int64 * max_groups)()
+    states = (agg_state * (max_groups * q.naggs))()
+    t0 = time.perf_counter()
+    ng = lib.cpu_agg_run_heap(C.byref(h), C.byref(q), nthreads, keys, states, max_groups)
     dt = time.perf_counter() - t0
     return dt, keys, states, int(ng)
