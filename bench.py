@@ -185,11 +185,21 @@ class ClockSampler:
             smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:           # noqa: BLE001
             smmax = None
+        source = "nvml, in-process"
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": smmax, "reasons": ["no samples"]}
+            # the region ended before the first call returned: the clocks are
+            # read now, microseconds after it (they have not dropped yet)
+            try:
+                reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                    pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                     int(reasons_fn(h))))
+                source = "nvml, in-process, right after the timed region"
+            except Exception:       # noqa: BLE001
+                return {"sm_mhz": None, "sm_max_mhz": smmax, "reasons": ["no samples"]}
         reasons = sorted(n for n, b in bits.items() if any(r & b for _, r in self.samples))
         return {"sm_mhz": float(np.median([c for c, _ in self.samples])), "sm_max_mhz": smmax,
-                "reasons": reasons, "samples": len(self.samples), "source": "nvml, in-process"}
+                "reasons": reasons, "samples": len(self.samples), "source": source}
 
     def stop(self):
         if self.nvml:
