@@ -22,7 +22,7 @@ def _run(args, env=None, timeout=300):
                           env=dict(os.environ, **(env or {})))
 
 
-@pytest.mark.parametrize("workload", ["nogrp_agg", "where_agg", "high_cardinality"])
+@pytest.mark.parametrize("workload", ["nogrp_agg", "where_agg", "high_cardinality", "nogrp_agg_heap"])
 def test_reference_arm_line(workload):
     r = _run(["--impl", "reference", "--workload", workload, "--rows", "500000",
               "--steps", "1", "--warmup", "1"])
