@@ -23,6 +23,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <sys/stat.h>
+#include <sched.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -1964,7 +1965,15 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
          * a straggler's flush + read-back (measured at 8 GPUs: the root's
          * merge kernel spent 0.07 ms per scan waiting) */
         s->push_pending = false;
-        cudaError_t pe = cudaStreamSynchronize(s->s_exec);
+        /* this rank is ahead of the root and its push kernel may sit waiting
+         * for the root's `done` word.  Poll and yield: as quick as spinning
+         * inside cudaStreamSynchronize() when the core is free, but a host
+         * core that is shared with another rank's thread (the root's turn-
+         * around is on the root's critical path) goes to that thread */
+        cudaError_t pe;
+        while ((pe = cudaStreamQuery(s->s_exec)) == cudaErrorNotReady)
+            sched_yield();
+        cudaGetLastError();         /* (cudaErrorNotReady is not an error) */
         if (pe != cudaSuccess)
         {
             set_error("pgs_preagg_finish: %s", cudaGetErrorString(pe));
