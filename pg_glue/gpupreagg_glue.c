@@ -36,6 +36,7 @@
 #include "parser/parse_func.h"
 #include "utils/guc.h"
 #include "utils/lsyscache.h"
+#include "utils/resowner.h"
 #include <ctype.h>
 #include <math.h>
 
@@ -918,9 +919,10 @@ typedef struct
     List       *outer_quals;    /* evaluated inside the kernel; kept for EXPLAIN */
 } GpuPreAggPlan;
 
-typedef struct
+typedef struct GpuPreAggState
 {
     CustomPlanState         cps;
+    struct GpuPreAggState  *next_live;  /* states with device work this backend holds */
     pgs_gpupreagg_state    *state;
     TupleDesc               scan_desc;
     bool                    outer_done;
@@ -931,6 +933,43 @@ typedef struct
     char                  **values;     /* [ncols]: packed values, or varlena pointers */
     uint8_t               **isnull;     /* [ncols] */
 } GpuPreAggState;
+
+/* Every state that holds a session is on this list until EndCustomPlan; a
+ * transaction that aborts in between gets them closed by the resource-owner
+ * callback below - in-flight chunks are waited for and handed back, nothing
+ * of the device is leaked (restrack.c:180-254). */
+static GpuPreAggState  *live_states = NULL;
+
+static void
+live_states_remove(GpuPreAggState *gpas)
+{
+    for (GpuPreAggState **p = &live_states; *p; p = &(*p)->next_live)
+        if (*p == gpas)
+        {
+            *p = gpas->next_live;
+            break;
+        }
+    gpas->next_live = NULL;
+}
+
+static void
+pgstrom_release_callback(ResourceReleasePhase phase, bool isCommit, bool isTopLevel, void *arg)
+{
+    (void) isTopLevel;
+    (void) arg;
+    if (phase != RESOURCE_RELEASE_BEFORE_LOCKS || isCommit)
+        return;
+    while (live_states)
+    {
+        GpuPreAggState *gpas = live_states;
+
+        live_states = gpas->next_live;
+        gpas->next_live = NULL;
+        if (gpas->state)
+            (void) gpupreagg_end(gpas->state);      /* drains, releases, closes */
+        gpas->state = NULL;
+    }
+}
 
 /* rewritten JSON + original tree -> plan nodes.  The rewritten tree is the
  * original one with CustomPlan nodes spliced in above the outer plan of each
@@ -1022,6 +1061,41 @@ pgstrom_grafter_entrypoint(Query *parse, int cursorOptions, ParamListInfo boundP
     }
     cursor = pgs_plan_tree_json(plan);
     result->planTree = graft_plan(jparse(&cursor), result->planTree, plan);
+    return result;
+}
+
+/* grafter.c:131-146: the sub-plans (InitPlans / SubPlans) are walked like the
+ * main tree, each with its own pgs_plan */
+static Plan *
+pgstrom_graft_one(PlannedStmt *pstmt, Plan *tree)
+{
+    char        *json = pgstrom_plan_to_json(pstmt, tree);
+    pgs_plan    *plan = pgstrom_grafter_json(json);
+    const char  *cursor;
+
+    pfree(json);
+    if (plan == NULL)
+        return tree;
+    if (pgs_plan_num_gpupreagg(plan) == 0)
+    {
+        pgs_plan_free(plan);
+        return tree;
+    }
+    cursor = pgs_plan_tree_json(plan);
+    return graft_plan(jparse(&cursor), tree, plan);
+}
+
+static PlannedStmt *
+pgstrom_grafter_with_subplans(Query *parse, int cursorOptions, ParamListInfo boundParams)
+{
+    PlannedStmt *result = pgstrom_grafter_entrypoint(parse, cursorOptions, boundParams);
+    ListCell    *cell;
+
+    if (result == NULL || !guc_enabled || !guc_enable_gpupreagg)
+        return result;
+    foreach (cell, result->subplans)
+        if (lfirst(cell) != NULL)
+            lfirst(cell) = pgstrom_graft_one(result, (Plan *) lfirst(cell));
     return result;
 }
 
@@ -1164,6 +1238,8 @@ gpupreagg_begin_glue(CustomPlan *node, EState *estate, int eflags)
     rc = gpupreagg_begin(gpreagg->plan, gpreagg->idx, 0, gpupreagg_next_chunk, gpas, &gpas->state);
     if (rc != 0)
         elog(ERROR, "PG-Strom: GpuPreAgg: %s (%s)", pgs_last_error(), pgstrom_strerror(rc));
+    gpas->next_live = live_states;
+    live_states = gpas;
     return &gpas->cps;
 }
 
@@ -1189,8 +1265,11 @@ static void
 gpupreagg_end_glue(CustomPlanState *node)
 {
     GpuPreAggState *gpas = (GpuPreAggState *) node;
-    const char     *notice = gpupreagg_end(gpas->state);
+    const char     *notice = NULL;
 
+    live_states_remove(gpas);
+    if (gpas->state)
+        notice = gpupreagg_end(gpas->state);
     if (notice)
         elog(NOTICE, "%s", notice);     /* "GpuPreAgg: %u chunks were re-checked by CPU" */
     gpas->state = NULL;
@@ -1307,6 +1386,7 @@ _PG_init(void)
      * runs a GpuPreAgg (pgs_cuda_init is idempotent and cheap) */
     pgstrom_init_gucs();
     pgstrom_init_gpupreagg();
+    RegisterResourceReleaseCallback(pgstrom_release_callback, NULL);
     planner_hook_next = planner_hook;
-    planner_hook = pgstrom_grafter_entrypoint;
+    planner_hook = pgstrom_grafter_with_subplans;
 }

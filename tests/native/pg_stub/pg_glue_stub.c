@@ -387,6 +387,21 @@ pg_stub_set_guc(const char *name, const char *value)
     return -1;
 }
 
+/* ---- resource owner: AbortTransaction runs the release callbacks ---- */
+static ResourceReleaseCallback stub_release_cb[8];
+static void *stub_release_arg[8];
+static int   stub_nrelease = 0;
+void RegisterResourceReleaseCallback(ResourceReleaseCallback callback, void *arg)
+{ stub_release_cb[stub_nrelease] = callback; stub_release_arg[stub_nrelease++] = arg; }
+int
+pg_stub_abort_transaction(void)
+{
+    for (int i = 0; i < stub_nrelease; i++)
+        for (int phase = 0; phase < 3; phase++)
+            stub_release_cb[i]((ResourceReleasePhase) phase, false, true, stub_release_arg[i]);
+    return stub_nrelease;
+}
+
 /* ---- planner ---- */
 static PlannedStmt *stub_next_plan = NULL;
 void pg_stub_set_standard_plan(PlannedStmt *pstmt) { stub_next_plan = pstmt; }

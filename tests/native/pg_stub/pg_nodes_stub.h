@@ -194,6 +194,9 @@ extern void DefineCustomRealVariable(const char *name, const char *short_desc, c
                                      GucContext context, int flags,
                                      void *check_hook, GucRealAssignHook assign_hook, void *show_hook);
 #define CHECK_FOR_INTERRUPTS()  ((void) 0)
+typedef enum { RESOURCE_RELEASE_BEFORE_LOCKS, RESOURCE_RELEASE_LOCKS, RESOURCE_RELEASE_AFTER_LOCKS } ResourceReleasePhase;
+typedef void (*ResourceReleaseCallback)(ResourceReleasePhase phase, bool isCommit, bool isTopLevel, void *arg);
+extern void RegisterResourceReleaseCallback(ResourceReleaseCallback callback, void *arg);
 
 /* ---- catalog look-ups (utils/lsyscache.h, parser/parse_func.h, catalog/namespace.h) ---- */
 extern char *get_rel_name(Oid relid);

@@ -126,6 +126,15 @@ def test_planner_hook_splices_gpupreagg(glue):
     assert glue.pg_stub_set_guc(b"pg_strom.enabled", b"on") == 0
 
 
+def test_abort_callback_is_registered(glue):
+    """restrack.c:180-254: a transaction that aborts while GpuPreAgg states are
+    open must not leak device work.  The glue registers a resource-owner
+    release callback in _PG_init that ends every open state; with none open
+    (no device here) an abort is a no-op."""
+    assert glue.pg_stub_abort_transaction() == 1        # one callback: the glue's
+    assert "GpuPreAgg" in glue.driver_run_planner(10, 1000).decode()    # and the backend lives on
+
+
 def _table(nrows):
     cols = W.where_columns(0, nrows)
     vals = np.zeros((nrows, 4), np.uint64)
