@@ -60,6 +60,8 @@ typedef struct {
     int32_t     naggs;
     int32_t     agg_kind[MAX_AGGS];
     int32_t     agg_col[MAX_AGGS];
+    int32_t     partitioned;    /* GROUP BY with very many groups: see cpu_agg_run */
+    int32_t     pad;
 } cpu_query;
 
 /* transition state of one aggregate of one group */
@@ -294,7 +296,7 @@ combine(agg_state *d, const agg_state *s, int kind)
 
 static void
 scan_range(const cpu_table *t, const cpu_query *q, int64_t lo, int64_t hi,
-           group_table *gt, agg_state *nogroup)
+           group_table *gt, agg_state *nogroup, int part, int nparts)
 {
     for (int64_t r = lo; r < hi; r++)
     {
@@ -312,6 +314,11 @@ scan_range(const cpu_table *t, const cpu_query *q, int64_t lo, int64_t hi,
             int64_t key = (t->coltype[q->key_col] == COL_INT8)
                 ? ((const int64_t *)t->values[q->key_col])[r]
                 : (int64_t)((const int32_t *)t->values[q->key_col])[r];
+            /* key-partitioned plan: this worker owns the groups whose key
+             * hashes into its partition (high bits: the table uses the low) */
+            if (nparts > 1 &&
+                (int)(((mix64((uint64_t)key) >> 40) * (uint64_t)nparts) >> 24) != part)
+                continue;
             st = table_lookup(gt, key);
         }
         else
@@ -325,6 +332,7 @@ typedef struct {
     const cpu_table *t;
     const cpu_query *q;
     int64_t     lo, hi;
+    int         part, nparts;
     group_table gt;
     agg_state   nogroup[MAX_AGGS];
 } worker_arg;
@@ -333,7 +341,7 @@ static void *
 worker_main(void *p)
 {
     worker_arg *w = (worker_arg *)p;
-    scan_range(w->t, w->q, w->lo, w->hi, &w->gt, w->nogroup);
+    scan_range(w->t, w->q, w->lo, w->hi, &w->gt, w->nogroup, w->part, w->nparts);
     return NULL;
 }
 
@@ -353,12 +361,31 @@ cpu_agg_run(const cpu_table *t, const cpu_query *q, int nthreads,
     int64_t per = (t->nrows + nthreads - 1) / nthreads;
     int64_t ngroups = 0;
 
+    /* GROUP BY with very many groups on several cores: per-worker tables over
+     * row ranges would each hold nearly every group and the combine step - one
+     * core re-inserting all of them - costs more than the scan (measured:
+     * 16 cores slower than 1).  Instead every worker reads all keys and
+     * aggregates the groups of its own hash partition: the tables are
+     * disjoint, their union is the result, nothing is combined.  (A worker
+     * per partition behind a repartitioning exchange is what a parallel
+     * executor does with such a plan.) */
+    const int partitioned = (q->partitioned && q->key_col >= 0 && nthreads > 1);
+
     for (int i = 0; i < nthreads; i++)
     {
         w[i].t = t;
         w[i].q = q;
         w[i].lo = per * i < t->nrows ? per * i : t->nrows;
         w[i].hi = per * (i + 1) < t->nrows ? per * (i + 1) : t->nrows;
+        w[i].part = 0;
+        w[i].nparts = 1;
+        if (partitioned)
+        {
+            w[i].lo = 0;
+            w[i].hi = t->nrows;
+            w[i].part = i;
+            w[i].nparts = nthreads;
+        }
         if (q->key_col >= 0)
             table_init(&w[i].gt, 1024, q->naggs);
         for (int j = 0; j < q->naggs; j++)
@@ -381,6 +408,20 @@ cpu_agg_run(const cpu_table *t, const cpu_query *q, int nthreads,
         {
             keys[0] = 0;
             memcpy(states, w[0].nogroup, sizeof(agg_state) * q->naggs);
+        }
+    }
+    else if (partitioned)
+    {
+        /* disjoint tables: the result is their concatenation */
+        for (int i = 0; i < nthreads; i++)
+        {
+            int64_t room = max_groups - ngroups;
+            int64_t ncopy = (int64_t)w[i].gt.nused < room ? (int64_t)w[i].gt.nused : (room > 0 ? room : 0);
+
+            memcpy(keys + ngroups, w[i].gt.keys, sizeof(int64_t) * ncopy);
+            memcpy(states + ngroups * q->naggs, w[i].gt.pool, sizeof(agg_state) * q->naggs * ncopy);
+            ngroups += (int64_t)w[i].gt.nused;
+            table_free(&w[i].gt);
         }
     }
     else

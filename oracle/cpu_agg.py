@@ -27,7 +27,8 @@ class cpu_table(C.Structure):
 class cpu_query(C.Structure):
     _fields_ = [("qual_col", C.c_int32), ("qual_const", C.c_int32),
                 ("key_col", C.c_int32), ("naggs", C.c_int32),
-                ("agg_kind", C.c_int32 * 16), ("agg_col", C.c_int32 * 16)]
+                ("agg_kind", C.c_int32 * 16), ("agg_col", C.c_int32 * 16),
+                ("partitioned", C.c_int32), ("pad", C.c_int32)]
 
 
 class cpu_heap(C.Structure):
@@ -74,7 +75,7 @@ QUERIES = {
     "where_agg": dict(coltypes=["int4", "int4", "float8", "int4"], qual=(0, 10), key=1, aggs=[
         ("count_star", 0), ("sum_int4", 3), ("avg_float8", 2), ("min_float8", 2),
         ("max_float8", 2)]),
-    "high_cardinality": dict(coltypes=["int8", "int8", "float8"], qual=None, key=0, aggs=[
+    "high_cardinality": dict(coltypes=["int8", "int8", "float8"], qual=None, key=0, partitioned=True, aggs=[
         ("count_star", 0), ("avg_int8", 1), ("avg_float8", 2), ("var_float8", 2)]),
 }
 
@@ -102,6 +103,7 @@ def _query(qd, qual_const):
     q.qual_const = 0 if qd["qual"] is None else (qual_const if qual_const is not None else qd["qual"][1])
     q.key_col = -1 if qd["key"] is None else qd["key"]
     q.naggs = len(qd["aggs"])
+    q.partitioned = 1 if qd.get("partitioned") else 0
     for j, (k, c) in enumerate(qd["aggs"]):
         q.agg_kind[j] = KINDS[k]
         q.agg_col[j] = c

@@ -75,3 +75,15 @@ def test_heap_pages_look_like_postgres_pages(lib):
     off3, len3 = lps[3] & 0x7fff, lps[3] >> 17
     assert page[off3 + 20] & 1 and page[off3 + 23] == 0b10 and page[off3 + 22] == 24 and len3 == 32
     assert upper == min(lp & 0x7fff for lp in lps)
+
+
+def test_key_partitioned_plan_equals_one_core(lib):
+    """GROUP BY with very many groups on several cores: every worker owns the
+    groups of one hash partition (no combine step).  Same groups, same states
+    as one core (the float columns sit on a dyadic grid: sums are exact)."""
+    cols = W.WORKLOADS["high_cardinality"]["columns"](0, 400_000)
+    _, k1, s1, n1 = cpu_agg.run("high_cardinality", cols, nthreads=1, max_groups=1 << 19)
+    want = _states("high_cardinality", k1, s1, n1)
+    for nthreads in (2, 7):
+        _, k2, s2, n2 = cpu_agg.run("high_cardinality", cols, nthreads=nthreads, max_groups=1 << 19)
+        assert n2 == n1 and _states("high_cardinality", k2, s2, n2) == want
