@@ -32,6 +32,7 @@
 #include "nodes/makefuncs.h"
 #include "nodes/plannodes.h"
 #include "nodes/primnodes.h"
+#include "optimizer/cost.h"
 #include "optimizer/planner.h"
 #include "parser/parse_func.h"
 #include "utils/guc.h"
@@ -1009,14 +1010,46 @@ graft_plan(JNode *j, Plan *orig, pgs_plan *plan)
     {
         /* target lists above a GpuPreAgg node refer to its output columns */
         JNode *child = jget(j, "lefttree");
+        JNode *gpreagg_json = NULL;
+        bool   sort_between = false;
         bool   spliced = false;
 
         for (JNode *c = child; c && c->kind == J_OBJ; c = jget(c, "lefttree"))
         {
             if (jis(c, "node", "CustomPlan") && jis(c, "custom_name", "GpuPreAgg"))
+            {
+                gpreagg_json = c;
                 spliced = true;
+            }
             if (!jis(c, "node", "Sort"))
                 break;
+            sort_between = true;
+        }
+        if (spliced && IsA(orig, Agg) && !guc_debug_force_gpupreagg &&
+            jget(gpreagg_json, "total_cost") != NULL)
+        {
+            /* gpupreagg.c:2105-2118: the library has priced the GpuPreAgg node
+             * (cost_gpupreagg, :366-464); what the Agg - and the Sort, if one
+             * sits between - cost on top of it is PostgreSQL's own arithmetic.
+             * The plan is only rewritten when that comes out cheaper. */
+            Agg    *agg = (Agg *) orig;
+            Path    dummy;
+            Cost    startup = jget(gpreagg_json, "startup_cost") ? jget(gpreagg_json, "startup_cost")->num : 0.0;
+            Cost    total = jget(gpreagg_json, "total_cost")->num;
+            double  rows = jget(gpreagg_json, "plan_rows") ? jget(gpreagg_json, "plan_rows")->num : orig->plan_rows;
+            int     width = jint(gpreagg_json, "plan_width", orig->plan_width);
+
+            memset(&dummy, 0, sizeof(dummy));
+            if (sort_between)
+            {
+                cost_sort(&dummy, NULL, NIL, total, rows, width, 0.0, work_mem, -1.0);
+                startup = dummy.startup_cost;
+                total = dummy.total_cost;
+            }
+            cost_agg(&dummy, NULL, agg->aggstrategy, NULL, agg->numCols, (double) agg->numGroups,
+                     startup, total, rows);
+            if (orig->total_cost <= dummy.total_cost)
+                return orig;            /* PostgreSQL's plan stays */
         }
         if (spliced)
         {

@@ -402,6 +402,48 @@ pg_stub_abort_transaction(void)
     return stub_nrelease;
 }
 
+/* ---- costs: the shape of costsize.c's cost_sort / cost_agg (in-memory sort,
+ * no aggregate transition costs) with PostgreSQL's default constants ---- */
+int    work_mem = 4096;
+double cpu_tuple_cost = 0.01, cpu_operator_cost = 0.0025;
+void
+cost_sort(Path *path, PlannerInfo *root, List *pathkeys, Cost input_cost, double tuples, int width,
+          Cost comparison_cost, int sort_mem, double limit_tuples)
+{
+    double  n = tuples < 2.0 ? 2.0 : tuples;
+    double  lg = 0.0;
+
+    (void) root; (void) pathkeys; (void) width; (void) sort_mem; (void) limit_tuples;
+    for (double x = n; x > 1.0; x /= 2.0)
+        lg += 1.0;
+    path->startup_cost = input_cost + (comparison_cost + 2.0 * cpu_operator_cost) * n * lg;
+    path->total_cost = path->startup_cost + cpu_operator_cost * n;
+}
+void
+cost_agg(Path *path, PlannerInfo *root, AggStrategy aggstrategy, const AggClauseCosts *aggcosts,
+         int numGroupCols, double numGroups, Cost input_startup_cost, Cost input_total_cost,
+         double input_tuples)
+{
+    (void) root; (void) aggcosts;
+    if (aggstrategy == AGG_PLAIN)
+    {
+        path->startup_cost = input_total_cost;
+        path->total_cost = path->startup_cost + cpu_tuple_cost;
+    }
+    else if (aggstrategy == AGG_SORTED)
+    {
+        path->startup_cost = input_startup_cost;
+        path->total_cost = input_total_cost + cpu_operator_cost * numGroupCols * input_tuples +
+            cpu_tuple_cost * numGroups;
+    }
+    else
+    {
+        path->startup_cost = input_total_cost + cpu_operator_cost * numGroupCols * input_tuples;
+        path->total_cost = path->startup_cost + cpu_tuple_cost * numGroups;
+    }
+    path->rows = numGroups;
+}
+
 /* ---- planner ---- */
 static PlannedStmt *stub_next_plan = NULL;
 void pg_stub_set_standard_plan(PlannedStmt *pstmt) { stub_next_plan = pstmt; }

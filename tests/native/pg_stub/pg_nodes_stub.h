@@ -170,6 +170,18 @@ typedef struct CustomPlanMethods
 typedef struct CustomPlan { Plan plan; const CustomPlanMethods *methods; } CustomPlan;
 typedef struct CustomPlanState { PlanState ps; const CustomPlanMethods *methods; } CustomPlanState;
 
+/* ---- optimizer/cost.h ---- */
+typedef struct Path { NodeTag type; Cost startup_cost, total_cost; double rows; } Path;
+typedef struct PlannerInfo PlannerInfo;
+typedef struct AggClauseCosts AggClauseCosts;
+extern int    work_mem;
+extern double cpu_tuple_cost, cpu_operator_cost;
+extern void cost_sort(Path *path, PlannerInfo *root, List *pathkeys, Cost input_cost, double tuples, int width,
+                      Cost comparison_cost, int sort_mem, double limit_tuples);
+extern void cost_agg(Path *path, PlannerInfo *root, AggStrategy aggstrategy, const AggClauseCosts *aggcosts,
+                     int numGroupCols, double numGroups, Cost input_startup_cost, Cost input_total_cost,
+                     double input_tuples);
+
 /* ---- planner hook, GUC, miscadmin ---- */
 typedef struct Query Query;
 typedef struct ParamListInfoData *ParamListInfo;

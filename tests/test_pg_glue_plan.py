@@ -126,6 +126,27 @@ def test_planner_hook_splices_gpupreagg(glue):
     assert glue.pg_stub_set_guc(b"pg_strom.enabled", b"on") == 0
 
 
+def test_cost_decision(glue):
+    """gpupreagg.c:2105-2118: unless pg_strom.debug_force_gpupreagg is on, the
+    plan is only rewritten when the Agg over GpuPreAgg (the library's
+    cost_gpupreagg numbers + PostgreSQL's cost_agg / cost_sort on top) comes
+    out cheaper than PostgreSQL's own plan."""
+    assert glue.pg_stub_set_guc(b"pg_strom.enabled", b"on") == 0
+    assert glue.pg_stub_set_guc(b"pg_strom.debug_force_gpupreagg", b"off") == 0
+    try:
+        # 12.5 M rows into 1000 groups: the device plan is cheaper
+        assert "GpuPreAgg" in glue.driver_run_planner(10, 1000).decode()
+        # an absurd set-up cost: PostgreSQL's plan stays, the scan keeps its qual
+        assert glue.pg_stub_set_guc(b"gpu_setup_cost", b"5e9") == 0
+        assert glue.driver_run_planner(10, 1000).decode() == "Agg[6] -> SeqScan[4] quals=1"
+        # ... unless forced
+        assert glue.pg_stub_set_guc(b"pg_strom.debug_force_gpupreagg", b"on") == 0
+        assert "GpuPreAgg" in glue.driver_run_planner(10, 1000).decode()
+    finally:
+        assert glue.pg_stub_set_guc(b"gpu_setup_cost", b"500") == 0
+        assert glue.pg_stub_set_guc(b"pg_strom.debug_force_gpupreagg", b"on") == 0
+
+
 def test_abort_callback_is_registered(glue):
     """restrack.c:180-254: a transaction that aborts while GpuPreAgg states are
     open must not leak device work.  The glue registers a resource-owner
