@@ -140,6 +140,14 @@ int         pgstrom_fixup_kernel_numeric(Datum datum, char *buf, size_t buflen);
  * bytes + length in one Datum); -> varlena with a 4-byte header, bpchar padded
  * to `typmod` (atttypmod, -1 = none).  Returns the size, 0 if buf is too small */
 size_t      pgstrom_fixup_kernel_text(Datum datum, int typmod, void *buf, size_t buflen);
+/* the same for any key: a text / bpchar key of more than 7 bytes comes back
+ * as a word of the session's key heap (pgs_preagg_key_heap(), section 5) -
+ * top byte 0x80, below it the offset of the string in that heap.  This is the
+ * reference's fix-up of varlena key pointers to host addresses
+ * (opencl_gpupreagg.h:326-366, pg_fixup_tupslot_varlena opencl_common.h:1060-1100) */
+size_t      pgstrom_fixup_kernel_text_heap(Datum datum, int typmod,
+                                           const void *key_heap, size_t key_heap_len,
+                                           void *buf, size_t buflen);
 /* PostgreSQL numeric varlena <-> decimal text (for numeric Consts and for
  * harnesses without a PostgreSQL to make datums); return the length, 0 on
  * error */
@@ -236,6 +244,21 @@ int64_t     pgs_preagg_recheck_rows(pgs_session *session, pgs_ticket ticket,
 int         pgs_preagg_finish(pgs_session *session, kern_data_store *kds_dst,
                               int reset, uint32_t *nrows_needed,
                               int32_t *status);
+/* Long text / bpchar grouping keys (opencl_gpupreagg.h:326-366: the
+ * reference keeps a varlena key as an offset into the chunk's toast area and
+ * fixes the pointers up for the host): a program that groups by text columns
+ * gets a key heap in HBM (GUC pg_strom.key_heap_size, MB; lookup table sized
+ * from the planner's group estimate).  A key of more than 7 bytes is stored
+ * there once and travels as an 8-byte word.  After pgs_preagg_finish() this
+ * returns the host copy of the heap the words of the returned rows point
+ * into (valid until the next finish / close; NULL, 0 when no long key was
+ * seen) - pass it to pgstrom_fixup_kernel_text_heap().  A full heap turns
+ * further rows with unseen long keys into CpuReCheck rows.  States with a key
+ * heap are session-local: the merge / export / import calls below refuse
+ * them (StromError_BadRequestMessage) and every device returns its own
+ * partial rows to PostgreSQL's final Agg. */
+int         pgs_preagg_key_heap(pgs_session *session, const void **heap,
+                                size_t *heap_len);
 /* NCCL communicator for one-process-per-GPU deployments: rank 0 makes the
  * id, the launcher (MPI, torch.distributed, PostgreSQL shared memory ...)
  * hands its 128 bytes to every rank, each rank joins.  libnccl.so.2 is
@@ -326,6 +349,13 @@ int         gpupreagg_begin(pgs_plan *plan, int idx, int device,
 /* ExecCustomPlan: gpupreagg_exec (gpupreagg.c:2665): returns 1 and fills one
  * partial row, 0 at end of data, <0 on error (-errcode) */
 int         gpupreagg_exec(pgs_gpupreagg_state *state, Datum *values, char *isnull);
+/* text / bpchar grouping keys of those rows are "kernel text" words; the
+ * strings of the long ones live in the key heap this returns once the first
+ * row has come back (pgs_preagg_key_heap; pgstrom_fixup_kernel_text_heap
+ * makes the varlena - the glue does that where the reference's
+ * pg_fixup_tupslot_varlena made host pointers) */
+int         gpupreagg_key_heap(pgs_gpupreagg_state *state, const void **heap,
+                               size_t *heap_len);
 /* rows the device left to the host: (chunk sequence number, row index) */
 int64_t     gpupreagg_recheck_rows(pgs_gpupreagg_state *state,
                                    uint32_t *chunk_seq, uint32_t *rows,

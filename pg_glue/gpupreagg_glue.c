@@ -26,6 +26,7 @@
 #include "fmgr.h"
 #include "miscadmin.h"
 #include "access/htup_details.h"
+#include "catalog/pg_type.h"
 #include "commands/explain.h"
 #include "executor/executor.h"
 #include "lib/stringinfo.h"
@@ -933,7 +934,17 @@ typedef struct GpuPreAggState
     uint32                  nrows, nrooms;
     char                  **values;     /* [ncols]: packed values, or varlena pointers */
     uint8_t               **isnull;     /* [ncols] */
+    /* text / bpchar grouping keys of the result: the library returns them as
+     * "kernel text" words, the slot needs varlena pointers */
+    int                     nresult;
+    int32                  *key_typmod;     /* [nresult]: KEY_NOT_TEXT or the atttypmod */
+    char                  **key_buf;        /* [nresult]: varlena of the current row */
+    size_t                 *key_buflen;
 } GpuPreAggState;
+#define KEY_NOT_TEXT    (-2)
+#ifndef Max
+#define Max(x, y)       ((x) > (y) ? (x) : (y))
+#endif
 
 /* Every state that holds a session is on this list until EndCustomPlan; a
  * transaction that aborts in between gets them closed by the resource-owner
@@ -1231,6 +1242,29 @@ gpupreagg_begin_glue(CustomPlan *node, EState *estate, int eflags)
     ExecInitResultTupleSlot(estate, &gpas->cps.ps);
     ExecAssignResultTypeFromTL(&gpas->cps.ps);
 
+    /* which result columns are text / bpchar grouping keys (a GpuPreAgg
+     * target list carries them as plain Vars of the outer plan) */
+    gpas->nresult = list_length(node->plan.targetlist);
+    gpas->key_typmod = (int32 *) palloc0(sizeof(int32) * (gpas->nresult + 1));
+    gpas->key_buf = (char **) palloc0(sizeof(char *) * (gpas->nresult + 1));
+    gpas->key_buflen = (size_t *) palloc0(sizeof(size_t) * (gpas->nresult + 1));
+    {
+        ListCell   *lc;
+        int         c = 0;
+
+        foreach(lc, node->plan.targetlist)
+        {
+            TargetEntry *tle = (TargetEntry *) lfirst(lc);
+            Var        *var = (Var *) tle->expr;
+
+            gpas->key_typmod[c] = KEY_NOT_TEXT;
+            if (var != NULL && IsA(var, Var) &&
+                (var->vartype == TEXTOID || var->vartype == BPCHAROID))
+                gpas->key_typmod[c] = var->vartypmod;
+            c++;
+        }
+    }
+
     /* column arrays of one chunk (pg_strom.chunk_size MB of outer tuples) */
     gpas->ncols = gpas->scan_desc->natts;
     gpas->colmeta = (kern_colmeta *) palloc0(sizeof(kern_colmeta) * gpas->ncols);
@@ -1291,6 +1325,40 @@ gpupreagg_exec_glue(CustomPlanState *node)
         elog(ERROR, "PG-Strom: GpuPreAgg: %s (%s)", pgs_last_error(), pgstrom_strerror(-rc));
     if (rc == 0)
         return NULL;
+    /* varlena grouping keys: word -> varlena that lives until the next call
+     * (the reference's kernels fix the key pointers up to host addresses,
+     * opencl_gpupreagg.h:326-366; here the strings of long keys come from the
+     * session's key heap) */
+    for (int c = 0; c < gpas->nresult; c++)
+    {
+        const void *heap = NULL;
+        size_t      heap_len = 0, n;
+
+        if (gpas->key_typmod[c] == KEY_NOT_TEXT || slot->tts_isnull[c])
+            continue;
+        if (gpupreagg_key_heap(gpas->state, &heap, &heap_len) != 0)
+            elog(ERROR, "PG-Strom: GpuPreAgg: %s", pgs_last_error());
+        for (;;)
+        {
+            if (gpas->key_buf[c] == NULL)
+            {
+                gpas->key_buflen[c] = 256;
+                gpas->key_buf[c] = (char *) palloc(gpas->key_buflen[c]);
+            }
+            n = pgstrom_fixup_kernel_text_heap(slot->tts_values[c], gpas->key_typmod[c],
+                                               heap, heap_len,
+                                               gpas->key_buf[c], gpas->key_buflen[c]);
+            if (n > 0)
+                break;
+            /* the longest value a key heap of this size can hold, padded */
+            if (gpas->key_buflen[c] >= heap_len + 4 * (size_t) Max(gpas->key_typmod[c], 0) + 64)
+                elog(ERROR, "PG-Strom: GpuPreAgg: corrupted text grouping key");
+            pfree(gpas->key_buf[c]);
+            gpas->key_buflen[c] = heap_len + 4 * (size_t) Max(gpas->key_typmod[c], 0) + 64;
+            gpas->key_buf[c] = (char *) palloc(gpas->key_buflen[c]);
+        }
+        slot->tts_values[c] = PointerGetDatum(gpas->key_buf[c]);
+    }
     return ExecStoreVirtualTuple(slot);
 }
 

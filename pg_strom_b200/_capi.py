@@ -89,6 +89,8 @@ PROTOTYPES = {
                                            C.POINTER(C.c_uint64), C.c_char_p]),
     "pgstrom_fixup_kernel_numeric": (C.c_int, [C.c_uint64, C.c_char_p, C.c_size_t]),
     "pgstrom_fixup_kernel_text": (C.c_size_t, [C.c_uint64, C.c_int, C.c_void_p, C.c_size_t]),
+    "pgstrom_fixup_kernel_text_heap": (C.c_size_t, [C.c_uint64, C.c_int, C.c_void_p, C.c_size_t,
+                                                    C.c_void_p, C.c_size_t]),
     "pgstrom_numeric_from_text": (C.c_size_t, [C.c_char_p, C.c_void_p, C.c_size_t]),
     "pgstrom_numeric_to_text": (C.c_size_t, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "pgs_program_build": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p),
@@ -131,6 +133,7 @@ PROTOTYPES = {
     "pgs_preagg_abort": (None, [C.c_void_p]),
     "pgs_preagg_close": (None, [C.c_void_p]),
     "pgs_preagg_stream": (C.c_void_p, [C.c_void_p]),
+    "pgs_preagg_key_heap": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "pgs_preagg_launch_count": (C.c_uint64, [C.c_void_p]),
     "pgs_device_alloc": (C.c_void_p, [C.c_int, C.c_size_t]),
     "pgs_device_free": (None, [C.c_int, C.c_void_p]),
@@ -139,6 +142,7 @@ PROTOTYPES = {
     "gpupreagg_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, BULK_EXEC_FN, C.c_void_p,
                                   C.POINTER(C.c_void_p)]),
     "gpupreagg_exec": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p]),
+    "gpupreagg_key_heap": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "gpupreagg_recheck_rows": (C.c_int64, [C.c_void_p, C.POINTER(C.c_uint32),
                                            C.POINTER(C.c_uint32), C.c_int64]),
     "gpupreagg_recheck_chunk": (C.c_void_p, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),

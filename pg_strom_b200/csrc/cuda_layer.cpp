@@ -924,6 +924,10 @@ struct pgs_session
     bool            push_pending = false;
     std::string     perfmon_buf;
     bool            aborted = false;
+    /* key heap: long text / bpchar grouping keys (kern_textlib.cuh) */
+    pgs_keyheap_ctl kh = {NULL, NULL, NULL, 0, 0, 0};
+    std::vector<unsigned char> kh_host;     /* the heap as the last finish saw it */
+    uint64_t        kh_finishes = 0;
 };
 
 static int launch_kernel(pgs_session *s, cudaKernel_t k, int grid, int block,
@@ -1190,9 +1194,53 @@ state_nslots(const pgs_session *s)
     return (size_t)s->gs.gh_nslots + (size_t)s->gs.part_nparts * s->gs.part_slots;
 }
 
+/* The key heap of a program that groups by text / bpchar columns: values of
+ * more than 7 bytes are stored once in HBM and travel as 8-byte words
+ * (kern_textlib.cuh; the reference moves varlena keys as toast offsets,
+ * opencl_gpupreagg.h:326-366).  pg_strom.key_heap_size (MB; 0 = no heap:
+ * rows with a long key are re-checked on the host) bounds the strings, the
+ * lookup table follows the planner's estimate of the number of groups. */
+static int
+session_alloc_keyheap(pgs_session *s)
+{
+    long long mb = pgs::guc_int("pg_strom.key_heap_size");
+    if (s->desc.num_text_keys == 0 || mb <= 0)
+        return StromError_Success;
+    void   *d_ctl = NULL;
+    size_t  ctl_bytes = 0;
+    if (cudaLibraryGetGlobal(&d_ctl, &ctl_bytes, s->library, "pgs_keyheap") != cudaSuccess ||
+        ctl_bytes != sizeof(pgs_keyheap_ctl))
+    {
+        cudaGetLastError();
+        return StromError_Success;      /* program without the lookup: long keys are re-checked */
+    }
+    size_t nslots = 1u << 16;
+    double want = 4.0 * std::max(1.0, s->config.num_groups) * s->desc.num_text_keys;
+    while (nslots < (1u << 26) && (double)nslots < want)
+        nslots <<= 1;
+    char *base = NULL;
+    size_t heap_bytes = (size_t)mb << 20;
+    CUDA_CHECK(cudaMalloc((void **)&base, 16 * nslots + 128 + heap_bytes));
+    s->kh.slots = (cl_ulong *)base;
+    s->kh.heap_used = (cl_ulong *)(base + 16 * nslots);
+    s->kh.heap = (unsigned char *)(base + 16 * nslots + 128);
+    s->kh.heap_bytes = heap_bytes;
+    s->kh.nslots = (cl_uint)nslots;
+    s->kh.max_probe = 512;
+    CUDA_CHECK(cudaMemcpy(d_ctl, &s->kh, sizeof(pgs_keyheap_ctl), cudaMemcpyHostToDevice));
+    return StromError_Success;
+}
+
 static int
 session_init_state(pgs_session *s)
 {
+    if (s->kh.nslots > 0)
+    {
+        /* a new scan starts with an empty key heap (stream ordered, like the
+         * state itself; what the host copied at the last finish stays valid) */
+        CUDA_CHECK(cudaMemsetAsync(s->kh.slots, 0, 16 * (size_t)s->kh.nslots, s->s_exec));
+        CUDA_CHECK(cudaMemsetAsync(s->kh.heap_used, 0, sizeof(cl_ulong), s->s_exec));
+    }
     void *args[] = { &s->gs };
     int grid = std::max(1, std::min<int>(s->num_sms * 8,
                                          (int)((state_nslots(s) + 255) / 256)));
@@ -1475,6 +1523,8 @@ pgs_preagg_open(pgs_program *program, const kern_parambuf *kparams,
     }
     {
         int rc = session_alloc_state(s);
+        if (rc == StromError_Success)
+            rc = session_alloc_keyheap(s);
         if (rc == StromError_Success)
             rc = session_init_state(s);
         if (rc != StromError_Success)
@@ -2065,6 +2115,20 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
         else if (h_status == StromError_Success)
             h_status = StromError_DataStoreNoSpace;
     }
+    if (e == cudaSuccess && s->kh.nslots > 0 && h_status == StromError_Success)
+    {
+        /* the strings behind the key-heap words of the result rows
+         * (pgs_preagg_key_heap / pgstrom_fixup_kernel_text_heap) */
+        cl_ulong used = 0;
+        e = cudaMemcpy(&used, s->kh.heap_used, sizeof(used), cudaMemcpyDeviceToHost);
+        used = std::min<cl_ulong>(used, s->kh.heap_bytes);
+        s->kh_host.resize((size_t)used);
+        if (e == cudaSuccess && used > 0)
+            e = cudaMemcpy(s->kh_host.data(), s->kh.heap, (size_t)used, cudaMemcpyDeviceToHost);
+        s->kh_finishes++;
+        s->num_dma_recv += 1;
+        s->bytes_dma_recv += used;
+    }
     if (e != cudaSuccess)
     {
         set_error("pgs_preagg_finish: %s", cudaGetErrorString(e));
@@ -2089,6 +2153,23 @@ pgs_preagg_finish(pgs_session *s, kern_data_store *kds_dst, int reset,
     return StromErrorIsSignificant(h_status) ? h_status : StromError_Success;
 }
 
+/* States whose text keys went through the key heap carry session-local
+ * words: they cannot be merged with another session's state.  Every device
+ * flushes its own partial rows instead, and PostgreSQL's final Agg merges
+ * rows of one key as it does in the reference (gpupreagg.c:2169-2186). */
+static int
+refuse_keyheap(const pgs_session *s, const char *what)
+{
+    if (s && s->kh.nslots > 0)
+    {
+        set_error("%s: the state groups by text keys of the session's key heap and "
+                  "cannot be merged across sessions; flush every device's own "
+                  "partial rows (or set pg_strom.key_heap_size = 0)", what);
+        return StromError_BadRequestMessage;
+    }
+    return StromError_Success;
+}
+
 extern "C" int
 pgs_preagg_state_reset(pgs_session *s)
 {
@@ -2106,6 +2187,8 @@ extern "C" int
 pgs_preagg_state_export(pgs_session *s, void *device_buf, size_t buflen,
                         uint32_t *nrecords, size_t *record_bytes)
 {
+    if (refuse_keyheap(s, "pgs_preagg_state_export") != StromError_Success)
+        return StromError_BadRequestMessage;
     CUDA_CHECK(cudaSetDevice(s->ordinal));
     int rc = drain(s);
     if (rc != StromError_Success)
@@ -2139,6 +2222,8 @@ pgs_preagg_state_export(pgs_session *s, void *device_buf, size_t buflen,
 extern "C" int
 pgs_preagg_state_import(pgs_session *s, const void *device_buf, uint32_t nrecords)
 {
+    if (refuse_keyheap(s, "pgs_preagg_state_import") != StromError_Success)
+        return StromError_BadRequestMessage;
     if (s)
         s->push_pending = false;
     CUDA_CHECK(cudaSetDevice(s->ordinal));
@@ -2283,6 +2368,8 @@ extern "C" int pgs_preagg_merge_exchange(pgs_session *s, void *nccl_comm, int ra
 extern "C" int
 pgs_preagg_merge_nccl(pgs_session *s, void *nccl_comm, int rank, int nranks, int root)
 {
+    if (refuse_keyheap(s, "pgs_preagg_merge_nccl") != StromError_Success)
+        return StromError_BadRequestMessage;
     /* ncclUint8 = 1 */
     const int NCCL_UINT8 = 1;
     int rc = nccl_load();
@@ -2365,6 +2452,8 @@ pgs_preagg_merge_nccl(pgs_session *s, void *nccl_comm, int rank, int nranks, int
 extern "C" int
 pgs_preagg_peer_setup(pgs_session *s, int rank, int nranks, int root, void *ipc_handle_64)
 {
+    if (refuse_keyheap(s, "pgs_preagg_peer_setup") != StromError_Success)
+        return StromError_BadRequestMessage;
     if (!s || nranks < 1 || nranks > PGS_EXCHANGE_MAX_RANKS || rank < 0 || rank >= nranks ||
         root < 0 || root >= nranks)
     {
@@ -2483,6 +2572,8 @@ merge_trace_end(pgs_session *s)
 extern "C" int
 pgs_preagg_merge_peer(pgs_session *s)
 {
+    if (refuse_keyheap(s, "pgs_preagg_merge_peer") != StromError_Success)
+        return StromError_BadRequestMessage;
     if (!s || !s->peer_area || !s->peer_root_area)
     {
         set_error("pgs_preagg_merge_peer: no exchange area (pgs_preagg_peer_setup / _attach)");
@@ -2567,6 +2658,8 @@ import_async(pgs_session *s, const void *device_buf, size_t nrecords)
 extern "C" int
 pgs_preagg_merge_exchange(pgs_session *s, void *nccl_comm, int rank, int nranks)
 {
+    if (refuse_keyheap(s, "pgs_preagg_merge_exchange") != StromError_Success)
+        return StromError_BadRequestMessage;
     const int NCCL_UINT8 = 1;
     if (!s || !nccl_comm || nranks < 1 || nranks > PGS_EXCHANGE_MAX_RANKS ||
         rank < 0 || rank >= nranks)
@@ -2756,6 +2849,9 @@ pgs_preagg_perfmon_json(pgs_session *s)
     o->set("stage_bytes", (long long)(s->tile_rows / 1024) * s->desc.stage_bytes);
     o->set("row_bytes", (long long)s->desc.row_bytes);
     o->set("slot_bytes", (long long)s->desc.slot_bytes);
+    o->set("key_heap_nslots", (long long)s->kh.nslots);
+    o->set("key_heap_bytes", (long long)s->kh.heap_bytes);
+    o->set("key_heap_used", (long long)s->kh_host.size());
     s->perfmon_buf = o->dump();
     return s->perfmon_buf.c_str();
 }
@@ -2812,6 +2908,7 @@ pgs_preagg_close(pgs_session *s)
         if (s->gs.part_recs) cudaFree(s->gs.part_recs);
         if (s->gs.part_images) cudaFree(s->gs.part_images);
         if (s->gs.part_seg_counts) cudaFree(s->gs.part_seg_counts);
+        if (s->kh.slots) cudaFree(s->kh.slots);
         if (s->d_result) cudaFree(s->d_result);
         if (s->d_kg_misc) cudaFree(s->d_kg_misc);
         if (s->h_result_head) cudaFreeHost(s->h_result_head);
@@ -2823,6 +2920,19 @@ pgs_preagg_close(pgs_session *s)
         if (s->library) cudaLibraryUnload(s->library);
     }
     delete s;
+}
+
+extern "C" int
+pgs_preagg_key_heap(pgs_session *s, const void **heap, size_t *heap_len)
+{
+    if (!s || !heap || !heap_len)
+    {
+        set_error("pgs_preagg_key_heap: bad arguments");
+        return StromError_BadRequestMessage;
+    }
+    *heap = s->kh_host.empty() ? NULL : s->kh_host.data();
+    *heap_len = s->kh_host.size();
+    return StromError_Success;
 }
 
 extern "C" void *

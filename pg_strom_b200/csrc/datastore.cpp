@@ -535,16 +535,49 @@ pgstrom_fixup_kernel_numeric(Datum datum, char *buf, size_t buflen)
 size_t
 pgstrom_fixup_kernel_text(Datum datum, int typmod, void *buf, size_t buflen)
 {
+    return pgstrom_fixup_kernel_text_heap(datum, typmod, NULL, 0, buf, buflen);
+}
+
+/*
+ * The same for any text / bpchar grouping key of a result row.  A key of more
+ * than 7 bytes comes back as a word of the session's key heap (top byte 0x80,
+ * below it the offset of [uint64 length | bytes] in the heap that
+ * pgs_preagg_key_heap() returns after pgs_preagg_finish()).  Returns 0 for a
+ * word that does not point at an entry inside the heap.
+ */
+size_t
+pgstrom_fixup_kernel_text_heap(Datum datum, int typmod,
+                               const void *key_heap, size_t key_heap_len,
+                               void *buf, size_t buflen)
+{
     cl_ulong    word = (cl_ulong)datum;
     size_t      len = (size_t)(word >> 56);
-    unsigned char payload[8];
+    unsigned char inline_payload[8];
+    const unsigned char *payload = inline_payload;
     size_t      nchars = 0, pad = 0;
 
-    if (len > 7)
+    if (len == 0x80)
+    {
+        size_t      off = (size_t)(word & 0x00FFFFFFFFFFFFFFULL);
+        uint64_t    n;
+
+        if (!key_heap || (off & 7) != 0 || off + 8 > key_heap_len)
+            return 0;
+        memcpy(&n, (const char *)key_heap + off, 8);
+        if (n <= 7 || n > key_heap_len - off - 8)
+            return 0;
+        len = (size_t)n;
+        payload = (const unsigned char *)key_heap + off + 8;
+    }
+    else if (len > 7)
         return 0;
+    else
+    {
+        for (size_t i = 0; i < len; i++)
+            inline_payload[i] = (unsigned char)(word >> (8 * i));
+    }
     for (size_t i = 0; i < len; i++)
     {
-        payload[i] = (unsigned char)(word >> (8 * i));
         if ((payload[i] & 0xC0) != 0x80)    /* not a UTF-8 continuation byte */
             nchars++;
     }

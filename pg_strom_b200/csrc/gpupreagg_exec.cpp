@@ -251,6 +251,16 @@ gpupreagg_exec(pgs_gpupreagg_state *st, Datum *values, char *isnull)
     return rc == StromError_Success ? 1 : -rc;
 }
 
+/* the strings behind long text / bpchar keys of the rows gpupreagg_exec()
+ * returns (pgs_preagg_key_heap): valid until ReScan / EndCustomPlan */
+int
+gpupreagg_key_heap(pgs_gpupreagg_state *st, const void **heap, size_t *heap_len)
+{
+    if (!st || !st->session)
+        return StromError_BadRequestMessage;
+    return pgs_preagg_key_heap(st->session, heap, heap_len);
+}
+
 int64_t
 gpupreagg_recheck_rows(pgs_gpupreagg_state *st, uint32_t *chunk_seq, uint32_t *rows,
                        int64_t max_rows)

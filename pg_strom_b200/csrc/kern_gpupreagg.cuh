@@ -4937,13 +4937,20 @@ gpupreagg_peer_pull(pgs_gstate gs, cl_ulong *area, cl_uint root, cl_uint nranks,
  * gpupreagg_describe - layout constants for the host
  * ------------------------------------------------------------------ */
 #define PGS_X_INCOL_ROWBYTES(slot,colidx,attlen)    rb += (attlen);
+/* text / bpchar grouping keys (their long values live in the key heap) */
+__host__ __device__ constexpr cl_uint pgs_is_text_key(const void *) { return 0; }
+#ifdef KERN_TEXTLIB_CUH
+__host__ __device__ constexpr cl_uint pgs_is_text_key(const pg_varlena_t *) { return 1; }
+#endif
+#define PGS_X_KEY_ISTEXT(keyidx,colidx,NAME)    ntk += pgs_is_text_key((const pg_##NAME##_t *)0);
 
 extern "C" __global__ void
 gpupreagg_describe(pgs_kern_desc *desc)
 {
-    cl_uint rb = 0;
+    cl_uint rb = 0, ntk = 0;
 
     GPUPREAGG_INCOL_LIST(PGS_X_INCOL_ROWBYTES)
+    GPUPREAGG_KEY_LIST(PGS_X_KEY_ISTEXT)
     desc->num_incols = GPUPREAGG_NUM_INCOLS;
     desc->num_keys = GPUPREAGG_NUM_KEYS;
     desc->num_aggs = GPUPREAGG_NUM_AGGS;
@@ -4964,6 +4971,7 @@ gpupreagg_describe(pgs_kern_desc *desc)
     desc->max_tile_rows = (GPUPREAGG_GATHER_PAYLOAD ? 8192 : 4096);
     desc->has_qual = GPUPREAGG_HAS_QUAL;
     desc->partagg_head_bytes = PGS_PARTAGG_HEAD_BYTES;
+    desc->num_text_keys = ntk;
 }
 
 #endif  /* KERN_GPUPREAGG_CUH */

@@ -74,6 +74,19 @@ typedef struct
     cl_uint     max_tile_rows;      /* upper bound of the tile size (multiple of 1024) */
     cl_uint     has_qual;           /* the scan evaluates a WHERE clause */
     cl_uint     partagg_head_bytes; /* shared memory of gpupreagg_partagg in front of the image */
+    cl_uint     num_text_keys;      /* text / bpchar grouping keys: the session gets a key heap */
 } pgs_kern_desc;
+
+/* key heap of a session whose program groups by text / bpchar columns
+ * (kern_textlib.cuh): the control block is the module global `pgs_keyheap` */
+typedef struct
+{
+    cl_ulong   *slots;          /* [nslots][2]: hash (0 = free), ref */
+    unsigned char *heap;
+    cl_ulong   *heap_used;      /* allocation cursor, bytes */
+    cl_ulong    heap_bytes;
+    cl_uint     nslots;         /* power of 2; 0 = no key heap */
+    cl_uint     max_probe;
+} pgs_keyheap_ctl;
 
 #endif  /* KERN_SHARED_H */

@@ -20,6 +20,7 @@
  */
 #ifndef KERN_TEXTLIB_CUH
 #define KERN_TEXTLIB_CUH
+#include "kern_shared.h"
 
 typedef struct {
     const unsigned char *value;     /* varlena header */
@@ -227,10 +228,165 @@ pgfn_text_cmp(cl_int *errcode, pg_text_t arg1, pg_text_t arg2)
  * (datastore.cpp), the counterpart of the reference's varlena fix-up of
  * grouping keys (opencl_gpupreagg.h:326-366, pg_fixup_tupslot_varlena).
  * bpchar compares without its trailing blanks, so those are not part of the
- * word; the host pads the value back to the column's typmod.  A longer key
- * (or a compressed / external datum) is a row for the host: CpuReCheck.
+ * word; the host pads the value back to the column's typmod.
+ *
+ * A longer key goes to the session's KEY HEAP (below): the string is stored
+ * once, its key word is the heap offset under the top byte 0x80 - again
+ * equal words <=> equal strings, within one session.  The reference keeps a
+ * varlena key as a pointer into the chunk's toast area and compares the
+ * strings in its generated keycomp (opencl_gpupreagg.h:326-366,
+ * gpupreagg.c:1234-1243); here the comparison happens once per row, when
+ * the string is looked up, and everything behind it works on 8-byte words.
+ * A compressed / external datum, a full heap or a session without a heap is
+ * a row for the host: CpuReCheck.
  * ------------------------------------------------------------------ */
 #define PGS_KERNEL_TEXT_MAXLEN  7
+#define PGS_KEYHEAP_TAG         0x80ULL     /* top byte of a key-heap word */
+
+/*
+ * The key heap of a session: an open-addressing table of (hash, ref) pairs
+ * over an append-only string heap, both in HBM.  `ref` is 1 + the byte
+ * offset of the entry [cl_ulong length | bytes, zero-padded to 8]; 0 =
+ * claimed but not yet published; PGS_KEYHEAP_NOROOM = the claimer found the
+ * heap full.  The control block is a module global that the CUDA layer fills
+ * in when it opens the session (a session loads its own instance of the
+ * program); a program that is never given a heap (nslots = 0) re-checks long
+ * keys.
+ */
+/* (pgs_keyheap_ctl: kern_shared.h) */
+
+#define PGS_KEYHEAP_NOROOM      0xFFFFFFFFFFFFFFFFULL
+#define PGS_KEYHEAP_MAX_SPINS   20000
+
+#ifdef __CUDACC__
+extern "C" { __device__ pgs_keyheap_ctl pgs_keyheap; }
+#define PGS_KEYHEAP_FENCE()         __threadfence()
+/* slots and entries are written by other SMs while this one reads their
+ * neighbours: every look goes to L2 */
+#define PGS_KEYHEAP_LOAD64(p)       __ldcg((const unsigned long long *)(p))
+#define PGS_KEYHEAP_PAUSE()         __nanosleep(100)
+#else
+static pgs_keyheap_ctl pgs_keyheap;     /* CPU build of the tests */
+#ifdef PGS_KEYHEAP_HOST_ATOMICS         /* ... with real threads */
+#define PGS_KEYHEAP_FENCE()         __atomic_thread_fence(__ATOMIC_SEQ_CST)
+#define PGS_KEYHEAP_LOAD64(p)       __atomic_load_n((const unsigned long long *)(p), __ATOMIC_ACQUIRE)
+#define PGS_KEYHEAP_PAUSE()         sched_yield()
+#else
+#define PGS_KEYHEAP_FENCE()         ((void)0)
+#define PGS_KEYHEAP_LOAD64(p)       (*(const volatile unsigned long long *)(p))
+#define PGS_KEYHEAP_PAUSE()         ((void)0)
+#endif
+#endif
+
+DEVFN cl_ulong
+pgs_keyheap_hash(const unsigned char *data, cl_int len)
+{
+    cl_ulong    h = 0xCBF29CE484222325ULL ^ (cl_ulong)(cl_uint)len;
+
+    for (cl_int i = 0; i < len; i++)
+        h = (h ^ data[i]) * 0x100000001B3ULL;       /* FNV-1a */
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ULL;
+    h ^= h >> 32;
+    return h ? h : 1;
+}
+
+/* bytes i .. i+7 of the string as one little-endian word, zero past its end */
+DEVFN cl_ulong
+pgs_keyheap_word(const unsigned char *data, cl_int len, cl_int i)
+{
+    cl_ulong    w = 0;
+    cl_int      n = (len - i < 8 ? len - i : 8);
+
+    for (cl_int k = 0; k < n; k++)
+        w |= (cl_ulong)data[i + k] << (8 * k);
+    return w;
+}
+
+/* -> key word of the string, or 0 with *ok = false (no heap / heap full /
+ * probe limit: the row is for the host) */
+DEVFN cl_ulong
+pgs_keyheap_intern(const unsigned char *data, cl_int len, bool *ok)
+{
+    const cl_uint   nslots = pgs_keyheap.nslots;
+    cl_ulong       *slots = pgs_keyheap.slots;
+    unsigned char  *heap = pgs_keyheap.heap;
+    cl_ulong        h;
+    cl_uint         pos, probes = 0, spins = 0;
+
+    *ok = false;
+    if (nslots == 0)
+        return 0;
+    h = pgs_keyheap_hash(data, len);
+    pos = (cl_uint)(h >> 17) & (nslots - 1);
+    /* one flat loop: a lane that finds a claimed but unpublished slot comes
+     * round again instead of spinning in a nested loop, so that the claimer
+     * - possibly a lane of the same warp - gets to publish.  The wait is
+     * bounded: a lane that has waited for ~2 ms gives its row to the host */
+    for (;;)
+    {
+        cl_ulong   *slot = slots + 2 * (size_t)pos;
+        cl_ulong    cur = PGS_KEYHEAP_LOAD64(slot);
+
+        if (cur == 0)
+        {
+            cur = atomicCAS((unsigned long long *)slot, 0ULL, (unsigned long long)h);
+            if (cur == 0)
+            {
+                /* ours: store the string, then publish it */
+                cl_ulong    need = 8 + (((cl_ulong)len + 7) & ~7ULL);
+                cl_ulong    off = atomicAdd((unsigned long long *)pgs_keyheap.heap_used,
+                                            (unsigned long long)need);
+                if (off + need > pgs_keyheap.heap_bytes)
+                {
+                    atomicExch((unsigned long long *)(slot + 1), PGS_KEYHEAP_NOROOM);
+                    return 0;
+                }
+                cl_ulong   *ent = (cl_ulong *)(heap + off);
+                ent[0] = (cl_ulong)(cl_uint)len;
+                for (cl_int i = 0; i < len; i += 8)
+                    ent[1 + (i >> 3)] = pgs_keyheap_word(data, len, i);
+                PGS_KEYHEAP_FENCE();
+                atomicExch((unsigned long long *)(slot + 1), (unsigned long long)(off + 1));
+                *ok = true;
+                return (PGS_KEYHEAP_TAG << 56) | off;
+            }
+        }
+        if (cur == h)
+        {
+            cl_ulong    ref = PGS_KEYHEAP_LOAD64(slot + 1);
+
+            if (ref == 0)
+            {
+                /* not published yet: look again */
+                if (++spins > PGS_KEYHEAP_MAX_SPINS)
+                    return 0;
+                PGS_KEYHEAP_PAUSE();
+                continue;
+            }
+            if (ref == PGS_KEYHEAP_NOROOM)
+                return 0;
+            PGS_KEYHEAP_FENCE();
+            const cl_ulong *ent = (const cl_ulong *)(heap + (ref - 1));
+            if (PGS_KEYHEAP_LOAD64(ent) == (cl_ulong)(cl_uint)len)
+            {
+                cl_int  i = 0;
+                while (i < len &&
+                       PGS_KEYHEAP_LOAD64(ent + 1 + (i >> 3)) == pgs_keyheap_word(data, len, i))
+                    i += 8;
+                if (i >= len)
+                {
+                    *ok = true;
+                    return (PGS_KEYHEAP_TAG << 56) | (ref - 1);
+                }
+            }
+            /* same hash, another string: next slot */
+        }
+        if (++probes > pgs_keyheap.max_probe)
+            return 0;
+        pos = (pos + 1) & (nslots - 1);
+    }
+}
 
 DEVFN cl_ulong
 pgs_text_keybits(cl_int *errcode, pg_varlena_t arg, bool ignore_trailing_blanks,
@@ -249,9 +405,16 @@ pgs_text_keybits(cl_int *errcode, pg_varlena_t arg, bool ignore_trailing_blanks,
             len--;
     if (len > PGS_KERNEL_TEXT_MAXLEN)
     {
-        *isnull = true;
-        STROM_SET_ERROR(errcode, StromError_CpuReCheck);
-        return 0;
+        bool    ok;
+
+        word = pgs_keyheap_intern(data, len, &ok);
+        if (!ok)
+        {
+            *isnull = true;
+            STROM_SET_ERROR(errcode, StromError_CpuReCheck);
+            return 0;
+        }
+        return word;
     }
     for (cl_int i = 0; i < len; i++)
         word |= (cl_ulong)data[i] << (8 * i);

@@ -51,6 +51,8 @@ make_guc_table()
          "Enables the use of GPU accelerated full-scan"},
         {"enable_gpuhashjoin", "bool", "on", "on", NULL, NULL, "USERSET",
          "Enables the use of GPU accelerated hash-join (accepted; operator not built)"},
+        {"pg_strom.key_heap_size", "int", "64", "64", "0", "65536", "USERSET",
+         "size of the device heap of long text grouping keys in MB (0: such rows are re-checked on the host)"},
         {"pg_strom.mqueue_timeout", "int", "60000", "60000", "1", "2147483647", "POSTMASTER",
          "timeout of device completion wait in ms (was: message queue wait)"},
         {"pg_strom.devprog_enable_optimization", "bool", "on", "on", NULL, NULL, "SIGHUP",

@@ -310,15 +310,23 @@ class HeapDataStore:
             pass
 
 
-def decode_datum(datum, isnull, typ, typmod=-1):
+def decode_datum(datum, isnull, typ, typmod=-1, key_heap=(None, 0)):
     """8-byte Datum of a TUPSLOT row -> python value (by-value types; text /
-    bpchar grouping keys come back as "kernel text" -> payload bytes)."""
+    bpchar grouping keys come back as "kernel text" -> payload bytes; the
+    long ones point into `key_heap` = (address, length) of the session)."""
     if isnull:
         return None
     if typ in ("text", "bpchar"):
         lib = _capi.load()
-        buf = C.create_string_buffer(max(64, typmod + 32))
-        n = lib.pgstrom_fixup_kernel_text(datum, typmod, buf, len(buf))
+        heap, heap_len = key_heap
+        size = max(64, typmod + 32)
+        while True:
+            buf = C.create_string_buffer(size)
+            n = lib.pgstrom_fixup_kernel_text_heap(datum, typmod, heap, heap_len, buf, len(buf))
+            if n == 0 and (datum >> 56) == 0x80 and heap and size < heap_len + 4 * max(typmod, 0) + 64:
+                size = heap_len + 4 * max(typmod, 0) + 64   # a long key: any entry fits this
+                continue
+            break
         if n == 0:
             raise ValueError("bad kernel text datum %#x" % datum)
         return buf.raw[4:n]
@@ -479,10 +487,18 @@ class GpuPreAggState:
                 break
             if rc < 0:
                 raise _capi.StromError(-rc, self.lib.pgs_last_error().decode(errors="replace"))
+            heap = self.key_heap()
             rows.append(tuple(decode_datum(values[i], isnull.raw[i] != 0, self.coltypes[i],
-                                           self.typmods[i])
+                                           self.typmods[i], heap)
                               for i in range(ncols)))
         return rows
+
+    def key_heap(self):
+        """(address, length) of the strings behind long text keys of the rows
+        gpupreagg_exec returned."""
+        heap, n = C.c_void_p(), C.c_size_t()
+        check(self.lib.gpupreagg_key_heap(self.state, C.byref(heap), C.byref(n)))
+        return heap.value, n.value
 
     def recheck_rows(self):
         n = self.lib.gpupreagg_recheck_rows(self.state, None, None, 0)
@@ -634,12 +650,20 @@ class Session:
         values = (C.c_uint64 * ncols)()
         isnull = C.create_string_buffer(ncols)
         rows = []
+        heap = self.key_heap()
         for r in range(kds.nitems):
             check(lib.pgstrom_fetch_data_store(buf, r, values, isnull))
             rows.append(tuple(decode_datum(values[i], isnull.raw[i] != 0, self.coltypes[i],
-                                           self.typmods[i])
+                                           self.typmods[i], heap)
                               for i in range(ncols)))
         return rows
+
+    def key_heap(self):
+        """(address, length) of the strings behind long text keys of the rows
+        of the last finish (pgs_preagg_key_heap)."""
+        heap, n = C.c_void_p(), C.c_size_t()
+        check(self.lib.pgs_preagg_key_heap(self.handle, C.byref(heap), C.byref(n)))
+        return heap.value, n.value
 
     def perfmon(self):
         return json.loads(self.lib.pgs_preagg_perfmon_json(self.handle).decode())

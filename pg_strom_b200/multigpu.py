@@ -78,14 +78,20 @@ def allgather_bytes(dist, payload, nbytes, device=None):
     return [bytes(t.cpu().numpy().tobytes()) for t in outs]
 
 
-def choose_merge(needs_grouping, gh_nslots, part_nparts):
+def choose_merge(needs_grouping, gh_nslots, part_nparts, key_heap_nslots=0):
     """How the per-GPU states come together before the final Agg:
+      'none'     - the state groups by text keys of the session's key heap
+                   (long strings travel as session-local words): every rank
+                   flushes its own partial rows and PostgreSQL's final Agg
+                   merges them, as the reference does (gpupreagg.c:2169-2186)
       'peer'     - no GROUP BY (one record) or a table of at most 64K slots:
                    the ranks push their records into the root's HBM over
                    NVLink peer memory, the root merges (pgs_preagg_merge_peer)
       'exchange' - larger states: the groups are partitioned over the ranks
                    by key hash (pgs_preagg_merge_exchange), every rank
                    flushes its own share"""
+    if key_heap_nslots > 0:
+        return "none"
     if not needs_grouping:
         return "peer"
     if part_nparts == 0 and gh_nslots <= 65536:
@@ -103,7 +109,8 @@ class StateMerge:
         self.lib, self.sess, self.ctx, self.root = lib, sess, ctx, root
         pm = sess.perfmon()
         self.mode = mode or choose_merge(bool(sess.desc["needs_grouping"]),
-                                         pm["gh_nslots"], pm["part_nparts"])
+                                         pm["gh_nslots"], pm["part_nparts"],
+                                         pm.get("key_heap_nslots", 0))
         if self.mode == "peer":
             handle = C.create_string_buffer(64)
             _capi.check(lib.pgs_preagg_peer_setup(sess.handle, ctx.rank, ctx.world, root, handle))
@@ -115,6 +122,8 @@ class StateMerge:
 
     def run(self):
         from . import _capi
+        if self.mode == "none":
+            return
         if self.mode == "peer":
             _capi.check(self.lib.pgs_preagg_merge_peer(self.sess.handle))
         else:
@@ -122,6 +131,9 @@ class StateMerge:
                                                            self.ctx.rank, self.ctx.world))
 
     def describe(self):
+        if self.mode == "none":
+            return ("no merge: text keys of the key heap are session-local, every rank returns "
+                    "its own partial rows to the final Agg")
         if self.mode == "peer":
             return ("NVLink peer memory: ranks push their state records into the root's HBM "
                     "(gpupreagg_peer_push), the root merges (gpupreagg_peer_pull); no collective")

@@ -46,6 +46,10 @@ typedef struct { cl_long value; bool isnull; } pg_timestamp_t;
         result.isnull = arg.isnull;                                     \
         return result;                                                  \
     }
+/* single-threaded stand-ins of the atomics of the key heap */
+template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T> static inline T atomicCAS(T *p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+template <typename T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
 #include "kern_numeric.cuh"
 #include "kern_timelib.cuh"
 #include "kern_textlib.cuh"
@@ -166,6 +170,20 @@ int shim_text_keybits(const unsigned char *a, int bpchar, uint64_t *out, int *is
     *out = pgs_text_keybits(&e, x, bpchar != 0, &n);
     *isnull = n;
     return e;
+}
+
+/* the key heap of the "session": nslots (power of 2, 0 = none) lookup slots
+ * and heap_bytes of strings in caller memory (slots: 16 bytes each, zeroed
+ * by the caller; used: the allocation cursor) */
+void shim_keyheap_set(void *slots, unsigned int nslots, void *heap, uint64_t heap_bytes,
+                      uint64_t *used, unsigned int max_probe)
+{
+    pgs_keyheap.slots = (cl_ulong *)slots;
+    pgs_keyheap.nslots = nslots;
+    pgs_keyheap.heap = (unsigned char *)heap;
+    pgs_keyheap.heap_bytes = heap_bytes;
+    pgs_keyheap.heap_used = (cl_ulong *)used;
+    pgs_keyheap.max_probe = max_probe;
 }
 
 /* float8 (is_f4 = 0) or float4 value -> packed device numeric */

@@ -43,6 +43,9 @@ def shim(lib):
                                       C.POINTER(C.c_int)]
     so.shim_text_keybits.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint64),
                                      C.POINTER(C.c_int)]
+    so.shim_keyheap_set.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint64,
+                                    C.c_void_p, C.c_uint]
+    so.shim_keyheap_set.restype = None
     return so
 
 
@@ -463,9 +466,133 @@ def test_kernel_text_fixup(lib, shim):
     for s in cases + [b"abcdefg", b"abcdef", b"b", b"ab"]:
         shim.shim_text_keybits(T.varlena(s), 0, C.byref(out), C.byref(isnull))
         assert words.setdefault(out.value, s) == s
-    # longer than 7 bytes: a row for the host
+    # longer than 7 bytes and no key heap: a row for the host
+    shim.shim_keyheap_set(None, 0, None, 0, None, 0)
     err = shim.shim_text_keybits(T.varlena(b"abcdefgh"), 0, C.byref(out), C.byref(isnull))
     assert err == CPU_RECHECK and isnull.value
     err = shim.shim_text_keybits(T.varlena(b"abcdefg   "), 1, C.byref(out), C.byref(isnull))
     assert err == 0 and not isnull.value
     assert lib.pgstrom_fixup_kernel_text(out.value, -1, buf, 8) == 0     # buffer too small
+
+
+class _KeyHeap:
+    """Host memory laid out like the key heap of a session (cuda_layer.cpp:
+    session_alloc_keyheap) for the CPU build of pgs_keyheap_intern."""
+
+    def __init__(self, shim, nslots, heap_bytes, max_probe=512):
+        self.slots = (C.c_uint64 * (2 * nslots))()
+        self.heap = C.create_string_buffer(max(heap_bytes, 8))
+        self.used = C.c_uint64(0)
+        self.heap_bytes = heap_bytes
+        shim.shim_keyheap_set(self.slots, nslots, self.heap, heap_bytes, C.byref(self.used),
+                              max_probe)
+
+
+def test_key_heap_interns_long_keys(lib, shim):
+    """text / bpchar keys of more than 7 bytes: the device stores the string
+    once in the session's key heap and groups by the 8-byte word (top byte
+    0x80 + heap offset); equal strings <=> equal words, the host gets the
+    varlena back from the heap copy (pgstrom_fixup_kernel_text_heap) - the
+    counterpart of the reference's varlena key move + pointer fix-up
+    (opencl_gpupreagg.h:326-366)."""
+    rng = random.Random(5)
+    kh = _KeyHeap(shim, 1 << 12, 1 << 20)
+    out, isnull = C.c_uint64(), C.c_int()
+    pool = [b"abcdefgh", b"abcdefgi", b"category-with-a-long-name", b"x" * 300, b"y" * 3000,
+            b"caf\xc3\xa9 au lait", b"12345678", b"\x00" * 9, b"trailing blank  "]
+    pool += [bytes(rng.randrange(256) for _ in range(rng.randrange(8, 60))) for _ in range(1500)]
+    pool = list(dict.fromkeys(pool))
+    words = {}
+    for rnd in range(3):
+        order = pool[:]
+        rng.shuffle(order)
+        for sval in order:
+            img = T.varlena(sval, short=(None if rnd else False))
+            err = shim.shim_text_keybits(img, 0, C.byref(out), C.byref(isnull))
+            assert err == 0 and not isnull.value, sval
+            assert out.value >> 56 == 0x80
+            assert words.setdefault(sval, out.value) == out.value       # same string, same word
+    assert len(set(words.values())) == len(pool)                        # other string, other word
+    # every string was stored exactly once
+    assert kh.used.value == sum(8 + (len(s) + 7) // 8 * 8 for s in pool)
+    # host side: the word + the heap copy -> the varlena PostgreSQL expects
+    heap = C.string_at(kh.heap, kh.used.value)
+    buf = C.create_string_buffer(4096)
+    for sval, w in words.items():
+        n = lib.pgstrom_fixup_kernel_text_heap(w, -1, heap, len(heap), buf, len(buf))
+        assert buf.raw[:n] == T.varlena(sval, short=False), sval
+    # without the heap, with a truncated heap, with a word that points nowhere: refused
+    w = words[b"y" * 3000]
+    assert lib.pgstrom_fixup_kernel_text_heap(w, -1, None, 0, buf, len(buf)) == 0
+    assert lib.pgstrom_fixup_kernel_text(w, -1, buf, len(buf)) == 0
+    off = w & ((1 << 56) - 1)
+    assert lib.pgstrom_fixup_kernel_text_heap(w, -1, heap, off + 100, buf, len(buf)) == 0
+    assert lib.pgstrom_fixup_kernel_text_heap(w | 4, -1, heap, len(heap), buf, len(buf)) == 0
+    assert lib.pgstrom_fixup_kernel_text_heap(w, -1, heap, len(heap), buf, 3000) == 0    # buf too small
+    # bpchar: trailing blanks are not part of the key, the typmod pads them back
+    err = shim.shim_text_keybits(T.varlena(b"abcdefgh   "), 1, C.byref(out), C.byref(isnull))
+    assert err == 0 and out.value == words[b"abcdefgh"]
+    n = lib.pgstrom_fixup_kernel_text_heap(out.value, 4 + 12, heap, len(heap), buf, len(buf))
+    assert buf.raw[4:n] == b"abcdefgh    "
+    # short keys never touch the heap
+    before = kh.used.value
+    err = shim.shim_text_keybits(T.varlena(b"abcdefg"), 0, C.byref(out), C.byref(isnull))
+    assert err == 0 and out.value >> 56 == 7 and kh.used.value == before
+    shim.shim_keyheap_set(None, 0, None, 0, None, 0)
+
+
+def test_key_heap_full_means_recheck(lib, shim):
+    """A heap without room (or a lookup table whose probe limit is hit) turns
+    rows with an unseen long key into rows for the host; keys stored before
+    keep working, and so does a later, shorter string only if it fits."""
+    out, isnull = C.c_uint64(), C.c_int()
+    kh = _KeyHeap(shim, 64, 80)                     # room for 24 + 24 + 24 bytes
+    a, b, c, d = b"first-key", b"second-long-key", b"third-long-keyyy", b"fourth-key"
+    for sval in (a, b, c):
+        assert shim.shim_text_keybits(T.varlena(sval), 0, C.byref(out), C.byref(isnull)) == 0
+    wa = C.c_uint64()
+    assert shim.shim_text_keybits(T.varlena(a), 0, C.byref(wa), C.byref(isnull)) == 0
+    assert kh.used.value == 72
+    err = shim.shim_text_keybits(T.varlena(d), 0, C.byref(out), C.byref(isnull))
+    assert err == CPU_RECHECK and isnull.value
+    # again: the slot says "no room", still a re-check; the others are still found
+    err = shim.shim_text_keybits(T.varlena(d), 0, C.byref(out), C.byref(isnull))
+    assert err == CPU_RECHECK and isnull.value
+    w2 = C.c_uint64()
+    assert shim.shim_text_keybits(T.varlena(a), 0, C.byref(w2), C.byref(isnull)) == 0
+    assert w2.value == wa.value
+    # probe limit: 8 slots, all taken by other strings
+    kh = _KeyHeap(shim, 8, 4096, max_probe=8)
+    got = 0
+    for i in range(40):
+        err = shim.shim_text_keybits(T.varlena(b"key-number-%04d" % i), 0, C.byref(out),
+                                     C.byref(isnull))
+        assert err in (0, CPU_RECHECK)
+        got += (err == 0)
+    assert got == 8
+    shim.shim_keyheap_set(None, 0, None, 0, None, 0)
+
+
+def test_key_heap_under_concurrency():
+    """The claim / publish / wait protocol of pgs_keyheap_intern with real
+    threads (tests/native/keyheap_stress.cpp: the device atomics mapped to
+    __atomic builtins): every thread gets the same word for the same string,
+    different strings get different words, every string is stored once; with
+    a heap that is too small the strings that found no room are refused for
+    every thread alike and nothing else changes."""
+    import json
+    exe = os.path.join(HERE, "native", "_keyheap_stress")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"),
+                    "-I", os.path.join(ROOT, "pg_strom_b200", "csrc"), "-o", exe,
+                    os.path.join(HERE, "native", "keyheap_stress.cpp")], check=True)
+    for args in (["8", "4000", "4", "16384", str(8 << 20)], ["32", "1500", "12", "4096", str(1 << 20)]):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=120)
+        d = json.loads(r.stdout)
+        assert r.returncode == 0, d
+        assert d["failed_lookups"] == 0 and d["mismatch"] == 0 and d["duplicate_words"] == 0
+        assert d["heap_used"] == d["expect_used"]
+    r = subprocess.run([exe, "8", "4000", "3", "16384", "40000"], capture_output=True, text=True,
+                       timeout=120)
+    d = json.loads(r.stdout)
+    assert d["failed_lookups"] > 0 and d["missing"] > 0
+    assert d["mismatch"] == 0 and d["duplicate_words"] == 0

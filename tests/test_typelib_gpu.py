@@ -245,11 +245,16 @@ def make_cats(n, seed):
 
 @pytest.mark.parametrize("fmt", ["column", "row"])
 @pytest.mark.parametrize("with_qual", [False, True])
-def test_text_and_bpchar_group_keys(cuda, fmt, with_qual):
+@pytest.mark.parametrize("key_heap_mb", [64, 0])
+def test_text_and_bpchar_group_keys(cuda, fmt, with_qual, key_heap_mb):
     """GROUP BY a text and a character(5) column: keys of at most 7 bytes are
-    grouped on the device ("kernel text"), rows with a longer key come back
-    for the host (CpuReCheck) and PostgreSQL's final Agg - here the checker -
-    merges both."""
+    their own 8-byte key word ("kernel text"), longer ones are stored once in
+    the session's key heap and grouped by their heap word - the device
+    returns every group, the host turns the words back into varlenas
+    (pgstrom_fixup_kernel_text_heap; the reference's varlena key move and
+    pointer fix-up, opencl_gpupreagg.h:326-366).  With pg_strom.key_heap_size
+    = 0 rows with a long key come back for the host instead (CpuReCheck) and
+    PostgreSQL's final Agg - here the checker - merges both."""
     t = CATS
     rows = make_cats(8000, seed=31)
     tree = P.make_agg_plan(
@@ -257,7 +262,7 @@ def test_text_and_bpchar_group_keys(cuda, fmt, with_qual):
             (P.Agg("sum", [t.col("f")]), "sum"), (P.Agg("min", [t.col("v")]), "min")],
         group_by=["cat", "code"], num_groups=200,
         where=[P.Op("<", t.col("f"), P.Const("int4", 50))] if with_qual else [])
-    plan = gp.Plan(tree, gucs=GUCS)
+    plan = gp.Plan(tree, gucs=dict(GUCS, **{"pg_strom.key_heap_size": key_heap_mb}))
     try:
         assert plan.num_gpupreagg == 1, plan.reject_reason
         desc = plan.describe()
@@ -286,9 +291,11 @@ def test_text_and_bpchar_group_keys(cuda, fmt, with_qual):
             ds.free()
     finally:
         plan.free()
+        gp._capi.load().pgstrom_guc_set(b"pg_strom.key_heap_size", b"64")
     long_rows = [i for i, r in enumerate(rows)
                  if r[0] is not None and len(r[0]) > 7 and (not with_qual or r[2] < 50)]
-    assert len(long_rows) > 50 and recheck == long_rows
+    assert len(long_rows) > 50
+    assert recheck == ([] if key_heap_mb else long_rows)
     # what gpupreagg_next_tuple_fallback produces for the flagged rows
     host, _ = partial.partial_rows(node, [rows[i] for i in recheck], len(t.columns))
     exp, _ = partial.partial_rows(node, rows, len(t.columns))
@@ -296,7 +303,11 @@ def test_text_and_bpchar_group_keys(cuda, fmt, with_qual):
     assert len(exp) > 100 and set(got) == set(exp)
     for key, erow in exp.items():
         assert list(got[key]) == list(erow), (key, got[key], erow)
-    # the device's own rows carry only short keys, padded back to character(5)
+    # character(5) keys come back padded; long keys only ever from the key heap
+    longest = max((len(r[0]) for r in device_rows if r[0] is not None), default=0)
+    assert longest == (300 if key_heap_mb else 7)
     for r in device_rows:
-        assert r[0] is None or len(r[0]) <= 7
         assert r[1] is None or len(r[1].decode("utf-8")) == 5
+    if key_heap_mb:
+        # one partial row per group: no group was split between device and host
+        assert len(device_rows) == len(exp)

@@ -86,6 +86,30 @@ def workload_sources():
     return out
 
 
+def textkey_sources():
+    """GROUP BY (text, character(5)): tests/test_typelib_gpu.py and
+    tools/gpu_keyheap_check.py (long keys go through the key heap)."""
+    from pg_strom_b200 import gpupreagg as gp
+    from pg_strom_b200 import pgplan as P
+    t = P.Table("cats", [("cat", "text"), ("code", "bpchar"), ("f", "int4"), ("v", "int8")],
+                typmods={"code": 4 + 5})
+    out = []
+    for num_groups in (200, 3000):
+        for with_qual in (False, True):
+            tree = P.make_agg_plan(
+                t, [(t.col("cat"), "cat"), (t.col("code"), "code"),
+                    (P.Agg("count", star=True), "count"), (P.Agg("sum", [t.col("f")]), "sum"),
+                    (P.Agg("min", [t.col("v")]), "min")],
+                group_by=["cat", "code"], num_groups=num_groups,
+                where=[P.Op("<", t.col("f"), P.Const("int4", 50))] if with_qual else [])
+            plan = gp.Plan(tree, gucs=GUCS)
+            try:
+                out.append((plan.kernel_source(), plan.extra_flags()))
+            finally:
+                plan.free()
+    return out
+
+
 def extra_sources():
     out = []
     if os.path.exists(EXTRA):
@@ -140,7 +164,7 @@ def main(jobs=None, force=False, quiet=False):
                 os.unlink(os.path.join(cache, fn))
             except OSError:
                 pass
-    items = regression_sources() + workload_sources() + extra_sources()
+    items = regression_sources() + workload_sources() + textkey_sources() + extra_sources()
     uniq = list({hashlib.sha1((s + "|%d" % f).encode()).hexdigest(): (s, f)
                  for s, f in items}.values())
     jobs = jobs or max(1, (os.cpu_count() or 2))
