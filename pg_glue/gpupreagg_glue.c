@@ -61,6 +61,7 @@ static bool     guc_debug_force_gpupreagg;
 static bool     guc_devprog_optimization;
 static int      guc_chunk_size;
 static int      guc_max_async_chunks;
+static int      guc_key_heap_size;
 static double   guc_gpu_setup_cost;
 static double   guc_gpu_operator_cost;
 static double   guc_gpu_tuple_cost;
@@ -81,6 +82,7 @@ GLUE_ASSIGN_BOOL(assign_debug_force_gpupreagg, "pg_strom.debug_force_gpupreagg")
 GLUE_ASSIGN_BOOL(assign_devprog_optimization, "pg_strom.devprog_enable_optimization")
 GLUE_ASSIGN_INT(assign_chunk_size, "pg_strom.chunk_size")
 GLUE_ASSIGN_INT(assign_max_async_chunks, "pg_strom.max_async_chunks")
+GLUE_ASSIGN_INT(assign_key_heap_size, "pg_strom.key_heap_size")
 GLUE_ASSIGN_REAL(assign_gpu_setup_cost, "gpu_setup_cost")
 GLUE_ASSIGN_REAL(assign_gpu_operator_cost, "gpu_operator_cost")
 GLUE_ASSIGN_REAL(assign_gpu_tuple_cost, "gpu_tuple_cost")
@@ -125,6 +127,11 @@ pgstrom_init_gucs(void)
     DefineCustomIntVariable("pg_strom.max_async_chunks", "max number of chunks in flight", NULL,
                             &guc_max_async_chunks, (int) boot_num("pg_strom.max_async_chunks", 3), 1, 1024,
                             PGC_USERSET, GUC_NOT_IN_SAMPLE, NULL, assign_max_async_chunks, NULL);
+    /* (not in the reference: its varlena grouping keys stay in the chunk's toast area) */
+    DefineCustomIntVariable("pg_strom.key_heap_size",
+                            "size of the device heap of long text grouping keys in MB", NULL,
+                            &guc_key_heap_size, (int) boot_num("pg_strom.key_heap_size", 64), 0, 65536,
+                            PGC_USERSET, GUC_NOT_IN_SAMPLE, NULL, assign_key_heap_size, NULL);
     /* main.c:158-186 */
     DefineCustomRealVariable("gpu_setup_cost", "Cost to setup GPU device to run", NULL,
                              &guc_gpu_setup_cost, boot_num("gpu_setup_cost", 500.0), 0, 1e30,
