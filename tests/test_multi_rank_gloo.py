@@ -118,6 +118,10 @@ def test_choose_merge():
     assert multigpu.choose_merge(True, 65536, 0) == "peer"
     assert multigpu.choose_merge(True, 131072, 0) == "exchange"
     assert multigpu.choose_merge(True, 2048, 19532) == "exchange"
+    # text keys of a session's key heap are session-local words: no merge, every
+    # rank returns its own partial rows to the final Agg (gpupreagg.c:2169-2186)
+    assert multigpu.choose_merge(True, 4096, 0, key_heap_nslots=65536) == "none"
+    assert multigpu.choose_merge(True, 2048, 19532, key_heap_nslots=65536) == "none"
 
 
 def test_deal_chunks():
