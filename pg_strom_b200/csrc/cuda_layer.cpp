@@ -1220,7 +1220,13 @@ session_alloc_keyheap(pgs_session *s)
         nslots <<= 1;
     char *base = NULL;
     size_t heap_bytes = (size_t)mb << 20;
-    CUDA_CHECK(cudaMalloc((void **)&base, 16 * nslots + 128 + heap_bytes));
+    if (cudaMalloc((void **)&base, 16 * nslots + 128 + heap_bytes) != cudaSuccess)
+    {
+        /* no room for the heap on this device: the query still runs, rows
+         * with a long key go to the host */
+        cudaGetLastError();
+        return StromError_Success;
+    }
     s->kh.slots = (cl_ulong *)base;
     s->kh.heap_used = (cl_ulong *)(base + 16 * nslots);
     s->kh.heap = (unsigned char *)(base + 16 * nslots + 128);
