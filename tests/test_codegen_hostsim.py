@@ -123,6 +123,20 @@ extern "C" int sim_row(const unsigned long long *vals, unsigned int valid,
     return e1 | (e2 << 8);
 }
 
+#ifdef KERN_TEXTLIB_CUH
+/* the session's key heap (kern_textlib.cuh) in caller memory; nslots = 0: none */
+extern "C" void sim_keyheap_set(void *slots, unsigned int nslots, void *heap,
+                                unsigned long long heap_bytes, void *used)
+{
+    pgs_keyheap.slots = (cl_ulong *)slots;
+    pgs_keyheap.nslots = nslots;
+    pgs_keyheap.heap = (unsigned char *)heap;
+    pgs_keyheap.heap_bytes = heap_bytes;
+    pgs_keyheap.heap_used = (cl_ulong *)used;
+    pgs_keyheap.max_probe = 512;
+}
+#endif
+
 /* ---- aggregation: the same rows through every flavour of the merge rules ----
  * The cell formats of the register flavours (PLAIN / THREAD, no GROUP BY) and
  * of the table flavours (ATOMIC / SHARED, GROUP BY) differ (e.g. int4 min /
@@ -411,9 +425,11 @@ def find_node(tree):
     raise AssertionError("no GpuPreAgg node")
 
 
-def check_query(table, tree, rows, simdir):
+def check_query(table, tree, rows, simdir, key_heap_bytes=0):
     """Runs every row through the compiled generated code and through the
-    oracle; returns (#passed, #errors) for the caller's sanity checks."""
+    oracle; returns (#passed, #errors) for the caller's sanity checks.
+    key_heap_bytes > 0: the program gets a key heap like a session's (text
+    keys of more than 7 bytes are grouped on the device)."""
     plan = gp.Plan(tree, gucs=GUCS)
     try:
         assert plan.num_gpupreagg == 1, plan.reject_reason
@@ -435,6 +451,14 @@ def check_query(table, tree, rows, simdir):
         key_null = C.create_string_buffer(16)
         agg_null = C.create_string_buffer(32)
         passed = C.c_int()
+        kh_heap = kh_used = None
+        if key_heap_bytes:
+            kh_slots = (C.c_uint64 * (2 * 1024))()
+            kh_heap = C.create_string_buffer(key_heap_bytes)
+            kh_used = C.c_uint64(0)
+            so.sim_keyheap_set.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint64, C.c_void_p]
+            so.sim_keyheap_set(kh_slots, 1024, kh_heap, key_heap_bytes, C.byref(kh_used))
+        words = {}
         for row in rows:
           try:
             valid, toast = fill_vals(row, incols, coltypes, vals)
@@ -472,7 +496,8 @@ def check_query(table, tree, rows, simdir):
             for c in keycols:
                 v = exp.get(c["resno"])
                 if c["type"] in ("text", "bpchar") and v is not None and \
-                        len(v.rstrip(b" ") if c["type"] == "bpchar" else v) > 7:
+                        len(v.rstrip(b" ") if c["type"] == "bpchar" else v) > 7 and \
+                        not key_heap_bytes:
                     perr = True
             if perr:
                 assert e2 == CPU_RECHECK, (row, rc)
@@ -480,8 +505,12 @@ def check_query(table, tree, rows, simdir):
                 continue
             assert e2 == 0, (row, rc)
             for i, c in enumerate(keycols):
+                heap = (C.addressof(kh_heap), kh_used.value) if key_heap_bytes else (None, 0)
                 got = None if key_null.raw[i] != b"\0"[0] else \
-                    gp.decode_datum(key_out[i], False, c["type"], c.get("typmod", -1))
+                    gp.decode_datum(key_out[i], False, c["type"], c.get("typmod", -1), heap)
+                if got is not None and c["type"] in ("text", "bpchar"):
+                    # equal strings <=> equal key words
+                    assert words.setdefault((i, got), key_out[i]) == key_out[i]
                 e = exp[c["resno"]]
                 if c["type"] in ("float4", "float8") and e is not None and e == 0:
                     e = 0.0                                     # -0 groups with +0
@@ -692,6 +721,33 @@ def test_hand_written_queries(simdir):
         where=[P.Not(P.And(t.col("b"), P.Op(">", t.col("d"), P.Const("date", 0))))])
     npass, nerr = check_query(t, q2, rows, simdir)
     assert npass > 50 and nerr > 5          # int4 * int2 overflow, division by zero
+
+
+def test_long_text_keys_go_through_the_key_heap(simdir):
+    """GROUP BY a text column (and a text CASE expression's input) whose
+    values are longer than the 7 bytes a key word holds: with a key heap the
+    generated projection interns the string (pgs_text_keybits ->
+    pgs_keyheap_intern) and the host gets it back from the heap copy; no row
+    is left to the host.  Without one the same rows are re-checked (the
+    default of every other test in this file)."""
+    rng = random.Random(77)
+    pool = [b"", b"abc", b"abcdefg", b"abcdefgh", b"abcdefgh ", b"category-with-a-long-name",
+            b"x" * 300, b"caf\xc3\xa9 au lait", b"zzzzzzzzzzzz"]
+    types = [t for _, t in TBL.columns]
+    rows = []
+    for _ in range(400):
+        r = list(rand_rows(1, rng)[0])
+        r[8] = None if rng.random() < 0.1 else rng.choice(pool)
+        rows.append(tuple(r))
+    assert types[8] == "text"
+    tree = P.make_agg_plan(TBL, [(TBL.col("tx"), "tx"), (P.Agg("count", star=True), "n"),
+                                 (P.Agg("max", [TBL.col("i4")]), "m")],
+                           group_by=["tx"], num_groups=16,
+                           where=[P.Op(">", TBL.col("k"), P.Const("int4", 0))])
+    npass, nerr = check_query(TBL, tree, rows, simdir, key_heap_bytes=1 << 16)
+    assert npass > 200 and nerr == 0
+    npass0, nerr0 = check_query(TBL, tree, rows, simdir)
+    assert npass0 == npass and nerr0 > 100         # long keys: rows for the host
 
 
 def test_fuzz_generated_code(simdir):
