@@ -257,6 +257,9 @@ pgfn_text_cmp(cl_int *errcode, pg_text_t arg1, pg_text_t arg2)
 
 #define PGS_KEYHEAP_NOROOM      0xFFFFFFFFFFFFFFFFULL
 #define PGS_KEYHEAP_MAX_SPINS   20000
+/* longer keys are left to the host: one thread hashes and compares the whole
+ * string (and a corrupt varlena header must not send it through gigabytes) */
+#define PGS_KEYHEAP_MAXLEN      65535
 
 #ifdef __CUDACC__
 extern "C" { __device__ pgs_keyheap_ctl pgs_keyheap; }
@@ -315,7 +318,7 @@ pgs_keyheap_intern(const unsigned char *data, cl_int len, bool *ok)
     cl_uint         pos, probes = 0, spins = 0;
 
     *ok = false;
-    if (nslots == 0)
+    if (nslots == 0 || len > PGS_KEYHEAP_MAXLEN)
         return 0;
     h = pgs_keyheap_hash(data, len);
     pos = (cl_uint)(h >> 17) & (nslots - 1);

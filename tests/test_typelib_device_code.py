@@ -534,6 +534,13 @@ def test_key_heap_interns_long_keys(lib, shim):
     assert err == 0 and out.value == words[b"abcdefgh"]
     n = lib.pgstrom_fixup_kernel_text_heap(out.value, 4 + 12, heap, len(heap), buf, len(buf))
     assert buf.raw[4:n] == b"abcdefgh    "
+    # a key of more than 64 KB is not worth a thread's time: a row for the host
+    err = shim.shim_text_keybits(T.varlena(b"z" * 65535, short=False), 0, C.byref(out),
+                                 C.byref(isnull))
+    assert err == 0 and out.value >> 56 == 0x80
+    err = shim.shim_text_keybits(T.varlena(b"z" * 65536, short=False), 0, C.byref(out),
+                                 C.byref(isnull))
+    assert err == CPU_RECHECK and isnull.value
     # short keys never touch the heap
     before = kh.used.value
     err = shim.shim_text_keybits(T.varlena(b"abcdefg"), 0, C.byref(out), C.byref(isnull))
