@@ -2718,8 +2718,12 @@ pgs_preagg_merge_exchange(pgs_session *s, void *nccl_comm, int rank, int nranks)
     CUDA_CHECK(cudaStreamSynchronize(s->s_exec));
     session_bury(s);
 
-    /* from here on the sends and receives must be issued: local failures
-     * (allocation) are remembered and reported after the exchange */
+    /* Every rank issues every send and receive with the counts agreed on
+     * above.  KNOWN GAP: a rank whose local work below fails (device memory
+     * for the buffers or the larger table) returns before the exchange and
+     * its peers then wait in ncclRecv until the caller aborts the
+     * communicator; a second all-gather of the local status in front of the
+     * group would close it. */
     std::vector<cl_uint> soff(R + 1, 0), roff(R + 1, 0);
     size_t total_send = 0, total_recv = 0;
     for (cl_uint d = 0; d < R; d++)
