@@ -603,3 +603,14 @@ def test_key_heap_under_concurrency():
     d = json.loads(r.stdout)
     assert d["failed_lookups"] > 0 and d["missing"] > 0
     assert d["mismatch"] == 0 and d["duplicate_words"] == 0
+    # the same under ThreadSanitizer (acquire / release as mapped above): no data race
+    tsan = os.path.join(HERE, "native", "_keyheap_stress_tsan")
+    c = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-w",
+                        "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "pg_strom_b200", "csrc"), "-o", tsan,
+                        os.path.join(HERE, "native", "keyheap_stress.cpp")], capture_output=True)
+    if c.returncode == 0:
+        r = subprocess.run([tsan, "8", "2000", "3", "8192", str(4 << 20)], capture_output=True,
+                           text=True, timeout=300)
+        assert "ThreadSanitizer" not in r.stderr, r.stderr[:2000]
+        assert r.returncode == 0, r.stdout
