@@ -1267,7 +1267,13 @@ gpupreagg_begin_glue(CustomPlan *node, EState *estate, int eflags)
             gpas->key_typmod[c] = KEY_NOT_TEXT;
             if (var != NULL && IsA(var, Var) &&
                 (var->vartype == TEXTOID || var->vartype == BPCHAROID))
+            {
                 gpas->key_typmod[c] = var->vartypmod;
+                /* allocated here, in the executor's per-query context;
+                 * repalloc() keeps a chunk in the context it came from */
+                gpas->key_buflen[c] = 256;
+                gpas->key_buf[c] = (char *) palloc(gpas->key_buflen[c]);
+            }
             c++;
         }
     }
@@ -1347,11 +1353,6 @@ gpupreagg_exec_glue(CustomPlanState *node)
             elog(ERROR, "PG-Strom: GpuPreAgg: %s", pgs_last_error());
         for (;;)
         {
-            if (gpas->key_buf[c] == NULL)
-            {
-                gpas->key_buflen[c] = 256;
-                gpas->key_buf[c] = (char *) palloc(gpas->key_buflen[c]);
-            }
             n = pgstrom_fixup_kernel_text_heap(slot->tts_values[c], gpas->key_typmod[c],
                                                heap, heap_len,
                                                gpas->key_buf[c], gpas->key_buflen[c]);
@@ -1360,9 +1361,8 @@ gpupreagg_exec_glue(CustomPlanState *node)
             /* the longest value a key heap of this size can hold, padded */
             if (gpas->key_buflen[c] >= heap_len + 4 * (size_t) Max(gpas->key_typmod[c], 0) + 64)
                 elog(ERROR, "PG-Strom: GpuPreAgg: corrupted text grouping key");
-            pfree(gpas->key_buf[c]);
             gpas->key_buflen[c] = heap_len + 4 * (size_t) Max(gpas->key_typmod[c], 0) + 64;
-            gpas->key_buf[c] = (char *) palloc(gpas->key_buflen[c]);
+            gpas->key_buf[c] = (char *) repalloc(gpas->key_buf[c], gpas->key_buflen[c]);
         }
         slot->tts_values[c] = PointerGetDatum(gpas->key_buf[c]);
     }

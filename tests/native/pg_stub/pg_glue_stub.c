@@ -65,6 +65,7 @@ void *palloc(Size n) { void *p = malloc(n ? n : 1); if (!p) abort(); return p; }
 void *palloc0(Size n) { void *p = calloc(1, n ? n : 1); if (!p) abort(); return p; }
 char *pstrdup(const char *s) { char *p = palloc(strlen(s) + 1); strcpy(p, s); return p; }
 void  pfree(void *p) { free(p); }
+void *repalloc(void *p, Size n) { p = realloc(p, n ? n : 1); if (!p) abort(); return p; }
 Node *pg_stub_new_node(Size size, NodeTag tag) { Node *n = palloc0(size); n->type = tag; return n; }
 
 static List *

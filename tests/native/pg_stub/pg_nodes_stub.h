@@ -38,6 +38,7 @@ extern void *palloc(Size n);
 extern void *palloc0(Size n);
 extern char *pstrdup(const char *s);
 extern void  pfree(void *p);
+extern void *repalloc(void *p, Size n);
 
 /* ---- nodes ---- */
 typedef enum NodeTag
