@@ -162,3 +162,16 @@ def test_device_calls_fail_loudly_without_gpu(lib):
     with pytest.raises(_capi.StromError):
         gp.Session(plan)
     plan.free()
+
+
+def test_key_heap_calls_check_their_arguments(lib):
+    """pgs_preagg_key_heap / gpupreagg_key_heap without a session, and the
+    host fix-up of a key-heap word without a heap: refused, nothing is read."""
+    import ctypes as C
+    heap, n = C.c_void_p(), C.c_size_t()
+    assert lib.pgs_preagg_key_heap(None, C.byref(heap), C.byref(n)) == 101  # StromError_BadRequestMessage
+    assert lib.gpupreagg_key_heap(None, C.byref(heap), C.byref(n)) == 101
+    buf = C.create_string_buffer(64)
+    word = (0x80 << 56) | 16
+    assert lib.pgstrom_fixup_kernel_text_heap(word, -1, None, 0, buf, len(buf)) == 0
+    assert lib.pgstrom_fixup_kernel_text(word, -1, buf, len(buf)) == 0
