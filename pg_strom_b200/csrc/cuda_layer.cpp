@@ -1198,8 +1198,9 @@ state_nslots(const pgs_session *s)
  * more than 7 bytes are stored once in HBM and travel as 8-byte words
  * (kern_textlib.cuh; the reference moves varlena keys as toast offsets,
  * opencl_gpupreagg.h:326-366).  pg_strom.key_heap_size (MB; 0 = no heap:
- * rows with a long key are re-checked on the host) bounds the strings, the
- * lookup table follows the planner's estimate of the number of groups. */
+ * rows with a long key are re-checked on the host) is the least room for the
+ * strings; the heap and the lookup table follow the planner's estimate of
+ * the number of groups beyond that. */
 static int
 session_alloc_keyheap(pgs_session *s)
 {
@@ -1220,6 +1221,21 @@ session_alloc_keyheap(pgs_session *s)
         nslots <<= 1;
     char *base = NULL;
     size_t heap_bytes = (size_t)mb << 20;
+    {
+        /* the GUC is the floor; a plan that expects many groups gets room for
+         * 64 bytes per expected key (8-byte length + a 56-byte string), as far
+         * as a quarter of the free device memory goes */
+        size_t free_b = 0, total_b = 0;
+        double by_estimate = 64.0 * std::max(1.0, s->config.num_groups) * s->desc.num_text_keys;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+        {
+            cudaGetLastError();
+            free_b = 0;
+        }
+        if (by_estimate > (double)heap_bytes)
+            heap_bytes = (size_t)std::min(by_estimate, (double)(free_b / 4));
+        heap_bytes = std::max(heap_bytes, (size_t)mb << 20) & ~(size_t)127;
+    }
     if (cudaMalloc((void **)&base, 16 * nslots + 128 + heap_bytes) != cudaSuccess)
     {
         /* no room for the heap on this device: the query still runs, rows
